@@ -1,0 +1,428 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the DI-engine learner hot path (``ding.rl_utils``).
+
+This module is the *checker*: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it. The product package (``di-engine_b200``) never
+does; it fails loudly when its CUDA library is missing.
+
+Every function restates one reference operator with plain fp32 torch-CPU primitives, in the reference's
+evaluation order (so that on CPU it is bit-identical to the reference, which ``tests/test_oracle_vs_reference.py``
+asserts whenever ``/root/reference`` is present, and which the committed fixtures in ``tests/golden/`` pin for
+the GPU box where the reference tree does not exist).  Parity status: **pinned** -- the reference has no golden
+vectors of its own for this path, so the pins are outputs of the reference itself, run in the
+build container by ``tests/golden/make_golden.py``.
+
+Citations are ``file:line`` relative to ``/root/reference/ding/rl_utils/``.
+Inputs are torch tensors; tensors that need gradients must have ``requires_grad`` set by the caller and the
+returned losses are differentiable through autograd (the oracle for the CUDA backward kernels).
+"""
+import math
+from typing import Optional, Sequence, Union
+
+import torch
+
+_F32_MIN = torch.finfo(torch.float32).min
+
+
+# --------------------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------------------
+def _trailing_ones(x: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """td.py:222-224 ``view_similar``: append singleton dims so ``x`` broadcasts against ``like``."""
+    return x.reshape(tuple(x.shape) + (1, ) * (like.dim() - x.dim()))
+
+
+def _log_softmax_rows(logit: torch.Tensor) -> torch.Tensor:
+    """``Categorical(logits=x).logits`` == ``x - logsumexp(x, -1, keepdim=True)`` (torch.distributions)."""
+    return logit - logit.logsumexp(dim=-1, keepdim=True)
+
+
+def _chosen(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    return table.gather(-1, idx.long().unsqueeze(-1)).squeeze(-1)
+
+
+def _row_entropy(logp: torch.Tensor) -> torch.Tensor:
+    """``Categorical.entropy``: -(clamp(logp, min=finfo.min) * softmax).sum(-1)."""
+    probs = torch.softmax(logp, dim=-1)
+    return -(logp.clamp(min=_F32_MIN) * probs).sum(-1)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# gae.py:25-70
+# --------------------------------------------------------------------------------------------------------------
+def gae(value, next_value, reward, done=None, traj_flag=None, gamma: float = 0.99, lambda_: float = 0.97):
+    """Generalised advantage estimate, reverse recurrence along dim 0.
+
+    gae.py:51-59 defaults/broadcast; :61 masks ``next_value`` IN PLACE; :62 delta; :63 trace factor; :67-69 the
+    loop ``A_t = delta_t + factor_t * A_{t+1}``.
+    """
+    if done is None:
+        done = torch.zeros_like(reward)
+    if traj_flag is None:
+        traj_flag = done
+    done = done.float()
+    traj_flag = traj_flag.float()
+    if value.dim() == reward.dim() + 1:  # (T,B,A) values with (T,B) rewards
+        reward, done, traj_flag = reward.unsqueeze(-1), done.unsqueeze(-1), traj_flag.unsqueeze(-1)
+    next_value *= (1 - done)  # caller-visible mutation, as in the reference
+    delta = reward + gamma * next_value - value
+    factor = gamma * lambda_ * (1 - traj_flag)
+    adv = torch.zeros_like(value)
+    carry = torch.zeros_like(value[0])
+    for t in range(reward.shape[0] - 1, -1, -1):
+        carry = delta[t] + factor[t] * carry
+        adv[t] = carry
+    return adv
+
+
+# --------------------------------------------------------------------------------------------------------------
+# ppo.py:77-275
+# --------------------------------------------------------------------------------------------------------------
+def ppo_error(
+        logit_new,
+        logit_old,
+        action,
+        value_new,
+        value_old,
+        adv,
+        return_,
+        weight=None,
+        logit_pretrained=None,
+        clip_ratio: float = 0.2,
+        use_value_clip: bool = True,
+        dual_clip: Optional[float] = None,
+        kl_type: str = 'k1'
+):
+    """Returns ``(policy_loss, value_loss, entropy_loss, kl_div, approx_kl, clipfrac)``.
+
+    The four losses are 0-dim tensors (differentiable), the two infos python floats (ppo.py:217-220).
+    """
+    assert dual_clip is None or dual_clip > 1.0, "dual_clip value must be greater than 1.0, but get value: {}".format(
+        dual_clip
+    )  # ppo.py:129
+    w_pol = torch.ones_like(adv) if weight is None else weight  # ppo.py:190-191
+    lp_new_all = _log_softmax_rows(logit_new)
+    lp_old_all = _log_softmax_rows(logit_old)
+    lp_new = _chosen(lp_new_all, action)  # ppo.py:194
+    lp_old = _chosen(lp_old_all, action)  # ppo.py:195
+    ent = _row_entropy(lp_new_all)  # ppo.py:198
+    if ent.shape != w_pol.shape:  # ppo.py:199-200 multi-agent: average over the agent axis
+        ent = ent.mean(dim=1)
+    entropy_loss = (ent * w_pol).mean()  # ppo.py:201
+    ratio = torch.exp(lp_new - lp_old)  # ppo.py:205
+    if ratio.shape != adv.shape:
+        ratio = ratio.mean(dim=1)  # ppo.py:206-207
+    s1 = ratio * adv
+    s2 = ratio.clamp(1 - clip_ratio, 1 + clip_ratio) * adv
+    if dual_clip is not None:  # ppo.py:210-214
+        inner = torch.min(s1, s2)
+        outer = torch.max(inner, dual_clip * adv)
+        policy_loss = -(torch.where(adv < 0, outer, inner) * w_pol).mean()
+    else:  # ppo.py:216
+        policy_loss = (-torch.min(s1, s2) * w_pol).mean()
+    with torch.no_grad():  # ppo.py:217-220
+        approx_kl = (lp_old - lp_new).mean().item()
+        clipped = ratio.gt(1 + clip_ratio) | ratio.lt(1 - clip_ratio)
+        clipfrac = clipped.float().mean().item()
+    if logit_pretrained is not None:  # ppo.py:222-226 + calculate_kl_div :30-54
+        lp_pre = _chosen(_log_softmax_rows(logit_pretrained), action)
+        log_ratio = lp_new - lp_pre
+        if kl_type == 'k1':
+            kl_div = log_ratio.mean()
+        elif kl_type == 'k2':
+            kl_div = (log_ratio ** 2 / 2).mean()
+        elif kl_type == 'k3':
+            kl_div = (torch.exp(-log_ratio) - 1 + log_ratio).mean()
+        else:
+            raise ValueError(f"Unknown kl_type: {kl_type}")
+    else:
+        kl_div = torch.tensor(0., dtype=policy_loss.dtype, device=policy_loss.device)  # ppo.py:228
+
+    w_val = torch.ones_like(value_old) if weight is None else weight  # ppo.py:264-265
+    if use_value_clip:  # ppo.py:267-272
+        v_clip = value_old + (value_new - value_old).clamp(-clip_ratio, clip_ratio)
+        e1 = (return_ - value_new).pow(2)
+        e2 = (return_ - v_clip).pow(2)
+        value_loss = 0.5 * (torch.max(e1, e2) * w_val).mean()
+    else:  # ppo.py:274
+        value_loss = 0.5 * ((return_ - value_new).pow(2) * w_val).mean()
+    return policy_loss, value_loss, entropy_loss, kl_div, approx_kl, clipfrac
+
+
+# --------------------------------------------------------------------------------------------------------------
+# td.py:230-286 nstep_return ; value_rescale.py:4-34
+# --------------------------------------------------------------------------------------------------------------
+def nstep_return(reward, next_value, done, gamma: Union[float, list], nstep: int, value_gamma=None):
+    assert reward.shape[0] == nstep  # td.py:257
+    if isinstance(gamma, float):  # td.py:260-273
+        disc = torch.ones(nstep)
+        for i in range(1, nstep):
+            disc[i] = gamma * disc[i - 1]
+        acc = reward.mul(_trailing_ones(disc, reward)).sum(0)
+        if value_gamma is None:
+            return acc + (gamma ** nstep) * next_value * (1 - done)
+        if not isinstance(value_gamma, torch.Tensor):  # np.isscalar branch td.py:269-270
+            value_gamma = torch.full_like(next_value, value_gamma)
+        return acc + _trailing_ones(value_gamma, next_value) * next_value * (1 - _trailing_ones(done, next_value))
+    if isinstance(gamma, list):  # NGU per-sample gamma, td.py:275-282
+        disc = torch.ones([nstep + 1, done.shape[0]])
+        g = torch.stack(gamma, dim=0)
+        for i in range(1, nstep + 1):
+            disc[i] = g * disc[i - 1]
+        disc = _trailing_ones(disc, reward)
+        acc = reward.mul(disc[:nstep]).sum(0)
+        return acc + disc[nstep] * next_value * (1 - done)
+    raise TypeError("The type of gamma should be float or list")  # td.py:284
+
+
+def value_transform(x, eps: float = 1e-2):
+    """value_rescale.py:19  h(x) = sign(x)(sqrt(|x|+1)-1) + eps*x"""
+    return torch.sign(x) * (torch.sqrt(torch.abs(x) + 1) - 1) + eps * x
+
+
+def value_inv_transform(x, eps: float = 1e-2):
+    """value_rescale.py:34"""
+    return torch.sign(x) * (((torch.sqrt(1 + 4 * eps * (torch.abs(x) + 1 + eps)) - 1) / (2 * eps)) ** 2 - 1)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# td.py:649-719 q_nstep_td_error ; td.py:810-867 ..._with_rescale
+# --------------------------------------------------------------------------------------------------------------
+def q_nstep_td_error(
+        q,
+        next_n_q,
+        action,
+        next_n_action,
+        reward,
+        done,
+        weight=None,
+        gamma: Union[float, list] = 0.99,
+        nstep: int = 1,
+        cum_reward: bool = False,
+        value_gamma=None,
+        criterion=None
+):
+    """Returns ``(loss, td_error_per_sample)``; default criterion is elementwise squared error (td.py:655)."""
+    if criterion is None:
+        criterion = torch.nn.MSELoss(reduction='none')
+    if weight is None:
+        weight = torch.ones_like(reward)  # td.py:692-693 -- (n, B) ones: the mean then runs over n*B rows
+    if action.dim() == 1 or action.dim() < q.dim():  # td.py:695-699
+        action = action.unsqueeze(-1)
+    elif action.dim() > 1:  # td.py:700-705 (MARL with already-expanded action)
+        reward = reward.unsqueeze(-1)
+        weight = weight.unsqueeze(-1)
+        done = done.unsqueeze(-1)
+        if value_gamma is not None:
+            value_gamma = value_gamma.unsqueeze(-1)
+    q_sa = q.gather(-1, action).squeeze(-1)  # td.py:707
+    tq = next_n_q.gather(-1, next_n_action.unsqueeze(-1)).squeeze(-1)  # td.py:709
+    if cum_reward:  # td.py:711-715
+        if value_gamma is None:
+            tq = reward + (gamma ** nstep) * tq * (1 - done)
+        else:
+            tq = reward + value_gamma * tq * (1 - done)
+    else:
+        tq = nstep_return(reward, tq, done, gamma, nstep, value_gamma)  # td.py:717
+    per_sample = criterion(q_sa, tq.detach())
+    return (per_sample * weight).mean(), per_sample
+
+
+def q_nstep_td_error_with_rescale(
+        q, next_n_q, action, next_n_action, reward, done, weight=None, gamma=0.99, nstep: int = 1, value_gamma=None,
+        criterion=None
+):
+    if criterion is None:
+        criterion = torch.nn.MSELoss(reduction='none')
+    assert action.dim() == 1, action.shape  # td.py:854
+    if weight is None:
+        weight = torch.ones_like(action)  # td.py:855-856 -- int64 ones
+    rows = torch.arange(action.shape[0])
+    q_sa = q[rows, action]
+    tq = next_n_q[rows, next_n_action]
+    tq = value_inv_transform(tq)  # td.py:862
+    tq = nstep_return(reward, tq, done, gamma, nstep, value_gamma)  # td.py:863
+    tq = value_transform(tq)  # td.py:864
+    per_sample = criterion(q_sa, tq.detach())
+    return (per_sample * weight).mean(), per_sample
+
+
+# --------------------------------------------------------------------------------------------------------------
+# td.py:413-523 dist_nstep_td_error (C51 categorical projection)
+# --------------------------------------------------------------------------------------------------------------
+def dist_nstep_td_error(
+        dist,
+        next_n_dist,
+        act,
+        next_n_act,
+        reward,
+        done,
+        weight=None,
+        gamma: float = 0.99,
+        v_min: float = -10.,
+        v_max: float = 10.,
+        n_atom: int = 51,
+        nstep: int = 1,
+        value_gamma=None
+):
+    """Returns ``(loss, td_error_per_sample)``; single-agent ``act (B,)`` and multi-agent ``act (B,A)``."""
+    disc = torch.ones(nstep)
+    for i in range(1, nstep):
+        disc[i] = gamma * disc[i - 1]
+    ret = torch.matmul(disc, reward)  # td.py:456
+    support = torch.linspace(v_min, v_max, n_atom)  # td.py:457
+    delta_z = (v_max - v_min) / (n_atom - 1)
+    if act.dim() == 1:  # td.py:459-469
+        ret = ret.unsqueeze(-1)
+        done = done.unsqueeze(-1)
+        nrow = act.shape[0]
+        rows = torch.arange(nrow)
+        if weight is None:
+            weight = torch.ones_like(ret)
+        elif isinstance(weight, float):
+            weight = torch.tensor(weight)
+        nd = next_n_dist[rows, next_n_act].detach()
+    else:  # td.py:470-489
+        n_b, n_a = act.shape
+        ret = ret.unsqueeze(-1).repeat(1, n_a)
+        done = done.unsqueeze(-1).repeat(1, n_a)
+        nrow = n_b * n_a
+        rows = torch.arange(nrow)
+        n_act = dist.shape[2]
+        dist = dist.reshape(nrow, n_act, -1)
+        ret = ret.reshape(nrow, -1)
+        done = done.reshape(nrow, -1)
+        next_n_dist = next_n_dist.reshape(nrow, n_act, -1)
+        next_n_act = next_n_act.reshape(nrow)
+        nd = next_n_dist[rows, next_n_act].detach().reshape(nrow, -1)
+        act = act.reshape(nrow)
+        if weight is None:
+            weight = torch.ones_like(ret)
+        elif isinstance(weight, float):
+            weight = torch.tensor(weight)
+    if value_gamma is None:  # td.py:491-498
+        tz = ret + (1 - done) * (gamma ** nstep) * support
+    elif isinstance(value_gamma, float):
+        tz = ret + (1 - done) * torch.tensor(value_gamma).unsqueeze(-1) * support
+    else:
+        tz = ret + (1 - done) * value_gamma.unsqueeze(-1) * support
+    tz = tz.clamp(min=v_min, max=v_max)
+    pos = (tz - v_min) / delta_z  # td.py:500
+    lo = pos.floor().long()
+    hi = pos.ceil().long()
+    lo[(hi > 0) * (lo == hi)] -= 1  # td.py:504
+    hi[(lo < (n_atom - 1)) * (lo == hi)] += 1  # td.py:505
+    proj = torch.zeros_like(nd)
+    base = torch.linspace(0, (nrow - 1) * n_atom, nrow).unsqueeze(1).expand(nrow, n_atom).long()  # td.py:508-509
+    proj.view(-1).index_add_(0, (lo + base).view(-1), (nd * (hi.float() - pos)).view(-1))
+    proj.view(-1).index_add_(0, (hi + base).view(-1), (nd * (pos - lo.float())).view(-1))
+    picked = dist[rows, act]
+    assert (picked > 0.0).all(), ("dist act", picked, "dist:", dist)  # td.py:513
+    log_p = torch.log(picked)
+    if weight.dim() == 1:
+        weight = weight.unsqueeze(-1)
+    per_sample = -(log_p * proj).sum(-1)  # td.py:519 (unweighted)
+    loss = -(log_p * proj * weight).sum(-1).mean()  # td.py:521 (weighted)
+    return loss, per_sample
+
+
+# --------------------------------------------------------------------------------------------------------------
+# td.py:1539-1651 td_lambda_error / generalized_lambda_returns / multistep_forward_view
+# --------------------------------------------------------------------------------------------------------------
+def generalized_lambda_returns(bootstrap_values, rewards, gammas, lambda_, done=None):
+    if not isinstance(gammas, torch.Tensor):
+        gammas = gammas * torch.ones_like(rewards)
+    if not isinstance(lambda_, torch.Tensor):
+        lambda_ = lambda_ * torch.ones_like(rewards)
+    nxt = bootstrap_values[1:, :]  # V_{t+1}, td.py:1604
+    out = torch.empty_like(rewards)
+    if done is None:
+        done = torch.zeros_like(rewards)
+    out[-1, :] = rewards[-1, :] + (1 - done[-1, :]) * gammas[-1, :] * nxt[-1, :]  # td.py:1642
+    trace = gammas * lambda_
+    for t in range(rewards.size(0) - 2, -1, -1):  # td.py:1644-1649
+        out[t, :] = rewards[t, :] + (1 - done[t, :]) * (trace[t, :] * out[t + 1, :] + (gammas[t, :] - trace[t, :]) * nxt[t, :])
+    return out
+
+
+def td_lambda_error(value, reward, weight=None, gamma: float = 0.9, lambda_: float = 0.8):
+    if weight is None:
+        weight = torch.ones_like(reward)
+    with torch.no_grad():
+        target = generalized_lambda_returns(value, reward, gamma, lambda_)
+    err = torch.nn.functional.mse_loss(target, value[:-1], reduction='none')
+    return 0.5 * (err * weight).mean()  # td.py:1570
+
+
+# --------------------------------------------------------------------------------------------------------------
+# upgo.py:7-111
+# --------------------------------------------------------------------------------------------------------------
+def upgo_returns(rewards, bootstrap_values):
+    keep = (rewards + bootstrap_values[1:]) >= bootstrap_values[:-1]  # upgo.py:66
+    keep = torch.cat([keep[1:], torch.ones_like(keep[-1:])], dim=0)  # upgo.py:67
+    return generalized_lambda_returns(bootstrap_values, rewards, 1.0, keep)
+
+
+def tb_cross_entropy(logit, label, mask=None):
+    """upgo.py:7-43: NEGATIVE cross entropy (i.e. log-prob of the label), (T,B) out."""
+    n_t, n_b = label.shape[:2]
+    ce_fn = torch.nn.functional.cross_entropy
+    if label.dim() > 2:
+        assert label.dim() == 3
+        s, n = logit.shape[-2:]
+        ce = -ce_fn(logit.reshape(-1, n), label.reshape(-1), reduction='none').view(n_t * n_b, -1)
+        if mask is not None:
+            ce = ce * mask.reshape(-1, s)
+        return ce.sum(dim=1).reshape(n_t, n_b)
+    ce = -ce_fn(logit.reshape(-1, logit.shape[-1]), label.reshape(-1), reduction='none')
+    return ce.reshape(n_t, n_b, -1).mean(dim=2)
+
+
+def upgo_loss(target_output, rhos, action, rewards, bootstrap_values, mask=None):
+    with torch.no_grad():
+        g = upgo_returns(rewards, bootstrap_values)
+        advantages = rhos * (g - bootstrap_values[:-1])
+    metric = tb_cross_entropy(target_output, action, mask)
+    assert metric.shape == action.shape[:2]
+    return -(advantages * metric).mean()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# vtrace.py:9-136 ; isw.py:55-58
+# --------------------------------------------------------------------------------------------------------------
+def vtrace_error_discrete_action(
+        target_output,
+        behaviour_output,
+        action,
+        value,
+        reward,
+        weight=None,
+        gamma: float = 0.99,
+        lambda_: float = 0.95,
+        rho_clip_ratio: float = 1.0,
+        c_clip_ratio: float = 1.0,
+        rho_pg_clip_ratio: float = 1.0
+):
+    """Returns ``(policy_loss, value_loss, entropy_loss)``."""
+    with torch.no_grad():
+        lp_t = _chosen(_log_softmax_rows(target_output), action)
+        lp_b = _chosen(_log_softmax_rows(behaviour_output), action)
+        isw = torch.exp(lp_t - lp_b)  # isw.py:55-58
+        rho = torch.clamp(isw, max=rho_clip_ratio)
+        cs = torch.clamp(isw, max=c_clip_ratio)
+        deltas = rho * (reward + gamma * value[1:] - value[:-1])  # vtrace.py:22
+        trace = gamma * lambda_
+        vs = value[:-1].clone()
+        carry = 0.
+        for t in range(reward.size(0) - 1, -1, -1):  # vtrace.py:26-28
+            carry = deltas[t] + trace * cs[t] * carry
+            vs[t] += carry
+        rho_pg = torch.clamp(isw, max=rho_pg_clip_ratio)
+        vs_next = torch.cat([vs[1:], value[-1:]], 0)  # vtrace.py:127
+        adv = rho_pg * (reward + gamma * vs_next - value[:-1])  # vtrace.py:45
+    if weight is None:
+        weight = torch.ones_like(reward)
+    lp_all = _log_softmax_rows(target_output)
+    pg_loss = -(_chosen(lp_all, action) * adv * weight).mean()
+    value_loss = (torch.nn.functional.mse_loss(value[:-1], vs, reduction='none') * weight).mean()  # no 0.5
+    entropy_loss = (_row_entropy(lp_all) * weight).mean()
+    return pg_loss, value_loss, entropy_loss

@@ -1,0 +1,441 @@
+"""Seeded parity cases for the nine hot-path operators + adapters that run them through
+
+  * an object exposing the **reference API** (``ding.rl_utils`` names/namedtuples): the real reference loaded by
+    ``oracle/ref_loader.py`` or the product package ``di_engine_b200.rl_utils`` -- same adapter for both;
+  * the flat-argument CPU oracle ``oracle/rl_oracle.py``.
+
+A case = (op, tensors, params).  ``tensors`` holds CPU tensors (or None / python floats for the weight/value_gamma
+variants); names listed in ``GRAD_INPUTS[op]`` get ``requires_grad``.  ``run_*`` return a flat dict of numpy arrays:
+``out_*`` forward results, ``grad_*`` input gradients of ``sum_k c_k * loss_k`` with the fixed mixing coefficients
+``LOSS_MIX`` (so every loss head's backward is exercised with a distinct upstream gradient).
+"""
+import copy
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+GRAD_INPUTS = {
+    'gae': [],
+    'ppo': ['logit_new', 'value_new'],
+    'qntd': ['q'],
+    'qntd_rescale': ['q'],
+    'dntd': ['dist'],
+    'td_lambda': ['value'],
+    'upgo': ['target_output'],
+    'vtrace': ['target_output', 'value'],
+}
+# upstream gradient for each returned loss head (distinct, non-trivial)
+LOSS_MIX = {
+    'ppo': [1.0, 0.5, -0.01, 0.3],
+    'qntd': [1.0],
+    'qntd_rescale': [1.0],
+    'dntd': [1.0],
+    'td_lambda': [1.0],
+    'upgo': [1.0],
+    'vtrace': [1.0, 0.5, -0.01],
+}
+
+
+def _g(seed):
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return g
+
+
+def _randn(g, *shape):
+    return torch.randn(*shape, generator=g)
+
+
+def _rand(g, *shape):
+    return torch.rand(*shape, generator=g)
+
+
+def _randint(g, hi, *shape):
+    return torch.randint(0, hi, shape, generator=g)
+
+
+def _bern(g, p, *shape):
+    return (torch.rand(*shape, generator=g) < p).float()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# case builders
+# ----------------------------------------------------------------------------------------------------------------
+def gae_case(seed, T, B, A=None, done='float', traj='float', gamma=0.99, lambda_=0.97, p_done=0.05, one_d=False):
+    g = _g(seed)
+    shp = (T, ) if one_d else (T, B)
+    vshp = shp if A is None else shp + (A, )
+    t = OrderedDict()
+    t['value'] = _randn(g, *vshp)
+    t['next_value'] = _randn(g, *vshp)
+    t['reward'] = _randn(g, *shp)
+    d = _bern(g, p_done, *shp)
+    tf = torch.clamp(d + _bern(g, p_done, *shp), max=1.0)
+    tf[-1] = 1.0
+    t['done'] = None if done is None else (d.bool() if done == 'bool' else d)
+    t['traj_flag'] = None if traj is None else (tf.bool() if traj == 'bool' else tf)
+    return 'gae', t, dict(gamma=gamma, lambda_=lambda_)
+
+
+def ppo_case(seed, B, N, A=None, weight='none', pretrained=False, lead=None, **params):
+    g = _g(seed)
+    rows = (B, ) if A is None else (B, A)
+    if lead is not None:
+        rows = tuple(lead) + rows
+    samp = rows if A is None else rows[:-1]
+    t = OrderedDict()
+    t['logit_new'] = _randn(g, *rows, N)
+    t['logit_old'] = t['logit_new'] + 0.1 * _rand(g, *rows, N)
+    t['action'] = _randint(g, N, *rows)
+    t['value_new'] = _randn(g, *samp)
+    t['value_old'] = t['value_new'] + 0.1 * _rand(g, *samp)
+    t['adv'] = _randn(g, *samp)
+    t['return_'] = _randn(g, *samp) * 2
+    t['weight'] = None if weight == 'none' else _rand(g, *samp)
+    t['logit_pretrained'] = (t['logit_new'] + 0.3 * _randn(g, *rows, N)) if pretrained else None
+    return 'ppo', t, params
+
+
+def qntd_case(seed, B, N, nstep, weight='none', value_gamma='none', gamma=0.95, cum_reward=False, list_gamma=False,
+              marl_A=None, done='randn', rescale=False):
+    g = _g(seed)
+    t = OrderedDict()
+    if marl_A is None:
+        t['q'] = _randn(g, B, N)
+        t['next_n_q'] = _randn(g, B, N)
+        t['action'] = _randint(g, N, B)
+        t['next_n_action'] = _randint(g, N, B)
+    else:
+        t['q'] = _randn(g, B, marl_A, N)
+        t['next_n_q'] = _randn(g, B, marl_A, N)
+        t['action'] = _randint(g, N, B, marl_A)
+        t['next_n_action'] = _randint(g, N, B, marl_A)
+    t['reward'] = _rand(g, B) if cum_reward else _rand(g, nstep, B)
+    t['done'] = _randn(g, B) if done == 'randn' else _bern(g, 0.3, B)
+    t['weight'] = None if weight == 'none' else _rand(g, B)
+    params = dict(gamma=gamma, nstep=nstep)
+    if not rescale:
+        params['cum_reward'] = cum_reward
+    if list_gamma:
+        params['gamma'] = [torch.tensor(0.9 + 0.01 * i) for i in range(B)]
+    if value_gamma == 'tensor':
+        t['value_gamma'] = _rand(g, B)
+    elif value_gamma == 'float':
+        params['value_gamma'] = 0.857
+    return ('qntd_rescale' if rescale else 'qntd'), t, params
+
+
+def dntd_case(seed, B, N, n_atom, nstep, weight='none', value_gamma='none', gamma=0.95, v_min=-10., v_max=10.,
+              marl_A=None, integer_bins=False, done='bern'):
+    g = _g(seed)
+    lead = (B, ) if marl_A is None else (B, marl_A)
+    t = OrderedDict()
+    t['dist'] = torch.softmax(_randn(g, *lead, N, n_atom), -1)
+    t['next_n_dist'] = torch.softmax(_randn(g, *lead, N, n_atom), -1)
+    t['act'] = _randint(g, N, *lead)
+    t['next_n_act'] = _randint(g, N, *lead)
+    t['reward'] = _randn(g, nstep, B)
+    t['done'] = _bern(g, 0.3, B) if done == 'bern' else _randn(g, B)
+    if integer_bins:
+        # reward 0 and done 1 -> target_z == support*0 + 0 -> b is an exact integer for every atom of those rows;
+        # large |reward| rows clamp to v_min / v_max (b == 0 or n_atom-1 exactly): exercises the l==u fix-ups.
+        t['reward'] = torch.zeros(nstep, B)
+        t['reward'][0, ::3] = 100.
+        t['reward'][0, 1::3] = -100.
+        t['done'] = torch.ones(B)
+        t['done'][::2] = 0.
+    params = dict(gamma=gamma, v_min=v_min, v_max=v_max, n_atom=n_atom, nstep=nstep)
+    if weight == 'tensor':
+        t['weight'] = _rand(g, B) if marl_A is None else _rand(g, B * marl_A)
+    elif weight == 'one':
+        t['weight'] = _rand(g, 1)
+    elif weight == 'float':
+        t['weight'] = None
+        params['weight_float'] = 0.7
+    else:
+        t['weight'] = None
+    if value_gamma == 'tensor':
+        t['value_gamma'] = _rand(g, B)
+    elif value_gamma == 'scalar_tensor':
+        t['value_gamma'] = torch.tensor(0.9)
+    elif value_gamma == 'float':
+        params['value_gamma'] = 0.857
+    return 'dntd', t, params
+
+
+def td_lambda_case(seed, T, B, weight='none', gamma=0.9, lambda_=0.8):
+    g = _g(seed)
+    t = OrderedDict()
+    t['value'] = _randn(g, T + 1, B)
+    t['reward'] = _rand(g, T, B)
+    t['weight'] = None if weight == 'none' else _rand(g, T, B)
+    return 'td_lambda', t, dict(gamma=gamma, lambda_=lambda_)
+
+
+def upgo_case(seed, T, B, N, N2=None, mask=False):
+    g = _g(seed)
+    t = OrderedDict()
+    if N2 is None:
+        t['target_output'] = _randn(g, T, B, N)
+        t['action'] = _randint(g, N, T, B)
+    else:
+        t['target_output'] = _randn(g, T, B, N2, N)
+        t['action'] = _randint(g, N, T, B, N2)
+    t['rhos'] = _rand(g, T, B) + 0.5
+    t['rewards'] = _randn(g, T, B)
+    t['bootstrap_values'] = _randn(g, T + 1, B)
+    t['mask'] = (_rand(g, T, B, N2) > 0.3).float() if mask else None
+    return 'upgo', t, {}
+
+
+def vtrace_case(seed, T, B, N, weight='none', **params):
+    g = _g(seed)
+    t = OrderedDict()
+    t['target_output'] = _randn(g, T, B, N)
+    t['behaviour_output'] = t['target_output'] + 0.5 * _randn(g, T, B, N)
+    t['action'] = _randint(g, N, T, B)
+    t['value'] = _randn(g, T + 1, B)
+    t['reward'] = _rand(g, T, B)
+    t['weight'] = None if weight == 'none' else _rand(g, T, B)
+    return 'vtrace', t, params
+
+
+def build_cases():
+    """Small cases: what the golden fixtures hold and what every implementation is compared on."""
+    c = OrderedDict()
+    # ---- gae (configs A + reference test shapes tests/test_gae.py:7-36) -------------------------------------
+    c['gae_cfgA'] = gae_case(1, 128, 8, gamma=0.9, lambda_=0.95)
+    c['gae_none'] = gae_case(2, 32, 6, done=None, traj=None)
+    c['gae_done_only'] = gae_case(3, 32, 6, traj=None, p_done=0.2)
+    c['gae_bool'] = gae_case(4, 40, 5, done='bool', traj='bool', p_done=0.2)
+    c['gae_1d'] = gae_case(5, 257, 1, one_d=True, p_done=0.03)
+    c['gae_marl'] = gae_case(6, 24, 4, A=3, p_done=0.2)
+    c['gae_wide'] = gae_case(7, 16, 200, p_done=0.1)
+    c['gae_T1'] = gae_case(8, 1, 7)
+    # ---- ppo (tests/test_ppo.py:24-92) -----------------------------------------------------------------------
+    c['ppo_cfgA'] = ppo_case(10, 64, 2, clip_ratio=0.2)
+    i = 11
+    for uvc in (True, False):
+        for dc in (None, 5.0):
+            for w in ('none', 'tensor'):
+                c['ppo_vc%d_dc%d_w%d' % (uvc, dc is not None, w == 'tensor')] = ppo_case(
+                    i, 48, 6, weight=w, use_value_clip=uvc, dual_clip=dc, clip_ratio=0.2
+                )
+                i += 1
+    for k in ('k1', 'k2', 'k3'):
+        c['ppo_kl_' + k] = ppo_case(i, 33, 5, pretrained=True, kl_type=k, weight='tensor')
+        i += 1
+    c['ppo_marl'] = ppo_case(i, 12, 7, A=4, weight='tensor')
+    c['ppo_marl_dc'] = ppo_case(i + 1, 12, 7, A=4, dual_clip=3.0)
+    c['ppo_wideN'] = ppo_case(i + 2, 9, 130, weight='tensor', clip_ratio=0.1)
+    c['ppo_seq'] = ppo_case(i + 3, 5, 6, lead=(3, ), weight='tensor')
+    c['ppo_one'] = ppo_case(i + 4, 1, 3)
+    # ---- q_nstep (tests/test_td.py:13-126) -------------------------------------------------------------------
+    c['qntd_cfgB'] = qntd_case(30, 64, 6, 3, value_gamma='tensor', gamma=0.99, done='bern')
+    c['qntd_n1'] = qntd_case(31, 5, 4, 1)
+    c['qntd_n5_w'] = qntd_case(32, 17, 3, 5, weight='tensor')
+    c['qntd_cum'] = qntd_case(33, 17, 3, 5, cum_reward=True, value_gamma='tensor')
+    c['qntd_cum_novg'] = qntd_case(34, 17, 3, 5, cum_reward=True)
+    c['qntd_vg_float'] = qntd_case(35, 9, 3, 2, value_gamma='float')
+    c['qntd_ngu'] = qntd_case(36, 6, 4, 3, list_gamma=True)
+    c['qntdr_n3'] = qntd_case(40, 33, 6, 3, rescale=True)
+    c['qntdr_n5_w_vg'] = qntd_case(41, 9, 4, 5, rescale=True, weight='tensor', value_gamma='tensor')
+    c['qntdr_ngu'] = qntd_case(42, 6, 4, 3, rescale=True, list_gamma=True)
+    # ---- dist_nstep (tests/test_td.py:130-204) ---------------------------------------------------------------
+    c['dntd_cfgC'] = dntd_case(50, 32, 6, 51, 3, gamma=0.99, value_gamma='tensor')
+    c['dntd_n5'] = dntd_case(51, 4, 3, 51, 5)
+    c['dntd_w_tensor'] = dntd_case(52, 7, 3, 51, 5, weight='tensor')
+    c['dntd_w_one'] = dntd_case(53, 7, 3, 51, 2, weight='one', done='randn')
+    c['dntd_w_float'] = dntd_case(54, 7, 3, 21, 2, weight='float', value_gamma='float')
+    c['dntd_vg_scalar'] = dntd_case(55, 7, 3, 51, 5, value_gamma='scalar_tensor')
+    c['dntd_intbins'] = dntd_case(56, 12, 4, 51, 2, integer_bins=True, gamma=1.0)
+    c['dntd_marl'] = dntd_case(57, 4, 3, 51, 5, marl_A=2)
+    c['dntd_atoms200'] = dntd_case(58, 5, 2, 200, 3, v_min=-1., v_max=5.)
+    # ---- td_lambda / upgo / vtrace ---------------------------------------------------------------------------
+    c['tdl_basic'] = td_lambda_case(60, 8, 4)
+    c['tdl_w'] = td_lambda_case(61, 33, 17, weight='tensor', gamma=0.99, lambda_=0.95)
+    c['tdl_T1'] = td_lambda_case(62, 1, 5)
+    c['upgo_3d'] = upgo_case(70, 4, 8, 5)
+    c['upgo_3d_big'] = upgo_case(71, 33, 19, 6)
+    c['upgo_4d'] = upgo_case(72, 4, 8, 5, N2=7)
+    c['upgo_4d_mask'] = upgo_case(73, 4, 8, 5, N2=7, mask=True)
+    c['vtrace_small'] = vtrace_case(80, 4, 8, 16, rho_clip_ratio=1.1)
+    c['vtrace_cfgE'] = vtrace_case(81, 16, 24, 6, weight='tensor', gamma=0.99, lambda_=0.95)
+    c['vtrace_clips'] = vtrace_case(82, 9, 5, 3, rho_clip_ratio=0.8, c_clip_ratio=1.3, rho_pg_clip_ratio=2.0)
+    return c
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# adapters
+# ----------------------------------------------------------------------------------------------------------------
+def prepare(op, tensors, device='cpu'):
+    """Deep-copy the case tensors to ``device`` and switch on requires_grad for the differentiable inputs."""
+    out = OrderedDict()
+    for k, v in tensors.items():
+        if isinstance(v, torch.Tensor):
+            v = v.clone().to(device)
+            if k in GRAD_INPUTS[op]:
+                v.requires_grad_(True)
+        out[k] = v
+    return out
+
+
+def _np(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy().copy()
+    return np.asarray(x)
+
+
+def _backward(op, losses, t, res):
+    mix = LOSS_MIX.get(op)
+    if not mix:
+        return
+    total = None
+    for c, l in zip(mix, losses):
+        if isinstance(l, torch.Tensor) and l.requires_grad:
+            total = c * l if total is None else total + c * l
+    if total is None:
+        return
+    total.backward()
+    for k in GRAD_INPUTS[op]:
+        if t[k].grad is not None:
+            res['grad_' + k] = _np(t[k].grad)
+
+
+def run_api(api, op, tensors, params, device='cpu'):
+    """Run a case through an object with the reference's names (the real reference or the product package)."""
+    t = prepare(op, tensors, device)
+    p = copy.copy(params)
+    res = OrderedDict()
+    if op == 'gae':
+        data = api.gae_data(t['value'], t['next_value'], t['reward'], t['done'], t['traj_flag'])
+        adv = api.gae(data, **p)
+        res['out_adv'] = _np(adv)
+        res['out_next_value_after'] = _np(t['next_value'])  # in-place mask, gae.py:61
+        return res
+    if op == 'ppo':
+        data = api.ppo_data(*[t[k] for k in ('logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv',
+                                              'return_', 'weight', 'logit_pretrained')])
+        loss, info = api.ppo_error(data, **p)
+        for k in ('policy_loss', 'value_loss', 'entropy_loss', 'kl_div'):
+            res['out_' + k] = _np(getattr(loss, k))
+        res['out_approx_kl'] = np.float32(info.approx_kl)
+        res['out_clipfrac'] = np.float32(info.clipfrac)
+        _backward(op, list(loss), t, res)
+        return res
+    if op in ('qntd', 'qntd_rescale'):
+        data = api.q_nstep_td_data(*[t[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done',
+                                                    'weight')])
+        gamma = p.pop('gamma')
+        if isinstance(gamma, list):
+            gamma = [x.to(device) for x in gamma]
+        if 'value_gamma' in t:
+            p['value_gamma'] = t['value_gamma']
+        fn = api.q_nstep_td_error if op == 'qntd' else api.q_nstep_td_error_with_rescale
+        loss, per = fn(data, gamma, **p)
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'dntd':
+        w = p.pop('weight_float', None)
+        data = api.dist_nstep_td_data(t['dist'], t['next_n_dist'], t['act'], t['next_n_act'], t['reward'], t['done'],
+                                      w if w is not None else t['weight'])
+        if 'value_gamma' in t:
+            p['value_gamma'] = t['value_gamma']
+        loss, per = api.dist_nstep_td_error(data, **p)
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'td_lambda':
+        loss = api.td_lambda_error(api.td_lambda_data(t['value'], t['reward'], t['weight']), **p)
+        res['out_loss'] = _np(loss)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'upgo':
+        loss = api.upgo_loss(t['target_output'], t['rhos'], t['action'], t['rewards'], t['bootstrap_values'],
+                             t['mask'])
+        res['out_loss'] = _np(loss)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'vtrace':
+        data = api.vtrace_data(t['target_output'], t['behaviour_output'], t['action'], t['value'], t['reward'],
+                               t['weight'])
+        loss = api.vtrace_error_discrete_action(data, **p)
+        for k in ('policy_loss', 'value_loss', 'entropy_loss'):
+            res['out_' + k] = _np(getattr(loss, k))
+        _backward(op, list(loss), t, res)
+        return res
+    raise KeyError(op)
+
+
+def run_oracle(orc, op, tensors, params):
+    """Run a case through the flat-argument CPU oracle (``oracle/rl_oracle.py``)."""
+    t = prepare(op, tensors, 'cpu')
+    p = copy.copy(params)
+    res = OrderedDict()
+    if op == 'gae':
+        adv = orc.gae(t['value'], t['next_value'], t['reward'], t['done'], t['traj_flag'], **p)
+        res['out_adv'] = _np(adv)
+        res['out_next_value_after'] = _np(t['next_value'])
+        return res
+    if op == 'ppo':
+        out = orc.ppo_error(**t, **p)
+        for k, v in zip(('policy_loss', 'value_loss', 'entropy_loss', 'kl_div'), out[:4]):
+            res['out_' + k] = _np(v)
+        res['out_approx_kl'] = np.float32(out[4])
+        res['out_clipfrac'] = np.float32(out[5])
+        _backward(op, list(out[:4]), t, res)
+        return res
+    if op in ('qntd', 'qntd_rescale'):
+        fn = orc.q_nstep_td_error if op == 'qntd' else orc.q_nstep_td_error_with_rescale
+        loss, per = fn(**t, **p)
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'dntd':
+        w = p.pop('weight_float', None)
+        if w is not None:
+            t['weight'] = w
+        loss, per = orc.dist_nstep_td_error(**t, **p)
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'td_lambda':
+        loss = orc.td_lambda_error(**t, **p)
+        res['out_loss'] = _np(loss)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'upgo':
+        loss = orc.upgo_loss(**t)
+        res['out_loss'] = _np(loss)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'vtrace':
+        out = orc.vtrace_error_discrete_action(**t, **p)
+        for k, v in zip(('policy_loss', 'value_loss', 'entropy_loss'), out):
+            res['out_' + k] = _np(v)
+        _backward(op, list(out), t, res)
+        return res
+    raise KeyError(op)
+
+
+# outputs that are driven by integer / boolean decisions and must match bit-for-bit on the GPU as well
+EXACT_KEYS = {'gae': ['out_adv', 'out_next_value_after']}
+
+
+def compare(res, ref, rtol=1e-5, atol=1e-5, exact=False):
+    """Assert two result dicts agree. fp32 tolerance ``|a-b| <= atol + rtol*|b|`` (north star: 1e-5)."""
+    assert set(res.keys()) == set(ref.keys()), (sorted(res.keys()), sorted(ref.keys()))
+    for k in ref:
+        a, b = np.asarray(res[k]), np.asarray(ref[k])
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        if exact:
+            assert np.array_equal(a, b, equal_nan=True), (k, float(np.max(np.abs(a.astype(np.float64) - b))))
+        else:
+            ok = np.allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+            assert ok, (k, float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))))
