@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""Benchmark of the learner hot path: GAE + ppo_error (forward AND backward) on a (T, B) trajectory batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Metric (BASELINE.json): learner transitions/sec, config D = Atari-PPO shape T=128, B=4096 per GPU, N=6 actions
+(``pong_ppo_config.py``: gamma 0.99, lambda 0.95, clip 0.2, value clip on).  One step = one pass of
+gae -> ppo_error forward -> backward(policy + 0.5 value - 0.01 entropy) over one batch of 524 288 transitions per GPU.
+
+  value     inputs resident in HBM; the three kernels replayed as a CUDA graph; input/output buffer sets are rotated
+            so that consecutive steps never find their data in the 126 MB L2 (4 sets x 67 MB); timed with CUDA events
+            on the launching stream between barrier + synchronize, max over ranks.
+  e2e       the same step through the public API (di_engine_b200.gae / ppo_error / backward) starting from PINNED
+            HOST buffers: per step H2D copy of every input, the three kernels, D2H read of the loss scalars.
+  roofline  per-kernel CUDA-event timing of the dominant kernel against MEASURED_PEAKS.json (HBM copy bandwidth).
+  cpu_baseline / --impl reference
+            the reference algorithm on the host cores: oracle/rl_oracle.py, the torch-CPU restatement that is pinned
+            bit-exact to ding.rl_utils (the reference is pure Python and cannot travel to the GPU box).
+
+Multi-GPU (torchrun, one rank per GPU): the batch shards along B with no data-path exchange; the only collective is
+one NCCL all-reduce per step of the packed loss scalars (mean-of-rank-means, as DI-engine's DDP does,
+ding/utils/pytorch_ddp_dist_helper.py:38-47), issued on a side stream so it overlaps the next step's kernels.
+Weak scaling: every rank holds a full T=128 x B=4096 shard.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_LEN, B_COLS, N_ACT = 128, 4096, 6
+GAMMA, LAMBDA, CLIP = 0.99, 0.95, 0.2
+W_VALUE, W_ENTROPY = 0.5, -0.01
+ALG_BYTES_PER_TR = {'gae': 24, 'ppo_fwd': 76, 'ppo_bwd': 100, 'step': 128}
+METRIC = 'learner transitions/sec (GAE+ppo_error fwd+bwd, T=128 x B=4096 per GPU)'
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic batch
+# ----------------------------------------------------------------------------------------------------------------
+def make_batch(seed, T=T_LEN, B=B_COLS, N=N_ACT):
+    g = torch.Generator().manual_seed(seed)
+    value = torch.randn(T, B, generator=g)
+    done = (torch.rand(T, B, generator=g) < 0.01).float()
+    next_value = torch.cat([value[1:], torch.randn(1, B, generator=g)], 0)
+    next_value = torch.where(done.bool(), torch.randn(T, B, generator=g), next_value).contiguous()
+    reward = torch.randn(T, B, generator=g)
+    traj = done.clone()
+    traj[-1] = 1.0
+    logit_new = torch.randn(T * B, N, generator=g)
+    logit_old = logit_new + 0.1 * torch.rand(T * B, N, generator=g)
+    action = torch.randint(0, N, (T * B, ), generator=g)
+    value_new = torch.randn(T * B, generator=g)
+    value_old = value_new + 0.1 * torch.rand(T * B, generator=g)
+    return_ = torch.randn(T * B, generator=g)
+    return dict(value=value, next_value=next_value, reward=reward, done=done, traj_flag=traj, logit_new=logit_new,
+                logit_old=logit_old, action=action, value_new=value_new, value_old=value_old, return_=return_)
+
+
+def batch_bytes(b):
+    return sum(v.numel() * v.element_size() for v in b.values())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_step(orc, b):
+    adv = orc.gae(b['value'], b['next_value'].clone(), b['reward'], b['done'], b['traj_flag'], GAMMA, LAMBDA)
+    ln = b['logit_new'].detach().requires_grad_(True)
+    vn = b['value_new'].detach().requires_grad_(True)
+    p, v, e, k, akl, cf = orc.ppo_error(ln, b['logit_old'], b['action'], vn, b['value_old'], adv.reshape(-1),
+                                        b['return_'], None, None, CLIP, True, None)
+    (p + W_VALUE * v + W_ENTROPY * e).backward()
+    return float(p)
+
+
+def run_cpu(steps, warmup):
+    from oracle import rl_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = make_batch(0)
+    for _ in range(warmup):
+        cpu_step(rl_oracle, b)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(rl_oracle, b)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return dict(value=T_LEN * B_COLS / med, ms_per_step=med * 1e3, total_s=sum(times), cores=cores,
+                threads=torch.get_num_threads())
+
+
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.proc = None
+        self.idx = gpu_index
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            f = [x.strip() for x in s.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class DeviceStep:
+    """One learner step on device-resident buffers, via the tensor-level layer under the public API."""
+
+    def __init__(self, host_batch, dev):
+        from di_engine_b200 import ops
+        self.ops = ops
+        self.b = {k: v.to(dev) for k, v in host_batch.items()}
+        self.nv0 = self.b['next_value'].clone()
+        self.S = T_LEN * B_COLS
+        self.g_p = torch.tensor(1.0, device=dev)
+        self.g_v = torch.tensor(W_VALUE, device=dev)
+        self.g_e = torch.tensor(W_ENTROPY, device=dev)
+        self.adv = torch.empty_like(self.b['value'])
+        self.out = torch.zeros(8, device=dev)
+        self.grad_logit = torch.empty_like(self.b['logit_new'])
+        self.grad_value = torch.empty_like(self.b['value_new'])
+        self.ws = ops.workspace(torch.device(dev))
+
+    def gae(self):
+        b, o = self.b, self.ops
+        rc = o.lib().b200rl_gae(o.ptr(b['value']), o.ptr(b['next_value']), o.ptr(b['reward']), o.ptr(b['done']),
+                                o.ptr(b['traj_flag']), o.ptr(self.adv), T_LEN, B_COLS, 1, GAMMA, LAMBDA, 1,
+                                o.stream_ptr())
+        assert rc == 0, rc
+
+    def ppo_fwd(self):
+        b, o = self.b, self.ops
+        rc = o.lib().b200rl_ppo_fwd(o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
+                                    o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(self.adv), o.ptr(b['return_']),
+                                    None, self.S, 1, N_ACT, CLIP, 1, 0.0, 1, o.ptr(self.out), o.ptr(self.ws),
+                                    self.ws.numel() * 4, o.stream_ptr())
+        assert rc == 0, rc
+
+    def ppo_bwd(self):
+        b, o = self.b, self.ops
+        rc = o.lib().b200rl_ppo_bwd(o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
+                                    o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(self.adv), o.ptr(b['return_']),
+                                    None, self.S, 1, N_ACT, CLIP, 1, 0.0, 1, o.ptr(self.g_p), o.ptr(self.g_v),
+                                    o.ptr(self.g_e), None, o.ptr(self.grad_logit), o.ptr(self.grad_value),
+                                    o.stream_ptr())
+        assert rc == 0, rc
+
+    def __call__(self):
+        self.gae()
+        self.ppo_fwd()
+        self.ppo_bwd()
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    import di_engine_b200 as b2
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        raise SystemExit('launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)' % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = 'cuda:%d' % local
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    NSETS = 4
+    sets = [DeviceStep(make_batch(1000 * rank + i), dev) for i in range(NSETS)]
+    step_bytes = ALG_BYTES_PER_TR['step'] * T_LEN * B_COLS
+    side = torch.cuda.Stream()
+    main = torch.cuda.Stream()
+    packed = [torch.zeros(8, device=dev) for _ in range(NSETS)]
+
+    # ---- correctness guard: first set against the CPU oracle on rank 0 (outside every timed region) ----------------
+    if rank == 0:
+        from oracle import rl_oracle
+        hb = make_batch(0)
+        s0 = sets[0]
+        s0()
+        torch.cuda.synchronize()
+        adv_ref = rl_oracle.gae(hb['value'], hb['next_value'].clone(), hb['reward'], hb['done'], hb['traj_flag'], GAMMA,
+                                LAMBDA)
+        assert torch.equal(s0.adv.cpu(), adv_ref), 'gae parity broken'
+        s0.b['next_value'].copy_(s0.nv0)
+
+    # ---- capture one graph per buffer set -------------------------------------------------------------------------
+    graphs = []
+    with torch.cuda.stream(main):
+        for s in sets:
+            s()
+            s()
+        main.synchronize()
+        for s in sets:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=main):
+                s()
+            graphs.append(g)
+    torch.cuda.synchronize()
+
+    def device_loop(n):
+        for i in range(n):
+            j = i % NSETS
+            graphs[j].replay()
+            if world > 1:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    packed[j].copy_(sets[j].out, non_blocking=True)
+                    dist.all_reduce(packed[j])
+        if world > 1:
+            main.wait_stream(side)
+
+    with torch.cuda.stream(main):
+        device_loop(max(W, 3))
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(main)
+        device_loop(K)
+        e1.record(main)
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+
+        # ---- per-kernel timing (eager launches, rotated sets), same stream ----------------------------------------
+        names = ['gae', 'ppo_fwd', 'ppo_bwd']
+        per = {n: [] for n in names}
+        for i in range(K + 3):
+            s = sets[i % NSETS]
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            evs[0].record(main)
+            s.gae()
+            evs[1].record(main)
+            s.ppo_fwd()
+            evs[2].record(main)
+            s.ppo_bwd()
+            evs[3].record(main)
+            main.synchronize()
+            if i >= 3:
+                for k, n in enumerate(names):
+                    per[n].append(evs[k].elapsed_time(evs[k + 1]))
+        clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the public API from pinned host buffers ------------------------------------------------
+    host = [{k: v.pin_memory() for k, v in make_batch(2000 * rank + i).items()} for i in range(2)]
+    h2d = batch_bytes(host[0])
+
+    def e2e_step(hb):
+        d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        adv = b2.gae(b2.gae_data(d['value'], d['next_value'], d['reward'], d['done'], d['traj_flag']), GAMMA, LAMBDA)
+        ln = d['logit_new'].requires_grad_(True)
+        vn = d['value_new'].requires_grad_(True)
+        loss, info = b2.ppo_error(
+            b2.ppo_data(ln, d['logit_old'], d['action'], vn, d['value_old'], adv.view(-1), d['return_'], None, None),
+            CLIP, True, None)
+        total = loss.policy_loss + W_VALUE * loss.value_loss + W_ENTROPY * loss.entropy_loss
+        total.backward()
+        return total.item()  # D2H read of the step's result (info already cost one 8-byte read)
+
+    e2e_steps = max(5, min(K, 20))
+    for i in range(3):
+        e2e_step(host[i % 2])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(e2e_steps):
+        e2e_step(host[i % 2])
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+
+    # ---- max over ranks --------------------------------------------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        tr_per_step = T_LEN * B_COLS * world
+        ms_step = dev_ms / K
+        value = tr_per_step / (ms_step * 1e-3)
+        kmean = {n: statistics.mean(v) for n, v in per.items()}
+        dom = max(kmean, key=kmean.get)
+        dom_bytes = ALG_BYTES_PER_TR[dom] * T_LEN * B_COLS
+        achieved = dom_bytes / (kmean[dom] * 1e-3) / 1e9
+        step_achieved = step_bytes / (ms_step * 1e-3) / 1e9
+        cpu = run_cpu(steps=8, warmup=2) if world == 1 else None
+        e2e_value = tr_per_step / (e2e_ms / e2e_steps * 1e-3)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'transitions/s', 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {
+                'workload': 'configs[3] Atari PPO gae+ppo_error T=128 B=4096 N=6 per GPU (B sharded across GPUs; obs '
+                            '[4,84,84] is not read by any kernel on this path and is not materialised)',
+                'transitions_per_step_per_gpu': T_LEN * B_COLS, 'gamma': GAMMA, 'lambda': LAMBDA, 'clip_ratio': CLIP,
+                'loss_mix': [1.0, W_VALUE, W_ENTROPY], 'parallelism': 'dp%d' % world,
+                'l2_policy': 'inputs rotated over %d buffer sets of 67 MB (> 126 MB L2) between consecutive steps' %
+                             NSETS,
+                'launch': 'CUDA graph replay of 3 kernels per step',
+                'collective': 'none' if world == 1 else 'one NCCL all-reduce of 8 packed loss floats per step, side stream',
+            },
+            'roofline': {
+                'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'alg_bytes_per_launch': dom_bytes, 'kernel_ms': kmean,
+                'step': {'alg_bytes': step_bytes, 'achieved': step_achieved, 'frac': step_achieved / peak},
+            },
+            'cpu_baseline': None if cpu is None else {
+                'value': cpu['value'], 'unit': 'transitions/s', 'cores': cpu['cores'], 'kind': 'port',
+                'sample': 'full T=128 x B=4096 batch, median of 8 steps after 2 warm-up (%.1f s CPU), %s' %
+                          (cpu['total_s'], cpu_model()),
+                'ms_per_step': cpu['ms_per_step'],
+            },
+            'e2e': {'value': e2e_value, 'unit': 'transitions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
+                    'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps},
+            'gpu_launches': 3 * K,
+            'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    r = run_cpu(steps=args.steps, warmup=max(args.warmup, 1))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': 'transitions/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': max(args.warmup, 1), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[3] Atari PPO gae+ppo_error T=128 B=4096 N=6 (one batch, host cores)',
+                   'parallelism': 'cpu'},
+        'cpu_baseline': {'value': r['value'], 'unit': 'transitions/s', 'cores': r['cores'], 'kind': 'port',
+                         'sample': 'full T=128 x B=4096 batch per step, %d torch threads, %s' %
+                                   (r['threads'], cpu_model())},
+        'e2e': {'value': r['value'], 'unit': 'transitions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        if args.steps > 400:
+            args.steps = 400  # bounded: ~50 ms of host work per step
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,73 @@
+"""ctypes binding of ``lib/libb200rl.so`` -- the C ABI declared in ``include/b200rl.h``.
+
+There is no fallback: if the shared library is missing (not built) importing the operators raises, and every
+operator raises when no CUDA device is present.  Build with ``python __graft_entry__.py`` / ``make -C csrc``.
+"""
+import ctypes
+import os
+from ctypes import c_double, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200rl.so")
+
+P = c_void_p  # device pointer
+LL = c_longlong
+D = c_double
+I = c_int
+
+# name -> argtypes (restype is int unless listed in _RESTYPE); mirrors include/b200rl.h one to one
+PROTOTYPES = {
+    "b200rl_version": [],
+    "b200rl_built_for_sm": [],
+    "b200rl_workspace_bytes": [],
+    "b200rl_gae": [P, P, P, P, P, P, LL, LL, LL, D, D, I, P],
+    "b200rl_ppo_fwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, c_size_t, P],
+    "b200rl_ppo_bwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, P],
+    "b200rl_qntd_fwd": [P, P, P, P, P, P, P, P, LL, P, LL, LL, I, D, I, I, D, I, D, P, P, P, P, P, c_size_t, P],
+    "b200rl_qntd_bwd": [P, P, P, LL, LL, P, P],
+    "b200rl_dntd_fwd": [P, P, P, P, P, P, P, LL, P, LL, P, LL, LL, LL, I, I, D, D, D, P, P, P, P, P, c_size_t, P],
+    "b200rl_dntd_bwd": [P, P, P, P, LL, P, LL, LL, I, P, P],
+    "b200rl_lambda_returns": [P, P, P, D, P, D, P, I, LL, LL, P, P],
+    "b200rl_td_lambda_fwd": [P, P, P, D, D, LL, LL, P, P, P, c_size_t, P],
+    "b200rl_scale": [P, P, P, LL, P],
+    "b200rl_upgo_head_fwd": [P, P, P, P, P, P, LL, LL, LL, P, P, P, c_size_t, P],
+    "b200rl_upgo_head_bwd": [P, P, P, P, P, LL, LL, LL, P, P],
+    "b200rl_vtrace_fwd": [P, P, P, P, P, P, LL, LL, LL, D, D, D, D, D, P, P, P, P, P, c_size_t, P],
+    "b200rl_vtrace_bwd": [P, P, P, P, P, P, P, P, LL, LL, LL, P, P, P],
+}
+_RESTYPE = {"b200rl_workspace_bytes": c_size_t}
+
+_lib = None
+
+
+class B200RLError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise B200RLError(
+            "di_engine_b200: CUDA library %s not found. Build it first (python __graft_entry__.py, or "
+            "make -C di-engine_b200/csrc). There is no CPU fallback." % LIB_PATH
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc == -1:
+        raise B200RLError("%s: invalid argument (B200RL_ERR_ARG)" % what)
+    if rc == -2:
+        raise B200RLError("%s: workspace too small for this problem size (B200RL_ERR_WORKSPACE)" % what)
+    raise B200RLError("%s: CUDA error %d at launch" % (what, rc))

@@ -1,0 +1,409 @@
+// Policy-gradient heads on (T, B, N) logits:
+//   upgo_loss (ding/rl_utils/upgo.py:77-111, tb_cross_entropy :7-43)           -> upgo_head_fwd / upgo_head_bwd
+//   vtrace_error_discrete_action (ding/rl_utils/vtrace.py:72-136, isw.py:55-58) -> vtrace_fwd / vtrace_bwd
+//
+// V-trace forward is two launches: a row kernel (log-softmax statistics of the target and behaviour logits, one pass
+// over the two (T,B,N) tensors, rows staged through shared memory) and a column-tile scan kernel (gae.cu scheme) that
+// turns the importance weights into vs / advantages, reduces the three losses in-kernel and leaves the per-element
+// gradient coefficients for the single backward launch.
+#include "../../include/b200rl.h"
+#include "common.cuh"
+
+namespace b200rl {
+
+// stage `nflt` contiguous floats gsrc[0..nflt) into shared memory, float4 when both sides are 16B-aligned
+template <int NT>
+__device__ __forceinline__ void stage_rows(float* sdst, const float* gsrc, int nflt, bool vec_ok) {
+    int done = 0;
+    if (vec_ok) {
+        const int nv4 = nflt >> 2;
+        for (int i = threadIdx.x; i < nv4; i += NT)
+            reinterpret_cast<float4*>(sdst)[i] = ldg_stream4(reinterpret_cast<const float4*>(gsrc) + i);
+        done = nv4 << 2;
+    }
+    for (int i = done + threadIdx.x; i < nflt; i += NT) sdst[i] = gsrc[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// UPGO head.  rows = T*B*K (K = 1 for (T,B,N) logits, K = N2 for (T,B,N2,N)); metric[t,b] = sum_k mask_k * logp(a_k);
+// adv = rho * (G - V_t) with G from lambda_returns(upgo mode); loss = -mean_{T*B}(adv * metric).
+// ---------------------------------------------------------------------------------------------------------------
+struct UpgoArgs {
+    const float* logit;       // (TB*K, N)
+    const long long* action;  // (TB*K)
+    const float* mask;        // nullable (TB*K)
+    const float* rho;         // (TB)
+    const float* ret;         // (TB) upgo returns
+    const float* value;       // (TB) = bootstrap_values[:-1]
+    long long TB;
+    int K;
+    int N;
+    float* loss;
+    float* adv_saved;  // (TB)
+    const float* g_loss;
+    float* grad_logit;
+};
+
+template <int NT, int L>
+__global__ void __launch_bounds__(NT) upgo_fwd_kernel(UpgoArgs a, float* ws) {
+    const int lane = (L == 32) ? (threadIdx.x & 31) : 0;
+    const long long s = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
+                                  : (long long)blockIdx.x * NT + threadIdx.x;
+    float acc[1] = {0.f};
+    if (s < a.TB) {
+        float metric = 0.f;
+        for (int k = 0; k < a.K; ++k) {
+            const long long row = s * a.K + k;
+            const float* z = a.logit + row * a.N;
+            const float lse = row_lse<L>([&](int j) { return z[j]; }, a.N, lane);
+            float lp = z[a.action[row]] - lse;
+            if (a.mask) lp *= a.mask[row];
+            metric += lp;
+        }
+        if (lane == 0) {
+            const float adv = fmul(a.rho[s], fsub(a.ret[s], a.value[s]));  // upgo.py:107
+            a.adv_saved[s] = adv;
+            acc[0] = adv * metric;
+        }
+    }
+    double tot[1];
+    if (grid_sum<1, NT>(acc, tot, ws, 0) && threadIdx.x == 0) a.loss[0] = (float)(-tot[0] / (double)a.TB);
+}
+
+template <int NT, int L>
+__global__ void __launch_bounds__(NT) upgo_bwd_kernel(UpgoArgs a) {
+    const int lane = (L == 32) ? (threadIdx.x & 31) : 0;
+    const long long row = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
+                                    : (long long)blockIdx.x * NT + threadIdx.x;
+    if (row >= a.TB * a.K) return;
+    const long long s = row / a.K;
+    const float* z = a.logit + row * a.N;
+    float* gz = a.grad_logit + row * a.N;
+    const float lse = row_lse<L>([&](int j) { return z[j]; }, a.N, lane);
+    const float g = a.g_loss ? *a.g_loss : 0.f;
+    float c = -g * a.adv_saved[s] / (float)a.TB;  // d loss / d logp(row)
+    if (a.mask) c *= a.mask[row];
+    const int act = (int)a.action[row];
+    for (int j = lane; j < a.N; j += L) {
+        float gj = -c * expf(z[j] - lse);
+        if (j == act) gj += c;
+        gz[j] = gj;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// V-trace
+// ---------------------------------------------------------------------------------------------------------------
+struct VtArgs {
+    const float* target;      // (M, N) M = T*B
+    const float* behaviour;   // (M, N)
+    const long long* action;  // (M)
+    const float* value;       // (T+1, B)
+    const float* reward;      // (T, B)
+    const float* weight;      // nullable (T, B)
+    long long T, B;
+    int N;
+    float gamma, gamma_lambda, rho_clip, c_clip, rho_pg_clip;
+    // forward scratch / saved (all (T, B))
+    float* lp_t;     // log pi(a)
+    float* isw;      // importance weight, overwritten in the scan kernel by c_pg = adv*w
+    float* ent;      // row entropy, overwritten by the scan kernel with dV = 2*w*(V - vs)/M
+    float* out;      // 3 losses
+    // backward
+    const float* g_pg;
+    const float* g_val;
+    const float* g_ent;
+    float* grad_logit;  // (M, N)
+    float* grad_value;  // (T+1, B)
+};
+
+// rows: one thread per (t,b) row; STAGED: NT consecutive rows of both logit tensors go through shared memory
+template <int NT, bool STAGED>
+__global__ void __launch_bounds__(NT) vtrace_rows_kernel(VtArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int N = a.N;
+    const long long M = a.T * a.B;
+    const long long row0 = (long long)blockIdx.x * NT;
+    const long long row = row0 + threadIdx.x;
+    const float *zt, *zb;
+    if (STAGED) {
+        const int nflt = (int)min((long long)NT, M - row0) * N;
+        stage_rows<NT>(smem, a.target + row0 * N, nflt, true);
+        stage_rows<NT>(smem + NT * N, a.behaviour + row0 * N, nflt, true);
+        __syncthreads();
+        zt = smem + threadIdx.x * N;
+        zb = smem + NT * N + threadIdx.x * N;
+    } else {
+        zt = a.target + row * N;
+        zb = a.behaviour + row * N;
+    }
+    if (row >= M) return;
+    const int act = (int)a.action[row];
+    float lse_t, ent;
+    row_lse_entropy<1>([&](int j) { return zt[j]; }, N, 0, lse_t, ent);
+    const float lse_b = row_lse<1>([&](int j) { return zb[j]; }, N, 0);
+    const float lp_t = zt[act] - lse_t;
+    const float lp_b = zb[act] - lse_b;
+    a.lp_t[row] = lp_t;
+    a.isw[row] = expf(lp_t - lp_b);
+    a.ent[row] = ent;
+}
+
+// large-N variant: warp per row
+template <int NT>
+__global__ void __launch_bounds__(NT) vtrace_rows_warp_kernel(VtArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    if (row >= a.T * a.B) return;
+    const float* zt = a.target + row * a.N;
+    const float* zb = a.behaviour + row * a.N;
+    const int act = (int)a.action[row];
+    float lse_t, ent;
+    row_lse_entropy<32>([&](int j) { return zt[j]; }, a.N, lane, lse_t, ent);
+    const float lse_b = row_lse<32>([&](int j) { return zb[j]; }, a.N, lane);
+    if (lane == 0) {
+        const float lp_t = zt[act] - lse_t;
+        a.lp_t[row] = lp_t;
+        a.isw[row] = expf(lp_t - (zb[act] - lse_b));
+        a.ent[row] = ent;
+    }
+}
+
+// column-tile scan: x_t = delta_t + (gl*c_t)*x_{t+1}; vs_t = V_t + x_t  (vtrace.py:22-29), then
+// adv_t = rho_pg*(r_t + g*vs_{t+1} - V_t) with vs_T = V_T (vtrace.py:126-128) and the three loss sums (:130-135).
+template <int TC, int NT, int CHUNK>
+__global__ void __launch_bounds__(NT) vtrace_scan_kernel(VtArgs a, float* ws) {
+    __shared__ float s_d[CHUNK][TC];   // delta, then x
+    __shared__ float s_f[CHUNK][TC];   // gl*c
+    __shared__ float s_vs[CHUNK + 1][TC];
+    const long long c0 = (long long)blockIdx.x * TC;
+    const long long T = a.T, B = a.B;
+    const float inv_m = 1.f / (float)(T * B);
+    float carry = 0.f;
+    float acc[3] = {0.f, 0.f, 0.f};
+    // scan lanes keep vs of the row just above the current slab in a register: V_T for the first slab (vtrace.py:127)
+    float above = 0.f;
+    if (threadIdx.x < TC && c0 + threadIdx.x < B) above = a.value[T * B + c0 + threadIdx.x];
+    for (long long hi = T; hi > 0; hi -= CHUNK) {
+        const long long lo = hi > CHUNK ? hi - CHUNK : 0;
+        const int rows = (int)(hi - lo);
+        for (int i = threadIdx.x; i < rows * TC; i += NT) {
+            const int r = i / TC, cc = i % TC;
+            const long long c = c0 + cc;
+            if (c < B) {
+                const long long off = (lo + r) * B + c;
+                const float is = a.isw[off];
+                const float rho = fminf(is, a.rho_clip), cs = fminf(is, a.c_clip);
+                const float v = a.value[off], vn = a.value[off + B];
+                s_d[r][cc] = fmul(rho, fsub(fadd(a.reward[off], fmul(a.gamma, vn)), v));
+                s_f[r][cc] = fmul(a.gamma_lambda, cs);
+                s_vs[r][cc] = v;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < TC && c0 + threadIdx.x < B) {
+            const int cc = threadIdx.x;
+            s_vs[rows][cc] = above;
+            float vs = above;
+            for (int r = rows - 1; r >= 0; --r) {
+                carry = fadd(s_d[r][cc], fmul(s_f[r][cc], carry));
+                vs = fadd(s_vs[r][cc], carry);  // result[t] += item
+                s_vs[r][cc] = vs;
+            }
+            above = vs;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * TC; i += NT) {
+            const int r = i / TC, cc = i % TC;
+            const long long c = c0 + cc;
+            if (c < B) {
+                const long long off = (lo + r) * B + c;
+                const float w = a.weight ? a.weight[off] : 1.f;
+                const float v = a.value[off];
+                const float vs = s_vs[r][cc], vs_next = s_vs[r + 1][cc];
+                const float rho_pg = fminf(a.isw[off], a.rho_pg_clip);
+                const float adv = fmul(rho_pg, fsub(fadd(a.reward[off], fmul(a.gamma, vs_next)), v));
+                const float dv = v - vs;
+                acc[0] += a.lp_t[off] * adv * w;
+                acc[1] += dv * dv * w;
+                acc[2] += a.ent[off] * w;
+                a.isw[off] = adv * w;               // coefficient of the policy-gradient term
+                a.ent[off] = 2.f * w * dv * inv_m;  // d value_loss / d V_t
+            }
+        }
+        __syncthreads();
+    }
+    double tot[3];
+    if (grid_sum<3, NT>(acc, tot, ws, 0) && threadIdx.x == 0) {
+        const double m = (double)T * (double)B;
+        a.out[0] = (float)(-tot[0] / m);
+        a.out[1] = (float)(tot[1] / m);
+        a.out[2] = (float)(tot[2] / m);
+    }
+}
+
+// backward: grad z_j = g_pg*(-adv*w/M)*(1[j==a]-p_j) + g_ent*(w/M)*(-p_j*(logp_j+H)); grad V_t = g_val*dV, grad V_T = 0
+template <int NT, int MODE>  // 0 staged thread/row, 1 direct thread/row, 2 warp/row
+__global__ void __launch_bounds__(NT) vtrace_bwd_kernel(VtArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int L = (MODE == 2) ? 32 : 1;
+    const int lane = (MODE == 2) ? (threadIdx.x & 31) : 0;
+    const int N = a.N;
+    const long long M = a.T * a.B;
+    const float g_pg = a.g_pg ? *a.g_pg : 0.f, g_val = a.g_val ? *a.g_val : 0.f, g_ent = a.g_ent ? *a.g_ent : 0.f;
+    const float inv_m = 1.f / (float)M;
+    long long row0 = 0, row;
+    int nflt = 0;
+    const float* z;
+    float* gz;
+    if (MODE == 0) {
+        row0 = (long long)blockIdx.x * NT;
+        nflt = (int)min((long long)NT, M - row0) * N;
+        stage_rows<NT>(smem, a.target + row0 * N, nflt, true);
+        __syncthreads();
+        row = row0 + threadIdx.x;
+        z = smem + threadIdx.x * N;
+        gz = smem + threadIdx.x * N;
+    } else {
+        row = (MODE == 2) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
+                          : (long long)blockIdx.x * NT + threadIdx.x;
+        z = a.target + row * N;
+        gz = a.grad_logit + row * N;
+    }
+    if (row < M) {
+        const float w = a.weight ? a.weight[row] : 1.f;
+        const int act = (int)a.action[row];
+        float lse, ent;
+        row_lse_entropy<L>([&](int j) { return z[j]; }, N, lane, lse, ent);
+        const float c_act = g_pg * (-a.isw[row]) * inv_m;  // isw now holds adv*w
+        const float c_ent = g_ent * w * inv_m;
+        for (int j = lane; j < N; j += L) {
+            const float lp = z[j] - lse;
+            const float p = expf(lp);
+            float gj = -c_act * p - c_ent * p * (lp + ent);
+            if (j == act) gj += c_act;
+            gz[j] = gj;
+        }
+        if (lane == 0) a.grad_value[row] = g_val * a.ent[row];  // ent now holds dV
+    }
+    // zero gradient for the bootstrap row V_T
+    {
+        const long long i = (long long)blockIdx.x * NT + threadIdx.x;  // gridDim.x * NT >= M >= B in every mode
+        if (i < a.B) a.grad_value[M + i] = 0.f;
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        float4* out4 = reinterpret_cast<float4*>(a.grad_logit + row0 * N);
+        const int nv4 = nflt >> 2;
+        for (int i = threadIdx.x; i < nv4; i += NT) stg_stream4(out4 + i, reinterpret_cast<const float4*>(smem)[i]);
+        for (int i = (nv4 << 2) + threadIdx.x; i < nflt; i += NT) a.grad_logit[row0 * N + i] = smem[i];
+    }
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" int b200rl_upgo_head_fwd(const float* logit, const long long* action, const float* mask, const float* rho,
+                                    const float* ret, const float* value, long long TB, long long K, long long N,
+                                    float* loss, float* adv_saved, float* workspace, size_t workspace_bytes,
+                                    void* stream) {
+    if (TB <= 0 || K < 1 || N < 1 || !logit || !action || !rho || !ret || !value || !loss || !adv_saved || !workspace)
+        return B200RL_ERR_ARG;
+    UpgoArgs a{};
+    a.logit = logit; a.action = action; a.mask = mask; a.rho = rho; a.ret = ret; a.value = value; a.TB = TB;
+    a.K = (int)K; a.N = (int)N; a.loss = loss; a.adv_saved = adv_saved;
+    constexpr int NT = 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 64) {
+        const int grid = div_up(TB, NT / 32);
+        if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+        upgo_fwd_kernel<NT, 32><<<grid, NT, 0, st>>>(a, workspace);
+    } else {
+        const int grid = div_up(TB, NT);
+        if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+        upgo_fwd_kernel<NT, 1><<<grid, NT, 0, st>>>(a, workspace);
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_upgo_head_bwd(const float* logit, const long long* action, const float* mask,
+                                    const float* adv_saved, const float* g_loss, long long TB, long long K,
+                                    long long N, float* grad_logit, void* stream) {
+    if (TB <= 0 || K < 1 || N < 1 || !logit || !action || !adv_saved || !grad_logit) return B200RL_ERR_ARG;
+    UpgoArgs a{};
+    a.logit = logit; a.action = action; a.mask = mask; a.adv_saved = const_cast<float*>(adv_saved); a.TB = TB;
+    a.K = (int)K; a.N = (int)N; a.g_loss = g_loss; a.grad_logit = grad_logit;
+    constexpr int NT = 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 64) upgo_bwd_kernel<NT, 32><<<div_up(TB * K, NT / 32), NT, 0, st>>>(a);
+    else upgo_bwd_kernel<NT, 1><<<div_up(TB * K, NT), NT, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+static int vt_mode(const VtArgs& a) {
+    const bool al = aligned16(a.target) && aligned16(a.behaviour) && (!a.grad_logit || aligned16(a.grad_logit));
+    if (a.N <= 32 && al) return 0;
+    if (a.N <= 64) return 1;
+    return 2;
+}
+
+extern "C" int b200rl_vtrace_fwd(const float* target_output, const float* behaviour_output, const long long* action,
+                                 const float* value, const float* reward, const float* weight, long long T,
+                                 long long B, long long N, double gamma, double lambda_, double rho_clip_ratio,
+                                 double c_clip_ratio, double rho_pg_clip_ratio, float* out3, float* lp_saved,
+                                 float* cpg_saved, float* dv_saved, float* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    if (T <= 0 || B <= 0 || N < 1 || !target_output || !behaviour_output || !action || !value || !reward || !out3 ||
+        !lp_saved || !cpg_saved || !dv_saved || !workspace)
+        return B200RL_ERR_ARG;
+    VtArgs a{};
+    a.target = target_output; a.behaviour = behaviour_output; a.action = action; a.value = value; a.reward = reward;
+    a.weight = weight; a.T = T; a.B = B; a.N = (int)N; a.gamma = (float)gamma;
+    a.gamma_lambda = (float)(gamma * lambda_);  // `factor = gamma * lambda_` in python double, vtrace.py:23
+    a.rho_clip = (float)rho_clip_ratio; a.c_clip = (float)c_clip_ratio; a.rho_pg_clip = (float)rho_pg_clip_ratio;
+    a.lp_t = lp_saved; a.isw = cpg_saved; a.ent = dv_saved; a.out = out3;
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int NT = 128;
+    const long long M = T * B;
+    const int mode = vt_mode(a);
+    if (mode == 0) {
+        vtrace_rows_kernel<NT, true><<<div_up(M, NT), NT, (size_t)2 * NT * a.N * sizeof(float), st>>>(a);
+    } else if (mode == 1) {
+        vtrace_rows_kernel<NT, false><<<div_up(M, NT), NT, 0, st>>>(a);
+    } else {
+        vtrace_rows_warp_kernel<NT><<<div_up(M, NT / 32), NT, 0, st>>>(a);
+    }
+    int rc = (int)cudaGetLastError();
+    if (rc) return rc;
+    if (B >= 16 * 296) {
+        if ((size_t)(WS_CTRL_WORDS + 3 * div_up(B, 16)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+        vtrace_scan_kernel<16, 128, 64><<<div_up(B, 16), 128, 0, st>>>(a, workspace);
+    } else {
+        if ((size_t)(WS_CTRL_WORDS + 3 * div_up(B, 8)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+        vtrace_scan_kernel<8, 64, 64><<<div_up(B, 8), 64, 0, st>>>(a, workspace);
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_vtrace_bwd(const float* target_output, const long long* action, const float* weight,
+                                 const float* cpg_saved, const float* dv_saved, const float* g_policy,
+                                 const float* g_value, const float* g_entropy, long long T, long long B, long long N,
+                                 float* grad_target_output, float* grad_value, void* stream) {
+    if (T <= 0 || B <= 0 || N < 1 || !target_output || !action || !cpg_saved || !dv_saved || !grad_target_output ||
+        !grad_value)
+        return B200RL_ERR_ARG;
+    VtArgs a{};
+    a.target = target_output; a.behaviour = target_output; a.action = action; a.weight = weight; a.T = T; a.B = B;
+    a.N = (int)N; a.isw = const_cast<float*>(cpg_saved); a.ent = const_cast<float*>(dv_saved);
+    a.g_pg = g_policy; a.g_val = g_value; a.g_ent = g_entropy; a.grad_logit = grad_target_output;
+    a.grad_value = grad_value;
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int NT = 128;
+    const long long M = T * B;
+    const int mode = vt_mode(a);
+    if (mode == 0) vtrace_bwd_kernel<NT, 0><<<div_up(M, NT), NT, (size_t)NT * a.N * sizeof(float), st>>>(a);
+    else if (mode == 1) vtrace_bwd_kernel<NT, 1><<<div_up(M, NT), NT, 0, st>>>(a);
+    else vtrace_bwd_kernel<NT, 2><<<div_up(M, NT / 32), NT, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,440 @@
+// n-step TD heads of ding/rl_utils/td.py:
+//   q_nstep_td_error (:649-719) / q_nstep_td_error_with_rescale (:810-867)  -> qntd_fwd / qntd_bwd
+//   dist_nstep_td_error (C51 projection, :413-523)                           -> dntd_fwd / dntd_bwd
+//   generalized_lambda_returns / multistep_forward_view (:1574-1651), td_lambda_error (:1539-1571) and the
+//   UPGO return (upgo.py:46-68)                                              -> lambda_returns (+ fused TD(lambda) head)
+// Each reference call is ~20-35 tiny torch launches plus an autograd backward; here it is one forward and one
+// backward launch.  These batches are small (B ~ 32..512): latency, not bandwidth, is what the kernels minimise.
+#include <math.h>
+
+#include "../../include/b200rl.h"
+#include "common.cuh"
+
+namespace b200rl {
+
+// ---------------------------------------------------------------------------------------------------------------
+// value rescaling h / h^-1 (value_rescale.py:4-34), evaluated in the reference's operation order
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+__device__ __forceinline__ float value_h(float x, float eps) {
+    return fadd(fmul(sgn(x), fsub(__fsqrt_rn(fadd(fabsf(x), 1.f)), 1.f)), fmul(eps, x));
+}
+__device__ __forceinline__ float value_h_inv(float x, float eps, float four_eps, float two_eps) {
+    float t = fadd(fadd(fabsf(x), 1.f), eps);
+    float u = __fdiv_rn(fsub(__fsqrt_rn(fadd(1.f, fmul(four_eps, t))), 1.f), two_eps);
+    return fmul(sgn(x), fsub(fmul(u, u), 1.f));
+}
+
+// elementwise criteria (reduction='none'): value and d/d(input)
+__device__ __forceinline__ float criterion_eval(int kind, float param, float x, float y, float& dx) {
+    const float d = x - y, ad = fabsf(d);
+    switch (kind) {
+        case 0: dx = 2.f * d; return d * d;                                        // nn.MSELoss
+        case 1: dx = sgn(d); return ad;                                            // nn.L1Loss
+        case 2:                                                                    // nn.SmoothL1Loss(beta)
+            if (ad < param) { dx = d / param; return 0.5f * d * d / param; }
+            dx = sgn(d); return ad - 0.5f * param;
+        default:                                                                   // nn.HuberLoss(delta)
+            if (ad <= param) { dx = d; return 0.5f * d * d; }
+            dx = param * sgn(d); return param * (ad - 0.5f * param);
+    }
+}
+
+struct QntdArgs {
+    const float* q;
+    const float* next_q;
+    const long long* action;
+    const long long* next_action;
+    const float* reward;       // (nstep, B) or (B) when cum_reward
+    const float* done;         // (B)
+    const float* weight;       // (B) or null
+    const float* value_gamma;  // null, or pointer with stride 0 (0-dim) / 1 (B)
+    long long value_gamma_stride;
+    const float* gamma_ps;     // NGU per-sample gamma (B) or null
+    long long B;
+    int N;
+    int nstep;
+    float gamma;
+    float gamma_pow_n;
+    int cum_reward;
+    int rescale;
+    float eps, four_eps, two_eps;
+    int criterion;
+    float crit_param;
+    float* loss;
+    float* td_err;
+    float* dq;  // saved d(loss)/d(q_sa) for unit upstream gradient
+    float* target;  // nullable: the (detached) n-step target, for callers that apply their own criterion
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) qntd_fwd_kernel(QntdArgs a, float* ws) {
+    const long long b = (long long)blockIdx.x * NT + threadIdx.x;
+    float acc[1] = {0.f};
+    if (b < a.B) {
+        const float q_sa = a.q[b * a.N + a.action[b]];
+        float tq = a.next_q[b * a.N + a.next_action[b]];
+        if (a.rescale) tq = value_h_inv(tq, a.eps, a.four_eps, a.two_eps);
+        const float nd = fsub(1.f, a.done[b]);
+        float target;
+        if (a.cum_reward) {
+            const float vg = a.value_gamma ? a.value_gamma[b * a.value_gamma_stride] : a.gamma_pow_n;
+            target = fadd(a.reward[b], fmul(fmul(vg, tq), nd));  // td.py:712-715
+        } else {
+            const float g = a.gamma_ps ? a.gamma_ps[b] : a.gamma;
+            float rf = 1.f, ret = 0.f;
+            for (int i = 0; i < a.nstep; ++i) {  // td.py:261-264 / :277-281
+                ret = fadd(ret, fmul(a.reward[(long long)i * a.B + b], rf));
+                rf = fmul(g, rf);
+            }
+            float vg;
+            if (a.gamma_ps) vg = rf;  // reward_factor[nstep]
+            else vg = a.value_gamma ? a.value_gamma[b * a.value_gamma_stride] : a.gamma_pow_n;
+            target = fadd(ret, fmul(fmul(vg, tq), nd));  // td.py:266 / :273 / :282
+        }
+        if (a.rescale) target = value_h(target, a.eps);
+        float dx;
+        const float td = criterion_eval(a.criterion, a.crit_param, q_sa, target, dx);
+        const float w = a.weight ? a.weight[b] : 1.f;
+        a.td_err[b] = td;
+        if (a.target) a.target[b] = target;
+        a.dq[b] = w * dx / (float)a.B;
+        acc[0] = td * w;
+    }
+    double tot[1];
+    if (grid_sum<1, NT>(acc, tot, ws, 0) && threadIdx.x == 0) a.loss[0] = (float)(tot[0] / (double)a.B);
+}
+
+__global__ void qntd_bwd_kernel(const float* __restrict__ dq, const long long* __restrict__ action,
+                                const float* __restrict__ g_loss, long long B, int N, float* __restrict__ grad_q) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * N) return;
+    const long long b = i / N;
+    const int j = (int)(i - b * N);
+    const float g = g_loss ? *g_loss : 0.f;
+    grad_q[i] = (j == (int)action[b]) ? g * dq[b] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C51 categorical projection: one warp per (sample, agent) row, lanes stride the atoms, the projected distribution is
+// accumulated with shared-memory atomics (the index_add_ of td.py:510-511) and kept for the backward pass.
+// ---------------------------------------------------------------------------------------------------------------
+struct DntdArgs {
+    const float* dist;       // (R, N, n_atom)
+    const float* next_dist;  // (R, N, n_atom)
+    const long long* act;    // (R)
+    const long long* next_act;
+    const float* reward;  // (nstep, B)
+    const float* done;    // (B)
+    const float* weight;  // null, or stride 0 / 1 over R
+    long long weight_stride;
+    const float* value_gamma;  // null or stride 0 / 1 over B
+    long long value_gamma_stride;
+    const float* support;  // (n_atom), torch.linspace(v_min, v_max, n_atom) computed by the caller
+    long long R;
+    long long A;  // rows per batch entry (1 single agent)
+    long long B;
+    int N;
+    int n_atom;
+    int nstep;
+    float gamma;
+    float gamma_pow_n;
+    float v_min, v_max, delta_z;
+    float* loss;
+    float* td_err;  // (R)
+    float* proj;    // (R, n_atom)
+    int* bad_flag;  // set to 1 if any selected dist entry is <= 0 (td.py:513)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
+    extern __shared__ float s_proj[];  // [NT/32][n_atom]
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (NT / 32) + wid;
+    float* pj = s_proj + wid * a.n_atom;
+    float acc[1] = {0.f};
+    if (r < a.R) {
+        const long long b = r / a.A;
+        for (int j = lane; j < a.n_atom; j += 32) pj[j] = 0.f;
+        float rf = 1.f, ret = 0.f;
+        for (int i = 0; i < a.nstep; ++i) {  // matmul(reward_factor, reward), td.py:453-456
+            ret = fadd(ret, fmul(rf, a.reward[(long long)i * a.B + b]));
+            rf = fmul(a.gamma, rf);
+        }
+        const float vg = a.value_gamma ? a.value_gamma[b * a.value_gamma_stride] : a.gamma_pow_n;
+        const float scale = fmul(fsub(1.f, a.done[b]), vg);  // (1-done) * gamma**n, td.py:492-498
+        const float* nd = a.next_dist + (r * a.N + a.next_act[r]) * a.n_atom;
+        const float* dd = a.dist + (r * a.N + a.act[r]) * a.n_atom;
+        __syncwarp();
+        for (int j = lane; j < a.n_atom; j += 32) {
+            float tz = fadd(ret, fmul(scale, a.support[j]));
+            tz = fminf(fmaxf(tz, a.v_min), a.v_max);
+            const float pos = __fdiv_rn(fsub(tz, a.v_min), a.delta_z);  // td.py:500
+            float lo = floorf(pos), hi = ceilf(pos);
+            if (hi > 0.f && lo == hi) lo -= 1.f;                          // td.py:504
+            if (lo < (float)(a.n_atom - 1) && lo == hi) hi += 1.f;        // td.py:505
+            const float p = nd[j];
+            atomicAdd(&pj[(int)lo], fmul(p, fsub(hi, pos)));
+            atomicAdd(&pj[(int)hi], fmul(p, fsub(pos, lo)));
+        }
+        __syncwarp();
+        float td = 0.f;
+        bool bad = false;
+        for (int j = lane; j < a.n_atom; j += 32) {
+            const float d = dd[j], m = pj[j];
+            bad |= !(d > 0.f);
+            td += logf(d) * m;
+            a.proj[r * a.n_atom + j] = m;
+        }
+        td = -warp_sum(td);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.bad_flag, 1);
+        if (lane == 0) {
+            a.td_err[r] = td;
+            const float w = a.weight ? a.weight[r * a.weight_stride] : 1.f;
+            acc[0] = td * w;
+        }
+    }
+    double tot[1];
+    if (grid_sum<1, NT>(acc, tot, ws, 0) && threadIdx.x == 0) a.loss[0] = (float)(tot[0] / (double)a.R);
+}
+
+__global__ void dntd_bwd_kernel(const float* __restrict__ dist, const long long* __restrict__ act,
+                                const float* __restrict__ proj, const float* __restrict__ weight,
+                                long long weight_stride, const float* __restrict__ g_loss, long long R, int N,
+                                int n_atom, float* __restrict__ grad_dist) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_row = (long long)N * n_atom;
+    if (i >= R * per_row) return;
+    const long long r = i / per_row;
+    const int rem = (int)(i - r * per_row);
+    const int n = rem / n_atom, j = rem - n * n_atom;
+    float out = 0.f;
+    if (n == (int)act[r]) {
+        const float g = g_loss ? *g_loss : 0.f;
+        const float w = weight ? weight[r * weight_stride] : 1.f;
+        out = -g * w / (float)R * proj[r * n_atom + j] / dist[i];
+    }
+    grad_dist[i] = out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// lambda-return scan along T on a (T, B) tile -- same three-phase tile scheme as gae.cu.
+//   G_{T-1} = r + ((1-d)*gamma)*V_T ;  G_t = r_t + (1-d_t)*(disc_t*G_{t+1} + (gamma_t - disc_t)*V_{t+1}),  disc = gamma*lambda
+// MODE 0: gamma/lambda scalars or (T,B) tensors, optional done (generalized_lambda_returns, td.py:1574-1651)
+// MODE 1: UPGO: gamma = 1, lambda_t = [r_{t+1} + V_{t+2} >= V_{t+1}], last = 1 (upgo.py:66-68)
+// HEAD 1: fused TD(lambda) loss head: loss = 0.5*mean(w*(G - V_t)^2) and the saved gradient dV (td.py:1570)
+// ---------------------------------------------------------------------------------------------------------------
+struct LamArgs {
+    const float* value;   // (T+1, B)
+    const float* reward;  // (T, B)
+    const float* gammas;  // nullable (T, B)
+    const float* lambdas; // nullable (T, B)
+    const float* done;    // nullable (T, B)
+    const float* weight;  // HEAD: nullable (T, B)
+    float gamma, lambda;
+    long long T, B;
+    float* ret;     // (T, B) output (nullable when HEAD)
+    float* loss;    // HEAD
+    float* dvalue;  // HEAD: (T+1, B) saved d loss / d value for unit upstream gradient
+};
+
+template <int TC, int NT, int CHUNK, int MODE, int HEAD>
+__global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
+    __shared__ float s_r[CHUNK][TC];
+    __shared__ float s_m[CHUNK][TC];
+    __shared__ float s_disc[CHUNK][TC];
+    __shared__ float s_c[CHUNK][TC];
+    const long long c0 = (long long)blockIdx.x * TC;
+    const long long T = a.T, B = a.B;
+    float carry = 0.f;
+    float acc[1] = {0.f};
+    for (long long hi = T; hi > 0; hi -= CHUNK) {
+        const long long lo = hi > CHUNK ? hi - CHUNK : 0;
+        const int rows = (int)(hi - lo);
+        for (int i = threadIdx.x; i < rows * TC; i += NT) {
+            const int r = i / TC, cc = i % TC;
+            const long long c = c0 + cc, t = lo + r;
+            if (c < B) {
+                const long long off = t * B + c;
+                const float rw = a.reward[off];
+                const float vn = a.value[off + B];  // V_{t+1}
+                float g, l;
+                if (MODE == 1) {
+                    g = 1.f;
+                    l = 1.f;
+                    if (t < T - 1) l = (fadd(a.reward[off + B], a.value[off + 2 * B]) >= vn) ? 1.f : 0.f;
+                } else {
+                    g = a.gammas ? a.gammas[off] : a.gamma;
+                    l = a.lambdas ? a.lambdas[off] : a.lambda;
+                }
+                const float m = a.done ? fsub(1.f, a.done[off]) : 1.f;
+                const float disc = fmul(g, l);
+                s_r[r][cc] = rw;
+                s_m[r][cc] = m;
+                if (t == T - 1) {
+                    // closed form of the last row kept in s_c; disc = 0 so the carry (0) is ignored exactly
+                    s_disc[r][cc] = 0.f;
+                    s_c[r][cc] = fmul(fmul(m, g), vn);
+                    s_m[r][cc] = 1.f;
+                } else {
+                    s_disc[r][cc] = disc;
+                    s_c[r][cc] = fmul(fsub(g, disc), vn);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < TC && c0 + threadIdx.x < B) {
+            const int cc = threadIdx.x;
+            for (int r = rows - 1; r >= 0; --r) {
+                carry = fadd(s_r[r][cc], fmul(s_m[r][cc], fadd(fmul(s_disc[r][cc], carry), s_c[r][cc])));
+                s_r[r][cc] = carry;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * TC; i += NT) {
+            const int r = i / TC, cc = i % TC;
+            const long long c = c0 + cc;
+            if (c < B) {
+                const long long off = (lo + r) * B + c;
+                const float gret = s_r[r][cc];
+                if (a.ret) a.ret[off] = gret;
+                if (HEAD == 1) {
+                    const float w = a.weight ? a.weight[off] : 1.f;
+                    const float d = gret - a.value[off];
+                    acc[0] += w * d * d;
+                    a.dvalue[off] = -w * d / (float)(T * B);  // 0.5 * w * 2 * (V - G) / count
+                }
+            }
+        }
+        if (lo > 0) __syncthreads();
+    }
+    if (HEAD == 1) {
+        // last value row receives no gradient (value[:-1], td.py:1570)
+        for (int cc = threadIdx.x; cc < TC; cc += NT)
+            if (c0 + cc < B) a.dvalue[T * B + c0 + cc] = 0.f;
+        double tot[1];
+        if (grid_sum<1, NT>(acc, tot, ws, 0) && threadIdx.x == 0)
+            a.loss[0] = (float)(0.5 * tot[0] / ((double)T * (double)B));
+    }
+}
+
+// out[i] = (*g) * in[i]  -- backward of the heads that saved their unit-upstream gradient in the forward pass
+__global__ void scale_kernel(const float* __restrict__ g, const float* __restrict__ in, float* __restrict__ out,
+                             long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (*g) * in[i];
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" int b200rl_qntd_fwd(const float* q, const float* next_n_q, const long long* action,
+                               const long long* next_n_action, const float* reward, const float* done,
+                               const float* weight, const float* value_gamma, long long value_gamma_stride,
+                               const float* gamma_per_sample, long long B, long long N, int nstep, double gamma,
+                               int cum_reward, int rescale, double rescale_eps, int criterion, double criterion_param,
+                               float* loss, float* td_error_per_sample, float* dq_saved, float* target_out,
+                               float* workspace, size_t workspace_bytes, void* stream) {
+    if (B <= 0 || N < 1 || nstep < 1 || !q || !next_n_q || !action || !next_n_action || !reward || !done || !loss ||
+        !td_error_per_sample || !dq_saved || !workspace)
+        return B200RL_ERR_ARG;
+    if (criterion < 0 || criterion > 3) return B200RL_ERR_ARG;
+    QntdArgs a{};
+    a.q = q; a.next_q = next_n_q; a.action = action; a.next_action = next_n_action; a.reward = reward; a.done = done;
+    a.weight = weight; a.value_gamma = value_gamma; a.value_gamma_stride = value_gamma_stride;
+    a.gamma_ps = gamma_per_sample; a.B = B; a.N = (int)N; a.nstep = nstep; a.gamma = (float)gamma;
+    a.gamma_pow_n = (float)pow(gamma, (double)nstep);  // python's `gamma ** nstep` (libm pow in double), then fp32
+    a.cum_reward = cum_reward; a.rescale = rescale; a.eps = (float)rescale_eps;
+    a.four_eps = (float)(4.0 * rescale_eps); a.two_eps = (float)(2.0 * rescale_eps);
+    a.criterion = criterion; a.crit_param = (float)criterion_param;
+    a.loss = loss; a.td_err = td_error_per_sample; a.dq = dq_saved; a.target = target_out;
+    constexpr int NT = 128;
+    const int grid = div_up(B, NT);
+    if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+    qntd_fwd_kernel<NT><<<grid, NT, 0, (cudaStream_t)stream>>>(a, workspace);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_qntd_bwd(const float* dq_saved, const long long* action, const float* g_loss, long long B,
+                               long long N, float* grad_q, void* stream) {
+    if (B <= 0 || N < 1 || !dq_saved || !action || !grad_q) return B200RL_ERR_ARG;
+    const int grid = div_up(B * N, 256);
+    qntd_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dq_saved, action, g_loss, B, (int)N, grad_q);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, const long long* act,
+                               const long long* next_n_act, const float* reward, const float* done,
+                               const float* weight, long long weight_stride, const float* value_gamma,
+                               long long value_gamma_stride, const float* support, long long B, long long A,
+                               long long N, int n_atom, int nstep, double gamma, double v_min, double v_max,
+                               float* loss, float* td_error_per_sample, float* proj_saved, int* bad_flag,
+                               float* workspace, size_t workspace_bytes, void* stream) {
+    if (B <= 0 || A < 1 || N < 1 || n_atom < 2 || nstep < 1 || !dist || !next_n_dist || !act || !next_n_act ||
+        !reward || !done || !support || !loss || !td_error_per_sample || !proj_saved || !bad_flag || !workspace)
+        return B200RL_ERR_ARG;
+    DntdArgs a{};
+    a.dist = dist; a.next_dist = next_n_dist; a.act = act; a.next_act = next_n_act; a.reward = reward; a.done = done;
+    a.weight = weight; a.weight_stride = weight_stride; a.value_gamma = value_gamma;
+    a.value_gamma_stride = value_gamma_stride; a.support = support; a.R = B * A; a.A = A; a.B = B; a.N = (int)N;
+    a.n_atom = n_atom; a.nstep = nstep; a.gamma = (float)gamma; a.gamma_pow_n = (float)pow(gamma, (double)nstep);
+    a.v_min = (float)v_min; a.v_max = (float)v_max; a.delta_z = (float)((v_max - v_min) / (double)(n_atom - 1));
+    a.loss = loss; a.td_err = td_error_per_sample; a.proj = proj_saved; a.bad_flag = bad_flag;
+    constexpr int NT = 128;
+    const int grid = div_up(a.R, NT / 32);
+    if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+    const size_t sm = (size_t)(NT / 32) * n_atom * sizeof(float);
+    if (sm > 48 * 1024) return B200RL_ERR_ARG;
+    dntd_fwd_kernel<NT><<<grid, NT, sm, (cudaStream_t)stream>>>(a, workspace);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_dntd_bwd(const float* dist, const long long* act, const float* proj_saved, const float* weight,
+                               long long weight_stride, const float* g_loss, long long R, long long N, int n_atom,
+                               float* grad_dist, void* stream) {
+    if (R <= 0 || N < 1 || n_atom < 2 || !dist || !act || !proj_saved || !grad_dist) return B200RL_ERR_ARG;
+    const int grid = div_up(R * N * n_atom, 256);
+    dntd_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dist, act, proj_saved, weight, weight_stride, g_loss, R,
+                                                            (int)N, n_atom, grad_dist);
+    return (int)cudaGetLastError();
+}
+
+template <int MODE, int HEAD>
+static int launch_lambda(const LamArgs& a, float* ws, cudaStream_t st) {
+    if (a.B >= 16 * 296) {
+        lambda_scan_kernel<16, 128, 64, MODE, HEAD><<<div_up(a.B, 16), 128, 0, st>>>(a, ws);
+    } else {
+        lambda_scan_kernel<8, 64, 128, MODE, HEAD><<<div_up(a.B, 8), 64, 0, st>>>(a, ws);
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_lambda_returns(const float* value, const float* reward, const float* gammas, double gamma,
+                                     const float* lambdas, double lambda_, const float* done, int upgo_mode,
+                                     long long T, long long B, float* ret, void* stream) {
+    if (T <= 0 || B <= 0 || !value || !reward || !ret) return B200RL_ERR_ARG;
+    LamArgs a{};
+    a.value = value; a.reward = reward; a.gammas = gammas; a.lambdas = lambdas; a.done = done;
+    a.gamma = (float)gamma; a.lambda = (float)lambda_; a.T = T; a.B = B; a.ret = ret;
+    return upgo_mode ? launch_lambda<1, 0>(a, nullptr, (cudaStream_t)stream)
+                     : launch_lambda<0, 0>(a, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b200rl_td_lambda_fwd(const float* value, const float* reward, const float* weight, double gamma,
+                                    double lambda_, long long T, long long B, float* loss, float* dvalue_saved,
+                                    float* workspace, size_t workspace_bytes, void* stream) {
+    if (T <= 0 || B <= 0 || !value || !reward || !loss || !dvalue_saved || !workspace) return B200RL_ERR_ARG;
+    LamArgs a{};
+    a.value = value; a.reward = reward; a.weight = weight; a.gamma = (float)gamma; a.lambda = (float)lambda_;
+    a.T = T; a.B = B; a.loss = loss; a.dvalue = dvalue_saved;
+    if ((size_t)(WS_CTRL_WORDS + div_up(B, 8)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+    return launch_lambda<0, 1>(a, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int b200rl_scale(const float* g, const float* in, float* out, long long n, void* stream) {
+    if (n < 0 || !g || (n > 0 && (!in || !out))) return B200RL_ERR_ARG;
+    if (n == 0) return B200RL_OK;
+    scale_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(g, in, out, n);
+    return (int)cudaGetLastError();
+}

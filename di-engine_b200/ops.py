@@ -1,0 +1,375 @@
+"""Tensor-level operators over the C ABI (``include/b200rl.h``): allocation of outputs, stream / workspace plumbing and
+``torch.autograd.Function`` wrappers.  torch is used for device memory, streams and autograd bookkeeping only; every
+arithmetic step of the hot path runs in the CUDA kernels of ``csrc/``.
+
+Nothing here computes on the CPU.  Host (CPU) tensors are accepted by the public API in ``rl_utils`` by staging them
+to the current CUDA device and returning results on the host -- the "host buffers" end-to-end path.
+"""
+import torch
+
+from . import _lib
+
+_WS = {}
+_CONST = {}
+
+
+def lib():
+    return _lib.load()
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.B200RLError(
+            "di_engine_b200 needs a CUDA device (sm_100a). There is no CPU implementation of the operators; "
+            "the CPU oracle under oracle/ is test infrastructure only."
+        )
+    lib()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def workspace(device):
+    """One zero-initialised scratch buffer per (device, stream): launches sharing it are stream-ordered."""
+    idx = device.index
+    if idx is None:
+        idx = torch.cuda.current_device() if device.type == 'cuda' else -1
+    key = (idx, stream_ptr())
+    ws = _WS.get(key)
+    if ws is None:
+        nbytes = lib().b200rl_workspace_bytes()
+        ws = torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def f32c(t, name='tensor'):
+    """fp32, contiguous; integer / bool flags (done, traj_flag, masks) are widened like the reference's ``.float()``."""
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        if t.dtype in (torch.float64, torch.float16, torch.bfloat16):
+            raise TypeError("di_engine_b200: %s must be float32 (got %s); the B200 path computes in fp32" %
+                            (name, t.dtype))
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def i64c(t):
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def to_device(t, device):
+    if isinstance(t, torch.Tensor) and t.device != device:
+        return t.to(device, non_blocking=True)
+    return t
+
+
+def compute_device(*tensors):
+    """Device the op runs on: the device of the first CUDA tensor, else the current CUDA device (host-buffer path)."""
+    require_cuda()
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def const_scalar(value, device):
+    """A cached 1-element device tensor holding a python scalar (weights / value_gamma given as floats)."""
+    key = (float(value), device.index)
+    t = _CONST.get(key)
+    if t is None:
+        t = torch.full((1, ), float(value), dtype=torch.float32, device=device)
+        _CONST[key] = t
+    return t
+
+
+def _g(grad):
+    """Upstream gradient of a 0-dim loss as a device pointer (None -> the kernel treats it as 0)."""
+    if grad is None:
+        return None, None
+    g = grad if grad.dtype == torch.float32 else grad.float()
+    return g, g.data_ptr()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# gae
+# ----------------------------------------------------------------------------------------------------------------
+def gae_(value, next_value, reward, done, traj_flag, gamma, lambda_, agents, mask_inplace=True):
+    """value/next_value (T, C) contiguous fp32 CUDA; reward/done/traj (T, C/agents). next_value is masked in place."""
+    T = value.shape[0]
+    C = value.numel() // T if T > 0 else 0
+    adv = torch.empty_like(value)
+    if value.numel() == 0:
+        return adv
+    with torch.cuda.device(value.device):
+        rc = lib().b200rl_gae(
+            ptr(value), ptr(next_value), ptr(reward), ptr(done), ptr(traj_flag), ptr(adv), T, C, agents, float(gamma),
+            float(lambda_), 1 if mask_inplace else 0, stream_ptr()
+        )
+    _lib.check(rc, 'b200rl_gae')
+    return adv
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# ppo
+# ----------------------------------------------------------------------------------------------------------------
+class PPOFunction(torch.autograd.Function):
+    """Outputs: policy_loss, value_loss, entropy_loss, kl_div (differentiable 0-dim) and the raw 8-float result vector
+    (non differentiable; [4]=approx_kl, [5]=clipfrac)."""
+
+    @staticmethod
+    def forward(ctx, logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre, S, G, N,
+                clip_ratio, use_value_clip, dual_clip, kl_type):
+        out = torch.empty(8, dtype=torch.float32, device=logit_new.device)
+        with torch.cuda.device(logit_new.device):
+            ws = workspace(logit_new.device)
+            rc = lib().b200rl_ppo_fwd(
+                ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old), ptr(adv),
+                ptr(return_), ptr(weight), S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, ptr(out), ptr(ws),
+                ws.numel() * 4, stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_ppo_fwd')
+        ctx.save_for_backward(logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre)
+        ctx.cfg = (S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type)
+        ctx.mark_non_differentiable(out)
+        p, v, e, k = out[0], out[1], out[2], out[3]
+        return p, v, e, k, out
+
+    @staticmethod
+    def backward(ctx, g_p, g_v, g_e, g_k, _g_out):
+        logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre = ctx.saved_tensors
+        S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type = ctx.cfg
+        grad_logit = torch.empty_like(logit_new)
+        grad_value = torch.empty_like(value_new)
+        kp, pp = _g(g_p)
+        kv, pv = _g(g_v)
+        ke, pe = _g(g_e)
+        kk, pk = _g(g_k)
+        with torch.cuda.device(logit_new.device):
+            rc = lib().b200rl_ppo_bwd(
+                ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old), ptr(adv),
+                ptr(return_), ptr(weight), S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, pp, pv, pe, pk,
+                ptr(grad_logit), ptr(grad_value), stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_ppo_bwd')
+        return (grad_logit, grad_value) + (None, ) * 14
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# q n-step TD
+# ----------------------------------------------------------------------------------------------------------------
+class QNStepTDFunction(torch.autograd.Function):
+    """Outputs: loss (differentiable w.r.t. q), td_error_per_sample and the detached target (non differentiable)."""
+
+    @staticmethod
+    def forward(ctx, q, next_n_q, action, next_n_action, reward, done, weight, value_gamma, vg_stride, gamma_ps, nstep,
+                gamma, cum_reward, rescale, eps, criterion, crit_param):
+        B, N = q.shape
+        dev = q.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        td = torch.empty(B, dtype=torch.float32, device=dev)
+        dq = torch.empty(B, dtype=torch.float32, device=dev)
+        target = torch.empty(B, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = workspace(dev)
+            rc = lib().b200rl_qntd_fwd(
+                ptr(q), ptr(next_n_q), ptr(action), ptr(next_n_action), ptr(reward), ptr(done), ptr(weight),
+                ptr(value_gamma), vg_stride, ptr(gamma_ps), B, N, nstep, gamma, cum_reward, rescale, eps, criterion,
+                crit_param, ptr(loss), ptr(td), ptr(dq), ptr(target), ptr(ws), ws.numel() * 4, stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_qntd_fwd')
+        ctx.save_for_backward(dq, action)
+        ctx.shape = (B, N)
+        ctx.mark_non_differentiable(td, target)
+        return loss, td, target
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_td, _g_target):
+        dq, action = ctx.saved_tensors
+        B, N = ctx.shape
+        grad_q = torch.empty(B, N, dtype=torch.float32, device=dq.device)
+        keep, pg = _g(g_loss)
+        with torch.cuda.device(dq.device):
+            rc = lib().b200rl_qntd_bwd(ptr(dq), ptr(action), pg, B, N, ptr(grad_q), stream_ptr())
+        _lib.check(rc, 'b200rl_qntd_bwd')
+        return (grad_q, ) + (None, ) * 16
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# distributional n-step TD (C51)
+# ----------------------------------------------------------------------------------------------------------------
+class DistNStepTDFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, dist, next_n_dist, act, next_n_act, reward, done, weight, w_stride, value_gamma, vg_stride,
+                support, B, A, N, n_atom, nstep, gamma, v_min, v_max, bad_flag):
+        dev = dist.device
+        R = B * A
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        td = torch.empty(R, dtype=torch.float32, device=dev)
+        proj = torch.empty(R, n_atom, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = workspace(dev)
+            rc = lib().b200rl_dntd_fwd(
+                ptr(dist), ptr(next_n_dist), ptr(act), ptr(next_n_act), ptr(reward), ptr(done), ptr(weight), w_stride,
+                ptr(value_gamma), vg_stride, ptr(support), B, A, N, n_atom, nstep, gamma, v_min, v_max, ptr(loss),
+                ptr(td), ptr(proj), ptr(bad_flag), ptr(ws), ws.numel() * 4, stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_dntd_fwd')
+        ctx.save_for_backward(dist, act, proj, weight)
+        ctx.cfg = (R, N, n_atom, w_stride)
+        ctx.mark_non_differentiable(td)
+        return loss, td
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_td):
+        dist, act, proj, weight = ctx.saved_tensors
+        R, N, n_atom, w_stride = ctx.cfg
+        grad = torch.empty_like(dist)
+        keep, pg = _g(g_loss)
+        with torch.cuda.device(dist.device):
+            rc = lib().b200rl_dntd_bwd(
+                ptr(dist), ptr(act), ptr(proj), ptr(weight), w_stride, pg, R, N, n_atom, ptr(grad), stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_dntd_bwd')
+        return (grad, ) + (None, ) * 19
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# lambda returns / TD(lambda)
+# ----------------------------------------------------------------------------------------------------------------
+def lambda_returns_(value, reward, gammas, gamma, lambdas, lambda_, done, upgo_mode):
+    T, B = reward.shape
+    ret = torch.empty_like(reward)
+    with torch.cuda.device(value.device):
+        rc = lib().b200rl_lambda_returns(
+            ptr(value), ptr(reward), ptr(gammas), float(gamma), ptr(lambdas), float(lambda_), ptr(done),
+            1 if upgo_mode else 0, T, B, ptr(ret), stream_ptr()
+        )
+    _lib.check(rc, 'b200rl_lambda_returns')
+    return ret
+
+
+class _ScaleSaved(torch.autograd.Function):
+    """loss whose gradient w.r.t. ``x`` was produced by the forward kernel for a unit upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, x, loss, saved_grad):
+        ctx.save_for_backward(saved_grad)
+        return loss.view_as(loss)
+
+    @staticmethod
+    def backward(ctx, g):
+        saved, = ctx.saved_tensors
+        out = torch.empty_like(saved)
+        keep, pg = _g(g)
+        with torch.cuda.device(saved.device):
+            rc = lib().b200rl_scale(pg, ptr(saved), ptr(out), saved.numel(), stream_ptr())
+        _lib.check(rc, 'b200rl_scale')
+        return out, None, None
+
+
+def td_lambda_(value, reward, weight, gamma, lambda_):
+    T, B = reward.shape
+    dev = value.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dvalue = torch.empty_like(value)
+    with torch.cuda.device(dev):
+        ws = workspace(dev)
+        rc = lib().b200rl_td_lambda_fwd(
+            ptr(value), ptr(reward), ptr(weight), float(gamma), float(lambda_), T, B, ptr(loss), ptr(dvalue), ptr(ws),
+            ws.numel() * 4, stream_ptr()
+        )
+    _lib.check(rc, 'b200rl_td_lambda_fwd')
+    if value.requires_grad and torch.is_grad_enabled():
+        return _ScaleSaved.apply(value, loss, dvalue)
+    return loss
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# UPGO head
+# ----------------------------------------------------------------------------------------------------------------
+class UPGOFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, logit, action, mask, rho, ret, value, TB, K, N):
+        dev = logit.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        adv = torch.empty(TB, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = workspace(dev)
+            rc = lib().b200rl_upgo_head_fwd(
+                ptr(logit), ptr(action), ptr(mask), ptr(rho), ptr(ret), ptr(value), TB, K, N, ptr(loss), ptr(adv),
+                ptr(ws), ws.numel() * 4, stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_upgo_head_fwd')
+        ctx.save_for_backward(logit, action, mask, adv)
+        ctx.cfg = (TB, K, N)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logit, action, mask, adv = ctx.saved_tensors
+        TB, K, N = ctx.cfg
+        grad = torch.empty_like(logit)
+        keep, pg = _g(g)
+        with torch.cuda.device(logit.device):
+            rc = lib().b200rl_upgo_head_bwd(
+                ptr(logit), ptr(action), ptr(mask), ptr(adv), pg, TB, K, N, ptr(grad), stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_upgo_head_bwd')
+        return (grad, ) + (None, ) * 8
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# V-trace
+# ----------------------------------------------------------------------------------------------------------------
+class VTraceFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, target_output, value, behaviour_output, action, reward, weight, gamma, lambda_, rho_clip, c_clip,
+                rho_pg_clip):
+        T, B = reward.shape
+        N = target_output.shape[-1]
+        dev = target_output.device
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        lp = torch.empty(T, B, dtype=torch.float32, device=dev)
+        cpg = torch.empty(T, B, dtype=torch.float32, device=dev)
+        dv = torch.empty(T, B, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = workspace(dev)
+            rc = lib().b200rl_vtrace_fwd(
+                ptr(target_output), ptr(behaviour_output), ptr(action), ptr(value), ptr(reward), ptr(weight), T, B, N,
+                gamma, lambda_, rho_clip, c_clip, rho_pg_clip, ptr(out), ptr(lp), ptr(cpg), ptr(dv), ptr(ws),
+                ws.numel() * 4, stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_vtrace_fwd')
+        ctx.save_for_backward(target_output, action, weight, cpg, dv)
+        ctx.cfg = (T, B, N)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_p, g_v, g_e):
+        target_output, action, weight, cpg, dv = ctx.saved_tensors
+        T, B, N = ctx.cfg
+        dev = target_output.device
+        grad_logit = torch.empty_like(target_output)
+        grad_value = torch.empty(T + 1, B, dtype=torch.float32, device=dev)
+        kp, pp = _g(g_p)
+        kv, pv = _g(g_v)
+        ke, pe = _g(g_e)
+        with torch.cuda.device(dev):
+            rc = lib().b200rl_vtrace_bwd(
+                ptr(target_output), ptr(action), ptr(weight), ptr(cpg), ptr(dv), pp, pv, pe, T, B, N, ptr(grad_logit),
+                ptr(grad_value), stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_vtrace_bwd')
+        return (grad_logit, grad_value) + (None, ) * 9

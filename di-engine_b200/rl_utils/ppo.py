@@ -1,0 +1,90 @@
+"""``ppo_error`` with the signature and namedtuples of ding/rl_utils/ppo.py:8-27,77-83 -- csrc/ppo.cu."""
+from collections import namedtuple
+from typing import Optional, Tuple
+
+import torch
+
+from .. import ops
+
+ppo_data = namedtuple(
+    'ppo_data',
+    ['logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv', 'return_', 'weight', 'logit_pretrained']
+)
+ppo_loss = namedtuple('ppo_loss', ['policy_loss', 'value_loss', 'entropy_loss', 'kl_div'])
+ppo_info = namedtuple('ppo_info', ['approx_kl', 'clipfrac'])
+
+_KL_TYPES = {'k1': 1, 'k2': 2, 'k3': 3}
+
+# When True ``ppo_info`` carries 0-dim device tensors instead of python floats, so a training step never blocks on
+# the host (the reference's two ``.item()`` calls, ppo.py:218-220, are the only host syncs of its PPO loss).
+LAZY_INFO = False
+
+
+def shape_fn_ppo(args, kwargs):
+    """Plugin-cache key of the reference boundary (ding/rl_utils/ppo.py:57-68): the shape of ``logit_new``."""
+    data = args[0] if len(args) > 0 else kwargs['data']
+    return data.logit_new.shape
+
+
+def ppo_error(
+        data: namedtuple,
+        clip_ratio: float = 0.2,
+        use_value_clip: bool = True,
+        dual_clip: Optional[float] = None,
+        kl_type: str = 'k1'
+) -> Tuple[namedtuple, namedtuple]:
+    """
+    PPO loss (clipped surrogate with optional dual clip, clipped value loss, entropy, optional KL to a pretrained
+    policy), drop-in for ding/rl_utils/ppo.py:77-140 (policy part :143-230, value part :233-275).
+
+    Shapes: logit_new / logit_old / logit_pretrained (..., N); action (...); value_new, value_old, adv, return_,
+    weight (...) -- or, multi-agent (ppo.py:199-200,:206-207), logits (B, A, N), action (B, A) with (B,) value/adv.
+    Returns ``(ppo_loss, ppo_info)``: four differentiable 0-dim tensors (gradients reach ``logit_new`` and
+    ``value_new``) and two python floats.
+    """
+    assert dual_clip is None or dual_clip > 1.0, "dual_clip value must be greater than 1.0, but get value: {}".format(
+        dual_clip
+    )
+    logit_new, logit_old, action, value_new, value_old, adv, return_, weight, logit_pretrained = data
+    if logit_pretrained is not None and kl_type not in _KL_TYPES:
+        raise ValueError(f"Unknown kl_type: {kl_type}")
+    dev = ops.compute_device(logit_new, value_new, logit_old)
+    host_out = not logit_new.is_cuda
+    N = logit_new.shape[-1]
+    rows = logit_new.numel() // N
+    S = adv.numel()
+    if S == 0 or rows % S != 0 or action.numel() != rows:
+        raise ValueError(
+            "ppo_error: logit %s / action %s / adv %s shapes do not match" %
+            (tuple(logit_new.shape), tuple(action.shape), tuple(adv.shape))
+        )
+    G = rows // S
+    if G > 1 and not (logit_new.dim() == adv.dim() + 2 and logit_new.shape[adv.dim()] == G):
+        raise ValueError("ppo_error: multi-agent logits must be (B, A, N) against (B,) adv")
+
+    def stage(t, name):
+        return ops.f32c(ops.to_device(t, dev), name) if t is not None else None
+
+    ln, lo, lp = stage(logit_new, 'logit_new'), stage(logit_old.detach(), 'logit_old'), None
+    if logit_pretrained is not None:
+        lp = stage(logit_pretrained.detach(), 'logit_pretrained')
+    vn = stage(value_new, 'value_new')
+    vo, ad, rt = stage(value_old.detach(), 'value_old'), stage(adv.detach(), 'adv'), stage(return_.detach(), 'return_')
+    w = None
+    if weight is not None:
+        w = stage(weight.detach(), 'weight')
+        if w.numel() != S:
+            w = w.expand_as(ad).contiguous()
+    act = ops.i64c(ops.to_device(action, dev))
+    p, v, e, k, out = ops.PPOFunction.apply(
+        ln, vn, lo, act, vo, ad, rt, w, lp, S, G, N, float(clip_ratio), 1 if use_value_clip else 0,
+        float(dual_clip) if dual_clip is not None else 0.0, _KL_TYPES.get(kl_type, 1)
+    )
+    if LAZY_INFO:
+        info = ppo_info(out[4], out[5])
+    else:
+        approx_kl, clipfrac = out[4:6].tolist()  # one D2H read for both monitors (reference: two .item() syncs)
+        info = ppo_info(approx_kl, clipfrac)
+    if host_out:
+        p, v, e, k = p.cpu(), v.cpu(), e.cpu(), k.cpu()
+    return ppo_loss(p, v, e, k), info

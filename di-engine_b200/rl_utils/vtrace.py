@@ -1,0 +1,59 @@
+"""``vtrace_error_discrete_action`` with the signature of ding/rl_utils/vtrace.py:48-49,72-79 -- csrc/pg.cu."""
+from collections import namedtuple
+
+import torch
+
+from .. import ops
+
+vtrace_data = namedtuple('vtrace_data', ['target_output', 'behaviour_output', 'action', 'value', 'reward', 'weight'])
+vtrace_loss = namedtuple('vtrace_loss', ['policy_loss', 'value_loss', 'entropy_loss'])
+
+
+def shape_fn_vtrace_discrete_action(args, kwargs):
+    """Plugin-cache key of the reference boundary (vtrace.py:52-63): the (T, B, N) shape of ``target_output``."""
+    data = args[0] if len(args) > 0 else kwargs['data']
+    return data.target_output.shape
+
+
+def vtrace_error_discrete_action(
+    data: namedtuple,
+    gamma: float = 0.99,
+    lambda_: float = 0.95,
+    rho_clip_ratio: float = 1.0,
+    c_clip_ratio: float = 1.0,
+    rho_pg_clip_ratio: float = 1.0
+):
+    """
+    V-trace actor-critic loss (IMPALA, arXiv:1802.01561), drop-in for ding/rl_utils/vtrace.py:72-136.
+    target_output, behaviour_output (T, B, N); action (T, B) int64; value (T+1, B); reward (T, B); weight None or
+    (T, B).  Returns ``vtrace_loss(policy_loss, value_loss, entropy_loss)``; gradients reach ``target_output`` and
+    ``value`` (row T of ``value`` gets zero, as value[:-1] in vtrace.py:134).
+    """
+    target_output, behaviour_output, action, value, reward, weight = data
+    dev = ops.compute_device(target_output, value)
+    host_out = not target_output.is_cuda
+    if target_output.dim() != 3 or value.dim() != 2 or reward.dim() != 2:
+        raise ValueError("expected target_output (T, B, N), value (T+1, B), reward (T, B)")
+    T, B, N = target_output.shape
+    if value.shape != (T + 1, B) or reward.shape != (T, B) or action.shape != (T, B) or \
+            behaviour_output.shape != target_output.shape:
+        raise ValueError("vtrace shapes do not match: target %s behaviour %s action %s value %s reward %s" % (
+            tuple(target_output.shape), tuple(behaviour_output.shape), tuple(action.shape), tuple(value.shape),
+            tuple(reward.shape)))
+    tgt = ops.f32c(ops.to_device(target_output, dev), 'target_output')
+    beh = ops.f32c(ops.to_device(behaviour_output.detach(), dev), 'behaviour_output')
+    act = ops.i64c(ops.to_device(action, dev))
+    v = ops.f32c(ops.to_device(value, dev), 'value')
+    r = ops.f32c(ops.to_device(reward.detach(), dev), 'reward')
+    w = None
+    if weight is not None:
+        w = ops.f32c(ops.to_device(weight.detach(), dev), 'weight')
+        if w.shape != r.shape:
+            w = w.expand_as(r).contiguous()
+    p, vl, e = ops.VTraceFunction.apply(
+        tgt, v, beh, act, r, w, float(gamma), float(lambda_), float(rho_clip_ratio), float(c_clip_ratio),
+        float(rho_pg_clip_ratio)
+    )
+    if host_out:
+        p, vl, e = p.cpu(), vl.cpu(), e.cpu()
+    return vtrace_loss(p, vl, e)

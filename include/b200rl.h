@@ -1,0 +1,148 @@
+/* b200rl -- C ABI of the B200 (sm_100a) learner hot path for DI-engine.
+ *
+ * This is the drop-in boundary: what a binding for the reference's plugin hook (ding/hpc_rl/wrapper.py:86-133,
+ * registry :62-73) would call for each of the hot-path operators of ding/rl_utils.  The reference's own boundary is a
+ * Python decorator that forwards to an external, un-vendored package (hpc_rll); this library is the compiled code
+ * under such a package: plain device pointers, sizes and scalars, no torch types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a dense row-major tensor: fp32 (`float`) unless declared `long long`
+ *     (the reference's int64 action tensors).  "nullable" pointers select the reference's `None` default.
+ *   - trajectory tensors are (T, B[, ...]) with time as the slowest axis, exactly as the reference lays them out.
+ *   - hyper-parameters are C doubles (python floats); the library narrows them to fp32 the way torch narrows a
+ *     python scalar operand, so products such as gamma*lambda_ are formed in double first.
+ *   - `stream` is a cudaStream_t (passed as void*); all work is enqueued on it, nothing synchronises, nothing
+ *     allocates.  Outputs are caller-allocated.
+ *   - `workspace` is a caller-owned scratch buffer of at least b200rl_workspace_bytes() bytes that must be
+ *     zero-filled once when it is created; launches that share a workspace must be ordered on one stream.
+ *   - return value: 0 success; > 0 a cudaError_t from the launch; B200RL_ERR_ARG (-1) bad argument;
+ *     B200RL_ERR_WORKSPACE (-2) workspace too small for this problem size.
+ *   - forward entry points that feed a backward entry point write "saved" tensors the caller keeps alive between
+ *     the two calls (the autograd context in the PyTorch binding).
+ *   - upstream gradients of the scalar losses are passed as device pointers to single floats (nullable = 0), so a
+ *     backward launch never needs a host read.
+ */
+#ifndef B200RL_H_
+#define B200RL_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200RL_API __attribute__((visibility("default")))
+#else
+#define B200RL_API
+#endif
+
+#define B200RL_ERR_ARG (-1)
+#define B200RL_ERR_WORKSPACE (-2)
+
+/* library / ABI version (major*100 + minor) and the compute capability the kernels were built for (100 = sm_100a) */
+B200RL_API int b200rl_version(void);
+B200RL_API int b200rl_built_for_sm(void);
+B200RL_API size_t b200rl_workspace_bytes(void);
+
+/* ---- gae: ding/rl_utils/gae.py:25-70 -------------------------------------------------------------------------
+ * value, next_value, adv: (T, C); reward, done, traj_flag: (T, C/A)  (A = 1, or the trailing agent dim of the
+ * multi-agent case gae.py:56-59).  done / traj_flag nullable (gae.py:51-54: done -> 0, traj_flag -> done).
+ * mask_next_value_inplace != 0 reproduces the reference's `next_value *= (1 - done)` side effect (gae.py:61).
+ * Bit-exact with the reference loop (separate fp32 mul / add in the same order). */
+B200RL_API int b200rl_gae(const float* value, float* next_value, const float* reward, const float* done, const float* traj_flag,
+               float* adv, long long T, long long C, long long A, double gamma, double lambda_,
+               int mask_next_value_inplace, void* stream);
+
+/* ---- ppo_error: ding/rl_utils/ppo.py:77-140 (policy :143-230, value :233-275, kl :30-54) -----------------------
+ * S samples, G rows per sample (1, or the agent dim of ppo.py:199-200,:206-207), N logits.
+ * logit_new/logit_old/logit_pretrained(nullable): (S*G, N); action: (S*G) int64;
+ * value_new, value_old, adv, return_, weight(nullable): (S).  dual_clip <= 0 means None; kl_type 1|2|3 = 'k1'|'k2'|'k3'.
+ * out[0..5] = policy_loss, value_loss, entropy_loss, kl_div, approx_kl, clipfrac  (out has room for 8 floats). */
+B200RL_API int b200rl_ppo_fwd(const float* logit_new, const float* logit_old, const float* logit_pretrained,
+                   const long long* action, const float* value_new, const float* value_old, const float* adv,
+                   const float* return_, const float* weight, long long S, long long G, long long N,
+                   double clip_ratio, int use_value_clip, double dual_clip, int kl_type, float* out,
+                   float* workspace, size_t workspace_bytes, void* stream);
+/* gradients of  g_policy*policy_loss + g_value*value_loss + g_entropy*entropy_loss + g_kl*kl_div  w.r.t.
+ * logit_new (S*G, N) and value_new (S); autograd tie rules of torch.min/max/clamp reproduced (ppo.py:208-216,:269-272) */
+B200RL_API int b200rl_ppo_bwd(const float* logit_new, const float* logit_old, const float* logit_pretrained,
+                   const long long* action, const float* value_new, const float* value_old, const float* adv,
+                   const float* return_, const float* weight, long long S, long long G, long long N,
+                   double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* g_policy,
+                   const float* g_value, const float* g_entropy, const float* g_kl, float* grad_logit_new,
+                   float* grad_value_new, void* stream);
+
+/* ---- q_nstep_td_error / q_nstep_td_error_with_rescale: ding/rl_utils/td.py:649-719, :810-867, nstep_return :230-286
+ * q, next_n_q: (B, N); action, next_n_action: (B) int64; reward: (nstep, B), or (B) when cum_reward; done: (B);
+ * weight nullable (B); value_gamma nullable, stride 0 (0-dim tensor / python scalar) or 1 ((B) tensor);
+ * gamma_per_sample nullable (B): the list-gamma form used by NGU (td.py:275-282).
+ * rescale != 0 applies value_inv_transform / value_transform (value_rescale.py:4-34) with eps = rescale_eps.
+ * criterion: 0 MSELoss, 1 L1Loss, 2 SmoothL1Loss(beta=criterion_param), 3 HuberLoss(delta=criterion_param), all
+ * reduction='none'.  Writes loss (1), td_error_per_sample (B), dq_saved (B) for the backward call and, when
+ * target_out is not null, the detached n-step target (B) for callers that apply a criterion of their own. */
+B200RL_API int b200rl_qntd_fwd(const float* q, const float* next_n_q, const long long* action, const long long* next_n_action,
+                    const float* reward, const float* done, const float* weight, const float* value_gamma,
+                    long long value_gamma_stride, const float* gamma_per_sample, long long B, long long N, int nstep,
+                    double gamma, int cum_reward, int rescale, double rescale_eps, int criterion,
+                    double criterion_param, float* loss, float* td_error_per_sample, float* dq_saved,
+                    float* target_out, float* workspace, size_t workspace_bytes, void* stream);
+B200RL_API int b200rl_qntd_bwd(const float* dq_saved, const long long* action, const float* g_loss, long long B, long long N,
+                    float* grad_q, void* stream);
+
+/* ---- dist_nstep_td_error (C51): ding/rl_utils/td.py:413-523 ----------------------------------------------------
+ * dist, next_n_dist: (B*A, N, n_atom); act, next_n_act: (B*A) int64; reward: (nstep, B); done: (B);
+ * weight nullable with stride 0 / 1 over the B*A rows; value_gamma nullable with stride 0 / 1 over B;
+ * support: (n_atom) = torch.linspace(v_min, v_max, n_atom) as computed by the caller's torch (td.py:457).
+ * bad_flag (int, caller-zeroed) is set when a selected dist entry is <= 0 (the reference's assert, td.py:513).
+ * Writes loss (1), td_error_per_sample (B*A, unweighted, td.py:519) and proj_saved (B*A, n_atom). */
+B200RL_API int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, const long long* act, const long long* next_n_act,
+                    const float* reward, const float* done, const float* weight, long long weight_stride,
+                    const float* value_gamma, long long value_gamma_stride, const float* support, long long B,
+                    long long A, long long N, int n_atom, int nstep, double gamma, double v_min, double v_max,
+                    float* loss, float* td_error_per_sample, float* proj_saved, int* bad_flag, float* workspace,
+                    size_t workspace_bytes, void* stream);
+B200RL_API int b200rl_dntd_bwd(const float* dist, const long long* act, const float* proj_saved, const float* weight,
+                    long long weight_stride, const float* g_loss, long long R, long long N, int n_atom,
+                    float* grad_dist, void* stream);
+
+/* ---- generalized_lambda_returns / upgo_returns: ding/rl_utils/td.py:1574-1651, upgo.py:46-68 -------------------
+ * value: (T+1, B); reward: (T, B); gammas / lambdas nullable (T, B) tensors overriding the scalars; done nullable.
+ * upgo_mode != 0: gamma = 1 and lambda_t = [r_{t+1} + V_{t+2} >= V_{t+1}] (last row 1).  ret: (T, B).  Bit-exact. */
+B200RL_API int b200rl_lambda_returns(const float* value, const float* reward, const float* gammas, double gamma,
+                          const float* lambdas, double lambda_, const float* done, int upgo_mode, long long T,
+                          long long B, float* ret, void* stream);
+/* ---- td_lambda_error: ding/rl_utils/td.py:1539-1571 (scan + loss head fused) -----------------------------------
+ * writes loss (1) and dvalue_saved (T+1, B) = d loss / d value for unit upstream gradient */
+B200RL_API int b200rl_td_lambda_fwd(const float* value, const float* reward, const float* weight, double gamma, double lambda_,
+                         long long T, long long B, float* loss, float* dvalue_saved, float* workspace,
+                         size_t workspace_bytes, void* stream);
+/* out[i] = (*g) * in[i] -- backward of heads whose forward saved the unit-upstream gradient */
+B200RL_API int b200rl_scale(const float* g, const float* in, float* out, long long n, void* stream);
+
+/* ---- upgo_loss head: ding/rl_utils/upgo.py:77-111 (tb_cross_entropy :7-43) --------------------------------------
+ * logit: (TB*K, N) with K = 1 for (T,B,N) logits or N2 for (T,B,N2,N); action, mask(nullable): (TB*K);
+ * rho, ret (from b200rl_lambda_returns upgo mode), value (= bootstrap_values[:-1]): (TB). */
+B200RL_API int b200rl_upgo_head_fwd(const float* logit, const long long* action, const float* mask, const float* rho,
+                         const float* ret, const float* value, long long TB, long long K, long long N, float* loss,
+                         float* adv_saved, float* workspace, size_t workspace_bytes, void* stream);
+B200RL_API int b200rl_upgo_head_bwd(const float* logit, const long long* action, const float* mask, const float* adv_saved,
+                         const float* g_loss, long long TB, long long K, long long N, float* grad_logit, void* stream);
+
+/* ---- vtrace_error_discrete_action: ding/rl_utils/vtrace.py:72-136 (returns :9-29, advantage :32-45, isw.py:55-58)
+ * target_output, behaviour_output: (T*B, N); action: (T*B) int64; value: (T+1, B); reward, weight(nullable): (T, B).
+ * out3 = policy_loss, value_loss, entropy_loss.  lp_saved / cpg_saved / dv_saved: (T, B) scratch kept for backward. */
+B200RL_API int b200rl_vtrace_fwd(const float* target_output, const float* behaviour_output, const long long* action,
+                      const float* value, const float* reward, const float* weight, long long T, long long B,
+                      long long N, double gamma, double lambda_, double rho_clip_ratio, double c_clip_ratio,
+                      double rho_pg_clip_ratio, float* out3, float* lp_saved, float* cpg_saved, float* dv_saved,
+                      float* workspace, size_t workspace_bytes, void* stream);
+B200RL_API int b200rl_vtrace_bwd(const float* target_output, const long long* action, const float* weight,
+                      const float* cpg_saved, const float* dv_saved, const float* g_policy, const float* g_value,
+                      const float* g_entropy, long long T, long long B, long long N, float* grad_target_output,
+                      float* grad_value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H_ */

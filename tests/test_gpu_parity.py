@@ -1,0 +1,217 @@
+"""GPU suite (-m gpu): parity of the CUDA path (through the C ABI) against
+
+1. the committed golden fixtures -- outputs of the unmodified reference (tests/golden/make_golden.py);
+2. the CPU oracle on the same seeded inputs at the BASELINE.json sizes;
+3. size-independent properties at full size, and the edge cases the reference's tests exercise.
+
+Tolerances (north star): bit-exact for gae / lambda-returns / in-place masks (pure fp32 mul-add in reference order
+and boolean-driven recurrences); |a-b| <= 1e-5 + 1e-5*|b| for everything that involves exp/log or a reduction.
+"""
+import numpy as np
+import pytest
+import torch
+
+import di_engine_b200 as b2
+from oracle import rl_oracle
+from tests import cases, golden_io
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _run(op, tensors, params, device=DEV):
+    return cases.run_api(b2.rl_utils, op, tensors, params, device=device)
+
+
+@pytest.mark.parametrize('name', golden_io.names())
+def test_matches_reference_golden(name):
+    op, tensors, params, expected = golden_io.load(name)
+    got = _run(op, tensors, params)
+    if op == 'gae':
+        cases.compare(got, expected, exact=True)
+    else:
+        cases.compare(got, expected, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('name', golden_io.names())
+def test_host_buffer_path_matches_golden(name):
+    """CPU tensors in -> staged to the GPU -> results (and the in-place next_value mask) back on the host."""
+    op, tensors, params, expected = golden_io.load(name)
+    got = _run(op, tensors, params, device='cpu')
+    cases.compare(got, expected, exact=(op == 'gae'))
+
+
+BIG = {
+    'gae_D': lambda: cases.gae_case(100, 128, 4096, p_done=0.01),
+    'gae_D_none': lambda: cases.gae_case(105, 128, 4096, done=None, traj=None),
+    'gae_long1d': lambda: cases.gae_case(106, 3200, 1, one_d=True, p_done=0.01),
+    'gae_ragged': lambda: cases.gae_case(107, 131, 1001, p_done=0.05),
+    'gae_T1024': lambda: cases.gae_case(108, 1024, 64, p_done=0.02),
+    'ppo_D': lambda: cases.ppo_case(101, 128 * 4096, 6, clip_ratio=0.2),
+    'ppo_D_w_dc': lambda: cases.ppo_case(109, 128 * 512 + 37, 6, weight='tensor', dual_clip=3.0),
+    'ppo_N18_kl': lambda: cases.ppo_case(110, 10000, 18, pretrained=True, kl_type='k3', weight='tensor'),
+    'ppo_N40': lambda: cases.ppo_case(111, 3000, 40, weight='tensor'),
+    'ppo_N1000': lambda: cases.ppo_case(112, 257, 1000),
+    'ppo_marl_big': lambda: cases.ppo_case(113, 2000, 9, A=5, weight='tensor'),
+    'qntd_B': lambda: cases.qntd_case(102, 512, 6, 3, value_gamma='tensor', gamma=0.99, done='bern'),
+    'qntd_big': lambda: cases.qntd_case(114, 100003, 18, 5, weight='tensor'),
+    'qntdr_B': lambda: cases.qntd_case(115, 512, 6, 3, rescale=True, value_gamma='tensor', done='bern'),
+    'dntd_C': lambda: cases.dntd_case(103, 512, 6, 51, 3, gamma=0.99, value_gamma='tensor'),
+    'dntd_big': lambda: cases.dntd_case(116, 4099, 4, 51, 5, weight='tensor'),
+    'tdl_hpc': lambda: cases.td_lambda_case(117, 1024, 64, weight='tensor'),
+    'tdl_wide': lambda: cases.td_lambda_case(118, 64, 8192, gamma=0.99, lambda_=0.95),
+    'upgo_big': lambda: cases.upgo_case(119, 64, 64, 64),
+    'upgo_N200': lambda: cases.upgo_case(120, 16, 16, 200),
+    'vtrace_E': lambda: cases.vtrace_case(104, 64, 8192, 6, gamma=0.99, lambda_=0.95),
+    'vtrace_ragged': lambda: cases.vtrace_case(121, 130, 333, 7, weight='tensor', rho_clip_ratio=0.9),
+    'vtrace_N100': lambda: cases.vtrace_case(122, 8, 16, 100),
+}
+
+
+@pytest.mark.parametrize('name', sorted(BIG.keys()))
+def test_matches_oracle_at_baseline_sizes(name):
+    op, tensors, params = BIG[name]()
+    want = cases.run_oracle(rl_oracle, op, tensors, params)
+    got = _run(op, tensors, params)
+    if op == 'gae':
+        cases.compare(got, want, exact=True)
+    else:
+        cases.compare(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_lambda_returns_bit_exact_including_tensor_operands():
+    g = torch.Generator().manual_seed(5)
+    T, B = 97, 203
+    v = torch.randn(T + 1, B, generator=g)
+    r = torch.randn(T, B, generator=g)
+    gam = torch.rand(T, B, generator=g)
+    lam = torch.rand(T, B, generator=g)
+    done = (torch.rand(T, B, generator=g) < 0.1).float()
+    for args in ((0.99, 0.95, None), (gam, lam, None), (gam, 0.9, done), (1.0, lam > 0.5, done)):
+        want = rl_oracle.generalized_lambda_returns(v, r, *args)
+        dargs = [a.to(DEV) if isinstance(a, torch.Tensor) else a for a in args]
+        got = b2.generalized_lambda_returns(v.to(DEV), r.to(DEV), *dargs).cpu()
+        assert torch.equal(got, want)
+    assert torch.equal(b2.upgo_returns(r.to(DEV), v.to(DEV)).cpu(), rl_oracle.upgo_returns(r, v))
+
+
+def test_gae_unaligned_noncontiguous_and_inplace_semantics():
+    op, t, p = cases.gae_case(7, 64, 260, p_done=0.1)
+    want = cases.run_oracle(rl_oracle, op, t, p)
+    # (a) views with an odd storage offset -> the scalar (non-float4) kernel path
+    pad = {k: torch.cat([torch.zeros(1), v.reshape(-1)]).to(DEV)[1:].view(v.shape) for k, v in t.items()}
+    adv = b2.gae(b2.gae_data(*pad.values()), **p)
+    assert np.array_equal(adv.cpu().numpy(), want['out_adv'])
+    assert np.array_equal(pad['next_value'].cpu().numpy(), want['out_next_value_after'])  # mutated in place
+    # (b) non-contiguous (transposed storage) inputs: result identical, caller's next_value still masked
+    nc = {k: v.t().contiguous().to(DEV).t() for k, v in t.items()}
+    assert not nc['value'].is_contiguous()
+    adv = b2.gae(b2.gae_data(*nc.values()), **p)
+    assert np.array_equal(adv.cpu().numpy(), want['out_adv'])
+    assert np.array_equal(nc['next_value'].cpu().numpy(), want['out_next_value_after'])
+
+
+def test_gae_properties_at_full_size():
+    T, B = 128, 4096
+    g = torch.Generator().manual_seed(11)
+    v, nv, r = (torch.randn(T, B, generator=g).to(DEV) for _ in range(3))
+    # lambda = 0 -> adv is exactly the one-step TD residual (no recurrence)
+    adv0 = b2.gae(b2.gae_data(v, nv.clone(), r, None, None), 0.99, 0.0)
+    assert torch.equal(adv0, r + 0.99 * nv - v)
+    # traj_flag = 1 everywhere cuts every trace: same result with any lambda
+    ones = torch.ones(T, B, device=DEV)
+    adv1 = b2.gae(b2.gae_data(v, nv.clone(), r, torch.zeros_like(ones), ones), 0.99, 0.95)
+    assert torch.equal(adv1, adv0)
+    # done = 1 everywhere: next_value is zeroed in place and adv = r - v (+ trace of the same)
+    nv2 = nv.clone()
+    adv2 = b2.gae(b2.gae_data(v, nv2, r, ones, ones), 0.99, 0.95)
+    assert torch.count_nonzero(nv2) == 0 and torch.equal(adv2, r + 0.99 * nv2 - v)
+
+
+def test_ppo_gradient_rows_sum_to_zero_at_full_size():
+    """d loss / d logits of any function of a softmax sums to zero along the action axis."""
+    op, t, p = cases.ppo_case(3, 128 * 4096, 6, weight='tensor')
+    got = _run(op, t, p)
+    gl = got['grad_logit_new'].astype(np.float64)
+    assert np.abs(gl.sum(-1)).max() < 1e-9
+    assert np.isfinite(gl).all() and np.abs(gl).max() > 0
+
+
+def test_c51_projection_conserves_mass_at_full_size():
+    op, t, p = cases.dntd_case(9, 512, 6, 51, 3, gamma=0.99)
+    t = dict(t)
+    t['dist'] = torch.full_like(t['dist'], 1.0 / 51)
+    got = _run(op, t, p)
+    assert np.allclose(got['out_td_error_per_sample'], np.log(51.0), atol=1e-5)
+
+
+def test_c51_nonpositive_dist_raises_like_reference():
+    op, t, p = cases.dntd_case(9, 8, 3, 51, 3)
+    t = dict(t)
+    t['dist'] = t['dist'].clone()
+    t['dist'][2, t['act'][2], 7] = 0.0
+    with pytest.raises(AssertionError):
+        _run(op, t, p)
+
+
+def test_repeated_calls_are_deterministic_and_workspace_is_reusable():
+    op, t, p = cases.ppo_case(4, 70001, 6, weight='tensor')
+    a = _run(op, t, p)
+    for _ in range(3):
+        b = _run(op, t, p)
+        cases.compare(b, a, exact=True)
+
+
+def test_criterion_variants_match_torch_modules():
+    import torch.nn as nn
+    op, t, p = cases.qntd_case(21, 257, 5, 3, weight='tensor')
+    for crit in (nn.SmoothL1Loss(reduction='none', beta=0.7), nn.HuberLoss(reduction='none', delta=0.4),
+                 nn.L1Loss(reduction='none')):
+        tt = cases.prepare(op, t)
+        want_l, want_p = rl_oracle.q_nstep_td_error(**tt, gamma=0.95, nstep=3, criterion=crit)
+        want_l.backward()
+        td = cases.prepare(op, t, DEV)
+        data = b2.q_nstep_td_data(*[td[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done',
+                                                    'weight')])
+        loss, per = b2.q_nstep_td_error(data, 0.95, nstep=3, criterion=crit)
+        loss.backward()
+        assert torch.allclose(loss.cpu(), want_l, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(per.cpu(), want_p, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(td['q'].grad.cpu(), tt['q'].grad, rtol=1e-5, atol=1e-6)
+
+
+def test_cuda_graph_capture_of_the_learner_step():
+    """gae -> ppo forward -> ppo backward recorded in one CUDA graph and replayed: same numbers as eager."""
+    from di_engine_b200 import ops
+    T, B, N = 128, 512, 6
+    _, tg, pg = cases.gae_case(31, T, B, p_done=0.01)
+    _, tp, pp = cases.ppo_case(32, T * B, N)
+    tg = {k: v.to(DEV) for k, v in tg.items()}
+    tp = {k: (v.to(DEV) if v is not None else None) for k, v in tp.items()}
+    nv0 = tg['next_value'].clone()
+    s = torch.cuda.Stream()
+    outs = {}
+
+    def step():
+        tg['next_value'].copy_(nv0)
+        adv = ops.gae_(tg['value'], tg['next_value'], tg['reward'], tg['done'], tg['traj_flag'], 0.99, 0.95, 1)
+        ln = tp['logit_new'].detach().requires_grad_(True)
+        vn = tp['value_new'].detach().requires_grad_(True)
+        p, v, e, k, _ = ops.PPOFunction.apply(ln, vn, tp['logit_old'], tp['action'], tp['value_old'], adv.view(-1),
+                                              tp['return_'], None, None, T * B, 1, N, 0.2, 1, 0.0, 1)
+        (p + 0.5 * v - 0.01 * e).backward()
+        outs.update(adv=adv, p=p, gl=ln.grad, gv=vn.grad)
+
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+        eager = {k: v.clone() for k, v in outs.items()}
+        s.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            step()
+        for _ in range(3):
+            graph.replay()
+    s.synchronize()
+    for k in eager:
+        assert torch.equal(outs[k], eager[k]), k

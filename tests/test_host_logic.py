@@ -1,0 +1,305 @@
+"""CPU suite (-m "not gpu"): host-side logic of the product package, with NO compute.
+
+* the C-ABI library loads and exports every symbol ``include/b200rl.h`` declares, and the ctypes prototypes agree
+  with the header's parameter lists;
+* the Python mirror of the reference interface: namedtuple fields, signatures/defaults, ``shape_fn_*`` return values
+  (ding/rl_utils/tests/test_td.py:509-588, test_ppo.py:17-21), error behaviour (ppo.py:129, :54; td.py:257, :284, :854);
+* every public operator marshals its arguments into the C entry points without error -- checked against a recording
+  stand-in for the library (no kernel runs: there is no GPU here);
+* ``install()`` / ``uninstall()`` rebinding and the ``hpc_rll`` shim layout (ding/hpc_rl/wrapper.py:62-73);
+* the product refuses to run without CUDA (no CPU fallback) and never imports the oracle.
+"""
+import contextlib
+import ctypes
+import inspect
+import os
+import re
+import sys
+import types
+
+import pytest
+import torch
+import torch.nn as nn
+
+import di_engine_b200 as b2
+from di_engine_b200 import _lib, ops
+from tests import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_decls():
+    text = open(os.path.join(ROOT, 'include', 'b200rl.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    decls = {}
+    for m in re.finditer(r'B200RL_API\s+(\w+)\s+(b200rl_\w+)\s*\((.*?)\)\s*;', text, flags=re.S):
+        params = [p.strip() for p in m.group(3).split(',')]
+        if params == ['void']:
+            params = []
+        decls[m.group(2)] = (m.group(1), params)
+    return decls
+
+
+def test_library_exports_every_declared_symbol():
+    decls = _header_decls()
+    assert len(decls) >= 17
+    lib = _lib.load()
+    for name in decls:
+        assert hasattr(lib, name), name
+    assert set(decls) == set(_lib.PROTOTYPES), set(decls) ^ set(_lib.PROTOTYPES)
+    assert lib.b200rl_version() >= 100
+    assert lib.b200rl_built_for_sm() == 100
+    assert lib.b200rl_workspace_bytes() >= 1 << 20
+
+
+def test_ctypes_prototypes_match_header():
+    ctype_of = {'double': ctypes.c_double, 'int': ctypes.c_int, 'long long': ctypes.c_longlong,
+                'size_t': ctypes.c_size_t}
+    for name, (ret, params) in _header_decls().items():
+        want = []
+        for p in params:
+            if '*' in p:
+                want.append(ctypes.c_void_p)
+            else:
+                ty = re.sub(r'\s+\w+$', '', p.replace('const ', '')).strip()
+                want.append(ctype_of[ty])
+        assert _lib.PROTOTYPES[name] == want, name
+
+
+def test_namedtuple_fields_match_reference():
+    r = b2.rl_utils
+    assert r.gae_data._fields == ('value', 'next_value', 'reward', 'done', 'traj_flag')  # gae.py:5
+    assert r.ppo_data._fields == ('logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv', 'return_',
+                                  'weight', 'logit_pretrained')  # ppo.py:8-11
+    assert r.ppo_loss._fields == ('policy_loss', 'value_loss', 'entropy_loss', 'kl_div')
+    assert r.ppo_info._fields == ('approx_kl', 'clipfrac')
+    assert r.q_nstep_td_data._fields == ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight')
+    assert r.dist_nstep_td_data._fields == ('dist', 'next_n_dist', 'act', 'next_n_act', 'reward', 'done', 'weight')
+    assert r.dist_nstep_td_data.__name__ == 'dist_1step_td_data'  # td.py:386
+    assert r.td_lambda_data._fields == ('value', 'reward', 'weight')
+    assert r.vtrace_data._fields == ('target_output', 'behaviour_output', 'action', 'value', 'reward', 'weight')
+    assert r.vtrace_loss._fields == ('policy_loss', 'value_loss', 'entropy_loss')
+
+
+def test_signatures_match_reference_defaults():
+    def sig(fn):
+        return [(k, v.default) for k, v in inspect.signature(fn).parameters.items()]
+
+    E = inspect.Parameter.empty
+    r = b2.rl_utils
+    assert sig(r.gae) == [('data', E), ('gamma', 0.99), ('lambda_', 0.97)]
+    assert sig(r.ppo_error) == [('data', E), ('clip_ratio', 0.2), ('use_value_clip', True), ('dual_clip', None),
+                                ('kl_type', 'k1')]
+    s = sig(r.q_nstep_td_error)
+    assert [k for k, _ in s] == ['data', 'gamma', 'nstep', 'cum_reward', 'value_gamma', 'criterion']
+    assert s[2][1] == 1 and s[3][1] is False and s[4][1] is None and isinstance(s[5][1], nn.MSELoss)
+    s = sig(r.q_nstep_td_error_with_rescale)
+    assert [k for k, _ in s] == ['data', 'gamma', 'nstep', 'value_gamma', 'criterion', 'trans_fn', 'inv_trans_fn']
+    assert s[5][1] is r.value_transform and s[6][1] is r.value_inv_transform
+    assert sig(r.dist_nstep_td_error) == [('data', E), ('gamma', E), ('v_min', E), ('v_max', E), ('n_atom', E),
+                                          ('nstep', 1), ('value_gamma', None)]
+    assert sig(r.td_lambda_error) == [('data', E), ('gamma', 0.9), ('lambda_', 0.8)]
+    assert sig(r.generalized_lambda_returns) == [('bootstrap_values', E), ('rewards', E), ('gammas', E),
+                                                 ('lambda_', E), ('done', None)]
+    assert sig(r.vtrace_error_discrete_action) == [('data', E), ('gamma', 0.99), ('lambda_', 0.95),
+                                                   ('rho_clip_ratio', 1.0), ('c_clip_ratio', 1.0),
+                                                   ('rho_pg_clip_ratio', 1.0)]
+    assert sig(r.upgo_loss) == [('target_output', E), ('rhos', E), ('action', E), ('rewards', E),
+                                ('bootstrap_values', E), ('mask', None)]
+
+
+def test_shape_fns():
+    r = b2.rl_utils
+    d = r.gae_data(None, None, torch.zeros(5, 3), None, None)
+    assert tuple(r.shape_fn_gae([d], {})) == (5, 3) and tuple(r.shape_fn_gae([], {'data': d})) == (5, 3)
+    d = r.ppo_data(torch.zeros(7, 4), *[None] * 8)
+    assert tuple(r.shape_fn_ppo([d], {})) == (7, 4) and tuple(r.shape_fn_ppo([], {'data': d})) == (7, 4)
+    d = r.q_nstep_td_data(torch.zeros(4, 3), None, None, None, torch.zeros(5, 4), None, None)
+    for fn in (r.shape_fn_qntd, r.shape_fn_qntd_rescale):
+        assert fn([d], {}) == [5, 4, 3] and fn([], {'data': d}) == [5, 4, 3]
+    d = r.dist_nstep_td_data(torch.zeros(4, 3, 51), None, None, None, torch.zeros(5, 4), None, None)
+    assert r.shape_fn_dntd([d], {}) == [5, 4, 3, 51] and r.shape_fn_dntd([], {'data': d}) == [5, 4, 3, 51]
+    d = r.td_lambda_data(None, torch.zeros(8, 4), None)
+    assert tuple(r.shape_fn_td_lambda([d], {})) == (8, 4)
+    assert r.shape_fn_td_lambda([], {'data': d}) == 8  # keyword form returns T only, td.py:1526-1527
+    d = r.vtrace_data(torch.zeros(4, 8, 16), None, None, None, None, None)
+    assert tuple(r.shape_fn_vtrace_discrete_action([d], {})) == (4, 8, 16)
+
+
+def test_no_cpu_fallback_and_no_oracle_import():
+    assert not torch.cuda.is_available(), "this test documents the CPU-only container"
+    t = torch.zeros(4, 3)
+    with pytest.raises(_lib.B200RLError):
+        b2.gae(b2.gae_data(t, t.clone(), t, None, None))
+    with pytest.raises(_lib.B200RLError):
+        b2.install()
+    pkg_dir = os.path.join(ROOT, 'di-engine_b200')
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f
+                assert 'rl_oracle' not in src and 'ref_loader' not in src, f
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# marshalling dry run against a recording stand-in for the library (no kernels, no GPU)
+# ----------------------------------------------------------------------------------------------------------------
+class _RecordingLib:
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        proto = _lib.PROTOTYPES[name]
+
+        def fn(*args):
+            assert len(args) == len(proto), (name, len(args), len(proto))
+            for a, ty in zip(args, proto):
+                ty.from_param(a)  # raises on a type ctypes could not marshal
+            self.calls.append(name)
+            return 0
+
+        if name == 'b200rl_workspace_bytes':
+            return lambda: 1 << 20
+        return fn
+
+
+@pytest.fixture
+def dry(monkeypatch):
+    rec = _RecordingLib()
+    monkeypatch.setattr(ops, 'lib', lambda: rec)
+    monkeypatch.setattr(ops, 'require_cuda', lambda: None)
+    monkeypatch.setattr(ops, 'compute_device', lambda *t: torch.device('cpu'))
+    monkeypatch.setattr(ops, 'stream_ptr', lambda: 0)
+    monkeypatch.setattr(torch.cuda, 'device', lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(b2.rl_utils.td, 'CHECK_DIST_POSITIVE', False)
+    ops._WS.clear()
+    yield rec
+    ops._WS.clear()
+    ops._CONST.clear()
+    b2.rl_utils.td._SUPPORT_CACHE.clear()
+
+
+EXPECTED_CALLS = {
+    'gae': ['b200rl_gae'],
+    'ppo': ['b200rl_ppo_fwd', 'b200rl_ppo_bwd'],
+    'qntd': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
+    'qntd_rescale': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
+    'dntd': ['b200rl_dntd_fwd', 'b200rl_dntd_bwd'],
+    'td_lambda': ['b200rl_td_lambda_fwd', 'b200rl_scale'],
+    'upgo': ['b200rl_lambda_returns', 'b200rl_upgo_head_fwd', 'b200rl_upgo_head_bwd'],
+    'vtrace': ['b200rl_vtrace_fwd', 'b200rl_vtrace_bwd'],
+}
+
+
+@pytest.mark.parametrize('name', sorted(cases.build_cases().keys()))
+def test_marshalling_dry_run(dry, name):
+    op, tensors, params = cases.build_cases()[name]
+    res = cases.run_api(b2.rl_utils, op, tensors, params)
+    assert dry.calls == EXPECTED_CALLS[op], dry.calls
+    assert any(k.startswith('out_') for k in res)
+    for k in cases.GRAD_INPUTS[op]:
+        assert 'grad_' + k in res and res['grad_' + k].shape == tuple(tensors[k].shape)
+
+
+def test_custom_criterion_and_transforms_dry_run(dry):
+    op, t, p = cases.qntd_case(1, 8, 4, 3, weight='tensor')
+    t = cases.prepare(op, t)
+    data = b2.q_nstep_td_data(*[t[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight')])
+
+    class Quartic(nn.Module):
+        reduction = 'none'
+
+        def forward(self, a, b):
+            return (a - b) ** 4
+
+    loss, per = b2.q_nstep_td_error(data, 0.9, nstep=3, criterion=Quartic())
+    assert dry.calls == ['b200rl_qntd_fwd'] and per.shape == (8, )
+    loss.backward()
+    assert t['q'].grad is not None
+    for crit in (nn.SmoothL1Loss(reduction='none'), nn.HuberLoss(reduction='none', delta=0.5),
+                 nn.L1Loss(reduction='none')):
+        dry.calls.clear()
+        b2.q_nstep_td_error(data, 0.9, nstep=3, criterion=crit)
+        assert dry.calls == ['b200rl_qntd_fwd']
+    dry.calls.clear()
+    loss, per = b2.q_nstep_td_error_with_rescale(data, 0.9, nstep=3, trans_fn=lambda x: x * 2,
+                                                  inv_trans_fn=lambda x: x / 2)
+    assert dry.calls == ['b200rl_qntd_fwd'] and per.shape == (8, )
+
+
+def test_error_behaviour_matches_reference(dry):
+    op, t, p = cases.ppo_case(1, 8, 4)
+    data = b2.ppo_data(*t.values())
+    with pytest.raises(AssertionError, match='dual_clip value must be greater than 1.0'):  # ppo.py:129
+        b2.ppo_error(data, dual_clip=0.5)
+    op, t, p = cases.ppo_case(1, 8, 4, pretrained=True)
+    with pytest.raises(ValueError, match='Unknown kl_type'):  # ppo.py:54
+        b2.ppo_error(b2.ppo_data(*t.values()), kl_type='k9')
+    op, t, p = cases.qntd_case(1, 8, 4, 3)
+    data = b2.q_nstep_td_data(*[t[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight')])
+    with pytest.raises(TypeError, match='gamma should be float or list'):  # td.py:284
+        b2.q_nstep_td_error(data, 1, nstep=3)
+    with pytest.raises(AssertionError):  # td.py:257
+        b2.q_nstep_td_error(data, 0.9, nstep=2)
+    bad = data._replace(action=torch.zeros(8, 2, dtype=torch.long))
+    with pytest.raises(AssertionError):  # td.py:854
+        b2.q_nstep_td_error_with_rescale(bad, 0.9, nstep=3)
+    with pytest.raises(TypeError, match='float32'):
+        v = torch.zeros(4, 3, dtype=torch.float64)
+        b2.gae(b2.gae_data(v, v.clone(), v, None, None))
+
+
+def test_install_rebinds_and_uninstall_restores(dry, monkeypatch):
+    def ref_gae(data, gamma=0.99, lambda_=0.97):
+        return 'reference'
+
+    def ref_ppo(data):
+        return 'reference'
+
+    fake = {}
+    for name in ('ding', 'ding.rl_utils', 'ding.rl_utils.gae', 'ding.rl_utils.ppo', 'ding.policy', 'ding.policy.ppo',
+                 'dizoo', 'dizoo.common', 'dizoo.common.policy', 'dizoo.common.policy.md_ppo', 'ding.rl_utils.adder'):
+        fake[name] = types.ModuleType(name)
+        monkeypatch.setitem(sys.modules, name, fake[name])
+    for m in ('ding.rl_utils', 'ding.rl_utils.gae', 'ding.policy.ppo', 'dizoo.common.policy.md_ppo',
+              'ding.rl_utils.adder'):
+        fake[m].gae = ref_gae
+    fake['ding.rl_utils'].ppo_error = ref_ppo
+    fake['ding.rl_utils.ppo'].ppo_error = ref_ppo
+    fake['ding.policy.ppo'].ppo_error = ref_ppo
+    fake['ding.policy.ppo'].unrelated = ref_ppo
+    done = b2.install(skip_modules=('ding.rl_utils.adder', ))
+    assert ('ding.policy.ppo', 'gae') in done and ('ding.policy.ppo', 'ppo_error') in done
+    assert fake['ding.policy.ppo'].gae is b2.rl_utils.gae
+    assert fake['dizoo.common.policy.md_ppo'].gae is b2.rl_utils.gae
+    assert fake['ding.rl_utils'].ppo_error is b2.rl_utils.ppo_error
+    assert fake['ding.rl_utils.adder'].gae is ref_gae  # skipped
+    assert fake['ding.policy.ppo'].unrelated is ref_ppo
+    b2.uninstall()
+    assert fake['ding.policy.ppo'].gae is ref_gae and fake['ding.rl_utils'].ppo_error is ref_ppo
+
+
+def test_hpc_rll_shim_layout(monkeypatch):
+    for k in list(sys.modules):
+        if k == 'hpc_rll' or k.startswith('hpc_rll.'):
+            monkeypatch.delitem(sys.modules, k)
+    b2.install_hpc_rll()
+    import importlib
+    mapping = {  # ding/hpc_rl/wrapper.py:62-73 (the eight operators on this path)
+        'gae': ['hpc_rll.rl_utils.gae', 'GAE'],
+        'dist_nstep_td_error': ['hpc_rll.rl_utils.td', 'DistNStepTD'],
+        'ppo_error': ['hpc_rll.rl_utils.ppo', 'PPO'],
+        'q_nstep_td_error': ['hpc_rll.rl_utils.td', 'QNStepTD'],
+        'q_nstep_td_error_with_rescale': ['hpc_rll.rl_utils.td', 'QNStepTDRescale'],
+        'td_lambda_error': ['hpc_rll.rl_utils.td', 'TDLambda'],
+        'upgo_loss': ['hpc_rll.rl_utils.upgo', 'UPGO'],
+        'vtrace_error_discrete_action': ['hpc_rll.rl_utils.vtrace', 'VTrace'],
+    }
+    for fn, (mod, cls) in mapping.items():
+        op = getattr(importlib.import_module(mod), cls)(4, 3).cuda()
+        assert callable(op)
+    for k in list(sys.modules):
+        if k == 'hpc_rll' or k.startswith('hpc_rll.'):
+            del sys.modules[k]
