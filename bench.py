@@ -40,7 +40,7 @@ import torch  # noqa: E402
 T_LEN, B_COLS, N_ACT = 128, 4096, 6
 GAMMA, LAMBDA, CLIP = 0.99, 0.95, 0.2
 W_VALUE, W_ENTROPY = 0.5, -0.01
-ALG_BYTES_PER_TR = {'gae': 24, 'ppo_fwd': 76, 'ppo_bwd': 100, 'step': 128}
+ALG_BYTES_PER_TR = {'gae': 24, 'ppo_fwd': 76, 'ppo_bwd': 100, 'ppo_fwd_grad': 104, 'ppo_bwd_check': 0, 'step': 128}
 METRIC = 'learner transitions/sec (GAE+ppo_error fwd+bwd, T=128 x B=4096 per GPU)'
 
 
@@ -80,14 +80,49 @@ def cpu_step(orc, b):
     p, v, e, k, akl, cf = orc.ppo_error(ln, b['logit_old'], b['action'], vn, b['value_old'], adv.reshape(-1),
                                         b['return_'], None, None, CLIP, True, None)
     (p + W_VALUE * v + W_ENTROPY * e).backward()
-    return float(p)
+    return float(p.detach())
+
+
+def usable_cores():
+    """Host cores this process may actually use: affinity mask, clipped by the cgroup CPU quota if there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def pick_threads(orc, b):
+    """All the host threads the reference can USE: the fastest of {usable, 64, 32, 16, 8} torch intra-op threads
+    (over-subscribing a throttled container makes torch slower, not faster)."""
+    usable = usable_cores()
+    best, best_t = None, None
+    for n in sorted({usable, 64, 32, 16, 8}):
+        if n > usable:
+            continue
+        torch.set_num_threads(n)
+        cpu_step(orc, b)
+        t0 = time.perf_counter()
+        cpu_step(orc, b)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+        if dt > 4 * best_t:
+            break
+    return best
 
 
 def run_cpu(steps, warmup):
     from oracle import rl_oracle
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     b = make_batch(0)
+    cores = pick_threads(rl_oracle, b)
+    torch.set_num_threads(cores)
     for _ in range(warmup):
         cpu_step(rl_oracle, b)
     times = []
@@ -180,9 +215,12 @@ def load_peaks():
 class DeviceStep:
     """One learner step on device-resident buffers, via the tensor-level layer under the public API."""
 
-    def __init__(self, host_batch, dev):
+    def __init__(self, host_batch, dev, fused=True):
         from di_engine_b200 import ops
         self.ops = ops
+        self.fused = fused
+        self.hint = torch.tensor([1.0, W_VALUE, W_ENTROPY, 0.0], device=dev)
+        self.g_used = torch.zeros(4, device=dev)
         self.b = {k: v.to(dev) for k, v in host_batch.items()}
         self.nv0 = self.b['next_value'].clone()
         self.S = T_LEN * B_COLS
@@ -215,14 +253,36 @@ class DeviceStep:
         rc = o.lib().b200rl_ppo_bwd(o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
                                     o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(self.adv), o.ptr(b['return_']),
                                     None, self.S, 1, N_ACT, CLIP, 1, 0.0, 1, o.ptr(self.g_p), o.ptr(self.g_v),
-                                    o.ptr(self.g_e), None, o.ptr(self.grad_logit), o.ptr(self.grad_value),
+                                    o.ptr(self.g_e), None, None, None, o.ptr(self.grad_logit), o.ptr(self.grad_value),
                                     o.stream_ptr())
         assert rc == 0, rc
 
+    def ppo_fwd_grad(self):
+        b, o = self.b, self.ops
+        rc = o.lib().b200rl_ppo_fwd_grad(o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
+                                         o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(self.adv),
+                                         o.ptr(b['return_']), None, self.S, 1, N_ACT, CLIP, 1, 0.0, 1, o.ptr(self.hint),
+                                         o.ptr(self.g_used), o.ptr(self.out), o.ptr(self.grad_logit),
+                                         o.ptr(self.grad_value), o.ptr(self.ws), self.ws.numel() * 4, o.stream_ptr())
+        assert rc == 0, rc
+
+    def ppo_bwd_check(self):
+        b, o = self.b, self.ops
+        rc = o.lib().b200rl_ppo_bwd(o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
+                                    o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(self.adv), o.ptr(b['return_']),
+                                    None, self.S, 1, N_ACT, CLIP, 1, 0.0, 1, o.ptr(self.g_p), o.ptr(self.g_v),
+                                    o.ptr(self.g_e), None, o.ptr(self.g_used), o.ptr(self.hint),
+                                    o.ptr(self.grad_logit), o.ptr(self.grad_value), o.stream_ptr())
+        assert rc == 0, rc
+
+    def kernels(self):
+        if self.fused:
+            return [('gae', self.gae), ('ppo_fwd_grad', self.ppo_fwd_grad), ('ppo_bwd_check', self.ppo_bwd_check)]
+        return [('gae', self.gae), ('ppo_fwd', self.ppo_fwd), ('ppo_bwd', self.ppo_bwd)]
+
     def __call__(self):
-        self.gae()
-        self.ppo_fwd()
-        self.ppo_bwd()
+        for _, k in self.kernels():
+            k()
 
 
 def run_gpu(args):
@@ -247,7 +307,7 @@ def run_gpu(args):
 
     K, W = args.steps, args.warmup
     NSETS = 4
-    sets = [DeviceStep(make_batch(1000 * rank + i), dev) for i in range(NSETS)]
+    sets = [DeviceStep(make_batch(1000 * rank + i), dev, fused=not args.unfused) for i in range(NSETS)]
     step_bytes = ALG_BYTES_PER_TR['step'] * T_LEN * B_COLS
     side = torch.cuda.Stream()
     main = torch.cuda.Stream()
@@ -307,23 +367,26 @@ def run_gpu(args):
         barrier()
         dev_ms = e0.elapsed_time(e1)
 
-        # ---- per-kernel timing (eager launches, rotated sets), same stream ----------------------------------------
-        names = ['gae', 'ppo_fwd', 'ppo_bwd']
-        per = {n: [] for n in names}
-        for i in range(K + 3):
-            s = sets[i % NSETS]
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            evs[0].record(main)
-            s.gae()
-            evs[1].record(main)
-            s.ppo_fwd()
-            evs[2].record(main)
-            s.ppo_bwd()
-            evs[3].record(main)
+        # ---- per-kernel timing: each kernel alone, back to back over the rotated buffer sets, replayed as a graph so
+        # that launch gaps of the host do not enter the figure (CUDA events on the launching stream)
+        names = [n for n, _ in sets[0].kernels()]
+        per = {}
+        reps = max(5, K // NSETS)
+        for ki, name in enumerate(names):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=main):
+                for s in sets:
+                    s.kernels()[ki][1]()
+            for _ in range(3):
+                g.replay()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             main.synchronize()
-            if i >= 3:
-                for k, n in enumerate(names):
-                    per[n].append(evs[k].elapsed_time(evs[k + 1]))
+            k0.record(main)
+            for _ in range(reps):
+                g.replay()
+            k1.record(main)
+            main.synchronize()
+            per[name] = [k0.elapsed_time(k1) / (reps * NSETS)]
         clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end through the public API from pinned host buffers ------------------------------------------------
@@ -383,7 +446,7 @@ def run_gpu(args):
                 'loss_mix': [1.0, W_VALUE, W_ENTROPY], 'parallelism': 'dp%d' % world,
                 'l2_policy': 'inputs rotated over %d buffer sets of 67 MB (> 126 MB L2) between consecutive steps' %
                              NSETS,
-                'launch': 'CUDA graph replay of 3 kernels per step',
+                'launch': 'CUDA graph replay of 3 kernels per step (%s)' % ', '.join(names),
                 'collective': 'none' if world == 1 else 'one NCCL all-reduce of 8 packed loss floats per step, side stream',
             },
             'roofline': {
@@ -433,6 +496,7 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--unfused', action='store_true', help='separate ppo forward / backward kernels')
     args = ap.parse_args()
     if args.impl == 'reference':
         if args.steps > 400:

@@ -22,7 +22,9 @@ PROTOTYPES = {
     "b200rl_workspace_bytes": [],
     "b200rl_gae": [P, P, P, P, P, P, LL, LL, LL, D, D, I, P],
     "b200rl_ppo_fwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, c_size_t, P],
-    "b200rl_ppo_bwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, P],
+    "b200rl_ppo_bwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, P, P, P],
+    "b200rl_ppo_fwd_grad": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, c_size_t, P],
+    "b200rl_ppo_fused_supported": [P, P, P, P, P, P, P, P, P, P, LL, LL],
     "b200rl_qntd_fwd": [P, P, P, P, P, P, P, P, LL, P, LL, LL, I, D, I, I, D, I, D, P, P, P, P, P, c_size_t, P],
     "b200rl_qntd_bwd": [P, P, P, LL, LL, P, P],
     "b200rl_dntd_fwd": [P, P, P, P, P, P, P, LL, P, LL, P, LL, LL, LL, I, I, D, D, D, P, P, P, P, P, c_size_t, P],
@@ -33,6 +35,7 @@ PROTOTYPES = {
     "b200rl_upgo_head_fwd": [P, P, P, P, P, P, LL, LL, LL, P, P, P, c_size_t, P],
     "b200rl_upgo_head_bwd": [P, P, P, P, P, LL, LL, LL, P, P],
     "b200rl_vtrace_fwd": [P, P, P, P, P, P, LL, LL, LL, D, D, D, D, D, P, P, P, P, P, c_size_t, P],
+    "b200rl_probe_copy": [P, P, LL, I, P],
     "b200rl_vtrace_bwd": [P, P, P, P, P, P, P, P, LL, LL, LL, P, P, P],
 }
 _RESTYPE = {"b200rl_workspace_bytes": c_size_t}

@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define B200RL_OK 0
 #ifndef B200RL_ERR_ARG
@@ -80,9 +81,21 @@ __device__ __forceinline__ bool grid_sum(float (&v)[K], double (&tot)[K], float*
     double acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += NT) {
+    // fixed summation order (deterministic); U rows of partials are loaded before any is consumed so the L2 latency of
+    // this serial tail is paid once, not once per row
+    constexpr int U = 8;
+    for (unsigned int b0 = threadIdx.x; b0 < gridDim.x; b0 += NT * U) {
+        float v_[U][K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] += (double)__ldcg(&part[(size_t)b * K + k]);
+        for (int u = 0; u < U; ++u) {
+            const unsigned int b = b0 + u * NT;
+#pragma unroll
+            for (int k = 0; k < K; ++k) v_[u][k] = (b < gridDim.x) ? __ldcg(&part[(size_t)b * K + k]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] += (double)v_[u][k];
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -135,6 +148,94 @@ __device__ __forceinline__ float row_lse(Ld ld, int n, int lane) {
     for (int j = lane; j < n; j += L) s += expf(ld(j) - m);
     if (L == 32) s = warp_sum(s);
     return m + logf(s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier, and bulk stores tracked by bulk groups.
+// Addresses and sizes must be multiples of 16 bytes.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (TMA store source)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of this library starts with pdl_prologue(): it lets the NEXT
+// kernel in the stream begin launching right away (its launch latency and prologue overlap this kernel's execution) and
+// then waits until all PREVIOUS kernels in the stream have completed and flushed their results -- so the usual stream
+// ordering of memory is preserved while the ~1.5 us launch gap between dependent kernels disappears.
+// Host side: launch_k() sets cudaLaunchAttributeProgrammaticStreamSerialization (B200RL_PDL=0 disables it).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+static inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200RL_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+static inline int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -46,6 +46,7 @@ struct UpgoArgs {
 
 template <int NT, int L>
 __global__ void __launch_bounds__(NT) upgo_fwd_kernel(UpgoArgs a, float* ws) {
+    pdl_prologue();
     const int lane = (L == 32) ? (threadIdx.x & 31) : 0;
     const long long s = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
                                   : (long long)blockIdx.x * NT + threadIdx.x;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(NT) upgo_fwd_kernel(UpgoArgs a, float* ws) {
 
 template <int NT, int L>
 __global__ void __launch_bounds__(NT) upgo_bwd_kernel(UpgoArgs a) {
+    pdl_prologue();
     const int lane = (L == 32) ? (threadIdx.x & 31) : 0;
     const long long row = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
                                     : (long long)blockIdx.x * NT + threadIdx.x;
@@ -120,6 +122,7 @@ struct VtArgs {
 // rows: one thread per (t,b) row; STAGED: NT consecutive rows of both logit tensors go through shared memory
 template <int NT, bool STAGED>
 __global__ void __launch_bounds__(NT) vtrace_rows_kernel(VtArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     const int N = a.N;
     const long long M = a.T * a.B;
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(NT) vtrace_rows_kernel(VtArgs a) {
 // large-N variant: warp per row
 template <int NT>
 __global__ void __launch_bounds__(NT) vtrace_rows_warp_kernel(VtArgs a) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     if (row >= a.T * a.B) return;
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(NT) vtrace_rows_warp_kernel(VtArgs a) {
 // adv_t = rho_pg*(r_t + g*vs_{t+1} - V_t) with vs_T = V_T (vtrace.py:126-128) and the three loss sums (:130-135).
 template <int TC, int NT, int CHUNK>
 __global__ void __launch_bounds__(NT) vtrace_scan_kernel(VtArgs a, float* ws) {
+    pdl_prologue();
     __shared__ float s_d[CHUNK][TC];   // delta, then x
     __shared__ float s_f[CHUNK][TC];   // gl*c
     __shared__ float s_vs[CHUNK + 1][TC];
@@ -245,6 +250,7 @@ __global__ void __launch_bounds__(NT) vtrace_scan_kernel(VtArgs a, float* ws) {
 // backward: grad z_j = g_pg*(-adv*w/M)*(1[j==a]-p_j) + g_ent*(w/M)*(-p_j*(logp_j+H)); grad V_t = g_val*dV, grad V_T = 0
 template <int NT, int MODE>  // 0 staged thread/row, 1 direct thread/row, 2 warp/row
 __global__ void __launch_bounds__(NT) vtrace_bwd_kernel(VtArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     constexpr int L = (MODE == 2) ? 32 : 1;
     const int lane = (MODE == 2) ? (threadIdx.x & 31) : 0;
@@ -318,11 +324,11 @@ extern "C" int b200rl_upgo_head_fwd(const float* logit, const long long* action,
     if (N > 64) {
         const int grid = div_up(TB, NT / 32);
         if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
-        upgo_fwd_kernel<NT, 32><<<grid, NT, 0, st>>>(a, workspace);
+        (void)launch_k(upgo_fwd_kernel<NT, 32>, grid, NT, 0, st, a, workspace);
     } else {
         const int grid = div_up(TB, NT);
         if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
-        upgo_fwd_kernel<NT, 1><<<grid, NT, 0, st>>>(a, workspace);
+        (void)launch_k(upgo_fwd_kernel<NT, 1>, grid, NT, 0, st, a, workspace);
     }
     return (int)cudaGetLastError();
 }
@@ -336,8 +342,8 @@ extern "C" int b200rl_upgo_head_bwd(const float* logit, const long long* action,
     a.K = (int)K; a.N = (int)N; a.g_loss = g_loss; a.grad_logit = grad_logit;
     constexpr int NT = 128;
     cudaStream_t st = (cudaStream_t)stream;
-    if (N > 64) upgo_bwd_kernel<NT, 32><<<div_up(TB * K, NT / 32), NT, 0, st>>>(a);
-    else upgo_bwd_kernel<NT, 1><<<div_up(TB * K, NT), NT, 0, st>>>(a);
+    if (N > 64) (void)launch_k(upgo_bwd_kernel<NT, 32>, div_up(TB * K, NT / 32), NT, 0, st, a);
+    else (void)launch_k(upgo_bwd_kernel<NT, 1>, div_up(TB * K, NT), NT, 0, st, a);
     return (int)cudaGetLastError();
 }
 
@@ -368,20 +374,20 @@ extern "C" int b200rl_vtrace_fwd(const float* target_output, const float* behavi
     const long long M = T * B;
     const int mode = vt_mode(a);
     if (mode == 0) {
-        vtrace_rows_kernel<NT, true><<<div_up(M, NT), NT, (size_t)2 * NT * a.N * sizeof(float), st>>>(a);
+        (void)launch_k(vtrace_rows_kernel<NT, true>, div_up(M, NT), NT, (size_t)2 * NT * a.N * sizeof(float), st, a);
     } else if (mode == 1) {
-        vtrace_rows_kernel<NT, false><<<div_up(M, NT), NT, 0, st>>>(a);
+        (void)launch_k(vtrace_rows_kernel<NT, false>, div_up(M, NT), NT, 0, st, a);
     } else {
-        vtrace_rows_warp_kernel<NT><<<div_up(M, NT / 32), NT, 0, st>>>(a);
+        (void)launch_k(vtrace_rows_warp_kernel<NT>, div_up(M, NT / 32), NT, 0, st, a);
     }
     int rc = (int)cudaGetLastError();
     if (rc) return rc;
     if (B >= 16 * 296) {
         if ((size_t)(WS_CTRL_WORDS + 3 * div_up(B, 16)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
-        vtrace_scan_kernel<16, 128, 64><<<div_up(B, 16), 128, 0, st>>>(a, workspace);
+        (void)launch_k(vtrace_scan_kernel<16, 128, 64>, div_up(B, 16), 128, 0, st, a, workspace);
     } else {
         if ((size_t)(WS_CTRL_WORDS + 3 * div_up(B, 8)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
-        vtrace_scan_kernel<8, 64, 64><<<div_up(B, 8), 64, 0, st>>>(a, workspace);
+        (void)launch_k(vtrace_scan_kernel<8, 64, 64>, div_up(B, 8), 64, 0, st, a, workspace);
     }
     return (int)cudaGetLastError();
 }
@@ -402,8 +408,8 @@ extern "C" int b200rl_vtrace_bwd(const float* target_output, const long long* ac
     constexpr int NT = 128;
     const long long M = T * B;
     const int mode = vt_mode(a);
-    if (mode == 0) vtrace_bwd_kernel<NT, 0><<<div_up(M, NT), NT, (size_t)NT * a.N * sizeof(float), st>>>(a);
-    else if (mode == 1) vtrace_bwd_kernel<NT, 1><<<div_up(M, NT), NT, 0, st>>>(a);
-    else vtrace_bwd_kernel<NT, 2><<<div_up(M, NT / 32), NT, 0, st>>>(a);
+    if (mode == 0) (void)launch_k(vtrace_bwd_kernel<NT, 0>, div_up(M, NT), NT, (size_t)NT * a.N * sizeof(float), st, a);
+    else if (mode == 1) (void)launch_k(vtrace_bwd_kernel<NT, 1>, div_up(M, NT), NT, 0, st, a);
+    else (void)launch_k(vtrace_bwd_kernel<NT, 2>, div_up(M, NT / 32), NT, 0, st, a);
     return (int)cudaGetLastError();
 }

@@ -69,6 +69,7 @@ struct QntdArgs {
 
 template <int NT>
 __global__ void __launch_bounds__(NT) qntd_fwd_kernel(QntdArgs a, float* ws) {
+    pdl_prologue();
     const long long b = (long long)blockIdx.x * NT + threadIdx.x;
     float acc[1] = {0.f};
     if (b < a.B) {
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(NT) qntd_fwd_kernel(QntdArgs a, float* ws) {
 
 __global__ void qntd_bwd_kernel(const float* __restrict__ dq, const long long* __restrict__ action,
                                 const float* __restrict__ g_loss, long long B, int N, float* __restrict__ grad_q) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * N) return;
     const long long b = i / N;
@@ -148,6 +150,7 @@ struct DntdArgs {
 
 template <int NT>
 __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
+    pdl_prologue();
     extern __shared__ float s_proj[];  // [NT/32][n_atom]
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * (NT / 32) + wid;
@@ -202,6 +205,7 @@ __global__ void dntd_bwd_kernel(const float* __restrict__ dist, const long long*
                                 const float* __restrict__ proj, const float* __restrict__ weight,
                                 long long weight_stride, const float* __restrict__ g_loss, long long R, int N,
                                 int n_atom, float* __restrict__ grad_dist) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_row = (long long)N * n_atom;
     if (i >= R * per_row) return;
@@ -240,6 +244,7 @@ struct LamArgs {
 
 template <int TC, int NT, int CHUNK, int MODE, int HEAD>
 __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
+    pdl_prologue();
     __shared__ float s_r[CHUNK][TC];
     __shared__ float s_m[CHUNK][TC];
     __shared__ float s_disc[CHUNK][TC];
@@ -321,6 +326,7 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
 // out[i] = (*g) * in[i]  -- backward of the heads that saved their unit-upstream gradient in the forward pass
 __global__ void scale_kernel(const float* __restrict__ g, const float* __restrict__ in, float* __restrict__ out,
                              long long n) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (*g) * in[i];
 }
@@ -352,7 +358,7 @@ extern "C" int b200rl_qntd_fwd(const float* q, const float* next_n_q, const long
     constexpr int NT = 128;
     const int grid = div_up(B, NT);
     if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
-    qntd_fwd_kernel<NT><<<grid, NT, 0, (cudaStream_t)stream>>>(a, workspace);
+    (void)launch_k(qntd_fwd_kernel<NT>, grid, NT, 0, (cudaStream_t)stream, a, workspace);
     return (int)cudaGetLastError();
 }
 
@@ -360,7 +366,7 @@ extern "C" int b200rl_qntd_bwd(const float* dq_saved, const long long* action, c
                                long long N, float* grad_q, void* stream) {
     if (B <= 0 || N < 1 || !dq_saved || !action || !grad_q) return B200RL_ERR_ARG;
     const int grid = div_up(B * N, 256);
-    qntd_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dq_saved, action, g_loss, B, (int)N, grad_q);
+    (void)launch_k(qntd_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dq_saved, action, g_loss, B, (int)N, grad_q);
     return (int)cudaGetLastError();
 }
 
@@ -386,7 +392,7 @@ extern "C" int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, cons
     if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
     const size_t sm = (size_t)(NT / 32) * n_atom * sizeof(float);
     if (sm > 48 * 1024) return B200RL_ERR_ARG;
-    dntd_fwd_kernel<NT><<<grid, NT, sm, (cudaStream_t)stream>>>(a, workspace);
+    (void)launch_k(dntd_fwd_kernel<NT>, grid, NT, sm, (cudaStream_t)stream, a, workspace);
     return (int)cudaGetLastError();
 }
 
@@ -395,7 +401,7 @@ extern "C" int b200rl_dntd_bwd(const float* dist, const long long* act, const fl
                                float* grad_dist, void* stream) {
     if (R <= 0 || N < 1 || n_atom < 2 || !dist || !act || !proj_saved || !grad_dist) return B200RL_ERR_ARG;
     const int grid = div_up(R * N * n_atom, 256);
-    dntd_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dist, act, proj_saved, weight, weight_stride, g_loss, R,
+    (void)launch_k(dntd_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dist, act, proj_saved, weight, weight_stride, g_loss, R,
                                                             (int)N, n_atom, grad_dist);
     return (int)cudaGetLastError();
 }
@@ -403,9 +409,9 @@ extern "C" int b200rl_dntd_bwd(const float* dist, const long long* act, const fl
 template <int MODE, int HEAD>
 static int launch_lambda(const LamArgs& a, float* ws, cudaStream_t st) {
     if (a.B >= 16 * 296) {
-        lambda_scan_kernel<16, 128, 64, MODE, HEAD><<<div_up(a.B, 16), 128, 0, st>>>(a, ws);
+        (void)launch_k(lambda_scan_kernel<16, 128, 64, MODE, HEAD>, div_up(a.B, 16), 128, 0, st, a, ws);
     } else {
-        lambda_scan_kernel<8, 64, 128, MODE, HEAD><<<div_up(a.B, 8), 64, 0, st>>>(a, ws);
+        (void)launch_k(lambda_scan_kernel<8, 64, 128, MODE, HEAD>, div_up(a.B, 8), 64, 0, st, a, ws);
     }
     return (int)cudaGetLastError();
 }
@@ -435,6 +441,6 @@ extern "C" int b200rl_td_lambda_fwd(const float* value, const float* reward, con
 extern "C" int b200rl_scale(const float* g, const float* in, float* out, long long n, void* stream) {
     if (n < 0 || !g || (n > 0 && (!in || !out))) return B200RL_ERR_ARG;
     if (n == 0) return B200RL_OK;
-    scale_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(g, in, out, n);
+    (void)launch_k(scale_kernel, div_up(n, 256), 256, 0, (cudaStream_t)stream, g, in, out, n);
     return (int)cudaGetLastError();
 }

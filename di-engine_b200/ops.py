@@ -121,6 +121,23 @@ def gae_(value, next_value, reward, done, traj_flag, gamma, lambda_, agents, mas
 # ----------------------------------------------------------------------------------------------------------------
 # ppo
 # ----------------------------------------------------------------------------------------------------------------
+# The forward pass also writes the gradients for the upstream gradients it expects (the loss weights of the training
+# loop, remembered on the device from the previous backward pass); backward() verifies them on the device and only
+# recomputes on a mismatch -- exact for any upstream gradient, no host sync.  False: separate backward kernel always.
+PPO_FUSED_BACKWARD = True
+_PPO_HINT = {}
+
+
+def ppo_hint(device):
+    """Device-resident expectation of (d total/d policy_loss, d/d value_loss, d/d entropy_loss, d/d kl_div)."""
+    key = device.index
+    h = _PPO_HINT.get(key)
+    if h is None:
+        h = torch.tensor([1.0, 0.5, -0.01, 0.0], dtype=torch.float32, device=device)
+        _PPO_HINT[key] = h
+    return h
+
+
 class PPOFunction(torch.autograd.Function):
     """Outputs: policy_loss, value_loss, entropy_loss, kl_div (differentiable 0-dim) and the raw 8-float result vector
     (non differentiable; [4]=approx_kl, [5]=clipfrac)."""
@@ -128,17 +145,33 @@ class PPOFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre, S, G, N,
                 clip_ratio, use_value_clip, dual_clip, kl_type):
-        out = torch.empty(8, dtype=torch.float32, device=logit_new.device)
-        with torch.cuda.device(logit_new.device):
-            ws = workspace(logit_new.device)
-            rc = lib().b200rl_ppo_fwd(
-                ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old), ptr(adv),
-                ptr(return_), ptr(weight), S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, ptr(out), ptr(ws),
-                ws.numel() * 4, stream_ptr()
-            )
-        _lib.check(rc, 'b200rl_ppo_fwd')
+        dev = logit_new.device
+        out = torch.empty(8, dtype=torch.float32, device=dev)
+        L = lib()
+        tensors = (ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old),
+                   ptr(adv), ptr(return_), ptr(weight))
+        cfg = (S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type)
+        ctx.fused = False
+        want_grad = PPO_FUSED_BACKWARD and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        with torch.cuda.device(dev):
+            ws = workspace(dev)
+            if want_grad:
+                grad_logit = torch.empty_like(logit_new)
+                grad_value = torch.empty_like(value_new)
+                if L.b200rl_ppo_fused_supported(*tensors, ptr(grad_logit), G, N):
+                    g_used = torch.empty(4, dtype=torch.float32, device=dev)
+                    rc = L.b200rl_ppo_fwd_grad(*tensors, *cfg, ptr(ppo_hint(dev)), ptr(g_used), ptr(out),
+                                               ptr(grad_logit), ptr(grad_value), ptr(ws), ws.numel() * 4,
+                                               stream_ptr())
+                    _lib.check(rc, 'b200rl_ppo_fwd_grad')
+                    ctx.fused = True
+                    ctx.spec = (grad_logit, grad_value, g_used)
+            if not ctx.fused:
+                rc = L.b200rl_ppo_fwd(*tensors, *cfg, ptr(out), ptr(ws), ws.numel() * 4, stream_ptr())
+                _lib.check(rc, 'b200rl_ppo_fwd')
         ctx.save_for_backward(logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre)
-        ctx.cfg = (S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type)
+        ctx.cfg = cfg
+        ctx.bwd_calls = 0
         ctx.mark_non_differentiable(out)
         p, v, e, k = out[0], out[1], out[2], out[3]
         return p, v, e, k, out
@@ -146,18 +179,25 @@ class PPOFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_p, g_v, g_e, g_k, _g_out):
         logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre = ctx.saved_tensors
-        S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type = ctx.cfg
-        grad_logit = torch.empty_like(logit_new)
-        grad_value = torch.empty_like(value_new)
+        dev = logit_new.device
         kp, pp = _g(g_p)
         kv, pv = _g(g_v)
         ke, pe = _g(g_e)
         kk, pk = _g(g_k)
-        with torch.cuda.device(logit_new.device):
+        first = ctx.bwd_calls == 0
+        ctx.bwd_calls += 1
+        if ctx.fused and first:
+            grad_logit, grad_value, g_used = ctx.spec  # valid if the expectation held; the kernel checks on the device
+            p_used, p_hint = ptr(g_used), ptr(ppo_hint(dev))
+        else:  # no fused forward, or a repeated backward (the first call's buffers may now belong to .grad)
+            grad_logit = torch.empty_like(logit_new)
+            grad_value = torch.empty_like(value_new)
+            p_used, p_hint = None, None
+        with torch.cuda.device(dev):
             rc = lib().b200rl_ppo_bwd(
                 ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old), ptr(adv),
-                ptr(return_), ptr(weight), S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, pp, pv, pe, pk,
-                ptr(grad_logit), ptr(grad_value), stream_ptr()
+                ptr(return_), ptr(weight), *ctx.cfg, pp, pv, pe, pk, p_used, p_hint, ptr(grad_logit), ptr(grad_value),
+                stream_ptr()
             )
         _lib.check(rc, 'b200rl_ppo_bwd')
         return (grad_logit, grad_value) + (None, ) * 14

@@ -65,13 +65,31 @@ B200RL_API int b200rl_ppo_fwd(const float* logit_new, const float* logit_old, co
                    double clip_ratio, int use_value_clip, double dual_clip, int kl_type, float* out,
                    float* workspace, size_t workspace_bytes, void* stream);
 /* gradients of  g_policy*policy_loss + g_value*value_loss + g_entropy*entropy_loss + g_kl*kl_div  w.r.t.
- * logit_new (S*G, N) and value_new (S); autograd tie rules of torch.min/max/clamp reproduced (ppo.py:208-216,:269-272) */
+ * logit_new (S*G, N) and value_new (S); autograd tie rules of torch.min/max/clamp reproduced (ppo.py:208-216,:269-272).
+ * g_used / g_hint (both nullable) belong to the fused forward below: when g_used is given and equals the four actual
+ * upstream values bit for bit, the gradients already sitting in grad_* are valid and the launch does nothing; g_hint
+ * (4 floats) is refreshed with the actual upstream values so the next forward pass can expect them. */
 B200RL_API int b200rl_ppo_bwd(const float* logit_new, const float* logit_old, const float* logit_pretrained,
                    const long long* action, const float* value_new, const float* value_old, const float* adv,
                    const float* return_, const float* weight, long long S, long long G, long long N,
                    double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* g_policy,
-                   const float* g_value, const float* g_entropy, const float* g_kl, float* grad_logit_new,
-                   float* grad_value_new, void* stream);
+                   const float* g_value, const float* g_entropy, const float* g_kl, const float* g_used,
+                   float* g_hint, float* grad_logit_new, float* grad_value_new, void* stream);
+/* Fused forward: the losses of b200rl_ppo_fwd AND the gradients of b200rl_ppo_bwd for the EXPECTED upstream gradients
+ * g_expected[0..3] (policy, value, entropy, kl; device floats -- the loss weights of the training loop), in one pass
+ * over the batch.  g_used[0..3] records what was applied; pass it to b200rl_ppo_bwd, which verifies the expectation on
+ * the device and only recomputes when it was wrong, so the pair is exact for any upstream gradient.
+ * Only available where b200rl_ppo_fused_supported(...) returns 1 (G == 1, N <= 32, 16-byte aligned tensors). */
+B200RL_API int b200rl_ppo_fwd_grad(const float* logit_new, const float* logit_old, const float* logit_pretrained,
+                        const long long* action, const float* value_new, const float* value_old, const float* adv,
+                        const float* return_, const float* weight, long long S, long long G, long long N,
+                        double clip_ratio, int use_value_clip, double dual_clip, int kl_type,
+                        const float* g_expected, float* g_used, float* out, float* grad_logit_new,
+                        float* grad_value_new, float* workspace, size_t workspace_bytes, void* stream);
+B200RL_API int b200rl_ppo_fused_supported(const float* logit_new, const float* logit_old, const float* logit_pretrained,
+                               const long long* action, const float* value_new, const float* value_old,
+                               const float* adv, const float* return_, const float* weight,
+                               const float* grad_logit_new, long long G, long long N);
 
 /* ---- q_nstep_td_error / q_nstep_td_error_with_rescale: ding/rl_utils/td.py:649-719, :810-867, nstep_return :230-286
  * q, next_n_q: (B, N); action, next_n_action: (B) int64; reward: (nstep, B), or (B) when cum_reward; done: (B);
@@ -141,6 +159,9 @@ B200RL_API int b200rl_vtrace_bwd(const float* target_output, const long long* ac
                       const float* cpg_saved, const float* dv_saved, const float* g_policy, const float* g_value,
                       const float* g_entropy, long long T, long long B, long long N, float* grad_target_output,
                       float* grad_value, void* stream);
+
+/* ---- calibration probe (not an operator): persistent float4 copy of n_floats (multiple of 4) -------------------- */
+B200RL_API int b200rl_probe_copy(const float* src, float* dst, long long n_floats, int ctas_per_sm, void* stream);
 
 #ifdef __cplusplus
 }

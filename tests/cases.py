@@ -437,5 +437,8 @@ def compare(res, ref, rtol=1e-5, atol=1e-5, exact=False):
         if exact:
             assert np.array_equal(a, b, equal_nan=True), (k, float(np.max(np.abs(a.astype(np.float64) - b))))
         else:
-            ok = np.allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
-            assert ok, (k, float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))))
+            # gradients of a mean over S samples scale like 1/S: make the absolute term relative to the tensor's scale
+            # so that the check stays meaningful at S = 524288 (|grad| ~ 1e-6)
+            scale = float(np.max(np.abs(b))) if (k.startswith('grad_') and b.size) else 1.0
+            ok = np.allclose(a, b, rtol=rtol, atol=atol * scale, equal_nan=True)
+            assert ok, (k, float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))), scale)

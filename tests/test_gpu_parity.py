@@ -215,3 +215,63 @@ def test_cuda_graph_capture_of_the_learner_step():
     s.synchronize()
     for k in eager:
         assert torch.equal(outs[k], eager[k]), k
+
+
+def _ppo_with_mix(t, p, mix, device=DEV, retain=False):
+    td = cases.prepare('ppo', t, device)
+    data = b2.ppo_data(*[td[k] for k in ('logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv',
+                                           'return_', 'weight', 'logit_pretrained')])
+    loss, info = b2.ppo_error(data, **p)
+    total = sum(c * l for c, l in zip(mix, loss))
+    total.backward(retain_graph=retain)
+    return td, loss, total
+
+
+def _ppo_oracle_with_mix(t, p, mix):
+    tt = cases.prepare('ppo', t)
+    out = rl_oracle.ppo_error(**tt, **p)
+    sum(c * l for c, l in zip(mix, out[:4])).backward()
+    return tt
+
+
+def test_ppo_fused_backward_is_exact_for_any_upstream_gradient():
+    """The forward pass pre-computes gradients for the loss mix it expects (learned from the previous backward);
+    a different mix at backward time must still give the right gradients (device-side check + recompute)."""
+    from di_engine_b200 import ops
+    assert ops.PPO_FUSED_BACKWARD
+    op, t, p = cases.ppo_case(77, 4099, 6, weight='tensor', pretrained=True, kl_type='k2')
+    for mix in ([1.0, 0.5, -0.01, 0.3], [1.0, 0.5, -0.01, 0.3], [0.7, 2.0, 0.05, -1.5], [0.0, 1.0, 0.0, 0.0],
+                [0.7, 2.0, 0.05, -1.5]):
+        want = _ppo_oracle_with_mix(t, p, mix)
+        td, _, _ = _ppo_with_mix(t, p, mix)
+        for k in ('logit_new', 'value_new'):
+            a, b = td[k].grad.cpu().numpy(), want[k].grad.numpy()
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max()), (mix, k)
+    # hint now equals the last mix: the expected path (no recompute) must give the same numbers
+    td2, _, _ = _ppo_with_mix(t, p, [0.7, 2.0, 0.05, -1.5])
+    ga, gb = td2['logit_new'].grad, td['logit_new'].grad
+    assert torch.allclose(ga, gb, rtol=1e-5, atol=1e-5 * float(gb.abs().max()))
+
+
+def test_ppo_repeated_backward_and_unfused_path_agree():
+    from di_engine_b200 import ops
+    op, t, p = cases.ppo_case(78, 1500, 5, weight='tensor')
+    mix = [1.0, 0.5, -0.01, 0.0]
+    td, loss, total = _ppo_with_mix(t, p, mix, retain=True)
+    g1 = td['logit_new'].grad.clone()
+    total.backward()  # second backward through the same graph accumulates the same gradient again
+    assert torch.allclose(td['logit_new'].grad, 2 * g1, rtol=1e-6, atol=0)
+    ops.PPO_FUSED_BACKWARD = False
+    try:
+        td3, _, _ = _ppo_with_mix(t, p, mix)
+    finally:
+        ops.PPO_FUSED_BACKWARD = True
+    assert torch.allclose(td3['logit_new'].grad, g1, rtol=1e-6, atol=1e-12)
+    assert torch.allclose(td3['value_new'].grad, td['value_new'].grad / 2, rtol=1e-6, atol=1e-12)
+    with torch.no_grad():
+        tn = cases.prepare('ppo', t, DEV)
+        data = b2.ppo_data(*[tn[k].detach() if isinstance(tn[k], torch.Tensor) else tn[k] for k in (
+            'logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv', 'return_', 'weight',
+            'logit_pretrained')])
+        l2, _ = b2.ppo_error(data, **p)
+    assert torch.allclose(l2.policy_loss, loss.policy_loss, rtol=1e-6)

@@ -42,7 +42,7 @@ def _header_decls():
 
 def test_library_exports_every_declared_symbol():
     decls = _header_decls()
-    assert len(decls) >= 17
+    assert len(decls) >= 19
     lib = _lib.load()
     for name in decls:
         assert hasattr(lib, name), name
@@ -158,7 +158,7 @@ class _RecordingLib:
             for a, ty in zip(args, proto):
                 ty.from_param(a)  # raises on a type ctypes could not marshal
             self.calls.append(name)
-            return 0
+            return 1 if name == 'b200rl_ppo_fused_supported' else 0
 
         if name == 'b200rl_workspace_bytes':
             return lambda: 1 << 20
@@ -183,7 +183,7 @@ def dry(monkeypatch):
 
 EXPECTED_CALLS = {
     'gae': ['b200rl_gae'],
-    'ppo': ['b200rl_ppo_fwd', 'b200rl_ppo_bwd'],
+    'ppo': ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad', 'b200rl_ppo_bwd'],
     'qntd': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'qntd_rescale': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'dntd': ['b200rl_dntd_fwd', 'b200rl_dntd_bwd'],

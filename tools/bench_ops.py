@@ -1,0 +1,118 @@
+"""Per-operator micro-benchmarks at the BASELINE.json configs (device-resident inputs, CUDA-graph replay over rotated
+buffer sets larger than L2, CUDA events).  Prints one JSON line per op: us per call and algorithmic GB/s.
+
+    python tools/bench_ops.py [gae] [qntd] [dntd] [vtrace] [tdl] [upgo]
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import di_engine_b200 as b2  # noqa: E402
+from tests import cases  # noqa: E402
+
+DEV = 'cuda:0'
+
+
+def timed(fn_sets, reps=50):
+    """fn_sets: list of zero-arg callables (one per buffer set). Returns us per call."""
+    main = torch.cuda.Stream()
+    with torch.cuda.stream(main):
+        for f in fn_sets:
+            f()
+            f()
+        main.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=main):
+            for f in fn_sets:
+                f()
+        for _ in range(3):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        main.synchronize()
+        e0.record(main)
+        for _ in range(reps):
+            g.replay()
+        e1.record(main)
+        main.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * len(fn_sets))
+
+
+def report(name, us, alg_bytes, units, unit_name):
+    print(json.dumps({'op': name, 'us_per_call': round(us, 3), 'alg_GBps': round(alg_bytes / us / 1e3, 1),
+                      'units_per_s': units / (us * 1e-6), 'unit': unit_name}))
+
+
+def bench_gae(T=128, B=4096, nsets=12):
+    from di_engine_b200 import ops
+    sets = []
+    for i in range(nsets):
+        _, t, p = cases.gae_case(i, T, B, p_done=0.01)
+        t = {k: v.to(DEV) for k, v in t.items()}
+        sets.append(lambda t=t: ops.gae_(t['value'], t['next_value'], t['reward'], t['done'], t['traj_flag'], 0.99,
+                                         0.95, 1))
+    report('gae T=%d B=%d' % (T, B), timed(sets), 24 * T * B, T * B, 'transitions')
+
+
+def fwd_bwd(op, mk, nsets, mix):
+    sets = []
+    for i in range(nsets):
+        _, t, p = mk(i)
+        td = cases.prepare(op, t, DEV)
+
+        def run(td=td, p=p):
+            for k in cases.GRAD_INPUTS[op]:
+                td[k].grad = None
+            res = cases.run_api  # noqa: F841
+            return None
+        sets.append((td, p))
+    return sets
+
+
+def bench_api(name, op, mk, alg_bytes, units, unit_name, nsets=4, reps=50):
+    """fwd+bwd through the public API, eager (the API reads flags/infos on the host for some ops), CUDA events."""
+    data = []
+    for i in range(nsets):
+        _, t, p = mk(i)
+        data.append((t, p))
+    for t, p in data:
+        cases.run_api(b2.rl_utils, op, t, p, device=DEV)
+    dev_sets = [(cases.prepare(op, t, DEV), p) for t, p in data]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for r in range(reps):
+        t, p = data[r % nsets]
+        cases.run_api(b2.rl_utils, op, t, p, device=DEV)
+    e1.record()
+    torch.cuda.synchronize()
+    report(name + ' (public API, eager, incl. H2D of inputs)', e0.elapsed_time(e1) * 1e3 / reps, alg_bytes, units,
+           unit_name)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['gae', 'qntd', 'dntd', 'vtrace', 'tdl', 'upgo']
+    b2.rl_utils.td.CHECK_DIST_POSITIVE = False
+    if 'gae' in which:
+        bench_gae()
+        bench_gae(T=1024, B=64, nsets=8)
+    if 'qntd' in which:
+        bench_api('q_nstep_td_error B=512 N=6 n=3', 'qntd',
+                  lambda i: cases.qntd_case(i, 512, 6, 3, value_gamma='tensor', gamma=0.99, done='bern'), 120 * 512,
+                  512, 'samples')
+    if 'dntd' in which:
+        bench_api('dist_nstep_td_error B=512 N=6 atoms=51 n=3', 'dntd',
+                  lambda i: cases.dntd_case(i, 512, 6, 51, 3, gamma=0.99, value_gamma='tensor'), 1670 * 512, 512,
+                  'samples')
+    if 'vtrace' in which:
+        bench_api('vtrace T=64 B=8192 N=6', 'vtrace',
+                  lambda i: cases.vtrace_case(i, 64, 8192, 6, gamma=0.99, lambda_=0.95), 96 * 64 * 8192, 64 * 8192,
+                  'transitions', reps=20)
+    if 'tdl' in which:
+        bench_api('td_lambda T=1024 B=64', 'td_lambda', lambda i: cases.td_lambda_case(i, 1024, 64), 16 * 1024 * 64,
+                  1024 * 64, 'transitions')
+    if 'upgo' in which:
+        bench_api('upgo T=256 B=256 N=256', 'upgo', lambda i: cases.upgo_case(i, 256, 256, 256),
+                  (8 * 256 + 20) * 65536, 65536, 'transitions', reps=10)
