@@ -311,7 +311,8 @@ def run_gpu(args):
     step_bytes = ALG_BYTES_PER_TR['step'] * T_LEN * B_COLS
     side = torch.cuda.Stream()
     main = torch.cuda.Stream()
-    packed = [torch.zeros(8, device=dev) for _ in range(NSETS)]
+    from di_engine_b200.parallel import LossAllReduce
+    reducers = [LossAllReduce(6, dev) for _ in range(NSETS)] if world > 1 else None
 
     # ---- correctness guard: first set against the CPU oracle on rank 0 (outside every timed region) ----------------
     if rank == 0:
@@ -326,31 +327,66 @@ def run_gpu(args):
         s0.b['next_value'].copy_(s0.nv0)
 
     # ---- capture one graph per buffer set -------------------------------------------------------------------------
+    # N > 1: the graph of step j also carries, on a forked branch, the all-reduce of the loss scalars of step j-1
+    # (software-pipelined: the collective of one step overlaps the kernels of the next; one graph launch per step)
     graphs = []
+    collective_mode = 'none'
     with torch.cuda.stream(main):
         for s in sets:
             s()
             s()
+        if world > 1:
+            for r in reducers:
+                r.reduce()
         main.synchronize()
-        for s in sets:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=main):
-                s()
-            graphs.append(g)
+
+        def capture(with_collective):
+            gs = []
+            for j, s in enumerate(sets):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=main):
+                    if with_collective:
+                        side.wait_stream(main)
+                        with torch.cuda.stream(side):
+                            prev = (j - 1) % NSETS
+                            reducers[prev].buf.copy_(sets[prev].out[:6], non_blocking=True)
+                            reducers[prev].reduce()
+                    s()
+                    if with_collective:
+                        main.wait_stream(side)
+                gs.append(g)
+            return gs
+
+        if world > 1:
+            try:
+                graphs = capture(True)
+                collective_mode = 'in-graph'
+            except Exception as e:  # NCCL capture unavailable: keep the collective eager on the side stream
+                if rank == 0:
+                    print('bench: NCCL graph capture failed (%s); eager side-stream all-reduce' % e, file=sys.stderr)
+                torch.cuda.synchronize()
+                graphs = capture(False)
+                collective_mode = 'eager'
+        else:
+            graphs = capture(False)
     torch.cuda.synchronize()
 
     def device_loop(n):
         for i in range(n):
             j = i % NSETS
             graphs[j].replay()
-            if world > 1:
+            if collective_mode == 'eager':
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
                 with torch.cuda.stream(side):
-                    packed[j].copy_(sets[j].out, non_blocking=True)
-                    dist.all_reduce(packed[j])
-        if world > 1:
+                    reducers[j].buf.copy_(sets[j].out[:6], non_blocking=True)
+                    reducers[j].reduce()  # one NCCL all-reduce (sum) + divide: mean of rank means
+        if collective_mode == 'in-graph':  # the last step's scalars (every earlier one rode in the next step's graph)
+            j = (n - 1) % NSETS
+            reducers[j].buf.copy_(sets[j].out[:6], non_blocking=True)
+            reducers[j].reduce()
+        elif collective_mode == 'eager':
             main.wait_stream(side)
 
     with torch.cuda.stream(main):
@@ -447,7 +483,7 @@ def run_gpu(args):
                 'l2_policy': 'inputs rotated over %d buffer sets of 67 MB (> 126 MB L2) between consecutive steps' %
                              NSETS,
                 'launch': 'CUDA graph replay of 3 kernels per step (%s)' % ', '.join(names),
-                'collective': 'none' if world == 1 else 'one NCCL all-reduce of 8 packed loss floats per step, side stream',
+                'collective': 'none' if world == 1 else 'one NCCL all-reduce of 6 packed loss floats per step (%s), overlapping the next step' % collective_mode,
             },
             'roofline': {
                 'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
@@ -466,9 +502,17 @@ def run_gpu(args):
             'gpu_launches': 3 * K,
             'clocks': clocks,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # graphs that captured NCCL work must be gone before the communicator is torn down; then leave without waiting on
+        # NCCL's own teardown (a destroy_process_group after captured collectives has been seen to hang)
+        del graphs
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_reference(args):
