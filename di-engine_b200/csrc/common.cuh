@@ -35,6 +35,16 @@ __device__ __forceinline__ float4 ldg_stream4(const float4* p) { return __ldcs(p
 __device__ __forceinline__ void stg_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void stg_stream4(float4* p, float4 v) { __stcs(p, v); }
 
+// release/acquire fence at GPU scope (MEMBAR.ALL.GPU) -- what the "write results, then signal a counter" patterns of this
+// library need; __threadfence() is the sequentially-consistent flavour (MEMBAR.SC.GPU), measurably slower under load
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -50,10 +60,12 @@ __device__ __forceinline__ float warp_max(float v) {
 // elsewhere) thread 0 holds the grid totals in tot[0..K).  `ws` must hold WS_CTRL_WORDS + gridDim.x*K floats,
 // control word `slot` must be zero on entry and is reset to zero on exit (stream-ordered reuse).
 template <int K, int NT>
-__device__ __forceinline__ bool grid_sum(float (&v)[K], double (&tot)[K], float* ws, int slot) {
+__device__ __forceinline__ bool grid_sum(float (&v)[K], double (&tot)[K], float* ws, int slot,
+                                         unsigned long long* trace = nullptr) {
     __shared__ float s_part[K][NT / 32];
     __shared__ double s_tot[K][NT / 32];
     __shared__ bool s_last;
+    __shared__ volatile unsigned int s_dep;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -61,23 +73,32 @@ __device__ __forceinline__ bool grid_sum(float (&v)[K], double (&tot)[K], float*
         if (lane == 0) s_part[k][wid] = r;
     }
     __syncthreads();
+    if (trace && threadIdx.x == 0) trace[0] = gtimer();
     float* part = ws + WS_CTRL_WORDS;
     unsigned int* ctrl = reinterpret_cast<unsigned int*>(ws);
     if (threadIdx.x == 0) {
+        // Publish this CTA's partial sums with RETURNING atomics (performed at L2, so they are visible device-wide once
+        // they return) and make the ticket depend on their return values.  This replaces "plain stores + gpu-scope
+        // fence + ticket": the fence had to wait for every outstanding store of the SM (the gradient tiles of the fused
+        // kernels) and was measured at ~3.3 us on the critical path of the grid reduction.
+        unsigned int dep = 0u;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             float r = 0.f;
 #pragma unroll
             for (int w = 0; w < NT / 32; ++w) r += s_part[k][w];
-            part[(size_t)blockIdx.x * K + k] = r;
+            dep |= atomicExch(reinterpret_cast<unsigned int*>(&part[(size_t)blockIdx.x * K + k]), __float_as_uint(r));
         }
-        __threadfence();
-        unsigned int ticket = atomicAdd(&ctrl[slot], 1u);
+        s_dep = dep;  // a real use of the returned values: instructions issue in order, so everything below waits here
+        asm volatile("" ::: "memory");
+        if (trace) trace[1] = gtimer();
+        unsigned int ticket = atomicAdd(&ctrl[slot], 1u);  // issued only after the exchanges returned
+        if (trace) trace[2] = gtimer();
         s_last = (ticket == gridDim.x - 1);
     }
     __syncthreads();
     if (!s_last) return false;
-    __threadfence();
+    if (trace && threadIdx.x == 0) trace[3] = gtimer();
     double acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
@@ -116,6 +137,73 @@ __device__ __forceinline__ bool grid_sum(float (&v)[K], double (&tot)[K], float*
         ctrl[slot] = 0u;
     }
     return true;
+}
+
+// Two-launch variant of the grid reduction for the big streaming kernels: every CTA just stores its K partial sums (no
+// atomics, no fence, no ticket -- kernel completion publishes them) and finalize_sums_kernel, a single small CTA launched
+// right behind, adds them in a fixed order (deterministic), scales, writes the results and clears `n_clear` control
+// words.  Measured on B200: the in-kernel ticket path costs the big kernels ~5 us of serial tail (3 us for the partial
+// publication to become visible behind the SM's outstanding traffic, 2 us for the last CTA); a dependent tiny launch
+// costs ~1 us.
+template <int K, int NT>
+__device__ __forceinline__ void grid_store_partials(float (&v)[K], float* ws) {
+    __shared__ float s_part2[K][NT / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float r = warp_sum(v[k]);
+        if (lane == 0) s_part2[k][wid] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        float r = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) r += s_part2[threadIdx.x][w];
+        ws[WS_CTRL_WORDS + (size_t)blockIdx.x * K + threadIdx.x] = r;
+    }
+}
+
+struct FinalizeArgs {
+    double scale[8];     // out[k] = sum_k * scale[k]
+    int k;               // number of sums
+    int n_blocks;        // partial rows
+    int clear_ctrl_from, clear_ctrl_n;  // control words [from, from+n) to zero
+    int clear_tail_off, clear_tail_n;   // workspace words [off, off+n) to zero (scheduling counters)
+};
+
+static __global__ void __launch_bounds__(256) finalize_sums_kernel(const float* __restrict__ ws, float* __restrict__ out,
+                                                            float* __restrict__ ws_rw, FinalizeArgs fa) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __shared__ double s_acc[8][8];
+    const int K = fa.k;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+    const float* part = ws + WS_CTRL_WORDS;
+    for (int b = threadIdx.x; b < fa.n_blocks; b += 256) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < K) acc[k] += (double)part[(size_t)b * K + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double r = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (lane == 0) s_acc[k][wid] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += s_acc[threadIdx.x][w];
+        out[threadIdx.x] = (float)(r * fa.scale[threadIdx.x]);
+    }
+    unsigned int* wsu = reinterpret_cast<unsigned int*>(ws_rw);
+    for (int i = threadIdx.x; i < fa.clear_ctrl_n; i += 256) wsu[fa.clear_ctrl_from + i] = 0u;
+    for (int i = threadIdx.x; i < fa.clear_tail_n; i += 256) wsu[fa.clear_tail_off + i] = 0u;
 }
 
 // log-softmax statistics of one row of n logits read through `ld(j)`; L cooperating lanes (1 or 32) stride the row.
@@ -223,8 +311,27 @@ static inline bool pdl_enabled() {
     return v == 1;
 }
 
+// All kernels of the library ask for the same L1/shared-memory split (maximum shared memory): consecutive kernels with
+// different carve-outs make the SMs drain and reconfigure between launches, which costs microseconds at these kernel
+// durations.  None of the kernels relies on L1 hit rates (streaming loads, explicit shared-memory staging).
+static inline void pin_carveout(const void* fn) {
+    static const void* seen[64];
+    static int n_seen = 0;
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i] == fn) return;
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("B200RL_CARVEOUT");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (enabled) (void)cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (n_seen < 64) seen[n_seen++] = fn;
+    (void)cudaGetLastError();
+}
+
 template <typename... KArgs, typename... Args>
 static inline int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    pin_carveout(reinterpret_cast<const void*>(kern));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -236,6 +343,10 @@ static inline int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return (int)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+static inline int launch_finalize(float* ws, float* out, const FinalizeArgs& fa, cudaStream_t st) {
+    return launch_k(finalize_sums_kernel, 1, 256, 0, st, (const float*)ws, out, ws, fa);
 }
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

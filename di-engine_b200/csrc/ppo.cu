@@ -25,173 +25,13 @@
 // Forward output: out[0..5] = policy_loss, value_loss, entropy_loss, kl_div, approx_kl, clipfrac (device floats, the
 // caller decides when to read them -- no host sync in here).
 #include "../../include/b200rl.h"
-#include "common.cuh"
+#include "ppo_math.cuh"
 
 namespace b200rl {
 
-struct PpoArgs {
-    const float* logit_new;
-    const float* logit_old;
-    const float* logit_pre;  // nullable
-    const long long* action;
-    const float* value_new;
-    const float* value_old;
-    const float* adv;
-    const float* ret;
-    const float* weight;  // nullable -> 1
-    long long S;
-    int G;
-    int N;
-    float clip;       // fp32(clip_ratio)
-    float clip_lo;    // fp32(1 - clip_ratio), computed in double like the python scalar of the reference
-    float clip_hi;    // fp32(1 + clip_ratio)
-    float dual_clip;  // <= 0: disabled
-    int use_value_clip;
-    int kl_type;  // 1,2,3
-    // upstream gradients (device scalars, nullable = 0): actual ones for BWD, expected ones for FWD_GRAD
-    const float* g_policy;
-    const float* g_value;
-    const float* g_entropy;
-    const float* g_kl;
-    float* grad_logit;
-    float* grad_value;
-    // FWD_GRAD: the 4 upstream values the gradients were scaled with are recorded here;
-    // BWD: when non-null and equal to the actual upstream values the launch is a no-op (gradients already written)
-    float* g_used;
-    float* g_hint;  // BWD: refreshed with the actual upstream values for the next forward pass (nullable)
-};
-
-// d(selected surrogate)/d(ratio) with torch's tie rules: min/max split the gradient 0.5/0.5 on equality, clamp passes
-// gradient on the closed interval (ppo.py:208-216).  Also returns the selected surrogate value.
-__device__ __forceinline__ float surrogate(float ratio, float adv, float lo, float hi, float dual_clip,
-                                           float& dsel_dratio) {
-    const float rc = fminf(fmaxf(ratio, lo), hi);
-    const float s1 = ratio * adv, s2 = rc * adv;
-    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
-    float w1, w2;
-    if (s1 < s2) { w1 = 1.f; w2 = 0.f; }
-    else if (s1 > s2) { w1 = 0.f; w2 = 1.f; }
-    else { w1 = 0.5f; w2 = 0.5f; }
-    float sel = fminf(s1, s2);
-    float d = adv * (w1 + w2 * in_range);
-    if (dual_clip > 0.f && adv < 0.f) {
-        const float floor_ = dual_clip * adv;
-        if (sel < floor_) { sel = floor_; d = 0.f; }
-        else if (sel == floor_) { d *= 0.5f; }
-    }
-    dsel_dratio = d;
-    return sel;
-}
-
-// 0.5*w*max(e1,e2) pieces: returns max(e1,e2) and d max / d value_new (ppo.py:267-274)
-__device__ __forceinline__ float value_term(float v, float v_old, float ret, float clip, int use_clip, float& dterm_dv) {
-    const float r1 = ret - v;
-    const float e1 = r1 * r1;
-    if (!use_clip) { dterm_dv = -2.f * r1; return e1; }
-    const float dv = v - v_old;
-    const float vc = v_old + fminf(fmaxf(dv, -clip), clip);
-    const float r2 = ret - vc;
-    const float e2 = r2 * r2;
-    const float pass = (dv >= -clip && dv <= clip) ? 1.f : 0.f;
-    const float d1 = -2.f * r1, d2 = -2.f * r2 * pass;
-    if (e1 > e2) { dterm_dv = d1; return e1; }
-    if (e1 < e2) { dterm_dv = d2; return e2; }
-    dterm_dv = 0.5f * (d1 + d2);
-    return e1;
-}
-
-// ===============================================================================================================
-// main path: persistent TMA-pipelined tile kernel
-// ===============================================================================================================
-constexpr int PPO_R = 128;      // rows per tile == consumer threads per CTA
-constexpr int PPO_THREADS = PPO_R + 32;  // + one producer warp
-constexpr int PPO_STAGES = 3;   // input ring depth
-constexpr int PPO_OUTBUFS = 2;  // gradient tile ring depth (per warp)
-enum { PPO_FWD = 0, PPO_FWD_GRAD = 1, PPO_BWD = 2 };
-
-// MUFU approximations with flush-to-zero (no denormal fix-up code around them): relative error ~2^-22
-__device__ __forceinline__ float ex2f_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2f_(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcpf_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-constexpr float kF32Min = -3.402823466e38f;
-
-__device__ __forceinline__ float kl_term(float log_ratio, int kl_type, float& dterm) {
-    if (kl_type == 1) { dterm = 1.f; return log_ratio; }
-    if (kl_type == 2) { dterm = log_ratio; return log_ratio * log_ratio / 2.f; }
-    const float e = ex2f_(-log_ratio * kLog2e);
-    dterm = 1.f - e;
-    return e - 1.f + log_ratio;
-}
-
-// one row of NC logits from shared memory into registers; 8/16-byte vector loads are bank-conflict free for the
-// row strides that occur (e.g. 24 B rows read as 3 x float2)
-template <int NC>
-__device__ __forceinline__ void load_row(const float* src, float (&z)[NC]) {
-    if (NC % 4 == 0) {
-#pragma unroll
-        for (int j = 0; j < NC / 4; ++j) {
-            const float4 v = reinterpret_cast<const float4*>(src)[j];
-            z[4 * j] = v.x; z[4 * j + 1] = v.y; z[4 * j + 2] = v.z; z[4 * j + 3] = v.w;
-        }
-    } else if (NC % 2 == 0) {
-#pragma unroll
-        for (int j = 0; j < NC / 2; ++j) {
-            const float2 v = reinterpret_cast<const float2*>(src)[j];
-            z[2 * j] = v.x; z[2 * j + 1] = v.y;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < NC; ++j) z[j] = src[j];
-    }
-}
-template <int NC>
-__device__ __forceinline__ void store_row(float* dst, const float (&g)[NC]) {
-    if (NC % 4 == 0) {
-#pragma unroll
-        for (int j = 0; j < NC / 4; ++j)
-            reinterpret_cast<float4*>(dst)[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-    } else if (NC % 2 == 0) {
-#pragma unroll
-        for (int j = 0; j < NC / 2; ++j) reinterpret_cast<float2*>(dst)[j] = make_float2(g[2 * j], g[2 * j + 1]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < NC; ++j) dst[j] = g[j];
-    }
-}
-
-// Softmax statistics of one row in the log2 domain: t_j = (z_j - max)*log2(e) <= 0, e_j = 2^t_j, s = sum e_j,
-// u2 = sum e_j t_j.  Then logsumexp = max + ln2*log2(s), entropy = ln2*(log2(s) - u2/s), p_j = e_j/s.
-struct RowStat {
-    float m, l2s, inv, log_s, ent;
-};
-
-struct PpoTileLayout {
-    int logit_bytes;  // one logit tile
-    int off_old, off_pre, off_act, off_vn, off_vo, off_adv, off_ret, off_w;
-    int stage_bytes;
-    int tx_bytes;  // bytes TMA delivers per stage
-};
-__host__ __device__ inline PpoTileLayout ppo_layout(int N, bool has_pre, bool has_w) {
-    PpoTileLayout L;
-    L.logit_bytes = PPO_R * N * 4;
-    int o = L.logit_bytes;
-    L.off_old = o; o += L.logit_bytes;
-    L.off_pre = o; if (has_pre) o += L.logit_bytes;
-    L.off_act = o; o += PPO_R * 8;
-    L.off_vn = o; o += PPO_R * 4;
-    L.off_vo = o; o += PPO_R * 4;
-    L.off_adv = o; o += PPO_R * 4;
-    L.off_ret = o; o += PPO_R * 4;
-    L.off_w = o; if (has_w) o += PPO_R * 4;
-    L.stage_bytes = (o + 127) & ~127;
-    L.tx_bytes = o;
-    return L;
-}
-
-template <int NC, int WHAT>
+template <int NC, int WHAT, int RPT>
 __global__ void __launch_bounds__(PPO_THREADS) ppo_tile_kernel(PpoArgs a, float* out, float* ws) {
+    constexpr int PPO_R = PPO_CT * RPT;  // rows per tile
     pdl_prologue();
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool GRADS = (WHAT != PPO_FWD);
@@ -199,10 +39,10 @@ __global__ void __launch_bounds__(PPO_THREADS) ppo_tile_kernel(PpoArgs a, float*
     const int N = NC ? NC : a.N;
     const int tid = threadIdx.x;
     const int wid = tid >> 5, lane = tid & 31;
-    const bool is_producer = wid == PPO_R / 32;  // warp 4: TMA issue only
+    const bool is_producer = wid == PPO_CW;  // warp 4: TMA issue only
     const bool has_pre = a.logit_pre != nullptr, has_w = a.weight != nullptr;
-    const PpoTileLayout L = ppo_layout(N, has_pre, has_w);
-    const int warp_out_bytes = 32 * N * 4;  // one warp's gradient rows of a tile
+    const PpoTileLayout L = ppo_layout(N, has_pre, has_w, PPO_R);
+    const int warp_out_bytes = 32 * RPT * N * 4;  // one warp's gradient rows of a tile (32*RPT consecutive rows)
     unsigned char* outbuf = smem + PPO_STAGES * L.stage_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(outbuf + (GRADS ? PPO_OUTBUFS * L.logit_bytes : 0));
     uint64_t* empty = full + PPO_STAGES;
@@ -228,7 +68,7 @@ __global__ void __launch_bounds__(PPO_THREADS) ppo_tile_kernel(PpoArgs a, float*
             a.g_used[0] = g_pol; a.g_used[1] = g_val; a.g_used[2] = g_ent; a.g_used[3] = g_kl;
         }
     }
-    const float inv_s = 1.f / (float)a.S;
+    const PpoUpstream up{g_pol, g_val, g_ent, g_kl, 1.f / (float)a.S};
 
     const long long n_full = a.S / PPO_R;
     const int tail_rows = (int)(a.S - n_full * PPO_R);
@@ -238,7 +78,7 @@ __global__ void __launch_bounds__(PPO_THREADS) ppo_tile_kernel(PpoArgs a, float*
     if (tid == 0) {
         for (int s = 0; s < PPO_STAGES; ++s) {
             mbar_init(&full[s], 1);           // producer's expect_tx arrive + TMA byte count
-            mbar_init(&empty[s], PPO_R / 32);  // one arrive per consumer warp
+            mbar_init(&empty[s], PPO_CW);  // one arrive per consumer warp
         }
         mbar_fence_init();
     }
@@ -278,139 +118,46 @@ __global__ void __launch_bounds__(PPO_THREADS) ppo_tile_kernel(PpoArgs a, float*
         const bool full_tile = t < n_full;
         if (full_tile) {
             mbar_wait(&full[sg], (uint32_t)((i / PPO_STAGES) & 1));
-        } else if (tid < tail_rows) {
-            // ragged last tile: every thread fetches its own row into its own slots of the stage (no sharing)
-            float* d0 = reinterpret_cast<float*>(st) + tid * N;
-            float* d1 = reinterpret_cast<float*>(st + L.off_old) + tid * N;
-            float* d2 = reinterpret_cast<float*>(st + L.off_pre) + tid * N;
-            for (int k = 0; k < N; ++k) {
-                d0[k] = a.logit_new[(row0 + tid) * N + k];
-                d1[k] = a.logit_old[(row0 + tid) * N + k];
-                if (has_pre) d2[k] = a.logit_pre[(row0 + tid) * N + k];
+        } else {
+            // ragged last tile: every thread fetches its own rows into their own slots of the stage (no sharing)
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+                const int rit = (wid * RPT + q) * 32 + lane;
+                if (rit >= tail_rows) continue;
+                float* d0 = reinterpret_cast<float*>(st) + rit * N;
+                float* d1 = reinterpret_cast<float*>(st + L.off_old) + rit * N;
+                float* d2 = reinterpret_cast<float*>(st + L.off_pre) + rit * N;
+                for (int k = 0; k < N; ++k) {
+                    d0[k] = a.logit_new[(row0 + rit) * N + k];
+                    d1[k] = a.logit_old[(row0 + rit) * N + k];
+                    if (has_pre) d2[k] = a.logit_pre[(row0 + rit) * N + k];
+                }
+                reinterpret_cast<long long*>(st + L.off_act)[rit] = a.action[row0 + rit];
+                reinterpret_cast<float*>(st + L.off_vn)[rit] = a.value_new[row0 + rit];
+                reinterpret_cast<float*>(st + L.off_vo)[rit] = a.value_old[row0 + rit];
+                reinterpret_cast<float*>(st + L.off_adv)[rit] = a.adv[row0 + rit];
+                reinterpret_cast<float*>(st + L.off_ret)[rit] = a.ret[row0 + rit];
+                if (has_w) reinterpret_cast<float*>(st + L.off_w)[rit] = a.weight[row0 + rit];
             }
-            reinterpret_cast<long long*>(st + L.off_act)[tid] = a.action[row0 + tid];
-            reinterpret_cast<float*>(st + L.off_vn)[tid] = a.value_new[row0 + tid];
-            reinterpret_cast<float*>(st + L.off_vo)[tid] = a.value_old[row0 + tid];
-            reinterpret_cast<float*>(st + L.off_adv)[tid] = a.adv[row0 + tid];
-            reinterpret_cast<float*>(st + L.off_ret)[tid] = a.ret[row0 + tid];
-            if (has_w) reinterpret_cast<float*>(st + L.off_w)[tid] = a.weight[row0 + tid];
         }
         // this warp's slice of the gradient-tile ring (2 buffers per warp inside the CTA's output area)
-        float* gtile = reinterpret_cast<float*>(outbuf + (wid * 2 + (i & 1)) * warp_out_bytes) - wid * 32 * N;
-        if (full_tile || tid < tail_rows) {
-            const float* zn = reinterpret_cast<const float*>(st) + tid * N;
-            const float* zo = reinterpret_cast<const float*>(st + L.off_old) + tid * N;
-            const int act = (int)reinterpret_cast<const long long*>(st + L.off_act)[tid];
-            const float v_new = reinterpret_cast<const float*>(st + L.off_vn)[tid];
-            const float v_old = reinterpret_cast<const float*>(st + L.off_vo)[tid];
-            const float adv = reinterpret_cast<const float*>(st + L.off_adv)[tid];
-            const float ret = reinterpret_cast<const float*>(st + L.off_ret)[tid];
-            const float w = has_w ? reinterpret_cast<const float*>(st + L.off_w)[tid] : 1.f;
-            constexpr int NR = NC ? NC : 1;
-            float tn[NR], en[NR];  // new-policy row: t_j and e_j (compile-time N only)
-            float m = kF32Min, s = 0.f, u2 = 0.f;
-            if (NC) {
-                load_row<NR>(zn, tn);
+        float* gtile = reinterpret_cast<float*>(outbuf + (wid * 2 + (i & 1)) * warp_out_bytes) - wid * 32 * RPT * N;
 #pragma unroll
-                for (int j = 0; j < NR; ++j) m = fmaxf(m, tn[j]);
-                const float m2 = m * kLog2e;
-#pragma unroll
-                for (int j = 0; j < NR; ++j) {
-                    tn[j] = fmaxf(fmaf(tn[j], kLog2e, -m2), kF32Min);  // clamp: Categorical.entropy's finfo.min
-                    en[j] = ex2f_(tn[j]);
-                    s += en[j];
-                    u2 = fmaf(en[j], tn[j], u2);
-                }
-            } else {
-                for (int j = 0; j < N; ++j) m = fmaxf(m, zn[j]);
-                const float m2 = m * kLog2e;
-                for (int j = 0; j < N; ++j) {
-                    const float t = fmaxf(fmaf(zn[j], kLog2e, -m2), kF32Min);
-                    const float e = ex2f_(t);
-                    s += e;
-                    u2 = fmaf(e, t, u2);
-                }
-            }
-            const float l2s = lg2f_(s), inv_sum = rcpf_(s);
-            const float log_s = l2s * kLn2;
-            const float ent = (l2s - u2 * inv_sum) * kLn2;
-            const float lp_n = (zn[act] - m) - log_s;
-            // behaviour ("old") policy row: only logsumexp is needed
-            float mo = kF32Min, so = 0.f;
-            if (NC) {
-                float to[NR];
-                load_row<NR>(zo, to);
-#pragma unroll
-                for (int j = 0; j < NR; ++j) mo = fmaxf(mo, to[j]);
-                const float mo2 = mo * kLog2e;
-#pragma unroll
-                for (int j = 0; j < NR; ++j) so += ex2f_(fmaf(to[j], kLog2e, -mo2));
-            } else {
-                for (int j = 0; j < N; ++j) mo = fmaxf(mo, zo[j]);
-                const float mo2 = mo * kLog2e;
-                for (int j = 0; j < N; ++j) so += ex2f_(fmaf(zo[j], kLog2e, -mo2));
-            }
-            const float lp_o = (zo[act] - mo) - lg2f_(so) * kLn2;
-            const float ratio = ex2f_((lp_n - lp_o) * kLog2e);
-            float dsel, dterm, dk = 0.f, klv = 0.f;
-            const float sel = surrogate(ratio, adv, a.clip_lo, a.clip_hi, a.dual_clip, dsel);
-            const float vt = value_term(v_new, v_old, ret, a.clip, a.use_value_clip, dterm);
-            if (has_pre) {
-                const float* zp = reinterpret_cast<const float*>(st + L.off_pre) + tid * N;
-                float mp = kF32Min, sp = 0.f;
-                for (int j = 0; j < N; ++j) mp = fmaxf(mp, zp[j]);
-                const float mp2 = mp * kLog2e;
-                for (int j = 0; j < N; ++j) sp += ex2f_(fmaf(zp[j], kLog2e, -mp2));
-                klv = kl_term(lp_n - ((zp[act] - mp) - lg2f_(sp) * kLn2), a.kl_type, dk);
-            }
-            if (LOSSES) {
-                acc[0] -= sel * w;
-                acc[1] += vt * w;
-                acc[2] += ent * w;
-                acc[3] += klv;
-                acc[4] += lp_o - lp_n;
-                acc[5] += (ratio > a.clip_hi || ratio < a.clip_lo) ? 1.f : 0.f;
-            }
-            if (GRADS) {
-                // d/dlogp(a): policy -(w/S)*dsel*ratio, kl dk/S;  d/dH: entropy w/S
-                const float c_act = g_pol * (-w * inv_s) * dsel * ratio + g_kl * dk * inv_s;
-                const float c_ent = g_ent * w * inv_s;
-                // grad z_j = c_act*(1[j==a] - p_j) - c_ent*p_j*(logp_j + H),  logp_j = ln2*t_j - log_s
-                //          = p_j*(k0 - k1*t_j) + 1[j==a]*c_act
-                const float k0 = -c_act - c_ent * (ent - log_s), k1 = c_ent * kLn2;
-                float* gr = full_tile ? gtile + tid * N : a.grad_logit + (row0 + tid) * N;
-                if (NC) {
-                    float gj[NR];
-#pragma unroll
-                    for (int j = 0; j < NR; ++j) {
-                        gj[j] = (en[j] * inv_sum) * fmaf(-k1, tn[j], k0);
-                        if (j == act) gj[j] += c_act;
-                    }
-                    if (full_tile) {
-                        store_row<NR>(gr, gj);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < NR; ++j) gr[j] = gj[j];
-                    }
-                } else {
-                    const float m2 = m * kLog2e;
-                    for (int j = 0; j < N; ++j) {
-                        const float t = fmaxf(fmaf(zn[j], kLog2e, -m2), kF32Min);
-                        float g = (ex2f_(t) * inv_sum) * fmaf(-k1, t, k0);
-                        if (j == act) g += c_act;
-                        gr[j] = g;
-                    }
-                }
-                a.grad_value[row0 + tid] = g_val * 0.5f * w * inv_s * dterm;
+        for (int q = 0; q < RPT; ++q) {
+            const int rit = (wid * RPT + q) * 32 + lane;  // row in tile: a warp covers 32*RPT consecutive rows
+            if ((full_tile || rit < tail_rows) && !(a.dbg & 1)) {
+                const float adv = reinterpret_cast<const float*>(st + L.off_adv)[rit];
+                ppo_row_compute<NC, LOSSES, GRADS>(a, L, st, rit, N, adv, full_tile, gtile, row0, up, acc);
             }
         }
         if (full_tile) {
-            if (GRADS) {
+            if (GRADS && !(a.dbg & 6)) {
                 // hand this warp's 32 gradient rows to the TMA store engine; keep at most one store reading smem
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_1d(a.grad_logit + (row0 + wid * 32) * N, gtile + wid * 32 * N, warp_out_bytes);
+                    tma_store_1d(a.grad_logit + (row0 + wid * 32 * RPT) * N, gtile + wid * 32 * RPT * N,
+                                 warp_out_bytes);
                     tma_store_commit();
                     tma_store_wait_read<1>();
                 }
@@ -421,18 +168,7 @@ __global__ void __launch_bounds__(PPO_THREADS) ppo_tile_kernel(PpoArgs a, float*
     }
     if (GRADS && lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the bulk stores that read it
     }
-    if (LOSSES) {
-        double tot[6];
-        if (grid_sum<6, PPO_THREADS>(acc, tot, ws, 0) && tid == 0) {
-            const double is = 1.0 / (double)a.S;
-            out[0] = (float)(tot[0] * is);
-            out[1] = (float)(0.5 * tot[1] * is);
-            out[2] = (float)(tot[2] * is);
-            out[3] = has_pre ? (float)(tot[3] * is) : 0.f;
-            out[4] = (float)(tot[4] * is);
-            out[5] = (float)(tot[5] * is);
-        }
-    }
+    if (LOSSES) grid_store_partials<6, PPO_THREADS>(acc, ws);  // summed by finalize_sums_kernel, launched right behind
 }
 
 // ===============================================================================================================
@@ -582,12 +318,13 @@ static bool tile_path_ok(const PpoArgs& a) {
 }
 
 // launch geometry of the persistent kernel: SM count x resident CTAs per SM for this instantiation / smem size
-template <int NC, int WHAT>
+template <int NC, int WHAT, int RPT>
 static int launch_tile(const PpoArgs& a, float* out, float* ws, size_t ws_bytes, cudaStream_t st) {
-    const PpoTileLayout L = ppo_layout(a.N, a.logit_pre != nullptr, a.weight != nullptr);
+    constexpr int PPO_R = PPO_CT * RPT;
+    const PpoTileLayout L = ppo_layout(a.N, a.logit_pre != nullptr, a.weight != nullptr, PPO_R);
     const size_t smem = (size_t)PPO_STAGES * L.stage_bytes + (WHAT != PPO_FWD ? (size_t)PPO_OUTBUFS * L.logit_bytes : 0) +
                         2 * PPO_STAGES * sizeof(uint64_t);
-    auto kern = ppo_tile_kernel<NC, WHAT>;
+    auto kern = ppo_tile_kernel<NC, WHAT, RPT>;
     static int sm_count = 0;
     static size_t smem_set = 0;
     cudaError_t e;
@@ -611,23 +348,57 @@ static int launch_tile(const PpoArgs& a, float* out, float* ws, size_t ws_bytes,
         occ_smem = smem;
     }
     if (per_sm < 1) return B200RL_ERR_ARG;
+    {
+        static int cap = -1;
+        if (cap < 0) {
+            const char* e = getenv("B200RL_PPO_CTAS");
+            cap = e ? atoi(e) : 0;
+        }
+        if (cap > 0 && cap < per_sm) per_sm = cap;
+    }
     const long long n_tiles = (a.S + PPO_R - 1) / PPO_R;
     // the verification launch that follows a fused forward normally exits at once: keep its grid to one CTA per SM
     long long grid = (long long)sm_count * ((WHAT == PPO_BWD && a.g_used) ? 1 : per_sm);
     if (grid > n_tiles) grid = n_tiles;
     if (WHAT != PPO_BWD && (size_t)(WS_CTRL_WORDS + grid * 6) * sizeof(float) > ws_bytes) return B200RL_ERR_WORKSPACE;
     (void)launch_k(kern, (int)grid, PPO_THREADS, smem, st, a, out, ws);
+    if (WHAT != PPO_BWD) {
+        FinalizeArgs fa{};
+        const double is = 1.0 / (double)a.S;
+        fa.scale[0] = is; fa.scale[1] = 0.5 * is; fa.scale[2] = is; fa.scale[3] = a.logit_pre ? is : 0.0;
+        fa.scale[4] = is; fa.scale[5] = is;
+        fa.k = 6; fa.n_blocks = (int)grid;
+        (void)launch_finalize(ws, out, fa, st);
+    }
     return (int)cudaGetLastError();
+}
+
+// rows per consumer thread: 2 (256-row tiles) once there are enough tiles to go round, else 1; B200RL_PPO_RPT overrides
+static int pick_rpt(long long S) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("B200RL_PPO_RPT");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 1 || forced == 2 || forced == 4) return forced;
+    return S >= 256LL * 148 * 4 ? 2 : 1;
 }
 
 template <int WHAT>
 static int dispatch_tile(const PpoArgs& a, float* out, float* ws, size_t ws_bytes, cudaStream_t st) {
+    const int rpt = pick_rpt(a.S);
     switch (a.N) {
-#define B200RL_CASE(n) case n: return launch_tile<n, WHAT>(a, out, ws, ws_bytes, st);
+#define B200RL_CASE(n)                                                           \
+    case n:                                                                      \
+        if (rpt == 4) return launch_tile<n, WHAT, 4>(a, out, ws, ws_bytes, st);  \
+        if (rpt == 2) return launch_tile<n, WHAT, 2>(a, out, ws, ws_bytes, st);  \
+        return launch_tile<n, WHAT, 1>(a, out, ws, ws_bytes, st);
         B200RL_CASE(2) B200RL_CASE(3) B200RL_CASE(4) B200RL_CASE(5) B200RL_CASE(6) B200RL_CASE(7) B200RL_CASE(8)
         B200RL_CASE(9) B200RL_CASE(10) B200RL_CASE(12) B200RL_CASE(14) B200RL_CASE(16) B200RL_CASE(18)
 #undef B200RL_CASE
-        default: return launch_tile<0, WHAT>(a, out, ws, ws_bytes, st);
+        default:
+            if (rpt >= 2) return launch_tile<0, WHAT, 2>(a, out, ws, ws_bytes, st);
+            return launch_tile<0, WHAT, 1>(a, out, ws, ws_bytes, st);
     }
 }
 
@@ -644,6 +415,14 @@ static int fill_args(PpoArgs& a, const float* logit_new, const float* logit_old,
     a.S = S; a.G = (int)G; a.N = (int)N; a.clip = (float)clip_ratio; a.clip_lo = (float)(1.0 - clip_ratio);
     a.clip_hi = (float)(1.0 + clip_ratio); a.dual_clip = (float)dual_clip;
     a.use_value_clip = use_value_clip; a.kl_type = kl_type;
+    {
+        static int dbg = -1;
+        if (dbg < 0) {
+            const char* e = getenv("B200RL_PPO_DBG");
+            dbg = e ? atoi(e) : 0;
+        }
+        a.dbg = dbg;
+    }
     if (S < 0 || G < 1 || N < 1) return B200RL_ERR_ARG;
     if (!logit_new || !logit_old || !action || !value_new || !value_old || !adv || !return_) return B200RL_ERR_ARG;
     if (kl_type < 1 || kl_type > 3) return B200RL_ERR_ARG;

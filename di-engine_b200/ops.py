@@ -203,6 +203,44 @@ class PPOFunction(torch.autograd.Function):
         return (grad_logit, grad_value) + (None, ) * 14
 
 
+class GAEPPOFunction(torch.autograd.Function):
+    """gae -> ppo_error in one launch (csrc/fused.cu).  Outputs: adv (T,B; non differentiable), the four losses and the
+    raw result vector; backward is the same device-verified scheme as PPOFunction."""
+
+    @staticmethod
+    def forward(ctx, logit_new, value_new, value, next_value, reward, done, traj_flag, logit_old, action, value_old,
+                return_, weight, logit_pre, T, B, N, gamma, lambda_, clip_ratio, use_value_clip, dual_clip, kl_type):
+        dev = logit_new.device
+        out = torch.empty(8, dtype=torch.float32, device=dev)
+        adv = torch.empty_like(value)
+        want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        grad_logit = torch.empty_like(logit_new) if want_grad else None
+        grad_value = torch.empty_like(value_new) if want_grad else None
+        g_used = torch.empty(4, dtype=torch.float32, device=dev) if want_grad else None
+        with torch.cuda.device(dev):
+            ws = workspace(dev)
+            rc = lib().b200rl_gae_ppo_fwd_grad(
+                ptr(value), ptr(next_value), ptr(reward), ptr(done), ptr(traj_flag), T, B, gamma, lambda_, 1,
+                ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old),
+                ptr(return_), ptr(weight), N, clip_ratio, use_value_clip, dual_clip, kl_type,
+                ptr(ppo_hint(dev)) if want_grad else None, ptr(g_used), ptr(adv), ptr(out), ptr(grad_logit),
+                ptr(grad_value), ptr(ws), ws.numel() * 4, stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_gae_ppo_fwd_grad')
+        ctx.save_for_backward(logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre)
+        ctx.cfg = (T * B, 1, N, clip_ratio, use_value_clip, dual_clip, kl_type)
+        ctx.fused = want_grad
+        ctx.spec = (grad_logit, grad_value, g_used)
+        ctx.bwd_calls = 0
+        ctx.mark_non_differentiable(out, adv)
+        return adv, out[0], out[1], out[2], out[3], out
+
+    @staticmethod
+    def backward(ctx, _g_adv, g_p, g_v, g_e, g_k, _g_out):
+        grads = PPOFunction.backward(ctx, g_p, g_v, g_e, g_k, None)
+        return (grads[0], grads[1]) + (None, ) * 20
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # q n-step TD
 # ----------------------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 """Mirror of the hot-path part of ``ding.rl_utils`` (ding/rl_utils/__init__.py:1-27): identical names, signatures and
 namedtuples, computed by the sm_100a kernels behind the C ABI of ``include/b200rl.h``."""
+from .fused import gae_ppo_error
 from .gae import gae, gae_data, shape_fn_gae
 from .ppo import ppo_data, ppo_error, ppo_info, ppo_loss, shape_fn_ppo
 from .td import (dist_nstep_td_data, dist_nstep_td_error, generalized_lambda_returns, q_nstep_td_data,

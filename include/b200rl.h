@@ -160,6 +160,27 @@ B200RL_API int b200rl_vtrace_bwd(const float* target_output, const long long* ac
                       const float* g_entropy, long long T, long long B, long long N, float* grad_target_output,
                       float* grad_value, void* stream);
 
+/* ---- fused learner step: gae (gae.py:25-70) followed by ppo_error (ppo.py:77-140) in ONE launch ------------------
+ * Semantics are exactly b200rl_gae(value, next_value, reward, done, traj_flag -> adv) followed by b200rl_ppo_fwd_grad
+ * (or b200rl_ppo_fwd when g_expected is null) with that adv, S = T*B, G = 1 -- same arithmetic, bit-identical adv.
+ * value/next_value/reward/done/traj_flag/adv: (T, B); logits: (T*B, N); action/value_new/value_old/return_/weight: (T*B).
+ * The advantage rows are produced newest-first and consumed by the PPO tiles in the same order inside the kernel, so the
+ * batch crosses HBM once.  Requires b200rl_gae_ppo_supported(...) == 1 (N <= 32, B % 4 == 0, 16-byte aligned tensors). */
+B200RL_API int b200rl_gae_ppo_supported(const float* value, const float* next_value, const float* reward,
+                             const float* done, const float* traj_flag, long long T, long long B,
+                             const float* logit_new, const float* logit_old, const float* logit_pretrained,
+                             const long long* action, const float* value_new, const float* value_old,
+                             const float* return_, const float* weight, long long N, const float* adv,
+                             const float* grad_logit_new);
+B200RL_API int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, const float* reward, const float* done,
+                            const float* traj_flag, long long T, long long B, double gamma, double lambda_,
+                            int mask_next_value_inplace, const float* logit_new, const float* logit_old,
+                            const float* logit_pretrained, const long long* action, const float* value_new,
+                            const float* value_old, const float* return_, const float* weight, long long N,
+                            double clip_ratio, int use_value_clip, double dual_clip, int kl_type,
+                            const float* g_expected, float* g_used, float* adv, float* out, float* grad_logit_new,
+                            float* grad_value_new, float* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- calibration probe (not an operator): persistent float4 copy of n_floats (multiple of 4) -------------------- */
 B200RL_API int b200rl_probe_copy(const float* src, float* dst, long long n_floats, int ctas_per_sm, void* stream);
 

@@ -11,7 +11,9 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-sets = [bench.DeviceStep(bench.make_batch(i), 'cuda:0') for i in range(4)]
+mode = sys.argv[2] if len(sys.argv) > 2 else 'onepass'
+mode = {'onepass': 'onepass', 'three': True, 'unfused': False}[mode]
+sets = [bench.DeviceStep(bench.make_batch(i), 'cuda:0', fused=mode) for i in range(4)]
 for i in range(steps):
     sets[i % 4]()
 torch.cuda.synchronize()
