@@ -373,7 +373,9 @@ static int launch_tile(const PpoArgs& a, float* out, float* ws, size_t ws_bytes,
     return (int)cudaGetLastError();
 }
 
-// rows per consumer thread: 2 (256-row tiles) once there are enough tiles to go round, else 1; B200RL_PPO_RPT overrides
+// rows per consumer thread (B200RL_PPO_RPT overrides).  Measured on B200 (tools/exp_step.py, config D): the forward-only
+// kernel gains from 256-row tiles (12.2 vs 13.6 us), the gradient-writing variants do not (15.6 us either way) and the
+// gae -> ppo -> verify sequence is fastest with 128-row tiles (24.3 vs 29.2 us per step), so 1 is the default.
 static int pick_rpt(long long S) {
     static int forced = -1;
     if (forced < 0) {
@@ -381,7 +383,8 @@ static int pick_rpt(long long S) {
         forced = e ? atoi(e) : 0;
     }
     if (forced == 1 || forced == 2 || forced == 4) return forced;
-    return S >= 256LL * 148 * 4 ? 2 : 1;
+    (void)S;
+    return 1;
 }
 
 template <int WHAT>
