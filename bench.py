@@ -324,8 +324,29 @@ def run_gpu(args):
     step_bytes = ALG_BYTES_PER_TR['step'] * T_LEN * B_COLS
     side = torch.cuda.Stream()
     main = torch.cuda.Stream()
-    from di_engine_b200.parallel import LossAllReduce
-    reducers = [LossAllReduce(6, dev) for _ in range(NSETS)] if world > 1 else None
+    from di_engine_b200.parallel import LossAllReduce, P2PLossAllReduce
+    reducers, exchange = None, 'none'
+    if world > 1:
+        if args.collective in ('auto', 'p2p'):
+            try:  # one small kernel over NVLink peer memory (symmetric memory); falls back to NCCL if unavailable
+                reducers = [P2PLossAllReduce(6, dev) for _ in range(NSETS)]
+                exchange = 'p2p'
+            except Exception as e:
+                if args.collective == 'p2p':
+                    raise
+                if rank == 0:
+                    print('bench: peer-memory all-reduce unavailable (%s); using NCCL' % e, file=sys.stderr)
+        if reducers is None:
+            reducers = [LossAllReduce(6, dev) for _ in range(NSETS)]
+            exchange = 'nccl'
+
+    def exchange_losses(j):
+        """mean over ranks of set j's six loss scalars (mean of rank means), on the current stream"""
+        if exchange == 'p2p':
+            reducers[j].reduce(sets[j].out)
+        else:
+            reducers[j].buf.copy_(sets[j].out[:6], non_blocking=True)
+            reducers[j].reduce()
 
     # ---- correctness guard: first set against the CPU oracle on rank 0 (outside every timed region) ----------------
     if rank == 0:
@@ -349,8 +370,8 @@ def run_gpu(args):
             s()
             s()
         if world > 1:
-            for r in reducers:
-                r.reduce()
+            for j in range(NSETS):
+                exchange_losses(j)
         main.synchronize()
 
         def capture(with_collective):
@@ -361,9 +382,7 @@ def run_gpu(args):
                     if with_collective:
                         side.wait_stream(main)
                         with torch.cuda.stream(side):
-                            prev = (j - 1) % NSETS
-                            reducers[prev].buf.copy_(sets[prev].out[:6], non_blocking=True)
-                            reducers[prev].reduce()
+                            exchange_losses((j - 1) % NSETS)
                     s()
                     if with_collective:
                         main.wait_stream(side)
@@ -393,12 +412,9 @@ def run_gpu(args):
                 ev.record(main)
                 side.wait_event(ev)
                 with torch.cuda.stream(side):
-                    reducers[j].buf.copy_(sets[j].out[:6], non_blocking=True)
-                    reducers[j].reduce()  # one NCCL all-reduce (sum) + divide: mean of rank means
+                    exchange_losses(j)
         if collective_mode == 'in-graph':  # the last step's scalars (every earlier one rode in the next step's graph)
-            j = (n - 1) % NSETS
-            reducers[j].buf.copy_(sets[j].out[:6], non_blocking=True)
-            reducers[j].reduce()
+            exchange_losses((n - 1) % NSETS)
         elif collective_mode == 'eager':
             main.wait_stream(side)
 
@@ -531,7 +547,7 @@ def run_gpu(args):
                 'l2_policy': 'inputs rotated over %d buffer sets of 67 MB (> 126 MB L2) between consecutive steps' %
                              NSETS,
                 'launch': 'CUDA graph replay of %d kernels per step (%s)' % (len(names), ', '.join(names)),
-                'collective': 'none' if world == 1 else 'one NCCL all-reduce of 6 packed loss floats per step (%s), overlapping the next step' % collective_mode,
+                'collective': 'none' if world == 1 else ('one all-reduce (mean) of the 6 loss scalars per step, %s, %s, overlapping the next step' % ('NVLink peer-memory kernel b200rl_p2p_allreduce_mean' if exchange == 'p2p' else 'NCCL', collective_mode)),
             },
             'roofline': {
                 'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
@@ -588,6 +604,8 @@ def main():
     ap.add_argument('--steps', type=int, default=2000)
     ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--collective', default='auto', choices=['auto', 'p2p', 'nccl'],
+                    help='N>1: exchange of the loss scalars (auto = NVLink peer-memory kernel, NCCL if unavailable)')
     ap.add_argument('--unfused', action='store_true', help='separate gae / ppo forward / ppo backward kernels')
     ap.add_argument('--onepass', action='store_true',
                     help='one-pass gae+ppo kernel + verification (default: gae, fused ppo forward+grad, verification)')

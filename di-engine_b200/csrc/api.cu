@@ -38,3 +38,75 @@ extern "C" int b200rl_probe_copy(const float* src, float* dst, long long n_float
                                                                           reinterpret_cast<float4*>(dst), n4);
     return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// One-shot all-reduce (mean) of up to 8 floats over NVLink peer memory -- the only exchange step of this path in data
+// parallel training (the packed loss scalars).  Every rank owns a mailbox in symmetric (peer-mapped)
+// memory, [2 slots][world][8 floats + sequence word]; the kernel is ONE small CTA:
+//   - lane (r, j) stores this rank's value j into peer r's mailbox (plain stores over NVLink), then publishes the step's
+//     sequence number there with a system-scope release store;
+//   - lane r waits until peer r's sequence number has arrived in the local mailbox (acquire loads), then lanes j add the
+//     world values in rank order -- identical, deterministic result on every rank -- and divide by the world size
+//     (the reference's all_reduce + div_(world_size), ding/utils/pytorch_ddp_dist_helper.py:38-47).
+// Latency is one NVLink store + flag round (~ a few us) instead of a small-message NCCL all-reduce, nothing else runs on
+// the SMs for it, and being an ordinary kernel it can be captured in the step's CUDA graph.  Two mailbox slots alternate by
+// sequence parity: a rank cannot be two steps ahead of a peer because it needs that peer's flag to finish a step.
+// ---------------------------------------------------------------------------------------------------------------
+namespace b200rl {
+constexpr int P2P_VALS = 8;
+constexpr int P2P_ENTRY = 16;  // floats per (slot, rank) entry: 8 values, 1 sequence word, padding to 64 bytes
+
+__global__ void __launch_bounds__(256) p2p_allreduce_mean_kernel(const float* __restrict__ local,
+                                                                 const unsigned long long* __restrict__ mailboxes,
+                                                                 int rank, int world, int n, unsigned int* seq_dev,
+                                                                 float* __restrict__ out) {
+    pdl_prologue();
+    __shared__ float s_val[64][P2P_VALS];
+    const unsigned int seq = *seq_dev + 1u;  // sequence number of this exchange (same on every rank)
+    const int slot = (int)(seq & 1u);
+    const int tid = threadIdx.x;
+    // ---- scatter: thread (r, j), r = tid / 8 (peer), j = tid % 8 (value); warp-uniform trip count ----
+    for (int r0 = 0; r0 < world; r0 += 256 / P2P_VALS) {
+        const int r = r0 + tid / P2P_VALS, j = tid % P2P_VALS;
+        const bool act = r < world;
+        float* peer = act ? reinterpret_cast<float*>(mailboxes[r]) + ((size_t)slot * world + rank) * P2P_ENTRY : nullptr;
+        if (act && j < n) peer[j] = local[j];
+        __threadfence_system();  // this lane's value is visible system-wide ...
+        __syncwarp();
+        if (act && j == 0)       // ... before the sequence word that announces the entry
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<unsigned int*>(peer + P2P_VALS)),
+                         "r"(seq)
+                         : "memory");
+    }
+    // ---- gather: thread r waits for peer r's flag in the LOCAL mailbox ----
+    const float* mine = reinterpret_cast<const float*>(mailboxes[rank]) + (size_t)slot * world * P2P_ENTRY;
+    for (int r = tid; r < world; r += 256) {
+        const unsigned int* flag = reinterpret_cast<const unsigned int*>(mine + (size_t)r * P2P_ENTRY + P2P_VALS);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v != seq) __nanosleep(64);
+        } while (v != seq);
+        for (int j = 0; j < n; ++j) s_val[r & 63][j] = __ldcv(mine + (size_t)r * P2P_ENTRY + j);
+    }
+    __syncthreads();
+    if (tid < n) {
+        float acc = 0.f;
+        for (int r = 0; r < world; ++r) acc += s_val[r][tid];
+        out[tid] = acc / (float)world;
+    }
+    if (tid == 0) *seq_dev = seq;
+}
+}  // namespace b200rl
+
+extern "C" int b200rl_p2p_allreduce_mean(const float* local, const unsigned long long* mailbox_ptrs_dev, int rank,
+                                         int world, int n, unsigned int* seq_dev, float* out, void* stream) {
+    if (!local || !mailbox_ptrs_dev || !seq_dev || !out || n < 1 || n > b200rl::P2P_VALS || world < 1 || world > 64 ||
+        rank < 0 || rank >= world)
+        return B200RL_ERR_ARG;
+    (void)b200rl::launch_k(b200rl::p2p_allreduce_mean_kernel, 1, 256, 0, (cudaStream_t)stream, local, mailbox_ptrs_dev,
+                           rank, world, n, seq_dev, out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" size_t b200rl_p2p_mailbox_floats(int world) { return (size_t)2 * world * b200rl::P2P_ENTRY; }

@@ -181,6 +181,16 @@ B200RL_API int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, co
                             const float* g_expected, float* g_used, float* adv, float* out, float* grad_logit_new,
                             float* grad_value_new, float* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- data-parallel exchange step: one-shot all-reduce (mean) of n <= 8 floats over NVLink peer memory -----------
+ * Replaces the small-message NCCL all-reduce of the packed loss scalars (mean of rank means,
+ * ding/utils/pytorch_ddp_dist_helper.py:38-47).  mailbox_ptrs_dev: device array of `world` pointers, entry r = the
+ * address (in THIS process) of rank r's mailbox of b200rl_p2p_mailbox_floats(world) floats in peer-mapped (symmetric)
+ * memory, zero-initialised; seq_dev: device counter, zero-initialised, advanced by every call (all ranks must call in
+ * the same order).  out[j] = mean over ranks of local[j], bit-identical on every rank.  One small CTA; graph-capturable. */
+B200RL_API int b200rl_p2p_allreduce_mean(const float* local, const unsigned long long* mailbox_ptrs_dev, int rank,
+                              int world, int n, unsigned int* seq_dev, float* out, void* stream);
+B200RL_API size_t b200rl_p2p_mailbox_floats(int world);
+
 /* ---- calibration probe (not an operator): persistent float4 copy of n_floats (multiple of 4) -------------------- */
 B200RL_API int b200rl_probe_copy(const float* src, float* dst, long long n_floats, int ctas_per_sm, void* stream);
 

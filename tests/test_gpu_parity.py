@@ -363,3 +363,32 @@ def test_fused_gae_ppo_repeatable_under_graph_capture():
             assert torch.allclose(res[k], eager[k], rtol=1e-6, atol=1e-7), k
         else:
             assert torch.equal(res[k], eager[k]), k
+
+
+def test_p2p_allreduce_kernel_single_rank_degenerate():
+    """world = 1: the mailbox exchange must reproduce the local values (mean over one rank), across many sequence
+    numbers and under CUDA-graph replay.  (Two and more ranks: tools/test_p2p.py under torchrun.)"""
+    from di_engine_b200 import ops
+    L = ops.lib()
+    mailbox = torch.zeros(L.b200rl_p2p_mailbox_floats(1), device=DEV)
+    ptrs = torch.tensor([mailbox.data_ptr()], dtype=torch.int64, device=DEV)
+    seq = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = torch.zeros(6, device=DEV)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for it in range(5):
+            src = torch.arange(8, device=DEV, dtype=torch.float32) + it
+            rc = L.b200rl_p2p_allreduce_mean(src.data_ptr(), ptrs.data_ptr(), 0, 1, 6, seq.data_ptr(), out.data_ptr(),
+                                             ops.stream_ptr())
+            assert rc == 0
+            s.synchronize()
+            assert torch.equal(out, src[:6]) and int(seq.item()) == it + 1
+        src = torch.full((8, ), 3.5, device=DEV)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            L.b200rl_p2p_allreduce_mean(src.data_ptr(), ptrs.data_ptr(), 0, 1, 6, seq.data_ptr(), out.data_ptr(),
+                                        ops.stream_ptr())
+        for _ in range(7):
+            g.replay()
+    s.synchronize()
+    assert torch.equal(out, src[:6]) and int(seq.item()) == 12
