@@ -420,11 +420,11 @@ def run_gpu(args):
 
     with torch.cuda.stream(main):
         device_loop(max(W, 3))
-        # pre-heat: ~0.3 s of the same steps (untimed) so SM/memory clocks and caches are in steady state -- one step is
-        # only ~30 us, far shorter than the clock governor's reaction time
-        t_end = time.perf_counter() + 0.3
-        while time.perf_counter() < t_end:
-            device_loop(4 * NSETS)
+        # pre-heat: ~0.25 s of the same steps (untimed) so SM/memory clocks and caches are in steady state -- one step is
+        # only ~30 us, far shorter than the clock governor's reaction time.  A FIXED step count: with a collective in the
+        # graph every rank must launch exactly the same number of steps.
+        for _ in range(8):
+            device_loop(1000)
             torch.cuda.synchronize()
         barrier()
         sampler = ClockSampler(local)
