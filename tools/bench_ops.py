@@ -66,40 +66,47 @@ def bench_gae(T=128, B=4096, nsets=12):
     report('gae T=%d B=%d' % (T, B), timed(sets), 24 * T * B, T * B, 'transitions')
 
 
-def fwd_bwd(op, mk, nsets, mix):
+def bench_api(name, op, mk, alg_bytes, units, unit_name, nsets=4):
+    """forward + backward through the PUBLIC API on device-resident tensors, captured once into a CUDA graph (so the
+    figure is the kernels' time, not the Python/ctypes dispatch), replayed over rotated input sets."""
+    import di_engine_b200.rl_utils.ppo as _p
+    _p.LAZY_INFO = True
     sets = []
     for i in range(nsets):
         _, t, p = mk(i)
         td = cases.prepare(op, t, DEV)
-
-        def run(td=td, p=p):
-            for k in cases.GRAD_INPUTS[op]:
-                td[k].grad = None
-            res = cases.run_api  # noqa: F841
-            return None
+        p = dict(p)
+        if 'gamma' in p and isinstance(p['gamma'], list):
+            p['gamma'] = [g.to(DEV) for g in p['gamma']]
         sets.append((td, p))
-    return sets
 
+    def call(td, p):
+        for k in cases.GRAD_INPUTS[op]:
+            td[k].grad = None
+        r = b2.rl_utils
+        if op == 'qntd':
+            data = r.q_nstep_td_data(*[td[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done',
+                                                        'weight')])
+            pp = dict(p); g = pp.pop('gamma')
+            loss = r.q_nstep_td_error(data, g, value_gamma=td.get('value_gamma'), **pp)[0]
+        elif op == 'dntd':
+            data = r.dist_nstep_td_data(td['dist'], td['next_n_dist'], td['act'], td['next_n_act'], td['reward'],
+                                        td['done'], td['weight'])
+            loss = r.dist_nstep_td_error(data, value_gamma=td.get('value_gamma'), **p)[0]
+        elif op == 'vtrace':
+            data = r.vtrace_data(td['target_output'], td['behaviour_output'], td['action'], td['value'], td['reward'],
+                                 td['weight'])
+            l = r.vtrace_error_discrete_action(data, **p)
+            loss = l.policy_loss + 0.5 * l.value_loss - 0.01 * l.entropy_loss
+        elif op == 'td_lambda':
+            loss = r.td_lambda_error(r.td_lambda_data(td['value'], td['reward'], td['weight']), **p)
+        elif op == 'upgo':
+            loss = r.upgo_loss(td['target_output'], td['rhos'], td['action'], td['rewards'], td['bootstrap_values'],
+                               td['mask'])
+        loss.backward()
 
-def bench_api(name, op, mk, alg_bytes, units, unit_name, nsets=4, reps=50):
-    """fwd+bwd through the public API, eager (the API reads flags/infos on the host for some ops), CUDA events."""
-    data = []
-    for i in range(nsets):
-        _, t, p = mk(i)
-        data.append((t, p))
-    for t, p in data:
-        cases.run_api(b2.rl_utils, op, t, p, device=DEV)
-    dev_sets = [(cases.prepare(op, t, DEV), p) for t, p in data]
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for r in range(reps):
-        t, p = data[r % nsets]
-        cases.run_api(b2.rl_utils, op, t, p, device=DEV)
-    e1.record()
-    torch.cuda.synchronize()
-    report(name + ' (public API, eager, incl. H2D of inputs)', e0.elapsed_time(e1) * 1e3 / reps, alg_bytes, units,
-           unit_name)
+    us = timed([lambda td=td, p=p: call(td, p) for td, p in sets], reps=200)
+    report(name + ' fwd+bwd (public API, graph-captured kernels)', us, alg_bytes, units, unit_name)
 
 
 if __name__ == '__main__':
@@ -119,10 +126,10 @@ if __name__ == '__main__':
     if 'vtrace' in which:
         bench_api('vtrace T=64 B=8192 N=6', 'vtrace',
                   lambda i: cases.vtrace_case(i, 64, 8192, 6, gamma=0.99, lambda_=0.95), 96 * 64 * 8192, 64 * 8192,
-                  'transitions', reps=20)
+                  'transitions')
     if 'tdl' in which:
         bench_api('td_lambda T=1024 B=64', 'td_lambda', lambda i: cases.td_lambda_case(i, 1024, 64), 16 * 1024 * 64,
                   1024 * 64, 'transitions')
     if 'upgo' in which:
         bench_api('upgo T=256 B=256 N=256', 'upgo', lambda i: cases.upgo_case(i, 256, 256, 256),
-                  (8 * 256 + 20) * 65536, 65536, 'transitions', reps=10)
+                  (8 * 256 + 20) * 65536, 65536, 'transitions')
