@@ -7,7 +7,7 @@
 // turns the importance weights into vs / advantages, reduces the three losses in-kernel and leaves the per-element
 // gradient coefficients for the single backward launch.
 #include "../../include/b200rl.h"
-#include "common.cuh"
+#include "ppo_math.cuh"
 
 namespace b200rl {
 
@@ -175,12 +175,19 @@ __global__ void __launch_bounds__(NT) vtrace_rows_warp_kernel(VtArgs a) {
 
 // column-tile scan: x_t = delta_t + (gl*c_t)*x_{t+1}; vs_t = V_t + x_t  (vtrace.py:22-29), then
 // adv_t = rho_pg*(r_t + g*vs_{t+1} - V_t) with vs_T = V_T (vtrace.py:126-128) and the three loss sums (:130-135).
+// Every input of the tile is read from HBM exactly once (phase 1) and kept in shared memory for the output phase.
 template <int TC, int NT, int CHUNK>
 __global__ void __launch_bounds__(NT) vtrace_scan_kernel(VtArgs a, float* ws) {
     pdl_prologue();
-    __shared__ float s_d[CHUNK][TC];   // delta, then x
-    __shared__ float s_f[CHUNK][TC];   // gl*c
-    __shared__ float s_vs[CHUNK + 1][TC];
+    __shared__ float s_d[CHUNK][TC];        // delta
+    __shared__ float s_f[CHUNK][TC];        // gl*c
+    __shared__ float s_v[CHUNK][TC];        // V_t
+    __shared__ float s_vs[CHUNK + 1][TC];   // vs_t (row `rows` = the row above the slab)
+    __shared__ float s_g[CHUNK][TC];        // rho_pg, then reused for nothing else
+    __shared__ float s_r[CHUNK][TC];        // reward
+    __shared__ float s_w[CHUNK][TC];        // weight
+    __shared__ float s_l[CHUNK][TC];        // log pi(a)
+    __shared__ float s_e[CHUNK][TC];        // entropy
     const long long c0 = (long long)blockIdx.x * TC;
     const long long T = a.T, B = a.B;
     const float inv_m = 1.f / (float)(T * B);
@@ -197,12 +204,17 @@ __global__ void __launch_bounds__(NT) vtrace_scan_kernel(VtArgs a, float* ws) {
             const long long c = c0 + cc;
             if (c < B) {
                 const long long off = (lo + r) * B + c;
-                const float is = a.isw[off];
-                const float rho = fminf(is, a.rho_clip), cs = fminf(is, a.c_clip);
+                const float is = ldg_stream(a.isw + off);
                 const float v = a.value[off], vn = a.value[off + B];
-                s_d[r][cc] = fmul(rho, fsub(fadd(a.reward[off], fmul(a.gamma, vn)), v));
-                s_f[r][cc] = fmul(a.gamma_lambda, cs);
-                s_vs[r][cc] = v;
+                const float rw = ldg_stream(a.reward + off);
+                s_d[r][cc] = fmul(fminf(is, a.rho_clip), fsub(fadd(rw, fmul(a.gamma, vn)), v));
+                s_f[r][cc] = fmul(a.gamma_lambda, fminf(is, a.c_clip));
+                s_v[r][cc] = v;
+                s_g[r][cc] = fminf(is, a.rho_pg_clip);
+                s_r[r][cc] = rw;
+                s_w[r][cc] = a.weight ? ldg_stream(a.weight + off) : 1.f;
+                s_l[r][cc] = ldg_stream(a.lp_t + off);
+                s_e[r][cc] = ldg_stream(a.ent + off);
             }
         }
         __syncthreads();
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(NT) vtrace_scan_kernel(VtArgs a, float* ws) {
             float vs = above;
             for (int r = rows - 1; r >= 0; --r) {
                 carry = fadd(s_d[r][cc], fmul(s_f[r][cc], carry));
-                vs = fadd(s_vs[r][cc], carry);  // result[t] += item
+                vs = fadd(s_v[r][cc], carry);  // result[t] += item
                 s_vs[r][cc] = vs;
             }
             above = vs;
@@ -223,17 +235,14 @@ __global__ void __launch_bounds__(NT) vtrace_scan_kernel(VtArgs a, float* ws) {
             const long long c = c0 + cc;
             if (c < B) {
                 const long long off = (lo + r) * B + c;
-                const float w = a.weight ? a.weight[off] : 1.f;
-                const float v = a.value[off];
-                const float vs = s_vs[r][cc], vs_next = s_vs[r + 1][cc];
-                const float rho_pg = fminf(a.isw[off], a.rho_pg_clip);
-                const float adv = fmul(rho_pg, fsub(fadd(a.reward[off], fmul(a.gamma, vs_next)), v));
-                const float dv = v - vs;
-                acc[0] += a.lp_t[off] * adv * w;
+                const float w = s_w[r][cc], v = s_v[r][cc];
+                const float adv = fmul(s_g[r][cc], fsub(fadd(s_r[r][cc], fmul(a.gamma, s_vs[r + 1][cc])), v));
+                const float dv = v - s_vs[r][cc];
+                acc[0] += s_l[r][cc] * adv * w;
                 acc[1] += dv * dv * w;
-                acc[2] += a.ent[off] * w;
-                a.isw[off] = adv * w;               // coefficient of the policy-gradient term
-                a.ent[off] = 2.f * w * dv * inv_m;  // d value_loss / d V_t
+                acc[2] += s_e[r][cc] * w;
+                stg_stream(a.isw + off, adv * w);               // coefficient of the policy-gradient term
+                stg_stream(a.ent + off, 2.f * w * dv * inv_m);  // d value_loss / d V_t
             }
         }
         __syncthreads();
@@ -347,6 +356,317 @@ extern "C" int b200rl_upgo_head_bwd(const float* logit, const long long* action,
     return (int)cudaGetLastError();
 }
 
+// ===============================================================================================================
+// V-trace row kernels on the persistent TMA pipeline of ppo.cu (producer warp + 4 consumer warps, 3-stage ring of
+// 1-D bulk copies, no CTA-wide barrier in the loop).  Used when N <= 32 and every tensor is 16-byte aligned.
+//   vt_rows_tile_kernel : stage = target logits | behaviour logits | actions  ->  lp(a), importance weight, entropy
+//   vt_bwd_tile_kernel  : stage = target logits | actions | adv*w | dV [| w]  ->  gradient rows through shared memory
+//                         and per-warp TMA bulk stores, d/dV straight from registers
+// ===============================================================================================================
+constexpr int VT_R = PPO_CT;  // rows per tile (one per consumer thread)
+
+template <int NC>
+__global__ void __launch_bounds__(PPO_THREADS) vt_rows_tile_kernel(VtArgs a) {
+    pdl_prologue();
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = NC ? NC : a.N;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const long long M = a.T * a.B;
+    const int logit_bytes = VT_R * N * 4;
+    const int off_beh = logit_bytes, off_act = 2 * logit_bytes;
+    const int stage_bytes = (2 * logit_bytes + VT_R * 8 + 127) & ~127;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + PPO_STAGES * stage_bytes);
+    uint64_t* empty = full + PPO_STAGES;
+    const long long n_full = M / VT_R;
+    const int tail_rows = (int)(M - n_full * VT_R);
+    const long long n_tiles = n_full + (tail_rows ? 1 : 0);
+    const int my_n = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    if (tid == 0) {
+        for (int s = 0; s < PPO_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], PPO_CW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (wid == PPO_CW) {
+        if (lane == 0) {
+            for (int i = 0; i < my_n; ++i) {
+                const long long t = blockIdx.x + (long long)i * gridDim.x;
+                if (t >= n_full) break;
+                const int sg = i % PPO_STAGES;
+                if (i >= PPO_STAGES) mbar_wait(&empty[sg], (uint32_t)(((i / PPO_STAGES) - 1) & 1));
+                const long long row0 = t * VT_R;
+                unsigned char* st = smem + sg * stage_bytes;
+                mbar_expect_tx(&full[sg], (uint32_t)(2 * logit_bytes + VT_R * 8));
+                tma_load_1d(st, a.target + row0 * N, logit_bytes, &full[sg]);
+                tma_load_1d(st + off_beh, a.behaviour + row0 * N, logit_bytes, &full[sg]);
+                tma_load_1d(st + off_act, a.action + row0, VT_R * 8, &full[sg]);
+            }
+        }
+        return;
+    }
+    for (int i = 0; i < my_n; ++i) {
+        const long long t = blockIdx.x + (long long)i * gridDim.x;
+        const long long row0 = t * VT_R;
+        const int sg = i % PPO_STAGES;
+        unsigned char* st = smem + sg * stage_bytes;
+        const bool full_tile = t < n_full;
+        if (full_tile) {
+            mbar_wait(&full[sg], (uint32_t)((i / PPO_STAGES) & 1));
+        } else if (tid < tail_rows) {
+            for (int k = 0; k < N; ++k) {
+                reinterpret_cast<float*>(st)[tid * N + k] = a.target[(row0 + tid) * N + k];
+                reinterpret_cast<float*>(st + off_beh)[tid * N + k] = a.behaviour[(row0 + tid) * N + k];
+            }
+            reinterpret_cast<long long*>(st + off_act)[tid] = a.action[row0 + tid];
+        }
+        if (full_tile || tid < tail_rows) {
+            const float* zt = reinterpret_cast<const float*>(st) + tid * N;
+            const float* zb = reinterpret_cast<const float*>(st + off_beh) + tid * N;
+            const int act = (int)reinterpret_cast<const long long*>(st + off_act)[tid];
+            constexpr int NR = NC ? NC : 1;
+            float m = kF32Min, s = 0.f, u2 = 0.f, mb = kF32Min, sb = 0.f;
+            if (NC) {
+                float tt[NR], tb[NR];
+                load_row<NR>(zt, tt);
+                load_row<NR>(zb, tb);
+#pragma unroll
+                for (int j = 0; j < NR; ++j) { m = fmaxf(m, tt[j]); mb = fmaxf(mb, tb[j]); }
+                const float m2 = m * kLog2e, mb2 = mb * kLog2e;
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const float x = fmaxf(fmaf(tt[j], kLog2e, -m2), kF32Min);
+                    const float e = ex2f_(x);
+                    s += e;
+                    u2 = fmaf(e, x, u2);
+                    sb += ex2f_(fmaf(tb[j], kLog2e, -mb2));
+                }
+            } else {
+                for (int j = 0; j < N; ++j) { m = fmaxf(m, zt[j]); mb = fmaxf(mb, zb[j]); }
+                const float m2 = m * kLog2e, mb2 = mb * kLog2e;
+                for (int j = 0; j < N; ++j) {
+                    const float x = fmaxf(fmaf(zt[j], kLog2e, -m2), kF32Min);
+                    const float e = ex2f_(x);
+                    s += e;
+                    u2 = fmaf(e, x, u2);
+                    sb += ex2f_(fmaf(zb[j], kLog2e, -mb2));
+                }
+            }
+            const float l2s = lg2f_(s);
+            const float lp_t = (zt[act] - m) - l2s * kLn2;
+            const float lp_b = (zb[act] - mb) - lg2f_(sb) * kLn2;
+            a.lp_t[row0 + tid] = lp_t;
+            a.isw[row0 + tid] = ex2f_((lp_t - lp_b) * kLog2e);
+            a.ent[row0 + tid] = (l2s - u2 * rcpf_(s)) * kLn2;
+        }
+        if (full_tile) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[sg]);
+        }
+    }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(PPO_THREADS) vt_bwd_tile_kernel(VtArgs a) {
+    pdl_prologue();
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = NC ? NC : a.N;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const long long M = a.T * a.B;
+    const bool has_w = a.weight != nullptr;
+    const int logit_bytes = VT_R * N * 4;
+    const int off_act = logit_bytes, off_c = off_act + VT_R * 8, off_dv = off_c + VT_R * 4, off_w = off_dv + VT_R * 4;
+    const int tx_bytes = off_w + (has_w ? VT_R * 4 : 0);
+    const int stage_bytes = (tx_bytes + 127) & ~127;
+    const int warp_out_bytes = 32 * N * 4;
+    unsigned char* outbuf = smem + PPO_STAGES * stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(outbuf + 2 * logit_bytes);
+    uint64_t* empty = full + PPO_STAGES;
+    const float g_pg = a.g_pg ? *a.g_pg : 0.f, g_val = a.g_val ? *a.g_val : 0.f, g_ent = a.g_ent ? *a.g_ent : 0.f;
+    const float inv_m = 1.f / (float)M;
+    {   // bootstrap row V_T receives no gradient (value[:-1], vtrace.py:134)
+        const long long i = (long long)blockIdx.x * PPO_THREADS + tid;
+        for (long long c = i; c < a.B; c += (long long)gridDim.x * PPO_THREADS) a.grad_value[M + c] = 0.f;
+    }
+    const long long n_full = M / VT_R;
+    const int tail_rows = (int)(M - n_full * VT_R);
+    const long long n_tiles = n_full + (tail_rows ? 1 : 0);
+    const int my_n = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    if (tid == 0) {
+        for (int s = 0; s < PPO_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], PPO_CW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (wid == PPO_CW) {
+        if (lane == 0) {
+            for (int i = 0; i < my_n; ++i) {
+                const long long t = blockIdx.x + (long long)i * gridDim.x;
+                if (t >= n_full) break;
+                const int sg = i % PPO_STAGES;
+                if (i >= PPO_STAGES) mbar_wait(&empty[sg], (uint32_t)(((i / PPO_STAGES) - 1) & 1));
+                const long long row0 = t * VT_R;
+                unsigned char* st = smem + sg * stage_bytes;
+                mbar_expect_tx(&full[sg], (uint32_t)tx_bytes);
+                tma_load_1d(st, a.target + row0 * N, logit_bytes, &full[sg]);
+                tma_load_1d(st + off_act, a.action + row0, VT_R * 8, &full[sg]);
+                tma_load_1d(st + off_c, a.isw + row0, VT_R * 4, &full[sg]);   // adv*w
+                tma_load_1d(st + off_dv, a.ent + row0, VT_R * 4, &full[sg]);  // dV
+                if (has_w) tma_load_1d(st + off_w, a.weight + row0, VT_R * 4, &full[sg]);
+            }
+        }
+        return;
+    }
+    for (int i = 0; i < my_n; ++i) {
+        const long long t = blockIdx.x + (long long)i * gridDim.x;
+        const long long row0 = t * VT_R;
+        const int sg = i % PPO_STAGES;
+        unsigned char* st = smem + sg * stage_bytes;
+        const bool full_tile = t < n_full;
+        if (full_tile) {
+            mbar_wait(&full[sg], (uint32_t)((i / PPO_STAGES) & 1));
+        } else if (tid < tail_rows) {
+            for (int k = 0; k < N; ++k) reinterpret_cast<float*>(st)[tid * N + k] = a.target[(row0 + tid) * N + k];
+            reinterpret_cast<long long*>(st + off_act)[tid] = a.action[row0 + tid];
+            reinterpret_cast<float*>(st + off_c)[tid] = a.isw[row0 + tid];
+            reinterpret_cast<float*>(st + off_dv)[tid] = a.ent[row0 + tid];
+            if (has_w) reinterpret_cast<float*>(st + off_w)[tid] = a.weight[row0 + tid];
+        }
+        float* wbuf = reinterpret_cast<float*>(outbuf + (wid * 2 + (i & 1)) * warp_out_bytes);
+        if (full_tile || tid < tail_rows) {
+            const float* z = reinterpret_cast<const float*>(st) + tid * N;
+            const int act = (int)reinterpret_cast<const long long*>(st + off_act)[tid];
+            const float cpg = reinterpret_cast<const float*>(st + off_c)[tid];
+            const float dv = reinterpret_cast<const float*>(st + off_dv)[tid];
+            const float w = has_w ? reinterpret_cast<const float*>(st + off_w)[tid] : 1.f;
+            constexpr int NR = NC ? NC : 1;
+            float tn[NR], en[NR];
+            float m = kF32Min, s = 0.f, u2 = 0.f;
+            if (NC) {
+                load_row<NR>(z, tn);
+#pragma unroll
+                for (int j = 0; j < NR; ++j) m = fmaxf(m, tn[j]);
+                const float m2 = m * kLog2e;
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    tn[j] = fmaxf(fmaf(tn[j], kLog2e, -m2), kF32Min);
+                    en[j] = ex2f_(tn[j]);
+                    s += en[j];
+                    u2 = fmaf(en[j], tn[j], u2);
+                }
+            } else {
+                for (int j = 0; j < N; ++j) m = fmaxf(m, z[j]);
+                const float m2 = m * kLog2e;
+                for (int j = 0; j < N; ++j) {
+                    const float x = fmaxf(fmaf(z[j], kLog2e, -m2), kF32Min);
+                    const float e = ex2f_(x);
+                    s += e;
+                    u2 = fmaf(e, x, u2);
+                }
+            }
+            const float l2s = lg2f_(s), inv_sum = rcpf_(s);
+            const float log_s = l2s * kLn2, ent = (l2s - u2 * inv_sum) * kLn2;
+            // grad z_j = c_act*(1[j==a]-p_j) - c_ent*p_j*(logp_j + H) = p_j*(k0 - k1*t_j) + 1[j==a]*c_act
+            const float c_act = g_pg * (-cpg) * inv_m, c_ent = g_ent * w * inv_m;
+            const float k0 = -c_act - c_ent * (ent - log_s), k1 = c_ent * kLn2;
+            float* gr = full_tile ? wbuf + lane * N : a.grad_logit + (row0 + tid) * N;
+            if (NC) {
+                float gj[NR];
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    gj[j] = (en[j] * inv_sum) * fmaf(-k1, tn[j], k0);
+                    if (j == act) gj[j] += c_act;
+                }
+                store_row<NR>(gr, gj);
+            } else {
+                const float m2 = m * kLog2e;
+                for (int j = 0; j < N; ++j) {
+                    const float x = fmaxf(fmaf(z[j], kLog2e, -m2), kF32Min);
+                    float g = (ex2f_(x) * inv_sum) * fmaf(-k1, x, k0);
+                    if (j == act) g += c_act;
+                    gr[j] = g;
+                }
+            }
+            a.grad_value[row0 + tid] = g_val * dv;
+        }
+        if (full_tile) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_1d(a.grad_logit + (row0 + wid * 32) * N, wbuf, warp_out_bytes);
+                tma_store_commit();
+                tma_store_wait_read<1>();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[sg]);
+        }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+}
+
+template <int NC, bool BWD>
+static int launch_vt_tile(const VtArgs& a, cudaStream_t st) {
+    const int N = a.N;
+    const int logit_bytes = VT_R * N * 4;
+    size_t smem;
+    if (BWD) {
+        const int tx = logit_bytes + VT_R * 8 + VT_R * 4 * 2 + (a.weight ? VT_R * 4 : 0);
+        smem = (size_t)PPO_STAGES * ((tx + 127) & ~127) + 2 * logit_bytes + 2 * PPO_STAGES * sizeof(uint64_t);
+    } else {
+        smem = (size_t)PPO_STAGES * ((2 * logit_bytes + VT_R * 8 + 127) & ~127) + 2 * PPO_STAGES * sizeof(uint64_t);
+    }
+    void (*kern)(VtArgs) = BWD ? vt_bwd_tile_kernel<NC> : vt_rows_tile_kernel<NC>;
+    static int sm_count = 0;
+    static size_t smem_set = 0, occ_smem = (size_t)-1;
+    static int per_sm = 0;
+    cudaError_t e;
+    if (sm_count == 0) {
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+        if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    }
+    if (smem > 48 * 1024 && smem > smem_set) {
+        if (smem > 227 * 1024) return B200RL_ERR_ARG;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+            return (int)e;
+        smem_set = smem;
+    }
+    if (occ_smem != smem) {
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PPO_THREADS, smem)) != cudaSuccess)
+            return (int)e;
+        if (per_sm > 6) per_sm = 6;
+        occ_smem = smem;
+    }
+    if (per_sm < 1) return B200RL_ERR_ARG;
+    const long long n_tiles = (a.T * a.B + VT_R - 1) / VT_R;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    (void)launch_k(kern, (int)grid, PPO_THREADS, smem, st, a);
+    return (int)cudaGetLastError();
+}
+
+template <bool BWD>
+static int dispatch_vt_tile(const VtArgs& a, cudaStream_t st) {
+    switch (a.N) {
+#define B200RL_CASE(n) case n: return launch_vt_tile<n, BWD>(a, st);
+        B200RL_CASE(2) B200RL_CASE(3) B200RL_CASE(4) B200RL_CASE(5) B200RL_CASE(6) B200RL_CASE(7) B200RL_CASE(8)
+        B200RL_CASE(9) B200RL_CASE(10) B200RL_CASE(12) B200RL_CASE(14) B200RL_CASE(16) B200RL_CASE(18)
+#undef B200RL_CASE
+        default: return launch_vt_tile<0, BWD>(a, st);
+    }
+}
+
+static bool vt_tile_ok(const VtArgs& a, bool bwd) {
+    bool al = aligned16(a.target) && aligned16(a.action) && aligned16(a.isw) && aligned16(a.ent) &&
+              (!a.weight || aligned16(a.weight));
+    if (bwd) al = al && aligned16(a.grad_logit);
+    else al = al && aligned16(a.behaviour);
+    return al && a.N <= 32;
+}
+
 static int vt_mode(const VtArgs& a) {
     const bool al = aligned16(a.target) && aligned16(a.behaviour) && (!a.grad_logit || aligned16(a.grad_logit));
     if (a.N <= 32 && al) return 0;
@@ -373,7 +693,10 @@ extern "C" int b200rl_vtrace_fwd(const float* target_output, const float* behavi
     constexpr int NT = 128;
     const long long M = T * B;
     const int mode = vt_mode(a);
-    if (mode == 0) {
+    if (vt_tile_ok(a, false)) {
+        int rc0 = dispatch_vt_tile<false>(a, st);
+        if (rc0) return rc0;
+    } else if (mode == 0) {
         (void)launch_k(vtrace_rows_kernel<NT, true>, div_up(M, NT), NT, (size_t)2 * NT * a.N * sizeof(float), st, a);
     } else if (mode == 1) {
         (void)launch_k(vtrace_rows_kernel<NT, false>, div_up(M, NT), NT, 0, st, a);
@@ -384,7 +707,7 @@ extern "C" int b200rl_vtrace_fwd(const float* target_output, const float* behavi
     if (rc) return rc;
     if (B >= 16 * 296) {
         if ((size_t)(WS_CTRL_WORDS + 3 * div_up(B, 16)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
-        (void)launch_k(vtrace_scan_kernel<16, 128, 64>, div_up(B, 16), 128, 0, st, a, workspace);
+        (void)launch_k(vtrace_scan_kernel<16, 256, 64>, div_up(B, 16), 256, 0, st, a, workspace);
     } else {
         if ((size_t)(WS_CTRL_WORDS + 3 * div_up(B, 8)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
         (void)launch_k(vtrace_scan_kernel<8, 64, 64>, div_up(B, 8), 64, 0, st, a, workspace);
@@ -408,6 +731,7 @@ extern "C" int b200rl_vtrace_bwd(const float* target_output, const long long* ac
     constexpr int NT = 128;
     const long long M = T * B;
     const int mode = vt_mode(a);
+    if (vt_tile_ok(a, true)) return dispatch_vt_tile<true>(a, st);
     if (mode == 0) (void)launch_k(vtrace_bwd_kernel<NT, 0>, div_up(M, NT), NT, (size_t)NT * a.N * sizeof(float), st, a);
     else if (mode == 1) (void)launch_k(vtrace_bwd_kernel<NT, 1>, div_up(M, NT), NT, 0, st, a);
     else (void)launch_k(vtrace_bwd_kernel<NT, 2>, div_up(M, NT / 32), NT, 0, st, a);

@@ -14,6 +14,9 @@ import di_engine_b200 as b2  # noqa: E402
 from tests import cases  # noqa: E402
 
 DEV = 'cuda:0'
+G1 = torch.tensor(1.0, device=DEV)
+G05 = torch.tensor(0.5, device=DEV)
+GM001 = torch.tensor(-0.01, device=DEV)
 
 
 def timed(fn_sets, reps=50):
@@ -97,7 +100,9 @@ def bench_api(name, op, mk, alg_bytes, units, unit_name, nsets=4):
             data = r.vtrace_data(td['target_output'], td['behaviour_output'], td['action'], td['value'], td['reward'],
                                  td['weight'])
             l = r.vtrace_error_discrete_action(data, **p)
-            loss = l.policy_loss + 0.5 * l.value_loss - 0.01 * l.entropy_loss
+            # upstream gradients as ready-made device scalars: no torch arithmetic kernels in the measured graph
+            torch.autograd.backward([l.policy_loss, l.value_loss, l.entropy_loss], [G1, G05, GM001])
+            return
         elif op == 'td_lambda':
             loss = r.td_lambda_error(r.td_lambda_data(td['value'], td['reward'], td['weight']), **p)
         elif op == 'upgo':
