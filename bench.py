@@ -374,19 +374,29 @@ def run_gpu(args):
                 exchange_losses(j)
         main.synchronize()
 
+        def record_step(j, with_collective):
+            if with_collective:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    exchange_losses((j - 1) % NSETS)
+            sets[j]()
+            if with_collective:
+                main.wait_stream(side)
+
         def capture(with_collective):
+            """graphs[j]: one step on buffer set j; graphs[NSETS]: the NSETS steps 0..NSETS-1 back to back (one host launch
+            per NSETS steps -- the per-launch host cost of a ~25 us step is not negligible)"""
             gs = []
-            for j, s in enumerate(sets):
+            for j in range(NSETS):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=main):
-                    if with_collective:
-                        side.wait_stream(main)
-                        with torch.cuda.stream(side):
-                            exchange_losses((j - 1) % NSETS)
-                    s()
-                    if with_collective:
-                        main.wait_stream(side)
+                    record_step(j, with_collective)
                 gs.append(g)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=main):
+                for j in range(NSETS):
+                    record_step(j, with_collective)
+            gs.append(g)
             return gs
 
         if world > 1:
@@ -404,7 +414,14 @@ def run_gpu(args):
     torch.cuda.synchronize()
 
     def device_loop(n):
-        for i in range(n):
+        """exactly n steps, buffer sets in the order 0,1,..,NSETS-1,0,1,.."""
+        if collective_mode != 'eager':
+            q, r = divmod(n, NSETS)
+            for _ in range(q):
+                graphs[NSETS].replay()
+            for j in range(r):
+                graphs[j].replay()
+        for i in range(n if collective_mode == 'eager' else 0):
             j = i % NSETS
             graphs[j].replay()
             if collective_mode == 'eager':
@@ -546,7 +563,7 @@ def run_gpu(args):
                 'loss_mix': [1.0, W_VALUE, W_ENTROPY], 'parallelism': 'dp%d' % world,
                 'l2_policy': 'inputs rotated over %d buffer sets of 67 MB (> 126 MB L2) between consecutive steps' %
                              NSETS,
-                'launch': 'CUDA graph replay of %d kernels per step (%s)' % (len(names), ', '.join(names)),
+                'launch': 'CUDA graph replay, %d steps per graph launch, %d kernels per step (%s)' % (NSETS, len(names), ', '.join(names)),
                 'collective': 'none' if world == 1 else ('one all-reduce (mean) of the 6 loss scalars per step, %s, %s, overlapping the next step' % ('NVLink peer-memory kernel b200rl_p2p_allreduce_mean' if exchange == 'p2p' else 'NCCL', collective_mode)),
             },
             'roofline': {
