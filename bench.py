@@ -550,6 +550,13 @@ def run_gpu(args):
         dom_bytes = ALG_BYTES_PER_TR[dom] * T_LEN * B_COLS
         achieved = dom_bytes / (kmean[dom] * 1e-3) / 1e9
         step_achieved = step_bytes / (ms_step * 1e-3) / 1e9
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dom)
+            if tr:
+                traffic = tr['dram_read'] + tr['dram_write']
+        except (OSError, ValueError, KeyError):
+            pass
         cpu = run_cpu(steps=8, warmup=2) if world == 1 else None
         e2e_value = tr_per_step / (e2e_ms / e2e_steps * 1e-3)
         line = {
@@ -568,7 +575,7 @@ def run_gpu(args):
             },
             'roofline': {
                 'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'alg_bytes_per_launch': dom_bytes, 'kernel_ms': kmean,
                 'step': {'alg_bytes': step_bytes, 'achieved': step_achieved, 'frac': step_achieved / peak},
             },
