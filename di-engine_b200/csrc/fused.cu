@@ -17,6 +17,7 @@
 #include "../../include/b200rl.h"
 #include "gae_tile.cuh"
 #include "ppo_math.cuh"
+#include "fused_args.cuh"
 
 namespace b200rl {
 
@@ -25,19 +26,6 @@ constexpr int WS_TILE_CTR = 1;                                // control word: n
 constexpr int WS_CHUNK_CTR_WORDS = 4096;                      // per-chunk completion counters (T <= 131072)
 constexpr int WS_CHUNK_CTR_OFF = (int)(WS_MIN_BYTES / 4) - WS_CHUNK_CTR_WORDS;
 static_assert((FUSED_TC / 4 + 1) * 32 == PPO_THREADS, "GAE tile roles must fill the PPO CTA exactly");
-
-struct FusedArgs {
-    PpoArgs p;  // p.adv = the (T*B) advantage buffer this kernel WRITES (phase G) and reads (phase P)
-    const float* value;
-    float* next_value;
-    const float* reward;
-    const float* done;
-    const float* traj;
-    long long T, B;
-    float gamma, gl;
-    int mask_inplace;
-    int trace;
-};
 
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
@@ -370,7 +358,24 @@ extern "C" int b200rl_gae_ppo_supported(const float* value, const float* next_va
     if (!value || !next_value || !reward || !logit_new || !logit_old || !action || !value_new || !value_old ||
         !return_ || !adv)
         return 0;
-    return fused_ok(f) ? 1 : 0;
+    return (fused_ok(f) || coltile_ok(f)) ? 1 : 0;
+}
+
+// implementation of the one-launch step: 0 = automatic, 1 = row tiles with chunk counters (gae_ppo_kernel, this file),
+// 2 = column tiles (gae_ppo_col_kernel, coltile.cu).  Initial value from B200RL_GAE_PPO_IMPL=row|col.
+static int g_impl = -1;
+static int current_impl() {
+    if (g_impl < 0) {
+        const char* e = getenv("B200RL_GAE_PPO_IMPL");
+        g_impl = (e && e[0] == 'r') ? 1 : (e && e[0] == 'c') ? 2 : 0;
+    }
+    return g_impl;
+}
+extern "C" int b200rl_gae_ppo_set_impl(int impl) {
+    if (impl < 0 || impl > 2) return B200RL_ERR_ARG;
+    const int old = current_impl();
+    g_impl = impl;
+    return old;
 }
 
 extern "C" int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, const float* reward, const float* done,
@@ -397,8 +402,14 @@ extern "C" int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, co
         f.p.g_kl = g_expected + 3; f.p.g_used = g_used; f.p.grad_logit = grad_logit_new;
         f.p.grad_value = grad_value_new;
     }
-    if (!fused_ok(f)) return B200RL_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool row_ok = fused_ok(f), col_ok = coltile_ok(f);
+    if (!row_ok && !col_ok) return B200RL_ERR_ARG;
+    // column tiles need enough columns to fill the machine (16 per CTA); tiny problems are launch-bound either way
+    const int impl = current_impl();
+    const bool want_col = impl == 2 || (impl == 0 && (B >= 16 * 64 || T * B <= 16384));
+    if (col_ok && (want_col || !row_ok)) return launch_coltile(f, grads, out, workspace, workspace_bytes, st);
+    if (!row_ok) return B200RL_ERR_ARG;
     return grads ? dispatch_fused<true>(f, out, workspace, workspace_bytes, st)
                  : dispatch_fused<false>(f, out, workspace, workspace_bytes, st);
 }

@@ -1,0 +1,25 @@
+#pragma once
+// Arguments shared by the two implementations of the one-launch learner step gae -> ppo_error:
+// fused.cu (row tiles + cross-CTA chunk counters) and coltile.cu (column tiles, no cross-CTA dependency).
+#include "ppo_math.cuh"
+
+namespace b200rl {
+
+struct FusedArgs {
+    PpoArgs p;  // p.adv = the (T*B) advantage buffer this kernel WRITES (phase G) and reads (phase P)
+    const float* value;
+    float* next_value;
+    const float* reward;
+    const float* done;
+    const float* traj;
+    long long T, B;
+    float gamma, gl;
+    int mask_inplace;
+    int trace;
+};
+
+// coltile.cu
+bool coltile_ok(const FusedArgs& f);
+int launch_coltile(const FusedArgs& f, bool grads, float* out, float* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace b200rl

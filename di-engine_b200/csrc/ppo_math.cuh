@@ -178,11 +178,13 @@ struct PpoUpstream {
 // One row (thread = row `tid` of the tile staged at `st`): softmax statistics, clipped surrogate, value term, optional
 // KL, loss partial sums (LOSSES) and the gradient row (GRADS; into the shared-memory tile `gtile` for full tiles, straight
 // to global memory for the ragged last tile).  `adv` is passed by value (staged by TMA in ppo.cu, read from L2 right
-// after the GAE scan produced it in fused.cu).
+// after the GAE scan produced it in fused.cu).  The destinations are explicit: `gr` receives the row's N logit gradients
+// (it may alias the row's own logit_new slot in `st`: every read of that slot precedes the write) and `gv` the value
+// gradient.
 template <int NC, bool LOSSES, bool GRADS>
-__device__ __forceinline__ void ppo_row_compute(const PpoArgs& a, const PpoTileLayout& L, const unsigned char* st,
-                                                int tid, int N, float adv, bool full_tile, float* gtile,
-                                                long long row0, const PpoUpstream& up, float (&acc)[6]) {
+__device__ __forceinline__ void ppo_row_compute_to(const PpoArgs& a, const PpoTileLayout& L, const unsigned char* st,
+                                                   int tid, int N, float adv, float* gr, float* gv,
+                                                   const PpoUpstream& up, float (&acc)[6]) {
     const bool has_pre = a.logit_pre != nullptr, has_w = a.weight != nullptr;
     const float g_pol = up.g_pol, g_val = up.g_val, g_ent = up.g_ent, g_kl = up.g_kl, inv_s = up.inv_s;
     {
@@ -265,8 +267,6 @@ __device__ __forceinline__ void ppo_row_compute(const PpoArgs& a, const PpoTileL
                 // grad z_j = c_act*(1[j==a] - p_j) - c_ent*p_j*(logp_j + H),  logp_j = ln2*t_j - log_s
                 //          = p_j*(k0 - k1*t_j) + 1[j==a]*c_act
                 const float k0 = -c_act - c_ent * (ent - log_s), k1 = c_ent * kLn2;
-                const bool via_smem = full_tile && !(a.dbg & 4);
-                float* gr = via_smem ? gtile + tid * N : a.grad_logit + (row0 + tid) * N;
                 if (NC) {
                     float gj[NR];
 #pragma unroll
@@ -284,9 +284,20 @@ __device__ __forceinline__ void ppo_row_compute(const PpoArgs& a, const PpoTileL
                         gr[j] = g;
                     }
                 }
-                a.grad_value[row0 + tid] = g_val * 0.5f * w * inv_s * dterm;
+                *gv = g_val * 0.5f * w * inv_s * dterm;
             }
         }
+}
+
+// row `tid` of a tile of consecutive rows starting at global row `row0` (ppo.cu, fused.cu)
+template <int NC, bool LOSSES, bool GRADS>
+__device__ __forceinline__ void ppo_row_compute(const PpoArgs& a, const PpoTileLayout& L, const unsigned char* st,
+                                                int tid, int N, float adv, bool full_tile, float* gtile,
+                                                long long row0, const PpoUpstream& up, float (&acc)[6]) {
+    const bool via_smem = full_tile && !(a.dbg & 4);
+    float* gr = GRADS ? (via_smem ? gtile + tid * N : a.grad_logit + (row0 + tid) * N) : nullptr;
+    float* gv = GRADS ? a.grad_value + row0 + tid : nullptr;
+    ppo_row_compute_to<NC, LOSSES, GRADS>(a, L, st, tid, N, adv, gr, gv, up, acc);
 }
 
 }  // namespace b200rl

@@ -290,7 +290,26 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
         __syncthreads();
         if (threadIdx.x < TC && c0 + threadIdx.x < B) {
             const int cc = threadIdx.x;
-            for (int r = rows - 1; r >= 0; --r) {
+            // 16 rows at a time: the shared-memory operands of the next 16 steps are in registers before the dependent
+            // chain needs them, so each step costs only its 4 dependent fp32 operations
+            constexpr int U = 16;
+            int r = rows - 1;
+            for (; r >= U - 1; r -= U) {
+                float rr[U], mm[U], dd[U], cq[U];
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    rr[j] = s_r[r - j][cc];
+                    mm[j] = s_m[r - j][cc];
+                    dd[j] = s_disc[r - j][cc];
+                    cq[j] = s_c[r - j][cc];
+                }
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    carry = fadd(rr[j], fmul(mm[j], fadd(fmul(dd[j], carry), cq[j])));
+                    s_r[r - j][cc] = carry;
+                }
+            }
+            for (; r >= 0; --r) {
                 carry = fadd(s_r[r][cc], fmul(s_m[r][cc], fadd(fmul(s_disc[r][cc], carry), s_c[r][cc])));
                 s_r[r][cc] = carry;
             }

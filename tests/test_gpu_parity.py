@@ -310,14 +310,29 @@ def _fused_vs_oracle(T, B, N, seed, mix=(1.0, 0.5, -0.01, 0.0), done='float', tr
             assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max()), k
 
 
+@pytest.fixture(params=['row', 'col'])
+def gae_ppo_impl(request):
+    """run the one-launch step through each of its two kernels (csrc/fused.cu row tiles, csrc/coltile.cu column tiles)"""
+    from di_engine_b200 import ops
+    old = ops.lib().b200rl_gae_ppo_set_impl({'row': 1, 'col': 2}[request.param])
+    yield request.param
+    ops.lib().b200rl_gae_ppo_set_impl(old)
+
+
 @pytest.mark.parametrize('shape', [(128, 4096, 6), (128, 512, 6), (100, 36, 6), (300, 64, 4), (1, 8, 3), (33, 20, 11),
-                                   (64, 260, 18), (7, 6, 6)])
-def test_fused_gae_ppo_matches_oracle(shape):
+                                   (64, 260, 18), (7, 6, 6), (257, 48, 6), (32, 16, 2), (5, 4, 7), (129, 1028, 6)])
+def test_fused_gae_ppo_matches_oracle(shape, gae_ppo_impl):
     T, B, N = shape
     _fused_vs_oracle(T, B, N, seed=500 + T)
 
 
-def test_fused_gae_ppo_variants():
+def test_fused_gae_ppo_auto_dispatch():
+    _fused_vs_oracle(128, 2048, 6, 700)  # B >= 1024 -> column tiles
+    _fused_vs_oracle(64, 512, 6, 701)    # -> row tiles
+    _fused_vs_oracle(16, 64, 6, 702)     # tiny -> column tiles
+
+
+def test_fused_gae_ppo_variants(gae_ppo_impl):
     _fused_vs_oracle(96, 128, 6, 600, weight='tensor', dual_clip=3.0)
     _fused_vs_oracle(96, 128, 5, 601, pretrained=True, kl_type='k3', mix=(1.0, 0.5, -0.01, 0.2))
     _fused_vs_oracle(96, 128, 6, 602, done=None, traj=None, use_value_clip=False)
@@ -328,7 +343,7 @@ def test_fused_gae_ppo_variants():
     _fused_vs_oracle(96, 128, 40, 607)  # N > 32 -> fallback
 
 
-def test_fused_gae_ppo_repeatable_under_graph_capture():
+def test_fused_gae_ppo_repeatable_under_graph_capture(gae_ppo_impl):
     from di_engine_b200 import ops
     T, B, N = 128, 512, 6
     hb = __import__('bench').make_batch(3, T=T, B=B, N=N)
@@ -359,7 +374,7 @@ def test_fused_gae_ppo_repeatable_under_graph_capture():
             g.replay()
     s.synchronize()
     for k in eager:
-        if k == 'p':  # loss scalar: dynamic tile hand-out -> summation order may differ in the last bits
+        if k == 'p' and gae_ppo_impl == 'row':  # dynamic tile hand-out -> summation order may differ in the last bits
             assert torch.allclose(res[k], eager[k], rtol=1e-6, atol=1e-7), k
         else:
             assert torch.equal(res[k], eager[k]), k
