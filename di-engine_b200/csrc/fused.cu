@@ -362,7 +362,8 @@ extern "C" int b200rl_gae_ppo_supported(const float* value, const float* next_va
 }
 
 // implementation of the one-launch step: 0 = automatic, 1 = row tiles with chunk counters (gae_ppo_kernel, this file),
-// 2 = column tiles (gae_ppo_col_kernel, coltile.cu).  Initial value from B200RL_GAE_PPO_IMPL=row|col.
+// 2 = column tiles, best kernel (colws.cu, else coltile.cu), 3 = column tiles, coltile.cu only, 4 = column tiles, TMA
+// kernel of coltma.cu where it supports the call.  Initial value from B200RL_GAE_PPO_IMPL=row|col.
 static int g_impl = -1;
 static int current_impl() {
     if (g_impl < 0) {
@@ -372,7 +373,7 @@ static int current_impl() {
     return g_impl;
 }
 extern "C" int b200rl_gae_ppo_set_impl(int impl) {
-    if (impl < 0 || impl > 2) return B200RL_ERR_ARG;
+    if (impl < 0 || impl > 4) return B200RL_ERR_ARG;
     const int old = current_impl();
     g_impl = impl;
     return old;
@@ -407,8 +408,9 @@ extern "C" int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, co
     if (!row_ok && !col_ok) return B200RL_ERR_ARG;
     // column tiles need enough columns to fill the machine (16 per CTA); tiny problems are launch-bound either way
     const int impl = current_impl();
-    const bool want_col = impl == 2 || (impl == 0 && (B >= 16 * 64 || T * B <= 16384));
-    if (col_ok && (want_col || !row_ok)) return launch_coltile(f, grads, out, workspace, workspace_bytes, st);
+    const bool want_col = impl >= 2 || (impl == 0 && (B >= 16 * 64 || T * B <= 16384));
+    if (col_ok && (want_col || !row_ok))
+        return launch_coltile(f, grads, impl == 3 ? 1 : impl == 4 ? 2 : 0, out, workspace, workspace_bytes, st);
     if (!row_ok) return B200RL_ERR_ARG;
     return grads ? dispatch_fused<true>(f, out, workspace, workspace_bytes, st)
                  : dispatch_fused<false>(f, out, workspace, workspace_bytes, st);

@@ -18,8 +18,16 @@ struct FusedArgs {
     int trace;
 };
 
-// coltile.cu
+// column-tile implementations.  coltile.cu: all threads copy (cp.async) and compute; it also hosts the dispatcher:
+// variant 0 = best available (colws > coltile), 1 = coltile.cu only, 2 = coltma.cu if it supports the call, 3 = colws.cu
 bool coltile_ok(const FusedArgs& f);
-int launch_coltile(const FusedArgs& f, bool grads, float* out, float* ws, size_t ws_bytes, cudaStream_t st);
+int launch_coltile(const FusedArgs& f, bool grads, int variant, float* out, float* ws, size_t ws_bytes,
+                   cudaStream_t st);
+// colws.cu (warp-specialised: loader / scanner / consumer warps, mbarrier pipeline, cp.async copies)
+bool colws_ok(const FusedArgs& f);
+int launch_colws(const FusedArgs& f, bool grads, float* out, float* ws, size_t ws_bytes, cudaStream_t st);
+// coltma.cu (2-D tensor-map TMA copies)
+bool coltma_ok(const FusedArgs& f);
+int launch_coltma(const FusedArgs& f, bool grads, float* out, float* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace b200rl

@@ -180,10 +180,13 @@ B200RL_API int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, co
                             double clip_ratio, int use_value_clip, double dual_clip, int kl_type,
                             const float* g_expected, float* g_used, float* adv, float* out, float* grad_logit_new,
                             float* grad_value_new, float* workspace, size_t workspace_bytes, void* stream);
-/* Two kernels implement the call above: column tiles (csrc/coltile.cu: a CTA owns 16 batch columns for all T, runs their
- * scan and their ppo_error rows -- no cross-CTA dependency; chosen when B >= 1024 or T*B <= 16384) and row tiles
- * (csrc/fused.cu: scan CTAs publish 32-step chunks that the PPO tiles of all CTAs consume).  impl: 0 automatic (default),
- * 1 row tiles, 2 column tiles; returns the previous setting (or B200RL_ERR_ARG).  Tuning / test hook, process-wide. */
+/* Kernels behind the call above.  Column tiles: a CTA owns 16 batch columns for all T and runs their scan and their
+ * ppo_error rows -- no cross-CTA dependency; chosen when B >= 1024 or T*B <= 16384.  Three builds of that scheme exist:
+ * csrc/colws.cu (warp-specialised loader / scanner / consumer warps on an mbarrier pipeline, cp.async copies; the default),
+ * csrc/coltile.cu (every thread copies and computes; any N <= 32) and csrc/coltma.cu (2-D tensor-map TMA copies;
+ * N <= 16, T % 128 == 0).  Row tiles: csrc/fused.cu (scan CTAs publish 32-step chunks that the PPO tiles of all CTAs
+ * consume).  impl: 0 automatic (default), 1 row tiles, 2 column tiles (best build), 3 coltile.cu, 4 coltma.cu; returns the
+ * previous setting (or B200RL_ERR_ARG).  Tuning / test hook, process-wide. */
 B200RL_API int b200rl_gae_ppo_set_impl(int impl);
 
 /* ---- data-parallel exchange step: one-shot all-reduce (mean) of n <= 8 floats over NVLink peer memory -----------

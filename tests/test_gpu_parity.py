@@ -310,11 +310,13 @@ def _fused_vs_oracle(T, B, N, seed, mix=(1.0, 0.5, -0.01, 0.0), done='float', tr
             assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max()), k
 
 
-@pytest.fixture(params=['row', 'col'])
+@pytest.fixture(params=['row', 'col', 'colcp', 'coltma'])
 def gae_ppo_impl(request):
-    """run the one-launch step through each of its two kernels (csrc/fused.cu row tiles, csrc/coltile.cu column tiles)"""
+    """run the one-launch step through each of its kernels: csrc/fused.cu (row tiles), csrc/colws.cu (column tiles,
+    warp-specialised; the default), csrc/coltile.cu (column tiles, all threads copy and compute) and csrc/coltma.cu
+    (column tiles, TMA; falls through to coltile.cu for N > 16, B < 16 or T % 128 != 0)"""
     from di_engine_b200 import ops
-    old = ops.lib().b200rl_gae_ppo_set_impl({'row': 1, 'col': 2}[request.param])
+    old = ops.lib().b200rl_gae_ppo_set_impl({'row': 1, 'col': 2, 'colcp': 3, 'coltma': 4}[request.param])
     yield request.param
     ops.lib().b200rl_gae_ppo_set_impl(old)
 

@@ -28,7 +28,7 @@ def reset(s):
 
 s = sets[0]
 reset(s); s.gae(); s.ppo_fwd_grad(); ref = snapshot(s)
-for name, impl in (('row', 1), ('col', 2)):
+for name, impl in (('row', 1), ('col', 2), ('colcp', 3), ('coltma', 4)):
     L.b200rl_gae_ppo_set_impl(impl)
     reset(s); s.gae_ppo_fwd_grad(); got = snapshot(s)
     ok = {
@@ -57,7 +57,7 @@ def one(s):
 
 
 res['step3_us'] = round(timed([lambda s=s: three(s) for s in sets], reps=30), 2)
-for name, impl in (('row', 1), ('col', 2)):
+for name, impl in (('row', 1), ('col', 2), ('colcp', 3), ('coltma', 4)):
     L.b200rl_gae_ppo_set_impl(impl)
     res['onepass_%s_us' % name] = round(timed([s.gae_ppo_fwd_grad for s in sets], reps=30), 2)
     res['step1_%s_us' % name] = round(timed([lambda s=s: one(s) for s in sets], reps=30), 2)
