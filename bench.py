@@ -7,11 +7,13 @@ Metric (BASELINE.json): learner transitions/sec, config D = Atari-PPO shape T=12
 (``pong_ppo_config.py``: gamma 0.99, lambda 0.95, clip 0.2, value clip on).  One step = one pass of
 gae -> ppo_error forward -> backward(policy + 0.5 value - 0.01 entropy) over one batch of 524 288 transitions per GPU.
 
-  value     inputs resident in HBM; the three kernels replayed as a CUDA graph; input/output buffer sets are rotated
-            so that consecutive steps never find their data in the 126 MB L2 (4 sets x 67 MB); timed with CUDA events
-            on the launching stream between barrier + synchronize, max over ranks.
-  e2e       the same step through the public API (di_engine_b200.gae / ppo_error / backward) starting from PINNED
-            HOST buffers: per step H2D copy of every input, the three kernels, D2H read of the loss scalars.
+  value     inputs resident in HBM; the step's kernels (default: the one-launch gae+ppo_error step of csrc/colws.cu, its
+            finalize_sums and the backward's verification launch; --three / --unfused: the separate operators) replayed
+            as a CUDA graph; input/output buffer sets are rotated so that consecutive steps never find their data in the
+            126 MB L2 (4 sets x 67 MB); timed with CUDA events on the launching stream between barrier + synchronize,
+            max over ranks.
+  e2e       the same step through the public API (di_engine_b200.gae_ppo_error / backward; --three: gae, ppo_error)
+            starting from PINNED HOST buffers: per step H2D copy of every input, the kernels, D2H read of the loss.
   roofline  per-kernel CUDA-event timing of the dominant kernel against MEASURED_PEAKS.json (HBM copy bandwidth).
   cpu_baseline / --impl reference
             the reference algorithm on the host cores: oracle/rl_oracle.py, the torch-CPU restatement that is pinned
@@ -319,7 +321,7 @@ def run_gpu(args):
 
     K, W = args.steps, args.warmup
     NSETS = 4
-    mode = False if args.unfused else ('onepass' if args.onepass else True)
+    mode = False if args.unfused else (True if args.three else 'onepass')
     sets = [DeviceStep(make_batch(1000 * rank + i), dev, fused=mode) for i in range(NSETS)]
     step_bytes = ALG_BYTES_PER_TR['step'] * T_LEN * B_COLS
     side = torch.cuda.Stream()
@@ -500,7 +502,7 @@ def run_gpu(args):
         ln = d['logit_new'].requires_grad_(True)
         vn = d['value_new'].requires_grad_(True)
         gd = b2.gae_data(d['value'], d['next_value'], d['reward'], d['done'], d['traj_flag'])
-        if args.onepass:
+        if not (args.three or args.unfused):
             adv, loss, info = b2.gae_ppo_error(
                 gd, b2.ppo_data(ln, d['logit_old'], d['action'], vn, d['value_old'], None, d['return_'], None, None),
                 GAMMA, LAMBDA, CLIP, True, None)
@@ -631,8 +633,10 @@ def main():
     ap.add_argument('--collective', default='auto', choices=['auto', 'p2p', 'nccl'],
                     help='N>1: exchange of the loss scalars (auto = NVLink peer-memory kernel, NCCL if unavailable)')
     ap.add_argument('--unfused', action='store_true', help='separate gae / ppo forward / ppo backward kernels')
-    ap.add_argument('--onepass', action='store_true',
-                    help='one-pass gae+ppo kernel + verification (default: gae, fused ppo forward+grad, verification)')
+    ap.add_argument('--three', action='store_true',
+                    help='gae, fused ppo forward+grad, verification as three kernels (default: the one-launch gae+ppo '
+                         'step of csrc/colws.cu + verification)')
+    ap.add_argument('--onepass', action='store_true', help='accepted for compatibility: the one-launch step is the default')
     args = ap.parse_args()
     if args.impl == 'reference':
         if args.steps > 400:

@@ -8,7 +8,8 @@ import os
 from ctypes import c_double, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200rl.so")
+# B200RL_LIB: load another build of the same ABI (tuning experiments build variants next to the default library)
+LIB_PATH = os.environ.get("B200RL_LIB") or os.path.join(_HERE, "lib", "libb200rl.so")
 
 P = c_void_p  # device pointer
 LL = c_longlong

@@ -20,6 +20,14 @@
 //              row code of ppo.cu) and store the gradient row and the value gradient straight to HBM; arrive on "done".
 // Rings run across tile boundaries (static tile -> CTA assignment: deterministic loss partial sums).
 //
+// Measured at config D (profiles/r01h_*): once the ring is primed the chunks land every 1.28 us per CTA, i.e. 6.5 TB/s over
+// the 256 CTAs -- the measured HBM peak; the kernel's 15.4 us are 10.2 us of streaming plus ~2.5 us until the first chunk
+// has landed and ~2.5 us of tail (last chunk's math, store drain, partial sums, finalize_sums launch).  Loader variants
+// tried and rejected (tools/sweep_col.py, B200RL_LIB builds): loop-invariant piece offsets in registers with one or two
+// loader warps (ring refilled in 0.25 us instead of 1 us: 16.4-17.4 us -- the burst of 4 stages x 296 CTAs delays chunk 0
+// and costs DRAM efficiency), the same with a throttled prologue (17.4 us), no unrolling of the copy loop (19.5 us),
+// 2 or 3 ring stages (+0.4 .. +1.7 us).
+//
 // Algorithmic traffic: 24 B (GAE) + 104 B (ppo_error forward + gradients, N = 6) = 128 B per transition, each byte once.
 #include "../../include/b200rl.h"
 #include "fused_args.cuh"
@@ -64,7 +72,9 @@ __host__ __device__ inline int cw_stage_bytes(int N, bool has_pre, bool has_w) {
 
 template <int NC, bool GRADS>
 __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, float* ws, int n_stages) {
-    pdl_prologue();
+    // PDL: the next kernel may start launching right away; the wait for the previous kernels' results comes after the
+    // barrier set-up below (nothing before it touches global memory except the optional trace stamp): -0.2 us measured
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(128) unsigned char smem[];
     const PpoArgs& a = f.p;
     const int N = NC ? NC : a.N;
@@ -108,6 +118,7 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
         }
         mbar_fence_init();
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
 
     auto item_valid = [&](const CwItem& it) { return it.tile < n_tiles; };
