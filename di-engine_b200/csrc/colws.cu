@@ -43,19 +43,6 @@ constexpr int CW_MAX_STAGES = 4;
 constexpr int CW_RAW_ARR = CW_R * CW_TC * 4;  // bytes of one raw GAE array chunk
 constexpr int CW_RAW_BYTES = 5 * CW_RAW_ARR;  // value | next_value | reward | done | traj_flag
 
-__device__ __forceinline__ void cpa16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cpa_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-// arrive on `bar` once all cp.async issued so far by this thread have landed (counts against the barrier's init count)
-__device__ __forceinline__ void cpa_mbar_arrive(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 #define CW_TRACE(slot)                                                                                   \
     do {                                                                                                 \
         if (f.trace) reinterpret_cast<unsigned long long*>(ws + 65536)[blockIdx.x * 32 + (slot)] = gtimer(); \

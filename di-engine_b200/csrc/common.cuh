@@ -291,6 +291,22 @@ __device__ __forceinline__ void tma_store_wait_all() {
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
+// 16-byte cp.async (LDGSTS) copies: per-thread groups, or completion counted on an mbarrier
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cpa16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (counts against the barrier's init count)
+__device__ __forceinline__ void cpa_mbar_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  Every kernel of this library starts with pdl_prologue(): it lets the NEXT
 // kernel in the stream begin launching right away (its launch latency and prologue overlap this kernel's execution) and
 // then waits until all PREVIOUS kernels in the stream have completed and flushed their results -- so the usual stream

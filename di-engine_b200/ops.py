@@ -188,6 +188,7 @@ class PPOFunction(torch.autograd.Function):
         ctx.bwd_calls += 1
         if ctx.fused and first:
             grad_logit, grad_value, g_used = ctx.spec  # valid if the expectation held; the kernel checks on the device
+            ctx.spec = None  # sole owner now: autograd can adopt the buffers as .grad instead of cloning them
             p_used, p_hint = ptr(g_used), ptr(ppo_hint(dev))
         else:  # no fused forward, or a repeated backward (the first call's buffers may now belong to .grad)
             grad_logit = torch.empty_like(logit_new)
@@ -410,6 +411,22 @@ class UPGOFunction(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------------------------
 # V-trace
 # ----------------------------------------------------------------------------------------------------------------
+# The one-launch kernel (csrc/vtws.cu) writes the gradients in the forward pass for the upstream gradients it expects (the
+# loss weights of the training loop, remembered on the device from the previous backward pass; IMPALA's defaults to start
+# with); backward() verifies them on the device and only recomputes on a mismatch.  False: rows / scan / backward kernels.
+VTRACE_FUSED = True
+_VT_HINT = {}
+
+
+def vtrace_hint(device):
+    """Device-resident expectation of (d total/d policy_loss, d/d value_loss, d/d entropy_loss)."""
+    h = _VT_HINT.get(device.index)
+    if h is None:
+        h = torch.tensor([1.0, 0.5, -0.01], dtype=torch.float32, device=device)
+        _VT_HINT[device.index] = h
+    return h
+
+
 class VTraceFunction(torch.autograd.Function):
 
     @staticmethod
@@ -419,31 +436,72 @@ class VTraceFunction(torch.autograd.Function):
         N = target_output.shape[-1]
         dev = target_output.device
         out = torch.empty(4, dtype=torch.float32, device=dev)
-        lp = torch.empty(T, B, dtype=torch.float32, device=dev)
-        cpg = torch.empty(T, B, dtype=torch.float32, device=dev)
-        dv = torch.empty(T, B, dtype=torch.float32, device=dev)
+        L = lib()
+        tensors = (ptr(target_output), ptr(behaviour_output), ptr(action), ptr(value), ptr(reward), ptr(weight))
+        want_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        ctx.cfg = (T, B, N)
+        ctx.fused = False
+        ctx.bwd_calls = 0
         with torch.cuda.device(dev):
             ws = workspace(dev)
-            rc = lib().b200rl_vtrace_fwd(
-                ptr(target_output), ptr(behaviour_output), ptr(action), ptr(value), ptr(reward), ptr(weight), T, B, N,
-                gamma, lambda_, rho_clip, c_clip, rho_pg_clip, ptr(out), ptr(lp), ptr(cpg), ptr(dv), ptr(ws),
-                ws.numel() * 4, stream_ptr()
+            if VTRACE_FUSED:
+                grad_logit = torch.empty_like(target_output) if want_grad else None
+                grad_value = torch.empty(T + 1, B, dtype=torch.float32, device=dev) if want_grad else None
+                if L.b200rl_vtrace_fused_supported(*tensors, T, B, N, ptr(grad_logit), ptr(grad_value)):
+                    g_used = torch.empty(3, dtype=torch.float32, device=dev) if want_grad else None
+                    rc = L.b200rl_vtrace_fwd_grad(
+                        *tensors, T, B, N, gamma, lambda_, rho_clip, c_clip, rho_pg_clip,
+                        ptr(vtrace_hint(dev)) if want_grad else None, 0, None, None, None, ptr(g_used), None, ptr(out),
+                        ptr(grad_logit), ptr(grad_value), ptr(ws), ws.numel() * 4, stream_ptr()
+                    )
+                    _lib.check(rc, 'b200rl_vtrace_fwd_grad')
+                    ctx.fused = True
+                    ctx.spec = (grad_logit, grad_value, g_used)
+                    ctx.scal = (gamma, lambda_, rho_clip, c_clip, rho_pg_clip)
+                    ctx.save_for_backward(target_output, behaviour_output, action, value, reward, weight)
+                    return out[0], out[1], out[2]
+            lp = torch.empty(T, B, dtype=torch.float32, device=dev)
+            cpg = torch.empty(T, B, dtype=torch.float32, device=dev)
+            dv = torch.empty(T, B, dtype=torch.float32, device=dev)
+            rc = L.b200rl_vtrace_fwd(
+                *tensors, T, B, N, gamma, lambda_, rho_clip, c_clip, rho_pg_clip, ptr(out), ptr(lp), ptr(cpg), ptr(dv),
+                ptr(ws), ws.numel() * 4, stream_ptr()
             )
         _lib.check(rc, 'b200rl_vtrace_fwd')
         ctx.save_for_backward(target_output, action, weight, cpg, dv)
-        ctx.cfg = (T, B, N)
         return out[0], out[1], out[2]
 
     @staticmethod
     def backward(ctx, g_p, g_v, g_e):
-        target_output, action, weight, cpg, dv = ctx.saved_tensors
         T, B, N = ctx.cfg
-        dev = target_output.device
-        grad_logit = torch.empty_like(target_output)
-        grad_value = torch.empty(T + 1, B, dtype=torch.float32, device=dev)
         kp, pp = _g(g_p)
         kv, pv = _g(g_v)
         ke, pe = _g(g_e)
+        if ctx.fused:
+            target_output, behaviour_output, action, value, reward, weight = ctx.saved_tensors
+            dev = target_output.device
+            first = ctx.bwd_calls == 0
+            ctx.bwd_calls += 1
+            if first:
+                grad_logit, grad_value, g_used = ctx.spec  # valid if the expectation held; the kernel checks on the device
+                ctx.spec = None  # sole owner now: autograd can adopt the buffers as .grad instead of cloning them
+            else:  # a repeated backward: the first call's buffers may now belong to .grad -> recompute into fresh ones
+                grad_logit = torch.empty_like(target_output)
+                grad_value = torch.empty(T + 1, B, dtype=torch.float32, device=dev)
+                g_used = torch.full((3, ), float('nan'), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                ws = workspace(dev)
+                rc = lib().b200rl_vtrace_fwd_grad(
+                    ptr(target_output), ptr(behaviour_output), ptr(action), ptr(value), ptr(reward), ptr(weight), T, B,
+                    N, *ctx.scal, None, 1, pp, pv, pe, ptr(g_used), ptr(vtrace_hint(dev)), None, ptr(grad_logit),
+                    ptr(grad_value), ptr(ws), ws.numel() * 4, stream_ptr()
+                )
+            _lib.check(rc, 'b200rl_vtrace_fwd_grad(verify)')
+            return (grad_logit, grad_value) + (None, ) * 9
+        target_output, action, weight, cpg, dv = ctx.saved_tensors
+        dev = target_output.device
+        grad_logit = torch.empty_like(target_output)
+        grad_value = torch.empty(T + 1, B, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = lib().b200rl_vtrace_bwd(
                 ptr(target_output), ptr(action), ptr(weight), ptr(cpg), ptr(dv), pp, pv, pe, T, B, N, ptr(grad_logit),

@@ -160,6 +160,28 @@ B200RL_API int b200rl_vtrace_bwd(const float* target_output, const long long* ac
                       const float* g_entropy, long long T, long long B, long long N, float* grad_target_output,
                       float* grad_value, void* stream);
 
+/* ---- V-trace in one launch: forward AND gradients (csrc/vtws.cu) ---------------------------------------------------
+ * Same semantics as b200rl_vtrace_fwd followed by b200rl_vtrace_bwd, but the batch crosses HBM once (96 B per transition at
+ * N = 6): column tiles, warp-specialised loader / scanner / consumer warps.  The gradients are produced in the forward
+ * launch (verify = 0) for the upstream gradients g_expected[3] = d total / d (policy, value, entropy) loss and the values
+ * used are recorded in g_used[3].  backward() calls the function again with verify = 1 and the actual upstream gradients
+ * (device scalars, null = 0): the launch is a no-op when they equal g_used, otherwise everything is recomputed with the
+ * actual values (exact for any upstream gradient, no host sync); g_hint (nullable) is refreshed with the actual values.
+ * grad_target_output == null (verify = 0 only): losses only.  out3 is written by the verify = 0 launch only.
+ * Requires b200rl_vtrace_fused_supported(...) == 1 (N <= 32 with the ring fitting two CTAs per SM, B % 4 == 0, 16-byte
+ * aligned tensors). */
+B200RL_API int b200rl_vtrace_fused_supported(const float* target_output, const float* behaviour_output,
+                                  const long long* action, const float* value, const float* reward,
+                                  const float* weight, long long T, long long B, long long N,
+                                  const float* grad_target_output, const float* grad_value);
+B200RL_API int b200rl_vtrace_fwd_grad(const float* target_output, const float* behaviour_output, const long long* action,
+                           const float* value, const float* reward, const float* weight, long long T, long long B,
+                           long long N, double gamma, double lambda_, double rho_clip_ratio, double c_clip_ratio,
+                           double rho_pg_clip_ratio, const float* g_expected, int verify, const float* g_policy,
+                           const float* g_value, const float* g_entropy, float* g_used, float* g_hint, float* out3,
+                           float* grad_target_output, float* grad_value, float* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* ---- fused learner step: gae (gae.py:25-70) followed by ppo_error (ppo.py:77-140) in ONE launch ------------------
  * Semantics are exactly b200rl_gae(value, next_value, reward, done, traj_flag -> adv) followed by b200rl_ppo_fwd_grad
  * (or b200rl_ppo_fwd when g_expected is null) with that adv, S = T*B, G = 1 -- same arithmetic, bit-identical adv.

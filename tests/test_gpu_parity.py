@@ -382,6 +382,106 @@ def test_fused_gae_ppo_repeatable_under_graph_capture(gae_ppo_impl):
             assert torch.equal(res[k], eager[k]), k
 
 
+def _vtrace_once(t, p, mix, device=DEV, retain=False, grad=True):
+    td = cases.prepare('vtrace', t, device)
+    if not grad:
+        td = {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in td.items()}
+    if device == 'cpu':
+        loss = rl_oracle.vtrace_error_discrete_action(**td, **p)
+    else:
+        loss = b2.vtrace_error_discrete_action(b2.vtrace_data(td['target_output'], td['behaviour_output'], td['action'],
+                                                              td['value'], td['reward'], td['weight']), **p)
+    total = sum(c * l for c, l in zip(mix, loss))
+    if grad:
+        total.backward(retain_graph=retain)
+    return td, loss, total
+
+
+def _vtrace_close(td, tw, loss, lw):
+    for got, want in zip(loss, lw):
+        assert torch.allclose(got.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-5)
+    for k in ('target_output', 'value'):
+        a, b = td[k].grad.cpu().numpy(), tw[k].grad.numpy()
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max()), k
+
+
+@pytest.mark.parametrize('shape', [(64, 8192, 6), (70, 48, 6), (16, 16, 2), (5, 4, 7), (33, 20, 11), (130, 1028, 6),
+                                   (1, 8, 3), (40, 64, 12)])
+def test_vtrace_one_launch_kernel_matches_oracle(shape):
+    """csrc/vtws.cu through the public operator: forward + gradients in one launch, device-verified backward"""
+    T, B, N = shape
+    from di_engine_b200 import ops
+    op, t, p = cases.vtrace_case(900 + T, T, B, N, weight='tensor' if T % 2 else 'none', gamma=0.99, lambda_=0.95,
+                                 rho_clip_ratio=0.9, c_clip_ratio=1.1, rho_pg_clip_ratio=1.3)
+    L = ops.lib()
+    d = cases.prepare('vtrace', t, DEV)
+    assert L.b200rl_vtrace_fused_supported(ops.ptr(d['target_output']), ops.ptr(d['behaviour_output']),
+                                           ops.ptr(d['action']), ops.ptr(d['value']), ops.ptr(d['reward']),
+                                           ops.ptr(d['weight']), T, B, N, None, None) == 1
+    for mix in ([1.0, 0.5, -0.01], [0.3, 1.7, 0.2], [0.3, 1.7, 0.2]):  # expected, unexpected, then expected again
+        tw, lw, _ = _vtrace_once(t, p, mix, device='cpu')
+        td, loss, _ = _vtrace_once(t, p, mix)
+        _vtrace_close(td, tw, loss, lw)
+    ops.vtrace_hint(torch.device(DEV)).copy_(torch.tensor([1.0, 0.5, -0.01]))
+
+
+def test_vtrace_one_launch_repeated_backward_nograd_legacy_and_fallback():
+    from di_engine_b200 import ops
+    op, t, p = cases.vtrace_case(950, 48, 64, 6, weight='tensor')
+    mix = [1.0, 0.5, -0.01]
+    tw, lw, _ = _vtrace_once(t, p, mix, device='cpu')
+    td, loss, total = _vtrace_once(t, p, mix, retain=True)
+    g1 = td['target_output'].grad.clone()
+    total.backward()  # second backward through the same graph accumulates the same gradient again
+    assert torch.allclose(td['target_output'].grad, 2 * g1, rtol=1e-6, atol=0)
+    with torch.no_grad():
+        _, l2, _ = _vtrace_once(t, p, mix, grad=False)
+    for got, want in zip(l2, lw):
+        assert torch.allclose(got.cpu(), want.detach(), rtol=1e-5, atol=1e-5)
+    ops.VTRACE_FUSED = False  # rows / scan / backward kernels of csrc/pg.cu
+    try:
+        td3, l3, _ = _vtrace_once(t, p, mix)
+    finally:
+        ops.VTRACE_FUSED = True
+    _vtrace_close(td3, tw, l3, lw)
+    assert torch.allclose(td3['target_output'].grad, g1, rtol=1e-5, atol=1e-9)
+    # B % 4 != 0, or N too large for a three-stage ring -> not supported by the one-launch kernel -> pg.cu path
+    for shape in ((20, 30, 6), (24, 64, 18)):
+        op, t, p = cases.vtrace_case(951, *shape)
+        tw, lw, _ = _vtrace_once(t, p, mix, device='cpu')
+        td, loss, _ = _vtrace_once(t, p, mix)
+        _vtrace_close(td, tw, loss, lw)
+
+
+def test_vtrace_one_launch_under_graph_capture():
+    op, t, p = cases.vtrace_case(960, 64, 512, 6)
+    d = cases.prepare('vtrace', t, DEV)
+    s = torch.cuda.Stream()
+    res = {}
+
+    def step():
+        tgt = d['target_output'].detach().requires_grad_(True)
+        val = d['value'].detach().requires_grad_(True)
+        loss = b2.vtrace_error_discrete_action(b2.vtrace_data(tgt, d['behaviour_output'], d['action'], val, d['reward'],
+                                                              None), **p)
+        (loss.policy_loss + 0.5 * loss.value_loss - 0.01 * loss.entropy_loss).backward()
+        res.update(p=loss.policy_loss, v=loss.value_loss, gl=tgt.grad, gv=val.grad)
+
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            step()
+        eager = {k: v.clone() for k, v in res.items()}
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            step()
+        for _ in range(5):
+            g.replay()
+    s.synchronize()
+    for k in eager:
+        assert torch.equal(res[k], eager[k]), k
+
+
 def test_p2p_allreduce_kernel_single_rank_degenerate():
     """world = 1: the mailbox exchange must reproduce the local values (mean over one rank), across many sequence
     numbers and under CUDA-graph replay.  (Two and more ranks: tools/test_p2p.py under torchrun.)"""

@@ -158,7 +158,7 @@ class _RecordingLib:
             for a, ty in zip(args, proto):
                 ty.from_param(a)  # raises on a type ctypes could not marshal
             self.calls.append(name)
-            return 1 if name == 'b200rl_ppo_fused_supported' else 0
+            return 1 if name in ('b200rl_ppo_fused_supported', 'b200rl_vtrace_fused_supported') else 0
 
         if name == 'b200rl_workspace_bytes':
             return lambda: 1 << 20
@@ -189,7 +189,7 @@ EXPECTED_CALLS = {
     'dntd': ['b200rl_dntd_fwd', 'b200rl_dntd_bwd'],
     'td_lambda': ['b200rl_td_lambda_fwd', 'b200rl_scale'],
     'upgo': ['b200rl_lambda_returns', 'b200rl_upgo_head_fwd', 'b200rl_upgo_head_bwd'],
-    'vtrace': ['b200rl_vtrace_fwd', 'b200rl_vtrace_bwd'],
+    'vtrace': ['b200rl_vtrace_fused_supported', 'b200rl_vtrace_fwd_grad', 'b200rl_vtrace_fwd_grad'],
 }
 
 
