@@ -28,10 +28,10 @@ constexpr int VW_CW = 8;
 constexpr int VW_CT = VW_CW * 32;        // consumer threads = transitions per chunk
 constexpr int VW_LW = 1;                 // loader warps (2: warp 0 target logits, warp 1 the rest -- measured slower, 17.1 vs 16.2 us)
 constexpr int VW_THREADS = VW_CT + VW_LW * 32 + 32;  // consumers + loaders + scanner
-constexpr int VW_TC = 16;
-constexpr int VW_R = VW_CT / VW_TC;      // 16 time steps per chunk
 constexpr int VW_MAX_STAGES = 4;
-constexpr int VW_ROW = VW_TC * 4;        // bytes of one (T, B) row segment of the tile
+// tile width TC (template parameter): 16 columns x 16 time steps per chunk, or 32 x 8 when 16-column tiles would outnumber
+// the resident CTAs (config E: 512 tiles on 296 CTAs leave the second half of the kernel under-subscribed; 256 tiles of 32
+// columns all stream from start to end)
 
 struct VtFusedArgs {
     const float* target;      // (T*B, N)
@@ -68,13 +68,18 @@ struct VwItem {
     long long q;  // chunk from the top: time steps [T - (q+1)R, T - qR)
 };
 
-__host__ __device__ inline int vw_stage_bytes(int N, bool has_w) {
-    // logits x2 | action | [weight] | value rows (R+1) | reward rows | IS | vs rows (R+1)
-    return VW_CT * (2 * N * 4 + 8 + (has_w ? 4 : 0)) + (VW_R + 1) * VW_ROW + VW_R * VW_ROW + VW_CT * 4 + (VW_R + 1) * VW_ROW;
+__host__ __device__ inline int vw_stage_bytes(int N, bool has_w, int tc) {
+    // logits x2 | action | [weight] | value rows (R+1) | reward rows | IS | vs rows (R+1);  R * tc == VW_CT
+    const int row = tc * 4;
+    return VW_CT * (2 * N * 4 + 8 + (has_w ? 4 : 0)) + (VW_CT * 4 + row) + VW_CT * 4 + VW_CT * 4 + (VW_CT * 4 + row);
 }
 
-template <int NC, bool GRADS>
+template <int NC, bool GRADS, int TC>
 __global__ void __launch_bounds__(VW_THREADS, 2) vtrace_ws_kernel(VtFusedArgs a, float* ws, int S) {
+    constexpr int VW_TC = TC;             // columns per tile
+    constexpr int VW_R = VW_CT / VW_TC;   // time steps per chunk
+    constexpr int VW_ROW = VW_TC * 4;     // bytes of one (T, B) row segment of the tile
+    constexpr int PPR = VW_TC / 4;        // 16-byte pieces per (T, B) row segment
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(128) unsigned char smem[];
     const int N = NC ? NC : a.N;
@@ -151,6 +156,7 @@ __global__ void __launch_bounds__(VW_THREADS, 2) vtrace_ws_kernel(VtFusedArgs a,
                 if (row >= jmin && o < Pv) cpa16(dst + p * 16, g + row * rstride + o * 16);
             }
         };
+        // (loop-invariant piece offsets in registers, as tried in colws.cu, are slower here too: 16.1 vs 15.7 us)
         VwItem it = first;
         int s = 0, ph = 0;
         for (int j = 0; item_valid(it); ++j) {
@@ -175,18 +181,18 @@ __global__ void __launch_bounds__(VW_THREADS, 2) vtrace_ws_kernel(VtFusedArgs a,
     } else if (wid == VW_CW + VW_LW) {
         // =============================================== scanner ==========================================================
         // value rows t0 .. t0+R (R+1 rows: the bootstrap row T belongs to the newest chunk) and reward rows t0 .. t0+R-1 of
-        // chunk k go to stage k % S; 4 + 4 pieces per row
+        // chunk k go to stage k % S; TC/4 16-byte pieces per row and tensor
         auto issue_raw = [&](const VwItem& it, int sg) {
             const long long c0 = it.tile * VW_TC;
             const long long t0 = T - (it.q + 1) * VW_R;
             const int W = (int)((B - c0) < VW_TC ? (B - c0) : VW_TC);
             unsigned char* st = smem + sg * stage_bytes;
-            for (int p = lane; p < (VW_R + 1) * 4; p += 32) {
-                const int row = p >> 2, o = p & 3;
+            for (int p = lane; p < (VW_R + 1) * PPR; p += 32) {
+                const int row = p / PPR, o = p % PPR;
                 if (t0 + row >= 0 && o * 4 < W) cpa16(st + off_v + p * 16, a.value + (t0 + row) * B + c0 + o * 4);
             }
-            for (int p = lane; p < VW_R * 4; p += 32) {
-                const int row = p >> 2, o = p & 3;
+            for (int p = lane; p < VW_R * PPR; p += 32) {
+                const int row = p / PPR, o = p % PPR;
                 if (t0 + row >= 0 && o * 4 < W) cpa16(st + off_r + p * 16, a.reward + (t0 + row) * B + c0 + o * 4);
             }
         };
@@ -403,12 +409,12 @@ __global__ void __launch_bounds__(VW_THREADS, 2) vtrace_ws_kernel(VtFusedArgs a,
     if (!a.verify) grid_store_partials<3, VW_THREADS>(acc, ws);  // summed by finalize_sums_kernel
 }
 
-static size_t vw_smem(int N, bool has_w, int stages) {
-    return (size_t)stages * vw_stage_bytes(N, has_w) + 4 * VW_MAX_STAGES * sizeof(uint64_t) + 64;
+static size_t vw_smem(int N, bool has_w, int stages, int tc) {
+    return (size_t)stages * vw_stage_bytes(N, has_w, tc) + 4 * VW_MAX_STAGES * sizeof(uint64_t) + 64;
 }
-static int vw_pick_stages(int N, bool has_w) {
+static int vw_pick_stages(int N, bool has_w, int tc = 32) {
     for (int s = VW_MAX_STAGES; s >= 3; --s)
-        if (vw_smem(N, has_w, s) <= 112 * 1024) return s;  // two CTAs per SM
+        if (vw_smem(N, has_w, s, tc) <= 112 * 1024) return s;  // two CTAs per SM
     return 0;
 }
 
@@ -419,11 +425,11 @@ static bool vtws_ok(const VtFusedArgs& a) {
     return al && a.N >= 1 && a.N <= 32 && a.T >= 1 && a.B >= 4 && (a.B % 4) == 0 && vw_pick_stages(a.N, a.weight != nullptr) >= 3;
 }
 
-template <int NC, bool GRADS>
+template <int NC, bool GRADS, int TC>
 static int launch_vtws(const VtFusedArgs& a, float* out, float* ws, size_t ws_bytes, cudaStream_t st) {
-    const int stages = vw_pick_stages(a.N, a.weight != nullptr);
-    const size_t smem = vw_smem(a.N, a.weight != nullptr, stages);
-    auto kern = vtrace_ws_kernel<NC, GRADS>;
+    const int stages = vw_pick_stages(a.N, a.weight != nullptr, TC);
+    const size_t smem = vw_smem(a.N, a.weight != nullptr, stages, TC);
+    auto kern = vtrace_ws_kernel<NC, GRADS, TC>;
     static int sm_count = 0;
     static size_t smem_set = 0;
     cudaError_t e;
@@ -445,7 +451,7 @@ static int launch_vtws(const VtFusedArgs& a, float* out, float* ws, size_t ws_by
         occ_smem = smem;
     }
     if (per_sm < 1) return B200RL_ERR_ARG;
-    const long long n_tiles = (a.B + VW_TC - 1) / VW_TC;
+    const long long n_tiles = (a.B + TC - 1) / TC;
     long long grid = (long long)sm_count * per_sm;
     if (grid > n_tiles) grid = n_tiles;
     if (ws_bytes < WS_MIN_BYTES || (size_t)(WS_CTRL_WORDS + grid * 3) * sizeof(float) > ws_bytes)
@@ -463,15 +469,25 @@ static int launch_vtws(const VtFusedArgs& a, float* out, float* ws, size_t ws_by
 
 template <bool GRADS>
 static int dispatch_vtws(const VtFusedArgs& a, float* out, float* ws, size_t ws_bytes, cudaStream_t st) {
+    // 32-column tiles when the 16-column tiles would not all be resident at once (two CTAs per SM on 148 SMs);
+    // B200RL_VT_TC = 16 | 32 overrides (tuning)
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("B200RL_VT_TC");
+        forced = e ? atoi(e) : 0;
+    }
+    const bool wide = forced == 32 || (forced != 16 && (a.B + 15) / 16 > 296 && a.B >= 32);
     switch (a.N) {
-#define B200RL_CASE(n) \
-    case n:            \
-        return launch_vtws<n, GRADS>(a, out, ws, ws_bytes, st);
+#define B200RL_CASE(n)                                                         \
+    case n:                                                                    \
+        if (wide) return launch_vtws<n, GRADS, 32>(a, out, ws, ws_bytes, st);  \
+        return launch_vtws<n, GRADS, 16>(a, out, ws, ws_bytes, st);
         B200RL_CASE(2) B200RL_CASE(3) B200RL_CASE(4) B200RL_CASE(5) B200RL_CASE(6) B200RL_CASE(7) B200RL_CASE(8)
         B200RL_CASE(9) B200RL_CASE(10) B200RL_CASE(12) B200RL_CASE(14) B200RL_CASE(16) B200RL_CASE(18)
 #undef B200RL_CASE
         default:
-            return launch_vtws<0, GRADS>(a, out, ws, ws_bytes, st);
+            if (wide) return launch_vtws<0, GRADS, 32>(a, out, ws, ws_bytes, st);
+            return launch_vtws<0, GRADS, 16>(a, out, ws, ws_bytes, st);
     }
 }
 

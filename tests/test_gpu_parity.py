@@ -406,7 +406,7 @@ def _vtrace_close(td, tw, loss, lw):
 
 
 @pytest.mark.parametrize('shape', [(64, 8192, 6), (70, 48, 6), (16, 16, 2), (5, 4, 7), (33, 20, 11), (130, 1028, 6),
-                                   (1, 8, 3), (40, 64, 12)])
+                                   (1, 8, 3), (40, 64, 12), (20, 4808, 3)])  # B > 4736: 32-column tiles (the last one 8 wide), ragged T
 def test_vtrace_one_launch_kernel_matches_oracle(shape):
     """csrc/vtws.cu through the public operator: forward + gradients in one launch, device-verified backward"""
     T, B, N = shape

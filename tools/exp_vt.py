@@ -58,28 +58,33 @@ class VtStep:
 
 
 sets = [VtStep(i) for i in range(6)]
-s = sets[0]
-s.legacy_fwd(); s.legacy_bwd(); torch.cuda.synchronize()
-ref = (s.out.clone(), s.gl.clone(), s.gv.clone())
-s.gl.zero_(); s.gv.zero_(); s.out.zero_()
-s.fused(); s.verify(); torch.cuda.synchronize()
-res = {'check': {'out': bool(torch.allclose(s.out[:3], ref[0][:3], rtol=1e-5, atol=1e-6)),
-                 'gl_maxdiff': float((s.gl - ref[1]).abs().max()), 'gl_absmax': float(ref[1].abs().max()),
-                 'gv_maxdiff': float((s.gv - ref[2]).abs().max())}}
+def main():
+    s = sets[0]
+    s.legacy_fwd(); s.legacy_bwd(); torch.cuda.synchronize()
+    ref = (s.out.clone(), s.gl.clone(), s.gv.clone())
+    s.gl.zero_(); s.gv.zero_(); s.out.zero_()
+    s.fused(); s.verify(); torch.cuda.synchronize()
+    res = {'check': {'out': bool(torch.allclose(s.out[:3], ref[0][:3], rtol=1e-5, atol=1e-6)),
+                     'gl_maxdiff': float((s.gl - ref[1]).abs().max()), 'gl_absmax': float(ref[1].abs().max()),
+                     'gv_maxdiff': float((s.gv - ref[2]).abs().max())}}
 
 
-def both(x):
-    x.fused(); x.verify()
+    def both(x):
+        x.fused(); x.verify()
 
 
-def legacy(x):
-    x.legacy_fwd(); x.legacy_bwd()
+    def legacy(x):
+        x.legacy_fwd(); x.legacy_bwd()
 
 
-res['fused_us'] = round(timed([x.fused for x in sets], reps=30), 2)
-res['fused_plus_verify_us'] = round(timed([lambda x=x: both(x) for x in sets], reps=30), 2)
-res['legacy_fwd_bwd_us'] = round(timed([lambda x=x: legacy(x) for x in sets], reps=30), 2)
-peak = bench.load_peaks()[0]
-res['fused_plus_verify_frac'] = round(96 * T * B / (res['fused_plus_verify_us'] * 1e-6) / 1e9 / peak, 4)
-res['legacy_frac'] = round(96 * T * B / (res['legacy_fwd_bwd_us'] * 1e-6) / 1e9 / peak, 4)
-print(json.dumps(res))
+    res['fused_us'] = round(timed([x.fused for x in sets], reps=30), 2)
+    res['fused_plus_verify_us'] = round(timed([lambda x=x: both(x) for x in sets], reps=30), 2)
+    res['legacy_fwd_bwd_us'] = round(timed([lambda x=x: legacy(x) for x in sets], reps=30), 2)
+    peak = bench.load_peaks()[0]
+    res['fused_plus_verify_frac'] = round(96 * T * B / (res['fused_plus_verify_us'] * 1e-6) / 1e9 / peak, 4)
+    res['legacy_frac'] = round(96 * T * B / (res['legacy_fwd_bwd_us'] * 1e-6) / 1e9 / peak, 4)
+    print(json.dumps(res))
+
+
+if __name__ == '__main__':
+    main()

@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 sys.argv = sys.argv[:1]
-import tools.exp_vt as ev  # runs the microbench once (and leaves the stamps of the last launches in the workspace)
+import tools.exp_vt as ev
+ev.main()
 torch.cuda.synchronize()
 for x in ev.sets[:2]:
     x.fused()
