@@ -1,7 +1,9 @@
 """n-step TD operators with the signatures of ding/rl_utils/td.py -- kernels in csrc/td.cu.
 
   q_nstep_td_error (td.py:649-719), q_nstep_td_error_with_rescale (:810-867), dist_nstep_td_error (:413-523),
-  td_lambda_error (:1539-1571), generalized_lambda_returns (:1574-1605).
+  td_lambda_error (:1539-1571), generalized_lambda_returns (:1574-1605),
+  and the 1-step / state-value siblings that reuse the q-n-step kernels:
+  q_1step_td_error (:26-72), v_1step_td_error (:529-573), v_nstep_td_error (:579-617).
 """
 from collections import namedtuple
 from typing import Callable, Optional, Union
@@ -20,6 +22,9 @@ dist_nstep_td_data = namedtuple(
     'dist_1step_td_data', ['dist', 'next_n_dist', 'act', 'next_n_act', 'reward', 'done', 'weight']
 )
 td_lambda_data = namedtuple('td_lambda_data', ['value', 'reward', 'weight'])
+q_1step_td_data = namedtuple('q_1step_td_data', ['q', 'next_q', 'act', 'next_act', 'reward', 'done', 'weight'])
+v_1step_td_data = namedtuple('v_1step_td_data', ['v', 'next_v', 'reward', 'done', 'weight'])
+v_nstep_td_data = namedtuple('v_nstep_td_data', ['v', 'next_n_v', 'reward', 'done', 'weight', 'value_gamma'])
 
 # The reference asserts ``dist[b, act] > 0`` on the host every call (td.py:513).  True keeps that behaviour (one
 # 4-byte D2H read per call); False skips the read -- a non-positive entry then shows up as nan/inf in the loss.
@@ -192,6 +197,96 @@ def q_nstep_td_error_with_rescale(
     """
     assert len(data.action.shape) == 1, data.action.shape  # td.py:854
     return _qntd(data, gamma, nstep, False, value_gamma, criterion, True, trans_fn, inv_trans_fn)
+
+
+def q_1step_td_error(
+        data: namedtuple,
+        gamma: float,
+        criterion: torch.nn.modules = nn.MSELoss(reduction='none'),
+) -> torch.Tensor:
+    """
+    1-step TD error for Q-learning, drop-in for ding/rl_utils/td.py:26-72: ``target = gamma*(1-done)*next_q[next_act] +
+    reward`` -- the n = 1 case of ``q_nstep_td_error`` (the reference pins that identity, tests/test_td.py:113-126), on the
+    same kernel.  q, next_q (B, N); act, next_act (B,) int64; reward, done (B,); weight (B,) or None.  Returns the loss only.
+    """
+    q, next_q, act, next_act, reward, done, weight = data
+    assert len(act.shape) == 1, act.shape        # td.py:64
+    assert len(reward.shape) == 1, reward.shape  # td.py:65
+    loss, _ = _qntd(q_nstep_td_data(q, next_q, act, next_act, reward.unsqueeze(0), done, weight), gamma, 1, False, None,
+                    criterion, False)
+    return loss
+
+
+def _as_columns(v, next_v, reward, done, weight, value_gamma=None, nstep=None):
+    """State values as a one-action Q table: (S, 1) q / next_q with action 0, per-sample tensors flattened to S = v.numel().
+    ``reward``/``done``/``value_gamma`` of shape (B,) against v (B, K) are repeated along K like the reference's
+    ``unsqueeze(1)`` broadcast (td.py:563-567)."""
+    dev = ops.compute_device(v, next_v)
+    S = v.numel()
+
+    def per_sample(x, lead=0):
+        if x is None:
+            return None
+        x = ops.to_device(x.detach() if isinstance(x, torch.Tensor) else x, dev)
+        if x.dim() - lead < v.dim():  # (B,) against (B, K): broadcast over the trailing dims of v
+            x = x.reshape(tuple(x.shape) + (1, ) * (v.dim() - (x.dim() - lead))).expand(tuple(x.shape[:lead]) + tuple(v.shape))
+        return x.reshape(tuple(x.shape[:lead]) + (S, ))
+
+    zero = torch.zeros(S, dtype=torch.int64, device=dev)
+    r = per_sample(reward, lead=0 if nstep is None else 1)
+    if nstep is None:
+        r = r.unsqueeze(0)
+    d = per_sample(done)
+    if d is None:
+        d = torch.zeros(S, dtype=torch.float32, device=dev)
+    w = per_sample(weight)
+    vg = value_gamma
+    if isinstance(vg, torch.Tensor) and vg.numel() > 1:
+        vg = per_sample(vg)
+    return q_nstep_td_data(ops.to_device(v, dev).reshape(S, 1), ops.to_device(next_v.detach(), dev).reshape(S, 1), zero,
+                           zero, r, d, w), vg
+
+
+def v_1step_td_error(
+        data: namedtuple,
+        gamma: float,
+        criterion: torch.nn.modules = nn.MSELoss(reduction='none'),
+) -> torch.Tensor:
+    """
+    1-step TD error for a state-value (or critic) head, drop-in for ding/rl_utils/td.py:529-573 -- the critic loss of
+    DDPG / TD3 / SAC / ...: ``target = gamma*(1-done)*next_v + reward``.  v, next_v (B,) or (B, K) with reward, done (B,)
+    broadcast over K; done and weight may be None.  Returns ``(loss, td_error_per_sample)`` (the latter detached and
+    shaped like ``v``).  Runs on the q-n-step kernel with one action column.
+    """
+    v, next_v, reward, done, weight = data
+    host_out = not v.is_cuda
+    qd, _ = _as_columns(v, next_v, reward, done, weight)
+    loss, per = _qntd(qd, gamma, 1, False, None, criterion, False)
+    per = per.reshape(v.shape)
+    if host_out:
+        loss, per = loss.cpu(), per.cpu()
+    return loss, per
+
+
+def v_nstep_td_error(
+        data: namedtuple,
+        gamma: float,
+        nstep: int = 1,
+        criterion: torch.nn.modules = nn.MSELoss(reduction='none'),
+) -> torch.Tensor:
+    """
+    n-step TD error for a state-value head, drop-in for ding/rl_utils/td.py:579-617: ``target = nstep_return(reward,
+    next_n_v, done, gamma, nstep, value_gamma)``.  v, next_n_v, done (B,); reward (nstep, B); weight, value_gamma (B,) or
+    None.  Returns ``(loss, td_error_per_sample)``.  Runs on the q-n-step kernel with one action column.
+    """
+    v, next_n_v, reward, done, weight, value_gamma = data
+    host_out = not v.is_cuda
+    qd, vg = _as_columns(v, next_n_v, reward, done, weight, value_gamma, nstep=nstep)
+    loss, per = _qntd(qd, gamma, nstep, False, vg, criterion, False)
+    per = per.reshape(v.shape)
+    if host_out:
+        loss, per = loss.cpu(), per.cpu()
+    return loss, per
 
 
 def _support(v_min, v_max, n_atom, dev):

@@ -247,6 +247,53 @@ def q_nstep_td_error_with_rescale(
 
 
 # --------------------------------------------------------------------------------------------------------------
+# td.py:26-72 q_1step_td_error ; td.py:529-573 v_1step_td_error ; td.py:579-617 v_nstep_td_error
+# --------------------------------------------------------------------------------------------------------------
+def q_1step_td_error(q, next_q, act, next_act, reward, done, weight=None, gamma: float = 0.99, criterion=None):
+    """Returns the loss only (td.py:63-72)."""
+    if criterion is None:
+        criterion = torch.nn.MSELoss(reduction='none')
+    assert len(act.shape) == 1, act.shape        # td.py:64
+    assert len(reward.shape) == 1, reward.shape  # td.py:65
+    rows = torch.arange(act.shape[0])
+    if weight is None:
+        weight = torch.ones_like(reward)
+    q_sa = q[rows, act]
+    tq = next_q[rows, next_act]
+    tq = gamma * (1 - done) * tq + reward  # td.py:71
+    return (criterion(q_sa, tq.detach()) * weight).mean()
+
+
+def v_1step_td_error(v, next_v, reward, done=None, weight=None, gamma: float = 0.99, criterion=None):
+    """Returns ``(loss, td_error_per_sample)`` (td.py:557-573)."""
+    if criterion is None:
+        criterion = torch.nn.MSELoss(reduction='none')
+    if weight is None:
+        weight = torch.ones_like(v)
+    if len(v.shape) == len(reward.shape):  # td.py:560-564
+        target_v = gamma * (1 - done) * next_v + reward if done is not None else gamma * next_v + reward
+    else:  # td.py:565-569
+        if done is not None:
+            target_v = gamma * (1 - done).unsqueeze(1) * next_v + reward.unsqueeze(1)
+        else:
+            target_v = gamma * next_v + reward.unsqueeze(1)
+    per_sample = criterion(v, target_v.detach())
+    return (per_sample * weight).mean(), per_sample
+
+
+def v_nstep_td_error(v, next_n_v, reward, done, weight=None, value_gamma=None, gamma: float = 0.99, nstep: int = 1,
+                     criterion=None):
+    """Returns ``(loss, td_error_per_sample)`` (td.py:611-617)."""
+    if criterion is None:
+        criterion = torch.nn.MSELoss(reduction='none')
+    if weight is None:
+        weight = torch.ones_like(v)
+    target_v = nstep_return(reward, next_n_v, done, gamma, nstep, value_gamma)
+    per_sample = criterion(v, target_v.detach())
+    return (per_sample * weight).mean(), per_sample
+
+
+# --------------------------------------------------------------------------------------------------------------
 # td.py:413-523 dist_nstep_td_error (C51 categorical projection)
 # --------------------------------------------------------------------------------------------------------------
 def dist_nstep_td_error(

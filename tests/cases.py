@@ -20,6 +20,9 @@ GRAD_INPUTS = {
     'ppo': ['logit_new', 'value_new'],
     'qntd': ['q'],
     'qntd_rescale': ['q'],
+    'q1td': ['q'],
+    'v1td': ['v'],
+    'vntd': ['v'],
     'dntd': ['dist'],
     'td_lambda': ['value'],
     'upgo': ['target_output'],
@@ -30,6 +33,9 @@ LOSS_MIX = {
     'ppo': [1.0, 0.5, -0.01, 0.3],
     'qntd': [1.0],
     'qntd_rescale': [1.0],
+    'q1td': [1.0],
+    'v1td': [1.0],
+    'vntd': [1.0],
     'dntd': [1.0],
     'td_lambda': [1.0],
     'upgo': [1.0],
@@ -124,6 +130,43 @@ def qntd_case(seed, B, N, nstep, weight='none', value_gamma='none', gamma=0.95, 
     elif value_gamma == 'float':
         params['value_gamma'] = 0.857
     return ('qntd_rescale' if rescale else 'qntd'), t, params
+
+
+def q1td_case(seed, B, N, weight='none', gamma=0.95):
+    g = _g(seed)
+    t = OrderedDict()
+    t['q'] = _randn(g, B, N)
+    t['next_q'] = _randn(g, B, N)
+    t['act'] = _randint(g, N, B)
+    t['next_act'] = _randint(g, N, B)
+    t['reward'] = _rand(g, B)
+    t['done'] = _bern(g, 0.3, B)
+    t['weight'] = None if weight == 'none' else _rand(g, B)
+    return 'q1td', t, dict(gamma=gamma)
+
+
+def v1td_case(seed, B, K=None, weight='none', done='bern', gamma=0.95):
+    g = _g(seed)
+    shape = (B, ) if K is None else (B, K)
+    t = OrderedDict()
+    t['v'] = _randn(g, *shape)
+    t['next_v'] = _randn(g, *shape)
+    t['reward'] = _rand(g, B)
+    t['done'] = None if done == 'none' else _bern(g, 0.3, B)
+    t['weight'] = None if weight == 'none' else _rand(g, *shape)
+    return 'v1td', t, dict(gamma=gamma)
+
+
+def vntd_case(seed, B, nstep, weight='none', value_gamma='none', gamma=0.95):
+    g = _g(seed)
+    t = OrderedDict()
+    t['v'] = _randn(g, B)
+    t['next_n_v'] = _randn(g, B)
+    t['reward'] = _rand(g, nstep, B)
+    t['done'] = _bern(g, 0.3, B)
+    t['weight'] = None if weight == 'none' else _rand(g, B)
+    t['value_gamma'] = None if value_gamma == 'none' else _rand(g, B)
+    return 'vntd', t, dict(gamma=gamma, nstep=nstep)
 
 
 def dntd_case(seed, B, N, n_atom, nstep, weight='none', value_gamma='none', gamma=0.95, v_min=-10., v_max=10.,
@@ -242,6 +285,14 @@ def build_cases():
     c['qntdr_n3'] = qntd_case(40, 33, 6, 3, rescale=True)
     c['qntdr_n5_w_vg'] = qntd_case(41, 9, 4, 5, rescale=True, weight='tensor', value_gamma='tensor')
     c['qntdr_ngu'] = qntd_case(42, 6, 4, 3, rescale=True, list_gamma=True)
+    # ---- 1-step / state-value siblings on the q-n-step kernels (tests/test_td.py:207-268) -----------------------
+    c['q1td_basic'] = q1td_case(43, 12, 5)
+    c['q1td_w'] = q1td_case(44, 64, 6, weight='tensor', gamma=0.99)
+    c['v1td_basic'] = v1td_case(45, 16, gamma=0.99)
+    c['v1td_w_nodone'] = v1td_case(46, 9, weight='tensor', done='none')
+    c['v1td_2d'] = v1td_case(47, 8, K=3, weight='tensor')
+    c['vntd_n3'] = vntd_case(48, 10, 3, gamma=0.99)
+    c['vntd_n5_w_vg'] = vntd_case(49, 7, 5, weight='tensor', value_gamma='tensor')
     # ---- dist_nstep (tests/test_td.py:130-204) ---------------------------------------------------------------
     c['dntd_cfgC'] = dntd_case(50, 32, 6, 51, 3, gamma=0.99, value_gamma='tensor')
     c['dntd_n5'] = dntd_case(51, 4, 3, 51, 5)
@@ -338,6 +389,26 @@ def run_api(api, op, tensors, params, device='cpu'):
         res['out_td_error_per_sample'] = _np(per)
         _backward(op, [loss], t, res)
         return res
+    if op == 'q1td':
+        data = api.q_1step_td_data(*[t[k] for k in ('q', 'next_q', 'act', 'next_act', 'reward', 'done', 'weight')])
+        loss = api.q_1step_td_error(data, p['gamma'])
+        res['out_loss'] = _np(loss)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'v1td':
+        data = api.v_1step_td_data(t['v'], t['next_v'], t['reward'], t['done'], t['weight'])
+        loss, per = api.v_1step_td_error(data, p['gamma'])
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'vntd':
+        data = api.v_nstep_td_data(t['v'], t['next_n_v'], t['reward'], t['done'], t['weight'], t['value_gamma'])
+        loss, per = api.v_nstep_td_error(data, p['gamma'], p['nstep'])
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
     if op == 'dntd':
         w = p.pop('weight_float', None)
         data = api.dist_nstep_td_data(t['dist'], t['next_n_dist'], t['act'], t['next_n_act'], t['reward'], t['done'],
@@ -391,6 +462,18 @@ def run_oracle(orc, op, tensors, params):
         return res
     if op in ('qntd', 'qntd_rescale'):
         fn = orc.q_nstep_td_error if op == 'qntd' else orc.q_nstep_td_error_with_rescale
+        loss, per = fn(**t, **p)
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'q1td':
+        loss = orc.q_1step_td_error(**t, **p)
+        res['out_loss'] = _np(loss)
+        _backward(op, [loss], t, res)
+        return res
+    if op in ('v1td', 'vntd'):
+        fn = orc.v_1step_td_error if op == 'v1td' else orc.v_nstep_td_error
         loss, per = fn(**t, **p)
         res['out_loss'] = _np(loss)
         res['out_td_error_per_sample'] = _np(per)

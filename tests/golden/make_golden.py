@@ -1,6 +1,7 @@
 """Mint the golden fixtures from the UNMODIFIED reference (run in the build container only).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # writes the fixtures that do not exist yet (new cases)
+    python tests/golden/make_golden.py --all    # re-mints every fixture
 
 For every case of ``tests/cases.build_cases()`` this runs the real ``ding.rl_utils`` functions (loaded read-only
 from /root/reference by ``oracle/ref_loader.py``) on CPU fp32 and stores inputs, scalar parameters, forward
@@ -37,6 +38,8 @@ def main():
     ref = ref_loader.load()
     n = 0
     for name, (op, tensors, params) in cases.build_cases().items():
+        if '--all' not in sys.argv and os.path.isfile(os.path.join(HERE, name + '.npz')):
+            continue
         res = cases.run_api(ref, op, tensors, params)
         blob = {}
         meta = {'op': op, 'params': _encode_params(params), 'none_inputs': [], 'bool_inputs': [],

@@ -15,6 +15,9 @@ INPUT_ORDER = {
             'logit_pretrained'],
     'qntd': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight', 'value_gamma'],
     'qntd_rescale': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight', 'value_gamma'],
+    'q1td': ['q', 'next_q', 'act', 'next_act', 'reward', 'done', 'weight'],
+    'v1td': ['v', 'next_v', 'reward', 'done', 'weight'],
+    'vntd': ['v', 'next_n_v', 'reward', 'done', 'weight', 'value_gamma'],
     'dntd': ['dist', 'next_n_dist', 'act', 'next_n_act', 'reward', 'done', 'weight', 'value_gamma'],
     'td_lambda': ['value', 'reward', 'weight'],
     'upgo': ['target_output', 'action', 'rhos', 'rewards', 'bootstrap_values', 'mask'],

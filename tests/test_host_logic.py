@@ -186,6 +186,9 @@ EXPECTED_CALLS = {
     'ppo': ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad', 'b200rl_ppo_bwd'],
     'qntd': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'qntd_rescale': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
+    'q1td': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
+    'v1td': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
+    'vntd': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'dntd': ['b200rl_dntd_fwd', 'b200rl_dntd_bwd'],
     'td_lambda': ['b200rl_td_lambda_fwd', 'b200rl_scale'],
     'upgo': ['b200rl_lambda_returns', 'b200rl_upgo_head_fwd', 'b200rl_upgo_head_bwd'],
