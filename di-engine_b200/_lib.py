@@ -25,6 +25,7 @@ PROTOTYPES = {
     "b200rl_ppo_fwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, c_size_t, P],
     "b200rl_ppo_bwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, P, P, P],
     "b200rl_ppo_fwd_grad": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, c_size_t, P],
+    "b200rl_ppo_value_fwd": [P, P, P, P, LL, D, I, P, P, P, c_size_t, P],
     "b200rl_ppo_fused_supported": [P, P, P, P, P, P, P, P, P, P, LL, LL],
     "b200rl_qntd_fwd": [P, P, P, P, P, P, P, P, LL, P, LL, LL, I, D, I, I, D, I, D, P, P, P, P, P, c_size_t, P],
     "b200rl_qntd_bwd": [P, P, P, LL, LL, P, P],

@@ -317,6 +317,28 @@ static bool tile_path_ok(const PpoArgs& a) {
     return a.G == 1 && a.N <= 32 && al;
 }
 
+// ppo_value_error alone (ppo.py:233-275; PPG's auxiliary phase and value-only updates call it without the policy part):
+// value loss and its gradient for a unit upstream gradient in one pass; backward is a scale of the saved gradient.
+template <int NT>
+__global__ void __launch_bounds__(NT) ppo_value_kernel(const float* __restrict__ value_new,
+                                                       const float* __restrict__ value_old,
+                                                       const float* __restrict__ ret, const float* __restrict__ weight,
+                                                       long long S, float clip, int use_clip, float* __restrict__ out,
+                                                       float* __restrict__ dvalue, float* ws) {
+    pdl_prologue();
+    float acc[1] = {0.f};
+    const float inv_s = 1.f / (float)S;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < S; i += (long long)gridDim.x * NT) {
+        const float w = weight ? weight[i] : 1.f;
+        float d;
+        const float t = value_term(value_new[i], use_clip ? value_old[i] : 0.f, ret[i], clip, use_clip, d);
+        acc[0] += t * w;
+        if (dvalue) dvalue[i] = 0.5f * w * inv_s * d;
+    }
+    double tot[1];
+    if (grid_sum<1, NT>(acc, tot, ws, 0) && threadIdx.x == 0) out[0] = (float)(0.5 * tot[0] / (double)S);
+}
+
 // launch geometry of the persistent kernel: SM count x resident CTAs per SM for this instantiation / smem size
 template <int NC, int WHAT, int RPT>
 static int launch_tile(const PpoArgs& a, float* out, float* ws, size_t ws_bytes, cudaStream_t st) {
@@ -506,5 +528,20 @@ extern "C" int b200rl_ppo_bwd(const float* logit_new, const float* logit_old, co
     constexpr int NT = 128;
     if (a.N > 64) (void)launch_k(ppo_bwd_kernel<NT, 2>, div_up(S, NT / 32), NT, 0, st, a);
     else (void)launch_k(ppo_bwd_kernel<NT, 1>, div_up(S, NT), NT, 0, st, a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_ppo_value_fwd(const float* value_new, const float* value_old, const float* return_,
+                                    const float* weight, long long S, double clip_ratio, int use_value_clip,
+                                    float* loss, float* dvalue_unit, float* workspace, size_t workspace_bytes,
+                                    void* stream) {
+    if (!value_new || !return_ || (use_value_clip && !value_old) || !loss || !workspace || S < 1) return B200RL_ERR_ARG;
+    constexpr int NT = 256;
+    long long grid = div_up(S, NT);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (workspace_bytes < WS_MIN_BYTES || (size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes)
+        return B200RL_ERR_WORKSPACE;
+    (void)launch_k(ppo_value_kernel<NT>, (int)grid, NT, 0, (cudaStream_t)stream, value_new, value_old, return_, weight, S,
+                   (float)clip_ratio, use_value_clip, loss, dvalue_unit, workspace);
     return (int)cudaGetLastError();
 }

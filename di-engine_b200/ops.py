@@ -128,12 +128,14 @@ PPO_FUSED_BACKWARD = True
 _PPO_HINT = {}
 
 
-def ppo_hint(device):
-    """Device-resident expectation of (d total/d policy_loss, d/d value_loss, d/d entropy_loss, d/d kl_div)."""
-    key = device.index
+def ppo_hint(device, kind='ppo'):
+    """Device-resident expectation of (d total/d policy_loss, d/d value_loss, d/d entropy_loss, d/d kl_div), one per call
+    site kind: a policy-only caller (``ppo_policy_error``: no value term) must not disturb ``ppo_error``'s expectation."""
+    key = (device.index, kind)
     h = _PPO_HINT.get(key)
     if h is None:
-        h = torch.tensor([1.0, 0.5, -0.01, 0.0], dtype=torch.float32, device=device)
+        init = [1.0, 0.5, -0.01, 0.0] if kind == 'ppo' else [1.0, 0.0, -0.01, 0.0]
+        h = torch.tensor(init, dtype=torch.float32, device=device)
         _PPO_HINT[key] = h
     return h
 
@@ -144,8 +146,9 @@ class PPOFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre, S, G, N,
-                clip_ratio, use_value_clip, dual_clip, kl_type):
+                clip_ratio, use_value_clip, dual_clip, kl_type, hint_kind):
         dev = logit_new.device
+        ctx.hint_kind = hint_kind
         out = torch.empty(8, dtype=torch.float32, device=dev)
         L = lib()
         tensors = (ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old),
@@ -160,7 +163,7 @@ class PPOFunction(torch.autograd.Function):
                 grad_value = torch.empty_like(value_new)
                 if L.b200rl_ppo_fused_supported(*tensors, ptr(grad_logit), G, N):
                     g_used = torch.empty(4, dtype=torch.float32, device=dev)
-                    rc = L.b200rl_ppo_fwd_grad(*tensors, *cfg, ptr(ppo_hint(dev)), ptr(g_used), ptr(out),
+                    rc = L.b200rl_ppo_fwd_grad(*tensors, *cfg, ptr(ppo_hint(dev, hint_kind)), ptr(g_used), ptr(out),
                                                ptr(grad_logit), ptr(grad_value), ptr(ws), ws.numel() * 4,
                                                stream_ptr())
                     _lib.check(rc, 'b200rl_ppo_fwd_grad')
@@ -189,7 +192,7 @@ class PPOFunction(torch.autograd.Function):
         if ctx.fused and first:
             grad_logit, grad_value, g_used = ctx.spec  # valid if the expectation held; the kernel checks on the device
             ctx.spec = None  # sole owner now: autograd can adopt the buffers as .grad instead of cloning them
-            p_used, p_hint = ptr(g_used), ptr(ppo_hint(dev))
+            p_used, p_hint = ptr(g_used), ptr(ppo_hint(dev, getattr(ctx, 'hint_kind', 'ppo')))
         else:  # no fused forward, or a repeated backward (the first call's buffers may now belong to .grad)
             grad_logit = torch.empty_like(logit_new)
             grad_value = torch.empty_like(value_new)
@@ -201,7 +204,7 @@ class PPOFunction(torch.autograd.Function):
                 stream_ptr()
             )
         _lib.check(rc, 'b200rl_ppo_bwd')
-        return (grad_logit, grad_value) + (None, ) * 14
+        return (grad_logit, grad_value) + (None, ) * 15
 
 
 class GAEPPOFunction(torch.autograd.Function):
@@ -240,6 +243,24 @@ class GAEPPOFunction(torch.autograd.Function):
     def backward(ctx, _g_adv, g_p, g_v, g_e, g_k, _g_out):
         grads = PPOFunction.backward(ctx, g_p, g_v, g_e, g_k, None)
         return (grads[0], grads[1]) + (None, ) * 20
+
+
+def ppo_value_(value_new, value_old, return_, weight, clip_ratio, use_value_clip):
+    """ppo_value_error (ppo.py:233-275): loss and, if needed, its gradient for a unit upstream gradient in one launch."""
+    dev = value_new.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    want_grad = value_new.requires_grad and torch.is_grad_enabled()
+    dvalue = torch.empty_like(value_new) if want_grad else None
+    with torch.cuda.device(dev):
+        ws = workspace(dev)
+        rc = lib().b200rl_ppo_value_fwd(
+            ptr(value_new), ptr(value_old), ptr(return_), ptr(weight), value_new.numel(), float(clip_ratio),
+            1 if use_value_clip else 0, ptr(loss), ptr(dvalue), ptr(ws), ws.numel() * 4, stream_ptr()
+        )
+    _lib.check(rc, 'b200rl_ppo_value_fwd')
+    if want_grad:
+        return _ScaleSaved.apply(value_new, loss, dvalue)
+    return loss
 
 
 # ----------------------------------------------------------------------------------------------------------------

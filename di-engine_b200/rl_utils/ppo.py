@@ -1,4 +1,6 @@
-"""``ppo_error`` with the signature and namedtuples of ding/rl_utils/ppo.py:8-27,77-83 -- csrc/ppo.cu."""
+"""``ppo_error`` with the signature and namedtuples of ding/rl_utils/ppo.py:8-27,77-83 -- csrc/ppo.cu; and its two halves as
+the reference exposes them separately (PPG, off-policy PPO, the hybrid-action PPO): ``ppo_policy_error`` (ppo.py:143-230) and
+``ppo_value_error`` (ppo.py:233-275)."""
 from collections import namedtuple
 from typing import Optional, Tuple
 
@@ -12,6 +14,9 @@ ppo_data = namedtuple(
 )
 ppo_loss = namedtuple('ppo_loss', ['policy_loss', 'value_loss', 'entropy_loss', 'kl_div'])
 ppo_info = namedtuple('ppo_info', ['approx_kl', 'clipfrac'])
+ppo_policy_data = namedtuple('ppo_policy_data', ['logit_new', 'logit_old', 'action', 'adv', 'weight', 'logit_pretrained'])
+ppo_policy_loss = namedtuple('ppo_policy_loss', ['policy_loss', 'entropy_loss', 'kl_div'])
+ppo_value_data = namedtuple('ppo_value_data', ['value_new', 'value_old', 'return_', 'weight'])
 
 _KL_TYPES = {'k1': 1, 'k2': 2, 'k3': 3}
 
@@ -42,6 +47,10 @@ def ppo_error(
     Returns ``(ppo_loss, ppo_info)``: four differentiable 0-dim tensors (gradients reach ``logit_new`` and
     ``value_new``) and two python floats.
     """
+    return _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, 'ppo')
+
+
+def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind):
     assert dual_clip is None or dual_clip > 1.0, "dual_clip value must be greater than 1.0, but get value: {}".format(
         dual_clip
     )
@@ -78,7 +87,7 @@ def ppo_error(
     act = ops.i64c(ops.to_device(action, dev))
     p, v, e, k, out = ops.PPOFunction.apply(
         ln, vn, lo, act, vo, ad, rt, w, lp, S, G, N, float(clip_ratio), 1 if use_value_clip else 0,
-        float(dual_clip) if dual_clip is not None else 0.0, _KL_TYPES.get(kl_type, 1)
+        float(dual_clip) if dual_clip is not None else 0.0, _KL_TYPES.get(kl_type, 1), _hint_kind
     )
     if LAZY_INFO:
         info = ppo_info(out[4], out[5])
@@ -88,3 +97,53 @@ def ppo_error(
     if host_out:
         p, v, e, k = p.cpu(), v.cpu(), e.cpu(), k.cpu()
     return ppo_loss(p, v, e, k), info
+
+
+def ppo_policy_error(
+        data: namedtuple,
+        clip_ratio: float = 0.2,
+        dual_clip: Optional[float] = None,
+        entropy_bonus: bool = True,
+        kl_type: str = 'k1'
+) -> Tuple[namedtuple, namedtuple]:
+    """
+    Policy half of the PPO loss, drop-in for ding/rl_utils/ppo.py:143-230: ``(ppo_policy_loss(policy_loss, entropy_loss,
+    kl_div), ppo_info)``.  Runs on the ``ppo_error`` kernel with a zero value head (value_new = value_old = return_ = 0
+    contributes nothing and receives no gradient); its expected-upstream-gradient record is kept apart from
+    ``ppo_error``'s, so alternating the two never forces a recomputation.
+    """
+    logit_new, logit_old, action, adv, weight, logit_pretrained = data
+    zero = torch.zeros_like(adv)
+    loss, info = _ppo_error(
+        ppo_data(logit_new, logit_old, action, zero, zero, adv, zero, weight, logit_pretrained), clip_ratio, False,
+        dual_clip, kl_type, 'policy'
+    )
+    entropy = loss.entropy_loss if entropy_bonus else torch.tensor(0.0)  # ppo.py:203
+    return ppo_policy_loss(loss.policy_loss, entropy, loss.kl_div), info
+
+
+def ppo_value_error(
+        data: namedtuple,
+        clip_ratio: float = 0.2,
+        use_value_clip: bool = True,
+) -> torch.Tensor:
+    """
+    Value half of the PPO loss, drop-in for ding/rl_utils/ppo.py:233-275: ``0.5 * mean(w * max((R - v)^2, (R - v_clip)^2))``
+    (or the unclipped form); differentiable w.r.t. ``value_new``.  One small kernel (csrc/ppo.cu: ppo_value_kernel).
+    """
+    value_new, value_old, return_, weight = data
+    dev = ops.compute_device(value_new)
+    host_out = not value_new.is_cuda
+    vn = ops.f32c(ops.to_device(value_new, dev), 'value_new')
+    vo = ops.f32c(ops.to_device(value_old.detach(), dev), 'value_old')
+    rt = ops.f32c(ops.to_device(return_.detach(), dev), 'return_')
+    if vo.numel() != vn.numel() or rt.numel() != vn.numel():
+        raise ValueError("ppo_value_error: value_new %s / value_old %s / return_ %s shapes do not match" %
+                         (tuple(value_new.shape), tuple(value_old.shape), tuple(return_.shape)))
+    w = None
+    if weight is not None:
+        w = ops.f32c(ops.to_device(weight.detach(), dev), 'weight')
+        if w.numel() != vn.numel():
+            w = w.expand_as(vn).contiguous()
+    loss = ops.ppo_value_(vn, vo, rt, w, clip_ratio, use_value_clip)
+    return loss.cpu() if host_out else loss

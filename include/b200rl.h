@@ -182,6 +182,13 @@ B200RL_API int b200rl_vtrace_fwd_grad(const float* target_output, const float* b
                            float* grad_target_output, float* grad_value, float* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* ---- ppo_value_error alone (ppo.py:233-275): loss = 0.5 * mean(w * max((R-v)^2, (R-v_clip)^2)) (or the unclipped form)
+ * and, when dvalue_unit != null, d loss / d value_new for a unit upstream gradient (backward = b200rl_scale of it).
+ * value_new, value_old, return_, weight (nullable = 1): (S). */
+B200RL_API int b200rl_ppo_value_fwd(const float* value_new, const float* value_old, const float* return_,
+                         const float* weight, long long S, double clip_ratio, int use_value_clip, float* loss,
+                         float* dvalue_unit, float* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- fused learner step: gae (gae.py:25-70) followed by ppo_error (ppo.py:77-140) in ONE launch ------------------
  * Semantics are exactly b200rl_gae(value, next_value, reward, done, traj_flag -> adv) followed by b200rl_ppo_fwd_grad
  * (or b200rl_ppo_fwd when g_expected is null) with that adv, S = T*B, G = 1 -- same arithmetic, bit-identical adv.

@@ -151,6 +151,29 @@ def ppo_error(
 # --------------------------------------------------------------------------------------------------------------
 # td.py:230-286 nstep_return ; value_rescale.py:4-34
 # --------------------------------------------------------------------------------------------------------------
+def ppo_policy_error(logit_new, logit_old, action, adv, weight=None, logit_pretrained=None, clip_ratio: float = 0.2,
+                     dual_clip: Optional[float] = None, entropy_bonus: bool = True, kl_type: str = 'k1'):
+    """ppo.py:143-230 -> ``(policy_loss, entropy_loss, kl_div, approx_kl, clipfrac)``: the policy part of ``ppo_error``."""
+    zero = torch.zeros_like(adv)
+    p, _, e, k, approx_kl, clipfrac = ppo_error(logit_new, logit_old, action, zero, zero, adv, zero, weight,
+                                                logit_pretrained, clip_ratio, False, dual_clip, kl_type)
+    if not entropy_bonus:  # ppo.py:202-203
+        e = torch.tensor(0.0)
+    return p, e, k, approx_kl, clipfrac
+
+
+def ppo_value_error(value_new, value_old, return_, weight=None, clip_ratio: float = 0.2, use_value_clip: bool = True):
+    """ppo.py:263-275"""
+    if weight is None:
+        weight = torch.ones_like(value_old)
+    if use_value_clip:
+        value_clip = value_old + (value_new - value_old).clamp(-clip_ratio, clip_ratio)
+        v1 = (return_ - value_new).pow(2)
+        v2 = (return_ - value_clip).pow(2)
+        return 0.5 * (torch.max(v1, v2) * weight).mean()
+    return 0.5 * ((return_ - value_new).pow(2) * weight).mean()
+
+
 def nstep_return(reward, next_value, done, gamma: Union[float, list], nstep: int, value_gamma=None):
     assert reward.shape[0] == nstep  # td.py:257
     if isinstance(gamma, float):  # td.py:260-273

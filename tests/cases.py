@@ -18,6 +18,8 @@ import torch
 GRAD_INPUTS = {
     'gae': [],
     'ppo': ['logit_new', 'value_new'],
+    'ppo_policy': ['logit_new'],
+    'ppo_value': ['value_new'],
     'qntd': ['q'],
     'qntd_rescale': ['q'],
     'q1td': ['q'],
@@ -31,6 +33,8 @@ GRAD_INPUTS = {
 # upstream gradient for each returned loss head (distinct, non-trivial)
 LOSS_MIX = {
     'ppo': [1.0, 0.5, -0.01, 0.3],
+    'ppo_policy': [1.0, -0.02, 0.3],
+    'ppo_value': [0.7],
     'qntd': [1.0],
     'qntd_rescale': [1.0],
     'q1td': [1.0],
@@ -130,6 +134,18 @@ def qntd_case(seed, B, N, nstep, weight='none', value_gamma='none', gamma=0.95, 
     elif value_gamma == 'float':
         params['value_gamma'] = 0.857
     return ('qntd_rescale' if rescale else 'qntd'), t, params
+
+
+def ppo_policy_case(seed, B, N, A=None, weight='none', pretrained=False, **params):
+    op, t, _ = ppo_case(seed, B, N, A=A, weight=weight, pretrained=pretrained)
+    keep = OrderedDict((k, t[k]) for k in ('logit_new', 'logit_old', 'action', 'adv', 'weight', 'logit_pretrained'))
+    return 'ppo_policy', keep, params
+
+
+def ppo_value_case(seed, B, weight='none', **params):
+    op, t, _ = ppo_case(seed, B, 3, weight=weight)
+    keep = OrderedDict((k, t[k]) for k in ('value_new', 'value_old', 'return_', 'weight'))
+    return 'ppo_value', keep, params
 
 
 def q1td_case(seed, B, N, weight='none', gamma=0.95):
@@ -274,6 +290,11 @@ def build_cases():
     c['ppo_wideN'] = ppo_case(i + 2, 9, 130, weight='tensor', clip_ratio=0.1)
     c['ppo_seq'] = ppo_case(i + 3, 5, 6, lead=(3, ), weight='tensor')
     c['ppo_one'] = ppo_case(i + 4, 1, 3)
+    c['ppo_policy_basic'] = ppo_policy_case(i + 5, 64, 6, clip_ratio=0.2)
+    c['ppo_policy_w_dc_kl'] = ppo_policy_case(i + 6, 33, 5, weight='tensor', pretrained=True, dual_clip=3.0, kl_type='k3')
+    c['ppo_policy_marl_noent'] = ppo_policy_case(i + 7, 12, 7, A=4, entropy_bonus=False)
+    c['ppo_value_clip'] = ppo_value_case(i + 8, 100, weight='tensor', clip_ratio=0.2)
+    c['ppo_value_noclip'] = ppo_value_case(i + 9, 37, use_value_clip=False)
     # ---- q_nstep (tests/test_td.py:13-126) -------------------------------------------------------------------
     c['qntd_cfgB'] = qntd_case(30, 64, 6, 3, value_gamma='tensor', gamma=0.99, done='bern')
     c['qntd_n1'] = qntd_case(31, 5, 4, 1)
@@ -375,6 +396,21 @@ def run_api(api, op, tensors, params, device='cpu'):
         res['out_clipfrac'] = np.float32(info.clipfrac)
         _backward(op, list(loss), t, res)
         return res
+    if op == 'ppo_policy':
+        data = api.ppo_policy_data(*[t[k] for k in ('logit_new', 'logit_old', 'action', 'adv', 'weight',
+                                                     'logit_pretrained')])
+        loss, info = api.ppo_policy_error(data, **p)
+        for k in ('policy_loss', 'entropy_loss', 'kl_div'):
+            res['out_' + k] = _np(getattr(loss, k))
+        res['out_approx_kl'] = np.float32(info.approx_kl)
+        res['out_clipfrac'] = np.float32(info.clipfrac)
+        _backward(op, list(loss), t, res)
+        return res
+    if op == 'ppo_value':
+        loss = api.ppo_value_error(api.ppo_value_data(t['value_new'], t['value_old'], t['return_'], t['weight']), **p)
+        res['out_value_loss'] = _np(loss)
+        _backward(op, [loss], t, res)
+        return res
     if op in ('qntd', 'qntd_rescale'):
         data = api.q_nstep_td_data(*[t[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done',
                                                     'weight')])
@@ -465,6 +501,19 @@ def run_oracle(orc, op, tensors, params):
         loss, per = fn(**t, **p)
         res['out_loss'] = _np(loss)
         res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'ppo_policy':
+        out = orc.ppo_policy_error(**t, **p)
+        for k, v in zip(('policy_loss', 'entropy_loss', 'kl_div'), out[:3]):
+            res['out_' + k] = _np(v)
+        res['out_approx_kl'] = np.float32(out[3])
+        res['out_clipfrac'] = np.float32(out[4])
+        _backward(op, list(out[:3]), t, res)
+        return res
+    if op == 'ppo_value':
+        loss = orc.ppo_value_error(**t, **p)
+        res['out_value_loss'] = _np(loss)
         _backward(op, [loss], t, res)
         return res
     if op == 'q1td':

@@ -198,7 +198,7 @@ def test_cuda_graph_capture_of_the_learner_step():
         ln = tp['logit_new'].detach().requires_grad_(True)
         vn = tp['value_new'].detach().requires_grad_(True)
         p, v, e, k, _ = ops.PPOFunction.apply(ln, vn, tp['logit_old'], tp['action'], tp['value_old'], adv.view(-1),
-                                              tp['return_'], None, None, T * B, 1, N, 0.2, 1, 0.0, 1)
+                                              tp['return_'], None, None, T * B, 1, N, 0.2, 1, 0.0, 1, 'ppo')
         (p + 0.5 * v - 0.01 * e).backward()
         outs.update(adv=adv, p=p, gl=ln.grad, gv=vn.grad)
 

@@ -79,6 +79,12 @@ def test_namedtuple_fields_match_reference():
     assert r.td_lambda_data._fields == ('value', 'reward', 'weight')
     assert r.vtrace_data._fields == ('target_output', 'behaviour_output', 'action', 'value', 'reward', 'weight')
     assert r.vtrace_loss._fields == ('policy_loss', 'value_loss', 'entropy_loss')
+    assert r.ppo_policy_data._fields == ('logit_new', 'logit_old', 'action', 'adv', 'weight', 'logit_pretrained')  # ppo.py:12-14
+    assert r.ppo_policy_loss._fields == ('policy_loss', 'entropy_loss', 'kl_div')
+    assert r.ppo_value_data._fields == ('value_new', 'value_old', 'return_', 'weight')
+    assert r.q_1step_td_data._fields == ('q', 'next_q', 'act', 'next_act', 'reward', 'done', 'weight')  # td.py:14
+    assert r.v_1step_td_data._fields == ('v', 'next_v', 'reward', 'done', 'weight')  # td.py:526
+    assert r.v_nstep_td_data._fields == ('v', 'next_n_v', 'reward', 'done', 'weight', 'value_gamma')  # td.py:576
 
 
 def test_signatures_match_reference_defaults():
@@ -90,6 +96,12 @@ def test_signatures_match_reference_defaults():
     assert sig(r.gae) == [('data', E), ('gamma', 0.99), ('lambda_', 0.97)]
     assert sig(r.ppo_error) == [('data', E), ('clip_ratio', 0.2), ('use_value_clip', True), ('dual_clip', None),
                                 ('kl_type', 'k1')]
+    assert sig(r.ppo_policy_error) == [('data', E), ('clip_ratio', 0.2), ('dual_clip', None), ('entropy_bonus', True),
+                                       ('kl_type', 'k1')]  # ppo.py:143-149
+    assert sig(r.ppo_value_error) == [('data', E), ('clip_ratio', 0.2), ('use_value_clip', True)]  # ppo.py:233-237
+    assert [k for k, _ in sig(r.q_1step_td_error)] == ['data', 'gamma', 'criterion']  # td.py:26-30
+    assert [k for k, _ in sig(r.v_1step_td_error)] == ['data', 'gamma', 'criterion']  # td.py:529-533
+    assert [(k, d) for k, d in sig(r.v_nstep_td_error)][:3] == [('data', E), ('gamma', E), ('nstep', 1)]  # td.py:579-584
     s = sig(r.q_nstep_td_error)
     assert [k for k, _ in s] == ['data', 'gamma', 'nstep', 'cum_reward', 'value_gamma', 'criterion']
     assert s[2][1] == 1 and s[3][1] is False and s[4][1] is None and isinstance(s[5][1], nn.MSELoss)
@@ -184,6 +196,8 @@ def dry(monkeypatch):
 EXPECTED_CALLS = {
     'gae': ['b200rl_gae'],
     'ppo': ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad', 'b200rl_ppo_bwd'],
+    'ppo_policy': ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad', 'b200rl_ppo_bwd'],
+    'ppo_value': ['b200rl_ppo_value_fwd', 'b200rl_scale'],
     'qntd': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'qntd_rescale': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'q1td': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
