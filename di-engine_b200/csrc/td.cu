@@ -256,34 +256,61 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
     for (long long hi = T; hi > 0; hi -= CHUNK) {
         const long long lo = hi > CHUNK ? hi - CHUNK : 0;
         const int rows = (int)(hi - lo);
-        for (int i = threadIdx.x; i < rows * TC; i += NT) {
-            const int r = i / TC, cc = i % TC;
-            const long long c = c0 + cc, t = lo + r;
-            if (c < B) {
-                const long long off = t * B + c;
-                const float rw = a.reward[off];
-                const float vn = a.value[off + B];  // V_{t+1}
-                float g, l;
-                if (MODE == 1) {
-                    g = 1.f;
-                    l = 1.f;
-                    if (t < T - 1) l = (fadd(a.reward[off + B], a.value[off + 2 * B]) >= vn) ? 1.f : 0.f;
-                } else {
-                    g = a.gammas ? a.gammas[off] : a.gamma;
-                    l = a.lambdas ? a.lambdas[off] : a.lambda;
+        // U elements per thread at a time: all global loads of the batch are issued before any of them is consumed (the
+        // shared-memory stores of a one-element loop body would serialise the loads: T=1024, B=64 took 78 us, mostly here)
+        constexpr int U = 8;
+        for (int i0 = threadIdx.x; i0 < rows * TC; i0 += NT * U) {
+            float rw[U], vn[U], g[U], l[U], dn[U], r2[U], v2[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * NT;
+                const int r = i / TC, cc = i % TC;
+                const long long c = c0 + cc, t = lo + r;
+                ok[u] = i < rows * TC && c < B;
+                rw[u] = vn[u] = dn[u] = r2[u] = v2[u] = 0.f;
+                g[u] = a.gamma;
+                l[u] = a.lambda;
+                if (ok[u]) {
+                    const long long off = t * B + c;
+                    rw[u] = a.reward[off];
+                    vn[u] = a.value[off + B];  // V_{t+1}
+                    if (MODE == 1) {
+                        if (t < T - 1) {
+                            r2[u] = a.reward[off + B];
+                            v2[u] = a.value[off + 2 * B];
+                        }
+                    } else {
+                        if (a.gammas) g[u] = a.gammas[off];
+                        if (a.lambdas) l[u] = a.lambdas[off];
+                    }
+                    if (a.done) dn[u] = a.done[off];
                 }
-                const float m = a.done ? fsub(1.f, a.done[off]) : 1.f;
-                const float disc = fmul(g, l);
-                s_r[r][cc] = rw;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                const int i = i0 + u * NT;
+                const int r = i / TC, cc = i % TC;
+                const long long t = lo + r;
+                float gg = g[u], ll = l[u];
+                if (MODE == 1) {
+                    gg = 1.f;
+                    ll = 1.f;
+                    if (t < T - 1) ll = (fadd(r2[u], v2[u]) >= vn[u]) ? 1.f : 0.f;
+                }
+                const float m = a.done ? fsub(1.f, dn[u]) : 1.f;
+                const float disc = fmul(gg, ll);
+                s_r[r][cc] = rw[u];
                 s_m[r][cc] = m;
                 if (t == T - 1) {
                     // closed form of the last row kept in s_c; disc = 0 so the carry (0) is ignored exactly
                     s_disc[r][cc] = 0.f;
-                    s_c[r][cc] = fmul(fmul(m, g), vn);
+                    s_c[r][cc] = fmul(fmul(m, gg), vn[u]);
                     s_m[r][cc] = 1.f;
                 } else {
                     s_disc[r][cc] = disc;
-                    s_c[r][cc] = fmul(fsub(g, disc), vn);
+                    s_c[r][cc] = fmul(fsub(gg, disc), vn[u]);
                 }
             }
         }
@@ -315,18 +342,34 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < rows * TC; i += NT) {
-            const int r = i / TC, cc = i % TC;
-            const long long c = c0 + cc;
-            if (c < B) {
-                const long long off = (lo + r) * B + c;
+        for (int i0 = threadIdx.x; i0 < rows * TC; i0 += NT * U) {
+            float w[U], v[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {  // the head's global loads first, batched like the input phase
+                const int i = i0 + u * NT;
+                const long long c = c0 + i % TC;
+                ok[u] = i < rows * TC && c < B;
+                w[u] = 1.f;
+                v[u] = 0.f;
+                if (HEAD == 1 && ok[u]) {
+                    const long long off = (lo + i / TC) * B + c;
+                    if (a.weight) w[u] = a.weight[off];
+                    v[u] = a.value[off];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                const int i = i0 + u * NT;
+                const int r = i / TC, cc = i % TC;
+                const long long off = (lo + r) * B + c0 + cc;
                 const float gret = s_r[r][cc];
                 if (a.ret) a.ret[off] = gret;
                 if (HEAD == 1) {
-                    const float w = a.weight ? a.weight[off] : 1.f;
-                    const float d = gret - a.value[off];
-                    acc[0] += w * d * d;
-                    a.dvalue[off] = -w * d / (float)(T * B);  // 0.5 * w * 2 * (V - G) / count
+                    const float d = gret - v[u];
+                    acc[0] += w[u] * d * d;
+                    a.dvalue[off] = -w[u] * d / (float)(T * B);  // 0.5 * w * 2 * (V - G) / count
                 }
             }
         }
