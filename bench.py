@@ -480,8 +480,14 @@ def run_gpu(args):
         clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end through the public API from pinned host buffers ------------------------------------------------
-    host = [{k: v.pin_memory() for k, v in make_batch(2000 * rank + i).items()} for i in range(2)]
-    h2d = batch_bytes(host[0])
+    packed = not args.e2e_separate_copies
+    if packed:  # one pinned buffer + one device buffer per slot: the H2D transfer of a step is a single copy
+        slots = [b2.PackedBatch(make_batch(2000 * rank + i), dev) for i in range(2)]
+        host = slots
+        h2d = slots[0].payload_bytes()
+    else:
+        host = [{k: v.pin_memory() for k, v in make_batch(2000 * rank + i).items()} for i in range(2)]
+        h2d = batch_bytes(host[0])
 
     # The host side is a two-deep prefetching loader (what DI-engine's CudaFetcher, ding/torch_utils/data_helper.py:543,
     # does for the learner): the H2D copy of step i+1 is enqueued on a copy stream before step i's result is read back,
@@ -489,6 +495,8 @@ def run_gpu(args):
     copy_stream = torch.cuda.Stream()
 
     def upload(hb):
+        if packed:
+            return hb.upload(copy_stream)
         with torch.cuda.stream(copy_stream):
             d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
             ev = torch.cuda.Event()
@@ -497,8 +505,9 @@ def run_gpu(args):
 
     def e2e_compute(d, ev):
         torch.cuda.current_stream().wait_event(ev)
-        for v in d.values():
-            v.record_stream(torch.cuda.current_stream())
+        if not packed:
+            for v in d.values():
+                v.record_stream(torch.cuda.current_stream())
         ln = d['logit_new'].requires_grad_(True)
         vn = d['value_new'].requires_grad_(True)
         gd = b2.gae_data(d['value'], d['next_value'], d['reward'], d['done'], d['traj_flag'])
@@ -637,6 +646,8 @@ def main():
                     help='gae, fused ppo forward+grad, verification as three kernels (default: the one-launch gae+ppo '
                          'step of csrc/colws.cu + verification)')
     ap.add_argument('--onepass', action='store_true', help='accepted for compatibility: the one-launch step is the default')
+    ap.add_argument('--e2e-separate-copies', action='store_true',
+                    help='e2e: one pinned tensor and one H2D copy per input (default: di_engine_b200.PackedBatch, one copy)')
     args = ap.parse_args()
     if args.impl == 'reference':
         if args.steps > 400:

@@ -482,6 +482,30 @@ def test_vtrace_one_launch_under_graph_capture():
         assert torch.equal(res[k], eager[k]), k
 
 
+def test_packed_batch_round_trip_and_use():
+    """di_engine_b200.PackedBatch: one pinned buffer -> one H2D copy -> device views with the original shapes / dtypes, usable
+    by the operators (alignment) and refreshed by the next upload."""
+    hb = __import__('bench').make_batch(5, T=32, B=48, N=6)
+    hb['weight'] = None
+    pb = b2.PackedBatch(hb, DEV)
+    assert pb.payload_bytes() == sum(v.numel() * v.element_size() for v in hb.values() if v is not None)
+    d, ev = pb.upload()
+    torch.cuda.current_stream().wait_event(ev)
+    for k, v in hb.items():
+        if v is None:
+            assert d[k] is None
+        else:
+            assert d[k].dtype == v.dtype and d[k].shape == v.shape and d[k].data_ptr() % 256 == 0
+            assert torch.equal(d[k].cpu(), v), k
+    adv = b2.gae(b2.gae_data(d['value'], d['next_value'], d['reward'], d['done'], d['traj_flag']), 0.99, 0.95)
+    ref = rl_oracle.gae(hb['value'], hb['next_value'].clone(), hb['reward'], hb['done'], hb['traj_flag'], 0.99, 0.95)
+    assert torch.equal(adv.cpu(), ref)
+    pb.host['reward'].mul_(2.0)  # the collector writes into the pinned views; the next upload carries the change
+    d2, ev2 = pb.upload()
+    torch.cuda.current_stream().wait_event(ev2)
+    assert torch.equal(d2['reward'].cpu(), hb['reward'] * 2.0)
+
+
 def test_p2p_allreduce_kernel_single_rank_degenerate():
     """world = 1: the mailbox exchange must reproduce the local values (mean over one rank), across many sequence
     numbers and under CUDA-graph replay.  (Two and more ranks: tools/test_p2p.py under torchrun.)"""
