@@ -28,7 +28,9 @@ class PackedBatch:
             self.layout[k] = (off, nbytes, v.dtype, tuple(v.shape))
             off = (off + nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
         self.nbytes = off
-        self.host_buf = torch.empty(max(off, 1), dtype=torch.uint8).pin_memory()
+        self.host_buf = torch.empty(max(off, 1), dtype=torch.uint8)
+        if self.device.type == 'cuda':
+            self.host_buf = self.host_buf.pin_memory()
         self.dev_buf = torch.empty(max(off, 1), dtype=torch.uint8, device=self.device)
         self.host = self._views(self.host_buf)
         for k, v in like.items():
@@ -50,6 +52,9 @@ class PackedBatch:
 
     def upload(self, stream=None):
         """Enqueue the single H2D copy on ``stream`` (default: the current one); returns (fresh device views, event)."""
+        if self.device.type != 'cuda':  # layout tests on a host without a GPU: plain copy, nothing to wait for
+            self.dev_buf.copy_(self.host_buf)
+            return self._views(self.dev_buf), None
         stream = stream if stream is not None else torch.cuda.current_stream(self.device)
         with torch.cuda.stream(stream):
             self.dev_buf.copy_(self.host_buf, non_blocking=True)

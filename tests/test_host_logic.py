@@ -320,3 +320,19 @@ def test_hpc_rll_shim_layout(monkeypatch):
     for k in list(sys.modules):
         if k == 'hpc_rll' or k.startswith('hpc_rll.'):
             del sys.modules[k]
+
+
+def test_packed_batch_layout():
+    """PackedBatch (data.py): 256-byte aligned back-to-back layout, dtype / shape preserving views, None passthrough."""
+    like = {'a': torch.arange(7, dtype=torch.float32), 'act': torch.arange(5, dtype=torch.int64).reshape(5, 1), 'none': None,
+            'm': torch.ones(3, 4, 2)}
+    pb = b2.PackedBatch(like, 'cpu')
+    offs = [spec[0] for spec in pb.layout.values() if spec is not None]
+    assert all(o % 256 == 0 for o in offs) and offs == sorted(offs)
+    assert pb.payload_bytes() == 7 * 4 + 5 * 8 + 24 * 4
+    d, ev = pb.upload()
+    assert ev is None and d['none'] is None
+    for k in ('a', 'act', 'm'):
+        assert d[k].dtype == like[k].dtype and d[k].shape == like[k].shape and torch.equal(d[k], like[k])
+    pb.host['a'].add_(1.0)
+    assert torch.equal(pb.upload()[0]['a'], like['a'] + 1.0)
