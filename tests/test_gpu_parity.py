@@ -482,6 +482,17 @@ def test_vtrace_one_launch_under_graph_capture():
         assert torch.equal(res[k], eager[k]), k
 
 
+def test_c_abi_from_plain_c():
+    """examples/c_abi_gae.c: gcc-compiled caller with cudaMalloc'd buffers and its own stream -- no torch in the process;
+    gae must be bit-identical to the host recurrence, including the in-place next_value mask."""
+    import subprocess
+    import __graft_entry__ as ge
+    exe = ge.build_c_example()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert '0 mismatching values' in r.stdout
+
+
 def test_packed_batch_round_trip_and_use():
     """di_engine_b200.PackedBatch: one pinned buffer -> one H2D copy -> device views with the original shapes / dtypes, usable
     by the operators (alignment) and refreshed by the next upload."""
