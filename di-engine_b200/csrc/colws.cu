@@ -1,5 +1,5 @@
 // Column-tile learner step, warp-specialised: gae -> ppo_error (+ gradients) in ONE launch, no cross-CTA dependency, no
-// CTA-wide barrier in the loop, every copy a plain 16-byte LDGSTS (cp.async) whose address arithmetic is loop-invariant.
+// CTA-wide barrier in the loop, every copy a plain 16-byte LDGSTS (cp.async) issued by a dedicated loader warp.
 //
 // History (profiles/r01f, r01g): coltile.cu (all threads copy + compute, __syncthreads per chunk) spent half of its 19.7
 // warp-instructions per transition on copy addressing and was issue-bound; coltma.cu moved the copies to 2-D TMA boxes and
@@ -20,7 +20,7 @@
 //              row code of ppo.cu) and store the gradient row and the value gradient straight to HBM; arrive on "done".
 // Rings run across tile boundaries (static tile -> CTA assignment: deterministic loss partial sums).
 //
-// Measured at config D (profiles/r01h_*): once the ring is primed the chunks land every 1.28 us per CTA, i.e. 6.5 TB/s over
+// Measured at config D (profiles/r01i_colws_timeline.txt): once the ring is primed the chunks land every 1.28 us per CTA, i.e. 6.5 TB/s over
 // the 256 CTAs -- the measured HBM peak; the kernel's 15.4 us are 10.2 us of streaming plus ~2.5 us until the first chunk
 // has landed and ~2.5 us of tail (last chunk's math, store drain, partial sums, finalize_sums launch).  Loader variants
 // tried and rejected (tools/sweep_col.py, B200RL_LIB builds): loop-invariant piece offsets in registers with one or two
