@@ -457,6 +457,24 @@ def run_gpu(args):
         barrier()
         dev_ms = e0.elapsed_time(e1)
 
+        # ---- the same step launched eagerly (one ctypes call per launch, no graph): host-bound, reported next to the replay
+        eager_ms = None
+        try:
+            n_eager = 200
+            for i in range(8):
+                sets[i % NSETS]()
+            main.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(main)
+            for i in range(n_eager):
+                sets[i % NSETS]()
+            g1.record(main)
+            main.synchronize()
+            eager_ms = g0.elapsed_time(g1) / n_eager
+        except Exception as e:  # never let the secondary figure break the benchmark
+            if rank == 0:
+                print('bench: eager-launch timing skipped (%s)' % e, file=sys.stderr)
+
         # ---- per-kernel timing: each kernel alone, back to back over the rotated buffer sets, replayed as a graph so
         # that launch gaps of the host do not enter the figure (CUDA events on the launching stream)
         names = [n for n, _ in sets[0].kernels()]
@@ -598,6 +616,7 @@ def run_gpu(args):
             },
             'e2e': {'value': e2e_value, 'unit': 'transitions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
                     'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps},
+            'eager_ms_per_step': eager_ms,  # same launches without the CUDA graph (host-bound; `value` is the graph replay)
             'gpu_launches': (len(names) + 1) * K,  # + the finalize_sums launch behind every loss-reducing kernel
             'clocks': clocks,
         }
