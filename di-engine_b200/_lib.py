@@ -27,11 +27,15 @@ PROTOTYPES = {
     "b200rl_ppo_fwd_grad": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, c_size_t, P],
     "b200rl_ppo_value_fwd": [P, P, P, P, LL, D, I, P, P, P, c_size_t, P],
     "b200rl_ppo_fused_supported": [P, P, P, P, P, P, P, P, P, P, LL, LL],
-    "b200rl_qntd_fwd": [P, P, P, P, P, P, P, P, LL, P, LL, LL, I, D, I, I, D, I, D, P, P, P, P, P, c_size_t, P],
-    "b200rl_qntd_bwd": [P, P, P, LL, LL, P, P],
-    "b200rl_dntd_fwd": [P, P, P, P, P, P, P, LL, P, LL, P, LL, LL, LL, I, I, D, D, D, P, P, P, P, P, c_size_t, P],
-    "b200rl_dntd_bwd": [P, P, P, P, LL, P, LL, LL, I, P, P],
+    "b200rl_qntd_fwd": [P, P, P, P, P, P, P, P, LL, P, LL, LL, LL, I, D, I, I, D, I, D, I, LL, D, P, P, P, P, P, P, P,
+                        c_size_t, P],
+    "b200rl_qntd_bwd": [P, P, P, P, P, LL, LL, LL, I, LL, I, P, P],
+    "b200rl_dntd_fwd": [P, P, P, P, P, P, P, LL, P, LL, P, LL, LL, LL, I, I, D, D, D, P, P, P, P, P, P, c_size_t, P],
+    "b200rl_dntd_bwd": [P, P, P, P, LL, P, LL, LL, I, I, P, P],
     "b200rl_lambda_returns": [P, P, P, D, P, D, P, I, LL, LL, P, P],
+    "b200rl_lambda_returns_bwd": [P, P, P, P, P, D, P, D, P, I, LL, LL, P, P, P, P, P],
+    "b200rl_tb_cross_entropy_fwd": [P, P, P, LL, LL, LL, P, P],
+    "b200rl_tb_cross_entropy_bwd": [P, P, P, P, LL, LL, LL, P, P],
     "b200rl_td_lambda_fwd": [P, P, P, D, D, LL, LL, P, P, P, c_size_t, P],
     "b200rl_scale": [P, P, P, LL, P],
     "b200rl_upgo_head_fwd": [P, P, P, P, P, P, LL, LL, LL, P, P, P, c_size_t, P],

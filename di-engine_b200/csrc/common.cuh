@@ -92,12 +92,16 @@ __device__ __forceinline__ bool grid_sum(float (&v)[K], double (&tot)[K], float*
         s_dep = dep;  // a real use of the returned values: instructions issue in order, so everything below waits here
         asm volatile("" ::: "memory");
         if (trace) trace[1] = gtimer();
-        unsigned int ticket = atomicAdd(&ctrl[slot], 1u);  // issued only after the exchanges returned
+        // release: the partials above (and, through the barrier before, whatever the CTA's threads stored) happen-before
+        // the ticket; acquire: the last CTA's reads below happen-after every earlier ticket (PTX memory model, gpu scope)
+        unsigned int ticket;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&ctrl[slot]) : "memory");
         if (trace) trace[2] = gtimer();
         s_last = (ticket == gridDim.x - 1);
     }
     __syncthreads();
     if (!s_last) return false;
+    fence_acq_rel_gpu();  // every thread of the last CTA reads other CTAs' results: order those reads after the ticket
     if (trace && threadIdx.x == 0) trace[3] = gtimer();
     double acc[K];
 #pragma unroll

@@ -93,6 +93,51 @@ __global__ void __launch_bounds__(NT) upgo_bwd_kernel(UpgoArgs a) {
     }
 }
 
+// tb_cross_entropy (upgo.py:7-43) on its own: ce[s] = sum_k mask_k * log p(a_k) (3-D logits: K = 1, the reference's mean
+// over a singleton dim) and its backward for an upstream gradient per (t, b) entry.
+template <int NT, int L>
+__global__ void __launch_bounds__(NT) tbce_fwd_kernel(const float* __restrict__ logit, const long long* __restrict__ action,
+                                                      const float* __restrict__ mask, long long TB, int K, int N,
+                                                      float* __restrict__ ce) {
+    pdl_prologue();
+    const int lane = (L == 32) ? (threadIdx.x & 31) : 0;
+    const long long s = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
+                                  : (long long)blockIdx.x * NT + threadIdx.x;
+    if (s >= TB) return;
+    float metric = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const long long row = s * K + k;
+        const float* z = logit + row * N;
+        const float lse = row_lse<L>([&](int j) { return z[j]; }, N, lane);
+        float lp = z[action[row]] - lse;
+        if (mask) lp *= mask[row];
+        metric += lp;
+    }
+    if (lane == 0) ce[s] = metric;
+}
+
+template <int NT, int L>
+__global__ void __launch_bounds__(NT) tbce_bwd_kernel(const float* __restrict__ logit, const long long* __restrict__ action,
+                                                      const float* __restrict__ mask, const float* __restrict__ g_ce,
+                                                      long long TB, int K, int N, float* __restrict__ grad_logit) {
+    pdl_prologue();
+    const int lane = (L == 32) ? (threadIdx.x & 31) : 0;
+    const long long row = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
+                                    : (long long)blockIdx.x * NT + threadIdx.x;
+    if (row >= TB * K) return;
+    const float* z = logit + row * N;
+    float* gz = grad_logit + row * N;
+    const float lse = row_lse<L>([&](int j) { return z[j]; }, N, lane);
+    float c = g_ce[row / K];
+    if (mask) c *= mask[row];
+    const int act = (int)action[row];
+    for (int j = lane; j < N; j += L) {
+        float gj = -c * expf(z[j] - lse);
+        if (j == act) gj += c;
+        gz[j] = gj;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // V-trace
 // ---------------------------------------------------------------------------------------------------------------
@@ -353,6 +398,27 @@ extern "C" int b200rl_upgo_head_bwd(const float* logit, const long long* action,
     cudaStream_t st = (cudaStream_t)stream;
     if (N > 64) (void)launch_k(upgo_bwd_kernel<NT, 32>, div_up(TB * K, NT / 32), NT, 0, st, a);
     else (void)launch_k(upgo_bwd_kernel<NT, 1>, div_up(TB * K, NT), NT, 0, st, a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_tb_cross_entropy_fwd(const float* logit, const long long* action, const float* mask, long long TB,
+                                           long long K, long long N, float* ce, void* stream) {
+    if (TB <= 0 || K < 1 || N < 1 || !logit || !action || !ce) return B200RL_ERR_ARG;
+    constexpr int NT = 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 64) (void)launch_k(tbce_fwd_kernel<NT, 32>, div_up(TB, NT / 32), NT, 0, st, logit, action, mask, TB, (int)K, (int)N, ce);
+    else (void)launch_k(tbce_fwd_kernel<NT, 1>, div_up(TB, NT), NT, 0, st, logit, action, mask, TB, (int)K, (int)N, ce);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_tb_cross_entropy_bwd(const float* logit, const long long* action, const float* mask,
+                                           const float* g_ce, long long TB, long long K, long long N, float* grad_logit,
+                                           void* stream) {
+    if (TB <= 0 || K < 1 || N < 1 || !logit || !action || !g_ce || !grad_logit) return B200RL_ERR_ARG;
+    constexpr int NT = 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 64) (void)launch_k(tbce_bwd_kernel<NT, 32>, div_up(TB * K, NT / 32), NT, 0, st, logit, action, mask, g_ce, TB, (int)K, (int)N, grad_logit);
+    else (void)launch_k(tbce_bwd_kernel<NT, 1>, div_up(TB * K, NT), NT, 0, st, logit, action, mask, g_ce, TB, (int)K, (int)N, grad_logit);
     return (int)cudaGetLastError();
 }
 

@@ -181,10 +181,12 @@ __global__ void __launch_bounds__(NT) ppo_fwd_kernel(PpoArgs a, float* out, floa
     constexpr int L = (MODE == 2) ? 32 : 1;
     const int lane = (MODE == 2) ? (threadIdx.x & 31) : 0;
     const int N = a.N, G = a.G;
-    const long long s = (MODE == 1) ? (long long)blockIdx.x * NT + threadIdx.x
-                                    : (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    // grid-stride over the samples: the grid (and with it the per-CTA partial sums in the workspace) is capped by the host
+    const long long per_cta = (MODE == 1) ? NT : NT / 32;
+    long long s = (MODE == 1) ? (long long)blockIdx.x * NT + threadIdx.x
+                              : (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // policy, value, entropy, kl, approx_kl, clipfrac
-    if (s < a.S) {
+    for (; s < a.S; s += per_cta * gridDim.x) {
         const float* zn = a.logit_new + s * G * N;
         const float* zo = a.logit_old + s * G * N;
         const float* zp = a.logit_pre ? a.logit_pre + s * G * N : nullptr;
@@ -215,13 +217,13 @@ __global__ void __launch_bounds__(NT) ppo_fwd_kernel(PpoArgs a, float* out, floa
             const float ent = (G == 1) ? ent_sum : ent_sum / (float)G;
             float dsel;
             const float sel = surrogate(ratio, adv, a.clip_lo, a.clip_hi, a.dual_clip, dsel);
-            acc[0] = -sel * w;
+            acc[0] -= sel * w;
             float dterm;
-            acc[1] = value_term(a.value_new[s], a.value_old[s], a.ret[s], a.clip, a.use_value_clip, dterm) * w;
-            acc[2] = ent * w;
-            acc[3] = kl;
-            acc[4] = akl;
-            acc[5] = (ratio > a.clip_hi || ratio < a.clip_lo) ? 1.f : 0.f;
+            acc[1] += value_term(a.value_new[s], a.value_old[s], a.ret[s], a.clip, a.use_value_clip, dterm) * w;
+            acc[2] += ent * w;
+            acc[3] += kl;
+            acc[4] += akl;
+            acc[5] += (ratio > a.clip_hi || ratio < a.clip_lo) ? 1.f : 0.f;
         }
     }
     double tot[6];
@@ -468,7 +470,8 @@ extern "C" int b200rl_ppo_fwd(const float* logit_new, const float* logit_old, co
     if (tile_path_ok(a)) return dispatch_tile<PPO_FWD>(a, out, workspace, workspace_bytes, st);
     constexpr int NT = 128;
     const bool warp = a.N > 64;
-    const int grid = warp ? div_up(S, NT / 32) : div_up(S, NT);
+    int grid = warp ? div_up(S, NT / 32) : div_up(S, NT);
+    if (grid > 148 * 16) grid = 148 * 16;  // grid-stride kernel: the workspace need is bounded whatever S is
     if ((size_t)(WS_CTRL_WORDS + (size_t)grid * 6) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
     if (warp) (void)launch_k(ppo_fwd_kernel<NT, 2>, grid, NT, 0, st, a, out, workspace);
     else (void)launch_k(ppo_fwd_kernel<NT, 1>, grid, NT, 0, st, a, out, workspace);

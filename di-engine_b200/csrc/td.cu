@@ -41,17 +41,19 @@ __device__ __forceinline__ float criterion_eval(int kind, float param, float x, 
 }
 
 struct QntdArgs {
-    const float* q;
-    const float* next_q;
-    const long long* action;
+    const float* q;            // (S, G, N)
+    const float* next_q;       // (S, G, N)
+    const long long* action;   // (S, G)
     const long long* next_action;
-    const float* reward;       // (nstep, B) or (B) when cum_reward
-    const float* done;         // (B)
-    const float* weight;       // (B) or null
-    const float* value_gamma;  // null, or pointer with stride 0 (0-dim) / 1 (B)
+    const float* reward;       // (nstep, S), (S) when cum_reward; sequence form (S = Tseq*Bcol): (Tseq, nstep, Bcol)
+    const float* done;         // (S)
+    const float* weight;       // (S) or null
+    const float* value_gamma;  // null, or pointer with stride 0 (0-dim) / 1 (S)
     long long value_gamma_stride;
-    const float* gamma_ps;     // NGU per-sample gamma (B) or null
-    long long B;
+    const float* gamma_ps;     // NGU per-sample gamma (Bcol) or null
+    long long S;               // samples
+    long long Bcol;            // == S, or the batch width of the sequence form (sample s = t*Bcol + b)
+    int G;                     // rows per sample: 1, the agent dim of the multi-agent form or the BDQ branches
     int N;
     int nstep;
     float gamma;
@@ -61,60 +63,126 @@ struct QntdArgs {
     float eps, four_eps, two_eps;
     int criterion;
     float crit_param;
+    int group_mean;    // td_error_per_sample (S) = mean over the G rows (bdq_nstep_td_error, td.py:788) instead of (S, G)
+    double loss_div;   // loss = sum(w*td) / loss_div
+    float prio_max_w, prio_mean_w, prio_div;  // sequence form: priority[b] = max_w*max_t|td| + mean_w*sum_t|td|/prio_div
     float* loss;
     float* td_err;
-    float* dq;  // saved d(loss)/d(q_sa) for unit upstream gradient
-    float* target;  // nullable: the (detached) n-step target, for callers that apply their own criterion
+    float* dcrit;      // (S, G) d criterion / d q_sa (unweighted): what the backward launch needs
+    float* target;     // nullable: the (detached) n-step target (S, G), for callers that apply their own criterion
+    float* grad_unit;  // nullable (S, G, N): d loss / d q for a unit upstream gradient, written by the forward launch
+    float* priority;   // nullable (Bcol): sequence form only
 };
 
+// One launch: n-step target, criterion, deterministic loss reduction, per-sample errors AND (grad_unit) the gradient of the
+// loss for a unit upstream gradient -- the backward launch only has to verify that the upstream gradient was 1.
 template <int NT>
 __global__ void __launch_bounds__(NT) qntd_fwd_kernel(QntdArgs a, float* ws) {
     pdl_prologue();
-    const long long b = (long long)blockIdx.x * NT + threadIdx.x;
+    __shared__ float s_coef[NT];
+    __shared__ int s_act[NT];
+    const long long s0 = (long long)blockIdx.x * NT;
+    const long long s = s0 + threadIdx.x;
+    const float inv_div = (float)(1.0 / a.loss_div);
     float acc[1] = {0.f};
-    if (b < a.B) {
-        const float q_sa = a.q[b * a.N + a.action[b]];
-        float tq = a.next_q[b * a.N + a.next_action[b]];
-        if (a.rescale) tq = value_h_inv(tq, a.eps, a.four_eps, a.two_eps);
-        const float nd = fsub(1.f, a.done[b]);
-        float target;
+    s_coef[threadIdx.x] = 0.f;
+    s_act[threadIdx.x] = -1;
+    if (s < a.S) {
+        const long long tq_ = s / a.Bcol, b = s - tq_ * a.Bcol;  // sequence step / batch column (tq_ = 0 when Bcol == S)
+        const float nd = fsub(1.f, a.done[s]);
+        const float w = a.weight ? a.weight[s] : 1.f;
+        float ret = 0.f, vg;
         if (a.cum_reward) {
-            const float vg = a.value_gamma ? a.value_gamma[b * a.value_gamma_stride] : a.gamma_pow_n;
-            target = fadd(a.reward[b], fmul(fmul(vg, tq), nd));  // td.py:712-715
+            ret = a.reward[s];
+            vg = a.value_gamma ? a.value_gamma[s * a.value_gamma_stride] : a.gamma_pow_n;
         } else {
             const float g = a.gamma_ps ? a.gamma_ps[b] : a.gamma;
-            float rf = 1.f, ret = 0.f;
+            const float* rw = a.reward + tq_ * a.nstep * a.Bcol + b;
+            float rf = 1.f;
             for (int i = 0; i < a.nstep; ++i) {  // td.py:261-264 / :277-281
-                ret = fadd(ret, fmul(a.reward[(long long)i * a.B + b], rf));
+                ret = fadd(ret, fmul(rw[(long long)i * a.Bcol], rf));
                 rf = fmul(g, rf);
             }
-            float vg;
             if (a.gamma_ps) vg = rf;  // reward_factor[nstep]
-            else vg = a.value_gamma ? a.value_gamma[b * a.value_gamma_stride] : a.gamma_pow_n;
-            target = fadd(ret, fmul(fmul(vg, tq), nd));  // td.py:266 / :273 / :282
+            else vg = a.value_gamma ? a.value_gamma[s * a.value_gamma_stride] : a.gamma_pow_n;
         }
-        if (a.rescale) target = value_h(target, a.eps);
-        float dx;
-        const float td = criterion_eval(a.criterion, a.crit_param, q_sa, target, dx);
-        const float w = a.weight ? a.weight[b] : 1.f;
-        a.td_err[b] = td;
-        if (a.target) a.target[b] = target;
-        a.dq[b] = w * dx / (float)a.B;
-        acc[0] = td * w;
+        float td_sum = 0.f;
+        for (int gi = 0; gi < a.G; ++gi) {
+            const long long r = s * a.G + gi;
+            const int act = (int)a.action[r];
+            const float q_sa = a.q[r * a.N + act];
+            float tq = a.next_q[r * a.N + a.next_action[r]];
+            if (a.rescale) tq = value_h_inv(tq, a.eps, a.four_eps, a.two_eps);
+            float target = fadd(ret, fmul(fmul(vg, tq), nd));  // td.py:266 / :273 / :282 / :712-715
+            if (a.rescale) target = value_h(target, a.eps);
+            float dx;
+            const float td = criterion_eval(a.criterion, a.crit_param, q_sa, target, dx);
+            if (a.group_mean) td_sum += td;
+            else a.td_err[r] = td;
+            if (a.target) a.target[r] = target;
+            a.dcrit[r] = dx;
+            acc[0] += td * w;
+            if (a.grad_unit) {
+                const float coef = w * dx * inv_div;
+                if (a.G == 1) {
+                    s_coef[threadIdx.x] = coef;
+                    s_act[threadIdx.x] = act;
+                } else {
+                    float* gq = a.grad_unit + r * a.N;
+                    for (int j = 0; j < a.N; ++j) gq[j] = (j == act) ? coef : 0.f;
+                }
+            }
+        }
+        if (a.group_mean) a.td_err[s] = td_sum / (float)a.G;
+    }
+    if (a.grad_unit && a.G == 1) {  // the block's NT gradient rows are contiguous: coalesced stores
+        __syncthreads();
+        const long long rows = (a.S - s0) < NT ? (a.S - s0) : NT;
+        float* gq = a.grad_unit + s0 * a.N;
+        for (long long i = threadIdx.x; i < rows * a.N; i += NT) {
+            const int rr = (int)(i / a.N), j = (int)(i - (long long)rr * a.N);
+            gq[i] = (j == s_act[rr]) ? s_coef[rr] : 0.f;
+        }
     }
     double tot[1];
-    if (grid_sum<1, NT>(acc, tot, ws, 0) && threadIdx.x == 0) a.loss[0] = (float)(tot[0] / (double)a.B);
+    const bool last = grid_sum<1, NT>(acc, tot, ws, 0);
+    if (last && threadIdx.x == 0) a.loss[0] = (float)(tot[0] / a.loss_div);
+    if (last && a.priority) {
+        // sequence form (ding/policy/r2d2.py:367-369): the last CTA sees every per-step error (published before the tickets)
+        const long long Tq = a.S / a.Bcol;
+        for (long long b = threadIdx.x; b < a.Bcol; b += NT) {
+            float mx = 0.f, sm = 0.f;
+            for (long long t = 0; t < Tq; ++t) {
+                const float e = fabsf(__ldcg(a.td_err + t * a.Bcol + b));
+                mx = (t == 0) ? e : fmaxf(mx, e);
+                sm += e;
+            }
+            a.priority[b] = a.prio_max_w * mx + a.prio_mean_w * (sm / a.prio_div);
+        }
+    }
 }
 
-__global__ void qntd_bwd_kernel(const float* __restrict__ dq, const long long* __restrict__ action,
-                                const float* __restrict__ g_loss, long long B, int N, float* __restrict__ grad_q) {
+// grad_q[r, j] = 1[j == a_r] * (g_loss * w_s / loss_div + g_td) * dcrit[r].  skip_if_unit: the forward launch already wrote
+// grad_q for g_loss == 1 and no per-sample upstream gradient -- verify on the device and leave at once if that held.
+__global__ void qntd_bwd_kernel(const float* __restrict__ dcrit, const float* __restrict__ weight,
+                                const long long* __restrict__ action, const float* __restrict__ g_loss,
+                                const float* __restrict__ g_td, long long S, int G, int N, int group_mean, float inv_div,
+                                int skip_if_unit, float* __restrict__ grad_q) {
     pdl_prologue();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * N) return;
-    const long long b = i / N;
-    const int j = (int)(i - b * N);
     const float g = g_loss ? *g_loss : 0.f;
-    grad_q[i] = (j == (int)action[b]) ? g * dq[b] : 0.f;
+    if (skip_if_unit && !g_td && g == 1.f) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * G * N) return;
+    const long long r = i / N;
+    const int j = (int)(i - r * N);
+    float out = 0.f;
+    if (j == (int)action[r]) {
+        const long long s = r / G;
+        float c = g * (weight ? weight[s] : 1.f) * inv_div;
+        if (g_td) c += group_mean ? g_td[s] / (float)G : g_td[r];
+        out = c * dcrit[r];
+    }
+    grad_q[i] = out;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -146,6 +214,7 @@ struct DntdArgs {
     float* td_err;  // (R)
     float* proj;    // (R, n_atom)
     int* bad_flag;  // set to 1 if any selected dist entry is <= 0 (td.py:513)
+    float* grad_unit;  // nullable (R, N, n_atom): d loss / d dist for a unit upstream gradient
 };
 
 template <int NT>
@@ -190,11 +259,19 @@ __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
             a.proj[r * a.n_atom + j] = m;
         }
         td = -warp_sum(td);
-        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.bad_flag, 1);
+        if (a.bad_flag && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.bad_flag, 1);
+        const float w = a.weight ? a.weight[r * a.weight_stride] : 1.f;
         if (lane == 0) {
             a.td_err[r] = td;
-            const float w = a.weight ? a.weight[r * a.weight_stride] : 1.f;
             acc[0] = td * w;
+        }
+        if (a.grad_unit) {  // dense (N, n_atom) gradient block of the row: non-zero on the chosen action only
+            const int sel = (int)a.act[r];
+            const float c = -w / (float)a.R;
+            float* gr = a.grad_unit + r * a.N * a.n_atom;
+            for (int n = 0; n < a.N; ++n)
+                for (int j = lane; j < a.n_atom; j += 32)
+                    gr[n * a.n_atom + j] = (n == sel) ? c * pj[j] / dd[j] : 0.f;
         }
     }
     double tot[1];
@@ -204,8 +281,10 @@ __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
 __global__ void dntd_bwd_kernel(const float* __restrict__ dist, const long long* __restrict__ act,
                                 const float* __restrict__ proj, const float* __restrict__ weight,
                                 long long weight_stride, const float* __restrict__ g_loss, long long R, int N,
-                                int n_atom, float* __restrict__ grad_dist) {
+                                int n_atom, int skip_if_unit, float* __restrict__ grad_dist) {
     pdl_prologue();
+    // skip_if_unit: the forward launch already wrote grad_dist for a unit upstream gradient -- verify and leave
+    if (skip_if_unit && g_loss && *g_loss == 1.f) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_row = (long long)N * n_atom;
     if (i >= R * per_row) return;
@@ -385,6 +464,84 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
     }
 }
 
+// Backward of the lambda-return scan (generalized_lambda_returns is differentiable in the reference, td.py:1574-1651; MBSAC
+// and Dreamer back-propagate an actor loss through it): the transposed recurrence runs FORWARD in time,
+//   a_t = gG_t + (1-d_{t-1})*disc_{t-1}*a_{t-1};  dr_t = a_t;  dV_{t+1} = a_t*(1-d_t)*(gamma_t - disc_t)  (last row: gamma_t)
+// and, when the (T, B) gamma / lambda tensors want gradients, dgamma_t = a_t*(1-d_t)*(lambda_t*G_{t+1} + (1-lambda_t)*V_{t+1}),
+// dlambda_t = a_t*(1-d_t)*gamma_t*(G_{t+1} - V_{t+1}).  Thread = column; every load of a step is independent of the carry.
+struct LamBwdArgs {
+    const float* g_ret;    // (T, B) upstream gradient
+    const float* value;    // (T+1, B)
+    const float* reward;   // (T, B)  (upgo mode: drives lambda)
+    const float* ret;      // (T, B) forward result (needed for dgamma / dlambda only)
+    const float* gammas;   // nullable
+    const float* lambdas;  // nullable
+    const float* done;     // nullable
+    float gamma, lambda;
+    int upgo_mode;
+    long long T, B;
+    float* g_value;    // (T+1, B)
+    float* g_reward;   // nullable (T, B)
+    float* g_gammas;   // nullable (T, B)
+    float* g_lambdas;  // nullable (T, B)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) lambda_returns_bwd_kernel(LamBwdArgs a) {
+    pdl_prologue();
+    const long long c = (long long)blockIdx.x * NT + threadIdx.x;
+    if (c >= a.B) return;
+    const long long T = a.T, B = a.B;
+    a.g_value[c] = 0.f;
+    float adj = 0.f, coef = 0.f;
+    constexpr int U = 8;
+    for (long long t0 = 0; t0 < T; t0 += U) {
+        float g[U], gg[U], ll[U], m[U], vn[U], gn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // all loads of U steps first
+            const long long t = t0 + u;
+            g[u] = 0.f; gg[u] = a.gamma; ll[u] = a.lambda; m[u] = 1.f; vn[u] = 0.f; gn[u] = 0.f;
+            if (t < T) {
+                const long long off = t * B + c;
+                g[u] = a.g_ret[off];
+                if (a.upgo_mode) {
+                    gg[u] = 1.f;
+                    ll[u] = 1.f;
+                    if (t < T - 1) ll[u] = (fadd(a.reward[off + B], a.value[off + 2 * B]) >= a.value[off + B]) ? 1.f : 0.f;
+                } else {
+                    if (a.gammas) gg[u] = a.gammas[off];
+                    if (a.lambdas) ll[u] = a.lambdas[off];
+                }
+                if (a.done) m[u] = 1.f - a.done[off];
+                if (a.g_gammas || a.g_lambdas) {
+                    vn[u] = a.value[off + B];
+                    gn[u] = (t < T - 1) ? a.ret[off + B] : 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long t = t0 + u;
+            if (t >= T) break;
+            const long long off = t * B + c;
+            adj = fmaf(coef, adj, g[u]);
+            if (a.g_reward) a.g_reward[off] = adj;
+            const float am = adj * m[u];
+            if (t == T - 1) {
+                a.g_value[off + B] = am * gg[u];
+                if (a.g_gammas) a.g_gammas[off] = am * vn[u];
+                if (a.g_lambdas) a.g_lambdas[off] = 0.f;
+            } else {
+                const float disc = gg[u] * ll[u];
+                a.g_value[off + B] = am * (gg[u] - disc);
+                if (a.g_gammas) a.g_gammas[off] = am * (ll[u] * gn[u] + (1.f - ll[u]) * vn[u]);
+                if (a.g_lambdas) a.g_lambdas[off] = am * gg[u] * (gn[u] - vn[u]);
+                coef = m[u] * disc;
+            }
+        }
+    }
+}
+
 // out[i] = (*g) * in[i]  -- backward of the heads that saved their unit-upstream gradient in the forward pass
 __global__ void scale_kernel(const float* __restrict__ g, const float* __restrict__ in, float* __restrict__ out,
                              long long n) {
@@ -397,38 +554,57 @@ __global__ void scale_kernel(const float* __restrict__ g, const float* __restric
 
 using namespace b200rl;
 
+static double qntd_loss_div(long long S, long long G, long long seq_len) {
+    if (seq_len <= 0) return (double)S * (double)G;  // (td * weight).mean() over every row
+    // sequence form: sum_t mean_b(...) / (len + 1e-8) -- a python float that torch narrows to fp32 (r2d2.py:364)
+    return (double)(S / seq_len) * (double)G * (double)(float)((double)seq_len + 1e-8);
+}
+
 extern "C" int b200rl_qntd_fwd(const float* q, const float* next_n_q, const long long* action,
                                const long long* next_n_action, const float* reward, const float* done,
                                const float* weight, const float* value_gamma, long long value_gamma_stride,
-                               const float* gamma_per_sample, long long B, long long N, int nstep, double gamma,
-                               int cum_reward, int rescale, double rescale_eps, int criterion, double criterion_param,
-                               float* loss, float* td_error_per_sample, float* dq_saved, float* target_out,
-                               float* workspace, size_t workspace_bytes, void* stream) {
-    if (B <= 0 || N < 1 || nstep < 1 || !q || !next_n_q || !action || !next_n_action || !reward || !done || !loss ||
-        !td_error_per_sample || !dq_saved || !workspace)
+                               const float* gamma_per_sample, long long S, long long G, long long N, int nstep,
+                               double gamma, int cum_reward, int rescale, double rescale_eps, int criterion,
+                               double criterion_param, int group_mean, long long seq_len, double priority_mix,
+                               float* loss, float* td_error_per_sample, float* dcrit_saved, float* target_out,
+                               float* grad_q_unit, float* priority_out, float* workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (S <= 0 || G < 1 || N < 1 || nstep < 1 || !q || !next_n_q || !action || !next_n_action || !reward || !done ||
+        !loss || !td_error_per_sample || !dcrit_saved || !workspace)
         return B200RL_ERR_ARG;
     if (criterion < 0 || criterion > 3) return B200RL_ERR_ARG;
+    if (seq_len < 0 || (seq_len > 0 && (S % seq_len != 0 || cum_reward)) || (priority_out && seq_len <= 0) ||
+        (priority_out && (G != 1 || group_mean)))
+        return B200RL_ERR_ARG;
     QntdArgs a{};
     a.q = q; a.next_q = next_n_q; a.action = action; a.next_action = next_n_action; a.reward = reward; a.done = done;
     a.weight = weight; a.value_gamma = value_gamma; a.value_gamma_stride = value_gamma_stride;
-    a.gamma_ps = gamma_per_sample; a.B = B; a.N = (int)N; a.nstep = nstep; a.gamma = (float)gamma;
+    a.gamma_ps = gamma_per_sample; a.S = S; a.Bcol = seq_len > 0 ? S / seq_len : S; a.G = (int)G; a.N = (int)N;
+    a.nstep = nstep; a.gamma = (float)gamma;
     a.gamma_pow_n = (float)pow(gamma, (double)nstep);  // python's `gamma ** nstep` (libm pow in double), then fp32
     a.cum_reward = cum_reward; a.rescale = rescale; a.eps = (float)rescale_eps;
     a.four_eps = (float)(4.0 * rescale_eps); a.two_eps = (float)(2.0 * rescale_eps);
-    a.criterion = criterion; a.crit_param = (float)criterion_param;
-    a.loss = loss; a.td_err = td_error_per_sample; a.dq = dq_saved; a.target = target_out;
+    a.criterion = criterion; a.crit_param = (float)criterion_param; a.group_mean = group_mean;
+    a.loss_div = qntd_loss_div(S, G, seq_len);
+    a.prio_max_w = (float)priority_mix; a.prio_mean_w = (float)(1.0 - priority_mix);
+    a.prio_div = (float)((double)seq_len + 1e-8);
+    a.loss = loss; a.td_err = td_error_per_sample; a.dcrit = dcrit_saved; a.target = target_out;
+    a.grad_unit = grad_q_unit; a.priority = priority_out;
     constexpr int NT = 128;
-    const int grid = div_up(B, NT);
+    const int grid = div_up(S, NT);
     if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
     (void)launch_k(qntd_fwd_kernel<NT>, grid, NT, 0, (cudaStream_t)stream, a, workspace);
     return (int)cudaGetLastError();
 }
 
-extern "C" int b200rl_qntd_bwd(const float* dq_saved, const long long* action, const float* g_loss, long long B,
-                               long long N, float* grad_q, void* stream) {
-    if (B <= 0 || N < 1 || !dq_saved || !action || !grad_q) return B200RL_ERR_ARG;
-    const int grid = div_up(B * N, 256);
-    (void)launch_k(qntd_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dq_saved, action, g_loss, B, (int)N, grad_q);
+extern "C" int b200rl_qntd_bwd(const float* dcrit_saved, const float* weight, const long long* action,
+                               const float* g_loss, const float* g_td, long long S, long long G, long long N,
+                               int group_mean, long long seq_len, int skip_if_unit, float* grad_q, void* stream) {
+    if (S <= 0 || G < 1 || N < 1 || !dcrit_saved || !action || !grad_q) return B200RL_ERR_ARG;
+    const int grid = div_up(S * G * N, 256);
+    const float inv_div = (float)(1.0 / qntd_loss_div(S, G, seq_len));
+    (void)launch_k(qntd_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dcrit_saved, weight, action, g_loss, g_td, S,
+                   (int)G, (int)N, group_mean, inv_div, skip_if_unit, grad_q);
     return (int)cudaGetLastError();
 }
 
@@ -438,9 +614,9 @@ extern "C" int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, cons
                                long long value_gamma_stride, const float* support, long long B, long long A,
                                long long N, int n_atom, int nstep, double gamma, double v_min, double v_max,
                                float* loss, float* td_error_per_sample, float* proj_saved, int* bad_flag,
-                               float* workspace, size_t workspace_bytes, void* stream) {
+                               float* grad_dist_unit, float* workspace, size_t workspace_bytes, void* stream) {
     if (B <= 0 || A < 1 || N < 1 || n_atom < 2 || nstep < 1 || !dist || !next_n_dist || !act || !next_n_act ||
-        !reward || !done || !support || !loss || !td_error_per_sample || !proj_saved || !bad_flag || !workspace)
+        !reward || !done || !support || !loss || !td_error_per_sample || !proj_saved || !workspace)
         return B200RL_ERR_ARG;
     DntdArgs a{};
     a.dist = dist; a.next_dist = next_n_dist; a.act = act; a.next_act = next_n_act; a.reward = reward; a.done = done;
@@ -449,6 +625,7 @@ extern "C" int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, cons
     a.n_atom = n_atom; a.nstep = nstep; a.gamma = (float)gamma; a.gamma_pow_n = (float)pow(gamma, (double)nstep);
     a.v_min = (float)v_min; a.v_max = (float)v_max; a.delta_z = (float)((v_max - v_min) / (double)(n_atom - 1));
     a.loss = loss; a.td_err = td_error_per_sample; a.proj = proj_saved; a.bad_flag = bad_flag;
+    a.grad_unit = grad_dist_unit;
     constexpr int NT = 128;
     const int grid = div_up(a.R, NT / 32);
     if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
@@ -460,11 +637,11 @@ extern "C" int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, cons
 
 extern "C" int b200rl_dntd_bwd(const float* dist, const long long* act, const float* proj_saved, const float* weight,
                                long long weight_stride, const float* g_loss, long long R, long long N, int n_atom,
-                               float* grad_dist, void* stream) {
+                               int skip_if_unit, float* grad_dist, void* stream) {
     if (R <= 0 || N < 1 || n_atom < 2 || !dist || !act || !proj_saved || !grad_dist) return B200RL_ERR_ARG;
     const int grid = div_up(R * N * n_atom, 256);
     (void)launch_k(dntd_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dist, act, proj_saved, weight, weight_stride, g_loss, R,
-                                                            (int)N, n_atom, grad_dist);
+                   (int)N, n_atom, skip_if_unit, grad_dist);
     return (int)cudaGetLastError();
 }
 
@@ -487,6 +664,21 @@ extern "C" int b200rl_lambda_returns(const float* value, const float* reward, co
     a.gamma = (float)gamma; a.lambda = (float)lambda_; a.T = T; a.B = B; a.ret = ret;
     return upgo_mode ? launch_lambda<1, 0>(a, nullptr, (cudaStream_t)stream)
                      : launch_lambda<0, 0>(a, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b200rl_lambda_returns_bwd(const float* g_ret, const float* value, const float* reward, const float* ret,
+                                         const float* gammas, double gamma, const float* lambdas, double lambda_,
+                                         const float* done, int upgo_mode, long long T, long long B, float* grad_value,
+                                         float* grad_reward, float* grad_gammas, float* grad_lambdas, void* stream) {
+    if (T <= 0 || B <= 0 || !g_ret || !value || !grad_value) return B200RL_ERR_ARG;
+    if ((upgo_mode && !reward) || ((grad_gammas || grad_lambdas) && !ret)) return B200RL_ERR_ARG;
+    LamBwdArgs a{};
+    a.g_ret = g_ret; a.value = value; a.reward = reward; a.ret = ret; a.gammas = gammas; a.lambdas = lambdas;
+    a.done = done; a.gamma = (float)gamma; a.lambda = (float)lambda_; a.upgo_mode = upgo_mode; a.T = T; a.B = B;
+    a.g_value = grad_value; a.g_reward = grad_reward; a.g_gammas = grad_gammas; a.g_lambdas = grad_lambdas;
+    constexpr int NT = 64;
+    (void)launch_k(lambda_returns_bwd_kernel<NT>, div_up(B, NT), NT, 0, (cudaStream_t)stream, a);
+    return (int)cudaGetLastError();
 }
 
 extern "C" int b200rl_td_lambda_fwd(const float* value, const float* reward, const float* weight, double gamma,

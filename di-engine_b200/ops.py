@@ -267,46 +267,74 @@ def ppo_value_(value_new, value_old, return_, weight, clip_ratio, use_value_clip
 # q n-step TD
 # ----------------------------------------------------------------------------------------------------------------
 class QNStepTDFunction(torch.autograd.Function):
-    """Outputs: loss (differentiable w.r.t. q), td_error_per_sample and the detached target (non differentiable)."""
+    """Outputs: loss and td_error_per_sample (both differentiable w.r.t. q, like the reference's, td.py:718-719), the
+    detached n-step target and (sequence form) the priority mix (non differentiable).
+
+    ONE forward launch also writes d loss / d q for a unit upstream gradient; ``backward`` hands that buffer to autograd
+    after a verification launch that returns at once when the upstream gradient really was 1 (and no gradient arrived
+    through td_error_per_sample), and recomputes otherwise -- exact for any upstream gradient, no host sync."""
 
     @staticmethod
-    def forward(ctx, q, next_n_q, action, next_n_action, reward, done, weight, value_gamma, vg_stride, gamma_ps, nstep,
-                gamma, cum_reward, rescale, eps, criterion, crit_param):
-        B, N = q.shape
+    def forward(ctx, q, next_n_q, action, next_n_action, reward, done, weight, value_gamma, vg_stride, gamma_ps, S, G,
+                N, nstep, gamma, cum_reward, rescale, eps, criterion, crit_param, group_mean, seq_len, priority_mix,
+                want_priority):
         dev = q.device
+        R = S * G
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        td = torch.empty(B, dtype=torch.float32, device=dev)
-        dq = torch.empty(B, dtype=torch.float32, device=dev)
-        target = torch.empty(B, dtype=torch.float32, device=dev)
+        td = torch.empty(S if group_mean else R, dtype=torch.float32, device=dev)
+        dcrit = torch.empty(R, dtype=torch.float32, device=dev)
+        target = torch.empty(R, dtype=torch.float32, device=dev)
+        prio = torch.empty(S // seq_len, dtype=torch.float32, device=dev) if want_priority else None
+        grad_unit = torch.empty(R, N, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
         with torch.cuda.device(dev):
             ws = workspace(dev)
             rc = lib().b200rl_qntd_fwd(
                 ptr(q), ptr(next_n_q), ptr(action), ptr(next_n_action), ptr(reward), ptr(done), ptr(weight),
-                ptr(value_gamma), vg_stride, ptr(gamma_ps), B, N, nstep, gamma, cum_reward, rescale, eps, criterion,
-                crit_param, ptr(loss), ptr(td), ptr(dq), ptr(target), ptr(ws), ws.numel() * 4, stream_ptr()
+                ptr(value_gamma), vg_stride, ptr(gamma_ps), S, G, N, nstep, gamma, cum_reward, rescale, eps, criterion,
+                crit_param, group_mean, seq_len, priority_mix, ptr(loss), ptr(td), ptr(dcrit), ptr(target),
+                ptr(grad_unit), ptr(prio), ptr(ws), ws.numel() * 4, stream_ptr()
             )
         _lib.check(rc, 'b200rl_qntd_fwd')
-        ctx.save_for_backward(dq, action)
-        ctx.shape = (B, N)
-        ctx.mark_non_differentiable(td, target)
-        return loss, td, target
+        ctx.save_for_backward(dcrit, action, weight)
+        ctx.cfg = (S, G, N, group_mean, seq_len)
+        ctx.q_shape = q.shape
+        ctx.spec = grad_unit
+        ctx.set_materialize_grads(False)
+        if prio is None:
+            prio = torch.empty(0, dtype=torch.float32, device=dev)
+        ctx.mark_non_differentiable(target, prio)
+        return loss, td, target, prio
 
     @staticmethod
-    def backward(ctx, g_loss, _g_td, _g_target):
-        dq, action = ctx.saved_tensors
-        B, N = ctx.shape
-        grad_q = torch.empty(B, N, dtype=torch.float32, device=dq.device)
+    def backward(ctx, g_loss, g_td, _g_target, _g_prio):
+        if g_loss is None and g_td is None:
+            return (None, ) * 24
+        dcrit, action, weight = ctx.saved_tensors
+        S, G, N, group_mean, seq_len = ctx.cfg
         keep, pg = _g(g_loss)
-        with torch.cuda.device(dq.device):
-            rc = lib().b200rl_qntd_bwd(ptr(dq), ptr(action), pg, B, N, ptr(grad_q), stream_ptr())
+        keep_td, ptd = None, None
+        if g_td is not None:
+            keep_td = f32c(g_td)
+            ptd = keep_td.data_ptr()
+        grad_q, skip = ctx.spec, 0
+        ctx.spec = None  # sole owner now: autograd can adopt the buffer as .grad instead of cloning it
+        if grad_q is not None and g_td is None:
+            skip = 1
+        else:
+            grad_q = torch.empty(S * G, N, dtype=torch.float32, device=dcrit.device)
+        with torch.cuda.device(dcrit.device):
+            rc = lib().b200rl_qntd_bwd(ptr(dcrit), ptr(weight), ptr(action), pg, ptd, S, G, N, group_mean, seq_len, skip,
+                                       ptr(grad_q), stream_ptr())
         _lib.check(rc, 'b200rl_qntd_bwd')
-        return (grad_q, ) + (None, ) * 16
+        return (grad_q.view(ctx.q_shape), ) + (None, ) * 23
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # distributional n-step TD (C51)
 # ----------------------------------------------------------------------------------------------------------------
 class DistNStepTDFunction(torch.autograd.Function):
+    """loss (differentiable w.r.t. dist) and the unweighted per-sample error; the forward launch also writes the gradient for
+    a unit upstream gradient (verified on the device by the backward launch, as QNStepTDFunction)."""
 
     @staticmethod
     def forward(ctx, dist, next_n_dist, act, next_n_act, reward, done, weight, w_stride, value_gamma, vg_stride,
@@ -316,28 +344,36 @@ class DistNStepTDFunction(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=dev)
         td = torch.empty(R, dtype=torch.float32, device=dev)
         proj = torch.empty(R, n_atom, dtype=torch.float32, device=dev)
+        grad_unit = torch.empty_like(dist) if ctx.needs_input_grad[0] else None
         with torch.cuda.device(dev):
             ws = workspace(dev)
             rc = lib().b200rl_dntd_fwd(
                 ptr(dist), ptr(next_n_dist), ptr(act), ptr(next_n_act), ptr(reward), ptr(done), ptr(weight), w_stride,
                 ptr(value_gamma), vg_stride, ptr(support), B, A, N, n_atom, nstep, gamma, v_min, v_max, ptr(loss),
-                ptr(td), ptr(proj), ptr(bad_flag), ptr(ws), ws.numel() * 4, stream_ptr()
+                ptr(td), ptr(proj), ptr(bad_flag), ptr(grad_unit), ptr(ws), ws.numel() * 4, stream_ptr()
             )
         _lib.check(rc, 'b200rl_dntd_fwd')
         ctx.save_for_backward(dist, act, proj, weight)
         ctx.cfg = (R, N, n_atom, w_stride)
+        ctx.spec = grad_unit
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(td)
         return loss, td
 
     @staticmethod
     def backward(ctx, g_loss, _g_td):
+        if g_loss is None:
+            return (None, ) * 20
         dist, act, proj, weight = ctx.saved_tensors
         R, N, n_atom, w_stride = ctx.cfg
-        grad = torch.empty_like(dist)
         keep, pg = _g(g_loss)
+        grad, skip = ctx.spec, 1
+        ctx.spec = None
+        if grad is None:  # a repeated backward: the first call's buffer may now belong to .grad
+            grad, skip = torch.empty_like(dist), 0
         with torch.cuda.device(dist.device):
             rc = lib().b200rl_dntd_bwd(
-                ptr(dist), ptr(act), ptr(proj), ptr(weight), w_stride, pg, R, N, n_atom, ptr(grad), stream_ptr()
+                ptr(dist), ptr(act), ptr(proj), ptr(weight), w_stride, pg, R, N, n_atom, skip, ptr(grad), stream_ptr()
             )
         _lib.check(rc, 'b200rl_dntd_bwd')
         return (grad, ) + (None, ) * 19
@@ -356,6 +392,64 @@ def lambda_returns_(value, reward, gammas, gamma, lambdas, lambda_, done, upgo_m
         )
     _lib.check(rc, 'b200rl_lambda_returns')
     return ret
+
+
+class LambdaReturnsFunction(torch.autograd.Function):
+    """generalized_lambda_returns / upgo_returns with the reference's differentiability (td.py:1574-1651 is plain torch
+    arithmetic): gradients reach bootstrap_values, rewards and -- when they are tensors that require grad -- gammas and
+    lambda_.  Backward is the transposed scan (csrc/td.cu: lambda_returns_bwd_kernel), one launch."""
+
+    @staticmethod
+    def forward(ctx, value, reward, gammas, lambdas, done, gamma, lambda_, upgo_mode):
+        ret = lambda_returns_(value, reward, gammas, gamma, lambdas, lambda_, done, upgo_mode)
+        ctx.save_for_backward(value, reward, gammas, lambdas, done, ret)
+        ctx.scal = (float(gamma), float(lambda_), 1 if upgo_mode else 0)
+        return ret
+
+    @staticmethod
+    def backward(ctx, g_ret):
+        value, reward, gammas, lambdas, done, ret = ctx.saved_tensors
+        gamma, lambda_, upgo = ctx.scal
+        T, B = reward.shape
+        g = f32c(g_ret)
+        need = ctx.needs_input_grad
+        gv = torch.empty_like(value)
+        gr = torch.empty_like(reward) if need[1] else None
+        gg = torch.empty_like(reward) if (need[2] and gammas is not None) else None
+        gl = torch.empty_like(reward) if (need[3] and lambdas is not None) else None
+        with torch.cuda.device(value.device):
+            rc = lib().b200rl_lambda_returns_bwd(
+                ptr(g), ptr(value), ptr(reward), ptr(ret), ptr(gammas), gamma, ptr(lambdas), lambda_, ptr(done), upgo,
+                T, B, ptr(gv), ptr(gr), ptr(gg), ptr(gl), stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_lambda_returns_bwd')
+        return gv if need[0] else None, gr, gg, gl, None, None, None, None
+
+
+class TBCrossEntropyFunction(torch.autograd.Function):
+    """tb_cross_entropy (upgo.py:7-43): ce (TB) = sum_k mask_k * log softmax(logit)[label]; gradient reaches ``logit``."""
+
+    @staticmethod
+    def forward(ctx, logit, label, mask, TB, K, N):
+        ce = torch.empty(TB, dtype=torch.float32, device=logit.device)
+        with torch.cuda.device(logit.device):
+            rc = lib().b200rl_tb_cross_entropy_fwd(ptr(logit), ptr(label), ptr(mask), TB, K, N, ptr(ce), stream_ptr())
+        _lib.check(rc, 'b200rl_tb_cross_entropy_fwd')
+        ctx.save_for_backward(logit, label, mask)
+        ctx.cfg = (TB, K, N)
+        return ce
+
+    @staticmethod
+    def backward(ctx, g_ce):
+        logit, label, mask = ctx.saved_tensors
+        TB, K, N = ctx.cfg
+        g = f32c(g_ce).reshape(-1)
+        grad = torch.empty_like(logit)
+        with torch.cuda.device(logit.device):
+            rc = lib().b200rl_tb_cross_entropy_bwd(ptr(logit), ptr(label), ptr(mask), ptr(g), TB, K, N, ptr(grad),
+                                                   stream_ptr())
+        _lib.check(rc, 'b200rl_tb_cross_entropy_bwd')
+        return grad, None, None, None, None, None
 
 
 class _ScaleSaved(torch.autograd.Function):

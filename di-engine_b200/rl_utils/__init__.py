@@ -4,11 +4,12 @@ from .fused import gae_ppo_error
 from .gae import gae, gae_data, shape_fn_gae
 from .ppo import (ppo_data, ppo_error, ppo_info, ppo_loss, ppo_policy_data, ppo_policy_error, ppo_policy_loss,
                   ppo_value_data, ppo_value_error, shape_fn_ppo)
-from .td import (dist_nstep_td_data, dist_nstep_td_error, generalized_lambda_returns, q_1step_td_data, q_1step_td_error,
-                 q_nstep_td_data, q_nstep_td_error, q_nstep_td_error_with_rescale, shape_fn_dntd, shape_fn_qntd,
-                 shape_fn_qntd_rescale, shape_fn_td_lambda, td_lambda_data, td_lambda_error, v_1step_td_data,
-                 v_1step_td_error, v_nstep_td_data, v_nstep_td_error)
-from .upgo import upgo_loss, upgo_returns
+from .td import (bdq_nstep_td_error, dist_1step_td_data, dist_1step_td_error, dist_nstep_td_data, dist_nstep_td_error,
+                 generalized_lambda_returns, q_1step_td_data, q_1step_td_error, q_nstep_td_data, q_nstep_td_error,
+                 q_nstep_td_error_sequence, q_nstep_td_error_with_rescale, q_nstep_td_seq_data, shape_fn_dntd,
+                 shape_fn_qntd, shape_fn_qntd_rescale, shape_fn_td_lambda, td_lambda_data, td_lambda_error,
+                 v_1step_td_data, v_1step_td_error, v_nstep_td_data, v_nstep_td_error)
+from .upgo import tb_cross_entropy, upgo_loss, upgo_returns
 from .value_rescale import value_inv_transform, value_transform
 from .vtrace import shape_fn_vtrace_discrete_action, vtrace_data, vtrace_error_discrete_action, vtrace_loss
 
@@ -16,10 +17,11 @@ HOT_PATH_FUNCTIONS = [
     'gae', 'ppo_error', 'q_nstep_td_error', 'q_nstep_td_error_with_rescale', 'dist_nstep_td_error', 'td_lambda_error',
     'generalized_lambda_returns', 'upgo_loss', 'vtrace_error_discrete_action',
     # siblings on the same kernels
-    'q_1step_td_error', 'v_1step_td_error', 'v_nstep_td_error', 'ppo_policy_error', 'ppo_value_error'
+    'q_1step_td_error', 'v_1step_td_error', 'v_nstep_td_error', 'ppo_policy_error', 'ppo_value_error',
+    'dist_1step_td_error', 'bdq_nstep_td_error', 'upgo_returns', 'tb_cross_entropy'
 ]
 HOT_PATH_TYPES = [
     'gae_data', 'ppo_data', 'ppo_loss', 'ppo_info', 'q_nstep_td_data', 'dist_nstep_td_data', 'td_lambda_data',
     'vtrace_data', 'vtrace_loss', 'q_1step_td_data', 'v_1step_td_data', 'v_nstep_td_data',
-    'ppo_policy_data', 'ppo_policy_loss', 'ppo_value_data'
+    'ppo_policy_data', 'ppo_policy_loss', 'ppo_value_data', 'dist_1step_td_data'
 ]

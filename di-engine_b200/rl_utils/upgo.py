@@ -1,20 +1,54 @@
-"""``upgo_loss`` / ``upgo_returns`` with the signatures of ding/rl_utils/upgo.py:46,77 -- csrc/td.cu + csrc/pg.cu."""
+"""``upgo_loss`` / ``upgo_returns`` / ``tb_cross_entropy`` with the signatures of ding/rl_utils/upgo.py:7,46,77 -- csrc/td.cu +
+csrc/pg.cu."""
 import torch
 
 from .. import ops
+
+
+def tb_cross_entropy(logit: torch.Tensor, label: torch.Tensor, mask=None) -> torch.Tensor:
+    """
+    Time-batch cross entropy "with the sign of a log-probability", drop-in for ding/rl_utils/upgo.py:7-43:
+    ``-F.cross_entropy(logit, label)`` per (t, b); logit (T, B, N) with label (T, B), or (T, B, N2, N) with label / mask
+    (T, B, N2), the masked per-entry values summed over N2 (the mask is ignored for 3-D logits, as in the reference).
+    Returns (T, B), differentiable w.r.t. ``logit``.
+    """
+    assert (len(label.shape) >= 2)  # upgo.py:23
+    T, B = label.shape[:2]
+    K = 1
+    if len(label.shape) > 2:
+        assert len(label.shape) == 3  # upgo.py:27
+        K = label.shape[2]
+    N = logit.shape[-1]
+    dev = ops.compute_device(logit)
+    host_out = not logit.is_cuda
+    if logit.numel() != T * B * K * N:
+        raise ValueError("logit %s does not match label %s" % (tuple(logit.shape), tuple(label.shape)))
+    z = ops.f32c(ops.to_device(logit, dev), 'logit')
+    lab = ops.i64c(ops.to_device(label, dev))
+    m = None
+    if mask is not None and K > 1:
+        m = ops.f32c(ops.to_device(mask.detach(), dev), 'mask')
+    ce = ops.TBCrossEntropyFunction.apply(z, lab, m, T * B, K, N).reshape(T, B)
+    return ce.cpu() if host_out else ce
 
 
 def upgo_returns(rewards: torch.Tensor, bootstrap_values: torch.Tensor) -> torch.Tensor:
     """
     UPGO return targets (ding/rl_utils/upgo.py:46-68): a lambda-return with gamma = 1 whose trace continues
     (lambda_t = 1) while r_{t+1} + V_{t+2} >= V_{t+1}.  rewards (T, B), bootstrap_values (T+1, B) -> (T, B).
-    The comparison and the recurrence are evaluated in one kernel, bit-exact with the reference.
+    The comparison and the recurrence are evaluated in one kernel, bit-exact with the reference; as in the reference the
+    result is differentiable w.r.t. both inputs (no gradient flows through the comparison).
     """
     dev = ops.compute_device(rewards, bootstrap_values)
     host_out = not rewards.is_cuda
-    v = ops.f32c(ops.to_device(bootstrap_values.detach(), dev), 'bootstrap_values')
-    r = ops.f32c(ops.to_device(rewards.detach(), dev), 'rewards')
-    ret = ops.lambda_returns_(v, r, None, 1.0, None, 1.0, None, True)
+    grad_on = torch.is_grad_enabled()
+    rg_v, rg_r = bootstrap_values.requires_grad and grad_on, rewards.requires_grad and grad_on
+    v = ops.f32c(ops.to_device(bootstrap_values if rg_v else bootstrap_values.detach(), dev), 'bootstrap_values')
+    r = ops.f32c(ops.to_device(rewards if rg_r else rewards.detach(), dev), 'rewards')
+    if rg_v or rg_r:
+        ret = ops.LambdaReturnsFunction.apply(v, r, None, None, None, 1.0, 1.0, True)
+    else:
+        ret = ops.lambda_returns_(v, r, None, 1.0, None, 1.0, None, True)
     return ret.cpu() if host_out else ret
 
 

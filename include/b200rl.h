@@ -92,37 +92,51 @@ B200RL_API int b200rl_ppo_fused_supported(const float* logit_new, const float* l
                                const float* grad_logit_new, long long G, long long N);
 
 /* ---- q_nstep_td_error / q_nstep_td_error_with_rescale: ding/rl_utils/td.py:649-719, :810-867, nstep_return :230-286
- * q, next_n_q: (B, N); action, next_n_action: (B) int64; reward: (nstep, B), or (B) when cum_reward; done: (B);
- * weight nullable (B); value_gamma nullable, stride 0 (0-dim tensor / python scalar) or 1 ((B) tensor);
- * gamma_per_sample nullable (B): the list-gamma form used by NGU (td.py:275-282).
+ *      and, on the same kernel: bdq_nstep_td_error (:722-789), q_1step / v_1step / v_nstep (:26-72, :529-617) and the
+ *      per-step loop of the recurrent Q-learners (ding/policy/r2d2.py:347-369, ngu.py:343-347) as ONE call.
+ * S samples with G rows each (G = 1; the agent dim of the multi-agent branch td.py:700-705; the branches of BDQ):
+ * q, next_n_q: (S, G, N); action, next_n_action: (S, G) int64; reward: (nstep, S), or (S) when cum_reward; done: (S);
+ * weight nullable (S); value_gamma nullable, stride 0 (0-dim tensor / python scalar) or 1 ((S) tensor);
+ * gamma_per_sample nullable: the list-gamma form used by NGU (td.py:275-282).
  * rescale != 0 applies value_inv_transform / value_transform (value_rescale.py:4-34) with eps = rescale_eps.
  * criterion: 0 MSELoss, 1 L1Loss, 2 SmoothL1Loss(beta=criterion_param), 3 HuberLoss(delta=criterion_param), all
- * reduction='none'.  Writes loss (1), td_error_per_sample (B), dq_saved (B) for the backward call and, when
- * target_out is not null, the detached n-step target (B) for callers that apply a criterion of their own. */
+ * reduction='none'.  group_mean != 0: td_error_per_sample is (S), the mean over the G rows (td.py:788); else (S, G).
+ * seq_len = T > 0 selects the sequence form: S = T*B samples in time-major order, reward (T, nstep, B), gamma_per_sample
+ * (B); loss = sum_t mean_b(w*td) / (T + 1e-8) and, when priority_out (B) is given, priority_out[b] = priority_mix *
+ * max_t|td| + (1 - priority_mix) * sum_t|td| / (T + 1e-8)  (r2d2.py:364-369).
+ * ONE launch writes loss (1), td_error_per_sample, dcrit_saved (S, G) for the backward call, the detached n-step target
+ * (target_out, nullable) and -- grad_q_unit (S, G, N), nullable -- d loss / d q for a unit upstream gradient.
+ * b200rl_qntd_bwd: grad_q = g_loss * dloss/dq + dtd/dq^T g_td (both upstream gradients nullable = 0; g_td shaped like
+ * td_error_per_sample).  skip_if_unit != 0: grad_q already holds grad_q_unit; the launch verifies on the device that
+ * *g_loss == 1 (and g_td is null) and returns at once, else it recomputes -- exact for any upstream gradient, no host sync. */
 B200RL_API int b200rl_qntd_fwd(const float* q, const float* next_n_q, const long long* action, const long long* next_n_action,
                     const float* reward, const float* done, const float* weight, const float* value_gamma,
-                    long long value_gamma_stride, const float* gamma_per_sample, long long B, long long N, int nstep,
-                    double gamma, int cum_reward, int rescale, double rescale_eps, int criterion,
-                    double criterion_param, float* loss, float* td_error_per_sample, float* dq_saved,
-                    float* target_out, float* workspace, size_t workspace_bytes, void* stream);
-B200RL_API int b200rl_qntd_bwd(const float* dq_saved, const long long* action, const float* g_loss, long long B, long long N,
-                    float* grad_q, void* stream);
+                    long long value_gamma_stride, const float* gamma_per_sample, long long S, long long G, long long N,
+                    int nstep, double gamma, int cum_reward, int rescale, double rescale_eps, int criterion,
+                    double criterion_param, int group_mean, long long seq_len, double priority_mix, float* loss,
+                    float* td_error_per_sample, float* dcrit_saved, float* target_out, float* grad_q_unit,
+                    float* priority_out, float* workspace, size_t workspace_bytes, void* stream);
+B200RL_API int b200rl_qntd_bwd(const float* dcrit_saved, const float* weight, const long long* action, const float* g_loss,
+                    const float* g_td, long long S, long long G, long long N, int group_mean, long long seq_len,
+                    int skip_if_unit, float* grad_q, void* stream);
 
-/* ---- dist_nstep_td_error (C51): ding/rl_utils/td.py:413-523 ----------------------------------------------------
+/* ---- dist_nstep_td_error (C51): ding/rl_utils/td.py:413-523; dist_1step_td_error (:294-383) is its nstep = 1 case ---
  * dist, next_n_dist: (B*A, N, n_atom); act, next_n_act: (B*A) int64; reward: (nstep, B); done: (B);
  * weight nullable with stride 0 / 1 over the B*A rows; value_gamma nullable with stride 0 / 1 over B;
  * support: (n_atom) = torch.linspace(v_min, v_max, n_atom) as computed by the caller's torch (td.py:457).
- * bad_flag (int, caller-zeroed) is set when a selected dist entry is <= 0 (the reference's assert, td.py:513).
- * Writes loss (1), td_error_per_sample (B*A, unweighted, td.py:519) and proj_saved (B*A, n_atom). */
+ * bad_flag (int, caller-zeroed, nullable) is set when a selected dist entry is <= 0 (the reference's assert, td.py:513).
+ * ONE launch writes loss (1), td_error_per_sample (B*A, unweighted, td.py:519), proj_saved (B*A, n_atom) and --
+ * grad_dist_unit (B*A, N, n_atom), nullable -- d loss / d dist for a unit upstream gradient.
+ * b200rl_dntd_bwd with skip_if_unit != 0: grad_dist already holds grad_dist_unit; no-op when *g_loss == 1, else recomputed. */
 B200RL_API int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, const long long* act, const long long* next_n_act,
                     const float* reward, const float* done, const float* weight, long long weight_stride,
                     const float* value_gamma, long long value_gamma_stride, const float* support, long long B,
                     long long A, long long N, int n_atom, int nstep, double gamma, double v_min, double v_max,
-                    float* loss, float* td_error_per_sample, float* proj_saved, int* bad_flag, float* workspace,
-                    size_t workspace_bytes, void* stream);
+                    float* loss, float* td_error_per_sample, float* proj_saved, int* bad_flag, float* grad_dist_unit,
+                    float* workspace, size_t workspace_bytes, void* stream);
 B200RL_API int b200rl_dntd_bwd(const float* dist, const long long* act, const float* proj_saved, const float* weight,
                     long long weight_stride, const float* g_loss, long long R, long long N, int n_atom,
-                    float* grad_dist, void* stream);
+                    int skip_if_unit, float* grad_dist, void* stream);
 
 /* ---- generalized_lambda_returns / upgo_returns: ding/rl_utils/td.py:1574-1651, upgo.py:46-68 -------------------
  * value: (T+1, B); reward: (T, B); gammas / lambdas nullable (T, B) tensors overriding the scalars; done nullable.
@@ -130,6 +144,14 @@ B200RL_API int b200rl_dntd_bwd(const float* dist, const long long* act, const fl
 B200RL_API int b200rl_lambda_returns(const float* value, const float* reward, const float* gammas, double gamma,
                           const float* lambdas, double lambda_, const float* done, int upgo_mode, long long T,
                           long long B, float* ret, void* stream);
+/* Backward of the lambda-return (the reference function is differentiable; MBSAC / Dreamer back-propagate through it,
+ * ding/policy/mbpolicy/mbsac.py:137, mbpolicy/utils.py:75): g_ret (T, B) upstream -> grad_value (T+1, B), and, each
+ * nullable, grad_reward (T, B), grad_gammas / grad_lambdas (T, B; need the forward result `ret`).  upgo_mode as above
+ * (lambda is recomputed from reward / value; no gradient flows through the comparison). */
+B200RL_API int b200rl_lambda_returns_bwd(const float* g_ret, const float* value, const float* reward, const float* ret,
+                              const float* gammas, double gamma, const float* lambdas, double lambda_,
+                              const float* done, int upgo_mode, long long T, long long B, float* grad_value,
+                              float* grad_reward, float* grad_gammas, float* grad_lambdas, void* stream);
 /* ---- td_lambda_error: ding/rl_utils/td.py:1539-1571 (scan + loss head fused) -----------------------------------
  * writes loss (1) and dvalue_saved (T+1, B) = d loss / d value for unit upstream gradient */
 B200RL_API int b200rl_td_lambda_fwd(const float* value, const float* reward, const float* weight, double gamma, double lambda_,
@@ -146,6 +168,13 @@ B200RL_API int b200rl_upgo_head_fwd(const float* logit, const long long* action,
                          float* adv_saved, float* workspace, size_t workspace_bytes, void* stream);
 B200RL_API int b200rl_upgo_head_bwd(const float* logit, const long long* action, const float* mask, const float* adv_saved,
                          const float* g_loss, long long TB, long long K, long long N, float* grad_logit, void* stream);
+
+/* tb_cross_entropy alone (upgo.py:7-43): ce (TB) = sum_k mask_k * log softmax(logit)[action]; backward for an upstream
+ * gradient g_ce (TB). */
+B200RL_API int b200rl_tb_cross_entropy_fwd(const float* logit, const long long* action, const float* mask, long long TB,
+                                long long K, long long N, float* ce, void* stream);
+B200RL_API int b200rl_tb_cross_entropy_bwd(const float* logit, const long long* action, const float* mask, const float* g_ce,
+                                long long TB, long long K, long long N, float* grad_logit, void* stream);
 
 /* ---- vtrace_error_discrete_action: ding/rl_utils/vtrace.py:72-136 (returns :9-29, advantage :32-45, isw.py:55-58)
  * target_output, behaviour_output: (T*B, N); action: (T*B) int64; value: (T+1, B); reward, weight(nullable): (T, B).

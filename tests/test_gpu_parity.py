@@ -519,7 +519,7 @@ def test_packed_batch_round_trip_and_use():
 
 def test_p2p_allreduce_kernel_single_rank_degenerate():
     """world = 1: the mailbox exchange must reproduce the local values (mean over one rank), across many sequence
-    numbers and under CUDA-graph replay.  (Two and more ranks: tools/test_p2p.py under torchrun.)"""
+    numbers and under CUDA-graph replay.  (Two and more ranks: tests/test_p2p_gpu.py, tools/p2p_check.py under torchrun.)"""
     from di_engine_b200 import ops
     L = ops.lib()
     mailbox = torch.zeros(L.b200rl_p2p_mailbox_floats(1), device=DEV)
