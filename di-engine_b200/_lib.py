@@ -31,7 +31,7 @@ PROTOTYPES = {
                         c_size_t, P],
     "b200rl_qntd_bwd": [P, P, P, P, P, LL, LL, LL, I, LL, I, P, P],
     "b200rl_dntd_fwd": [P, P, P, P, P, P, P, LL, P, LL, P, LL, LL, LL, I, I, D, D, D, P, P, P, P, P, P, c_size_t, P],
-    "b200rl_dntd_bwd": [P, P, P, P, LL, P, LL, LL, I, I, P, P],
+    "b200rl_dntd_bwd": [P, P, P, P, LL, P, P, LL, LL, I, I, P, P],
     "b200rl_lambda_returns": [P, P, P, D, P, D, P, I, LL, LL, P, P],
     "b200rl_lambda_returns_bwd": [P, P, P, P, P, D, P, D, P, I, LL, LL, P, P, P, P, P],
     "b200rl_tb_cross_entropy_fwd": [P, P, P, LL, LL, LL, P, P],

@@ -280,11 +280,12 @@ __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
 
 __global__ void dntd_bwd_kernel(const float* __restrict__ dist, const long long* __restrict__ act,
                                 const float* __restrict__ proj, const float* __restrict__ weight,
-                                long long weight_stride, const float* __restrict__ g_loss, long long R, int N,
-                                int n_atom, int skip_if_unit, float* __restrict__ grad_dist) {
+                                long long weight_stride, const float* __restrict__ g_loss,
+                                const float* __restrict__ g_td, long long R, int N, int n_atom, int skip_if_unit,
+                                float* __restrict__ grad_dist) {
     pdl_prologue();
     // skip_if_unit: the forward launch already wrote grad_dist for a unit upstream gradient -- verify and leave
-    if (skip_if_unit && g_loss && *g_loss == 1.f) return;
+    if (skip_if_unit && !g_td && g_loss && *g_loss == 1.f) return;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_row = (long long)N * n_atom;
     if (i >= R * per_row) return;
@@ -295,7 +296,9 @@ __global__ void dntd_bwd_kernel(const float* __restrict__ dist, const long long*
     if (n == (int)act[r]) {
         const float g = g_loss ? *g_loss : 0.f;
         const float w = weight ? weight[r * weight_stride] : 1.f;
-        out = -g * w / (float)R * proj[r * n_atom + j] / dist[i];
+        float c = g * w / (float)R;
+        if (g_td) c += g_td[r];  // the unweighted per-sample error carries gradient too (td.py:519)
+        out = -c * proj[r * n_atom + j] / dist[i];
     }
     grad_dist[i] = out;
 }
@@ -636,12 +639,12 @@ extern "C" int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, cons
 }
 
 extern "C" int b200rl_dntd_bwd(const float* dist, const long long* act, const float* proj_saved, const float* weight,
-                               long long weight_stride, const float* g_loss, long long R, long long N, int n_atom,
-                               int skip_if_unit, float* grad_dist, void* stream) {
+                               long long weight_stride, const float* g_loss, const float* g_td, long long R,
+                               long long N, int n_atom, int skip_if_unit, float* grad_dist, void* stream) {
     if (R <= 0 || N < 1 || n_atom < 2 || !dist || !act || !proj_saved || !grad_dist) return B200RL_ERR_ARG;
     const int grid = div_up(R * N * n_atom, 256);
-    (void)launch_k(dntd_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dist, act, proj_saved, weight, weight_stride, g_loss, R,
-                   (int)N, n_atom, skip_if_unit, grad_dist);
+    (void)launch_k(dntd_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dist, act, proj_saved, weight, weight_stride, g_loss, g_td,
+                   R, (int)N, n_atom, skip_if_unit, grad_dist);
     return (int)cudaGetLastError();
 }
 

@@ -357,23 +357,24 @@ class DistNStepTDFunction(torch.autograd.Function):
         ctx.cfg = (R, N, n_atom, w_stride)
         ctx.spec = grad_unit
         ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(td)
         return loss, td
 
     @staticmethod
-    def backward(ctx, g_loss, _g_td):
-        if g_loss is None:
+    def backward(ctx, g_loss, g_td):
+        if g_loss is None and g_td is None:
             return (None, ) * 20
         dist, act, proj, weight = ctx.saved_tensors
         R, N, n_atom, w_stride = ctx.cfg
         keep, pg = _g(g_loss)
+        keep_td = f32c(g_td) if g_td is not None else None
         grad, skip = ctx.spec, 1
         ctx.spec = None
-        if grad is None:  # a repeated backward: the first call's buffer may now belong to .grad
+        if grad is None or g_td is not None:  # a repeated backward (the first buffer may belong to .grad) / per-sample path
             grad, skip = torch.empty_like(dist), 0
         with torch.cuda.device(dist.device):
             rc = lib().b200rl_dntd_bwd(
-                ptr(dist), ptr(act), ptr(proj), ptr(weight), w_stride, pg, R, N, n_atom, skip, ptr(grad), stream_ptr()
+                ptr(dist), ptr(act), ptr(proj), ptr(weight), w_stride, pg, ptr(keep_td), R, N, n_atom, skip, ptr(grad),
+                stream_ptr()
             )
         _lib.check(rc, 'b200rl_dntd_bwd')
         return (grad, ) + (None, ) * 19

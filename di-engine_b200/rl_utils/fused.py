@@ -51,6 +51,11 @@ def gae_ppo_error(
     N = logit_new.shape[-1]
     if logit_new.numel() != T * B * N or value_new.numel() != T * B or action.numel() != T * B:
         return fallback()
+    for name, t_, want in (('logit_old', logit_old, T * B * N), ('logit_pretrained', logit_pretrained, T * B * N),
+                           ('value_old', value_old, T * B), ('return_', return_, T * B), ('next_value', next_value, T * B),
+                           ('done', done, T * B), ('traj_flag', traj_flag, T * B)):
+        if t_ is not None and t_.numel() != want:
+            raise ValueError("gae_ppo_error: %s %s does not cover the (T=%d, B=%d) batch" % (name, tuple(t_.shape), T, B))
     f32 = ops.f32c
     v, r = f32(value.detach(), 'value'), f32(reward.detach(), 'reward')
     nv_src = next_value.detach()

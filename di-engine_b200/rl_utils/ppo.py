@@ -70,6 +70,12 @@ def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind)
     G = rows // S
     if G > 1 and not (logit_new.dim() == adv.dim() + 2 and logit_new.shape[adv.dim()] == G):
         raise ValueError("ppo_error: multi-agent logits must be (B, A, N) against (B,) adv")
+    # raw pointers go to the kernels: every operand must cover exactly the rows / samples the sizes above promise
+    for name, t_, want in (('logit_old', logit_old, rows * N), ('logit_pretrained', logit_pretrained, rows * N),
+                           ('value_new', value_new, S), ('value_old', value_old, S), ('return_', return_, S)):
+        if t_ is not None and t_.numel() != want:
+            raise ValueError("ppo_error: %s %s does not match logit_new %s / adv %s" %
+                             (name, tuple(t_.shape), tuple(logit_new.shape), tuple(adv.shape)))
 
     def stage(t, name):
         return ops.f32c(ops.to_device(t, dev), name) if t is not None else None

@@ -127,7 +127,8 @@ B200RL_API int b200rl_qntd_bwd(const float* dcrit_saved, const float* weight, co
  * bad_flag (int, caller-zeroed, nullable) is set when a selected dist entry is <= 0 (the reference's assert, td.py:513).
  * ONE launch writes loss (1), td_error_per_sample (B*A, unweighted, td.py:519), proj_saved (B*A, n_atom) and --
  * grad_dist_unit (B*A, N, n_atom), nullable -- d loss / d dist for a unit upstream gradient.
- * b200rl_dntd_bwd with skip_if_unit != 0: grad_dist already holds grad_dist_unit; no-op when *g_loss == 1, else recomputed. */
+ * b200rl_dntd_bwd: g_loss / g_td (R) are the upstream gradients of loss / td_error_per_sample (nullable = 0).  skip_if_unit
+ * != 0: grad_dist already holds grad_dist_unit; no-op when *g_loss == 1 and g_td is null, else recomputed. */
 B200RL_API int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, const long long* act, const long long* next_n_act,
                     const float* reward, const float* done, const float* weight, long long weight_stride,
                     const float* value_gamma, long long value_gamma_stride, const float* support, long long B,
@@ -135,8 +136,8 @@ B200RL_API int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, cons
                     float* loss, float* td_error_per_sample, float* proj_saved, int* bad_flag, float* grad_dist_unit,
                     float* workspace, size_t workspace_bytes, void* stream);
 B200RL_API int b200rl_dntd_bwd(const float* dist, const long long* act, const float* proj_saved, const float* weight,
-                    long long weight_stride, const float* g_loss, long long R, long long N, int n_atom,
-                    int skip_if_unit, float* grad_dist, void* stream);
+                    long long weight_stride, const float* g_loss, const float* g_td, long long R, long long N,
+                    int n_atom, int skip_if_unit, float* grad_dist, void* stream);
 
 /* ---- generalized_lambda_returns / upgo_returns: ding/rl_utils/td.py:1574-1651, upgo.py:46-68 -------------------
  * value: (T+1, B); reward: (T, B); gammas / lambdas nullable (T, B) tensors overriding the scalars; done nullable.

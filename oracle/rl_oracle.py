@@ -269,6 +269,50 @@ def q_nstep_td_error_with_rescale(
     return (per_sample * weight).mean(), per_sample
 
 
+def bdq_nstep_td_error(q, next_n_q, action, next_n_action, reward, done, weight=None, gamma=0.99, nstep: int = 1,
+                       cum_reward: bool = False, value_gamma=None, criterion=None):
+    """td.py:722-789: branching dueling Q; q (B, D, N), action (B, D); per-sample error = mean over the D branches (:788)."""
+    if criterion is None:
+        criterion = torch.nn.MSELoss(reduction='none')
+    if weight is None:
+        weight = torch.ones_like(reward)  # td.py:771-772
+    reward = reward.unsqueeze(-1)  # td.py:773-776
+    done = done.unsqueeze(-1)
+    if value_gamma is not None:
+        value_gamma = value_gamma.unsqueeze(-1)
+    q_sa = q.gather(-1, action.unsqueeze(-1)).squeeze(-1)  # td.py:778
+    tq = next_n_q.gather(-1, next_n_action.unsqueeze(-1)).squeeze(-1)
+    if cum_reward:  # td.py:781-785
+        if value_gamma is None:
+            tq = reward + (gamma ** nstep) * tq * (1 - done)
+        else:
+            tq = reward + value_gamma * tq * (1 - done)
+    else:
+        tq = nstep_return(reward, tq, done, gamma, nstep, value_gamma)  # td.py:787
+    per_sample = criterion(q_sa, tq.detach())
+    per_sample = per_sample.mean(-1)  # td.py:788
+    return (per_sample * weight).mean(), per_sample
+
+
+def q_nstep_td_error_sequence(q, next_n_q, action, next_n_action, reward, done, weight=None, value_gamma=None,
+                              gamma=0.99, nstep: int = 1, rescale: bool = False, priority_mix: float = 0.9):
+    """The learner loop around the operator in the recurrent Q policies (ding/policy/r2d2.py:347-369; ngu.py:330-360):
+    q (T, B, N), reward (T, nstep, B), done / weight / value_gamma (T, B).  Returns (loss, priority, td (T, B))."""
+    fn = q_nstep_td_error_with_rescale if rescale else q_nstep_td_error
+    losses, errs, raw = [], [], []
+    for t in range(q.shape[0]):  # r2d2.py:347
+        l, e = fn(q[t], next_n_q[t], action[t], next_n_action[t], reward[t], done[t],
+                  None if weight is None else weight[t], gamma, nstep,
+                  value_gamma=None if value_gamma is None else value_gamma[t])
+        losses.append(l)
+        errs.append(e.abs())
+        raw.append(e)
+    loss = sum(losses) / (len(losses) + 1e-8)  # r2d2.py:364
+    prio = priority_mix * torch.max(torch.stack(errs), dim=0)[0] + (1 - priority_mix) * (
+        torch.sum(torch.stack(errs), dim=0) / (len(errs) + 1e-8))  # r2d2.py:367-369
+    return loss, prio.detach(), torch.stack(raw)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # td.py:26-72 q_1step_td_error ; td.py:529-573 v_1step_td_error ; td.py:579-617 v_nstep_td_error
 # --------------------------------------------------------------------------------------------------------------
@@ -395,6 +439,52 @@ def dist_nstep_td_error(
     return loss, per_sample
 
 
+def dist_1step_td_error(dist, next_dist, act, next_act, reward, done, weight=None, gamma: float = 0.99,
+                        v_min: float = -10., v_max: float = 10., n_atom: int = 51):
+    """td.py:294-383: C51 1-step; same projection as the n-step form with target_z = r + (1-done)*gamma*z; returns the loss
+    only; no positivity assert."""
+    assert len(reward.shape) == 1, reward.shape  # td.py:343
+    support = torch.linspace(v_min, v_max, n_atom)
+    delta_z = (v_max - v_min) / (n_atom - 1)
+    if act.dim() == 1:  # td.py:347-354
+        reward = reward.unsqueeze(-1)
+        done = done.unsqueeze(-1)
+        nrow = act.shape[0]
+        rows = torch.arange(nrow)
+        if weight is None:
+            weight = torch.ones_like(reward)
+        nd = next_dist[rows, next_act].detach()
+    else:  # td.py:355-371
+        n_b, n_a = act.shape
+        reward = reward.unsqueeze(-1).repeat(1, n_a)
+        done = done.unsqueeze(-1).repeat(1, n_a)
+        nrow = n_b * n_a
+        rows = torch.arange(nrow)
+        n_act = dist.shape[2]
+        dist = dist.reshape(nrow, n_act, -1)
+        reward = reward.reshape(nrow, -1)
+        done = done.reshape(nrow, -1)
+        next_dist = next_dist.reshape(nrow, n_act, -1)
+        next_act = next_act.reshape(nrow)
+        nd = next_dist[rows, next_act].detach().reshape(nrow, -1)
+        act = act.reshape(nrow)
+        if weight is None:
+            weight = torch.ones_like(reward)
+    tz = reward + (1 - done) * gamma * support  # td.py:372
+    tz = tz.clamp(min=v_min, max=v_max)
+    pos = (tz - v_min) / delta_z
+    lo = pos.floor().long()
+    hi = pos.ceil().long()
+    lo[(hi > 0) * (lo == hi)] -= 1
+    hi[(lo < (n_atom - 1)) * (lo == hi)] += 1
+    proj = torch.zeros_like(nd)
+    offset = torch.linspace(0, (nrow - 1) * n_atom, nrow).unsqueeze(1).expand(nrow, n_atom).long()
+    proj.view(-1).index_add_(0, (lo + offset).view(-1), (nd * (hi.float() - pos)).view(-1))
+    proj.view(-1).index_add_(0, (hi + offset).view(-1), (nd * (pos - lo.float())).view(-1))
+    log_p = torch.log(dist[rows, act])
+    return -(log_p * proj * weight).sum(-1).mean()  # td.py:382
+
+
 # --------------------------------------------------------------------------------------------------------------
 # td.py:1539-1651 td_lambda_error / generalized_lambda_returns / multistep_forward_view
 # --------------------------------------------------------------------------------------------------------------
@@ -412,6 +502,26 @@ def generalized_lambda_returns(bootstrap_values, rewards, gammas, lambda_, done=
     for t in range(rewards.size(0) - 2, -1, -1):  # td.py:1644-1649
         out[t, :] = rewards[t, :] + (1 - done[t, :]) * (trace[t, :] * out[t + 1, :] + (gammas[t, :] - trace[t, :]) * nxt[t, :])
     return out
+
+
+def lambda_returns_functional(bootstrap_values, rewards, gammas, lambda_, done=None):
+    """The same recurrence written out of place (list + stack), so that autograd can differentiate it w.r.t. EVERY operand,
+    including tensor gammas / lambdas -- the reference's in-place loop (td.py:1642-1649) supports gradients for
+    bootstrap_values and rewards only.  Checker for the product's transposed-scan backward."""
+    if not isinstance(gammas, torch.Tensor):
+        gammas = gammas * torch.ones_like(rewards)
+    if not isinstance(lambda_, torch.Tensor):
+        lambda_ = lambda_ * torch.ones_like(rewards)
+    if done is None:
+        done = torch.zeros_like(rewards)
+    nxt = bootstrap_values[1:]
+    T = rewards.shape[0]
+    rows = [None] * T
+    rows[T - 1] = rewards[T - 1] + (1 - done[T - 1]) * gammas[T - 1] * nxt[T - 1]
+    trace = gammas * lambda_
+    for t in range(T - 2, -1, -1):
+        rows[t] = rewards[t] + (1 - done[t]) * (trace[t] * rows[t + 1] + (gammas[t] - trace[t]) * nxt[t])
+    return torch.stack(rows, 0)
 
 
 def td_lambda_error(value, reward, weight=None, gamma: float = 0.9, lambda_: float = 0.8):

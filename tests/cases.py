@@ -25,6 +25,9 @@ GRAD_INPUTS = {
     'q1td': ['q'],
     'v1td': ['v'],
     'vntd': ['v'],
+    'bdq': ['q'],
+    'qseq': ['q'],
+    'd1td': ['dist'],
     'dntd': ['dist'],
     'td_lambda': ['value'],
     'upgo': ['target_output'],
@@ -40,6 +43,9 @@ LOSS_MIX = {
     'q1td': [1.0],
     'v1td': [1.0],
     'vntd': [1.0],
+    'bdq': [1.0],
+    'qseq': [1.0],
+    'd1td': [1.0],
     'dntd': [1.0],
     'td_lambda': [1.0],
     'upgo': [1.0],
@@ -185,6 +191,54 @@ def vntd_case(seed, B, nstep, weight='none', value_gamma='none', gamma=0.95):
     return 'vntd', t, dict(gamma=gamma, nstep=nstep)
 
 
+def bdq_case(seed, B, D, N, nstep, weight='none', value_gamma='none', gamma=0.95, cum_reward=False):
+    g = _g(seed)
+    t = OrderedDict()
+    t['q'] = _randn(g, B, D, N)
+    t['next_n_q'] = _randn(g, B, D, N)
+    t['action'] = _randint(g, N, B, D)
+    t['next_n_action'] = _randint(g, N, B, D)
+    t['reward'] = _rand(g, B) if cum_reward else _rand(g, nstep, B)
+    t['done'] = _bern(g, 0.3, B)
+    t['weight'] = None if weight == 'none' else _rand(g, B)
+    params = dict(gamma=gamma, nstep=nstep, cum_reward=cum_reward)
+    if value_gamma == 'tensor':
+        t['value_gamma'] = _rand(g, B)
+    return 'bdq', t, params
+
+
+def qseq_case(seed, T, B, N, nstep, weight='tensor', value_gamma='tensor', gamma=0.997, rescale=False, list_gamma=False):
+    """The recurrent learners' per-step loop (ding/policy/r2d2.py:347-369): reward already in the (T, nstep, B) layout."""
+    g = _g(seed)
+    t = OrderedDict()
+    t['q'] = _randn(g, T, B, N)
+    t['next_n_q'] = _randn(g, T, B, N)
+    t['action'] = _randint(g, N, T, B)
+    t['next_n_action'] = _randint(g, N, T, B)
+    t['reward'] = _rand(g, T, nstep, B)
+    t['done'] = _bern(g, 0.1, T, B)
+    t['weight'] = None if weight == 'none' else _rand(g, T, B)
+    t['value_gamma'] = None if value_gamma == 'none' else _rand(g, T, B)
+    params = dict(gamma=gamma, nstep=nstep, rescale=rescale)
+    if list_gamma:
+        params['gamma'] = [torch.tensor(0.9 + 0.01 * i) for i in range(B)]
+    return 'qseq', t, params
+
+
+def d1td_case(seed, B, N, n_atom, gamma=0.95, v_min=-10., v_max=10., marl_A=None):
+    g = _g(seed)
+    lead = (B, ) if marl_A is None else (B, marl_A)
+    t = OrderedDict()
+    t['dist'] = torch.softmax(_randn(g, *lead, N, n_atom), -1)
+    t['next_dist'] = torch.softmax(_randn(g, *lead, N, n_atom), -1)
+    t['act'] = _randint(g, N, *lead)
+    t['next_act'] = _randint(g, N, *lead)
+    t['reward'] = _randn(g, B)
+    t['done'] = _bern(g, 0.3, B)
+    t['weight'] = None
+    return 'd1td', t, dict(gamma=gamma, v_min=v_min, v_max=v_max, n_atom=n_atom)
+
+
 def dntd_case(seed, B, N, n_atom, nstep, weight='none', value_gamma='none', gamma=0.95, v_min=-10., v_max=10.,
               marl_A=None, integer_bins=False, done='bern'):
     g = _g(seed)
@@ -260,6 +314,38 @@ def vtrace_case(seed, T, B, N, weight='none', **params):
     return 'vtrace', t, params
 
 
+def _qntd_cum_nb(seed):
+    """cum_reward=True with an (nstep, B) reward: the reference broadcasts to (nstep, B) errors (tests/test_td.py:29-35)."""
+    g = _g(seed)
+    B, N, nstep = 6, 4, 3
+    t = OrderedDict()
+    t['q'] = _randn(g, B, N)
+    t['next_n_q'] = _randn(g, B, N)
+    t['action'] = _randint(g, N, B)
+    t['next_n_action'] = _randint(g, N, B)
+    t['reward'] = _rand(g, nstep, B)
+    t['done'] = _randn(g, B)
+    t['weight'] = None
+    t['value_gamma'] = torch.tensor(0.9)
+    return t, dict(gamma=0.95, nstep=nstep, cum_reward=True)
+
+
+def _qntd_marl(seed):
+    """The reference's multi-agent branch: action (B, A, 1) against q (B, A, N) (td.py:700-705)."""
+    g = _g(seed)
+    B, A, N, nstep = 5, 3, 4, 2
+    t = OrderedDict()
+    t['q'] = _randn(g, B, A, N)
+    t['next_n_q'] = _randn(g, B, A, N)
+    t['action'] = _randint(g, N, B, A, 1)
+    t['next_n_action'] = _randint(g, N, B, A)
+    t['reward'] = _rand(g, nstep, B)
+    t['done'] = _bern(g, 0.3, B)
+    t['weight'] = _rand(g, B)
+    t['value_gamma'] = _rand(g, B)
+    return t, dict(gamma=0.9, nstep=nstep, cum_reward=False)
+
+
 def build_cases():
     """Small cases: what the golden fixtures hold and what every implementation is compared on."""
     c = OrderedDict()
@@ -314,6 +400,18 @@ def build_cases():
     c['v1td_2d'] = v1td_case(47, 8, K=3, weight='tensor')
     c['vntd_n3'] = vntd_case(48, 10, 3, gamma=0.99)
     c['vntd_n5_w_vg'] = vntd_case(49, 7, 5, weight='tensor', value_gamma='tensor')
+    # ---- shapes beyond (B, N)/(B,) that the reference's broadcasting accepts (tests/test_td.py:29-35, td.py:700-705) ----
+    c['qntd_cum_nstep_reward'] = ('qntd', ) + _qntd_cum_nb(90)
+    c['qntd_marl_branch'] = ('qntd', ) + _qntd_marl(91)
+    # ---- bdq_nstep (tests/test_td.py:40-68), the recurrent learners' loop (policy/r2d2.py:347-369), dist_1step -------------
+    c['bdq_n3'] = bdq_case(92, 8, 6, 3, 3)
+    c['bdq_n5_w_vg'] = bdq_case(93, 9, 4, 5, 5, weight='tensor', value_gamma='tensor')
+    c['bdq_cum'] = bdq_case(94, 7, 3, 4, 2, cum_reward=True, weight='tensor')
+    c['qseq_r2d2'] = qseq_case(95, 10, 12, 6, 3)
+    c['qseq_rescale_now'] = qseq_case(96, 7, 5, 4, 2, weight='none', value_gamma='none', rescale=True)
+    c['qseq_ngu'] = qseq_case(97, 5, 6, 3, 2, list_gamma=True, value_gamma='none')
+    c['d1td_basic'] = d1td_case(98, 9, 4, 51)
+    c['d1td_marl'] = d1td_case(99, 4, 3, 21, marl_A=2, v_min=-2., v_max=3.)
     # ---- dist_nstep (tests/test_td.py:130-204) ---------------------------------------------------------------
     c['dntd_cfgC'] = dntd_case(50, 32, 6, 51, 3, gamma=0.99, value_gamma='tensor')
     c['dntd_n5'] = dntd_case(51, 4, 3, 51, 5)
@@ -425,6 +523,53 @@ def run_api(api, op, tensors, params, device='cpu'):
         res['out_td_error_per_sample'] = _np(per)
         _backward(op, [loss], t, res)
         return res
+    if op == 'bdq':
+        data = api.q_nstep_td_data(*[t[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done',
+                                                    'weight')])
+        if 'value_gamma' in t:
+            p['value_gamma'] = t['value_gamma']
+        loss, per = api.bdq_nstep_td_error(data, p.pop('gamma'), **p)
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'qseq':
+        gamma = p['gamma']
+        if isinstance(gamma, list):
+            gamma = [x.to(device) for x in gamma]
+        if hasattr(api, 'q_nstep_td_error_sequence'):
+            data = api.q_nstep_td_seq_data(*[t[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done',
+                                                            'weight')])
+            loss, prio, per = api.q_nstep_td_error_sequence(data, gamma, p['nstep'], value_gamma=t['value_gamma'],
+                                                            rescale=p['rescale'])
+        else:  # the reference: the loop of ding/policy/r2d2.py:347-369 around its operator
+            fn = api.q_nstep_td_error_with_rescale if p['rescale'] else api.q_nstep_td_error
+            losses, errs, raw = [], [], []
+            for i in range(t['q'].shape[0]):
+                td_data = api.q_nstep_td_data(t['q'][i], t['next_n_q'][i], t['action'][i], t['next_n_action'][i],
+                                              t['reward'][i], t['done'][i],
+                                              None if t['weight'] is None else t['weight'][i])
+                l, e = fn(td_data, gamma, p['nstep'],
+                          value_gamma=None if t['value_gamma'] is None else t['value_gamma'][i])
+                losses.append(l)
+                errs.append(e.abs())
+                raw.append(e)
+            loss = sum(losses) / (len(losses) + 1e-8)
+            prio = 0.9 * torch.max(torch.stack(errs), dim=0)[0] + (1 - 0.9) * (torch.sum(torch.stack(errs), dim=0) /
+                                                                               (len(errs) + 1e-8))
+            per = torch.stack(raw)
+        res['out_loss'] = _np(loss)
+        res['out_priority'] = _np(prio)
+        res['out_td_error'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'd1td':
+        data = api.dist_1step_td_data(t['dist'], t['next_dist'], t['act'], t['next_act'], t['reward'], t['done'],
+                                      t['weight'])
+        loss = api.dist_1step_td_error(data, **p)
+        res['out_loss'] = _np(loss)
+        _backward(op, [loss], t, res)
+        return res
     if op == 'q1td':
         data = api.q_1step_td_data(*[t[k] for k in ('q', 'next_q', 'act', 'next_act', 'reward', 'done', 'weight')])
         loss = api.q_1step_td_error(data, p['gamma'])
@@ -514,6 +659,24 @@ def run_oracle(orc, op, tensors, params):
     if op == 'ppo_value':
         loss = orc.ppo_value_error(**t, **p)
         res['out_value_loss'] = _np(loss)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'bdq':
+        loss, per = orc.bdq_nstep_td_error(**t, **p)
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'qseq':
+        loss, prio, per = orc.q_nstep_td_error_sequence(**t, **p)
+        res['out_loss'] = _np(loss)
+        res['out_priority'] = _np(prio)
+        res['out_td_error'] = _np(per)
+        _backward(op, [loss], t, res)
+        return res
+    if op == 'd1td':
+        loss = orc.dist_1step_td_error(**t, **p)
+        res['out_loss'] = _np(loss)
         _backward(op, [loss], t, res)
         return res
     if op == 'q1td':

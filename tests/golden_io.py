@@ -20,6 +20,9 @@ INPUT_ORDER = {
     'q1td': ['q', 'next_q', 'act', 'next_act', 'reward', 'done', 'weight'],
     'v1td': ['v', 'next_v', 'reward', 'done', 'weight'],
     'vntd': ['v', 'next_n_v', 'reward', 'done', 'weight', 'value_gamma'],
+    'bdq': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight', 'value_gamma'],
+    'qseq': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight', 'value_gamma'],
+    'd1td': ['dist', 'next_dist', 'act', 'next_act', 'reward', 'done', 'weight'],
     'dntd': ['dist', 'next_n_dist', 'act', 'next_n_act', 'reward', 'done', 'weight', 'value_gamma'],
     'td_lambda': ['value', 'reward', 'weight'],
     'upgo': ['target_output', 'action', 'rhos', 'rewards', 'bootstrap_values', 'mask'],

@@ -544,3 +544,147 @@ def test_p2p_allreduce_kernel_single_rank_degenerate():
             g.replay()
     s.synchronize()
     assert torch.equal(out, src[:6]) and int(seq.item()) == 12
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# round 2: one-launch TD heads (forward also writes the unit-upstream gradient), attached td errors, sequence form,
+# differentiable lambda returns
+# ----------------------------------------------------------------------------------------------------------------
+BIG_TD = {
+    'bdq_big': lambda: cases.bdq_case(130, 4099, 6, 11, 3, weight='tensor', value_gamma='tensor'),
+    'qseq_r2d2_size': lambda: cases.qseq_case(131, 75, 64, 6, 5),            # ding/policy/r2d2.py defaults on Atari
+    'qseq_rescale_wide': lambda: cases.qseq_case(132, 40, 1031, 18, 3, rescale=True),
+    'qseq_T1': lambda: cases.qseq_case(133, 1, 9, 3, 2, weight='none'),
+    'd1td_big': lambda: cases.d1td_case(134, 2050, 6, 51),
+}
+
+
+@pytest.mark.parametrize('name', sorted(BIG_TD.keys()))
+def test_td_siblings_match_oracle(name):
+    op, tensors, params = BIG_TD[name]()
+    want = cases.run_oracle(rl_oracle, op, tensors, params)
+    got = _run(op, tensors, params)
+    cases.compare(got, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('op_case', ['qntd', 'qntdr', 'dntd', 'bdq'])
+def test_td_heads_exact_for_any_upstream_gradient(op_case):
+    """The forward launch writes the gradient for a unit upstream gradient; any other upstream value (and gradients that
+    arrive through td_error_per_sample) must be honoured by the backward launch; repeated backward accumulates."""
+    if op_case == 'qntd':
+        op, t, p = cases.qntd_case(140, 777, 6, 3, weight='tensor', value_gamma='tensor')
+    elif op_case == 'qntdr':
+        op, t, p = cases.qntd_case(141, 300, 5, 4, rescale=True, weight='tensor')
+    elif op_case == 'bdq':
+        op, t, p = cases.bdq_case(142, 130, 5, 4, 3, weight='tensor')
+    else:
+        op, t, p = cases.dntd_case(143, 260, 4, 51, 3, weight='tensor')
+    gin = cases.GRAD_INPUTS[op][0]
+
+    def run(api_kind, scale, use_td):
+        dev = DEV if api_kind == 'b200' else 'cpu'
+        tt = cases.prepare(op, t, dev)
+        pp = dict(p)
+        if api_kind == 'b200':
+            if op == 'dntd':
+                data = b2.dist_nstep_td_data(*[tt[k] for k in ('dist', 'next_n_dist', 'act', 'next_n_act', 'reward', 'done',
+                                                                'weight')])
+                loss, per = b2.dist_nstep_td_error(data, **pp)
+            else:
+                data = b2.q_nstep_td_data(*[tt[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done',
+                                                             'weight')])
+                if 'value_gamma' in tt:
+                    pp['value_gamma'] = tt['value_gamma']
+                gamma = pp.pop('gamma')
+                fn = {'qntd': b2.q_nstep_td_error, 'qntd_rescale': b2.q_nstep_td_error_with_rescale,
+                      'bdq': b2.bdq_nstep_td_error}[op]
+                loss, per = fn(data, gamma, **pp)
+        else:
+            fn = {'qntd': rl_oracle.q_nstep_td_error, 'qntd_rescale': rl_oracle.q_nstep_td_error_with_rescale,
+                  'bdq': rl_oracle.bdq_nstep_td_error, 'dntd': rl_oracle.dist_nstep_td_error}[op]
+            loss, per = fn(**tt, **pp)
+        total = scale * loss
+        if use_td and per.requires_grad:
+            coef = torch.linspace(-1, 1, per.numel(), device=per.device).reshape(per.shape)
+            total = total + (per * coef).sum()
+        total.backward(retain_graph=True)
+        g1 = tt[gin].grad.clone()
+        total.backward()
+        return g1, tt[gin].grad.clone()
+
+    for scale, use_td in ((1.0, False), (2.5, False), (1.0, True), (0.0, True)):
+        w1, w2 = run('oracle', scale, use_td)
+        g1, g2 = run('b200', scale, use_td)
+        for a, b in ((g1, w1), (g2, w2)):
+            a, b = a.cpu().numpy(), b.numpy()
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * max(np.abs(b).max(), 1e-30)), (op_case, scale, use_td)
+
+
+def test_lambda_returns_backward_matches_autograd_of_the_recurrence():
+    """Gradients w.r.t. values, rewards and tensor gammas / lambdas against autograd of an out-of-place restatement
+    (the reference's in-place loop supports the first two; MBSAC needs them, mbpolicy/mbsac.py:137,153); UPGO mode too."""
+    g = torch.Generator().manual_seed(150)
+    for T, B in ((17, 33), (130, 260), (1, 5), (64, 1)):
+        v = torch.randn(T + 1, B, generator=g)
+        r = torch.randn(T, B, generator=g)
+        gam = torch.rand(T, B, generator=g)
+        lam = torch.rand(T, B, generator=g)
+        done = (torch.rand(T, B, generator=g) < 0.1).float()
+        w = torch.randn(T, B, generator=g)
+        for use_t, dn in ((True, done), (False, None), (True, None)):
+            leaves_c = [x.clone().requires_grad_(True) for x in (v, r, gam, lam)]
+            leaves_d = [x.clone().to(DEV).requires_grad_(True) for x in (v, r, gam, lam)]
+            if use_t:
+                want = rl_oracle.lambda_returns_functional(leaves_c[0], leaves_c[1], leaves_c[2], leaves_c[3], dn)
+                got = b2.generalized_lambda_returns(leaves_d[0], leaves_d[1], leaves_d[2], leaves_d[3],
+                                                    None if dn is None else dn.to(DEV))
+            else:
+                want = rl_oracle.lambda_returns_functional(leaves_c[0], leaves_c[1], 0.97, 0.9, dn)
+                got = b2.generalized_lambda_returns(leaves_d[0], leaves_d[1], 0.97, 0.9, dn)
+            assert torch.equal(got.detach().cpu(), rl_oracle.generalized_lambda_returns(
+                v, r, gam if use_t else 0.97, lam if use_t else 0.9, dn)), 'forward stays bit-exact'
+            (want * w).sum().backward()
+            (got * w.to(DEV)).sum().backward()
+            for a, b in zip(leaves_d[:4 if use_t else 2], leaves_c):
+                a, b = a.grad.cpu().numpy(), b.grad.numpy()
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * max(np.abs(b).max(), 1e-30)), (T, B, use_t)
+        # upgo_returns: gradient to rewards and bootstrap values, none through the comparison
+        vc, rc = v.clone().requires_grad_(True), r.clone().requires_grad_(True)
+        lambdas = (rc + vc[1:]) >= vc[:-1]
+        lambdas = torch.cat([lambdas[1:], torch.ones_like(lambdas[-1:])], dim=0)
+        want = rl_oracle.lambda_returns_functional(vc, rc, 1.0, lambdas.float())
+        vd, rd = v.clone().to(DEV).requires_grad_(True), r.clone().to(DEV).requires_grad_(True)
+        got = b2.upgo_returns(rd, vd)
+        assert torch.equal(got.detach().cpu(), rl_oracle.upgo_returns(r, v))
+        (want * w).sum().backward()
+        (got * w.to(DEV)).sum().backward()
+        for a, b in ((vd, vc), (rd, rc)):
+            a, b = a.grad.cpu().numpy(), b.grad.numpy()
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * max(np.abs(b).max(), 1e-30)), (T, B, 'upgo')
+
+
+def test_tb_cross_entropy_matches_torch():
+    g = torch.Generator().manual_seed(151)
+    for shape, masked in (((9, 7, 6), False), ((5, 4, 3, 11), True), ((3, 2, 2, 130), False)):
+        logit = torch.randn(*shape, generator=g)
+        label = torch.randint(0, shape[-1], shape[:-1], generator=g)
+        mask = (torch.rand(*shape[:-1], generator=g) > 0.3).float() if masked else None
+        lc = logit.clone().requires_grad_(True)
+        want = rl_oracle.tb_cross_entropy(lc, label, mask)
+        ld = logit.clone().to(DEV).requires_grad_(True)
+        got = b2.tb_cross_entropy(ld, label.to(DEV), None if mask is None else mask.to(DEV))
+        assert got.shape == want.shape
+        assert torch.allclose(got.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-5)
+        w = torch.randn(*want.shape, generator=g)
+        (want * w).sum().backward()
+        (got * w.to(DEV)).sum().backward()
+        assert torch.allclose(ld.grad.cpu(), lc.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_ppo_fallback_grid_is_bounded_for_large_batches():
+    """N > 64 takes the warp-per-row kernel: its grid (and workspace need) used to grow with S; 300k rows x 70."""
+    op, t, p = cases.ppo_case(152, 300000, 70)
+    t = {k: (v if v is None else v) for k, v in t.items()}
+    want = cases.run_oracle(rl_oracle, op, t, p)
+    got = _run(op, t, p)
+    cases.compare(got, want, rtol=1e-5, atol=1e-5)

@@ -204,6 +204,9 @@ EXPECTED_CALLS = {
     'v1td': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'vntd': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'dntd': ['b200rl_dntd_fwd', 'b200rl_dntd_bwd'],
+    'bdq': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
+    'qseq': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
+    'd1td': ['b200rl_dntd_fwd', 'b200rl_dntd_bwd'],
     'td_lambda': ['b200rl_td_lambda_fwd', 'b200rl_scale'],
     'upgo': ['b200rl_lambda_returns', 'b200rl_upgo_head_fwd', 'b200rl_upgo_head_bwd'],
     'vtrace': ['b200rl_vtrace_fused_supported', 'b200rl_vtrace_fwd_grad', 'b200rl_vtrace_fwd_grad'],
