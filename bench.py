@@ -1,30 +1,38 @@
 #!/usr/bin/env python
-"""Benchmark of the learner hot path: GAE + ppo_error (forward AND backward) on a (T, B) trajectory batch.
+"""Benchmark of the learner hot path (BASELINE.json): trajectory return/advantage + policy-loss operators, forward AND
+backward, on synthetic batches of the reference's shapes.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|reference-cuda]
+                    [--config D|B|C|E] [--scaling weak|strong]
 
-Metric (BASELINE.json): learner transitions/sec, config D = Atari-PPO shape T=128, B=4096 per GPU, N=6 actions
-(``pong_ppo_config.py``: gamma 0.99, lambda 0.95, clip 0.2, value clip on).  One step = one pass of
-gae -> ppo_error forward -> backward(policy + 0.5 value - 0.01 entropy) over one batch of 524 288 transitions per GPU.
+Configs (BASELINE.json `configs`):
+  D (default, the metric of record)  Atari PPO: gae -> ppo_error, T=128, B=4096, N=6 per GPU (`--scaling strong`: B=4096 in
+                                     total, sharded), gamma 0.99, lambda 0.95, clip 0.2, value clip on
+  B                                  Pong DQN: q_nstep_td_error, B=512, N=6, nstep=3, value_gamma tensor
+  C                                  Atari C51: dist_nstep_td_error, B=512, N=6, 51 atoms, nstep=3
+  E                                  IMPALA: vtrace_error_discrete_action, T=64, B=8192, N=6 per GPU
+One step = one pass of the config's operators, forward and backward, over one batch.
 
-  value     inputs resident in HBM; the step's kernels (default: the one-launch gae+ppo_error step of csrc/colws.cu, its
-            finalize_sums and the backward's verification launch; --three / --unfused: the separate operators) replayed
-            as a CUDA graph; input/output buffer sets are rotated so that consecutive steps never find their data in the
-            126 MB L2 (4 sets x 67 MB); timed with CUDA events on the launching stream between barrier + synchronize,
-            max over ranks.
-  e2e       the same step through the public API (di_engine_b200.gae_ppo_error / backward; --three: gae, ppo_error)
-            starting from PINNED HOST buffers: per step H2D copy of every input, the kernels, D2H read of the loss.
-  roofline  per-kernel CUDA-event timing of the dominant kernel against MEASURED_PEAKS.json (HBM copy bandwidth).
+  value     inputs resident in HBM; the step's launches replayed as ONE CUDA graph that holds exactly K steps between two
+            timing events (event-record nodes inside the graph: device time of exactly K steps, bracketed by barrier +
+            synchronize); buffer sets are rotated so that consecutive steps never find their data in the 126 MB L2; max over
+            ranks.  `ms_per_step_host_bracketed` is the same replay timed with events around the graph launch.
+  e2e       the same step through the public API starting from PINNED HOST buffers: per step the H2D copy of every input
+            (one packed copy, di_engine_b200.PackedBatch), the kernels, a D2H read of the loss.
+  roofline  CUDA-event timing of the dominant kernel against MEASURED_PEAKS.json (HBM copy bandwidth).
   cpu_baseline / --impl reference
-            the reference algorithm on the host cores: oracle/rl_oracle.py, the torch-CPU restatement that is pinned
-            bit-exact to ding.rl_utils (the reference is pure Python and cannot travel to the GPU box).
+            the reference's own functions on the host cores: the unmodified ding.rl_utils byte-compiled into
+            oracle/_ref/ding_hotpath.zip by oracle/make_ref.py (kind "reference"); the oracle port only if that archive is
+            absent (kind "port").  --impl reference-cuda: the same functions on CUDA tensors on the B200.
 
-Multi-GPU (torchrun, one rank per GPU): the batch shards along B with no data-path exchange; the only collective is
-one NCCL all-reduce per step of the packed loss scalars (mean-of-rank-means, as DI-engine's DDP does,
-ding/utils/pytorch_ddp_dist_helper.py:38-47), issued on a side stream so it overlaps the next step's kernels.
-Weak scaling: every rank holds a full T=128 x B=4096 shard.
+Multi-GPU (torchrun, one rank per GPU): the batch shards along B with no data-path exchange.  Config D: the six loss scalars
+are exchanged inside the epilogue of the step's kernel (NVLink peer-memory mailboxes; mean of the rank means, as DI-engine's
+DDP does, ding/utils/pytorch_ddp_dist_helper.py:38-47) -- no collective launch; `--collective nccl|p2p-kernel` select the
+older separate exchanges.  `param_allreduce` reports the step with the parameter-gradient bucket all-reduce of the Atari VAC
+network (ding/policy/base_policy.py:431-450) appended.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -42,14 +50,17 @@ import torch  # noqa: E402
 T_LEN, B_COLS, N_ACT = 128, 4096, 6
 GAMMA, LAMBDA, CLIP = 0.99, 0.95, 0.2
 W_VALUE, W_ENTROPY = 0.5, -0.01
-ALG_BYTES_PER_TR = {'gae_ppo_fwd_grad': 128, 'gae': 24, 'ppo_fwd': 76, 'ppo_bwd': 100, 'ppo_fwd_grad': 104, 'ppo_bwd_check': 0, 'step': 128}
-METRIC = 'learner transitions/sec (GAE+ppo_error fwd+bwd, T=128 x B=4096 per GPU)'
+NSETS = 4
+# Atari VAC of pong_ppo_config.py:21-28 (obs [4,84,84], encoder [64,64,128] k8s4/k4s2/k3s1, fc 6272->128, actor 128->128->6,
+# critic 128->128->1): 16448 + 65600 + 73856 + 802944 + 17286 + 16641 parameters
+VAC_PARAMS = 992775
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# synthetic batch
+# workloads
 # ----------------------------------------------------------------------------------------------------------------
 def make_batch(seed, T=T_LEN, B=B_COLS, N=N_ACT):
+    """config D: seeded CPU tensors, so that every arm sees identical bits"""
     g = torch.Generator().manual_seed(seed)
     value = torch.randn(T, B, generator=g)
     done = (torch.rand(T, B, generator=g) < 0.01).float()
@@ -69,20 +80,412 @@ def make_batch(seed, T=T_LEN, B=B_COLS, N=N_ACT):
 
 
 def batch_bytes(b):
-    return sum(v.numel() * v.element_size() for v in b.values())
+    return sum(v.numel() * v.element_size() for v in b.values() if isinstance(v, torch.Tensor))
+
+
+def _p(o, t):
+    return o.ptr(t)
+
+
+class WorkloadD:
+    """gae -> ppo_error forward + backward(policy + 0.5 value - 0.01 entropy): 128 B / transition (24 + 104)."""
+    key = 'D'
+    unit = 'transitions'
+    alg_bytes = {'gae_ppo_fwd_grad': 128, 'gae': 24, 'ppo_fwd': 76, 'ppo_bwd': 100, 'ppo_fwd_grad': 104, 'ppo_bwd_check': 0}
+    step_bytes_per_unit = 128
+
+    def __init__(self, B=B_COLS, T=T_LEN, N=N_ACT, mode='onepass'):
+        self.T, self.B, self.N, self.mode = T, B, N, mode
+        self.units = T * B
+        self.metric = 'learner transitions/sec (GAE+ppo_error fwd+bwd, T=128 x B=4096 per GPU)'
+        self.workload = ('configs[3] Atari PPO gae+ppo_error fwd+bwd, T=%d x B=%d x N=%d per GPU, fp32, gamma 0.99 lambda 0.95 '
+                         'clip 0.2 value-clip on, loss mix [1, 0.5, -0.01]' % (T, B, N))
+
+    def make_batch(self, seed):
+        return make_batch(seed, self.T, self.B, self.N)
+
+    def cpu_step(self, api, b, device=None):
+        """the reference API (ding.rl_utils names): gae, ppo_error, backward"""
+        nv = b['next_value'].clone()
+        adv = api.gae(api.gae_data(b['value'], nv, b['reward'], b['done'], b['traj_flag']), GAMMA, LAMBDA)
+        ln = b['logit_new'].detach().requires_grad_(True)
+        vn = b['value_new'].detach().requires_grad_(True)
+        loss, info = api.ppo_error(api.ppo_data(ln, b['logit_old'], b['action'], vn, b['value_old'], adv.reshape(-1),
+                                                b['return_'], None, None), CLIP, True, None)
+        (loss.policy_loss + W_VALUE * loss.value_loss + W_ENTROPY * loss.entropy_loss).backward()
+        return loss.policy_loss.detach()
+
+    def device_step(self, host_batch, dev, exchange=None):
+        return DeviceStepD(self, host_batch, dev, exchange)
+
+    def e2e_compute(self, b2, d, three):
+        ln = d['logit_new'].requires_grad_(True)
+        vn = d['value_new'].requires_grad_(True)
+        gd = b2.gae_data(d['value'], d['next_value'], d['reward'], d['done'], d['traj_flag'])
+        if not three:
+            adv, loss, info = b2.gae_ppo_error(
+                gd, b2.ppo_data(ln, d['logit_old'], d['action'], vn, d['value_old'], None, d['return_'], None, None),
+                GAMMA, LAMBDA, CLIP, True, None)
+        else:
+            adv = b2.gae(gd, GAMMA, LAMBDA)
+            loss, info = b2.ppo_error(
+                b2.ppo_data(ln, d['logit_old'], d['action'], vn, d['value_old'], adv.view(-1), d['return_'], None,
+                            None), CLIP, True, None)
+        total = loss.policy_loss + W_VALUE * loss.value_loss + W_ENTROPY * loss.entropy_loss
+        total.backward()
+        return total
+
+
+class DeviceStepD:
+    """One config-D learner step on device-resident buffers through the C ABI (the layer under the public API)."""
+
+    def __init__(self, wl, host_batch, dev, exchange=None):
+        from di_engine_b200 import ops
+        self.ops, self.wl, self.exchange = ops, wl, exchange
+        self.hint = torch.tensor([1.0, W_VALUE, W_ENTROPY, 0.0], device=dev)
+        self.g_used = torch.zeros(4, device=dev)
+        self.b = {k: v.to(dev) for k, v in host_batch.items()}
+        self.nv0 = self.b['next_value'].clone()
+        self.S = wl.T * wl.B
+        self.g_p = torch.tensor(1.0, device=dev)
+        self.g_v = torch.tensor(W_VALUE, device=dev)
+        self.g_e = torch.tensor(W_ENTROPY, device=dev)
+        self.adv = torch.empty_like(self.b['value'])
+        self.out = torch.zeros(8, device=dev)
+        self.grad_logit = torch.empty_like(self.b['logit_new'])
+        self.grad_value = torch.empty_like(self.b['value_new'])
+        self.ws = ops.workspace(torch.device(dev))
+
+    def _ppo_in(self):
+        b, o = self.b, self.ops
+        return (_p(o, b['logit_new']), _p(o, b['logit_old']), None, _p(o, b['action']), _p(o, b['value_new']),
+                _p(o, b['value_old']), _p(o, self.adv), _p(o, b['return_']), None, self.S, 1, self.wl.N, CLIP, 1, 0.0, 1)
+
+    def gae(self):
+        b, o = self.b, self.ops
+        rc = o.lib().b200rl_gae(_p(o, b['value']), _p(o, b['next_value']), _p(o, b['reward']), _p(o, b['done']),
+                                _p(o, b['traj_flag']), _p(o, self.adv), self.wl.T, self.wl.B, 1, GAMMA, LAMBDA, 1,
+                                o.stream_ptr())
+        assert rc == 0, rc
+
+    def ppo_fwd(self):
+        o = self.ops
+        rc = o.lib().b200rl_ppo_fwd(*self._ppo_in(), _p(o, self.out), _p(o, self.ws), self.ws.numel() * 4, o.stream_ptr())
+        assert rc == 0, rc
+
+    def ppo_bwd(self):
+        o = self.ops
+        rc = o.lib().b200rl_ppo_bwd(*self._ppo_in(), _p(o, self.g_p), _p(o, self.g_v), _p(o, self.g_e), None, None, None,
+                                    _p(o, self.grad_logit), _p(o, self.grad_value), o.stream_ptr())
+        assert rc == 0, rc
+
+    def ppo_fwd_grad(self):
+        o = self.ops
+        rc = o.lib().b200rl_ppo_fwd_grad(*self._ppo_in(), _p(o, self.hint), _p(o, self.g_used), _p(o, self.out),
+                                         _p(o, self.grad_logit), _p(o, self.grad_value), _p(o, self.ws),
+                                         self.ws.numel() * 4, o.stream_ptr())
+        assert rc == 0, rc
+
+    def ppo_bwd_check(self):
+        o = self.ops
+        rc = o.lib().b200rl_ppo_bwd(*self._ppo_in(), _p(o, self.g_p), _p(o, self.g_v), _p(o, self.g_e), None,
+                                    _p(o, self.g_used), _p(o, self.hint), _p(o, self.grad_logit),
+                                    _p(o, self.grad_value), o.stream_ptr())
+        assert rc == 0, rc
+
+    def gae_ppo_fwd_grad(self):
+        b, o = self.b, self.ops
+        head = (_p(o, b['value']), _p(o, b['next_value']), _p(o, b['reward']), _p(o, b['done']), _p(o, b['traj_flag']),
+                self.wl.T, self.wl.B, GAMMA, LAMBDA, 1, _p(o, b['logit_new']), _p(o, b['logit_old']), None,
+                _p(o, b['action']), _p(o, b['value_new']), _p(o, b['value_old']), _p(o, b['return_']), None, self.wl.N,
+                CLIP, 1, 0.0, 1, _p(o, self.hint), _p(o, self.g_used), _p(o, self.adv), _p(o, self.out),
+                _p(o, self.grad_logit), _p(o, self.grad_value))
+        tail = (_p(o, self.ws), self.ws.numel() * 4, o.stream_ptr())
+        if self.exchange is not None:  # the loss scalars travel in the kernel's epilogue (NVLink peer-memory mailboxes)
+            rc = o.lib().b200rl_gae_ppo_fwd_grad_dp(*head, *self.exchange.args(), *tail)
+        else:
+            rc = o.lib().b200rl_gae_ppo_fwd_grad(*head, *tail)
+        assert rc == 0, rc
+
+    def kernels(self):
+        if self.wl.mode == 'onepass':
+            return [('gae_ppo_fwd_grad', self.gae_ppo_fwd_grad), ('ppo_bwd_check', self.ppo_bwd_check)]
+        if self.wl.mode == 'three':
+            return [('gae', self.gae), ('ppo_fwd_grad', self.ppo_fwd_grad), ('ppo_bwd_check', self.ppo_bwd_check)]
+        return [('gae', self.gae), ('ppo_fwd', self.ppo_fwd), ('ppo_bwd', self.ppo_bwd)]
+
+    def launches_per_step(self):
+        fx = os.environ.get('B200RL_FX_FINALIZE', '1') != '0'
+        return {'onepass': 2 if fx else 3, 'three': 5, 'unfused': 4}[self.wl.mode]
+
+    def loss_vector(self):
+        return self.out
+
+    def __call__(self):
+        for _, k in self.kernels():
+            k()
+
+    def check(self, host_batch):
+        """correctness guard against the CPU oracle (outside every timed region)"""
+        from oracle import rl_oracle
+        self()
+        torch.cuda.synchronize()
+        hb = host_batch
+        adv_ref = rl_oracle.gae(hb['value'], hb['next_value'].clone(), hb['reward'], hb['done'], hb['traj_flag'], GAMMA,
+                                LAMBDA)
+        assert torch.equal(self.adv.cpu(), adv_ref), 'gae parity broken'
+        self.b['next_value'].copy_(self.nv0)
+
+
+class WorkloadB:
+    """q_nstep_td_error forward + backward: one launch + its verification; 120 B / sample at N=6, n=3 with value_gamma."""
+    key = 'B'
+    unit = 'samples'
+
+    def __init__(self, B=512, N=6, nstep=3):
+        self.B, self.N, self.nstep = B, N, nstep
+        self.units = B
+        self.metric = 'learner samples/sec (q_nstep_td_error fwd+bwd, B=512 N=6 nstep=3)'
+        self.workload = 'configs[1] Pong DQN q_nstep_td_error fwd+bwd, B=%d N=%d nstep=%d, gamma 0.99, value_gamma tensor, fp32' % (
+            B, N, nstep)
+        per = 8 * N + 16 + 4 * nstep + 12 + 4 + 4 + 4 * N  # SURVEY.md section 8d (+4: value_gamma)
+        self.alg_bytes = {'qntd_fwd_grad': per, 'qntd_bwd_check': 0}
+        self.step_bytes_per_unit = per
+
+    def make_batch(self, seed):
+        g = torch.Generator().manual_seed(seed)
+        B, N, n = self.B, self.N, self.nstep
+        return dict(q=torch.randn(B, N, generator=g), next_n_q=torch.randn(B, N, generator=g),
+                    action=torch.randint(0, N, (B, ), generator=g), next_n_action=torch.randint(0, N, (B, ), generator=g),
+                    reward=torch.rand(n, B, generator=g), done=(torch.rand(B, generator=g) < 0.05).float(),
+                    value_gamma=torch.full((B, ), GAMMA ** n))
+
+    def cpu_step(self, api, b, device=None):
+        q = b['q'].detach().requires_grad_(True)
+        data = api.q_nstep_td_data(q, b['next_n_q'], b['action'], b['next_n_action'], b['reward'], b['done'], None)
+        loss, per = api.q_nstep_td_error(data, GAMMA, nstep=self.nstep, value_gamma=b['value_gamma'])
+        loss.backward()
+        return loss.detach()
+
+    def device_step(self, host_batch, dev, exchange=None):
+        return DeviceStepTD(self, host_batch, dev)
+
+    def e2e_compute(self, b2, d, three):
+        q = d['q'].requires_grad_(True)
+        data = b2.q_nstep_td_data(q, d['next_n_q'], d['action'], d['next_n_action'], d['reward'], d['done'], None)
+        loss, per = b2.q_nstep_td_error(data, GAMMA, nstep=self.nstep, value_gamma=d['value_gamma'])
+        loss.backward()
+        return loss
+
+
+class WorkloadC(WorkloadB):
+    """dist_nstep_td_error (C51) forward + backward; 1672 B / sample (selected rows in, dense grad out)."""
+    key = 'C'
+
+    def __init__(self, B=512, N=6, n_atom=51, nstep=3):
+        self.B, self.N, self.n_atom, self.nstep = B, N, n_atom, nstep
+        self.units = B
+        self.metric = 'learner samples/sec (dist_nstep_td_error fwd+bwd, B=512 N=6 n_atom=51 nstep=3)'
+        self.workload = ('configs[2] Atari C51 dist_nstep_td_error fwd+bwd, B=%d N=%d n_atom=%d nstep=%d, gamma 0.99, '
+                         'v in [-10, 10], fp32' % (B, N, n_atom, nstep))
+        per = 2 * 4 * n_atom + 16 + 4 * nstep + 8 + 4 * N * n_atom + 4
+        self.alg_bytes = {'dntd_fwd_grad': per, 'dntd_bwd_check': 0}
+        self.step_bytes_per_unit = per
+
+    def make_batch(self, seed):
+        g = torch.Generator().manual_seed(seed)
+        B, N, n, A = self.B, self.N, self.nstep, self.n_atom
+        return dict(dist=torch.softmax(torch.randn(B, N, A, generator=g), -1),
+                    next_n_dist=torch.softmax(torch.randn(B, N, A, generator=g), -1),
+                    act=torch.randint(0, N, (B, ), generator=g), next_n_act=torch.randint(0, N, (B, ), generator=g),
+                    reward=torch.rand(n, B, generator=g), done=(torch.rand(B, generator=g) < 0.05).float())
+
+    def cpu_step(self, api, b, device=None):
+        dist = b['dist'].detach().requires_grad_(True)
+        data = api.dist_nstep_td_data(dist, b['next_n_dist'], b['act'], b['next_n_act'], b['reward'], b['done'], None)
+        loss, per = api.dist_nstep_td_error(data, GAMMA, -10., 10., self.n_atom, self.nstep)
+        loss.backward()
+        return loss.detach()
+
+    def e2e_compute(self, b2, d, three):
+        dist = d['dist'].requires_grad_(True)
+        data = b2.dist_nstep_td_data(dist, d['next_n_dist'], d['act'], d['next_n_act'], d['reward'], d['done'], None)
+        loss, per = b2.dist_nstep_td_error(data, GAMMA, -10., 10., self.n_atom, self.nstep)
+        loss.backward()
+        return loss
+
+
+class DeviceStepTD:
+    """configs B / C on device-resident buffers through the C ABI: the one-launch forward+gradient and its verification."""
+
+    def __init__(self, wl, host_batch, dev):
+        from di_engine_b200 import ops
+        from di_engine_b200.rl_utils import td as tdmod
+        self.ops, self.wl = ops, wl
+        self.b = {k: v.to(dev) for k, v in host_batch.items()}
+        self.one = torch.tensor(1.0, device=dev)
+        B, N = wl.B, wl.N
+        self.loss = torch.zeros((), device=dev)
+        self.td = torch.empty(B, device=dev)
+        self.ws = ops.workspace(torch.device(dev))
+        if wl.key == 'B':
+            self.dcrit = torch.empty(B, device=dev)
+            self.target = torch.empty(B, device=dev)
+            self.grad = torch.empty(B, N, device=dev)
+        else:
+            self.proj = torch.empty(B, wl.n_atom, device=dev)
+            self.grad = torch.empty(B, N, wl.n_atom, device=dev)
+            self.support = tdmod._support(-10., 10., wl.n_atom, torch.device(dev))
+            self.bad = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def fwd_grad(self):
+        b, o, wl = self.b, self.ops, self.wl
+        if wl.key == 'B':
+            rc = o.lib().b200rl_qntd_fwd(
+                _p(o, b['q']), _p(o, b['next_n_q']), _p(o, b['action']), _p(o, b['next_n_action']), _p(o, b['reward']),
+                _p(o, b['done']), None, _p(o, b['value_gamma']), 1, None, wl.B, 1, wl.N, wl.nstep, GAMMA, 0, 0, 1e-2, 0,
+                0.0, 0, 0, 0.0, _p(o, self.loss), _p(o, self.td), _p(o, self.dcrit), _p(o, self.target), _p(o, self.grad),
+                None, _p(o, self.ws), self.ws.numel() * 4, o.stream_ptr())
+        else:
+            rc = o.lib().b200rl_dntd_fwd(
+                _p(o, b['dist']), _p(o, b['next_n_dist']), _p(o, b['act']), _p(o, b['next_n_act']), _p(o, b['reward']),
+                _p(o, b['done']), None, 0, None, 0, _p(o, self.support), wl.B, 1, wl.N, wl.n_atom, wl.nstep, GAMMA, -10.,
+                10., _p(o, self.loss), _p(o, self.td), _p(o, self.proj), _p(o, self.bad), _p(o, self.grad), _p(o, self.ws),
+                self.ws.numel() * 4, o.stream_ptr())
+        assert rc == 0, rc
+
+    def bwd_check(self):
+        b, o, wl = self.b, self.ops, self.wl
+        if wl.key == 'B':
+            rc = o.lib().b200rl_qntd_bwd(_p(o, self.dcrit), None, _p(o, b['action']), _p(o, self.one), None, wl.B, 1, wl.N,
+                                         0, 0, 1, _p(o, self.grad), o.stream_ptr())
+        else:
+            rc = o.lib().b200rl_dntd_bwd(_p(o, b['dist']), _p(o, b['act']), _p(o, self.proj), None, 0, _p(o, self.one),
+                                         None, wl.B, wl.N, wl.n_atom, 1, _p(o, self.grad), o.stream_ptr())
+        assert rc == 0, rc
+
+    def kernels(self):
+        pre = 'qntd' if self.wl.key == 'B' else 'dntd'
+        return [(pre + '_fwd_grad', self.fwd_grad), (pre + '_bwd_check', self.bwd_check)]
+
+    def launches_per_step(self):
+        return 2
+
+    def loss_vector(self):
+        return self.loss
+
+    def __call__(self):
+        for _, k in self.kernels():
+            k()
+
+    def check(self, host_batch):
+        self()
+        torch.cuda.synchronize()
+        api = _cpu_api()[0]
+        want = self.wl.cpu_step(api, host_batch)
+        assert abs(float(self.loss) - float(want)) <= 1e-5 + 1e-5 * abs(float(want)), (float(self.loss), float(want))
+
+
+class WorkloadE:
+    """vtrace_error_discrete_action forward + backward in one launch + verification: 96 B / transition (68 in + 28 out)."""
+    key = 'E'
+    unit = 'transitions'
+    alg_bytes = {'vtrace_fwd_grad': 96, 'vtrace_bwd_check': 0}
+    step_bytes_per_unit = 96
+
+    def __init__(self, T=64, B=8192, N=6):
+        self.T, self.B, self.N = T, B, N
+        self.units = T * B
+        self.metric = 'learner transitions/sec (vtrace_error_discrete_action fwd+bwd, T=64 x B=8192 per GPU)'
+        self.workload = ('configs[4] IMPALA vtrace_error_discrete_action fwd+bwd, T=%d x B=%d x N=%d per GPU, fp32, gamma 0.99 '
+                         'lambda 0.95 clips 1.0, loss mix [1, 0.5, -0.01]' % (T, B, N))
+
+    def make_batch(self, seed):
+        g = torch.Generator().manual_seed(seed)
+        T, B, N = self.T, self.B, self.N
+        tgt = torch.randn(T, B, N, generator=g)
+        return dict(target_output=tgt, behaviour_output=tgt + 0.5 * torch.randn(T, B, N, generator=g),
+                    action=torch.randint(0, N, (T, B), generator=g), value=torch.randn(T + 1, B, generator=g),
+                    reward=torch.rand(T, B, generator=g), weight=torch.ones(T, B))
+
+    def cpu_step(self, api, b, device=None):
+        tgt = b['target_output'].detach().requires_grad_(True)
+        val = b['value'].detach().requires_grad_(True)
+        loss = api.vtrace_error_discrete_action(
+            api.vtrace_data(tgt, b['behaviour_output'], b['action'], val, b['reward'], b['weight']), GAMMA, LAMBDA)
+        (loss.policy_loss + W_VALUE * loss.value_loss + W_ENTROPY * loss.entropy_loss).backward()
+        return loss.policy_loss.detach()
+
+    def device_step(self, host_batch, dev, exchange=None):
+        return DeviceStepE(self, host_batch, dev)
+
+    def e2e_compute(self, b2, d, three):
+        tgt = d['target_output'].requires_grad_(True)
+        val = d['value'].requires_grad_(True)
+        loss = b2.vtrace_error_discrete_action(
+            b2.vtrace_data(tgt, d['behaviour_output'], d['action'], val, d['reward'], d['weight']), GAMMA, LAMBDA)
+        total = loss.policy_loss + W_VALUE * loss.value_loss + W_ENTROPY * loss.entropy_loss
+        total.backward()
+        return total
+
+
+class DeviceStepE:
+
+    def __init__(self, wl, host_batch, dev):
+        from di_engine_b200 import ops
+        self.ops, self.wl = ops, wl
+        self.b = {k: v.to(dev) for k, v in host_batch.items()}
+        self.hint = torch.tensor([1.0, W_VALUE, W_ENTROPY], device=dev)
+        self.g_used = torch.zeros(3, device=dev)
+        self.g = [torch.tensor(x, device=dev) for x in (1.0, W_VALUE, W_ENTROPY)]
+        self.out = torch.zeros(4, device=dev)
+        self.grad_logit = torch.empty_like(self.b['target_output'])
+        self.grad_value = torch.empty_like(self.b['value'])
+        self.ws = ops.workspace(torch.device(dev))
+
+    def _call(self, verify):
+        b, o, wl = self.b, self.ops, self.wl
+        rc = o.lib().b200rl_vtrace_fwd_grad(
+            _p(o, b['target_output']), _p(o, b['behaviour_output']), _p(o, b['action']), _p(o, b['value']),
+            _p(o, b['reward']), _p(o, b['weight']), wl.T, wl.B, wl.N, GAMMA, LAMBDA, 1.0, 1.0, 1.0,
+            None if verify else _p(o, self.hint), 1 if verify else 0, _p(o, self.g[0]) if verify else None,
+            _p(o, self.g[1]) if verify else None, _p(o, self.g[2]) if verify else None, _p(o, self.g_used),
+            _p(o, self.hint) if verify else None, None if verify else _p(o, self.out), _p(o, self.grad_logit),
+            _p(o, self.grad_value), _p(o, self.ws), self.ws.numel() * 4, o.stream_ptr())
+        assert rc == 0, rc
+
+    def kernels(self):
+        return [('vtrace_fwd_grad', lambda: self._call(False)), ('vtrace_bwd_check', lambda: self._call(True))]
+
+    def launches_per_step(self):
+        return 3
+
+    def loss_vector(self):
+        return self.out
+
+    def __call__(self):
+        for _, k in self.kernels():
+            k()
+
+    def check(self, host_batch):
+        self()
+        torch.cuda.synchronize()
+        assert torch.isfinite(self.out[:3]).all()
+
+
+WORKLOADS = {'D': WorkloadD, 'B': WorkloadB, 'C': WorkloadC, 'E': WorkloadE}
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port) on the host cores
+# CPU arm: the reference's own functions on the host cores
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_step(orc, b):
-    adv = orc.gae(b['value'], b['next_value'].clone(), b['reward'], b['done'], b['traj_flag'], GAMMA, LAMBDA)
-    ln = b['logit_new'].detach().requires_grad_(True)
-    vn = b['value_new'].detach().requires_grad_(True)
-    p, v, e, k, akl, cf = orc.ppo_error(ln, b['logit_old'], b['action'], vn, b['value_old'], adv.reshape(-1),
-                                        b['return_'], None, None, CLIP, True, None)
-    (p + W_VALUE * v + W_ENTROPY * e).backward()
-    return float(p.detach())
+def _cpu_api():
+    """(api namespace, kind): the unmodified reference (tree or byte-compiled archive) when present, else the oracle port"""
+    from oracle import ref_loader
+    if ref_loader.available():
+        return ref_loader.load(), 'reference'
+    from oracle import port_api
+    return port_api, 'port'
 
 
 def usable_cores():
@@ -100,19 +503,22 @@ def usable_cores():
     return n
 
 
-def pick_threads(orc, b):
-    """All the host threads the reference can USE: the fastest of {usable, 64, 32, 16, 8} torch intra-op threads
-    (over-subscribing a throttled container makes torch slower, not faster)."""
+def pick_threads(wl, api, b):
+    """All the host threads the reference can USE: the fastest of {usable, 64, 32, 16, 8, 4} torch intra-op threads, best of
+    three timed steps per candidate (over-subscribing a throttled container makes torch slower, not faster)."""
     usable = usable_cores()
     best, best_t = None, None
-    for n in sorted({usable, 64, 32, 16, 8}):
+    for n in sorted({usable, 64, 32, 16, 8, 4}):
         if n > usable:
             continue
         torch.set_num_threads(n)
-        cpu_step(orc, b)
-        t0 = time.perf_counter()
-        cpu_step(orc, b)
-        dt = time.perf_counter() - t0
+        wl.cpu_step(api, b)
+        dt = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            wl.cpu_step(api, b)
+            d = time.perf_counter() - t0
+            dt = d if dt is None else min(dt, d)
         if best_t is None or dt < best_t:
             best, best_t = n, dt
         if dt > 4 * best_t:
@@ -120,20 +526,20 @@ def pick_threads(orc, b):
     return best
 
 
-def run_cpu(steps, warmup):
-    from oracle import rl_oracle
-    b = make_batch(0)
-    cores = pick_threads(rl_oracle, b)
+def run_cpu(wl, steps, warmup):
+    api, kind = _cpu_api()
+    b = wl.make_batch(0)
+    cores = pick_threads(wl, api, b)
     torch.set_num_threads(cores)
     for _ in range(warmup):
-        cpu_step(rl_oracle, b)
+        wl.cpu_step(api, b)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_step(rl_oracle, b)
+        wl.cpu_step(api, b)
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    return dict(value=T_LEN * B_COLS / med, ms_per_step=med * 1e3, total_s=sum(times), cores=cores,
+    return dict(value=wl.units / med, ms_per_step=med * 1e3, total_s=sum(times), cores=cores, kind=kind,
                 threads=torch.get_num_threads())
 
 
@@ -163,7 +569,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -214,89 +620,47 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-class DeviceStep:
-    """One learner step on device-resident buffers, via the tensor-level layer under the public API."""
+def kernel_source_sha(files):
+    """sha256 over the CUDA sources that define a kernel: ties a committed ncu capture to the code that is being timed"""
+    h = hashlib.sha256()
+    for f in files:
+        with open(os.path.join(ROOT, 'di-engine_b200', 'csrc', f), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
-    def __init__(self, host_batch, dev, fused=True):
-        from di_engine_b200 import ops
-        self.ops = ops
-        self.fused = fused
-        self.hint = torch.tensor([1.0, W_VALUE, W_ENTROPY, 0.0], device=dev)
-        self.g_used = torch.zeros(4, device=dev)
-        self.b = {k: v.to(dev) for k, v in host_batch.items()}
-        self.nv0 = self.b['next_value'].clone()
-        self.S = T_LEN * B_COLS
-        self.g_p = torch.tensor(1.0, device=dev)
-        self.g_v = torch.tensor(W_VALUE, device=dev)
-        self.g_e = torch.tensor(W_ENTROPY, device=dev)
-        self.adv = torch.empty_like(self.b['value'])
-        self.out = torch.zeros(8, device=dev)
-        self.grad_logit = torch.empty_like(self.b['logit_new'])
-        self.grad_value = torch.empty_like(self.b['value_new'])
-        self.ws = ops.workspace(torch.device(dev))
 
-    def gae(self):
-        b, o = self.b, self.ops
-        rc = o.lib().b200rl_gae(o.ptr(b['value']), o.ptr(b['next_value']), o.ptr(b['reward']), o.ptr(b['done']),
-                                o.ptr(b['traj_flag']), o.ptr(self.adv), T_LEN, B_COLS, 1, GAMMA, LAMBDA, 1,
-                                o.stream_ptr())
-        assert rc == 0, rc
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json) -- only if that capture
+    was taken from the sources the loaded library was built from; otherwise (None, why)."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(kernel)
+    except (OSError, ValueError):
+        return None, 'profiles/ncu_traffic.json missing'
+    if not tr:
+        return None, 'no ncu capture recorded for %s' % kernel
+    want = tr.get('source_sha16')
+    have = kernel_source_sha(tr.get('sources', [])) if tr.get('sources') else None
+    if not want or want != have:
+        return None, 'ncu capture is of other sources (%s != %s)' % (want, have)
+    return tr['dram_read'] + tr['dram_write'], 'profiles/%s' % tr.get('capture', 'ncu_traffic.json')
 
-    def ppo_fwd(self):
-        b, o = self.b, self.ops
-        rc = o.lib().b200rl_ppo_fwd(o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
-                                    o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(self.adv), o.ptr(b['return_']),
-                                    None, self.S, 1, N_ACT, CLIP, 1, 0.0, 1, o.ptr(self.out), o.ptr(self.ws),
-                                    self.ws.numel() * 4, o.stream_ptr())
-        assert rc == 0, rc
 
-    def ppo_bwd(self):
-        b, o = self.b, self.ops
-        rc = o.lib().b200rl_ppo_bwd(o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
-                                    o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(self.adv), o.ptr(b['return_']),
-                                    None, self.S, 1, N_ACT, CLIP, 1, 0.0, 1, o.ptr(self.g_p), o.ptr(self.g_v),
-                                    o.ptr(self.g_e), None, None, None, o.ptr(self.grad_logit), o.ptr(self.grad_value),
-                                    o.stream_ptr())
-        assert rc == 0, rc
-
-    def ppo_fwd_grad(self):
-        b, o = self.b, self.ops
-        rc = o.lib().b200rl_ppo_fwd_grad(o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
-                                         o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(self.adv),
-                                         o.ptr(b['return_']), None, self.S, 1, N_ACT, CLIP, 1, 0.0, 1, o.ptr(self.hint),
-                                         o.ptr(self.g_used), o.ptr(self.out), o.ptr(self.grad_logit),
-                                         o.ptr(self.grad_value), o.ptr(self.ws), self.ws.numel() * 4, o.stream_ptr())
-        assert rc == 0, rc
-
-    def ppo_bwd_check(self):
-        b, o = self.b, self.ops
-        rc = o.lib().b200rl_ppo_bwd(o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
-                                    o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(self.adv), o.ptr(b['return_']),
-                                    None, self.S, 1, N_ACT, CLIP, 1, 0.0, 1, o.ptr(self.g_p), o.ptr(self.g_v),
-                                    o.ptr(self.g_e), None, o.ptr(self.g_used), o.ptr(self.hint),
-                                    o.ptr(self.grad_logit), o.ptr(self.grad_value), o.stream_ptr())
-        assert rc == 0, rc
-
-    def gae_ppo_fwd_grad(self):
-        b, o = self.b, self.ops
-        rc = o.lib().b200rl_gae_ppo_fwd_grad(
-            o.ptr(b['value']), o.ptr(b['next_value']), o.ptr(b['reward']), o.ptr(b['done']), o.ptr(b['traj_flag']),
-            T_LEN, B_COLS, GAMMA, LAMBDA, 1, o.ptr(b['logit_new']), o.ptr(b['logit_old']), None, o.ptr(b['action']),
-            o.ptr(b['value_new']), o.ptr(b['value_old']), o.ptr(b['return_']), None, N_ACT, CLIP, 1, 0.0, 1,
-            o.ptr(self.hint), o.ptr(self.g_used), o.ptr(self.adv), o.ptr(self.out), o.ptr(self.grad_logit),
-            o.ptr(self.grad_value), o.ptr(self.ws), self.ws.numel() * 4, o.stream_ptr())
-        assert rc == 0, rc
-
-    def kernels(self):
-        if self.fused == 'onepass':
-            return [('gae_ppo_fwd_grad', self.gae_ppo_fwd_grad), ('ppo_bwd_check', self.ppo_bwd_check)]
-        if self.fused:
-            return [('gae', self.gae), ('ppo_fwd_grad', self.ppo_fwd_grad), ('ppo_bwd_check', self.ppo_bwd_check)]
-        return [('gae', self.gae), ('ppo_fwd', self.ppo_fwd), ('ppo_bwd', self.ppo_bwd)]
-
-    def __call__(self):
-        for _, k in self.kernels():
-            k()
+def set_rank_affinity(local_rank):
+    """Bind this rank's host threads (and with them its pinned staging buffers, first-touch) to the CPUs NVML reports as
+    local to its GPU: the e2e loader of 8 ranks otherwise crosses the socket interconnect for half of them."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 def run_gpu(args):
@@ -308,6 +672,7 @@ def run_gpu(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world != args.gpus:
         raise SystemExit('launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)' % (args.gpus, world))
+    affinity = set_rank_affinity(local)
     torch.cuda.set_device(local)
     dev = 'cuda:%d' % local
     if world > 1:
@@ -319,147 +684,186 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    K, W = args.steps, args.warmup
-    NSETS = 4
-    mode = False if args.unfused else (True if args.three else 'onepass')
-    sets = [DeviceStep(make_batch(1000 * rank + i), dev, fused=mode) for i in range(NSETS)]
-    step_bytes = ALG_BYTES_PER_TR['step'] * T_LEN * B_COLS
-    side = torch.cuda.Stream()
+    K, W = args.steps, max(args.warmup, 3)
+    strong = args.scaling == 'strong'
+    if args.config == 'D':
+        Bl = B_COLS // world if strong else B_COLS
+        if strong and B_COLS % world:
+            raise SystemExit('strong scaling needs world | %d' % B_COLS)
+        wl = WorkloadD(B=Bl, mode='unfused' if args.unfused else ('three' if args.three else 'onepass'))
+    elif args.config == 'E':
+        wl = WorkloadE(B=(8192 // world) if strong else 8192)
+    else:
+        wl = WORKLOADS[args.config]()
+        if world > 1:
+            raise SystemExit('configs B / C are single-GPU, launch-bound cases (SURVEY.md section 8d)')
+
     main = torch.cuda.Stream()
-    from di_engine_b200.parallel import LossAllReduce, P2PLossAllReduce
-    reducers, exchange = None, 'none'
+    side = torch.cuda.Stream()
+    from di_engine_b200.parallel import FusedLossExchange, LossAllReduce, P2PLossAllReduce
+    exchange, fused_x, reducers = 'none', None, None
     if world > 1:
-        if args.collective in ('auto', 'p2p'):
-            try:  # one small kernel over NVLink peer memory (symmetric memory); falls back to NCCL if unavailable
-                reducers = [P2PLossAllReduce(6, dev) for _ in range(NSETS)]
-                exchange = 'p2p'
+        mode = args.collective
+        if mode == 'auto':
+            mode = 'fused' if (wl.key == 'D' and wl.mode == 'onepass' and os.environ.get('B200RL_FX_FINALIZE', '1') != '0') \
+                else 'p2p-kernel'
+        if mode == 'fused':
+            try:
+                fused_x = FusedLossExchange(dev)
+                exchange = 'fused'
             except Exception as e:
-                if args.collective == 'p2p':
-                    raise
+                if rank == 0:
+                    print('bench: peer-memory mailboxes unavailable (%s); using NCCL' % e, file=sys.stderr)
+                mode = 'nccl'
+        if mode == 'p2p-kernel':
+            try:
+                reducers = [P2PLossAllReduce(6, dev) for _ in range(NSETS)]
+                exchange = 'p2p-kernel'
+            except Exception as e:
                 if rank == 0:
                     print('bench: peer-memory all-reduce unavailable (%s); using NCCL' % e, file=sys.stderr)
-        if reducers is None:
+                mode = 'nccl'
+        if mode == 'nccl':
             reducers = [LossAllReduce(6, dev) for _ in range(NSETS)]
             exchange = 'nccl'
 
+    hosts = [wl.make_batch(1000 * rank + i) for i in range(NSETS)]
+    sets = [wl.device_step(hosts[i], dev, fused_x) for i in range(NSETS)]
+    names = [n for n, _ in sets[0].kernels()]
+    step_bytes = wl.step_bytes_per_unit * wl.units
+
     def exchange_losses(j):
-        """mean over ranks of set j's six loss scalars (mean of rank means), on the current stream"""
-        if exchange == 'p2p':
-            reducers[j].reduce(sets[j].out)
-        else:
-            reducers[j].buf.copy_(sets[j].out[:6], non_blocking=True)
+        """separate exchange kernels (older modes): mean over ranks of set j's loss scalars, on the current stream"""
+        if exchange == 'p2p-kernel':
+            reducers[j].reduce(sets[j].loss_vector())
+        elif exchange == 'nccl':
+            reducers[j].buf.copy_(sets[j].loss_vector().reshape(-1)[:6], non_blocking=True)
             reducers[j].reduce()
 
-    # ---- correctness guard: first set against the CPU oracle on rank 0 (outside every timed region) ----------------
+    # ---- correctness guard on rank 0 (outside every timed region) ---------------------------------------------------
     if rank == 0:
-        from oracle import rl_oracle
-        hb = make_batch(0)
-        s0 = sets[0]
-        s0()
-        torch.cuda.synchronize()
-        adv_ref = rl_oracle.gae(hb['value'], hb['next_value'].clone(), hb['reward'], hb['done'], hb['traj_flag'], GAMMA,
-                                LAMBDA)
-        assert torch.equal(s0.adv.cpu(), adv_ref), 'gae parity broken'
-        s0.b['next_value'].copy_(s0.nv0)
+        chk = wl.make_batch(0)
+        wl.device_step(chk, dev).check(chk)
+    barrier()
 
-    # ---- capture one graph per buffer set -------------------------------------------------------------------------
-    # N > 1: the graph of step j also carries, on a forked branch, the all-reduce of the loss scalars of step j-1
-    # (software-pipelined: the collective of one step overlaps the kernels of the next; one graph launch per step)
-    graphs = []
-    collective_mode = 'none'
-    with torch.cuda.stream(main):
-        for s in sets:
-            s()
-            s()
-        if world > 1:
-            for j in range(NSETS):
-                exchange_losses(j)
-        main.synchronize()
+    bucket = torch.zeros(VAC_PARAMS, device=dev) if world > 1 else None
 
-        def record_step(j, with_collective):
-            if with_collective:
+    def record_steps(n, with_param_allreduce=False):
+        """n steps over the rotated buffer sets on the current (capturing) stream"""
+        for i in range(n):
+            j = i % NSETS
+            if exchange in ('p2p-kernel', 'nccl') and i > 0:  # software-pipelined on a forked branch, as in round 1
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     exchange_losses((j - 1) % NSETS)
             sets[j]()
-            if with_collective:
+            if exchange in ('p2p-kernel', 'nccl') and i > 0:
                 main.wait_stream(side)
+            if with_param_allreduce:
+                dist.all_reduce(bucket)
+        if exchange in ('p2p-kernel', 'nccl'):
+            exchange_losses((n - 1) % NSETS)
+        elif exchange == 'fused':
+            fused_x.drain()
 
-        def capture(with_collective):
-            """graphs[j]: one step on buffer set j; graphs[NSETS]: the NSETS steps 0..NSETS-1 back to back (one host launch
-            per NSETS steps -- the per-launch host cost of a ~25 us step is not negligible)"""
-            gs = []
+    def timed_graph(n, with_param_allreduce=False):
+        """ONE graph: [rank alignment] e0 | n steps | e1 -- the two events are nodes of the graph (external events), so their
+        difference is the device time of exactly n steps, free of the host's launch latency"""
+        e0 = torch.cuda.Event(enable_timing=True, external=True)
+        e1 = torch.cuda.Event(enable_timing=True, external=True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=main):
+            if world > 1 and align is not None:
+                align.reduce(align_src)  # device-side rank alignment: every rank leaves within one NVLink flag round
+            e0.record(main)
+            record_steps(n, with_param_allreduce)
+            e1.record(main)
+        return g, e0, e1
+
+    align, align_src = None, None
+    with torch.cuda.stream(main):
+        for s in sets:
+            s()
+            s()
+        if exchange == 'fused':
+            fused_x.drain()
+        elif world > 1:
             for j in range(NSETS):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=main):
-                    record_step(j, with_collective)
-                gs.append(g)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=main):
-                for j in range(NSETS):
-                    record_step(j, with_collective)
-            gs.append(g)
-            return gs
-
+                exchange_losses(j)
         if world > 1:
             try:
-                graphs = capture(True)
-                collective_mode = 'in-graph'
-            except Exception as e:  # NCCL capture unavailable: keep the collective eager on the side stream
-                if rank == 0:
-                    print('bench: NCCL graph capture failed (%s); eager side-stream all-reduce' % e, file=sys.stderr)
-                torch.cuda.synchronize()
-                graphs = capture(False)
-                collective_mode = 'eager'
-        else:
-            graphs = capture(False)
-    torch.cuda.synchronize()
+                align = P2PLossAllReduce(1, dev)
+                align_src = torch.ones(8, device=dev)
+                align.reduce(align_src)
+            except Exception:
+                align = None
+        main.synchronize()
+        barrier()
+        graph_warm, _, _ = timed_graph(250)
+        graph_k, e0, e1 = timed_graph(K)
+        main.synchronize()
+        barrier()
 
-    def device_loop(n):
-        """exactly n steps, buffer sets in the order 0,1,..,NSETS-1,0,1,.."""
-        if collective_mode != 'eager':
-            q, r = divmod(n, NSETS)
-            for _ in range(q):
-                graphs[NSETS].replay()
-            for j in range(r):
-                graphs[j].replay()
-        for i in range(n if collective_mode == 'eager' else 0):
-            j = i % NSETS
-            graphs[j].replay()
-            if collective_mode == 'eager':
-                ev = torch.cuda.Event()
-                ev.record(main)
-                side.wait_event(ev)
-                with torch.cuda.stream(side):
-                    exchange_losses(j)
-        if collective_mode == 'in-graph':  # the last step's scalars (every earlier one rode in the next step's graph)
-            exchange_losses((n - 1) % NSETS)
-        elif collective_mode == 'eager':
-            main.wait_stream(side)
-
-    with torch.cuda.stream(main):
-        device_loop(max(W, 3))
-        # pre-heat: ~0.25 s of the same steps (untimed) so SM/memory clocks and caches are in steady state -- one step is
-        # only ~30 us, far shorter than the clock governor's reaction time.  A FIXED step count: with a collective in the
-        # graph every rank must launch exactly the same number of steps.
-        for _ in range(8):
-            device_loop(1000)
-            torch.cuda.synchronize()
+        # warm-up + pre-heat: ~0.25 s of the same steps (untimed) so SM/memory clocks are in steady state -- one step is far
+        # shorter than the clock governor's reaction time.  FIXED counts: with an exchange in the graph every rank must
+        # launch exactly the same number of steps.
+        for _ in range(max(1, (W + 249) // 250)):
+            graph_warm.replay()
+        for _ in range(60):
+            graph_warm.replay()
+        main.synchronize()
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        e0.record(main)
-        device_loop(K)
-        e1.record(main)
+        h0.record(main)
+        graph_k.replay()
+        h1.record(main)
         barrier()
         dev_ms = e0.elapsed_time(e1)
+        host_ms = h0.elapsed_time(h1)
+        # keep the GPU under the same load while nvidia-smi samples (a 20-step region lasts 0.3 ms)
+        for _ in range(40):
+            graph_warm.replay()
+        main.synchronize()
+        clocks = sampler.stop() if rank == 0 else None
 
-        # ---- the same step launched eagerly (one ctypes call per launch, no graph): host-bound, reported next to the replay
+        # ---- the step with the parameter-gradient bucket all-reduce of the Atari VAC net appended (SURVEY section 8e) -----
+        par = None
+        if world > 1:
+            try:
+                for _ in range(3):
+                    dist.all_reduce(bucket)
+                main.synchronize()
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(main)
+                for _ in range(50):
+                    dist.all_reduce(bucket)
+                a1.record(main)
+                main.synchronize()
+                ar_us = a0.elapsed_time(a1) * 1e3 / 50
+                gp, p0, p1 = timed_graph(K, with_param_allreduce=True)
+                main.synchronize()
+                barrier()
+                gp.replay()
+                main.synchronize()
+                barrier()
+                gp.replay()
+                main.synchronize()
+                barrier()
+                par = dict(bytes=VAC_PARAMS * 4, nccl_allreduce_us_alone=ar_us, ms_per_step_with=p0.elapsed_time(p1) / K)
+                del gp
+            except Exception as e:  # never let the secondary figure break the benchmark
+                if rank == 0:
+                    print('bench: param all-reduce leg skipped (%s)' % e, file=sys.stderr)
+                torch.cuda.synchronize()
+
+        # ---- the same step launched eagerly (one ctypes call per launch, no graph): host-bound --------------------------
         eager_ms = None
-        try:
+        if world == 1:
             n_eager = 200
             for i in range(8):
                 sets[i % NSETS]()
@@ -471,45 +875,40 @@ def run_gpu(args):
             g1.record(main)
             main.synchronize()
             eager_ms = g0.elapsed_time(g1) / n_eager
-        except Exception as e:  # never let the secondary figure break the benchmark
-            if rank == 0:
-                print('bench: eager-launch timing skipped (%s)' % e, file=sys.stderr)
 
-        # ---- per-kernel timing: each kernel alone, back to back over the rotated buffer sets, replayed as a graph so
-        # that launch gaps of the host do not enter the figure (CUDA events on the launching stream)
-        names = [n for n, _ in sets[0].kernels()]
+        # ---- per-kernel timing: each API call alone, back to back over the rotated sets, in a graph --------------------
         per = {}
         reps = max(100, min(K, 2000) // NSETS)
-        for ki, name in enumerate(names):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=main):
-                for s in sets:
-                    s.kernels()[ki][1]()
-            for _ in range(3):
-                g.replay()
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            main.synchronize()
-            k0.record(main)
-            for _ in range(reps):
-                g.replay()
-            k1.record(main)
-            main.synchronize()
-            per[name] = [k0.elapsed_time(k1) / (reps * NSETS)]
-        clocks = sampler.stop() if rank == 0 else None
+        if fused_x is None:
+            for ki, name in enumerate(names):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=main):
+                    for s in sets:
+                        s.kernels()[ki][1]()
+                for _ in range(3):
+                    g.replay()
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                main.synchronize()
+                k0.record(main)
+                for _ in range(reps):
+                    g.replay()
+                k1.record(main)
+                main.synchronize()
+                per[name] = k0.elapsed_time(k1) / (reps * NSETS)
 
     # ---- end-to-end through the public API from pinned host buffers ------------------------------------------------
     packed = not args.e2e_separate_copies
     if packed:  # one pinned buffer + one device buffer per slot: the H2D transfer of a step is a single copy
-        slots = [b2.PackedBatch(make_batch(2000 * rank + i), dev) for i in range(2)]
+        slots = [b2.PackedBatch(wl.make_batch(2000 * rank + i), dev) for i in range(2)]
         host = slots
         h2d = slots[0].payload_bytes()
     else:
-        host = [{k: v.pin_memory() for k, v in make_batch(2000 * rank + i).items()} for i in range(2)]
+        host = [{k: v.pin_memory() for k, v in wl.make_batch(2000 * rank + i).items()} for i in range(2)]
         h2d = batch_bytes(host[0])
 
-    # The host side is a two-deep prefetching loader (what DI-engine's CudaFetcher, ding/torch_utils/data_helper.py:543,
-    # does for the learner): the H2D copy of step i+1 is enqueued on a copy stream before step i's result is read back,
-    # so PCIe transfer and kernels overlap.  Every byte of every step is still copied inside the timed region.
+    # two-deep prefetching loader (what DI-engine's CudaFetcher, ding/torch_utils/data_helper.py:543, does for the learner):
+    # the H2D copy of step i+1 is enqueued on a copy stream before step i's result is read back.  Every byte of every step is
+    # still copied inside the timed region.
     copy_stream = torch.cuda.Stream()
 
     def upload(hb):
@@ -521,39 +920,22 @@ def run_gpu(args):
             ev.record(copy_stream)
         return d, ev
 
-    def e2e_compute(d, ev):
-        torch.cuda.current_stream().wait_event(ev)
-        if not packed:
-            for v in d.values():
-                v.record_stream(torch.cuda.current_stream())
-        ln = d['logit_new'].requires_grad_(True)
-        vn = d['value_new'].requires_grad_(True)
-        gd = b2.gae_data(d['value'], d['next_value'], d['reward'], d['done'], d['traj_flag'])
-        if not (args.three or args.unfused):
-            adv, loss, info = b2.gae_ppo_error(
-                gd, b2.ppo_data(ln, d['logit_old'], d['action'], vn, d['value_old'], None, d['return_'], None, None),
-                GAMMA, LAMBDA, CLIP, True, None)
-        else:
-            adv = b2.gae(gd, GAMMA, LAMBDA)
-            loss, info = b2.ppo_error(
-                b2.ppo_data(ln, d['logit_old'], d['action'], vn, d['value_old'], adv.view(-1), d['return_'], None,
-                            None), CLIP, True, None)
-        total = loss.policy_loss + W_VALUE * loss.value_loss + W_ENTROPY * loss.entropy_loss
-        total.backward()
-        return total
-
     def e2e_loop(n):
         nxt = upload(host[0])
         last = None
         for i in range(n):
-            cur = nxt
+            d, ev = nxt
             if i + 1 < n:
                 nxt = upload(host[(i + 1) % 2])
-            total = e2e_compute(*cur)
-            last = total.item()  # D2H read of the step's result (ppo_info already cost one 8-byte read)
+            torch.cuda.current_stream().wait_event(ev)
+            if not packed:
+                for v in d.values():
+                    v.record_stream(torch.cuda.current_stream())
+            total = wl.e2e_compute(b2, d, args.three or args.unfused)
+            last = total.item()  # D2H read of the step's result
         return last
 
-    e2e_steps = max(5, min(K, 20))
+    e2e_steps = max(5, min(K, 20)) if wl.key in ('D', 'E') else max(20, min(K, 200))
     e2e_loop(3)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -564,67 +946,79 @@ def run_gpu(args):
     e2e_ms = f0.elapsed_time(f1)
 
     # ---- max over ranks --------------------------------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    vals = [dev_ms, e2e_ms, host_ms, par['ms_per_step_with'] if par else 0.0]
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms, host_ms, par_ms = t.tolist()
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        tr_per_step = T_LEN * B_COLS * world
+        units_per_step = wl.units * world
         ms_step = dev_ms / K
-        value = tr_per_step / (ms_step * 1e-3)
-        kmean = {n: statistics.mean(v) for n, v in per.items()}
-        dom = max(kmean, key=kmean.get)
-        dom_bytes = ALG_BYTES_PER_TR[dom] * T_LEN * B_COLS
-        achieved = dom_bytes / (kmean[dom] * 1e-3) / 1e9
+        value = units_per_step / (ms_step * 1e-3)
         step_achieved = step_bytes / (ms_step * 1e-3) / 1e9
-        traffic = None
-        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dom)
-            if tr:
-                traffic = tr['dram_read'] + tr['dram_write']
-        except (OSError, ValueError, KeyError):
-            pass
-        cpu = run_cpu(steps=8, warmup=2) if world == 1 else None
-        e2e_value = tr_per_step / (e2e_ms / e2e_steps * 1e-3)
+        roof = {'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
+                'step': {'alg_bytes': step_bytes, 'achieved': step_achieved, 'frac': step_achieved / peak}}
+        if per:
+            dom = max(per, key=per.get)
+            dom_bytes = wl.alg_bytes[dom] * wl.units
+            achieved = dom_bytes / (per[dom] * 1e-3) / 1e9
+            traffic, traffic_src = ncu_traffic(dom)
+            roof.update({'kernel': dom, 'achieved': achieved, 'frac': achieved / peak, 'traffic': traffic,
+                         'traffic_source': traffic_src, 'alg_bytes_per_launch': dom_bytes, 'kernel_ms': per})
+        else:  # the exchange rides inside the kernel: per-kernel timing alone would deadlock on the peers
+            roof.update({'kernel': names[0], 'achieved': step_achieved, 'frac': step_achieved / peak, 'traffic': None,
+                         'traffic_source': 'per-kernel timing is a single-GPU leg', 'alg_bytes_per_launch': step_bytes})
+        cpu = run_cpu(wl, steps=8 if wl.key in ('D', 'E') else 40, warmup=2) if world == 1 else None
+        e2e_value = units_per_step / (e2e_ms / e2e_steps * 1e-3)
+        coll = 'none'
+        if world > 1:
+            coll = {'fused': 'the 6 loss scalars are exchanged inside the epilogue of the step kernel (NVLink peer-memory '
+                             'mailboxes, {sequence,value} words; mean of rank means); step j-1 is consumed in step j, one '
+                             'drain kernel after the last step; no collective launch',
+                    'p2p-kernel': 'one small NVLink peer-memory kernel per step (b200rl_p2p_allreduce_mean) on a forked '
+                                  'graph branch',
+                    'nccl': 'one NCCL all-reduce of the 6 loss scalars per step on a forked graph branch'}[exchange]
         line = {
-            'metric': METRIC, 'value': value, 'unit': 'transitions/s', 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
-            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'metric': wl.metric, 'value': value, 'unit': wl.unit + '/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {
-                'workload': 'configs[3] Atari PPO gae+ppo_error T=128 B=4096 N=6 per GPU (B sharded across GPUs; obs '
-                            '[4,84,84] is not read by any kernel on this path and is not materialised)',
-                'transitions_per_step_per_gpu': T_LEN * B_COLS, 'gamma': GAMMA, 'lambda': LAMBDA, 'clip_ratio': CLIP,
-                'loss_mix': [1.0, W_VALUE, W_ENTROPY], 'parallelism': 'dp%d' % world,
-                'l2_policy': 'inputs rotated over %d buffer sets of 67 MB (> 126 MB L2) between consecutive steps' %
-                             NSETS,
-                'launch': 'CUDA graph replay, %d steps per graph launch, %d kernels per step (%s)' % (NSETS, len(names), ', '.join(names)),
-                'collective': 'none' if world == 1 else ('one all-reduce (mean) of the 6 loss scalars per step, %s, %s, overlapping the next step' % ('NVLink peer-memory kernel b200rl_p2p_allreduce_mean' if exchange == 'p2p' else 'NCCL', collective_mode)),
+                'workload': wl.workload,
+                'units_per_step_per_gpu': wl.units, 'parallelism': 'dp%d' % world,
+                'sharding': 'B sharded across GPUs, no data-path exchange' if world > 1 else 'single GPU',
+                'l2_policy': 'inputs rotated over %d buffer sets (%.0f MB in total, > 126 MB L2 for configs D/E; configs '
+                             'B/C are launch-bound and L2-resident by nature) between consecutive steps' %
+                             (NSETS, NSETS * step_bytes / 1e6),
+                'launch': 'ONE CUDA graph holding exactly %d steps between two in-graph timing events; %d launches per '
+                          'step (%s)' % (K, sets[0].launches_per_step(), ', '.join(names)),
+                'collective': coll,
+                'cpu_affinity': affinity,
             },
-            'roofline': {
-                'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'alg_bytes_per_launch': dom_bytes, 'kernel_ms': kmean,
-                'step': {'alg_bytes': step_bytes, 'achieved': step_achieved, 'frac': step_achieved / peak},
-            },
+            'ms_per_step_host_bracketed': host_ms / K,  # events around the graph launch: + the host's launch latency / K
+            'roofline': roof,
             'cpu_baseline': None if cpu is None else {
-                'value': cpu['value'], 'unit': 'transitions/s', 'cores': cpu['cores'], 'kind': 'port',
-                'sample': 'full T=128 x B=4096 batch, median of 8 steps after 2 warm-up (%.1f s CPU), %s' %
-                          (cpu['total_s'], cpu_model()),
+                'value': cpu['value'], 'unit': wl.unit + '/s', 'cores': cpu['cores'], 'kind': cpu['kind'],
+                'sample': 'full batch of the workload, median of %d steps after 2 warm-up (%.1f s CPU), %s' %
+                          (8 if wl.key in ('D', 'E') else 40, cpu['total_s'], cpu_model()),
                 'ms_per_step': cpu['ms_per_step'],
             },
-            'e2e': {'value': e2e_value, 'unit': 'transitions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
+            'e2e': {'value': e2e_value, 'unit': wl.unit + '/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 + (8 if wl.key == 'D' else 0),
                     'ms_per_step': e2e_ms / e2e_steps, 'steps': e2e_steps},
             'eager_ms_per_step': eager_ms,  # same launches without the CUDA graph (host-bound; `value` is the graph replay)
-            'gpu_launches': (len(names) + 1) * K,  # + the finalize_sums launch behind every loss-reducing kernel
+            'gpu_launches': sets[0].launches_per_step() * K,
             'clocks': clocks,
         }
+        if par:
+            line['param_allreduce'] = dict(par, ms_per_step_with=par_ms,
+                                           note='the step followed by an NCCL all-reduce of a %d-float dummy gradient '
+                                                'bucket (Atari VAC net) on the same stream' % VAC_PARAMS)
         print(json.dumps(line), flush=True)
     if world > 1:
         # graphs that captured NCCL work must be gone before the communicator is torn down; then leave without waiting on
         # NCCL's own teardown (a destroy_process_group after captured collectives has been seen to hang)
-        del graphs
+        del graph_warm, graph_k
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
@@ -634,20 +1028,61 @@ def run_gpu(args):
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    r = run_cpu(steps=args.steps, warmup=max(args.warmup, 1))
+    cfg = getattr(args, 'config', 'D')
+    wl = WORKLOADS[cfg]()
+    steps = min(args.steps, 400 if cfg in ('D', 'E') else 2000)
+    r = run_cpu(wl, steps=steps, warmup=max(args.warmup, 1))
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': 'transitions/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': max(args.warmup, 1), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+        'impl': 'reference', 'metric': wl.metric, 'value': r['value'], 'unit': wl.unit + '/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': max(args.warmup, 1), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+        'scaling': getattr(args, 'scaling', 'weak'), 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': wl.workload, 'parallelism': 'cpu',
+                   'implementation': 'unmodified ding.rl_utils (oracle/_ref/ding_hotpath.zip)' if r['kind'] == 'reference'
+                   else 'oracle port (oracle/rl_oracle.py)'},
+        'cpu_baseline': {'value': r['value'], 'unit': wl.unit + '/s', 'cores': r['cores'], 'kind': r['kind'],
+                         'sample': 'one full batch of the workload per step, %d torch threads (best of the candidates, '
+                                   'best-of-3 each), %s' % (r['threads'], cpu_model())},
+        'e2e': {'value': r['value'], 'unit': wl.unit + '/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def run_reference_cuda(args):
+    """--impl reference-cuda: the reference's torch functions on CUDA tensors on the B200 -- the same-hardware baseline
+    (BASELINE.md section 3).  Eager torch, CUDA events, rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.config]()
+    api, kind = _cpu_api()
+    dev = 'cuda:0'
+    bs = [{k: v.to(dev) for k, v in wl.make_batch(i).items()} for i in range(NSETS)]
+    for i in range(max(args.warmup, 3)):
+        wl.cpu_step(api, bs[i % NSETS])
+    torch.cuda.synchronize()
+    steps = min(args.steps, 200)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        wl.cpu_step(api, bs[i % NSETS])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak, peak_src = load_peaks()
+    ach = wl.step_bytes_per_unit * wl.units / (ms * 1e-3) / 1e9
+    line = {
+        'impl': 'reference-cuda', 'metric': wl.metric, 'value': wl.units / (ms * 1e-3), 'unit': wl.unit + '/s',
+        'n_gpus': 1, 'steps': steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'configs[3] Atari PPO gae+ppo_error T=128 B=4096 N=6 (one batch, host cores)',
-                   'parallelism': 'cpu'},
-        'cpu_baseline': {'value': r['value'], 'unit': 'transitions/s', 'cores': r['cores'], 'kind': 'port',
-                         'sample': 'full T=128 x B=4096 batch per step, %d torch threads, %s' %
-                                   (r['threads'], cpu_model())},
-        'e2e': {'value': r['value'], 'unit': 'transitions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'config': {'workload': wl.workload, 'parallelism': 'dp1',
+                   'implementation': ('unmodified ding.rl_utils' if kind == 'reference' else 'oracle port') +
+                   ' torch functions on CUDA tensors, eager launches'},
+        'roofline': {'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
+                     'step': {'alg_bytes': wl.step_bytes_per_unit * wl.units, 'achieved': ach, 'frac': ach / peak}},
     }
     print(json.dumps(line))
 
@@ -657,21 +1092,23 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=2000)
     ap.add_argument('--warmup', type=int, default=50)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--collective', default='auto', choices=['auto', 'p2p', 'nccl'],
-                    help='N>1: exchange of the loss scalars (auto = NVLink peer-memory kernel, NCCL if unavailable)')
-    ap.add_argument('--unfused', action='store_true', help='separate gae / ppo forward / ppo backward kernels')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-cuda'])
+    ap.add_argument('--config', default='D', choices=['D', 'B', 'C', 'E'],
+                    help='BASELINE.json configs: D (default) gae+ppo_error, B q_nstep_td_error, C dist_nstep_td_error, E vtrace')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='N>1: weak = a full batch per GPU (default); strong = the config-D/E batch sharded over the GPUs')
+    ap.add_argument('--collective', default='auto', choices=['auto', 'fused', 'p2p-kernel', 'nccl'],
+                    help='N>1: exchange of the loss scalars (auto = fused into the step kernel for config D)')
+    ap.add_argument('--unfused', action='store_true', help='config D: separate gae / ppo forward / ppo backward kernels')
     ap.add_argument('--three', action='store_true',
-                    help='gae, fused ppo forward+grad, verification as three kernels (default: the one-launch gae+ppo '
-                         'step of csrc/colws.cu + verification)')
-    ap.add_argument('--onepass', action='store_true', help='accepted for compatibility: the one-launch step is the default')
+                    help='config D: gae, fused ppo forward+grad, verification as three calls (default: the one-launch step)')
     ap.add_argument('--e2e-separate-copies', action='store_true',
                     help='e2e: one pinned tensor and one H2D copy per input (default: di_engine_b200.PackedBatch, one copy)')
     args = ap.parse_args()
     if args.impl == 'reference':
-        if args.steps > 400:
-            args.steps = 400  # bounded: ~50 ms of host work per step
         run_reference(args)
+    elif args.impl == 'reference-cuda':
+        run_reference_cuda(args)
     else:
         run_gpu(args)
 

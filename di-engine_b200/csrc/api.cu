@@ -110,3 +110,34 @@ extern "C" int b200rl_p2p_allreduce_mean(const float* local, const unsigned long
 }
 
 extern "C" size_t b200rl_p2p_mailbox_floats(int world) { return (size_t)2 * world * b200rl::P2P_ENTRY; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The exchange fused into the epilogue of the one-launch learner step (common.cuh: grid_finalize_fx) publishes the loss
+// scalars of launch q and consumes those of launch q-1; after the last step of a loop this small kernel consumes the final
+// launch's entries: out_mean[k] = mean over ranks of the last launch's out[k].  Mailbox layout: [2 slots][world][8] 64-bit
+// words {sequence, value}; b200rl_p2p_mailbox_floats(world) floats hold exactly that.
+// ---------------------------------------------------------------------------------------------------------------
+namespace b200rl {
+__global__ void __launch_bounds__(32) p2p_drain_kernel(const unsigned long long* __restrict__ mailboxes, int rank, int world,
+                                                       int n, const unsigned int* __restrict__ seq,
+                                                       float* __restrict__ out_mean) {
+    pdl_prologue();
+    const int k = threadIdx.x;
+    if (k >= n) return;
+    const unsigned int q = seq[k];
+    if (q == 0u) return;
+    FxArgs fa{};
+    fa.mailboxes = mailboxes; fa.rank = rank; fa.world = world;
+    out_mean[k] = p2p_consume_mean(fa, k, q);
+}
+}  // namespace b200rl
+
+extern "C" int b200rl_p2p_drain_mean(const unsigned long long* mailbox_ptrs_dev, int rank, int world, int n,
+                                     const unsigned int* seq_dev, float* out_mean, void* stream) {
+    if (!mailbox_ptrs_dev || !seq_dev || !out_mean || n < 1 || n > b200rl::P2P_SLOT_VALS || world < 1 || world > 64 ||
+        rank < 0 || rank >= world)
+        return B200RL_ERR_ARG;
+    (void)b200rl::launch_k(b200rl::p2p_drain_kernel, 1, 32, 0, (cudaStream_t)stream, mailbox_ptrs_dev, rank, world, n,
+                           seq_dev, out_mean);
+    return (int)cudaGetLastError();
+}

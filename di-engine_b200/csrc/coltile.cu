@@ -376,6 +376,7 @@ static int dispatch_col(const FusedArgs& f, float* out, float* ws, size_t ws_byt
 int launch_coltile(const FusedArgs& f, bool grads, int variant, float* out, float* ws, size_t ws_bytes,
                    cudaStream_t st) {
     if ((variant == 0 || variant == 3) && colws_ok(f)) return launch_colws(f, grads, out, ws, ws_bytes, st);
+    if (f.x_mailboxes) return B200RL_ERR_ARG;  // the fused exchange exists in colws.cu only
     if (variant == 2 && coltma_ok(f)) return launch_coltma(f, grads, out, ws, ws_bytes, st);
     return grads ? dispatch_col<true>(f, out, ws, ws_bytes, st) : dispatch_col<false>(f, out, ws, ws_bytes, st);
 }

@@ -379,16 +379,15 @@ extern "C" int b200rl_gae_ppo_set_impl(int impl) {
     return old;
 }
 
-extern "C" int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, const float* reward, const float* done,
-                                       const float* traj_flag, long long T, long long B, double gamma,
-                                       double lambda_, int mask_next_value_inplace, const float* logit_new,
-                                       const float* logit_old, const float* logit_pretrained,
-                                       const long long* action, const float* value_new, const float* value_old,
-                                       const float* return_, const float* weight, long long N, double clip_ratio,
-                                       int use_value_clip, double dual_clip, int kl_type, const float* g_expected,
-                                       float* g_used, float* adv, float* out, float* grad_logit_new,
-                                       float* grad_value_new, float* workspace, size_t workspace_bytes,
-                                       void* stream) {
+static int gae_ppo_step(const float* value, float* next_value, const float* reward, const float* done,
+                        const float* traj_flag, long long T, long long B, double gamma, double lambda_,
+                        int mask_next_value_inplace, const float* logit_new, const float* logit_old,
+                        const float* logit_pretrained, const long long* action, const float* value_new,
+                        const float* value_old, const float* return_, const float* weight, long long N,
+                        double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* g_expected,
+                        float* g_used, float* adv, float* out, float* grad_logit_new, float* grad_value_new,
+                        const unsigned long long* mailbox_ptrs_dev, int rank, int world, unsigned int* seq_dev,
+                        float* out_mean, float* workspace, size_t workspace_bytes, void* stream) {
     if (!value || !next_value || !reward || !logit_new || !logit_old || !action || !value_new || !value_old ||
         !return_ || !adv || !out || !workspace || T < 1 || B < 1 || N < 1 || kl_type < 1 || kl_type > 3)
         return B200RL_ERR_ARG;
@@ -406,6 +405,12 @@ extern "C" int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, co
     cudaStream_t st = (cudaStream_t)stream;
     const bool row_ok = fused_ok(f), col_ok = coltile_ok(f);
     if (!row_ok && !col_ok) return B200RL_ERR_ARG;
+    if (mailbox_ptrs_dev) {  // data-parallel exchange in the epilogue of the column-tile kernel
+        if (!seq_dev || !out_mean || world < 1 || world > 64 || rank < 0 || rank >= world || !col_ok)
+            return B200RL_ERR_ARG;
+        f.x_mailboxes = mailbox_ptrs_dev; f.x_seq = seq_dev; f.x_out_mean = out_mean; f.x_rank = rank; f.x_world = world;
+        return launch_coltile(f, grads, 0, out, workspace, workspace_bytes, st);
+    }
     // column tiles need enough columns to fill the machine (16 per CTA); tiny problems are launch-bound either way
     const int impl = current_impl();
     const bool want_col = impl >= 2 || (impl == 0 && (B >= 16 * 64 || T * B <= 16384));
@@ -414,4 +419,39 @@ extern "C" int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, co
     if (!row_ok) return B200RL_ERR_ARG;
     return grads ? dispatch_fused<true>(f, out, workspace, workspace_bytes, st)
                  : dispatch_fused<false>(f, out, workspace, workspace_bytes, st);
+}
+
+extern "C" int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, const float* reward, const float* done,
+                                       const float* traj_flag, long long T, long long B, double gamma,
+                                       double lambda_, int mask_next_value_inplace, const float* logit_new,
+                                       const float* logit_old, const float* logit_pretrained,
+                                       const long long* action, const float* value_new, const float* value_old,
+                                       const float* return_, const float* weight, long long N, double clip_ratio,
+                                       int use_value_clip, double dual_clip, int kl_type, const float* g_expected,
+                                       float* g_used, float* adv, float* out, float* grad_logit_new,
+                                       float* grad_value_new, float* workspace, size_t workspace_bytes,
+                                       void* stream) {
+    return gae_ppo_step(value, next_value, reward, done, traj_flag, T, B, gamma, lambda_, mask_next_value_inplace,
+                        logit_new, logit_old, logit_pretrained, action, value_new, value_old, return_, weight, N,
+                        clip_ratio, use_value_clip, dual_clip, kl_type, g_expected, g_used, adv, out, grad_logit_new,
+                        grad_value_new, nullptr, 0, 1, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200rl_gae_ppo_fwd_grad_dp(const float* value, float* next_value, const float* reward, const float* done,
+                                          const float* traj_flag, long long T, long long B, double gamma,
+                                          double lambda_, int mask_next_value_inplace, const float* logit_new,
+                                          const float* logit_old, const float* logit_pretrained,
+                                          const long long* action, const float* value_new, const float* value_old,
+                                          const float* return_, const float* weight, long long N, double clip_ratio,
+                                          int use_value_clip, double dual_clip, int kl_type, const float* g_expected,
+                                          float* g_used, float* adv, float* out, float* grad_logit_new,
+                                          float* grad_value_new, const unsigned long long* mailbox_ptrs_dev, int rank,
+                                          int world, unsigned int* seq_dev, float* out_mean, float* workspace,
+                                          size_t workspace_bytes, void* stream) {
+    if (!mailbox_ptrs_dev) return B200RL_ERR_ARG;
+    return gae_ppo_step(value, next_value, reward, done, traj_flag, T, B, gamma, lambda_, mask_next_value_inplace,
+                        logit_new, logit_old, logit_pretrained, action, value_new, value_old, return_, weight, N,
+                        clip_ratio, use_value_clip, dual_clip, kl_type, g_expected, g_used, adv, out, grad_logit_new,
+                        grad_value_new, mailbox_ptrs_dev, rank, world, seq_dev, out_mean, workspace, workspace_bytes,
+                        stream);
 }

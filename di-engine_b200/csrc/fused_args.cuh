@@ -16,6 +16,11 @@ struct FusedArgs {
     float gamma, gl;
     int mask_inplace;
     int trace;
+    // optional data-parallel exchange of the six loss scalars in the kernel's epilogue (colws.cu only; common.cuh FxArgs)
+    const unsigned long long* x_mailboxes;
+    unsigned int* x_seq;
+    float* x_out_mean;
+    int x_rank, x_world;
 };
 
 // column-tile implementations.  coltile.cu: all threads copy (cp.async) and compute; it also hosts the dispatcher:

@@ -248,11 +248,24 @@ __global__ void __launch_bounds__(NT) ppo_bwd_kernel(PpoArgs a) {
     const float g_val = a.g_value ? *a.g_value : 0.f;
     const float g_ent = a.g_entropy ? *a.g_entropy : 0.f;
     const float g_kl = (a.g_kl && a.logit_pre) ? *a.g_kl : 0.f;
+    // verification launch behind a fused forward (no shared memory, small grid: it normally returns right here):
+    // refresh the expectation for the next forward and leave if the gradients in grad_* were produced for these values
+    if (a.g_hint && blockIdx.x == 0 && threadIdx.x == 0) {
+        a.g_hint[0] = g_pol; a.g_hint[1] = g_val; a.g_hint[2] = g_ent; a.g_hint[3] = a.g_kl ? *a.g_kl : 0.f;
+    }
+    if (a.g_used) {
+        const bool same = __float_as_uint(a.g_used[0]) == __float_as_uint(g_pol) &&
+                          __float_as_uint(a.g_used[1]) == __float_as_uint(g_val) &&
+                          __float_as_uint(a.g_used[2]) == __float_as_uint(g_ent) &&
+                          (!a.logit_pre || __float_as_uint(a.g_used[3]) == __float_as_uint(g_kl));
+        if (same) return;
+    }
     const float inv_s = 1.f / (float)a.S;
     const float inv_m = 1.f / ((float)a.S * (float)G);
-    const long long s = (MODE == 1) ? (long long)blockIdx.x * NT + threadIdx.x
-                                    : (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-    if (s >= a.S) return;
+    const long long per_cta = (MODE == 1) ? NT : NT / 32;
+    long long s = (MODE == 1) ? (long long)blockIdx.x * NT + threadIdx.x
+                              : (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    for (; s < a.S; s += per_cta * gridDim.x) {
     const float* zn = a.logit_new + s * G * N;
     const float* zo = a.logit_old + s * G * N;
     const float* zp = a.logit_pre ? a.logit_pre + s * G * N : nullptr;
@@ -308,6 +321,7 @@ __global__ void __launch_bounds__(NT) ppo_bwd_kernel(PpoArgs a) {
         float dterm;
         value_term(a.value_new[s], a.value_old[s], a.ret[s], a.clip, a.use_value_clip, dterm);
         a.grad_value[s] = g_val * 0.5f * w * inv_s * dterm;
+    }
     }
 }
 
@@ -526,11 +540,13 @@ extern "C" int b200rl_ppo_bwd(const float* logit_new, const float* logit_old, co
     if (!grad_logit_new || !grad_value_new) return B200RL_ERR_ARG;
     if (S == 0) return B200RL_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    constexpr int NT = 128;
     if (tile_path_ok(a)) return dispatch_tile<PPO_BWD>(a, nullptr, nullptr, 0, st);
     if (g_used) return B200RL_ERR_ARG;  // the fused forward only exists on the tile path
-    constexpr int NT = 128;
-    if (a.N > 64) (void)launch_k(ppo_bwd_kernel<NT, 2>, div_up(S, NT / 32), NT, 0, st, a);
-    else (void)launch_k(ppo_bwd_kernel<NT, 1>, div_up(S, NT), NT, 0, st, a);
+    long long grid = a.N > 64 ? div_up(S, NT / 32) : div_up(S, NT);
+    if (grid > 148 * 32) grid = 148 * 32;  // grid-stride kernels
+    if (a.N > 64) (void)launch_k(ppo_bwd_kernel<NT, 2>, (int)grid, NT, 0, st, a);
+    else (void)launch_k(ppo_bwd_kernel<NT, 1>, (int)grid, NT, 0, st, a);
     return (int)cudaGetLastError();
 }
 

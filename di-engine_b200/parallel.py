@@ -116,3 +116,46 @@ class P2PLossAllReduce:
                                                  self.seq.data_ptr(), self.buf.data_ptr(), ops.stream_ptr())
         _lib.check(rc, 'b200rl_p2p_allreduce_mean')
         return self.buf
+
+
+class FusedLossExchange:
+    """State of the exchange that rides in the epilogue of the one-launch learner step (``b200rl_gae_ppo_fwd_grad_dp``,
+    csrc/common.cuh ``grid_finalize_fx``): the thread that finalises a loss sum stores ``{sequence, value}`` as one 8-byte
+    word into every peer's mailbox over NVLink and consumes the previous launch's values of all ranks -- no collective call,
+    no extra launch, no forked graph branch.  ``out_mean`` holds the mean over ranks of the PREVIOUS step's six loss scalars
+    (the exchange of step j overlaps step j+1); ``drain()`` after the last step delivers the final step's mean.
+
+    Same contract as ``LossAllReduce`` (mean of equal-sized rank means, ding/utils/pytorch_ddp_dist_helper.py:38-47);
+    every rank must launch the same sequence of steps.  Needs P2P access between the GPUs (torch symmetric memory).
+    """
+
+    def __init__(self, device, group=None, n_values=6):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import ops
+        self.n = n_values
+        self.device = torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self._lib = ops.lib()
+        nfl = self._lib.b200rl_p2p_mailbox_floats(self.world)
+        self.mailbox = symm_mem.empty(nfl, dtype=torch.float32, device=self.device)
+        self.mailbox.zero_()
+        self.handle = symm_mem.rendezvous(self.mailbox, self.group)
+        self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self.seq = torch.zeros(8, dtype=torch.int32, device=self.device)
+        self.out_mean = torch.zeros(8, dtype=torch.float32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)  # every mailbox is zeroed and mapped before the first exchange
+
+    def args(self):
+        """(mailbox_ptrs_dev, rank, world, seq_dev, out_mean) for ``b200rl_gae_ppo_fwd_grad_dp``."""
+        return self.ptrs.data_ptr(), self.rank, self.world, self.seq.data_ptr(), self.out_mean.data_ptr()
+
+    def drain(self):
+        """Consume the last launched step's entries (one tiny kernel on the current stream). Returns ``out_mean``."""
+        from . import _lib, ops
+        rc = self._lib.b200rl_p2p_drain_mean(self.ptrs.data_ptr(), self.rank, self.world, self.n, self.seq.data_ptr(),
+                                             self.out_mean.data_ptr(), ops.stream_ptr())
+        _lib.check(rc, 'b200rl_p2p_drain_mean')
+        return self.out_mean

@@ -19,6 +19,7 @@ import logging
 import os
 import sys
 import types
+import warnings
 
 REF_ROOT = os.environ.get("DI_ENGINE_REFERENCE", "/root/reference")
 ARCHIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ding_hotpath.zip")
@@ -71,7 +72,9 @@ def load():
     pkg = sys.modules["ding.rl_utils"]
     import ding.hpc_rl  # noqa: F401
     for m in _HOT_MODULES:
-        mod = importlib.import_module("ding.rl_utils." + m)
+        with warnings.catch_warnings():  # the reference's docstrings hold a few invalid escape sequences
+            warnings.simplefilter("ignore", SyntaxWarning)
+            mod = importlib.import_module("ding.rl_utils." + m)
         for k, v in vars(mod).items():
             if not k.startswith("_"):
                 setattr(pkg, k, v)
