@@ -26,7 +26,7 @@ One step = one pass of the config's operators, forward and backward, over one ba
             absent (kind "port").  --impl reference-cuda: the same functions on CUDA tensors on the B200.
 
 Multi-GPU (torchrun, one rank per GPU): the batch shards along B with no data-path exchange.  Config D: the six loss scalars
-are exchanged inside the epilogue of the step's kernel (NVLink peer-memory mailboxes; mean of the rank means, as DI-engine's
+are exchanged by the step's own loss-finalisation launch (NVLink peer-memory mailboxes; mean of the rank means, as DI-engine's
 DDP does, ding/utils/pytorch_ddp_dist_helper.py:38-47) -- no collective launch; `--collective nccl|p2p-kernel` select the
 older separate exchanges.  `param_allreduce` reports the step with the parameter-gradient bucket all-reduce of the Atari VAC
 network (ding/policy/base_policy.py:431-450) appended.
@@ -201,7 +201,7 @@ class DeviceStepD:
                 CLIP, 1, 0.0, 1, _p(o, self.hint), _p(o, self.g_used), _p(o, self.adv), _p(o, self.out),
                 _p(o, self.grad_logit), _p(o, self.grad_value))
         tail = (_p(o, self.ws), self.ws.numel() * 4, o.stream_ptr())
-        if self.exchange is not None:  # the loss scalars travel in the kernel's epilogue (NVLink peer-memory mailboxes)
+        if self.exchange is not None:  # the loss scalars travel in the step's finalize launch (NVLink mailboxes)
             rc = o.lib().b200rl_gae_ppo_fwd_grad_dp(*head, *self.exchange.args(), *tail)
         else:
             rc = o.lib().b200rl_gae_ppo_fwd_grad(*head, *tail)
@@ -215,8 +215,7 @@ class DeviceStepD:
         return [('gae', self.gae), ('ppo_fwd', self.ppo_fwd), ('ppo_bwd', self.ppo_bwd)]
 
     def launches_per_step(self):
-        fx = os.environ.get('B200RL_FX_FINALIZE', '1') != '0'
-        return {'onepass': 2 if fx else 3, 'three': 5, 'unfused': 4}[self.wl.mode]
+        return {'onepass': 3, 'three': 5, 'unfused': 4}[self.wl.mode]
 
     def loss_vector(self):
         return self.out
@@ -663,6 +662,11 @@ def set_rank_affinity(local_rank):
     return None
 
 
+def dbg(*a):
+    if os.environ.get('BENCH_DEBUG'):
+        print('[bench %s]' % os.environ.get('RANK', '0'), *a, file=sys.stderr, flush=True)
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import di_engine_b200 as b2
@@ -705,8 +709,7 @@ def run_gpu(args):
     if world > 1:
         mode = args.collective
         if mode == 'auto':
-            mode = 'fused' if (wl.key == 'D' and wl.mode == 'onepass' and os.environ.get('B200RL_FX_FINALIZE', '1') != '0') \
-                else 'p2p-kernel'
+            mode = 'fused' if (wl.key == 'D' and wl.mode == 'onepass') else 'p2p-kernel'
         if mode == 'fused':
             try:
                 fused_x = FusedLossExchange(dev)
@@ -727,6 +730,7 @@ def run_gpu(args):
             reducers = [LossAllReduce(6, dev) for _ in range(NSETS)]
             exchange = 'nccl'
 
+    dbg('setup done')
     hosts = [wl.make_batch(1000 * rank + i) for i in range(NSETS)]
     sets = [wl.device_step(hosts[i], dev, fused_x) for i in range(NSETS)]
     names = [n for n, _ in sets[0].kernels()]
@@ -746,6 +750,7 @@ def run_gpu(args):
         wl.device_step(chk, dev).check(chk)
     barrier()
 
+    dbg('check done')
     bucket = torch.zeros(VAC_PARAMS, device=dev) if world > 1 else None
 
     def record_steps(n, with_param_allreduce=False):
@@ -799,7 +804,8 @@ def run_gpu(args):
                 align = None
         main.synchronize()
         barrier()
-        graph_warm, _, _ = timed_graph(250)
+        dbg('eager warm done')
+        graph_warm, _w0, _w1 = timed_graph(250)  # (the event-record nodes need their events alive)
         graph_k, e0, e1 = timed_graph(K)
         main.synchronize()
         barrier()
@@ -807,12 +813,14 @@ def run_gpu(args):
         # warm-up + pre-heat: ~0.25 s of the same steps (untimed) so SM/memory clocks are in steady state -- one step is far
         # shorter than the clock governor's reaction time.  FIXED counts: with an exchange in the graph every rank must
         # launch exactly the same number of steps.
+        dbg('graphs captured')
         for _ in range(max(1, (W + 249) // 250)):
             graph_warm.replay()
         for _ in range(60):
             graph_warm.replay()
         main.synchronize()
         barrier()
+        dbg('preheat done')
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -822,6 +830,7 @@ def run_gpu(args):
         graph_k.replay()
         h1.record(main)
         barrier()
+        dbg('timed replay done')
         dev_ms = e0.elapsed_time(e1)
         host_ms = h0.elapsed_time(h1)
         # keep the GPU under the same load while nvidia-smi samples (a 20-step region lasts 0.3 ms)
@@ -862,6 +871,7 @@ def run_gpu(args):
                 torch.cuda.synchronize()
 
         # ---- the same step launched eagerly (one ctypes call per launch, no graph): host-bound --------------------------
+        dbg('param leg done')
         eager_ms = None
         if world == 1:
             n_eager = 200
@@ -877,6 +887,7 @@ def run_gpu(args):
             eager_ms = g0.elapsed_time(g1) / n_eager
 
         # ---- per-kernel timing: each API call alone, back to back over the rotated sets, in a graph --------------------
+        dbg('eager done')
         per = {}
         reps = max(100, min(K, 2000) // NSETS)
         if fused_x is None:
@@ -897,6 +908,7 @@ def run_gpu(args):
                 per[name] = k0.elapsed_time(k1) / (reps * NSETS)
 
     # ---- end-to-end through the public API from pinned host buffers ------------------------------------------------
+    dbg('per-kernel done')
     packed = not args.e2e_separate_copies
     if packed:  # one pinned buffer + one device buffer per slot: the H2D transfer of a step is a single copy
         slots = [b2.PackedBatch(wl.make_batch(2000 * rank + i), dev) for i in range(2)]
@@ -946,6 +958,7 @@ def run_gpu(args):
     e2e_ms = f0.elapsed_time(f1)
 
     # ---- max over ranks --------------------------------------------------------------------------------------------
+    dbg('e2e done')
     vals = [dev_ms, e2e_ms, host_ms, par['ms_per_step_with'] if par else 0.0]
     t = torch.tensor(vals, device=dev, dtype=torch.float64)
     if world > 1:
@@ -974,7 +987,7 @@ def run_gpu(args):
         e2e_value = units_per_step / (e2e_ms / e2e_steps * 1e-3)
         coll = 'none'
         if world > 1:
-            coll = {'fused': 'the 6 loss scalars are exchanged inside the epilogue of the step kernel (NVLink peer-memory '
+            coll = {'fused': 'the 6 loss scalars are exchanged by the step\'s own finalize launch (NVLink peer-memory '
                              'mailboxes, {sequence,value} words; mean of rank means); step j-1 is consumed in step j, one '
                              'drain kernel after the last step; no collective launch',
                     'p2p-kernel': 'one small NVLink peer-memory kernel per step (b200rl_p2p_allreduce_mean) on a forked '

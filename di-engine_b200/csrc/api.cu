@@ -112,7 +112,7 @@ extern "C" int b200rl_p2p_allreduce_mean(const float* local, const unsigned long
 extern "C" size_t b200rl_p2p_mailbox_floats(int world) { return (size_t)2 * world * b200rl::P2P_ENTRY; }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The exchange fused into the epilogue of the one-launch learner step (common.cuh: grid_finalize_fx) publishes the loss
+// The exchange fused into the loss finalisation of the one-launch learner step (common.cuh: p2p_exchange_value) publishes the loss
 // scalars of launch q and consumes those of launch q-1; after the last step of a loop this small kernel consumes the final
 // launch's entries: out_mean[k] = mean over ranks of the last launch's out[k].  Mailbox layout: [2 slots][world][8] 64-bit
 // words {sequence, value}; b200rl_p2p_mailbox_floats(world) floats hold exactly that.
@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(32) p2p_drain_kernel(const unsigned long long*
     if (k >= n) return;
     const unsigned int q = seq[k];
     if (q == 0u) return;
-    FxArgs fa{};
-    fa.mailboxes = mailboxes; fa.rank = rank; fa.world = world;
-    out_mean[k] = p2p_consume_mean(fa, k, q);
+    XchgArgs x{};
+    x.mailboxes = mailboxes; x.rank = rank; x.world = world;
+    out_mean[k] = p2p_consume_mean(x, k, q);
 }
 }  // namespace b200rl
 

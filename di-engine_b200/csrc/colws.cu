@@ -58,8 +58,7 @@ __host__ __device__ inline int cw_stage_bytes(int N, bool has_pre, bool has_w) {
 }
 
 template <int NC, bool GRADS>
-__global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, float* ws, int n_stages, FxArgs fx,
-                                                                   int use_fx) {
+__global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, float* ws, int n_stages) {
     // PDL: the next kernel may start launching right away; the wait for the previous kernels' results comes after the
     // barrier set-up below (nothing before it touches global memory except the optional trace stamp): -0.2 us measured
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -316,8 +315,7 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
             item_next(it);
         }
     }
-    if (use_fx) grid_finalize_fx<6, CW_THREADS>(acc, fx);  // one atomic round trip per CTA; the last adder writes the losses
-    else grid_store_partials<6, CW_THREADS>(acc, ws);      // summed by finalize_sums_kernel
+    grid_store_partials<6, CW_THREADS>(acc, ws);  // summed by finalize_sums_kernel
 }
 
 static size_t cw_smem(int N, bool has_pre, bool has_w, int stages) {
@@ -379,22 +377,16 @@ static int launch_ws(const FusedArgs& f, float* out, float* ws, size_t ws_bytes,
     if (grid > n_tiles) grid = n_tiles;
     if (ws_bytes < WS_MIN_BYTES || (size_t)(WS_CTRL_WORDS + grid * 6) * sizeof(float) > ws_bytes)
         return B200RL_ERR_WORKSPACE;
+    (void)launch_k(kern, (int)grid, CW_THREADS, smem, st, f, ws, stages);
+    FinalizeArgs fa{};
     const double is = 1.0 / (double)a.S;
-    const double scale[6] = {is, 0.5 * is, is, a.logit_pre ? is : 0.0, is, is};
-    const bool use_fx = fx_finalize_enabled() && grid <= 511;
-    if (f.x_mailboxes && !use_fx) return B200RL_ERR_ARG;  // the exchange rides in the in-kernel epilogue
-    FxArgs fx{};
-    for (int k = 0; k < 6; ++k) fx.scale[k] = scale[k];
-    fx.acc = reinterpret_cast<unsigned long long*>(ws + WS_FX_OFF_WORDS);
-    fx.out = out;
-    fx.mailboxes = f.x_mailboxes; fx.seq = f.x_seq; fx.out_mean = f.x_out_mean; fx.rank = f.x_rank; fx.world = f.x_world;
-    (void)launch_k(kern, (int)grid, CW_THREADS, smem, st, f, ws, stages, fx, use_fx ? 1 : 0);
-    if (!use_fx) {
-        FinalizeArgs fa{};
-        for (int k = 0; k < 6; ++k) fa.scale[k] = scale[k];
-        fa.k = 6; fa.n_blocks = (int)grid;
-        (void)launch_finalize(ws, out, fa, st);
-    }
+    fa.scale[0] = is; fa.scale[1] = 0.5 * is; fa.scale[2] = is; fa.scale[3] = a.logit_pre ? is : 0.0;
+    fa.scale[4] = is; fa.scale[5] = is;
+    fa.k = 6; fa.n_blocks = (int)grid;
+    // data-parallel training: the six scalars leave for the peers' mailboxes from the finalising threads themselves
+    fa.x.mailboxes = f.x_mailboxes; fa.x.seq = f.x_seq; fa.x.out_mean = f.x_out_mean; fa.x.rank = f.x_rank;
+    fa.x.world = f.x_world;
+    (void)launch_finalize(ws, out, fa, st);
     return (int)cudaGetLastError();
 }
 

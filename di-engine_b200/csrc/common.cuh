@@ -168,47 +168,28 @@ __device__ __forceinline__ void grid_store_partials(float (&v)[K], float* ws) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// In-kernel grid reduction with ONE atomic round trip per CTA -- no ticket, no dependent finalize launch (a dependent tiny
-// launch costs ~1.5 us on B200 even with PDL; the ticket scheme of grid_sum costs the big streaming kernels three serial
-// L2 round trips behind their store traffic).
-//
-// Every sum k owns two packed 64-bit accumulators in the workspace.  A CTA turns its partial sum, already scaled (double),
-// into 128-bit fixed point c = hi + lo*2^-40 and adds   word0 += lo<<9 | 1,   word1 += hi<<18 | poison<<9 | 1   with two
-// returning atomics in flight together.  The low 9 bits count the CTAs that have added (grid <= 511): the CTA whose add to
-// word0 returns count == grid-1 knows that word0 is complete and equal to (returned + own); it takes word1 the same way (or,
-// if another CTA's add to word1 is still in flight -- two CTAs finishing within one round trip of each other -- polls it
-// until its count is complete), converts, writes out[k] and resets both words for the next launch.  Integer addition is
-// associative, so the result is bit-identical from run to run whatever the order of arrival; resolution 2^-40 absolute on
-// the scaled sum, range |CTA contribution| < 2^36 (non-finite or larger contributions are counted in the "poison" field and
-// the result is NaN, as a float sum that met an inf/NaN would be).
-//
-// Optional data-parallel exchange fused into the same epilogue (mean of the rank means,
-// ding/utils/pytorch_ddp_dist_helper.py:38-47): the thread that finalises sum k first CONSUMES the previous launch's values
-// of all ranks from its own mailbox (they have had a whole step to arrive over NVLink) into out_mean[k], then stores
+// Data-parallel exchange of the loss scalars, fused into finalize_sums_kernel (mean of the rank means,
+// ding/utils/pytorch_ddp_dist_helper.py:38-47).  The thread that writes out[k] first CONSUMES the previous launch's values of
+// all ranks from its own mailbox (they have had a whole step to arrive over NVLink) into out_mean[k], then stores
 // {sequence, value} as ONE 8-byte word into every peer's mailbox (peer-mapped symmetric memory).  Value and tag travel in a
 // single store, so no flag ordering is needed; consume-before-publish makes the two alternating slots safe (a peer can only
 // overwrite slot s after it has seen this rank's newer entry, which is written after this rank consumed slot s).
+// No extra launch, no collective call, no kernel that only waits: the exchange of step j overlaps step j+1.
+//
+// (Measured and rejected, profiles/r02_fx_finalize.md: summing the partials INSIDE the streaming kernel with one returning
+// atomic round trip per CTA on packed fixed-point accumulators -- bit-reproducible and one launch fewer, but the atomics
+// return only after the SM's store traffic has drained: kernel 15.8 -> 16.9 us, step 17.3 -> 18.9 us.)
 // ---------------------------------------------------------------------------------------------------------------
 #define WS_PARTIAL_LIMIT_WORDS 256000  // per-CTA partial sums of every kernel stay below this word of the workspace
-#define WS_FX_OFF_WORDS 257024         // 16 packed u64 accumulators (zero between launches)
-constexpr int FX_MAX_K = 8;
 constexpr int P2P_SLOT_VALS = 8;       // u64 entries per (slot, rank) in an exchange mailbox
 
-struct FxArgs {
-    double scale[FX_MAX_K];            // out[k] = sum_k * scale[k]
-    unsigned long long* acc;           // 2 * K packed words inside the workspace
-    float* out;                        // K results
-    const unsigned long long* mailboxes;  // nullable: device array [world] of mailbox base addresses (exchange)
-    unsigned int* seq;                 // exchange: K sequence counters (device, zero-initialised, owned by the exchange)
-    float* out_mean;                   // exchange: K values = mean over ranks of the PREVIOUS launch's out[k]
+struct XchgArgs {
+    const unsigned long long* mailboxes;  // nullable: device array [world] of mailbox base addresses as seen from this rank
+    unsigned int* seq;                    // 8 sequence counters (device, zero-initialised, owned by the exchange)
+    float* out_mean;                      // 8 values = mean over ranks of the PREVIOUS launch's out[k]
     int rank, world;
 };
 
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -219,82 +200,29 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsign
 }
 
 // consume the entries tagged `q` of every rank for value k from the local mailbox; mean in rank order (deterministic)
-__device__ __forceinline__ float p2p_consume_mean(const FxArgs& fa, int k, unsigned int q) {
+__device__ __forceinline__ float p2p_consume_mean(const XchgArgs& x, int k, unsigned int q) {
     const unsigned long long* mine =
-        reinterpret_cast<const unsigned long long*>(fa.mailboxes[fa.rank]) + (size_t)(q & 1u) * fa.world * P2P_SLOT_VALS;
+        reinterpret_cast<const unsigned long long*>(x.mailboxes[x.rank]) + (size_t)(q & 1u) * x.world * P2P_SLOT_VALS;
     float acc = 0.f;
-    for (int r = 0; r < fa.world; ++r) {
+    for (int r = 0; r < x.world; ++r) {
         unsigned long long w;
         while ((unsigned int)((w = ld_relaxed_sys_u64(mine + (size_t)r * P2P_SLOT_VALS + k)) >> 32) != q) __nanosleep(32);
         acc += __uint_as_float((unsigned int)w);
     }
-    return acc / (float)fa.world;
+    return acc / (float)x.world;
 }
 
-template <int K, int NT>
-__device__ __forceinline__ void grid_finalize_fx(float (&v)[K], const FxArgs& fa) {
-    static_assert(K <= FX_MAX_K, "K");
-    __shared__ float s_fx[K][NT / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        float r = warp_sum(v[k]);
-        if (lane == 0) s_fx[k][wid] = r;
+// thread k of the finalising CTA, after it has produced res = out[k]
+__device__ __forceinline__ void p2p_exchange_value(const XchgArgs& x, int k, float res) {
+    const unsigned int q = x.seq[k] + 1u;  // only the thread that owns value k touches seq[k]
+    if (q > 1u) x.out_mean[k] = p2p_consume_mean(x, k, q - 1u);
+    const unsigned long long word = ((unsigned long long)q << 32) | (unsigned long long)__float_as_uint(res);
+    for (int p = 0; p < x.world; ++p) {
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(x.mailboxes[p]) +
+                                  ((size_t)(q & 1u) * x.world + x.rank) * P2P_SLOT_VALS + k;
+        st_relaxed_sys_u64(dst, word);
     }
-    __syncthreads();
-    if (threadIdx.x >= K) return;
-    const int k = threadIdx.x;
-    float r = 0.f;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) r += s_fx[k][w];
-    double sc = 0.0;  // selects instead of a dynamic index: indexing kernel parameters forces a local-memory copy of them
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-        if (k == j) sc = fa.scale[j];
-    const double c = (double)r * sc;
-    const bool bad = !(fabs(c) < 68719476736.0);  // 2^36; also catches NaN
-    long long hi = 0;
-    unsigned long long lo = 0;
-    if (!bad) {
-        const double fl = floor(c);
-        hi = (long long)fl;
-        lo = (unsigned long long)((c - fl) * 1099511627776.0);  // (c - floor c) is exact; 2^40
-    }
-    const unsigned long long w0 = (lo << 9) + 1ull;
-    const unsigned long long w1 = ((unsigned long long)hi << 18) + (bad ? (1ull << 9) : 0ull) + 1ull;
-    unsigned long long* a0 = fa.acc + 2 * k;
-    const unsigned long long old0 = atomicAdd(a0, w0);
-    const unsigned long long old1 = atomicAdd(a0 + 1, w1);
-    if ((unsigned int)(old0 & 511ull) != gridDim.x - 1) return;
-    const unsigned long long t0 = old0 + w0;
-    unsigned long long t1 = old1 + w1;
-    while ((unsigned int)(t1 & 511ull) != gridDim.x) t1 = ld_relaxed_gpu_u64(a0 + 1);
-    const unsigned int poison = (unsigned int)(t1 >> 9) & 511u;
-    const double tot = (double)((long long)t1 >> 18) + (double)(t0 >> 9) * (1.0 / 1099511627776.0);
-    const float res = poison ? __int_as_float(0x7fc00000) : (float)tot;
-    fa.out[k] = res;
-    a0[0] = 0ull;  // every CTA of this launch has added; the next launch adds only after this one has completed
-    a0[1] = 0ull;
-    if (fa.mailboxes) {
-        const unsigned int q = fa.seq[k] + 1u;  // only the finalising thread of sum k touches seq[k]
-        if (q > 1u) fa.out_mean[k] = p2p_consume_mean(fa, k, q - 1u);
-        const unsigned long long word = ((unsigned long long)q << 32) | (unsigned long long)__float_as_uint(res);
-        for (int p = 0; p < fa.world; ++p) {
-            unsigned long long* dst = reinterpret_cast<unsigned long long*>(fa.mailboxes[p]) +
-                                      ((size_t)(q & 1u) * fa.world + fa.rank) * P2P_SLOT_VALS + k;
-            st_relaxed_sys_u64(dst, word);
-        }
-        fa.seq[k] = q;
-    }
-}
-
-static inline bool fx_finalize_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("B200RL_FX_FINALIZE");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
+    x.seq[k] = q;
 }
 
 struct FinalizeArgs {
@@ -303,6 +231,7 @@ struct FinalizeArgs {
     int n_blocks;        // partial rows
     int clear_ctrl_from, clear_ctrl_n;  // control words [from, from+n) to zero
     int clear_tail_off, clear_tail_n;   // workspace words [off, off+n) to zero (scheduling counters)
+    XchgArgs x;                         // optional data-parallel exchange of the K results (x.mailboxes != null)
 };
 
 static __global__ void __launch_bounds__(256) finalize_sums_kernel(const float* __restrict__ ws, float* __restrict__ out,
@@ -333,7 +262,9 @@ static __global__ void __launch_bounds__(256) finalize_sums_kernel(const float* 
         double r = 0.0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) r += s_acc[threadIdx.x][w];
-        out[threadIdx.x] = (float)(r * fa.scale[threadIdx.x]);
+        const float res = (float)(r * fa.scale[threadIdx.x]);
+        out[threadIdx.x] = res;
+        if (fa.x.mailboxes) p2p_exchange_value(fa.x, threadIdx.x, res);
     }
     unsigned int* wsu = reinterpret_cast<unsigned int*>(ws_rw);
     for (int i = threadIdx.x; i < fa.clear_ctrl_n; i += 256) wsu[fa.clear_ctrl_from + i] = 0u;

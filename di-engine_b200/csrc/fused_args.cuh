@@ -16,7 +16,7 @@ struct FusedArgs {
     float gamma, gl;
     int mask_inplace;
     int trace;
-    // optional data-parallel exchange of the six loss scalars in the kernel's epilogue (colws.cu only; common.cuh FxArgs)
+    // optional data-parallel exchange of the six loss scalars, fused into the step's finalize launch (colws.cu; common.cuh)
     const unsigned long long* x_mailboxes;
     unsigned int* x_seq;
     float* x_out_mean;

@@ -119,8 +119,8 @@ class P2PLossAllReduce:
 
 
 class FusedLossExchange:
-    """State of the exchange that rides in the epilogue of the one-launch learner step (``b200rl_gae_ppo_fwd_grad_dp``,
-    csrc/common.cuh ``grid_finalize_fx``): the thread that finalises a loss sum stores ``{sequence, value}`` as one 8-byte
+    """State of the exchange that rides in the loss-finalisation launch of the one-launch learner step
+    (``b200rl_gae_ppo_fwd_grad_dp``, csrc/common.cuh ``p2p_exchange_value``): the thread that writes a loss stores ``{sequence, value}`` as one 8-byte
     word into every peer's mailbox over NVLink and consumes the previous launch's values of all ranks -- no collective call,
     no extra launch, no forked graph branch.  ``out_mean`` holds the mean over ranks of the PREVIOUS step's six loss scalars
     (the exchange of step j overlaps step j+1); ``drain()`` after the last step delivers the final step's mean.

@@ -240,7 +240,7 @@ B200RL_API int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, co
                             const float* g_expected, float* g_used, float* adv, float* out, float* grad_logit_new,
                             float* grad_value_new, float* workspace, size_t workspace_bytes, void* stream);
 /* The same step in data-parallel training (B sharded across ranks): the six loss scalars out[0..5] are
- * exchanged INSIDE the kernel's epilogue -- no second launch, no collective call.  The thread that finalises a loss sum
+ * exchanged by the step's own loss-finalisation launch -- no extra launch, no collective call.  The thread that writes out[k]
  * stores {sequence, value} as one 8-byte word into every peer's mailbox over NVLink (peer-mapped symmetric memory;
  * mailbox_ptrs_dev: device array of `world` mailbox base addresses as seen from THIS process, each
  * b200rl_p2p_mailbox_floats(world) floats, zero-initialised) and first consumes the PREVIOUS launch's values of all ranks
