@@ -810,22 +810,23 @@ def run_gpu(args):
         main.synchronize()
         barrier()
 
-        # warm-up + pre-heat: ~0.25 s of the same steps (untimed) so SM/memory clocks are in steady state -- one step is far
-        # shorter than the clock governor's reaction time.  FIXED counts: with an exchange in the graph every rank must
-        # launch exactly the same number of steps.
-        dbg('graphs captured')
-        for _ in range(max(1, (W + 249) // 250)):
-            graph_warm.replay()
+        # pre-heat: ~0.25 s of the same steps (untimed) so SM/memory clocks are in steady state -- one step is far shorter
+        # than the clock governor's reaction time.  FIXED counts: with an exchange in the graph every rank must launch exactly
+        # the same number of steps.
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()  # spawned before the pre-heat so that the process start-up does not leave the GPU idle later
         for _ in range(60):
             graph_warm.replay()
         main.synchronize()
-        barrier()
         dbg('preheat done')
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        # the W warm-up steps run IMMEDIATELY before the K timed steps (enqueued back to back, no idle gap: a GPU that has sat
+        # idle for a barrier runs its first tens of microseconds slower); the timed region is delimited by the two event
+        # nodes inside graph_k
+        for _ in range(max(1, (W + 249) // 250)):
+            graph_warm.replay()
         h0.record(main)
         graph_k.replay()
         h1.record(main)

@@ -337,7 +337,7 @@ static int launch_col(const FusedArgs& f, float* out, float* ws, size_t ws_bytes
     long long grid = (long long)sm_count * per_sm;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
-    if (ws_bytes < WS_MIN_BYTES || (size_t)(WS_CTRL_WORDS + grid * 6) * sizeof(float) > ws_bytes)
+    if (ws_bytes < WS_MIN_BYTES || !ws_partials_fit((long long)(grid * 6), ws_bytes))
         return B200RL_ERR_WORKSPACE;
     (void)launch_k(kern, (int)grid, CT_THREADS, smem, st, f, ws);
     FinalizeArgs fa{};

@@ -441,7 +441,7 @@ static int launch_tma(const FusedArgs& f, float* out, float* ws, size_t ws_bytes
     const long long n_tiles = (f.B + TM_TC - 1) / TM_TC;
     long long grid = (long long)sm_count * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    if (ws_bytes < WS_MIN_BYTES || (size_t)(WS_CTRL_WORDS + grid * 6) * sizeof(float) > ws_bytes)
+    if (ws_bytes < WS_MIN_BYTES || !ws_partials_fit((long long)(grid * 6), ws_bytes))
         return B200RL_ERR_WORKSPACE;
     ColMaps m;
     const long long T = f.T, B = f.B;

@@ -143,6 +143,70 @@ __device__ __forceinline__ bool grid_sum(float (&v)[K], double (&tot)[K], float*
     return true;
 }
 
+// Grid reduction with ONE atomic round trip per CTA for the SMALL, latency-bound kernels (q-n-step, C51, ...): no ticket, no
+// fence, no second read -- and nothing that relies on when another CTA's plain stores become visible.
+// Every sum k owns two packed 64-bit accumulators in the workspace.  A CTA turns its partial sum (double) into 128-bit fixed
+// point c = hi + lo*2^-40 and adds   word0 += lo<<9 | 1,   word1 += hi<<18 | poison<<9 | 1   with two returning atomics in
+// flight together.  The low 9 bits count the CTAs that have added (grid <= 511): the CTA whose add to word0 returns
+// count == grid-1 knows that word0 is complete and equal to (returned + own); it takes word1 the same way (or, if another
+// CTA's add to word1 is still in flight, polls it until its count is complete), calls fin(k, total) and resets both words for
+// the next launch.  Integer addition is associative: the result is bit-identical from run to run whatever the order of
+// arrival.  Resolution 2^-40 absolute, |CTA partial| < 2^36 (larger / non-finite partials are counted in the poison field and
+// the total is NaN).  A one-CTA grid skips the atomics.  (In the big streaming kernels the same scheme LOSES to a dependent
+// finalize launch -- the atomics return only after the SM's store traffic has drained; profiles/r02_fx_finalize.md.)
+#define WS_FX_OFF_WORDS 257024  // 16 packed u64 accumulators (zero between launches), above every kernel's partial sums
+constexpr int FX_MAX_K = 8;
+constexpr unsigned int FX_MAX_GRID = 511;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int K, int NT, class Fin>
+__device__ __forceinline__ void grid_sum_fx(float (&v)[K], float* ws, Fin fin) {
+    static_assert(K <= FX_MAX_K, "K");
+    __shared__ float s_fx[K][NT / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float r = warp_sum(v[k]);
+        if (lane == 0) s_fx[k][wid] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x >= K) return;
+    const int k = threadIdx.x;
+    double c = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) c += (double)s_fx[k][w];
+    if (gridDim.x == 1) {
+        fin(k, c);
+        return;
+    }
+    const bool bad = !(fabs(c) < 68719476736.0);  // 2^36; also catches NaN
+    long long hi = 0;
+    unsigned long long lo = 0;
+    if (!bad) {
+        const double fl = floor(c);
+        hi = (long long)fl;
+        lo = (unsigned long long)((c - fl) * 1099511627776.0);  // (c - floor c) is exact; 2^40
+    }
+    const unsigned long long w0 = (lo << 9) + 1ull;
+    const unsigned long long w1 = ((unsigned long long)hi << 18) + (bad ? (1ull << 9) : 0ull) + 1ull;
+    unsigned long long* a0 = reinterpret_cast<unsigned long long*>(ws + WS_FX_OFF_WORDS) + 2 * k;
+    const unsigned long long old0 = atomicAdd(a0, w0);
+    const unsigned long long old1 = atomicAdd(a0 + 1, w1);
+    if ((unsigned int)(old0 & 511ull) != gridDim.x - 1) return;
+    const unsigned long long t0 = old0 + w0;
+    unsigned long long t1 = old1 + w1;
+    while ((unsigned int)(t1 & 511ull) != gridDim.x) t1 = ld_relaxed_gpu_u64(a0 + 1);
+    const unsigned int poison = (unsigned int)(t1 >> 9) & 511u;
+    const double tot = (double)((long long)t1 >> 18) + (double)(t0 >> 9) * (1.0 / 1099511627776.0);
+    a0[0] = 0ull;  // every CTA of this launch has added; the next launch adds only after this one has completed
+    a0[1] = 0ull;
+    fin(k, poison ? (double)__int_as_float(0x7fc00000) : tot);
+}
+
 // Two-launch variant of the grid reduction for the big streaming kernels: every CTA just stores its K partial sums (no
 // atomics, no fence, no ticket -- kernel completion publishes them) and finalize_sums_kernel, a single small CTA launched
 // right behind, adds them in a fixed order (deterministic), scales, writes the results and clears `n_clear` control
@@ -429,6 +493,12 @@ static inline int launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t
 
 static inline int launch_finalize(float* ws, float* out, const FinalizeArgs& fa, cudaStream_t st) {
     return launch_k(finalize_sums_kernel, 1, 256, 0, st, (const float*)ws, out, ws, fa);
+}
+
+// per-CTA partial sums live in workspace words [WS_CTRL_WORDS, WS_PARTIAL_LIMIT_WORDS): above them sit the packed accumulators of
+// grid_sum_fx and the scheduling counters of fused.cu, which must stay zero between launches
+static inline bool ws_partials_fit(long long n_words, size_t ws_bytes) {
+    return ws_bytes >= (size_t)WS_MIN_BYTES && (long long)WS_CTRL_WORDS + n_words <= (long long)WS_PARTIAL_LIMIT_WORDS;
 }
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -266,9 +266,7 @@ static int launch_fused(const FusedArgs& f, float* out, float* ws, size_t ws_byt
     long long grid = (long long)sm_count * per_sm;  // never more than can be resident (phase P spins on phase G)
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
-    if ((size_t)(WS_CTRL_WORDS + grid * 6) * sizeof(float) > ws_bytes - WS_CHUNK_CTR_WORDS * sizeof(float) ||
-        ws_bytes < WS_MIN_BYTES)
-        return B200RL_ERR_WORKSPACE;
+    if (!ws_partials_fit((long long)(grid * 6), ws_bytes)) return B200RL_ERR_WORKSPACE;
     (void)launch_k(kern, (int)grid, PPO_THREADS, smem, st, f, out, ws);
     {
         FinalizeArgs fa{};

@@ -377,11 +377,11 @@ extern "C" int b200rl_upgo_head_fwd(const float* logit, const long long* action,
     cudaStream_t st = (cudaStream_t)stream;
     if (N > 64) {
         const int grid = div_up(TB, NT / 32);
-        if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+        if (!ws_partials_fit((long long)(grid), workspace_bytes)) return B200RL_ERR_WORKSPACE;
         (void)launch_k(upgo_fwd_kernel<NT, 32>, grid, NT, 0, st, a, workspace);
     } else {
         const int grid = div_up(TB, NT);
-        if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+        if (!ws_partials_fit((long long)(grid), workspace_bytes)) return B200RL_ERR_WORKSPACE;
         (void)launch_k(upgo_fwd_kernel<NT, 1>, grid, NT, 0, st, a, workspace);
     }
     return (int)cudaGetLastError();
@@ -772,10 +772,10 @@ extern "C" int b200rl_vtrace_fwd(const float* target_output, const float* behavi
     int rc = (int)cudaGetLastError();
     if (rc) return rc;
     if (B >= 16 * 296) {
-        if ((size_t)(WS_CTRL_WORDS + 3 * div_up(B, 16)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+        if (!ws_partials_fit((long long)(3 * div_up(B, 16)), workspace_bytes)) return B200RL_ERR_WORKSPACE;
         (void)launch_k(vtrace_scan_kernel<16, 256, 64>, div_up(B, 16), 256, 0, st, a, workspace);
     } else {
-        if ((size_t)(WS_CTRL_WORDS + 3 * div_up(B, 8)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+        if (!ws_partials_fit((long long)(3 * div_up(B, 8)), workspace_bytes)) return B200RL_ERR_WORKSPACE;
         (void)launch_k(vtrace_scan_kernel<8, 64, 64>, div_up(B, 8), 64, 0, st, a, workspace);
     }
     return (int)cudaGetLastError();

@@ -398,7 +398,7 @@ static int launch_tile(const PpoArgs& a, float* out, float* ws, size_t ws_bytes,
     // the verification launch that follows a fused forward normally exits at once: keep its grid to one CTA per SM
     long long grid = (long long)sm_count * ((WHAT == PPO_BWD && a.g_used) ? 1 : per_sm);
     if (grid > n_tiles) grid = n_tiles;
-    if (WHAT != PPO_BWD && (size_t)(WS_CTRL_WORDS + grid * 6) * sizeof(float) > ws_bytes) return B200RL_ERR_WORKSPACE;
+    if (WHAT != PPO_BWD && !ws_partials_fit((long long)(grid * 6), ws_bytes)) return B200RL_ERR_WORKSPACE;
     (void)launch_k(kern, (int)grid, PPO_THREADS, smem, st, a, out, ws);
     if (WHAT != PPO_BWD) {
         FinalizeArgs fa{};
@@ -486,7 +486,7 @@ extern "C" int b200rl_ppo_fwd(const float* logit_new, const float* logit_old, co
     const bool warp = a.N > 64;
     int grid = warp ? div_up(S, NT / 32) : div_up(S, NT);
     if (grid > 148 * 16) grid = 148 * 16;  // grid-stride kernel: the workspace need is bounded whatever S is
-    if ((size_t)(WS_CTRL_WORDS + (size_t)grid * 6) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+    if (!ws_partials_fit((long long)((size_t)grid * 6), workspace_bytes)) return B200RL_ERR_WORKSPACE;
     if (warp) (void)launch_k(ppo_fwd_kernel<NT, 2>, grid, NT, 0, st, a, out, workspace);
     else (void)launch_k(ppo_fwd_kernel<NT, 1>, grid, NT, 0, st, a, out, workspace);
     return (int)cudaGetLastError();
@@ -558,7 +558,7 @@ extern "C" int b200rl_ppo_value_fwd(const float* value_new, const float* value_o
     constexpr int NT = 256;
     long long grid = div_up(S, NT);
     if (grid > 148 * 8) grid = 148 * 8;
-    if (workspace_bytes < WS_MIN_BYTES || (size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes)
+    if (workspace_bytes < WS_MIN_BYTES || !ws_partials_fit((long long)(grid), workspace_bytes))
         return B200RL_ERR_WORKSPACE;
     (void)launch_k(ppo_value_kernel<NT>, (int)grid, NT, 0, (cudaStream_t)stream, value_new, value_old, return_, weight, S,
                    (float)clip_ratio, use_value_clip, loss, dvalue_unit, workspace);

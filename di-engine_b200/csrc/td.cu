@@ -144,6 +144,10 @@ __global__ void __launch_bounds__(NT) qntd_fwd_kernel(QntdArgs a, float* ws) {
             gq[i] = (j == s_act[rr]) ? s_coef[rr] : 0.f;
         }
     }
+    if (!a.priority && gridDim.x <= FX_MAX_GRID) {  // one atomic round trip (none for a one-CTA grid)
+        grid_sum_fx<1, NT>(acc, ws, [&](int, double t) { a.loss[0] = (float)(t / a.loss_div); });
+        return;
+    }
     double tot[1];
     const bool last = grid_sum<1, NT>(acc, tot, ws, 0);
     if (last && threadIdx.x == 0) a.loss[0] = (float)(tot[0] / a.loss_div);
@@ -273,6 +277,10 @@ __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
                 for (int j = lane; j < a.n_atom; j += 32)
                     gr[n * a.n_atom + j] = (n == sel) ? c * pj[j] / dd[j] : 0.f;
         }
+    }
+    if (gridDim.x <= FX_MAX_GRID) {
+        grid_sum_fx<1, NT>(acc, ws, [&](int, double t) { a.loss[0] = (float)(t / (double)a.R); });
+        return;
     }
     double tot[1];
     if (grid_sum<1, NT>(acc, tot, ws, 0) && threadIdx.x == 0) a.loss[0] = (float)(tot[0] / (double)a.R);
@@ -593,9 +601,17 @@ extern "C" int b200rl_qntd_fwd(const float* q, const float* next_n_q, const long
     a.prio_div = (float)((double)seq_len + 1e-8);
     a.loss = loss; a.td_err = td_error_per_sample; a.dcrit = dcrit_saved; a.target = target_out;
     a.grad_unit = grad_q_unit; a.priority = priority_out;
+    if (workspace_bytes < WS_MIN_BYTES) return B200RL_ERR_WORKSPACE;
+    if (S <= 1024 && !priority_out) {  // the usual replay-buffer batch: ONE CTA, no grid reduction at all
+        const int nt = S <= 256 ? 256 : (S <= 512 ? 512 : 1024);
+        if (nt == 256) (void)launch_k(qntd_fwd_kernel<256>, 1, 256, 0, (cudaStream_t)stream, a, workspace);
+        else if (nt == 512) (void)launch_k(qntd_fwd_kernel<512>, 1, 512, 0, (cudaStream_t)stream, a, workspace);
+        else (void)launch_k(qntd_fwd_kernel<1024>, 1, 1024, 0, (cudaStream_t)stream, a, workspace);
+        return (int)cudaGetLastError();
+    }
     constexpr int NT = 128;
     const int grid = div_up(S, NT);
-    if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+    if ((size_t)(WS_CTRL_WORDS + grid) > WS_PARTIAL_LIMIT_WORDS) return B200RL_ERR_WORKSPACE;
     (void)launch_k(qntd_fwd_kernel<NT>, grid, NT, 0, (cudaStream_t)stream, a, workspace);
     return (int)cudaGetLastError();
 }
@@ -629,9 +645,16 @@ extern "C" int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, cons
     a.v_min = (float)v_min; a.v_max = (float)v_max; a.delta_z = (float)((v_max - v_min) / (double)(n_atom - 1));
     a.loss = loss; a.td_err = td_error_per_sample; a.proj = proj_saved; a.bad_flag = bad_flag;
     a.grad_unit = grad_dist_unit;
+    if (workspace_bytes < WS_MIN_BYTES) return B200RL_ERR_WORKSPACE;
+    if (a.R <= 16 * 511 && n_atom <= 384) {  // 16 rows per CTA: few enough CTAs for the one-round-trip reduction
+        constexpr int NT = 512;
+        const size_t sm = (size_t)(NT / 32) * n_atom * sizeof(float);
+        (void)launch_k(dntd_fwd_kernel<NT>, div_up(a.R, NT / 32), NT, sm, (cudaStream_t)stream, a, workspace);
+        return (int)cudaGetLastError();
+    }
     constexpr int NT = 128;
     const int grid = div_up(a.R, NT / 32);
-    if ((size_t)(WS_CTRL_WORDS + grid) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+    if ((size_t)(WS_CTRL_WORDS + grid) > WS_PARTIAL_LIMIT_WORDS) return B200RL_ERR_WORKSPACE;
     const size_t sm = (size_t)(NT / 32) * n_atom * sizeof(float);
     if (sm > 48 * 1024) return B200RL_ERR_ARG;
     (void)launch_k(dntd_fwd_kernel<NT>, grid, NT, sm, (cudaStream_t)stream, a, workspace);
@@ -691,7 +714,7 @@ extern "C" int b200rl_td_lambda_fwd(const float* value, const float* reward, con
     LamArgs a{};
     a.value = value; a.reward = reward; a.weight = weight; a.gamma = (float)gamma; a.lambda = (float)lambda_;
     a.T = T; a.B = B; a.loss = loss; a.dvalue = dvalue_saved;
-    if ((size_t)(WS_CTRL_WORDS + div_up(B, 8)) * sizeof(float) > workspace_bytes) return B200RL_ERR_WORKSPACE;
+    if (!ws_partials_fit((long long)(div_up(B, 8)), workspace_bytes)) return B200RL_ERR_WORKSPACE;
     return launch_lambda<0, 1>(a, workspace, (cudaStream_t)stream);
 }
 

@@ -454,7 +454,7 @@ static int launch_vtws(const VtFusedArgs& a, float* out, float* ws, size_t ws_by
     const long long n_tiles = (a.B + TC - 1) / TC;
     long long grid = (long long)sm_count * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    if (ws_bytes < WS_MIN_BYTES || (size_t)(WS_CTRL_WORDS + grid * 3) * sizeof(float) > ws_bytes)
+    if (ws_bytes < WS_MIN_BYTES || !ws_partials_fit((long long)(grid * 3), ws_bytes))
         return B200RL_ERR_WORKSPACE;
     (void)launch_k(kern, (int)grid, VW_THREADS, smem, st, a, ws, stages);
     if (!a.verify) {
