@@ -753,7 +753,7 @@ def run_gpu(args):
     dbg('check done')
     bucket = torch.zeros(VAC_PARAMS, device=dev) if world > 1 else None
 
-    def record_steps(n, with_param_allreduce=False):
+    def record_steps(n):
         """n steps over the rotated buffer sets on the current (capturing) stream"""
         for i in range(n):
             j = i % NSETS
@@ -764,14 +764,12 @@ def run_gpu(args):
             sets[j]()
             if exchange in ('p2p-kernel', 'nccl') and i > 0:
                 main.wait_stream(side)
-            if with_param_allreduce:
-                dist.all_reduce(bucket)
         if exchange in ('p2p-kernel', 'nccl'):
             exchange_losses((n - 1) % NSETS)
         elif exchange == 'fused':
             fused_x.drain()
 
-    def timed_graph(n, with_param_allreduce=False):
+    def timed_graph(n):
         """ONE graph: [rank alignment] e0 | n steps | e1 -- the two events are nodes of the graph (external events), so their
         difference is the device time of exactly n steps, free of the host's launch latency"""
         e0 = torch.cuda.Event(enable_timing=True, external=True)
@@ -781,7 +779,7 @@ def run_gpu(args):
             if world > 1 and align is not None:
                 align.reduce(align_src)  # device-side rank alignment: every rank leaves within one NVLink flag round
             e0.record(main)
-            record_steps(n, with_param_allreduce)
+            record_steps(n)
             e1.record(main)
         return g, e0, e1
 
@@ -855,17 +853,21 @@ def run_gpu(args):
                 a1.record(main)
                 main.synchronize()
                 ar_us = a0.elapsed_time(a1) * 1e3 / 50
-                gp, p0, p1 = timed_graph(K, with_param_allreduce=True)
+                # eager launches (no NCCL inside a CUDA graph: an eager collective after a captured one has been seen to hang)
+                n_par = max(20, min(K, 200))
+                barrier()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record(main)
+                for i in range(n_par):
+                    sets[i % NSETS]()
+                    dist.all_reduce(bucket)
+                if exchange == 'fused':
+                    fused_x.drain()
+                p1.record(main)
                 main.synchronize()
                 barrier()
-                gp.replay()
-                main.synchronize()
-                barrier()
-                gp.replay()
-                main.synchronize()
-                barrier()
-                par = dict(bytes=VAC_PARAMS * 4, nccl_allreduce_us_alone=ar_us, ms_per_step_with=p0.elapsed_time(p1) / K)
-                del gp
+                par = dict(bytes=VAC_PARAMS * 4, nccl_allreduce_us_alone=ar_us, ms_per_step_with=p0.elapsed_time(p1) / n_par,
+                           steps=n_par, launch='eager')
             except Exception as e:  # never let the secondary figure break the benchmark
                 if rank == 0:
                     print('bench: param all-reduce leg skipped (%s)' % e, file=sys.stderr)
@@ -1027,7 +1029,7 @@ def run_gpu(args):
         if par:
             line['param_allreduce'] = dict(par, ms_per_step_with=par_ms,
                                            note='the step followed by an NCCL all-reduce of a %d-float dummy gradient '
-                                                'bucket (Atari VAC net) on the same stream' % VAC_PARAMS)
+                                                'bucket (Atari VAC net) on the same stream, eager launches' % VAC_PARAMS)
         print(json.dumps(line), flush=True)
     if world > 1:
         # graphs that captured NCCL work must be gone before the communicator is torn down; then leave without waiting on

@@ -112,28 +112,29 @@ extern "C" int b200rl_p2p_allreduce_mean(const float* local, const unsigned long
 extern "C" size_t b200rl_p2p_mailbox_floats(int world) { return (size_t)2 * world * b200rl::P2P_ENTRY; }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The exchange fused into the loss finalisation of the one-launch learner step (common.cuh: p2p_exchange_value) publishes the loss
-// scalars of launch q and consumes those of launch q-1; after the last step of a loop this small kernel consumes the final
-// launch's entries: out_mean[k] = mean over ranks of the last launch's out[k].  Mailbox layout: [2 slots][world][8] 64-bit
-// words {sequence, value}; b200rl_p2p_mailbox_floats(world) floats hold exactly that.
+// Tail of the exchange that rides on the learner step's own launches (common.cuh: p2p_stage_and_consume /
+// p2p_publish_staged): the last step's values are staged but not yet published (no next step), so this small kernel
+// publishes them and consumes the entries of all ranks: out_mean[k] = mean over ranks of the last step's out[k].
+// Mailbox layout: [2 slots][world][8] 64-bit words {tag, value}; b200rl_p2p_mailbox_floats(world) floats hold exactly that.
 // ---------------------------------------------------------------------------------------------------------------
 namespace b200rl {
 __global__ void __launch_bounds__(32) p2p_drain_kernel(const unsigned long long* __restrict__ mailboxes, int rank, int world,
-                                                       int n, const unsigned int* __restrict__ seq,
-                                                       float* __restrict__ out_mean) {
+                                                       int n, unsigned int* __restrict__ state, float* __restrict__ out_mean) {
     pdl_prologue();
     const int k = threadIdx.x;
     if (k >= n) return;
-    const unsigned int q = seq[k];
+    XchgArgs x{mailboxes, state, out_mean, rank, world};
+    const unsigned int q = state[k];
     if (q == 0u) return;
-    XchgArgs x{};
-    x.mailboxes = mailboxes; x.rank = rank; x.world = world;
-    out_mean[k] = p2p_consume_mean(x, k, q);
+    p2p_publish_staged(x, k);
+    float acc = 0.f;
+    for (int r = 0; r < world; ++r) acc += p2p_poll_entry(x, k, r, q);
+    out_mean[k] = acc / (float)world;
 }
 }  // namespace b200rl
 
 extern "C" int b200rl_p2p_drain_mean(const unsigned long long* mailbox_ptrs_dev, int rank, int world, int n,
-                                     const unsigned int* seq_dev, float* out_mean, void* stream) {
+                                     unsigned int* seq_dev, float* out_mean, void* stream) {
     if (!mailbox_ptrs_dev || !seq_dev || !out_mean || n < 1 || n > b200rl::P2P_SLOT_VALS || world < 1 || world > 64 ||
         rank < 0 || rank >= world)
         return B200RL_ERR_ARG;

@@ -232,13 +232,18 @@ __device__ __forceinline__ void grid_store_partials(float (&v)[K], float* ws) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Data-parallel exchange of the loss scalars, fused into finalize_sums_kernel (mean of the rank means,
-// ding/utils/pytorch_ddp_dist_helper.py:38-47).  The thread that writes out[k] first CONSUMES the previous launch's values of
-// all ranks from its own mailbox (they have had a whole step to arrive over NVLink) into out_mean[k], then stores
-// {sequence, value} as ONE 8-byte word into every peer's mailbox (peer-mapped symmetric memory).  Value and tag travel in a
-// single store, so no flag ordering is needed; consume-before-publish makes the two alternating slots safe (a peer can only
-// overwrite slot s after it has seen this rank's newer entry, which is written after this rank consumed slot s).
-// No extra launch, no collective call, no kernel that only waits: the exchange of step j overlaps step j+1.
+// Data-parallel exchange of the loss scalars without a launch of its own (mean of the rank means,
+// ding/utils/pytorch_ddp_dist_helper.py:38-47), software-pipelined over the launches the learner step makes anyway:
+//   finalize_sums of step q   (thread k, after writing out[k])  stages {q, out[k]} in LOCAL memory and consumes the entries
+//                              tagged q-1 of all ranks from its own mailbox into out_mean[k] (they were published ~a step ago);
+//   streaming kernel of step q+1 (first CTA, prologue)           publishes the staged {q, value} as ONE 8-byte store into every
+//                              peer's mailbox (peer-mapped symmetric memory over NVLink) and goes on with its ~14 us of work.
+// A remote store is only complete when its acknowledgement has crossed NVLink (~1.5 us): issued from the short finalize
+// launch it delayed that launch's completion and everything ordered behind it (N=2: 15.9 -> 17.5 us per step,
+// profiles/r02_scaling.md); issued at the START of the long kernel it costs nothing.  Value and tag travel in a single store,
+// so no flag ordering is needed.  Two mailbox slots alternate by tag parity: tag q+2 is published by step q+3's kernel, after
+// this rank's finalize q+2 consumed tag q+1 of every peer, which each peer published after consuming tag q -- so a slot is
+// never overwritten before every peer has read it.  After the last step b200rl_p2p_drain_mean publishes and consumes the tail.
 //
 // (Measured and rejected, profiles/r02_fx_finalize.md: summing the partials INSIDE the streaming kernel with one returning
 // atomic round trip per CTA on packed fixed-point accumulators -- bit-reproducible and one launch fewer, but the atomics
@@ -249,8 +254,8 @@ constexpr int P2P_SLOT_VALS = 8;       // u64 entries per (slot, rank) in an exc
 
 struct XchgArgs {
     const unsigned long long* mailboxes;  // nullable: device array [world] of mailbox base addresses as seen from this rank
-    unsigned int* seq;                    // 8 sequence counters (device, zero-initialised, owned by the exchange)
-    float* out_mean;                      // 8 values = mean over ranks of the PREVIOUS launch's out[k]
+    unsigned int* state;                  // 16 words owned by the exchange (zero-initialised): [0,8) tags, [8,16) staged values
+    float* out_mean;                      // 8 values = mean over ranks of the PREVIOUS step's out[k]
     int rank, world;
 };
 
@@ -263,30 +268,52 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsign
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// consume the entries tagged `q` of every rank for value k from the local mailbox; mean in rank order (deterministic)
-__device__ __forceinline__ float p2p_consume_mean(const XchgArgs& x, int k, unsigned int q) {
-    const unsigned long long* mine =
-        reinterpret_cast<const unsigned long long*>(x.mailboxes[x.rank]) + (size_t)(q & 1u) * x.world * P2P_SLOT_VALS;
-    float acc = 0.f;
-    for (int r = 0; r < x.world; ++r) {
-        unsigned long long w;
-        while ((unsigned int)((w = ld_relaxed_sys_u64(mine + (size_t)r * P2P_SLOT_VALS + k)) >> 32) != q) __nanosleep(32);
-        acc += __uint_as_float((unsigned int)w);
-    }
-    return acc / (float)x.world;
+// one entry of the local mailbox: value k of rank r tagged q (polls until it has arrived)
+__device__ __forceinline__ float p2p_poll_entry(const XchgArgs& x, int k, int r, unsigned int q) {
+    const unsigned long long* e = reinterpret_cast<const unsigned long long*>(x.mailboxes[x.rank]) +
+                                  ((size_t)(q & 1u) * x.world + r) * P2P_SLOT_VALS + k;
+    unsigned long long w;
+    while ((unsigned int)((w = ld_relaxed_sys_u64(e)) >> 32) != q) __nanosleep(32);
+    return __uint_as_float((unsigned int)w);
 }
 
-// thread k of the finalising CTA, after it has produced res = out[k]
-__device__ __forceinline__ void p2p_exchange_value(const XchgArgs& x, int k, float res) {
-    const unsigned int q = x.seq[k] + 1u;  // only the thread that owns value k touches seq[k]
-    if (q > 1u) x.out_mean[k] = p2p_consume_mean(x, k, q - 1u);
-    const unsigned long long word = ((unsigned long long)q << 32) | (unsigned long long)__float_as_uint(res);
-    for (int p = 0; p < x.world; ++p) {
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(x.mailboxes[p]) +
+// CTA-wide (all NT threads call it; res is meaningful in threads k < K): stage this step's K values and consume the previous
+// step's entries of all ranks.  The K*world mailbox reads are independent round trips to system-coherent memory (~0.7 us
+// each): one thread per (value, rank) polls its entry, then thread k adds them in rank order (deterministic).
+template <int NT>
+__device__ __forceinline__ void p2p_stage_and_consume(const XchgArgs& x, int K, float res) {
+    __shared__ float s_x[P2P_SLOT_VALS][64];
+    const int n = K * x.world;
+    for (int i = threadIdx.x; i < n; i += NT) {
+        const int k = i / x.world, r = i - k * x.world;
+        const unsigned int q = x.state[k];  // tag of the previous step (this step's is q + 1)
+        if (q >= 1u) s_x[k][r] = p2p_poll_entry(x, k, r, q);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < K) {
+        const int k = threadIdx.x;
+        const unsigned int q = x.state[k];  // only the thread that owns value k writes state[k] / state[8 + k]
+        if (q >= 1u) {
+            float acc = 0.f;
+            for (int r = 0; r < x.world; ++r) acc += s_x[k][r];
+            x.out_mean[k] = acc / (float)x.world;
+        }
+        x.state[8 + k] = __float_as_uint(res);
+        x.state[k] = q + 1u;
+    }
+}
+
+// prologue of the next long kernel: publish the staged value k to rank p's mailbox (p < 0: to every rank)
+__device__ __forceinline__ void p2p_publish_staged(const XchgArgs& x, int k, int p = -1) {
+    const unsigned int q = x.state[k];
+    if (q == 0u) return;
+    const unsigned long long word = ((unsigned long long)q << 32) | (unsigned long long)x.state[8 + k];
+    const int p0 = p < 0 ? 0 : p, p1 = p < 0 ? x.world : p + 1;
+    for (int d = p0; d < p1; ++d) {
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(x.mailboxes[d]) +
                                   ((size_t)(q & 1u) * x.world + x.rank) * P2P_SLOT_VALS + k;
         st_relaxed_sys_u64(dst, word);
     }
-    x.seq[k] = q;
 }
 
 struct FinalizeArgs {
@@ -322,14 +349,15 @@ static __global__ void __launch_bounds__(256) finalize_sums_kernel(const float* 
         if (lane == 0) s_acc[k][wid] = r;
     }
     __syncthreads();
+    float res = 0.f;
     if (threadIdx.x < K) {
         double r = 0.0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) r += s_acc[threadIdx.x][w];
-        const float res = (float)(r * fa.scale[threadIdx.x]);
+        res = (float)(r * fa.scale[threadIdx.x]);
         out[threadIdx.x] = res;
-        if (fa.x.mailboxes) p2p_exchange_value(fa.x, threadIdx.x, res);
     }
+    if (fa.x.mailboxes) p2p_stage_and_consume<256>(fa.x, K, res);  // data-parallel exchange (uniform branch)
     unsigned int* wsu = reinterpret_cast<unsigned int*>(ws_rw);
     for (int i = threadIdx.x; i < fa.clear_ctrl_n; i += 256) wsu[fa.clear_ctrl_from + i] = 0u;
     for (int i = threadIdx.x; i < fa.clear_tail_n; i += 256) wsu[fa.clear_tail_off + i] = 0u;

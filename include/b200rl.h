@@ -240,14 +240,16 @@ B200RL_API int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, co
                             const float* g_expected, float* g_used, float* adv, float* out, float* grad_logit_new,
                             float* grad_value_new, float* workspace, size_t workspace_bytes, void* stream);
 /* The same step in data-parallel training (B sharded across ranks): the six loss scalars out[0..5] are
- * exchanged by the step's own loss-finalisation launch -- no extra launch, no collective call.  The thread that writes out[k]
- * stores {sequence, value} as one 8-byte word into every peer's mailbox over NVLink (peer-mapped symmetric memory;
- * mailbox_ptrs_dev: device array of `world` mailbox base addresses as seen from THIS process, each
- * b200rl_p2p_mailbox_floats(world) floats, zero-initialised) and first consumes the PREVIOUS launch's values of all ranks
- * into out_mean[0..5] (mean of the rank means, ding/utils/pytorch_ddp_dist_helper.py:38-47) -- software pipelining: the
- * exchange of step j overlaps step j+1.  seq_dev: 8 device counters, zero-initialised, owned by this exchange; every rank
- * must make the same sequence of calls.  After the last step b200rl_p2p_drain_mean delivers the final launch's mean.
- * Requires the column-tile kernel (b200rl_gae_ppo_supported, B >= 16) and P2P access between the ranks' GPUs. */
+ * exchanged by launches the step makes anyway -- no extra launch, no collective call.  Step q's loss-finalisation launch
+ * stages {q, out[k]} locally and consumes the entries tagged q-1 of all ranks from this rank's mailbox into out_mean[0..5]
+ * (mean of the rank means, ding/utils/pytorch_ddp_dist_helper.py:38-47); step q+1's streaming kernel publishes the staged
+ * word to every peer's mailbox over NVLink in its prologue (one 8-byte store per peer and value; the acknowledgements return
+ * while the kernel streams).  So out_mean lags out by one step: the exchange of step q overlaps step q+1.
+ * mailbox_ptrs_dev: device array of `world` mailbox base addresses as seen from THIS process (peer-mapped symmetric memory),
+ * each b200rl_p2p_mailbox_floats(world) floats, zero-initialised; seq_dev: 16 32-bit device words, zero-initialised, owned
+ * by this exchange; every rank must make the same sequence of calls.  After the last step b200rl_p2p_drain_mean publishes
+ * and consumes the final step's values.  Requires the column-tile kernel (b200rl_gae_ppo_supported, B >= 16) and P2P access
+ * between the ranks' GPUs. */
 B200RL_API int b200rl_gae_ppo_fwd_grad_dp(const float* value, float* next_value, const float* reward, const float* done,
                                const float* traj_flag, long long T, long long B, double gamma, double lambda_,
                                int mask_next_value_inplace, const float* logit_new, const float* logit_old,
@@ -259,7 +261,7 @@ B200RL_API int b200rl_gae_ppo_fwd_grad_dp(const float* value, float* next_value,
                                unsigned int* seq_dev, float* out_mean, float* workspace, size_t workspace_bytes,
                                void* stream);
 B200RL_API int b200rl_p2p_drain_mean(const unsigned long long* mailbox_ptrs_dev, int rank, int world, int n,
-                          const unsigned int* seq_dev, float* out_mean, void* stream);
+                          unsigned int* seq_dev, float* out_mean, void* stream);
 /* Kernels behind the calls above.  Column tiles: a CTA owns 16 batch columns for all T and runs their scan and their
  * ppo_error rows -- no cross-CTA dependency; chosen when B >= 1024 or T*B <= 16384.  Three builds of that scheme exist:
  * csrc/colws.cu (warp-specialised loader / scanner / consumer warps on an mbarrier pipeline, cp.async copies; the default),
