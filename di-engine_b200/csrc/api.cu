@@ -112,33 +112,35 @@ extern "C" int b200rl_p2p_allreduce_mean(const float* local, const unsigned long
 extern "C" size_t b200rl_p2p_mailbox_floats(int world) { return (size_t)2 * world * b200rl::P2P_ENTRY; }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Tail of the exchange that rides on the learner step's own launches (common.cuh: p2p_stage_and_consume /
-// p2p_publish_staged): the last step's values are staged but not yet published (no next step), so this small kernel
-// publishes them and consumes the entries of all ranks: out_mean[k] = mean over ranks of the last step's out[k].
+// Tail of the exchange that rides on the learner step's own launches (common.cuh): after the last step Q its values are
+// staged but not published and tag Q-1 is published but not consumed (no next step): warp k of this small kernel consumes
+// Q-1, publishes Q and consumes Q, so that out_mean[k] = mean over ranks of the LAST step's out[k] (out_mean[8+k]: step Q-1).
 // Mailbox layout: [2 slots][world][8] 64-bit words {tag, value}; b200rl_p2p_mailbox_floats(world) floats hold exactly that.
+// The tail is idempotent for the pipeline: the next step's kernel re-publishes tag Q (same word) and re-consumes Q-1.
 // ---------------------------------------------------------------------------------------------------------------
 namespace b200rl {
-__global__ void __launch_bounds__(32) p2p_drain_kernel(const unsigned long long* __restrict__ mailboxes, int rank, int world,
-                                                       int n, unsigned int* __restrict__ state, float* __restrict__ out_mean) {
+__global__ void __launch_bounds__(256) p2p_drain_kernel(const unsigned long long* __restrict__ mailboxes, int rank, int world,
+                                                        int n, unsigned int* __restrict__ state, float* __restrict__ out_mean) {
     pdl_prologue();
-    const int k = threadIdx.x;
+    const int k = threadIdx.x >> 5;
     if (k >= n) return;
     XchgArgs x{mailboxes, state, out_mean, rank, world};
     const unsigned int q = state[k];
     if (q == 0u) return;
-    p2p_publish_staged(x, k);
-    float acc = 0.f;
-    for (int r = 0; r < world; ++r) acc += p2p_poll_entry(x, k, r, q);
-    out_mean[k] = acc / (float)world;
+    if (q >= 2u && state[16 + k] < q - 1u) p2p_consume_warp(x, k, q - 1u);
+    __syncwarp();
+    p2p_publish_warp(x, k);
+    __syncwarp();
+    if (state[16 + k] < q) p2p_consume_warp(x, k, q);
 }
 }  // namespace b200rl
 
 extern "C" int b200rl_p2p_drain_mean(const unsigned long long* mailbox_ptrs_dev, int rank, int world, int n,
                                      unsigned int* seq_dev, float* out_mean, void* stream) {
-    if (!mailbox_ptrs_dev || !seq_dev || !out_mean || n < 1 || n > b200rl::P2P_SLOT_VALS || world < 1 || world > 64 ||
+    if (!mailbox_ptrs_dev || !seq_dev || !out_mean || n < 1 || n > b200rl::P2P_SLOT_VALS || world < 1 || world > 32 ||
         rank < 0 || rank >= world)
         return B200RL_ERR_ARG;
-    (void)b200rl::launch_k(b200rl::p2p_drain_kernel, 1, 32, 0, (cudaStream_t)stream, mailbox_ptrs_dev, rank, world, n,
+    (void)b200rl::launch_k(b200rl::p2p_drain_kernel, 1, 256, 0, (cudaStream_t)stream, mailbox_ptrs_dev, rank, world, n,
                            seq_dev, out_mean);
     return (int)cudaGetLastError();
 }

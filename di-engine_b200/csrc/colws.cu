@@ -107,12 +107,12 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
-    // data-parallel training: the previous step's loss scalars (staged by its finalize launch) leave for the peers' mailboxes
-    // now -- the NVLink store acknowledgements return while this kernel streams (common.cuh)
-    if (f.x_mailboxes && blockIdx.x == 0) {
+    // data-parallel training: consumer warp k of the first CTA consumes the loss scalar k of two steps ago from its mailbox and
+    // publishes the previous step's (staged by its finalize launch) to the peers -- while it would otherwise just wait for its
+    // first chunk; the NVLink acknowledgements return while this kernel streams (common.cuh)
+    if (f.x_mailboxes && blockIdx.x == 0 && wid < 6) {
         XchgArgs x{f.x_mailboxes, f.x_seq, f.x_out_mean, f.x_rank, f.x_world};
-        for (int i = tid; i < 6 * f.x_world; i += CW_THREADS)
-            p2p_publish_staged(x, i / f.x_world, i % f.x_world);  // one thread per (value, peer)
+        p2p_pipeline_warp(x, wid);
     }
 
     auto item_valid = [&](const CwItem& it) { return it.tile < n_tiles; };
@@ -390,7 +390,7 @@ static int launch_ws(const FusedArgs& f, float* out, float* ws, size_t ws_bytes,
     fa.scale[0] = is; fa.scale[1] = 0.5 * is; fa.scale[2] = is; fa.scale[3] = a.logit_pre ? is : 0.0;
     fa.scale[4] = is; fa.scale[5] = is;
     fa.k = 6; fa.n_blocks = (int)grid;
-    // data-parallel training: the finalising threads stage the six scalars and consume the previous step's (common.cuh)
+    // data-parallel training: the finalising threads stage the six scalars for the next step's kernel to publish (common.cuh)
     fa.x.mailboxes = f.x_mailboxes; fa.x.state = f.x_seq; fa.x.out_mean = f.x_out_mean; fa.x.rank = f.x_rank;
     fa.x.world = f.x_world;
     (void)launch_finalize(ws, out, fa, st);

@@ -232,18 +232,21 @@ __device__ __forceinline__ void grid_store_partials(float (&v)[K], float* ws) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Data-parallel exchange of the loss scalars without a launch of its own (mean of the rank means,
-// ding/utils/pytorch_ddp_dist_helper.py:38-47), software-pipelined over the launches the learner step makes anyway:
-//   finalize_sums of step q   (thread k, after writing out[k])  stages {q, out[k]} in LOCAL memory and consumes the entries
-//                              tagged q-1 of all ranks from its own mailbox into out_mean[k] (they were published ~a step ago);
-//   streaming kernel of step q+1 (first CTA, prologue)           publishes the staged {q, value} as ONE 8-byte store into every
-//                              peer's mailbox (peer-mapped symmetric memory over NVLink) and goes on with its ~14 us of work.
-// A remote store is only complete when its acknowledgement has crossed NVLink (~1.5 us): issued from the short finalize
-// launch it delayed that launch's completion and everything ordered behind it (N=2: 15.9 -> 17.5 us per step,
-// profiles/r02_scaling.md); issued at the START of the long kernel it costs nothing.  Value and tag travel in a single store,
-// so no flag ordering is needed.  Two mailbox slots alternate by tag parity: tag q+2 is published by step q+3's kernel, after
-// this rank's finalize q+2 consumed tag q+1 of every peer, which each peer published after consuming tag q -- so a slot is
-// never overwritten before every peer has read it.  After the last step b200rl_p2p_drain_mean publishes and consumes the tail.
+// Data-parallel exchange of the loss scalars without a launch of its own and without anything on the critical path
+// (mean of the rank means, ding/utils/pytorch_ddp_dist_helper.py:38-47), software-pipelined over the
+// launches the learner step makes anyway:
+//   finalize_sums of step q      (thread k, after writing out[k])   stages {tag q, out[k]} in LOCAL memory -- two plain stores;
+//   streaming kernel of step q+1 (first CTA, consumer warp k, while it waits for its first chunk to land anyway)
+//                                 consumes the entries tagged q-1 of all ranks from its own mailbox into out_mean[k] (they
+//                                 were published a whole step ago), then publishes the staged {q, value} as ONE 8-byte store
+//                                 into every peer's mailbox (peer-mapped symmetric memory over NVLink).
+// Both the remote stores (complete only when their acknowledgement has crossed NVLink, ~1.5 us) and the system-scope reads
+// of the mailbox (~0.7 us) are hidden behind the ~14 us the kernel streams: measured at N=2, exchange in the short finalize
+// launch 15.9 -> 17.5 us per step, here -> the N=1 time (profiles/r02_scaling.md).  Value and tag travel in a single store,
+// so no flag ordering is needed.  Two mailbox slots alternate by tag parity; warp k consumes tag q-1 BEFORE it publishes tag q,
+// so when a rank publishes tag q+1 (same slot as q-1) every peer's tag q has arrived, i.e. every peer has consumed q-1.
+// out_mean[k] is the mean of the latest consumed step (two steps behind out[k]), out_mean[8+k] the one before;
+// b200rl_p2p_drain_mean after the last step publishes / consumes the tail so that out_mean[k] is the LAST step's mean.
 //
 // (Measured and rejected, profiles/r02_fx_finalize.md: summing the partials INSIDE the streaming kernel with one returning
 // atomic round trip per CTA on packed fixed-point accumulators -- bit-reproducible and one launch fewer, but the atomics
@@ -254,8 +257,9 @@ constexpr int P2P_SLOT_VALS = 8;       // u64 entries per (slot, rank) in an exc
 
 struct XchgArgs {
     const unsigned long long* mailboxes;  // nullable: device array [world] of mailbox base addresses as seen from this rank
-    unsigned int* state;                  // 16 words owned by the exchange (zero-initialised): [0,8) tags, [8,16) staged values
-    float* out_mean;                      // 8 values = mean over ranks of the PREVIOUS step's out[k]
+    unsigned int* state;                  // 24 words owned by the exchange (zero-initialised): [0,8) staged tags, [8,16) staged
+                                          // values, [16,24) last consumed tags
+    float* out_mean;                      // 16 floats: [0,8) mean over ranks of the latest consumed step, [8,16) the one before
     int rank, world;
 };
 
@@ -268,52 +272,51 @@ __device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsign
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// one entry of the local mailbox: value k of rank r tagged q (polls until it has arrived)
-__device__ __forceinline__ float p2p_poll_entry(const XchgArgs& x, int k, int r, unsigned int q) {
-    const unsigned long long* e = reinterpret_cast<const unsigned long long*>(x.mailboxes[x.rank]) +
-                                  ((size_t)(q & 1u) * x.world + r) * P2P_SLOT_VALS + k;
-    unsigned long long w;
-    while ((unsigned int)((w = ld_relaxed_sys_u64(e)) >> 32) != q) __nanosleep(32);
-    return __uint_as_float((unsigned int)w);
+// finalize launch, thread k, after it has produced res = out[k]: stage this step's value (local stores only)
+__device__ __forceinline__ void p2p_stage(const XchgArgs& x, int k, float res) {
+    x.state[8 + k] = __float_as_uint(res);
+    x.state[k] = x.state[k] + 1u;  // only the thread that owns value k writes state[k] / state[8 + k]
 }
 
-// CTA-wide (all NT threads call it; res is meaningful in threads k < K): stage this step's K values and consume the previous
-// step's entries of all ranks.  The K*world mailbox reads are independent round trips to system-coherent memory (~0.7 us
-// each): one thread per (value, rank) polls its entry, then thread k adds them in rank order (deterministic).
-template <int NT>
-__device__ __forceinline__ void p2p_stage_and_consume(const XchgArgs& x, int K, float res) {
-    __shared__ float s_x[P2P_SLOT_VALS][64];
-    const int n = K * x.world;
-    for (int i = threadIdx.x; i < n; i += NT) {
-        const int k = i / x.world, r = i - k * x.world;
-        const unsigned int q = x.state[k];  // tag of the previous step (this step's is q + 1)
-        if (q >= 1u) s_x[k][r] = p2p_poll_entry(x, k, r, q);
+// one warp per value k (all 32 lanes call; world <= 32): consume the entries tagged `q` of all ranks -- lane r polls rank r's
+// entry, lane 0 adds them in rank order (deterministic) -- and shift out_mean
+__device__ __forceinline__ void p2p_consume_warp(const XchgArgs& x, int k, unsigned int q) {
+    const int lane = threadIdx.x & 31;
+    float v = 0.f;
+    if (lane < x.world) {
+        const unsigned long long* e = reinterpret_cast<const unsigned long long*>(x.mailboxes[x.rank]) +
+                                      ((size_t)(q & 1u) * x.world + lane) * P2P_SLOT_VALS + k;
+        unsigned long long w;
+        while ((unsigned int)((w = ld_relaxed_sys_u64(e)) >> 32) != q) __nanosleep(32);
+        v = __uint_as_float((unsigned int)w);
     }
-    __syncthreads();
-    if ((int)threadIdx.x < K) {
-        const int k = threadIdx.x;
-        const unsigned int q = x.state[k];  // only the thread that owns value k writes state[k] / state[8 + k]
-        if (q >= 1u) {
-            float acc = 0.f;
-            for (int r = 0; r < x.world; ++r) acc += s_x[k][r];
-            x.out_mean[k] = acc / (float)x.world;
-        }
-        x.state[8 + k] = __float_as_uint(res);
-        x.state[k] = q + 1u;
+    float acc = 0.f;
+    for (int r = 0; r < x.world; ++r) acc += __shfl_sync(0xffffffffu, v, r);
+    if (lane == 0) {
+        x.out_mean[8 + k] = x.out_mean[k];
+        x.out_mean[k] = acc / (float)x.world;
+        x.state[16 + k] = q;
     }
+    __syncwarp();
 }
 
-// prologue of the next long kernel: publish the staged value k to rank p's mailbox (p < 0: to every rank)
-__device__ __forceinline__ void p2p_publish_staged(const XchgArgs& x, int k, int p = -1) {
+// one warp per value k: lane p publishes the staged {tag, value} to rank p's mailbox
+__device__ __forceinline__ void p2p_publish_warp(const XchgArgs& x, int k) {
+    const int lane = threadIdx.x & 31;
     const unsigned int q = x.state[k];
-    if (q == 0u) return;
+    if (q == 0u || lane >= x.world) return;
     const unsigned long long word = ((unsigned long long)q << 32) | (unsigned long long)x.state[8 + k];
-    const int p0 = p < 0 ? 0 : p, p1 = p < 0 ? x.world : p + 1;
-    for (int d = p0; d < p1; ++d) {
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(x.mailboxes[d]) +
-                                  ((size_t)(q & 1u) * x.world + x.rank) * P2P_SLOT_VALS + k;
-        st_relaxed_sys_u64(dst, word);
-    }
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(x.mailboxes[lane]) +
+                              ((size_t)(q & 1u) * x.world + x.rank) * P2P_SLOT_VALS + k;
+    st_relaxed_sys_u64(dst, word);
+}
+
+// prologue of the long kernel of step q+1, warp k of its first CTA: consume tag q-1, then publish tag q
+__device__ __forceinline__ void p2p_pipeline_warp(const XchgArgs& x, int k) {
+    const unsigned int q = x.state[k];
+    if (q >= 2u && x.state[16 + k] < q - 1u) p2p_consume_warp(x, k, q - 1u);  // (not again after a drain)
+    __syncwarp();
+    p2p_publish_warp(x, k);
 }
 
 struct FinalizeArgs {
@@ -349,15 +352,14 @@ static __global__ void __launch_bounds__(256) finalize_sums_kernel(const float* 
         if (lane == 0) s_acc[k][wid] = r;
     }
     __syncthreads();
-    float res = 0.f;
     if (threadIdx.x < K) {
         double r = 0.0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) r += s_acc[threadIdx.x][w];
-        res = (float)(r * fa.scale[threadIdx.x]);
+        const float res = (float)(r * fa.scale[threadIdx.x]);
         out[threadIdx.x] = res;
+        if (fa.x.mailboxes) p2p_stage(fa.x, threadIdx.x, res);  // data-parallel exchange: the next step's kernel publishes it
     }
-    if (fa.x.mailboxes) p2p_stage_and_consume<256>(fa.x, K, res);  // data-parallel exchange (uniform branch)
     unsigned int* wsu = reinterpret_cast<unsigned int*>(ws_rw);
     for (int i = threadIdx.x; i < fa.clear_ctrl_n; i += 256) wsu[fa.clear_ctrl_from + i] = 0u;
     for (int i = threadIdx.x; i < fa.clear_tail_n; i += 256) wsu[fa.clear_tail_off + i] = 0u;

@@ -404,7 +404,7 @@ static int gae_ppo_step(const float* value, float* next_value, const float* rewa
     const bool row_ok = fused_ok(f), col_ok = coltile_ok(f);
     if (!row_ok && !col_ok) return B200RL_ERR_ARG;
     if (mailbox_ptrs_dev) {  // data-parallel exchange in the epilogue of the column-tile kernel
-        if (!seq_dev || !out_mean || world < 1 || world > 64 || rank < 0 || rank >= world || !col_ok)
+        if (!seq_dev || !out_mean || world < 1 || world > 32 || rank < 0 || rank >= world || !col_ok)
             return B200RL_ERR_ARG;
         f.x_mailboxes = mailbox_ptrs_dev; f.x_seq = seq_dev; f.x_out_mean = out_mean; f.x_rank = rank; f.x_world = world;
         return launch_coltile(f, grads, 0, out, workspace, workspace_bytes, st);

@@ -120,11 +120,12 @@ class P2PLossAllReduce:
 
 class FusedLossExchange:
     """State of the exchange that rides on the launches of the one-launch learner step (``b200rl_gae_ppo_fwd_grad_dp``,
-    csrc/common.cuh): step q's loss-finalisation launch stages ``{q, value}`` locally and consumes the previous step's
-    entries of all ranks; step q+1's streaming kernel publishes the staged word into every peer's mailbox over NVLink in its
-    prologue -- no collective call, no extra launch, no forked graph branch, and no remote store on the critical path.
-    ``out_mean`` holds the mean over ranks of the PREVIOUS step's six loss scalars (the exchange of step j overlaps step
-    j+1); ``drain()`` after the last step delivers the final step's mean.
+    csrc/common.cuh): step q's loss-finalisation launch stages ``{q, value}`` locally; step q+1's streaming kernel -- six
+    warps of its first CTA, while they wait for their first chunk anyway -- consumes the entries of step q-1 of all ranks
+    and publishes the staged word into every peer's mailbox over NVLink.  No collective call, no extra launch, no forked graph
+    branch, and neither the remote stores nor the mailbox reads on the critical path.
+    ``out_mean[:6]`` holds the mean over ranks of the latest consumed step (two steps behind the local losses),
+    ``out_mean[8:14]`` the step before; ``drain()`` after the last step delivers the last step's mean (and the one before).
 
     Same contract as ``LossAllReduce`` (mean of equal-sized rank means, ding/utils/pytorch_ddp_dist_helper.py:38-47);
     every rank must launch the same sequence of steps.  Needs P2P access between the GPUs (torch symmetric memory).
@@ -144,8 +145,8 @@ class FusedLossExchange:
         self.mailbox.zero_()
         self.handle = symm_mem.rendezvous(self.mailbox, self.group)
         self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=self.device)
-        self.seq = torch.zeros(16, dtype=torch.int32, device=self.device)  # 8 tags + 8 staged values
-        self.out_mean = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.seq = torch.zeros(24, dtype=torch.int32, device=self.device)  # staged tags, staged values, consumed tags
+        self.out_mean = torch.zeros(16, dtype=torch.float32, device=self.device)  # [0:8] latest mean, [8:16] the one before
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)  # every mailbox is zeroed and mapped before the first exchange
 

@@ -240,16 +240,17 @@ B200RL_API int b200rl_gae_ppo_fwd_grad(const float* value, float* next_value, co
                             const float* g_expected, float* g_used, float* adv, float* out, float* grad_logit_new,
                             float* grad_value_new, float* workspace, size_t workspace_bytes, void* stream);
 /* The same step in data-parallel training (B sharded across ranks): the six loss scalars out[0..5] are
- * exchanged by launches the step makes anyway -- no extra launch, no collective call.  Step q's loss-finalisation launch
- * stages {q, out[k]} locally and consumes the entries tagged q-1 of all ranks from this rank's mailbox into out_mean[0..5]
- * (mean of the rank means, ding/utils/pytorch_ddp_dist_helper.py:38-47); step q+1's streaming kernel publishes the staged
- * word to every peer's mailbox over NVLink in its prologue (one 8-byte store per peer and value; the acknowledgements return
- * while the kernel streams).  So out_mean lags out by one step: the exchange of step q overlaps step q+1.
- * mailbox_ptrs_dev: device array of `world` mailbox base addresses as seen from THIS process (peer-mapped symmetric memory),
- * each b200rl_p2p_mailbox_floats(world) floats, zero-initialised; seq_dev: 16 32-bit device words, zero-initialised, owned
- * by this exchange; every rank must make the same sequence of calls.  After the last step b200rl_p2p_drain_mean publishes
- * and consumes the final step's values.  Requires the column-tile kernel (b200rl_gae_ppo_supported, B >= 16) and P2P access
- * between the ranks' GPUs. */
+ * exchanged by launches the step makes anyway -- no extra launch, no collective call, nothing on the critical path.  Step q's
+ * loss-finalisation launch stages {q, out[k]} locally; step q+1's streaming kernel (six warps of its first CTA, while they
+ * would wait for their first chunk anyway) consumes the entries tagged q-1 of all ranks from this rank's mailbox into
+ * out_mean and publishes the staged word to every peer's mailbox over NVLink (one 8-byte store per peer and value; the
+ * acknowledgements return while the kernel streams).  out_mean[0..5] = mean over ranks of the latest consumed step (mean of
+ * the rank means, ding/utils/pytorch_ddp_dist_helper.py:38-47), two steps behind out; out_mean[8..13] the step before.
+ * mailbox_ptrs_dev: device array of `world` (<= 32) mailbox base addresses as seen from THIS process (peer-mapped symmetric
+ * memory), each b200rl_p2p_mailbox_floats(world) floats, zero-initialised; seq_dev: 24 32-bit device words and out_mean: 16
+ * floats, zero-initialised, owned by this exchange; every rank must make the same sequence of calls.  After the last step
+ * b200rl_p2p_drain_mean publishes / consumes the tail: out_mean[0..5] = the LAST step's mean, out_mean[8..13] the one before.
+ * Requires the column-tile kernel (b200rl_gae_ppo_supported, B >= 16) and P2P access between the ranks' GPUs. */
 B200RL_API int b200rl_gae_ppo_fwd_grad_dp(const float* value, float* next_value, const float* reward, const float* done,
                                const float* traj_flag, long long T, long long B, double gamma, double lambda_,
                                int mask_next_value_inplace, const float* logit_new, const float* logit_old,

@@ -63,10 +63,12 @@ def _worker(rank, world, port, out_dir):
     for s in range(steps):
         devsteps[s]()
         torch.cuda.synchronize()
-        if s > 0:  # the mean of step s-1 was consumed by step s
+        if s > 1:  # step s consumed the mean of step s-2 (step s-1's was published by step s's kernel)
             results.append(x.out_mean[:6].clone().cpu())
-    results.append(x.drain()[:6].clone().cpu())
+    x.drain()
     torch.cuda.synchronize()
+    results.append(x.out_mean[8:14].clone().cpu())  # step Q-1
+    results.append(x.out_mean[:6].clone().cpu())    # step Q
     advs = [torch.zeros_like(devsteps[0].adv) for _ in range(world)]
     dist.all_gather(advs, devsteps[0].adv)
     local = torch.stack([d.out[:6].clone() for d in devsteps]).cpu()
@@ -122,7 +124,7 @@ def test_two_rank_exchange_kernels(tmp_path):
                                   full['value_old'], adv.reshape(-1), full['return_'], None, None, bench.CLIP, True, None)
         want = np.array([float(v) for v in out[:4]] + [out[4], out[5]], dtype=np.float32)
         assert np.allclose(z['means'][s], want, rtol=1e-5, atol=1e-6), (s, z['means'][s], want)
-    # after the replays the last consumed entry is step 1's mean
+    # after the replays (each ends with a drain) the latest mean is that of the graph's last step, buffer set 1
     full = bench.make_batch(101, T=T, B=B, N=N)
     adv = rl_oracle.gae(full['value'], full['next_value'].clone(), full['reward'], full['done'], full['traj_flag'],
                         bench.GAMMA, bench.LAMBDA)
