@@ -27,34 +27,48 @@ template <int TC, bool VEC>
 __global__ void __launch_bounds__((TC / 4 + 1) * 32) gae_ws_kernel(
     const float* __restrict__ value, float* __restrict__ next_value, const float* __restrict__ reward,
     const float* __restrict__ done, const float* __restrict__ traj, float* __restrict__ adv, long long T,
-    long long C, long long A, float gamma, float gl, int mask_inplace) {
+    long long C, long long A, float gamma, float gl, int mask_inplace, float vscale) {
     pdl_prologue();
     __shared__ __align__(16) float s_d[GAE_NCHUNK][GAE_CH][TC];
     __shared__ __align__(16) float s_f[GAE_NCHUNK][GAE_CH][TC];
     gae_tile_body<TC, VEC>(value, next_value, reward, done, traj, adv, T, C, A, gamma, gl, mask_inplace,
-                           (long long)blockIdx.x * TC, s_d, s_f, [](long long, bool) {});
+                           (long long)blockIdx.x * TC, s_d, s_f, [](long long, bool) {}, vscale);
 }
 
 template <int TC>
 static int launch_gae(const float* value, float* next_value, const float* reward, const float* done,
                       const float* traj, float* adv, long long T, long long C, long long A, float gamma, float gl,
-                      int mask_inplace, bool vec, cudaStream_t st) {
+                      int mask_inplace, bool vec, cudaStream_t st, float vscale) {
     const int grid = div_up(C, TC);
     constexpr int NT = (TC / 4 + 1) * 32;
     if (vec)
         (void)launch_k(gae_ws_kernel<TC, true>, grid, NT, 0, st, value, next_value, reward, done, traj, adv, T, C, A, gamma, gl,
-                                                      mask_inplace);
+                                                      mask_inplace, vscale);
     else
         (void)launch_k(gae_ws_kernel<TC, false>, grid, NT, 0, st, value, next_value, reward, done, traj, adv, T, C, A, gamma, gl,
-                                                       mask_inplace);
+                                                       mask_inplace, vscale);
     return (int)cudaGetLastError();
 }
 
 }  // namespace b200rl
 
+namespace b200rl {
+int gae_scan(const float* value, float* next_value, const float* reward, const float* done, const float* traj_flag, float* adv,
+             long long T, long long C, long long A, double gamma_d, double lambda_d, int mask_next_value_inplace,
+             float vscale, void* stream);
+}
+
 extern "C" int b200rl_gae(const float* value, float* next_value, const float* reward, const float* done,
                           const float* traj_flag, float* adv, long long T, long long C, long long A, double gamma_d,
                           double lambda_d, int mask_next_value_inplace, void* stream) {
+    return b200rl::gae_scan(value, next_value, reward, done, traj_flag, adv, T, C, A, gamma_d, lambda_d,
+                            mask_next_value_inplace, 0.f, stream);
+}
+
+// vscale != 0: value and next_value are multiplied by it on load (PPOPolicy's value_norm, ding/policy/ppo.py:276-278)
+int b200rl::gae_scan(const float* value, float* next_value, const float* reward, const float* done, const float* traj_flag,
+                     float* adv, long long T, long long C, long long A, double gamma_d, double lambda_d,
+                     int mask_next_value_inplace, float vscale, void* stream) {
     using namespace b200rl;
     // python scalars reach torch as fp32(gamma) and fp32(gamma*lambda_) (product taken in double), gae.py:62-63
     const float gamma = (float)gamma_d, gamma_lambda = (float)(gamma_d * lambda_d);
@@ -73,10 +87,10 @@ extern "C" int b200rl_gae(const float* value, float* next_value, const float* re
     }
     if (forced_tc == 32 || (forced_tc == 0 && C >= 32 * 296))
         return launch_gae<32>(value, next_value, reward, done, traj_flag, adv, T, C, A, gamma, gamma_lambda,
-                              mask_next_value_inplace, vec, st);
+                              mask_next_value_inplace, vec, st, vscale);
     if (forced_tc == 16 || (forced_tc == 0 && C >= 16 * 296))
         return launch_gae<16>(value, next_value, reward, done, traj_flag, adv, T, C, A, gamma, gamma_lambda,
-                              mask_next_value_inplace, vec, st);
+                              mask_next_value_inplace, vec, st, vscale);
     return launch_gae<8>(value, next_value, reward, done, traj_flag, adv, T, C, A, gamma, gamma_lambda,
-                         mask_next_value_inplace, vec, st);
+                         mask_next_value_inplace, vec, st, vscale);
 }

@@ -54,7 +54,7 @@ __device__ __forceinline__ void gae_tile_body(
     const float* __restrict__ value, float* __restrict__ next_value, const float* __restrict__ reward,
     const float* __restrict__ done, const float* __restrict__ traj, float* __restrict__ adv, long long T,
     long long C, long long A, float gamma, float gl, int mask_inplace, long long c0,
-    float (*s_d)[GAE_CH][TC], float (*s_f)[GAE_CH][TC], OnChunk on_chunk_done) {
+    float (*s_d)[GAE_CH][TC], float (*s_f)[GAE_CH][TC], OnChunk on_chunk_done, float vscale = 0.f) {
     constexpr int NL = (TC / 4) * 32;  // loader threads
     constexpr int NTHREADS = NL + 32;
     const long long Caux = C / A;
@@ -105,6 +105,10 @@ __device__ __forceinline__ void gae_tile_body(
                         bool changed = false;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
+                            if (vscale != 0.f) {  // value_norm: value *= std; next_value *= std (ding/policy/ppo.py:276-278)
+                                vv[q] = fmul(vv[q], vscale);
+                                nn[q] = fmul(nn[q], vscale);
+                            }
                             if (done) {
                                 changed |= (dd[q] != 0.f);
                                 nn[q] = fmul(nn[q], fsub(1.f, dd[q]));
@@ -133,6 +137,7 @@ __device__ __forceinline__ void gae_tile_body(
                             const long long off = (lo + r) * C + c;
                             const long long aoff = (lo + r) * Caux + c / A;
                             float nvv = next_value[off];
+                            if (vscale != 0.f) nvv = fmul(nvv, vscale);
                             const float dnn = done ? done[aoff] : 0.f;
                             const float tff = traj ? traj[aoff] : dnn;
                             if (done) {
@@ -140,7 +145,8 @@ __device__ __forceinline__ void gae_tile_body(
                                 if (mask_inplace && dnn != 0.f) next_value[off] = mm;
                                 nvv = mm;
                             }
-                            s_d[k][rr][cc] = fsub(fadd(reward[aoff], fmul(gamma, nvv)), value[off]);
+                            const float vvv = vscale != 0.f ? fmul(value[off], vscale) : value[off];
+                            s_d[k][rr][cc] = fsub(fadd(reward[aoff], fmul(gamma, nvv)), vvv);
                             s_f[k][rr][cc] = fmul(gl, fsub(1.f, tff));
                         }
                     }

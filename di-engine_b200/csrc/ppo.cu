@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(NT) ppo_fwd_kernel(PpoArgs a, float* out, floa
         }
         if (lane == 0) {
             const float w = a.weight ? a.weight[s] : 1.f;
-            const float adv = a.adv[s];
+            const float adv = adv_in(a, a.adv[s]);
             const float ratio = (G == 1) ? ratio_sum : ratio_sum / (float)G;
             const float ent = (G == 1) ? ent_sum : ent_sum / (float)G;
             float dsel;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(NT) ppo_bwd_kernel(PpoArgs a) {
     const float* zp = a.logit_pre ? a.logit_pre + s * G * N : nullptr;
     float* gz = a.grad_logit + s * G * N;
     const float w = a.weight ? a.weight[s] : 1.f;
-    const float adv = a.adv[s];
+    const float adv = adv_in(a, a.adv[s]);
     // pass A (only when G > 1): the sample's mean ratio decides the clip branch for all of its rows
     float ratio_s = 0.f;
     if (G > 1) {
@@ -450,7 +450,8 @@ using namespace b200rl;
 static int fill_args(PpoArgs& a, const float* logit_new, const float* logit_old, const float* logit_pretrained,
                      const long long* action, const float* value_new, const float* value_old, const float* adv,
                      const float* return_, const float* weight, long long S, long long G, long long N,
-                     double clip_ratio, int use_value_clip, double dual_clip, int kl_type) {
+                     double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* adv_stats) {
+    a.adv_stats = adv_stats;
     a.logit_new = logit_new; a.logit_old = logit_old; a.logit_pre = logit_pretrained; a.action = action;
     a.value_new = value_new; a.value_old = value_old; a.adv = adv; a.ret = return_; a.weight = weight;
     a.S = S; a.G = (int)G; a.N = (int)N; a.clip = (float)clip_ratio; a.clip_lo = (float)(1.0 - clip_ratio);
@@ -474,10 +475,11 @@ extern "C" int b200rl_ppo_fwd(const float* logit_new, const float* logit_old, co
                               const long long* action, const float* value_new, const float* value_old,
                               const float* adv, const float* return_, const float* weight, long long S, long long G,
                               long long N, double clip_ratio, int use_value_clip, double dual_clip, int kl_type,
-                              float* out, float* workspace, size_t workspace_bytes, void* stream) {
+                              const float* adv_stats, float* out, float* workspace, size_t workspace_bytes,
+                              void* stream) {
     PpoArgs a{};
     int rc = fill_args(a, logit_new, logit_old, logit_pretrained, action, value_new, value_old, adv, return_, weight,
-                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type);
+                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, adv_stats);
     if (rc != B200RL_OK || !out || !workspace) return rc != B200RL_OK ? rc : B200RL_ERR_ARG;
     if (S == 0) return B200RL_ERR_ARG;  // mean over an empty batch is undefined (reference returns nan)
     cudaStream_t st = (cudaStream_t)stream;
@@ -496,12 +498,12 @@ extern "C" int b200rl_ppo_fwd_grad(const float* logit_new, const float* logit_ol
                                    const long long* action, const float* value_new, const float* value_old,
                                    const float* adv, const float* return_, const float* weight, long long S,
                                    long long G, long long N, double clip_ratio, int use_value_clip, double dual_clip,
-                                   int kl_type, const float* g_expected, float* g_used, float* out,
+                                   int kl_type, const float* adv_stats, const float* g_expected, float* g_used, float* out,
                                    float* grad_logit_new, float* grad_value_new, float* workspace,
                                    size_t workspace_bytes, void* stream) {
     PpoArgs a{};
     int rc = fill_args(a, logit_new, logit_old, logit_pretrained, action, value_new, value_old, adv, return_, weight,
-                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type);
+                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, adv_stats);
     if (rc != B200RL_OK) return rc;
     if (!out || !workspace || !g_expected || !g_used || !grad_logit_new || !grad_value_new || S == 0)
         return B200RL_ERR_ARG;
@@ -527,12 +529,13 @@ extern "C" int b200rl_ppo_bwd(const float* logit_new, const float* logit_old, co
                               const long long* action, const float* value_new, const float* value_old,
                               const float* adv, const float* return_, const float* weight, long long S, long long G,
                               long long N, double clip_ratio, int use_value_clip, double dual_clip, int kl_type,
-                              const float* g_policy, const float* g_value, const float* g_entropy, const float* g_kl,
+                              const float* adv_stats, const float* g_policy, const float* g_value, const float* g_entropy,
+                              const float* g_kl,
                               const float* g_used, float* g_hint, float* grad_logit_new, float* grad_value_new,
                               void* stream) {
     PpoArgs a{};
     int rc = fill_args(a, logit_new, logit_old, logit_pretrained, action, value_new, value_old, adv, return_, weight,
-                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type);
+                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, adv_stats);
     if (rc != B200RL_OK) return rc;
     a.g_policy = g_policy; a.g_value = g_value; a.g_entropy = g_entropy; a.g_kl = g_kl;
     a.g_used = const_cast<float*>(g_used); a.g_hint = g_hint;

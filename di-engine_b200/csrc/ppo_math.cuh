@@ -35,6 +35,9 @@ struct PpoArgs {
     // BWD: when non-null and equal to the actual upstream values the launch is a no-op (gradients already written)
     float* g_used;
     float* g_hint;  // BWD: refreshed with the actual upstream values for the next forward pass (nullable)
+    // nullable: {mean, std + 1e-8} of the advantage batch (device floats, b200rl_adv_stats): when given every kernel uses
+    // (adv - mean) / (std + 1e-8) -- PPOPolicy's per-batch advantage normalisation (ding/policy/ppo.py:304-306) applied on load
+    const float* adv_stats;
     int dbg;        // tuning experiments only (B200RL_PPO_DBG): 1 = consumers skip the row math, 2 = skip gradient stores
 };
 
@@ -96,6 +99,11 @@ __device__ __forceinline__ float rcpf_(float x) { float y; asm("rcp.approx.ftz.f
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kF32Min = -3.402823466e38f;
+
+// advantage as the loss sees it: raw, or normalised with the batch statistics (two fp32 ops, as torch evaluates the expression)
+__device__ __forceinline__ float adv_in(const PpoArgs& a, float adv) {
+    return a.adv_stats ? __fdiv_rn(fsub(adv, a.adv_stats[0]), a.adv_stats[1]) : adv;
+}
 
 __device__ __forceinline__ float kl_term(float log_ratio, int kl_type, float& dterm) {
     if (kl_type == 1) { dterm = 1.f; return log_ratio; }
@@ -185,6 +193,7 @@ template <int NC, bool LOSSES, bool GRADS>
 __device__ __forceinline__ void ppo_row_compute_to(const PpoArgs& a, const PpoTileLayout& L, const unsigned char* st,
                                                    int tid, int N, float adv, float* gr, float* gv,
                                                    const PpoUpstream& up, float (&acc)[6]) {
+    adv = adv_in(a, adv);
     const bool has_pre = a.logit_pre != nullptr, has_w = a.weight != nullptr;
     const float g_pol = up.g_pol, g_val = up.g_val, g_ent = up.g_ent, g_kl = up.g_kl, inv_s = up.inv_s;
     {

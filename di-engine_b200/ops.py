@@ -109,6 +109,10 @@ def gae_(value, next_value, reward, done, traj_flag, gamma, lambda_, agents, mas
     adv = torch.empty_like(value)
     if value.numel() == 0:
         return adv
+    if C == 1 and agents == 1:
+        # ONE sequence (the real PPO learner, ding/policy/ppo.py:280-282: n_sample steps of concatenated trajectories): the
+        # segment-parallel single-CTA kernel of csrc/policy.cu instead of one lane walking all T steps
+        return gae_returns_(value, next_value, reward, done, traj_flag, gamma, lambda_, 1, 0.0, False, False, mask_inplace)[0]
     with torch.cuda.device(value.device):
         rc = lib().b200rl_gae(
             ptr(value), ptr(next_value), ptr(reward), ptr(done), ptr(traj_flag), ptr(adv), T, C, agents, float(gamma),
@@ -116,6 +120,47 @@ def gae_(value, next_value, reward, done, traj_flag, gamma, lambda_, agents, mas
         )
     _lib.check(rc, 'b200rl_gae')
     return adv
+
+
+def gae_returns_(value, next_value, reward, done, traj_flag, gamma, lambda_, agents, vscale, want_returns, want_stats,
+                 mask_inplace=False):
+    """gae + the pieces around it in PPOPolicy._forward_learn (ding/policy/ppo.py:274-297) -- csrc/policy.cu.
+    -> (adv, unnormalized_return, value_out, return_out, stats3) (None where not requested)."""
+    T = value.shape[0]
+    C = value.numel() // T
+    dev = value.device
+    adv = torch.empty_like(value)
+    unnorm = torch.empty_like(value) if want_returns else None
+    vout = torch.empty_like(value) if (want_returns and vscale != 0.0) else None
+    rout = torch.empty_like(value) if (want_returns and vscale != 0.0) else None
+    stats = torch.empty(3, dtype=torch.float32, device=dev) if want_stats else None
+    with torch.cuda.device(dev):
+        ws = workspace(dev)
+        rc = lib().b200rl_gae_returns(
+            ptr(value), ptr(next_value), ptr(reward), ptr(done), ptr(traj_flag), T, C, agents, float(gamma), float(lambda_),
+            1 if mask_inplace else 0, float(vscale), ptr(adv), ptr(unnorm), ptr(vout), ptr(rout), ptr(stats), ptr(ws),
+            ws.numel() * 4, stream_ptr()
+        )
+    _lib.check(rc, 'b200rl_gae_returns')
+    return adv, unnorm, vout, rout, stats
+
+
+def adv_stats_(x):
+    """{mean, std(unbiased) + 1e-8} of ``x`` as two device floats (ding/policy/ppo.py:304-306), one launch."""
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = workspace(x.device)
+        rc = lib().b200rl_adv_stats(ptr(x), x.numel(), ptr(out), ptr(ws), ws.numel() * 4, stream_ptr())
+    _lib.check(rc, 'b200rl_adv_stats')
+    return out
+
+
+def normalize_(x, stats):
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib().b200rl_normalize(ptr(x), ptr(stats), x.numel(), ptr(out), stream_ptr())
+    _lib.check(rc, 'b200rl_normalize')
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -146,14 +191,15 @@ class PPOFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre, S, G, N,
-                clip_ratio, use_value_clip, dual_clip, kl_type, hint_kind):
+                clip_ratio, use_value_clip, dual_clip, kl_type, hint_kind, adv_stats=None):
         dev = logit_new.device
         ctx.hint_kind = hint_kind
+        ctx.adv_stats = adv_stats  # {mean, std + 1e-8} device floats or None; kept alive for the backward launch
         out = torch.empty(8, dtype=torch.float32, device=dev)
         L = lib()
         tensors = (ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old),
                    ptr(adv), ptr(return_), ptr(weight))
-        cfg = (S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type)
+        cfg = (S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, ptr(adv_stats))
         ctx.fused = False
         want_grad = PPO_FUSED_BACKWARD and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         with torch.cuda.device(dev):
@@ -204,7 +250,7 @@ class PPOFunction(torch.autograd.Function):
                 stream_ptr()
             )
         _lib.check(rc, 'b200rl_ppo_bwd')
-        return (grad_logit, grad_value) + (None, ) * 15
+        return (grad_logit, grad_value) + (None, ) * 16
 
 
 class GAEPPOFunction(torch.autograd.Function):
@@ -232,7 +278,7 @@ class GAEPPOFunction(torch.autograd.Function):
             )
         _lib.check(rc, 'b200rl_gae_ppo_fwd_grad')
         ctx.save_for_backward(logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre)
-        ctx.cfg = (T * B, 1, N, clip_ratio, use_value_clip, dual_clip, kl_type)
+        ctx.cfg = (T * B, 1, N, clip_ratio, use_value_clip, dual_clip, kl_type, None)
         ctx.fused = want_grad
         ctx.spec = (grad_logit, grad_value, g_used)
         ctx.bwd_calls = 0

@@ -1,8 +1,8 @@
 """Mirror of the hot-path part of ``ding.rl_utils`` (ding/rl_utils/__init__.py:1-27): identical names, signatures and
 namedtuples, computed by the sm_100a kernels behind the C ABI of ``include/b200rl.h``."""
 from .fused import gae_ppo_error
-from .gae import gae, gae_data, shape_fn_gae
-from .ppo import (ppo_data, ppo_error, ppo_info, ppo_loss, ppo_policy_data, ppo_policy_error, ppo_policy_loss,
+from .gae import gae, gae_data, gae_returns, gae_returns_out, shape_fn_gae
+from .ppo import (normalize_advantage, ppo_data, ppo_error, ppo_error_adv_norm, ppo_info, ppo_loss, ppo_policy_data, ppo_policy_error, ppo_policy_loss,
                   ppo_value_data, ppo_value_error, shape_fn_ppo)
 from .td import (bdq_nstep_td_error, dist_1step_td_data, dist_1step_td_error, dist_nstep_td_data, dist_nstep_td_error,
                  generalized_lambda_returns, q_1step_td_data, q_1step_td_error, q_nstep_td_data, q_nstep_td_error,

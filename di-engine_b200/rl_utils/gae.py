@@ -6,6 +6,7 @@ import torch
 from .. import ops
 
 gae_data = namedtuple('gae_data', ['value', 'next_value', 'reward', 'done', 'traj_flag'])
+gae_returns_out = namedtuple('gae_returns_out', ['adv', 'value', 'return_', 'unnormalized_return', 'return_stats'])
 
 
 def shape_fn_gae(args, kwargs):
@@ -54,3 +55,40 @@ def gae(data: namedtuple, gamma: float = 0.99, lambda_: float = 0.97) -> torch.F
         with torch.no_grad():
             next_value.copy_(nv.to(next_value.device))
     return adv.cpu() if host_out else adv
+
+
+def gae_returns(data: namedtuple, gamma: float = 0.99, lambda_: float = 0.97, value_norm_std=None) -> namedtuple:
+    """
+    ``gae`` together with the batch-level pieces ``PPOPolicy._forward_learn`` wraps around it when it recomputes the advantage
+    (ding/policy/ppo.py:274-297) -- not a reference function, exactly those reference lines in one call (csrc/policy.cu)::
+
+        value *= std; next_value *= std                      # only with value_norm (std = RunningMeanStd.std, a float)
+        adv = gae(gae_data(value, next_value, reward, done, traj_flag), gamma, lambda_)
+        unnormalized_returns = value + adv
+        value = value / std; return_ = unnormalized_returns / std   # value / return_ as the learner stores them
+        running_mean_std.update(unnormalized_returns.cpu().numpy()) # here: three device floats {mean, np.var, count}
+
+    ``data`` as for ``gae`` with value shaped like reward ((T,) -- the real learner: ONE sequence of n_sample steps, cut into
+    independent segments at every traj_flag == 1 and scanned segment-parallel, bit-identical to the loop -- or (T, B));
+    ``value_norm_std`` None (value_norm off) or the running std.  The inputs are NOT modified.  Returns
+    ``gae_returns_out(adv, value, return_, unnormalized_return, return_stats)``; ``return_stats`` = (mean, population variance,
+    count) of the unnormalized returns: what ``RunningMeanStd.update`` (ding/utils/default_helper.py:547-567) computes from the
+    array the reference first copies to the host.
+    """
+    value, next_value, reward, done, traj_flag = data
+    dev = ops.compute_device(value, next_value, reward)
+    host_out = not value.is_cuda
+    if value.shape != reward.shape or next_value.shape != value.shape or value.dim() not in (1, 2):
+        raise ValueError("gae_returns: value %s / next_value %s / reward %s must share a (T,) or (T, B) shape" %
+                         (tuple(value.shape), tuple(next_value.shape), tuple(reward.shape)))
+    v = ops.f32c(ops.to_device(value.detach(), dev), 'value')
+    nv = ops.f32c(ops.to_device(next_value.detach(), dev), 'next_value')
+    r = ops.f32c(ops.to_device(reward.detach(), dev), 'reward')
+    d = ops.f32c(ops.to_device(done.detach(), dev), 'done') if done is not None else None
+    tf = ops.f32c(ops.to_device(traj_flag.detach(), dev), 'traj_flag') if traj_flag is not None else None
+    vs = 0.0 if value_norm_std is None else float(value_norm_std)
+    adv, unnorm, vout, rout, stats = ops.gae_returns_(v, nv, r, d, tf, gamma, lambda_, 1, vs, True, True)
+    if vs == 0.0:
+        vout, rout = v, unnorm
+    out = gae_returns_out(adv, vout, rout, unnorm, stats)
+    return gae_returns_out(*[t.cpu() for t in out]) if host_out else out

@@ -31,6 +31,17 @@ def shape_fn_ppo(args, kwargs):
     return data.logit_new.shape
 
 
+def normalize_advantage(adv: torch.Tensor) -> torch.Tensor:
+    """``(adv - adv.mean()) / (adv.std() + 1e-8)`` -- PPOPolicy's per-train-batch advantage normalisation
+    (ding/policy/ppo.py:304-306) as two small launches (statistics; elementwise).  ``ppo_error(..., adv_norm=True)`` applies
+    the same normalisation inside the loss kernels without materialising the tensor."""
+    dev = ops.compute_device(adv)
+    host_out = not adv.is_cuda
+    a = ops.f32c(ops.to_device(adv.detach(), dev), 'adv')
+    out = ops.normalize_(a, ops.adv_stats_(a))
+    return out.cpu() if host_out else out
+
+
 def ppo_error(
         data: namedtuple,
         clip_ratio: float = 0.2,
@@ -46,11 +57,28 @@ def ppo_error(
     weight (...) -- or, multi-agent (ppo.py:199-200,:206-207), logits (B, A, N), action (B, A) with (B,) value/adv.
     Returns ``(ppo_loss, ppo_info)``: four differentiable 0-dim tensors (gradients reach ``logit_new`` and
     ``value_new``) and two python floats.
+
     """
     return _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, 'ppo')
 
 
-def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind):
+def ppo_error_adv_norm(
+        data: namedtuple,
+        clip_ratio: float = 0.2,
+        use_value_clip: bool = True,
+        dual_clip: Optional[float] = None,
+        kl_type: str = 'k1'
+) -> Tuple[namedtuple, namedtuple]:
+    """
+    ``ppo_error`` evaluated on ``(adv - adv.mean()) / (adv.std() + 1e-8)`` -- the normalisation PPOPolicy applies to every
+    train batch right before the call (ding/policy/ppo.py:304-306; not a reference function, exactly those lines + ppo_error).
+    One small statistics launch; the normalisation itself happens on load inside the loss kernels (no normalised copy of
+    ``adv`` is written).  Same arguments and results as ``ppo_error``.
+    """
+    return _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, 'ppo', True)
+
+
+def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind, adv_norm=False):
     assert dual_clip is None or dual_clip > 1.0, "dual_clip value must be greater than 1.0, but get value: {}".format(
         dual_clip
     )
@@ -91,9 +119,10 @@ def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind)
         if w.numel() != S:
             w = w.expand_as(ad).contiguous()
     act = ops.i64c(ops.to_device(action, dev))
+    stats = ops.adv_stats_(ad) if adv_norm else None
     p, v, e, k, out = ops.PPOFunction.apply(
         ln, vn, lo, act, vo, ad, rt, w, lp, S, G, N, float(clip_ratio), 1 if use_value_clip else 0,
-        float(dual_clip) if dual_clip is not None else 0.0, _KL_TYPES.get(kl_type, 1), _hint_kind
+        float(dual_clip) if dual_clip is not None else 0.0, _KL_TYPES.get(kl_type, 1), _hint_kind, stats
     )
     if LAZY_INFO:
         info = ppo_info(out[4], out[5])

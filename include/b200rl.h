@@ -54,16 +54,37 @@ B200RL_API int b200rl_gae(const float* value, float* next_value, const float* re
                float* adv, long long T, long long C, long long A, double gamma, double lambda_,
                int mask_next_value_inplace, void* stream);
 
+/* ---- the batch-level pieces around gae in PPOPolicy._forward_learn (ding/policy/ppo.py:274-297), SURVEY section 8f ----
+ * adv = gae(value*s, next_value*s, reward, done, traj_flag); unnormalized_return = value*s + adv; value_out = (value*s)/s;
+ * return_out = unnormalized_return / s; stats3 = {mean, population variance, count} of unnormalized_return -- the three
+ * numbers RunningMeanStd.update (ding/utils/default_helper.py:547-567) needs, instead of the reference's full D2H copy.
+ * value_scale = s = RunningMeanStd.std (0: value_norm off, s = 1 and no scaling).  Every output but adv is nullable.
+ * C == 1 (the real learner: ONE sequence of n_sample steps, T <= 24576): one launch of one CTA; the sequence is cut at every
+ * traj_flag == 1 and each segment is scanned by its own lane -- bit-identical to the reference loop.  (T, C > 1): the
+ * streaming scan of b200rl_gae (value_scale applied on load) plus one elementwise epilogue launch. */
+B200RL_API int b200rl_gae_returns(const float* value, float* next_value, const float* reward, const float* done,
+                       const float* traj_flag, long long T, long long C, long long A, double gamma, double lambda_,
+                       int mask_next_value_inplace, double value_scale, float* adv, float* unnormalized_return,
+                       float* value_out, float* return_out, float* stats3, float* workspace, size_t workspace_bytes,
+                       void* stream);
+/* {mean, std(unbiased) + 1e-8} of x[0..n) as two device floats (ding/policy/ppo.py:304-306: adv.mean(), adv.std() + 1e-8),
+ * one launch; pass the result as `adv_stats` to the ppo entry points, or materialise (x - mean) / (std + 1e-8): */
+B200RL_API int b200rl_adv_stats(const float* x, long long n, float* stats2, float* workspace, size_t workspace_bytes,
+                     void* stream);
+B200RL_API int b200rl_normalize(const float* x, const float* stats2, long long n, float* out, void* stream);
+
 /* ---- ppo_error: ding/rl_utils/ppo.py:77-140 (policy :143-230, value :233-275, kl :30-54) -----------------------
  * S samples, G rows per sample (1, or the agent dim of ppo.py:199-200,:206-207), N logits.
  * logit_new/logit_old/logit_pretrained(nullable): (S*G, N); action: (S*G) int64;
  * value_new, value_old, adv, return_, weight(nullable): (S).  dual_clip <= 0 means None; kl_type 1|2|3 = 'k1'|'k2'|'k3'.
+ * adv_stats (nullable): {mean, std + 1e-8} of the advantage batch as two device floats (b200rl_adv_stats); when given the
+ * kernels use (adv - mean) / (std + 1e-8) -- PPOPolicy's advantage normalisation (ding/policy/ppo.py:304-306) -- on load.
  * out[0..5] = policy_loss, value_loss, entropy_loss, kl_div, approx_kl, clipfrac  (out has room for 8 floats). */
 B200RL_API int b200rl_ppo_fwd(const float* logit_new, const float* logit_old, const float* logit_pretrained,
                    const long long* action, const float* value_new, const float* value_old, const float* adv,
                    const float* return_, const float* weight, long long S, long long G, long long N,
-                   double clip_ratio, int use_value_clip, double dual_clip, int kl_type, float* out,
-                   float* workspace, size_t workspace_bytes, void* stream);
+                   double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* adv_stats,
+                   float* out, float* workspace, size_t workspace_bytes, void* stream);
 /* gradients of  g_policy*policy_loss + g_value*value_loss + g_entropy*entropy_loss + g_kl*kl_div  w.r.t.
  * logit_new (S*G, N) and value_new (S); autograd tie rules of torch.min/max/clamp reproduced (ppo.py:208-216,:269-272).
  * g_used / g_hint (both nullable) belong to the fused forward below: when g_used is given and equals the four actual
@@ -72,9 +93,9 @@ B200RL_API int b200rl_ppo_fwd(const float* logit_new, const float* logit_old, co
 B200RL_API int b200rl_ppo_bwd(const float* logit_new, const float* logit_old, const float* logit_pretrained,
                    const long long* action, const float* value_new, const float* value_old, const float* adv,
                    const float* return_, const float* weight, long long S, long long G, long long N,
-                   double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* g_policy,
-                   const float* g_value, const float* g_entropy, const float* g_kl, const float* g_used,
-                   float* g_hint, float* grad_logit_new, float* grad_value_new, void* stream);
+                   double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* adv_stats,
+                   const float* g_policy, const float* g_value, const float* g_entropy, const float* g_kl,
+                   const float* g_used, float* g_hint, float* grad_logit_new, float* grad_value_new, void* stream);
 /* Fused forward: the losses of b200rl_ppo_fwd AND the gradients of b200rl_ppo_bwd for the EXPECTED upstream gradients
  * g_expected[0..3] (policy, value, entropy, kl; device floats -- the loss weights of the training loop), in one pass
  * over the batch.  g_used[0..3] records what was applied; pass it to b200rl_ppo_bwd, which verifies the expectation on
@@ -83,7 +104,7 @@ B200RL_API int b200rl_ppo_bwd(const float* logit_new, const float* logit_old, co
 B200RL_API int b200rl_ppo_fwd_grad(const float* logit_new, const float* logit_old, const float* logit_pretrained,
                         const long long* action, const float* value_new, const float* value_old, const float* adv,
                         const float* return_, const float* weight, long long S, long long G, long long N,
-                        double clip_ratio, int use_value_clip, double dual_clip, int kl_type,
+                        double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* adv_stats,
                         const float* g_expected, float* g_used, float* out, float* grad_logit_new,
                         float* grad_value_new, float* workspace, size_t workspace_bytes, void* stream);
 B200RL_API int b200rl_ppo_fused_supported(const float* logit_new, const float* logit_old, const float* logit_pretrained,

@@ -75,6 +75,33 @@ def gae(value, next_value, reward, done=None, traj_flag=None, gamma: float = 0.9
 
 
 # --------------------------------------------------------------------------------------------------------------
+# the batch-level pieces PPOPolicy._forward_learn wraps around gae / ppo_error (ding/policy/ppo.py:274-306)
+# --------------------------------------------------------------------------------------------------------------
+def ppo_policy_gae_returns(value, next_value, reward, done, traj_flag, gamma, lambda_, std=None):
+    """policy/ppo.py:274-297 (recompute_adv branch).  ``std`` = RunningMeanStd.std (a python / numpy float) or None when
+    value_norm is off.  Returns (adv, value, return_, unnormalized_returns, (batch_mean, batch_var, batch_count)) where the
+    statistics are what RunningMeanStd.update (utils/default_helper.py:547-567) derives from the array -- over ALL elements."""
+    import numpy as np
+    value, next_value = value.clone(), next_value.clone()
+    if std is not None:
+        value *= std  # :277
+        next_value *= std  # :278
+    adv = gae(value, next_value, reward, done, traj_flag, gamma, lambda_)  # :280-282
+    unnorm = value + adv  # :284
+    if std is not None:
+        v, ret = value / std, unnorm / std  # :287-288
+    else:
+        v, ret = value, unnorm  # :291-292
+    x = unnorm.numpy().reshape(-1)
+    return adv, v, ret, unnorm, (float(np.mean(x)), float(np.var(x)), float(x.shape[0]))
+
+
+def normalize_advantage(adv):
+    """policy/ppo.py:304-306: ``(adv - adv.mean()) / (adv.std() + 1e-8)`` (torch.std: unbiased)."""
+    return (adv - adv.mean()) / (adv.std() + 1e-8)
+
+
+# --------------------------------------------------------------------------------------------------------------
 # ppo.py:77-275
 # --------------------------------------------------------------------------------------------------------------
 def ppo_error(

@@ -198,7 +198,7 @@ def test_cuda_graph_capture_of_the_learner_step():
         ln = tp['logit_new'].detach().requires_grad_(True)
         vn = tp['value_new'].detach().requires_grad_(True)
         p, v, e, k, _ = ops.PPOFunction.apply(ln, vn, tp['logit_old'], tp['action'], tp['value_old'], adv.view(-1),
-                                              tp['return_'], None, None, T * B, 1, N, 0.2, 1, 0.0, 1, 'ppo')
+                                              tp['return_'], None, None, T * B, 1, N, 0.2, 1, 0.0, 1, 'ppo', None)
         (p + 0.5 * v - 0.01 * e).backward()
         outs.update(adv=adv, p=p, gl=ln.grad, gv=vn.grad)
 
@@ -689,3 +689,86 @@ def test_ppo_fallback_grid_is_bounded_for_large_batches():
     want = cases.run_oracle(rl_oracle, op, t, p)
     got = _run(op, t, p)
     cases.compare(got, want, rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the batch-level pieces around gae / ppo_error in PPOPolicy._forward_learn (policy/ppo.py:274-306)
+# ----------------------------------------------------------------------------------------------------------------
+def _learner_sequence(seed, T, n_env=8, p_done=0.003, flags=True):
+    """ONE sequence of n_sample steps as the serial collector delivers it: n_env trajectories back to back, traj_flag = 1 at the
+    end of each (and at every done), ding/policy/ppo.py:279-281"""
+    g = torch.Generator().manual_seed(seed)
+    value, next_value, reward = (torch.randn(T, generator=g) for _ in range(3))
+    done = (torch.rand(T, generator=g) < p_done).float()
+    traj = done.clone()
+    if flags:
+        seg = max(1, T // n_env)
+        traj[seg - 1::seg] = 1.0
+    traj[-1] = 1.0
+    return value, next_value, reward, done, traj
+
+
+@pytest.mark.parametrize('case', ['n_sample_3200', 'with_value_norm', 'no_flags_one_segment', 'every_step_an_end', 'T1',
+                                  'T24576', 'batched_128x4096', 'batched_value_norm_ragged'])
+def test_gae_returns_matches_policy_lines(case):
+    std = None
+    if case == 'n_sample_3200':
+        data = _learner_sequence(200, 3200)
+    elif case == 'with_value_norm':
+        data, std = _learner_sequence(201, 3200, p_done=0.01), 2.236068
+    elif case == 'no_flags_one_segment':
+        data = _learner_sequence(202, 5000, p_done=0.0, flags=False)
+    elif case == 'every_step_an_end':
+        v, nv, r, d, tf = _learner_sequence(203, 2000)
+        data = (v, nv, r, d, torch.ones_like(tf))
+    elif case == 'T1':
+        data = _learner_sequence(204, 1)
+    elif case == 'T24576':
+        data = _learner_sequence(205, 24576, n_env=64)
+    elif case == 'batched_128x4096':
+        _, t, _ = cases.gae_case(206, 128, 4096, p_done=0.01)
+        data = tuple(t.values())
+    else:
+        _, t, _ = cases.gae_case(207, 67, 1001, p_done=0.05)
+        data, std = tuple(t.values()), 0.37
+    want = rl_oracle.ppo_policy_gae_returns(*[x.clone() for x in data], 0.99, 0.95, std)
+    dev = [x.clone().to(DEV) for x in data]
+    got = b2.gae_returns(b2.gae_data(*dev), 0.99, 0.95, value_norm_std=std)
+    for name, a, b in zip(got._fields[:4], got[:4], want[:4]):
+        assert torch.equal(a.cpu(), b), name  # pure fp32 mul / add / div in the reference's order: bit-exact
+    for x, y in zip(dev, data):
+        assert torch.equal(x.cpu(), y), 'inputs must not be modified'
+    st = got.return_stats.cpu().numpy().astype(np.float64)
+    assert np.allclose(st, np.array(want[4]), rtol=2e-6, atol=1e-6), (st, want[4])
+    # plain gae on one sequence takes the same segment-parallel kernel: identical advantage, in-place mask as the reference
+    dev2 = [x.clone().to(DEV) for x in data]
+    if std is None:
+        adv = b2.gae(b2.gae_data(*dev2), 0.99, 0.95)
+        ref_in = [x.clone() for x in data]
+        assert torch.equal(adv.cpu(), rl_oracle.gae(*ref_in, 0.99, 0.95))
+        assert torch.equal(dev2[1].cpu(), ref_in[1]), 'next_value masked in place'
+
+
+@pytest.mark.parametrize('S,N', [(320, 6), (64, 6), (524288, 6), (1000, 40)])
+def test_ppo_error_adv_norm_matches_policy_lines(S, N):
+    op, t, p = cases.ppo_case(210 + N, S, N, weight='tensor', clip_ratio=0.2)
+    t = dict(t)
+    t['adv'] = t['adv'] * 3.0 + 0.7  # far from normalised
+    tt = cases.prepare('ppo', t)
+    tt['adv'] = rl_oracle.normalize_advantage(tt['adv'])
+    out = rl_oracle.ppo_error(**tt, **p)
+    mix = cases.LOSS_MIX['ppo']
+    sum(c * l for c, l in zip(mix, out[:4])).backward()
+    td = cases.prepare('ppo', t, DEV)
+    data = b2.ppo_data(*[td[k] for k in ('logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv', 'return_',
+                                           'weight', 'logit_pretrained')])
+    loss, info = b2.ppo_error_adv_norm(data, **p)
+    for got, want in zip(loss, out[:4]):
+        assert torch.allclose(got.cpu(), want.detach(), rtol=1e-5, atol=1e-5)
+    assert abs(info.approx_kl - out[4]) < 1e-5 and abs(info.clipfrac - out[5]) < 2e-5
+    sum(c * l for c, l in zip(mix, loss)).backward()
+    for k in ('logit_new', 'value_new'):
+        a, b = td[k].grad.cpu().numpy(), tt[k].grad.numpy()
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max()), k
+    na = b2.normalize_advantage(td['adv'])
+    assert torch.allclose(na.cpu(), tt['adv'], rtol=1e-6, atol=1e-6)

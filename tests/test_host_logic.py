@@ -217,7 +217,10 @@ EXPECTED_CALLS = {
 def test_marshalling_dry_run(dry, name):
     op, tensors, params = cases.build_cases()[name]
     res = cases.run_api(b2.rl_utils, op, tensors, params)
-    assert dry.calls == EXPECTED_CALLS[op], dry.calls
+    want = EXPECTED_CALLS[op]
+    if op == 'gae' and tensors['value'].dim() == 1:
+        want = ['b200rl_gae_returns']  # ONE sequence: the segment-parallel single-CTA kernel (csrc/policy.cu)
+    assert dry.calls == want, dry.calls
     assert any(k.startswith('out_') for k in res)
     for k in cases.GRAD_INPUTS[op]:
         assert 'grad_' + k in res and res['grad_' + k].shape == tuple(tensors[k].shape)

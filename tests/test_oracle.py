@@ -118,3 +118,35 @@ def test_projection_conserves_mass():
     t['dist'] = torch.full_like(t['dist'], 1.0 / 51)
     _, per = rl_oracle.dist_nstep_td_error(**t, **p)
     assert torch.allclose(per, torch.full_like(per, float(np.log(51.0))), atol=1e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference not importable here')
+def test_policy_level_restatements_match_the_reference_lines():
+    """ding/policy/ppo.py cannot be imported (it pulls the whole framework), so its lines :276-292 and :304-306 are executed
+    here literally around the LIVE reference gae and compared with the oracle's restatement, bit for bit."""
+    ref = ref_loader.load()
+    g = torch.Generator().manual_seed(77)
+    for shape, std in (((400, ), None), ((400, ), 1.7320508), ((33, 5), 0.6)):
+        value = torch.randn(*shape, generator=g)
+        next_value = torch.randn(*shape, generator=g)
+        reward = torch.randn(*shape, generator=g)
+        done = (torch.rand(*shape, generator=g) < 0.05).float()
+        traj = done.clone()
+        traj[-1] = 1.0
+        got = rl_oracle.ppo_policy_gae_returns(value, next_value, reward, done, traj, 0.99, 0.95, std)
+        v, nv = value.clone(), next_value.clone()
+        if std is not None:
+            v *= std
+            nv *= std
+        adv = ref.gae(ref.gae_data(v, nv, reward, done, traj), 0.99, 0.95)
+        unnormalized_returns = v + adv
+        if std is not None:
+            val, ret = v / std, unnormalized_returns / std
+        else:
+            val, ret = v, unnormalized_returns
+        for a, b in zip(got[:4], (adv, val, ret, unnormalized_returns)):
+            assert torch.equal(a, b)
+        x = unnormalized_returns.numpy().reshape(-1)
+        assert got[4] == (float(np.mean(x)), float(np.var(x)), float(x.shape[0]))
+    adv = torch.randn(320, generator=g) * 3 + 1
+    assert torch.equal(rl_oracle.normalize_advantage(adv), (adv - adv.mean()) / (adv.std() + 1e-8))
