@@ -267,6 +267,28 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict_
         out[i] = __fdiv_rn(fsub(x[i], m), d);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// IMPALAPolicy._reshape_data masking (ding/policy/impala.py:316-322), one elementwise launch:
+//   weights_ = 1 - done;  values[1:] *= weights_;  weights = ones; weights[1:] = weights_[:-1];  rewards *= weights
+// backward: d/d values[t] = g[t] * (1 - done[t-1]) for t >= 1 (the in-place product of the reference), same kernel shape.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) impala_mask_kernel(const float* __restrict__ values, const float* __restrict__ rewards,
+                                                          const float* __restrict__ done, long long T, long long B,
+                                                          float* __restrict__ values_out, float* __restrict__ rewards_out,
+                                                          float* __restrict__ weights_out) {
+    pdl_prologue();
+    const long long n = (T + 1) * B;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const long long t = i / B;
+        const float m = t >= 1 ? fsub(1.f, done[i - B]) : 1.f;  // 1 - done[t-1]
+        values_out[i] = t >= 1 ? fmul(values[i], m) : values[i];
+        if (t < T) {
+            if (weights_out) weights_out[i] = m;
+            if (rewards_out) rewards_out[i] = fmul(rewards[i], m);
+        }
+    }
+}
+
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -336,5 +358,16 @@ extern "C" int b200rl_gae_returns(const float* value, float* next_value, const f
         (void)launch_k(returns_kernel, (int)grid, 256, 0, st, value, (const float*)adv, n, ra, ws_doubles(workspace),
                        ws_joins(workspace));
     }
+    return (int)cudaGetLastError();
+}
+
+/* rewards / rewards_out / weights_out nullable (the backward pass masks a gradient with values = g, the other outputs off) */
+extern "C" int b200rl_impala_mask(const float* values, const float* rewards, const float* done, long long T, long long B,
+                                  float* values_out, float* rewards_out, float* weights_out, void* stream) {
+    if (!values || !done || !values_out || T < 1 || B < 1 || (rewards_out && !rewards)) return B200RL_ERR_ARG;
+    long long grid = div_up((T + 1) * B, 256 * 4);
+    if (grid > 148 * 8) grid = 148 * 8;
+    (void)launch_k(impala_mask_kernel, (int)grid, 256, 0, (cudaStream_t)stream, values, rewards, done, T, B, values_out,
+                   rewards_out, weights_out);
     return (int)cudaGetLastError();
 }

@@ -570,6 +570,36 @@ class UPGOFunction(torch.autograd.Function):
         return (grad, ) + (None, ) * 8
 
 
+class ImpalaMaskFunction(torch.autograd.Function):
+    """IMPALAPolicy._reshape_data masking (ding/policy/impala.py:316-322): values (T+1, B) (differentiable), rewards, done
+    (T, B) -> (values', rewards', weights).  The reference multiplies ``values[1:]`` in place, so gradient reaches the critic
+    output through the mask; backward is the same kernel applied to the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, values, rewards, done):
+        T, B = rewards.shape
+        vo = torch.empty_like(values)
+        ro = torch.empty_like(rewards)
+        wo = torch.empty_like(rewards)
+        with torch.cuda.device(values.device):
+            rc = lib().b200rl_impala_mask(ptr(values), ptr(rewards), ptr(done), T, B, ptr(vo), ptr(ro), ptr(wo), stream_ptr())
+        _lib.check(rc, 'b200rl_impala_mask')
+        ctx.save_for_backward(done)
+        ctx.mark_non_differentiable(ro, wo)
+        return vo, ro, wo
+
+    @staticmethod
+    def backward(ctx, g_v, _g_r, _g_w):
+        done, = ctx.saved_tensors
+        T, B = done.shape
+        g = f32c(g_v)
+        out = torch.empty_like(g)
+        with torch.cuda.device(g.device):
+            rc = lib().b200rl_impala_mask(ptr(g), None, ptr(done), T, B, ptr(out), None, None, stream_ptr())
+        _lib.check(rc, 'b200rl_impala_mask')
+        return out, None, None
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # V-trace
 # ----------------------------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ from .td import (bdq_nstep_td_error, dist_1step_td_data, dist_1step_td_error, di
                  v_1step_td_data, v_1step_td_error, v_nstep_td_data, v_nstep_td_error)
 from .upgo import tb_cross_entropy, upgo_loss, upgo_returns
 from .value_rescale import value_inv_transform, value_transform
-from .vtrace import shape_fn_vtrace_discrete_action, vtrace_data, vtrace_error_discrete_action, vtrace_loss
+from .vtrace import impala_reshape_data, shape_fn_vtrace_discrete_action, vtrace_data, vtrace_error_discrete_action, vtrace_loss
 
 HOT_PATH_FUNCTIONS = [
     'gae', 'ppo_error', 'q_nstep_td_error', 'q_nstep_td_error_with_rescale', 'dist_nstep_td_error', 'td_lambda_error',

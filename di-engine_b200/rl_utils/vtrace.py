@@ -57,3 +57,27 @@ def vtrace_error_discrete_action(
     if host_out:
         p, vl, e = p.cpu(), vl.cpu(), e.cpu()
     return vtrace_loss(p, vl, e)
+
+
+def impala_reshape_data(values: torch.Tensor, rewards: torch.Tensor, done: torch.Tensor):
+    """
+    The masking ``IMPALAPolicy._reshape_data`` applies between the model output and ``vtrace_error_*`` (ding/policy/impala.py:
+    316-322) -- not a reference function, exactly those lines in one elementwise launch (csrc/policy.cu)::
+
+        weights_ = 1 - done.float();  weights = torch.ones_like(rewards)
+        values[1:] = values[1:] * weights_;  weights[1:] = weights_[:-1];  rewards = rewards * weights
+
+    values (T+1, B) -- gradient flows back through the mask to the critic output --, rewards and done (T, B).
+    Returns ``(values, rewards, weights)`` ready for ``vtrace_data(..., value=values, reward=rewards, weight=weights)``.
+    Unlike the reference the input ``values`` is not modified in place.
+    """
+    dev = ops.compute_device(values, rewards)
+    host_out = not values.is_cuda
+    v = ops.f32c(ops.to_device(values, dev), 'values')
+    r = ops.f32c(ops.to_device(rewards.detach(), dev), 'rewards')
+    d = ops.f32c(ops.to_device(done.detach(), dev), 'done')
+    if v.dim() != 2 or r.dim() != 2 or v.shape[0] != r.shape[0] + 1 or v.shape[1] != r.shape[1] or d.shape != r.shape:
+        raise ValueError("expected values (T+1, B), rewards / done (T, B); got %s / %s / %s" %
+                         (tuple(values.shape), tuple(rewards.shape), tuple(done.shape)))
+    vo, ro, wo = ops.ImpalaMaskFunction.apply(v, r, d)
+    return (vo.cpu(), ro.cpu(), wo.cpu()) if host_out else (vo, ro, wo)

@@ -73,6 +73,13 @@ B200RL_API int b200rl_adv_stats(const float* x, long long n, float* stats2, floa
                      void* stream);
 B200RL_API int b200rl_normalize(const float* x, const float* stats2, long long n, float* out, void* stream);
 
+/* IMPALAPolicy._reshape_data masking (ding/policy/impala.py:316-322) in one elementwise launch: values (T+1, B), rewards /
+ * done (T, B) -> values_out[t] = values[t] * (1 - done[t-1]) (t >= 1), weights_out[t] = 1 - done[t-1] (1 at t = 0),
+ * rewards_out = rewards * weights_out.  rewards_out / weights_out nullable: the backward pass masks d/d values with the same
+ * launch (values = upstream gradient). */
+B200RL_API int b200rl_impala_mask(const float* values, const float* rewards, const float* done, long long T, long long B,
+                       float* values_out, float* rewards_out, float* weights_out, void* stream);
+
 /* ---- ppo_error: ding/rl_utils/ppo.py:77-140 (policy :143-230, value :233-275, kl :30-54) -----------------------
  * S samples, G rows per sample (1, or the agent dim of ppo.py:199-200,:206-207), N logits.
  * logit_new/logit_old/logit_pretrained(nullable): (S*G, N); action: (S*G) int64;

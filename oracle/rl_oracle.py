@@ -96,6 +96,16 @@ def ppo_policy_gae_returns(value, next_value, reward, done, traj_flag, gamma, la
     return adv, v, ret, unnorm, (float(np.mean(x)), float(np.var(x)), float(x.shape[0]))
 
 
+def impala_reshape_data(values, rewards, done):
+    """policy/impala.py:316-322 (on a copy: the reference multiplies ``values[1:]`` in place)."""
+    weights_ = 1 - done.float()
+    weights = torch.ones_like(rewards)
+    values = torch.cat([values[:1], values[1:] * weights_], 0)
+    weights = torch.cat([weights[:1], weights_[:-1]], 0)
+    rewards = rewards * weights
+    return values, rewards, weights
+
+
 def normalize_advantage(adv):
     """policy/ppo.py:304-306: ``(adv - adv.mean()) / (adv.std() + 1e-8)`` (torch.std: unbiased)."""
     return (adv - adv.mean()) / (adv.std() + 1e-8)

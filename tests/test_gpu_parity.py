@@ -772,3 +772,30 @@ def test_ppo_error_adv_norm_matches_policy_lines(S, N):
         assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max()), k
     na = b2.normalize_advantage(td['adv'])
     assert torch.allclose(na.cpu(), tt['adv'], rtol=1e-6, atol=1e-6)
+
+
+def test_impala_reshape_data_then_vtrace_matches_policy_lines():
+    """IMPALAPolicy._reshape_data masking (policy/impala.py:316-322) in front of vtrace_error_discrete_action: values, losses
+    and the gradient that flows back THROUGH the mask to the critic output."""
+    g = torch.Generator().manual_seed(220)
+    for T, B, N in ((64, 8192, 6), (33, 257, 7)):
+        tgt = torch.randn(T, B, N, generator=g)
+        beh = tgt + 0.5 * torch.randn(T, B, N, generator=g)
+        act = torch.randint(0, N, (T, B), generator=g)
+        val = torch.randn(T + 1, B, generator=g)
+        rew = torch.rand(T, B, generator=g)
+        done = (torch.rand(T, B, generator=g) < 0.05).float()
+        vc, tc = val.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+        v2, r2, w2 = rl_oracle.impala_reshape_data(vc, rew, done)
+        want = rl_oracle.vtrace_error_discrete_action(tc, beh, act, v2, r2, w2, gamma=0.99, lambda_=0.95)
+        (want[0] + 0.5 * want[1] - 0.01 * want[2]).backward()
+        vd, td = val.clone().to(DEV).requires_grad_(True), tgt.clone().to(DEV).requires_grad_(True)
+        v3, r3, w3 = b2.impala_reshape_data(vd, rew.to(DEV), done.to(DEV))
+        assert torch.equal(v3.detach().cpu(), v2.detach()) and torch.equal(r3.cpu(), r2) and torch.equal(w3.cpu(), w2)
+        got = b2.vtrace_error_discrete_action(b2.vtrace_data(td, beh.to(DEV), act.to(DEV), v3, r3, w3), 0.99, 0.95)
+        for a, b in zip(got, want):
+            assert torch.allclose(a.cpu(), b.detach(), rtol=1e-5, atol=1e-5)
+        (got[0] + 0.5 * got[1] - 0.01 * got[2]).backward()
+        for a, b in ((vd, vc), (td, tc)):
+            a, b = a.grad.cpu().numpy(), b.grad.numpy()
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max())

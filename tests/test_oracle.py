@@ -150,3 +150,15 @@ def test_policy_level_restatements_match_the_reference_lines():
         assert got[4] == (float(np.mean(x)), float(np.var(x)), float(x.shape[0]))
     adv = torch.randn(320, generator=g) * 3 + 1
     assert torch.equal(rl_oracle.normalize_advantage(adv), (adv - adv.mean()) / (adv.std() + 1e-8))
+    # IMPALAPolicy._reshape_data, policy/impala.py:316-322, executed literally
+    values = torch.randn(9, 4, generator=g)
+    rewards = torch.rand(8, 4, generator=g)
+    done = (torch.rand(8, 4, generator=g) < 0.3)
+    got = rl_oracle.impala_reshape_data(values, rewards, done)
+    v = values.clone()
+    weights_ = 1 - done.float()
+    weights = torch.ones_like(rewards)
+    v[1:] = v[1:] * weights_
+    weights[1:] = weights_[:-1]
+    r = rewards * weights
+    assert torch.equal(got[0], v) and torch.equal(got[1], r) and torch.equal(got[2], weights)

@@ -1,6 +1,7 @@
-"""Eager replay of the benchmark's learner step (config D) for ncu captures -- no graphs, no CPU baseline.
+"""Eager replay of a benchmark workload's step (bench.py --config D|B|C|E) for ncu captures -- no graphs, no CPU baseline.
 
-    ncu --set full ... -k regex:"gae_tile|ppo_fwd|ppo_bwd" -s 12 -c 3 -o gpurun_out/prof python tools/prof_step.py
+    ncu --set full --clock-control none --import-source on -k regex:gae_ppo_ws -s 4 -c 1 -o gpurun_out/prof \
+        python tools/prof_step.py D 8
 """
 import os
 import sys
@@ -10,11 +11,11 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-mode = sys.argv[2] if len(sys.argv) > 2 else 'onepass'
-mode = {'onepass': 'onepass', 'three': True, 'unfused': False}[mode]
-sets = [bench.DeviceStep(bench.make_batch(i), 'cuda:0', fused=mode) for i in range(4)]
+cfg = sys.argv[1] if len(sys.argv) > 1 else 'D'
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+wl = bench.WORKLOADS[cfg]()
+sets = [wl.device_step(wl.make_batch(i), 'cuda:0') for i in range(4)]
 for i in range(steps):
     sets[i % 4]()
 torch.cuda.synchronize()
-print('ran', steps, 'steps')
+print('ran', steps, 'steps of config', cfg)
