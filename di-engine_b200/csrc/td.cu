@@ -221,7 +221,11 @@ struct DntdArgs {
     float* grad_unit;  // nullable (R, N, n_atom): d loss / d dist for a unit upstream gradient
 };
 
-template <int NT>
+// NJ = atoms per lane (ceil(n_atom / 32), 2 for C51): every global operand of a row -- the chosen rows of dist / next_n_dist,
+// the support, the n-step rewards -- is requested in ONE batch right after the two action indices have arrived, and lives in
+// registers from then on (the first build reloaded dist[j] in every iteration of the gradient loop: 12 dependent L2 round
+// trips per row, 10.8 us at config C; profiles/r02_ncu_small_kernels.md).
+template <int NT, int NJ>
 __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
     pdl_prologue();
     extern __shared__ float s_proj[];  // [NT/32][n_atom]
@@ -231,7 +235,19 @@ __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
     float acc[1] = {0.f};
     if (r < a.R) {
         const long long b = r / a.A;
-        for (int j = lane; j < a.n_atom; j += 32) pj[j] = 0.f;
+        const int sel = (int)a.act[r], nsel = (int)a.next_act[r];
+        const float* nd = a.next_dist + (r * a.N + nsel) * a.n_atom;
+        const float* dd = a.dist + (r * a.N + sel) * a.n_atom;
+        float p_[NJ], d_[NJ], z_[NJ];
+#pragma unroll
+        for (int u = 0; u < NJ; ++u) {
+            const int j = lane + 32 * u;
+            const bool ok = j < a.n_atom;
+            p_[u] = ok ? nd[j] : 0.f;
+            d_[u] = ok ? dd[j] : 1.f;
+            z_[u] = ok ? a.support[j] : 0.f;
+            if (ok) pj[j] = 0.f;
+        }
         float rf = 1.f, ret = 0.f;
         for (int i = 0; i < a.nstep; ++i) {  // matmul(reward_factor, reward), td.py:453-456
             ret = fadd(ret, fmul(rf, a.reward[(long long)i * a.B + b]));
@@ -239,43 +255,56 @@ __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
         }
         const float vg = a.value_gamma ? a.value_gamma[b * a.value_gamma_stride] : a.gamma_pow_n;
         const float scale = fmul(fsub(1.f, a.done[b]), vg);  // (1-done) * gamma**n, td.py:492-498
-        const float* nd = a.next_dist + (r * a.N + a.next_act[r]) * a.n_atom;
-        const float* dd = a.dist + (r * a.N + a.act[r]) * a.n_atom;
+        const float w = a.weight ? a.weight[r * a.weight_stride] : 1.f;
         __syncwarp();
-        for (int j = lane; j < a.n_atom; j += 32) {
-            float tz = fadd(ret, fmul(scale, a.support[j]));
-            tz = fminf(fmaxf(tz, a.v_min), a.v_max);
-            const float pos = __fdiv_rn(fsub(tz, a.v_min), a.delta_z);  // td.py:500
-            float lo = floorf(pos), hi = ceilf(pos);
-            if (hi > 0.f && lo == hi) lo -= 1.f;                          // td.py:504
-            if (lo < (float)(a.n_atom - 1) && lo == hi) hi += 1.f;        // td.py:505
-            const float p = nd[j];
-            atomicAdd(&pj[(int)lo], fmul(p, fsub(hi, pos)));
-            atomicAdd(&pj[(int)hi], fmul(p, fsub(pos, lo)));
+#pragma unroll
+        for (int u = 0; u < NJ; ++u) {
+            const int j = lane + 32 * u;
+            if (j < a.n_atom) {
+                float tz = fadd(ret, fmul(scale, z_[u]));
+                tz = fminf(fmaxf(tz, a.v_min), a.v_max);
+                const float pos = __fdiv_rn(fsub(tz, a.v_min), a.delta_z);  // td.py:500
+                float lo = floorf(pos), hi = ceilf(pos);
+                if (hi > 0.f && lo == hi) lo -= 1.f;                          // td.py:504
+                if (lo < (float)(a.n_atom - 1) && lo == hi) hi += 1.f;        // td.py:505
+                atomicAdd(&pj[(int)lo], fmul(p_[u], fsub(hi, pos)));
+                atomicAdd(&pj[(int)hi], fmul(p_[u], fsub(pos, lo)));
+            }
         }
         __syncwarp();
         float td = 0.f;
         bool bad = false;
-        for (int j = lane; j < a.n_atom; j += 32) {
-            const float d = dd[j], m = pj[j];
-            bad |= !(d > 0.f);
-            td += logf(d) * m;
-            a.proj[r * a.n_atom + j] = m;
+        float m_[NJ];
+#pragma unroll
+        for (int u = 0; u < NJ; ++u) {
+            const int j = lane + 32 * u;
+            m_[u] = 0.f;
+            if (j < a.n_atom) {
+                m_[u] = pj[j];
+                bad |= !(d_[u] > 0.f);
+                td += logf(d_[u]) * m_[u];
+                a.proj[r * a.n_atom + j] = m_[u];
+            }
         }
         td = -warp_sum(td);
         if (a.bad_flag && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.bad_flag, 1);
-        const float w = a.weight ? a.weight[r * a.weight_stride] : 1.f;
         if (lane == 0) {
             a.td_err[r] = td;
             acc[0] = td * w;
         }
         if (a.grad_unit) {  // dense (N, n_atom) gradient block of the row: non-zero on the chosen action only
-            const int sel = (int)a.act[r];
             const float c = -w / (float)a.R;
             float* gr = a.grad_unit + r * a.N * a.n_atom;
-            for (int n = 0; n < a.N; ++n)
-                for (int j = lane; j < a.n_atom; j += 32)
-                    gr[n * a.n_atom + j] = (n == sel) ? c * pj[j] / dd[j] : 0.f;
+            float g_[NJ];
+#pragma unroll
+            for (int u = 0; u < NJ; ++u) g_[u] = c * m_[u] / d_[u];
+            for (int n = 0; n < a.N; ++n) {
+#pragma unroll
+                for (int u = 0; u < NJ; ++u) {
+                    const int j = lane + 32 * u;
+                    if (j < a.n_atom) gr[n * a.n_atom + j] = (n == sel) ? g_[u] : 0.f;
+                }
+            }
         }
     }
     if (gridDim.x <= FX_MAX_GRID) {
@@ -646,18 +675,22 @@ extern "C" int b200rl_dntd_fwd(const float* dist, const float* next_n_dist, cons
     a.loss = loss; a.td_err = td_error_per_sample; a.proj = proj_saved; a.bad_flag = bad_flag;
     a.grad_unit = grad_dist_unit;
     if (workspace_bytes < WS_MIN_BYTES) return B200RL_ERR_WORKSPACE;
-    if (a.R <= 16 * 511 && n_atom <= 384) {  // 16 rows per CTA: few enough CTAs for the one-round-trip reduction
-        constexpr int NT = 512;
+    if (n_atom > 256) return B200RL_ERR_ARG;  // 8 atoms per lane in registers
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a.R <= 8 * 511) {  // 8 rows per CTA: few enough CTAs for the one-round-trip reduction
+        constexpr int NT = 256;
         const size_t sm = (size_t)(NT / 32) * n_atom * sizeof(float);
-        (void)launch_k(dntd_fwd_kernel<NT>, div_up(a.R, NT / 32), NT, sm, (cudaStream_t)stream, a, workspace);
+        const int grid = div_up(a.R, NT / 32);
+        if (n_atom <= 64) (void)launch_k(dntd_fwd_kernel<NT, 2>, grid, NT, sm, st, a, workspace);
+        else (void)launch_k(dntd_fwd_kernel<NT, 8>, grid, NT, sm, st, a, workspace);
         return (int)cudaGetLastError();
     }
     constexpr int NT = 128;
     const int grid = div_up(a.R, NT / 32);
     if ((size_t)(WS_CTRL_WORDS + grid) > WS_PARTIAL_LIMIT_WORDS) return B200RL_ERR_WORKSPACE;
     const size_t sm = (size_t)(NT / 32) * n_atom * sizeof(float);
-    if (sm > 48 * 1024) return B200RL_ERR_ARG;
-    (void)launch_k(dntd_fwd_kernel<NT>, grid, NT, sm, (cudaStream_t)stream, a, workspace);
+    if (n_atom <= 64) (void)launch_k(dntd_fwd_kernel<NT, 2>, grid, NT, sm, st, a, workspace);
+    else (void)launch_k(dntd_fwd_kernel<NT, 8>, grid, NT, sm, st, a, workspace);
     return (int)cudaGetLastError();
 }
 
