@@ -9,6 +9,7 @@
 
 #include "../../include/b200rl.h"
 #include "common.cuh"
+#include "ppo_math.cuh"  // lg2f_ / rcpf_ / kLn2
 
 namespace b200rl {
 
@@ -89,29 +90,45 @@ __global__ void __launch_bounds__(NT) qntd_fwd_kernel(QntdArgs a, float* ws) {
     s_act[threadIdx.x] = -1;
     if (s < a.S) {
         const long long tq_ = s / a.Bcol, b = s - tq_ * a.Bcol;  // sequence step / batch column (tq_ = 0 when Bcol == S)
-        const float nd = fsub(1.f, a.done[s]);
+        // every per-sample operand is requested before any is used: a load inside the n-step loop is one L2 round trip per step
+        const float* __restrict__ rw = a.cum_reward ? a.reward + s : a.reward + tq_ * a.nstep * a.Bcol + b;
+        const size_t Bi = (size_t)a.Bcol;
+        const int nrw = a.cum_reward ? 1 : a.nstep;
+        float rwv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rwv[i] = i < nrw ? rw[i * Bi] : 0.f;
+        const float dn = a.done[s];
         const float w = a.weight ? a.weight[s] : 1.f;
+        const float vgl = a.value_gamma ? a.value_gamma[s * a.value_gamma_stride] : a.gamma_pow_n;
+        const float g = a.gamma_ps ? a.gamma_ps[b] : a.gamma;
+        const int act0 = (int)a.action[s * a.G], nact0 = (int)a.next_action[s * a.G];
+        const float q0 = a.q[s * a.G * a.N + act0], nq0 = a.next_q[s * a.G * a.N + nact0];
+        const float nd = fsub(1.f, dn);
         float ret = 0.f, vg;
         if (a.cum_reward) {
-            ret = a.reward[s];
-            vg = a.value_gamma ? a.value_gamma[s * a.value_gamma_stride] : a.gamma_pow_n;
+            ret = rwv[0];
+            vg = vgl;
         } else {
-            const float g = a.gamma_ps ? a.gamma_ps[b] : a.gamma;
-            const float* rw = a.reward + tq_ * a.nstep * a.Bcol + b;
             float rf = 1.f;
-            for (int i = 0; i < a.nstep; ++i) {  // td.py:261-264 / :277-281
-                ret = fadd(ret, fmul(rw[(long long)i * a.Bcol], rf));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {  // td.py:261-264 / :277-281
+                if (i < a.nstep) {
+                    ret = fadd(ret, fmul(rwv[i], rf));
+                    rf = fmul(g, rf);
+                }
+            }
+            for (int i = 8; i < a.nstep; ++i) {
+                ret = fadd(ret, fmul(rw[i * Bi], rf));
                 rf = fmul(g, rf);
             }
-            if (a.gamma_ps) vg = rf;  // reward_factor[nstep]
-            else vg = a.value_gamma ? a.value_gamma[s * a.value_gamma_stride] : a.gamma_pow_n;
+            vg = a.gamma_ps ? rf : vgl;  // reward_factor[nstep] for the NGU list-gamma form
         }
         float td_sum = 0.f;
         for (int gi = 0; gi < a.G; ++gi) {
             const long long r = s * a.G + gi;
-            const int act = (int)a.action[r];
-            const float q_sa = a.q[r * a.N + act];
-            float tq = a.next_q[r * a.N + a.next_action[r]];
+            const int act = gi == 0 ? act0 : (int)a.action[r];
+            const float q_sa = gi == 0 ? q0 : a.q[r * a.N + act];
+            float tq = gi == 0 ? nq0 : a.next_q[r * a.N + a.next_action[r]];
             if (a.rescale) tq = value_h_inv(tq, a.eps, a.four_eps, a.two_eps);
             float target = fadd(ret, fmul(fmul(vg, tq), nd));  // td.py:266 / :273 / :282 / :712-715
             if (a.rescale) target = value_h(target, a.eps);
@@ -175,18 +192,19 @@ __global__ void qntd_bwd_kernel(const float* __restrict__ dcrit, const float* __
     pdl_prologue();
     const float g = g_loss ? *g_loss : 0.f;
     if (skip_if_unit && !g_td && g == 1.f) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S * G * N) return;
-    const long long r = i / N;
-    const int j = (int)(i - r * N);
-    float out = 0.f;
-    if (j == (int)action[r]) {
-        const long long s = r / G;
-        float c = g * (weight ? weight[s] : 1.f) * inv_div;
-        if (g_td) c += group_mean ? g_td[s] / (float)G : g_td[r];
-        out = c * dcrit[r];
+    const long long n = S * G * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / N;
+        const int j = (int)(i - r * N);
+        float out = 0.f;
+        if (j == (int)action[r]) {
+            const long long s = r / G;
+            float c = g * (weight ? weight[s] : 1.f) * inv_div;
+            if (g_td) c += group_mean ? g_td[s] / (float)G : g_td[r];
+            out = c * dcrit[r];
+        }
+        grad_q[i] = out;
     }
-    grad_q[i] = out;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -231,59 +249,98 @@ __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
     extern __shared__ float s_proj[];  // [NT/32][n_atom]
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * (NT / 32) + wid;
-    float* pj = s_proj + wid * a.n_atom;
+    const int na = a.n_atom;
+    float* pj = s_proj + wid * na;
     float acc[1] = {0.f};
+    // a row's work is one serial chain in one warp (~700 instructions): 32-bit index arithmetic, MUFU log / reciprocal where
+    // the reference's bits do not depend on them (the bin positions keep the IEEE division of td.py:500)
     if (r < a.R) {
         const long long b = r / a.A;
         const int sel = (int)a.act[r], nsel = (int)a.next_act[r];
-        const float* nd = a.next_dist + (r * a.N + nsel) * a.n_atom;
-        const float* dd = a.dist + (r * a.N + sel) * a.n_atom;
+        const float* __restrict__ nd = a.next_dist + (r * a.N + nsel) * na;
+        const float* __restrict__ dd = a.dist + (r * a.N + sel) * na;
         float p_[NJ], d_[NJ], z_[NJ];
 #pragma unroll
         for (int u = 0; u < NJ; ++u) {
             const int j = lane + 32 * u;
-            const bool ok = j < a.n_atom;
+            const bool ok = j < na;
             p_[u] = ok ? nd[j] : 0.f;
             d_[u] = ok ? dd[j] : 1.f;
             z_[u] = ok ? a.support[j] : 0.f;
             if (ok) pj[j] = 0.f;
         }
+        // every per-sample scalar is requested before any is used (a load inside the n-step loop costs one L2 round trip per
+        // step: the first build spent 6 serialised round trips here, ~4 of its 8 us)
+        const float* __restrict__ rw = a.reward + b;
+        const size_t Bi = (size_t)a.B;
+        float rwv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rwv[i] = i < a.nstep ? rw[i * Bi] : 0.f;
+        const float dn = a.done[b];
+        const float vg = a.value_gamma ? a.value_gamma[b * a.value_gamma_stride] : a.gamma_pow_n;
+        const float w = a.weight ? a.weight[r * a.weight_stride] : 1.f;
         float rf = 1.f, ret = 0.f;
-        for (int i = 0; i < a.nstep; ++i) {  // matmul(reward_factor, reward), td.py:453-456
-            ret = fadd(ret, fmul(rf, a.reward[(long long)i * a.B + b]));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // matmul(reward_factor, reward), td.py:453-456
+            if (i < a.nstep) {
+                ret = fadd(ret, fmul(rf, rwv[i]));
+                rf = fmul(a.gamma, rf);
+            }
+        }
+        for (int i = 8; i < a.nstep; ++i) {
+            ret = fadd(ret, fmul(rf, rw[i * Bi]));
             rf = fmul(a.gamma, rf);
         }
-        const float vg = a.value_gamma ? a.value_gamma[b * a.value_gamma_stride] : a.gamma_pow_n;
-        const float scale = fmul(fsub(1.f, a.done[b]), vg);  // (1-done) * gamma**n, td.py:492-498
-        const float w = a.weight ? a.weight[r * a.weight_stride] : 1.f;
+        const float scale = fmul(fsub(1.f, dn), vg);  // (1-done) * gamma**n, td.py:492-498
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < NJ; ++u) {
             const int j = lane + 32 * u;
-            if (j < a.n_atom) {
+            int key = -1 - lane;  // lanes past n_atom: unique keys, zero contributions
+            float clo = 0.f, chi = 0.f;
+            if (j < na) {
                 float tz = fadd(ret, fmul(scale, z_[u]));
                 tz = fminf(fmaxf(tz, a.v_min), a.v_max);
                 const float pos = __fdiv_rn(fsub(tz, a.v_min), a.delta_z);  // td.py:500
                 float lo = floorf(pos), hi = ceilf(pos);
                 if (hi > 0.f && lo == hi) lo -= 1.f;                          // td.py:504
-                if (lo < (float)(a.n_atom - 1) && lo == hi) hi += 1.f;        // td.py:505
-                atomicAdd(&pj[(int)lo], fmul(p_[u], fsub(hi, pos)));
-                atomicAdd(&pj[(int)hi], fmul(p_[u], fsub(pos, lo)));
+                if (lo < (float)(na - 1) && lo == hi) hi += 1.f;              // td.py:505 (now hi == lo + 1 always)
+                key = (int)lo;
+                clo = fmul(p_[u], fsub(hi, pos));
+                chi = fmul(p_[u], fsub(pos, lo));
+            }
+            // Tz is monotone in the atom index, so lanes that hit the same bin are CONTIGUOUS (a terminal sample, done = 1, or a
+            // clamped tail sends all of them to one bin): a segmented warp scan adds them up and only the last lane of a
+            // segment touches shared memory -- the 32-way CAS loop of the first build cost up to ~3 us per such row
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int k2 = __shfl_up_sync(0xffffffffu, key, d);
+                const float l2 = __shfl_up_sync(0xffffffffu, clo, d), h2 = __shfl_up_sync(0xffffffffu, chi, d);
+                if (lane >= d && k2 == key) {
+                    clo += l2;
+                    chi += h2;
+                }
+            }
+            const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+            if (key >= 0 && (lane == 31 || knext != key)) {
+                atomicAdd(&pj[key], clo);
+                atomicAdd(&pj[key + 1], chi);
             }
         }
         __syncwarp();
         float td = 0.f;
         bool bad = false;
         float m_[NJ];
+        float* __restrict__ prow = a.proj + r * na;
 #pragma unroll
         for (int u = 0; u < NJ; ++u) {
             const int j = lane + 32 * u;
             m_[u] = 0.f;
-            if (j < a.n_atom) {
+            if (j < na) {
                 m_[u] = pj[j];
                 bad |= !(d_[u] > 0.f);
-                td += logf(d_[u]) * m_[u];
-                a.proj[r * a.n_atom + j] = m_[u];
+                td = fmaf(lg2f_(d_[u]) * kLn2, m_[u], td);
+                prow[j] = m_[u];
             }
         }
         td = -warp_sum(td);
@@ -294,15 +351,16 @@ __global__ void __launch_bounds__(NT) dntd_fwd_kernel(DntdArgs a, float* ws) {
         }
         if (a.grad_unit) {  // dense (N, n_atom) gradient block of the row: non-zero on the chosen action only
             const float c = -w / (float)a.R;
-            float* gr = a.grad_unit + r * a.N * a.n_atom;
+            float* __restrict__ gr = a.grad_unit + r * a.N * na;
             float g_[NJ];
 #pragma unroll
-            for (int u = 0; u < NJ; ++u) g_[u] = c * m_[u] / d_[u];
-            for (int n = 0; n < a.N; ++n) {
+            for (int u = 0; u < NJ; ++u) g_[u] = c * m_[u] * rcpf_(d_[u]);
+            const int Ni = a.N;
+            for (int n = 0; n < Ni; ++n) {
 #pragma unroll
                 for (int u = 0; u < NJ; ++u) {
                     const int j = lane + 32 * u;
-                    if (j < a.n_atom) gr[n * a.n_atom + j] = (n == sel) ? g_[u] : 0.f;
+                    if (j < na) gr[n * na + j] = (n == sel) ? g_[u] : 0.f;
                 }
             }
         }
@@ -323,21 +381,22 @@ __global__ void dntd_bwd_kernel(const float* __restrict__ dist, const long long*
     pdl_prologue();
     // skip_if_unit: the forward launch already wrote grad_dist for a unit upstream gradient -- verify and leave
     if (skip_if_unit && !g_td && g_loss && *g_loss == 1.f) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_row = (long long)N * n_atom;
-    if (i >= R * per_row) return;
-    const long long r = i / per_row;
-    const int rem = (int)(i - r * per_row);
-    const int n = rem / n_atom, j = rem - n * n_atom;
-    float out = 0.f;
-    if (n == (int)act[r]) {
-        const float g = g_loss ? *g_loss : 0.f;
-        const float w = weight ? weight[r * weight_stride] : 1.f;
-        float c = g * w / (float)R;
-        if (g_td) c += g_td[r];  // the unweighted per-sample error carries gradient too (td.py:519)
-        out = -c * proj[r * n_atom + j] / dist[i];
+    const float g = g_loss ? *g_loss : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < R * per_row;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / per_row;
+        const int rem = (int)(i - r * per_row);
+        const int n = rem / n_atom, j = rem - n * n_atom;
+        float out = 0.f;
+        if (n == (int)act[r]) {
+            const float w = weight ? weight[r * weight_stride] : 1.f;
+            float c = g * w / (float)R;
+            if (g_td) c += g_td[r];  // the unweighted per-sample error carries gradient too (td.py:519)
+            out = -c * proj[r * n_atom + j] / dist[i];
+        }
+        grad_dist[i] = out;
     }
-    grad_dist[i] = out;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -649,9 +708,10 @@ extern "C" int b200rl_qntd_bwd(const float* dcrit_saved, const float* weight, co
                                const float* g_loss, const float* g_td, long long S, long long G, long long N,
                                int group_mean, long long seq_len, int skip_if_unit, float* grad_q, void* stream) {
     if (S <= 0 || G < 1 || N < 1 || !dcrit_saved || !action || !grad_q) return B200RL_ERR_ARG;
-    const int grid = div_up(S * G * N, 256);
+    long long grid = div_up(S * G * N, 256);
+    if (grid > 148 * 8) grid = 148 * 8;  // grid-stride; the verification launch normally returns at once
     const float inv_div = (float)(1.0 / qntd_loss_div(S, G, seq_len));
-    (void)launch_k(qntd_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dcrit_saved, weight, action, g_loss, g_td, S,
+    (void)launch_k(qntd_bwd_kernel, (int)grid, 256, 0, (cudaStream_t)stream, dcrit_saved, weight, action, g_loss, g_td, S,
                    (int)G, (int)N, group_mean, inv_div, skip_if_unit, grad_q);
     return (int)cudaGetLastError();
 }
@@ -698,8 +758,9 @@ extern "C" int b200rl_dntd_bwd(const float* dist, const long long* act, const fl
                                long long weight_stride, const float* g_loss, const float* g_td, long long R,
                                long long N, int n_atom, int skip_if_unit, float* grad_dist, void* stream) {
     if (R <= 0 || N < 1 || n_atom < 2 || !dist || !act || !proj_saved || !grad_dist) return B200RL_ERR_ARG;
-    const int grid = div_up(R * N * n_atom, 256);
-    (void)launch_k(dntd_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dist, act, proj_saved, weight, weight_stride, g_loss, g_td,
+    long long grid = div_up(R * N * n_atom, 256);
+    if (grid > 148 * 8) grid = 148 * 8;  // grid-stride; the verification launch normally returns at once
+    (void)launch_k(dntd_bwd_kernel, (int)grid, 256, 0, (cudaStream_t)stream, dist, act, proj_saved, weight, weight_stride, g_loss, g_td,
                    R, (int)N, n_atom, skip_if_unit, grad_dist);
     return (int)cudaGetLastError();
 }
