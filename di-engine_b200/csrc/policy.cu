@@ -139,7 +139,25 @@ __global__ void __launch_bounds__(GS_NT) gae_seq_kernel(const float* __restrict_
             const int hi = s_end[tid];
             const int lo = tid ? s_end[tid - 1] + 1 : 0;
             float carry = 0.f;  // the step after a segment end contributes f * carry with f == 0 -> +0 exactly as in the loop
-            for (int t = hi; t >= lo; --t) {
+            // 16 steps at a time: the shared-memory operands are in registers before the dependent chain needs them (a
+            // load / compute / store loop costs ~40 cycles per step, the chain alone 8)
+            int t = hi;
+            for (; t - 15 >= lo; t -= 16) {
+                float d[16], f[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    d[k] = s_d[t - k];
+                    f[k] = s_f[t - k];
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    carry = fadd(d[k], fmul(f[k], carry));
+                    d[k] = carry;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) s_d[t - k] = d[k];
+            }
+            for (; t >= lo; --t) {
                 carry = fadd(s_d[t], fmul(s_f[t], carry));
                 s_d[t] = carry;
             }

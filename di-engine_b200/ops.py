@@ -27,7 +27,33 @@ def require_cuda():
 
 
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    """raw cudaStream_t of torch's current stream on the current device (the fast private accessor when torch has it: the
+    public ``torch.cuda.current_stream().cuda_stream`` costs ~1.5 us of host time per call, and an operator asks twice)"""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:
+        return torch.cuda.current_stream().cuda_stream
+
+
+class _NoCtx:
+
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NOCTX = _NoCtx()
+
+
+def on_device(device):
+    """``torch.cuda.device(device)`` only when ``device`` is not already current (entering the guard costs several
+    microseconds of host time -- more than the launch it protects at the learner's real batch sizes)"""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NOCTX
+    return torch.cuda.device(device)
 
 
 def workspace(device):
@@ -113,7 +139,7 @@ def gae_(value, next_value, reward, done, traj_flag, gamma, lambda_, agents, mas
         # ONE sequence (the real PPO learner, ding/policy/ppo.py:280-282: n_sample steps of concatenated trajectories): the
         # segment-parallel single-CTA kernel of csrc/policy.cu instead of one lane walking all T steps
         return gae_returns_(value, next_value, reward, done, traj_flag, gamma, lambda_, 1, 0.0, False, False, mask_inplace)[0]
-    with torch.cuda.device(value.device):
+    with on_device(value.device):
         rc = lib().b200rl_gae(
             ptr(value), ptr(next_value), ptr(reward), ptr(done), ptr(traj_flag), ptr(adv), T, C, agents, float(gamma),
             float(lambda_), 1 if mask_inplace else 0, stream_ptr()
@@ -134,7 +160,7 @@ def gae_returns_(value, next_value, reward, done, traj_flag, gamma, lambda_, age
     vout = torch.empty_like(value) if (want_returns and vscale != 0.0) else None
     rout = torch.empty_like(value) if (want_returns and vscale != 0.0) else None
     stats = torch.empty(3, dtype=torch.float32, device=dev) if want_stats else None
-    with torch.cuda.device(dev):
+    with on_device(dev):
         ws = workspace(dev)
         rc = lib().b200rl_gae_returns(
             ptr(value), ptr(next_value), ptr(reward), ptr(done), ptr(traj_flag), T, C, agents, float(gamma), float(lambda_),
@@ -148,7 +174,7 @@ def gae_returns_(value, next_value, reward, done, traj_flag, gamma, lambda_, age
 def adv_stats_(x):
     """{mean, std(unbiased) + 1e-8} of ``x`` as two device floats (ding/policy/ppo.py:304-306), one launch."""
     out = torch.empty(2, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         ws = workspace(x.device)
         rc = lib().b200rl_adv_stats(ptr(x), x.numel(), ptr(out), ptr(ws), ws.numel() * 4, stream_ptr())
     _lib.check(rc, 'b200rl_adv_stats')
@@ -157,7 +183,7 @@ def adv_stats_(x):
 
 def normalize_(x, stats):
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with on_device(x.device):
         rc = lib().b200rl_normalize(ptr(x), ptr(stats), x.numel(), ptr(out), stream_ptr())
     _lib.check(rc, 'b200rl_normalize')
     return out
@@ -202,7 +228,7 @@ class PPOFunction(torch.autograd.Function):
         cfg = (S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, ptr(adv_stats))
         ctx.fused = False
         want_grad = PPO_FUSED_BACKWARD and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        with torch.cuda.device(dev):
+        with on_device(dev):
             ws = workspace(dev)
             if want_grad:
                 grad_logit = torch.empty_like(logit_new)
@@ -243,7 +269,7 @@ class PPOFunction(torch.autograd.Function):
             grad_logit = torch.empty_like(logit_new)
             grad_value = torch.empty_like(value_new)
             p_used, p_hint = None, None
-        with torch.cuda.device(dev):
+        with on_device(dev):
             rc = lib().b200rl_ppo_bwd(
                 ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old), ptr(adv),
                 ptr(return_), ptr(weight), *ctx.cfg, pp, pv, pe, pk, p_used, p_hint, ptr(grad_logit), ptr(grad_value),
@@ -267,7 +293,7 @@ class GAEPPOFunction(torch.autograd.Function):
         grad_logit = torch.empty_like(logit_new) if want_grad else None
         grad_value = torch.empty_like(value_new) if want_grad else None
         g_used = torch.empty(4, dtype=torch.float32, device=dev) if want_grad else None
-        with torch.cuda.device(dev):
+        with on_device(dev):
             ws = workspace(dev)
             rc = lib().b200rl_gae_ppo_fwd_grad(
                 ptr(value), ptr(next_value), ptr(reward), ptr(done), ptr(traj_flag), T, B, gamma, lambda_, 1,
@@ -297,7 +323,7 @@ def ppo_value_(value_new, value_old, return_, weight, clip_ratio, use_value_clip
     loss = torch.empty((), dtype=torch.float32, device=dev)
     want_grad = value_new.requires_grad and torch.is_grad_enabled()
     dvalue = torch.empty_like(value_new) if want_grad else None
-    with torch.cuda.device(dev):
+    with on_device(dev):
         ws = workspace(dev)
         rc = lib().b200rl_ppo_value_fwd(
             ptr(value_new), ptr(value_old), ptr(return_), ptr(weight), value_new.numel(), float(clip_ratio),
@@ -332,7 +358,7 @@ class QNStepTDFunction(torch.autograd.Function):
         target = torch.empty(R, dtype=torch.float32, device=dev)
         prio = torch.empty(S // seq_len, dtype=torch.float32, device=dev) if want_priority else None
         grad_unit = torch.empty(R, N, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
-        with torch.cuda.device(dev):
+        with on_device(dev):
             ws = workspace(dev)
             rc = lib().b200rl_qntd_fwd(
                 ptr(q), ptr(next_n_q), ptr(action), ptr(next_n_action), ptr(reward), ptr(done), ptr(weight),
@@ -368,7 +394,7 @@ class QNStepTDFunction(torch.autograd.Function):
             skip = 1
         else:
             grad_q = torch.empty(S * G, N, dtype=torch.float32, device=dcrit.device)
-        with torch.cuda.device(dcrit.device):
+        with on_device(dcrit.device):
             rc = lib().b200rl_qntd_bwd(ptr(dcrit), ptr(weight), ptr(action), pg, ptd, S, G, N, group_mean, seq_len, skip,
                                        ptr(grad_q), stream_ptr())
         _lib.check(rc, 'b200rl_qntd_bwd')
@@ -391,7 +417,7 @@ class DistNStepTDFunction(torch.autograd.Function):
         td = torch.empty(R, dtype=torch.float32, device=dev)
         proj = torch.empty(R, n_atom, dtype=torch.float32, device=dev)
         grad_unit = torch.empty_like(dist) if ctx.needs_input_grad[0] else None
-        with torch.cuda.device(dev):
+        with on_device(dev):
             ws = workspace(dev)
             rc = lib().b200rl_dntd_fwd(
                 ptr(dist), ptr(next_n_dist), ptr(act), ptr(next_n_act), ptr(reward), ptr(done), ptr(weight), w_stride,
@@ -417,7 +443,7 @@ class DistNStepTDFunction(torch.autograd.Function):
         ctx.spec = None
         if grad is None or g_td is not None:  # a repeated backward (the first buffer may belong to .grad) / per-sample path
             grad, skip = torch.empty_like(dist), 0
-        with torch.cuda.device(dist.device):
+        with on_device(dist.device):
             rc = lib().b200rl_dntd_bwd(
                 ptr(dist), ptr(act), ptr(proj), ptr(weight), w_stride, pg, ptr(keep_td), R, N, n_atom, skip, ptr(grad),
                 stream_ptr()
@@ -432,7 +458,7 @@ class DistNStepTDFunction(torch.autograd.Function):
 def lambda_returns_(value, reward, gammas, gamma, lambdas, lambda_, done, upgo_mode):
     T, B = reward.shape
     ret = torch.empty_like(reward)
-    with torch.cuda.device(value.device):
+    with on_device(value.device):
         rc = lib().b200rl_lambda_returns(
             ptr(value), ptr(reward), ptr(gammas), float(gamma), ptr(lambdas), float(lambda_), ptr(done),
             1 if upgo_mode else 0, T, B, ptr(ret), stream_ptr()
@@ -464,7 +490,7 @@ class LambdaReturnsFunction(torch.autograd.Function):
         gr = torch.empty_like(reward) if need[1] else None
         gg = torch.empty_like(reward) if (need[2] and gammas is not None) else None
         gl = torch.empty_like(reward) if (need[3] and lambdas is not None) else None
-        with torch.cuda.device(value.device):
+        with on_device(value.device):
             rc = lib().b200rl_lambda_returns_bwd(
                 ptr(g), ptr(value), ptr(reward), ptr(ret), ptr(gammas), gamma, ptr(lambdas), lambda_, ptr(done), upgo,
                 T, B, ptr(gv), ptr(gr), ptr(gg), ptr(gl), stream_ptr()
@@ -479,7 +505,7 @@ class TBCrossEntropyFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logit, label, mask, TB, K, N):
         ce = torch.empty(TB, dtype=torch.float32, device=logit.device)
-        with torch.cuda.device(logit.device):
+        with on_device(logit.device):
             rc = lib().b200rl_tb_cross_entropy_fwd(ptr(logit), ptr(label), ptr(mask), TB, K, N, ptr(ce), stream_ptr())
         _lib.check(rc, 'b200rl_tb_cross_entropy_fwd')
         ctx.save_for_backward(logit, label, mask)
@@ -492,7 +518,7 @@ class TBCrossEntropyFunction(torch.autograd.Function):
         TB, K, N = ctx.cfg
         g = f32c(g_ce).reshape(-1)
         grad = torch.empty_like(logit)
-        with torch.cuda.device(logit.device):
+        with on_device(logit.device):
             rc = lib().b200rl_tb_cross_entropy_bwd(ptr(logit), ptr(label), ptr(mask), ptr(g), TB, K, N, ptr(grad),
                                                    stream_ptr())
         _lib.check(rc, 'b200rl_tb_cross_entropy_bwd')
@@ -512,7 +538,7 @@ class _ScaleSaved(torch.autograd.Function):
         saved, = ctx.saved_tensors
         out = torch.empty_like(saved)
         keep, pg = _g(g)
-        with torch.cuda.device(saved.device):
+        with on_device(saved.device):
             rc = lib().b200rl_scale(pg, ptr(saved), ptr(out), saved.numel(), stream_ptr())
         _lib.check(rc, 'b200rl_scale')
         return out, None, None
@@ -523,7 +549,7 @@ def td_lambda_(value, reward, weight, gamma, lambda_):
     dev = value.device
     loss = torch.empty((), dtype=torch.float32, device=dev)
     dvalue = torch.empty_like(value)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         ws = workspace(dev)
         rc = lib().b200rl_td_lambda_fwd(
             ptr(value), ptr(reward), ptr(weight), float(gamma), float(lambda_), T, B, ptr(loss), ptr(dvalue), ptr(ws),
@@ -545,7 +571,7 @@ class UPGOFunction(torch.autograd.Function):
         dev = logit.device
         loss = torch.empty((), dtype=torch.float32, device=dev)
         adv = torch.empty(TB, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             ws = workspace(dev)
             rc = lib().b200rl_upgo_head_fwd(
                 ptr(logit), ptr(action), ptr(mask), ptr(rho), ptr(ret), ptr(value), TB, K, N, ptr(loss), ptr(adv),
@@ -562,7 +588,7 @@ class UPGOFunction(torch.autograd.Function):
         TB, K, N = ctx.cfg
         grad = torch.empty_like(logit)
         keep, pg = _g(g)
-        with torch.cuda.device(logit.device):
+        with on_device(logit.device):
             rc = lib().b200rl_upgo_head_bwd(
                 ptr(logit), ptr(action), ptr(mask), ptr(adv), pg, TB, K, N, ptr(grad), stream_ptr()
             )
@@ -581,7 +607,7 @@ class ImpalaMaskFunction(torch.autograd.Function):
         vo = torch.empty_like(values)
         ro = torch.empty_like(rewards)
         wo = torch.empty_like(rewards)
-        with torch.cuda.device(values.device):
+        with on_device(values.device):
             rc = lib().b200rl_impala_mask(ptr(values), ptr(rewards), ptr(done), T, B, ptr(vo), ptr(ro), ptr(wo), stream_ptr())
         _lib.check(rc, 'b200rl_impala_mask')
         ctx.save_for_backward(done)
@@ -594,7 +620,7 @@ class ImpalaMaskFunction(torch.autograd.Function):
         T, B = done.shape
         g = f32c(g_v)
         out = torch.empty_like(g)
-        with torch.cuda.device(g.device):
+        with on_device(g.device):
             rc = lib().b200rl_impala_mask(ptr(g), None, ptr(done), T, B, ptr(out), None, None, stream_ptr())
         _lib.check(rc, 'b200rl_impala_mask')
         return out, None, None
@@ -634,7 +660,7 @@ class VTraceFunction(torch.autograd.Function):
         ctx.cfg = (T, B, N)
         ctx.fused = False
         ctx.bwd_calls = 0
-        with torch.cuda.device(dev):
+        with on_device(dev):
             ws = workspace(dev)
             if VTRACE_FUSED:
                 grad_logit = torch.empty_like(target_output) if want_grad else None
@@ -681,7 +707,7 @@ class VTraceFunction(torch.autograd.Function):
                 grad_logit = torch.empty_like(target_output)
                 grad_value = torch.empty(T + 1, B, dtype=torch.float32, device=dev)
                 g_used = torch.full((3, ), float('nan'), dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
+            with on_device(dev):
                 ws = workspace(dev)
                 rc = lib().b200rl_vtrace_fwd_grad(
                     ptr(target_output), ptr(behaviour_output), ptr(action), ptr(value), ptr(reward), ptr(weight), T, B,
@@ -694,7 +720,7 @@ class VTraceFunction(torch.autograd.Function):
         dev = target_output.device
         grad_logit = torch.empty_like(target_output)
         grad_value = torch.empty(T + 1, B, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             rc = lib().b200rl_vtrace_bwd(
                 ptr(target_output), ptr(action), ptr(weight), ptr(cpg), ptr(dv), pp, pv, pe, T, B, N, ptr(grad_logit),
                 ptr(grad_value), stream_ptr()
