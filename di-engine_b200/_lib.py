@@ -53,6 +53,9 @@ PROTOTYPES = {
     "b200rl_gae_ppo_fwd_grad_dp": [P, P, P, P, P, LL, LL, D, D, I, P, P, P, P, P, P, P, P, LL, D, I, D, I, P, P, P, P, P,
                                    P, P, I, I, P, P, P, c_size_t, P],
     "b200rl_p2p_drain_mean": [P, I, I, I, P, P, P],
+    "b200rl_a2c_fwd_grad": [P, P, P, P, P, P, LL, LL, P, I, P, P, P, P, P, P, P, P, P, c_size_t, P],
+    "b200rl_ppo_continuous_fwd_grad": [P, P, P, P, P, P, P, P, P, P, P, P, LL, LL, D, I, D, I, P, I, P, P, P, P, P, P, P, P, P,
+                                       P, P, c_size_t, P],
     "b200rl_gae_ppo_set_impl": [I],
     "b200rl_p2p_allreduce_mean": [P, P, I, I, I, P, P, P],
     "b200rl_p2p_mailbox_floats": [I],

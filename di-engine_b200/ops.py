@@ -596,6 +596,118 @@ class UPGOFunction(torch.autograd.Function):
         return (grad, ) + (None, ) * 8
 
 
+_HEAD_HINT = {}
+
+
+def head_hint(device, kind, init):
+    """device-resident expectation of the upstream gradients of a loss head (one record per head kind and device)"""
+    key = (device.index, kind)
+    h = _HEAD_HINT.get(key)
+    if h is None:
+        h = torch.tensor(init, dtype=torch.float32, device=device)
+        _HEAD_HINT[key] = h
+    return h
+
+
+class A2CFunction(torch.autograd.Function):
+    """a2c_error (ding/rl_utils/a2c.py:10-44): three differentiable 0-dim losses; gradients reach logit and value.  One launch
+    forward (losses + gradients for the expected upstream gradients), one verification launch backward (csrc/heads.cu)."""
+
+    @staticmethod
+    def forward(ctx, logit, value, action, adv, return_, weight, S, N):
+        dev = logit.device
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gl = torch.empty_like(logit) if want else None
+        gv = torch.empty_like(value) if want else None
+        g_used = torch.empty(4, dtype=torch.float32, device=dev) if want else None
+        ctx.hint = head_hint(dev, 'a2c', [1.0, 0.5, -0.01, 0.0])
+        with on_device(dev):
+            ws = workspace(dev)
+            rc = lib().b200rl_a2c_fwd_grad(ptr(logit), ptr(action), ptr(value), ptr(adv), ptr(return_), ptr(weight), S, N,
+                                           ptr(ctx.hint) if want else None, 0, None, None, None, ptr(g_used), None, ptr(out),
+                                           ptr(gl), ptr(gv), ptr(ws), ws.numel() * 4, stream_ptr())
+        _lib.check(rc, 'b200rl_a2c_fwd_grad')
+        ctx.save_for_backward(logit, value, action, adv, return_, weight)
+        ctx.cfg = (S, N)
+        ctx.spec = (gl, gv, g_used)
+        ctx.set_materialize_grads(False)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_p, g_v, g_e):
+        logit, value, action, adv, return_, weight = ctx.saved_tensors
+        S, N = ctx.cfg
+        kp, pp = _g(g_p)
+        kv, pv = _g(g_v)
+        ke, pe = _g(g_e)
+        spec, ctx.spec = ctx.spec, None
+        if spec is not None and spec[0] is not None:
+            gl, gv, g_used = spec
+        else:  # a repeated backward: the first call's buffers may now belong to .grad -> recompute into fresh ones
+            gl, gv = torch.empty_like(logit), torch.empty_like(value)
+            g_used = torch.full((4, ), float('nan'), dtype=torch.float32, device=logit.device)
+        with on_device(logit.device):
+            ws = workspace(logit.device)
+            rc = lib().b200rl_a2c_fwd_grad(ptr(logit), ptr(action), ptr(value), ptr(adv), ptr(return_), ptr(weight), S, N,
+                                           None, 1, pp, pv, pe, ptr(g_used), ptr(ctx.hint), None, ptr(gl), ptr(gv), ptr(ws),
+                                           ws.numel() * 4, stream_ptr())
+        _lib.check(rc, 'b200rl_a2c_fwd_grad(verify)')
+        return gl, gv, None, None, None, None, None, None
+
+
+class PPOContinuousFunction(torch.autograd.Function):
+    """ppo_error_continuous (ding/rl_utils/ppo.py:278-374): gradients reach mu_new, sigma_new and value_new (csrc/heads.cu)."""
+
+    @staticmethod
+    def forward(ctx, mu, sigma, value_new, mu_old, sigma_old, mu_pre, sigma_pre, action, value_old, adv, return_, weight, S,
+                D, clip_ratio, use_value_clip, dual_clip, kl_type):
+        dev = mu.device
+        out = torch.empty(8, dtype=torch.float32, device=dev)
+        want = any(ctx.needs_input_grad[:3])
+        gm = torch.empty_like(mu) if want else None
+        gs = torch.empty_like(sigma) if want else None
+        gv = torch.empty_like(value_new) if want else None
+        g_used = torch.empty(4, dtype=torch.float32, device=dev) if want else None
+        ctx.hint = head_hint(dev, 'ppoc', [1.0, 0.5, -0.01, 0.0])
+        ctx.args = (S, D, clip_ratio, use_value_clip, dual_clip, kl_type)
+        with on_device(dev):
+            ws = workspace(dev)
+            rc = lib().b200rl_ppo_continuous_fwd_grad(
+                ptr(mu), ptr(sigma), ptr(mu_old), ptr(sigma_old), ptr(mu_pre), ptr(sigma_pre), ptr(action), ptr(value_new),
+                ptr(value_old), ptr(adv), ptr(return_), ptr(weight), *ctx.args, ptr(ctx.hint) if want else None, 0, None,
+                None, None, None, ptr(g_used), None, ptr(out), ptr(gm), ptr(gs), ptr(gv), ptr(ws), ws.numel() * 4,
+                stream_ptr())
+        _lib.check(rc, 'b200rl_ppo_continuous_fwd_grad')
+        ctx.save_for_backward(mu, sigma, value_new, mu_old, sigma_old, mu_pre, sigma_pre, action, value_old, adv, return_,
+                              weight)
+        ctx.spec = (gm, gs, gv, g_used)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(out)
+        return out[0], out[1], out[2], out[3], out
+
+    @staticmethod
+    def backward(ctx, g_p, g_v, g_e, g_k, _g_out):
+        (mu, sigma, value_new, mu_old, sigma_old, mu_pre, sigma_pre, action, value_old, adv, return_,
+         weight) = ctx.saved_tensors
+        keep = [_g(x) for x in (g_p, g_v, g_e, g_k)]
+        spec, ctx.spec = ctx.spec, None
+        if spec is not None and spec[0] is not None:
+            gm, gs, gv, g_used = spec
+        else:
+            gm, gs, gv = torch.empty_like(mu), torch.empty_like(sigma), torch.empty_like(value_new)
+            g_used = torch.full((4, ), float('nan'), dtype=torch.float32, device=mu.device)
+        with on_device(mu.device):
+            ws = workspace(mu.device)
+            rc = lib().b200rl_ppo_continuous_fwd_grad(
+                ptr(mu), ptr(sigma), ptr(mu_old), ptr(sigma_old), ptr(mu_pre), ptr(sigma_pre), ptr(action), ptr(value_new),
+                ptr(value_old), ptr(adv), ptr(return_), ptr(weight), *ctx.args, None, 1, keep[0][1], keep[1][1], keep[2][1],
+                keep[3][1], ptr(g_used), ptr(ctx.hint), None, ptr(gm), ptr(gs), ptr(gv), ptr(ws), ws.numel() * 4,
+                stream_ptr())
+        _lib.check(rc, 'b200rl_ppo_continuous_fwd_grad(verify)')
+        return (gm, gs, gv) + (None, ) * 15
+
+
 class ImpalaMaskFunction(torch.autograd.Function):
     """IMPALAPolicy._reshape_data masking (ding/policy/impala.py:316-322): values (T+1, B) (differentiable), rewards, done
     (T, B) -> (values', rewards', weights).  The reference multiplies ``values[1:]`` in place, so gradient reaches the critic

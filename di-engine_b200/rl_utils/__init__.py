@@ -1,8 +1,9 @@
 """Mirror of the hot-path part of ``ding.rl_utils`` (ding/rl_utils/__init__.py:1-27): identical names, signatures and
 namedtuples, computed by the sm_100a kernels behind the C ABI of ``include/b200rl.h``."""
+from .a2c import a2c_data, a2c_error, a2c_loss
 from .fused import gae_ppo_error
 from .gae import gae, gae_data, gae_returns, gae_returns_out, shape_fn_gae
-from .ppo import (normalize_advantage, ppo_data, ppo_error, ppo_error_adv_norm, ppo_info, ppo_loss, ppo_policy_data, ppo_policy_error, ppo_policy_loss,
+from .ppo import (normalize_advantage, ppo_data, ppo_error, ppo_error_adv_norm, ppo_error_continuous, ppo_info, ppo_loss, ppo_policy_data, ppo_policy_error, ppo_policy_loss,
                   ppo_value_data, ppo_value_error, shape_fn_ppo)
 from .td import (bdq_nstep_td_error, dist_1step_td_data, dist_1step_td_error, dist_nstep_td_data, dist_nstep_td_error,
                  generalized_lambda_returns, q_1step_td_data, q_1step_td_error, q_nstep_td_data, q_nstep_td_error,
@@ -18,10 +19,10 @@ HOT_PATH_FUNCTIONS = [
     'generalized_lambda_returns', 'upgo_loss', 'vtrace_error_discrete_action',
     # siblings on the same kernels
     'q_1step_td_error', 'v_1step_td_error', 'v_nstep_td_error', 'ppo_policy_error', 'ppo_value_error',
-    'dist_1step_td_error', 'bdq_nstep_td_error', 'upgo_returns', 'tb_cross_entropy'
+    'dist_1step_td_error', 'bdq_nstep_td_error', 'upgo_returns', 'tb_cross_entropy', 'ppo_error_continuous', 'a2c_error'
 ]
 HOT_PATH_TYPES = [
     'gae_data', 'ppo_data', 'ppo_loss', 'ppo_info', 'q_nstep_td_data', 'dist_nstep_td_data', 'td_lambda_data',
     'vtrace_data', 'vtrace_loss', 'q_1step_td_data', 'v_1step_td_data', 'v_nstep_td_data',
-    'ppo_policy_data', 'ppo_policy_loss', 'ppo_value_data', 'dist_1step_td_data'
+    'ppo_policy_data', 'ppo_policy_loss', 'ppo_value_data', 'dist_1step_td_data', 'a2c_data', 'a2c_loss'
 ]

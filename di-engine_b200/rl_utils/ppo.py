@@ -134,6 +134,63 @@ def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind,
     return ppo_loss(p, v, e, k), info
 
 
+def ppo_error_continuous(
+        data: namedtuple,
+        clip_ratio: float = 0.2,
+        use_value_clip: bool = True,
+        dual_clip: Optional[float] = None,
+        kl_type: str = 'k1'
+) -> Tuple[namedtuple, namedtuple]:
+    """
+    PPO loss for a continuous action space, drop-in for ding/rl_utils/ppo.py:278-374: the policies are
+    ``Independent(Normal(mu, sigma), 1)`` given as dicts ``{'mu': (B, D), 'sigma': (B, D)}`` in the ``logit_new`` / ``logit_old``
+    / ``logit_pretrained`` fields of ``ppo_data`` (a 1-D old policy is one action dim, ppo.py:336-337); action (B, D) float.
+    Returns ``(ppo_loss, ppo_info)``; gradients reach ``mu``, ``sigma`` of the new policy and ``value_new``.  Forward and
+    gradients in one launch (csrc/heads.cu), device-verified backward.
+    """
+    assert dual_clip is None or dual_clip > 1.0, "dual_clip value must be greater than 1.0, but get value: {}".format(
+        dual_clip
+    )
+    mu_sigma_new, mu_sigma_old, action, value_new, value_old, adv, return_, weight, logit_pretrained = data
+    if logit_pretrained is not None and kl_type not in _KL_TYPES:
+        raise ValueError(f"Unknown kl_type: {kl_type}")
+    mu, sigma = mu_sigma_new['mu'], mu_sigma_new['sigma']
+    dev = ops.compute_device(mu, value_new)
+    host_out = not mu.is_cuda
+    S = adv.numel()
+    D = mu.numel() // S
+
+    def stage(t, name, n):
+        t = ops.f32c(ops.to_device(t, dev), name)
+        if t.numel() != n:
+            raise ValueError("ppo_error_continuous: %s %s does not match adv %s / action dims %d" %
+                             (name, tuple(t.shape), tuple(adv.shape), D))
+        return t
+
+    mo, so = mu_sigma_old['mu'].detach(), mu_sigma_old['sigma'].detach()
+    args = [stage(mu, 'mu', S * D), stage(sigma, 'sigma', S * D), stage(value_new, 'value_new', S), stage(mo, 'mu_old', S * D),
+            stage(so, 'sigma_old', S * D)]
+    if logit_pretrained is not None:
+        args += [stage(logit_pretrained['mu'].detach(), 'mu_pretrained', S * D),
+                 stage(logit_pretrained['sigma'].detach(), 'sigma_pretrained', S * D)]
+    else:
+        args += [None, None]
+    args += [stage(action.detach(), 'action', S * D), stage(value_old.detach(), 'value_old', S), stage(adv.detach(), 'adv', S),
+             stage(return_.detach(), 'return_', S),
+             stage(weight.detach(), 'weight', S) if weight is not None else None]
+    p, v, e, k, out = ops.PPOContinuousFunction.apply(
+        *args, S, D, float(clip_ratio), 1 if use_value_clip else 0, float(dual_clip) if dual_clip is not None else 0.0,
+        _KL_TYPES.get(kl_type, 1))
+    if LAZY_INFO:
+        info = ppo_info(out[4], out[5])
+    else:
+        approx_kl, clipfrac = out[4:6].tolist()
+        info = ppo_info(approx_kl, clipfrac)
+    if host_out:
+        p, v, e, k = p.cpu(), v.cpu(), e.cpu(), k.cpu()
+    return ppo_loss(p, v, e, k), info
+
+
 def ppo_policy_error(
         data: namedtuple,
         clip_ratio: float = 0.2,

@@ -247,6 +247,28 @@ B200RL_API int b200rl_ppo_value_fwd(const float* value_new, const float* value_o
                          const float* weight, long long S, double clip_ratio, int use_value_clip, float* loss,
                          float* dvalue_unit, float* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- sibling heads, forward + gradients in ONE launch each (csrc/heads.cu) ---------------------
+ * Same backward contract as b200rl_vtrace_fwd_grad: verify = 0 writes the losses and (grad_* non-null) the gradients for the
+ * expected upstream gradients g_expected[k], recording them in g_used; verify = 1 with the actual upstream gradients (device
+ * scalars, null = 0) returns at once when they equal g_used and recomputes the gradients otherwise; g_hint (nullable) is
+ * refreshed with the actual values.
+ * a2c_error (ding/rl_utils/a2c.py:10-44): logit (S, N), action (S) int64, value / adv / return_ / weight(nullable) (S);
+ * out3 = policy_loss -mean(logp*adv*w), value_loss mean(w*(return_-value)^2), entropy_loss mean(H*w).
+ * ppo_error_continuous (ding/rl_utils/ppo.py:278-374): Independent(Normal(mu, sigma)) policies, mu / sigma / action (S, D)
+ * (a 1-D old policy is D = 1), pretrained pair nullable; out6 as b200rl_ppo_fwd. */
+B200RL_API int b200rl_a2c_fwd_grad(const float* logit, const long long* action, const float* value, const float* adv,
+                        const float* return_, const float* weight, long long S, long long N, const float* g_expected,
+                        int verify, const float* g_policy, const float* g_value, const float* g_entropy, float* g_used,
+                        float* g_hint, float* out3, float* grad_logit, float* grad_value, float* workspace,
+                        size_t workspace_bytes, void* stream);
+B200RL_API int b200rl_ppo_continuous_fwd_grad(
+    const float* mu_new, const float* sigma_new, const float* mu_old, const float* sigma_old, const float* mu_pretrained,
+    const float* sigma_pretrained, const float* action, const float* value_new, const float* value_old, const float* adv,
+    const float* return_, const float* weight, long long S, long long D, double clip_ratio, int use_value_clip,
+    double dual_clip, int kl_type, const float* g_expected, int verify, const float* g_policy, const float* g_value,
+    const float* g_entropy, const float* g_kl, float* g_used, float* g_hint, float* out6, float* grad_mu, float* grad_sigma,
+    float* grad_value, float* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- fused learner step: gae (gae.py:25-70) followed by ppo_error (ppo.py:77-140) in ONE launch ------------------
  * Semantics are exactly b200rl_gae(value, next_value, reward, done, traj_flag -> adv) followed by b200rl_ppo_fwd_grad
  * (or b200rl_ppo_fwd when g_expected is null) with that adv, S = T*B, G = 1 -- same arithmetic, bit-identical adv.

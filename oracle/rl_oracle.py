@@ -188,6 +188,68 @@ def ppo_error(
 # --------------------------------------------------------------------------------------------------------------
 # td.py:230-286 nstep_return ; value_rescale.py:4-34
 # --------------------------------------------------------------------------------------------------------------
+def ppo_error_continuous(mu_new, sigma_new, mu_old, sigma_old, action, value_new, value_old, adv, return_, weight=None,
+                         mu_pretrained=None, sigma_pretrained=None, clip_ratio: float = 0.2, use_value_clip: bool = True,
+                         dual_clip: Optional[float] = None, kl_type: str = 'k1'):
+    """ppo.py:278-374 with the Independent(Normal) log-prob / entropy written out (torch.distributions.Normal.log_prob:
+    ``-((x-mu)^2)/(2 var) - log(sigma) - log(sqrt(2 pi))``; entropy ``0.5 + 0.5 log(2 pi) + log(sigma)``; Independent sums the
+    last dim).  Returns (policy, value, entropy, kl, approx_kl, clipfrac)."""
+    assert dual_clip is None or dual_clip > 1.0
+    if weight is None:
+        weight = torch.ones_like(adv)
+
+    def logp(mu, sigma):
+        var = sigma ** 2
+        return (-((action - mu) ** 2) / (2 * var) - sigma.log() - math.log(math.sqrt(2 * math.pi))).sum(-1)
+
+    if mu_old.dim() == 1:  # ppo.py:336-337
+        mu_old, sigma_old = mu_old.unsqueeze(-1), sigma_old.unsqueeze(-1)
+    logp_new, logp_old = logp(mu_new, sigma_new), logp(mu_old, sigma_old)
+    entropy = (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(sigma_new)).sum(-1)
+    entropy_loss = (entropy * weight).mean()
+    ratio = torch.exp(logp_new - logp_old)
+    surr1 = ratio * adv
+    surr2 = ratio.clamp(1 - clip_ratio, 1 + clip_ratio) * adv
+    if dual_clip is not None:
+        policy_loss = (-torch.max(torch.min(surr1, surr2), dual_clip * adv) * weight).mean()
+    else:
+        policy_loss = (-torch.min(surr1, surr2) * weight).mean()
+    with torch.no_grad():
+        approx_kl = (logp_old - logp_new).mean().item()
+        clipped = ratio.gt(1 + clip_ratio) | ratio.lt(1 - clip_ratio)
+        clipfrac = torch.as_tensor(clipped).float().mean().item()
+    if use_value_clip:
+        value_clip = value_old + (value_new - value_old).clamp(-clip_ratio, clip_ratio)
+        value_loss = 0.5 * (torch.max((return_ - value_new).pow(2), (return_ - value_clip).pow(2)) * weight).mean()
+    else:
+        value_loss = 0.5 * ((return_ - value_new).pow(2) * weight).mean()
+    if mu_pretrained is not None:
+        log_ratio = logp_new - logp(mu_pretrained, sigma_pretrained)
+        if kl_type == 'k1':
+            kl_div = log_ratio.mean()
+        elif kl_type == 'k2':
+            kl_div = (log_ratio ** 2 / 2).mean()
+        elif kl_type == 'k3':
+            kl_div = (torch.exp(-log_ratio) - 1 + log_ratio).mean()
+        else:
+            raise ValueError(f"Unknown kl_type: {kl_type}")
+    else:
+        kl_div = torch.tensor(0.)
+    return policy_loss, value_loss, entropy_loss, kl_div, approx_kl, clipfrac
+
+
+def a2c_error(logit, action, value, adv, return_, weight=None):
+    """a2c.py:10-44."""
+    if weight is None:
+        weight = torch.ones_like(value)
+    logp_all = _log_softmax_rows(logit)
+    logp = _chosen(logp_all, action)
+    entropy_loss = (_row_entropy(logp_all) * weight).mean()
+    policy_loss = -(logp * adv * weight).mean()
+    value_loss = (torch.nn.functional.mse_loss(return_, value, reduction='none') * weight).mean()
+    return policy_loss, value_loss, entropy_loss
+
+
 def ppo_policy_error(logit_new, logit_old, action, adv, weight=None, logit_pretrained=None, clip_ratio: float = 0.2,
                      dual_clip: Optional[float] = None, entropy_bonus: bool = True, kl_type: str = 'k1'):
     """ppo.py:143-230 -> ``(policy_loss, entropy_loss, kl_div, approx_kl, clipfrac)``: the policy part of ``ppo_error``."""

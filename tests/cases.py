@@ -20,6 +20,8 @@ GRAD_INPUTS = {
     'ppo': ['logit_new', 'value_new'],
     'ppo_policy': ['logit_new'],
     'ppo_value': ['value_new'],
+    'ppoc': ['mu_new', 'sigma_new', 'value_new'],
+    'a2c': ['logit', 'value'],
     'qntd': ['q'],
     'qntd_rescale': ['q'],
     'q1td': ['q'],
@@ -38,6 +40,8 @@ LOSS_MIX = {
     'ppo': [1.0, 0.5, -0.01, 0.3],
     'ppo_policy': [1.0, -0.02, 0.3],
     'ppo_value': [0.7],
+    'ppoc': [1.0, 0.5, -0.01, 0.3],
+    'a2c': [1.0, 0.5, -0.01],
     'qntd': [1.0],
     'qntd_rescale': [1.0],
     'q1td': [1.0],
@@ -152,6 +156,42 @@ def ppo_value_case(seed, B, weight='none', **params):
     op, t, _ = ppo_case(seed, B, 3, weight=weight)
     keep = OrderedDict((k, t[k]) for k in ('value_new', 'value_old', 'return_', 'weight'))
     return 'ppo_value', keep, params
+
+
+def ppoc_case(seed, B, D, weight='none', pretrained=False, old_1d=False, **params):
+    """ppo_error_continuous (tests/test_ppo.py:71-92): Independent(Normal(mu, sigma)) policies"""
+    g = _g(seed)
+    t = OrderedDict()
+    t['mu_new'] = _rand(g, B, D)
+    t['sigma_new'] = _rand(g, B, D) + 0.3
+    if old_1d:
+        assert D == 1
+        t['mu_old'] = t['mu_new'][:, 0] + 0.1 * _rand(g, B)
+        t['sigma_old'] = t['sigma_new'][:, 0] + 0.1 * _rand(g, B)
+    else:
+        t['mu_old'] = t['mu_new'] + 0.1 * _rand(g, B, D)
+        t['sigma_old'] = t['sigma_new'] + 0.1 * _rand(g, B, D)
+    t['action'] = _rand(g, B, D)
+    t['value_new'] = _randn(g, B)
+    t['value_old'] = t['value_new'] + 0.1 * _rand(g, B)
+    t['adv'] = _randn(g, B)
+    t['return_'] = _randn(g, B) * 2
+    t['weight'] = None if weight == 'none' else _rand(g, B) + 1
+    t['mu_pretrained'] = (t['mu_new'] + 0.3 * _randn(g, B, D)) if pretrained else None
+    t['sigma_pretrained'] = (t['sigma_new'] + 0.2 * _rand(g, B, D)) if pretrained else None
+    return 'ppoc', t, params
+
+
+def a2c_case(seed, B, N, weight='none'):
+    g = _g(seed)
+    t = OrderedDict()
+    t['logit'] = _randn(g, B, N)
+    t['action'] = _randint(g, N, B)
+    t['value'] = _randn(g, B)
+    t['adv'] = _rand(g, B)
+    t['return_'] = _randn(g, B) * 2
+    t['weight'] = None if weight == 'none' else _rand(g, B) + 1
+    return 'a2c', t, {}
 
 
 def q1td_case(seed, B, N, weight='none', gamma=0.95):
@@ -412,6 +452,13 @@ def build_cases():
     c['qseq_ngu'] = qseq_case(97, 5, 6, 3, 2, list_gamma=True, value_gamma='none')
     c['d1td_basic'] = d1td_case(98, 9, 4, 51)
     c['d1td_marl'] = d1td_case(99, 4, 3, 21, marl_A=2, v_min=-2., v_max=3.)
+    # ---- sibling heads: ppo_error_continuous (tests/test_ppo.py:71-92), a2c_error (tests/test_a2c.py)
+    c['ppoc_basic'] = ppoc_case(110, 64, 6, clip_ratio=0.2)
+    c['ppoc_w_dc_novc'] = ppoc_case(111, 33, 3, weight='tensor', dual_clip=5.0, use_value_clip=False)
+    c['ppoc_kl_k3'] = ppoc_case(112, 20, 4, weight='tensor', pretrained=True, kl_type='k3')
+    c['ppoc_old_1d'] = ppoc_case(113, 17, 1, old_1d=True)
+    c['a2c_basic'] = a2c_case(114, 64, 6)
+    c['a2c_w_wide'] = a2c_case(115, 9, 130, weight='tensor')
     # ---- dist_nstep (tests/test_td.py:130-204) ---------------------------------------------------------------
     c['dntd_cfgC'] = dntd_case(50, 32, 6, 51, 3, gamma=0.99, value_gamma='tensor')
     c['dntd_n5'] = dntd_case(51, 4, 3, 51, 5)
@@ -492,6 +539,23 @@ def run_api(api, op, tensors, params, device='cpu'):
             res['out_' + k] = _np(getattr(loss, k))
         res['out_approx_kl'] = np.float32(info.approx_kl)
         res['out_clipfrac'] = np.float32(info.clipfrac)
+        _backward(op, list(loss), t, res)
+        return res
+    if op == 'ppoc':
+        pre = None if t['mu_pretrained'] is None else {'mu': t['mu_pretrained'], 'sigma': t['sigma_pretrained']}
+        data = api.ppo_data({'mu': t['mu_new'], 'sigma': t['sigma_new']}, {'mu': t['mu_old'], 'sigma': t['sigma_old']},
+                            t['action'], t['value_new'], t['value_old'], t['adv'], t['return_'], t['weight'], pre)
+        loss, info = api.ppo_error_continuous(data, **p)
+        for k in ('policy_loss', 'value_loss', 'entropy_loss', 'kl_div'):
+            res['out_' + k] = _np(getattr(loss, k))
+        res['out_approx_kl'] = np.float32(info.approx_kl)
+        res['out_clipfrac'] = np.float32(info.clipfrac)
+        _backward(op, list(loss), t, res)
+        return res
+    if op == 'a2c':
+        loss = api.a2c_error(api.a2c_data(t['logit'], t['action'], t['value'], t['adv'], t['return_'], t['weight']))
+        for k in ('policy_loss', 'value_loss', 'entropy_loss'):
+            res['out_' + k] = _np(getattr(loss, k))
         _backward(op, list(loss), t, res)
         return res
     if op == 'ppo_policy':
@@ -647,6 +711,20 @@ def run_oracle(orc, op, tensors, params):
         res['out_loss'] = _np(loss)
         res['out_td_error_per_sample'] = _np(per)
         _backward(op, [loss], t, res)
+        return res
+    if op == 'ppoc':
+        out = orc.ppo_error_continuous(**t, **p)
+        for k, v in zip(('policy_loss', 'value_loss', 'entropy_loss', 'kl_div'), out[:4]):
+            res['out_' + k] = _np(v)
+        res['out_approx_kl'] = np.float32(out[4])
+        res['out_clipfrac'] = np.float32(out[5])
+        _backward(op, list(out[:4]), t, res)
+        return res
+    if op == 'a2c':
+        out = orc.a2c_error(**t)
+        for k, v in zip(('policy_loss', 'value_loss', 'entropy_loss'), out):
+            res['out_' + k] = _np(v)
+        _backward(op, list(out), t, res)
         return res
     if op == 'ppo_policy':
         out = orc.ppo_policy_error(**t, **p)

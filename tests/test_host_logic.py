@@ -198,6 +198,8 @@ EXPECTED_CALLS = {
     'ppo': ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad', 'b200rl_ppo_bwd'],
     'ppo_policy': ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad', 'b200rl_ppo_bwd'],
     'ppo_value': ['b200rl_ppo_value_fwd', 'b200rl_scale'],
+    'ppoc': ['b200rl_ppo_continuous_fwd_grad', 'b200rl_ppo_continuous_fwd_grad'],
+    'a2c': ['b200rl_a2c_fwd_grad', 'b200rl_a2c_fwd_grad'],
     'qntd': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'qntd_rescale': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'q1td': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
@@ -342,3 +344,72 @@ def test_packed_batch_layout():
         assert d[k].dtype == like[k].dtype and d[k].shape == like[k].shape and torch.equal(d[k], like[k])
     pb.host['a'].add_(1.0)
     assert torch.equal(pb.upload()[0]['a'], like['a'] + 1.0)
+
+
+@pytest.mark.skipif(not __import__('oracle.ref_loader', fromlist=['x']).available(), reason='reference not importable here')
+def test_live_hpc_wrapper_dispatches_into_the_shim(dry, monkeypatch):
+    """The boundary end to end on the CPU box: the LIVE reference decorator (ding/hpc_rl/wrapper.py:86-133, the unmodified
+    ding.rl_utils functions it wraps) with ``ding.enable_hpc_rl = True`` resolves ``hpc_rll.rl_utils.*`` to the classes
+    ``install_hpc_rll()`` registers, constructs them as ``Class(*shape).cuda()``, caches them per shape (:74-83) and calls
+    them with the whitelisted arguments -- which must reach the C ABI (here: the recording stand-in for the library)."""
+    from oracle import ref_loader
+    ref = ref_loader.load()  # puts the reference (tree or byte-compiled archive) on sys.path
+    import ding
+    import ding.hpc_rl.wrapper as hw
+    for k in list(sys.modules):
+        if k == 'hpc_rll' or k.startswith('hpc_rll.'):
+            monkeypatch.delitem(sys.modules, k)
+    b2.install_hpc_rll(force=True)
+    monkeypatch.setattr(ding, 'enable_hpc_rl', True)
+    hw.hpc_fns.clear()
+    g = torch.Generator().manual_seed(5)
+    try:
+        # gae: include_args [0,1,2] -> hpc_fn(*data, gamma, lambda_)
+        T, B = 16, 8
+        d = ref.gae_data(torch.randn(T, B, generator=g), torch.randn(T, B, generator=g), torch.randn(T, B, generator=g),
+                         torch.zeros(T, B), None)
+        adv = ref.gae(d, 0.99, 0.95)
+        assert dry.calls == ['b200rl_gae'] and adv.shape == (T, B)
+        assert list(hw.hpc_fns['gae'].keys()) == ['gae_%d_%d' % (T, B)]  # runtime_name = fn name + shape_fn(...) (:97)
+        ref.gae(d, gamma=0.9, lambda_=0.8)  # keyword form: 'lambda_' is renamed 'lambda' by the wrapper (:113-114)
+        assert dry.calls == ['b200rl_gae'] * 2 and len(hw.hpc_fns['gae']) == 1  # cached instance reused
+        # ppo_error: hpc_fn(*data (9 fields), clip_ratio, use_value_clip, dual_clip)
+        dry.calls.clear()
+        op, t, p = cases.ppo_case(3, 12, 5, weight='tensor')
+        tt = cases.prepare(op, t)
+        data = ref.ppo_data(*[tt[k] for k in ('logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv', 'return_',
+                                              'weight', 'logit_pretrained')])
+        loss, info = ref.ppo_error(data, 0.2, True, None)
+        assert dry.calls[:2] == ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad'] and len(loss) == 4
+        # q_nstep_td_error: only (data, gamma) are forwarded (:648); nstep is re-derived from the reward tensor by the shim
+        dry.calls.clear()
+        op, t, p = cases.qntd_case(4, 8, 4, 3)
+        data = ref.q_nstep_td_data(*[t[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight')])
+        loss, per = ref.q_nstep_td_error(data, 0.95, nstep=3)
+        assert dry.calls == ['b200rl_qntd_fwd'] and per.shape == (8, )
+        # dist_nstep_td_error: (data, gamma, v_min, v_max) forwarded, n_atom / nstep dropped with a warning (:407-412)
+        dry.calls.clear()
+        op, t, p = cases.dntd_case(5, 6, 3, 51, 2)
+        data = ref.dist_nstep_td_data(*[t[k] for k in ('dist', 'next_n_dist', 'act', 'next_n_act', 'reward', 'done', 'weight')])
+        loss, per = ref.dist_nstep_td_error(data, 0.95, -10., 10., 51, 2)
+        assert dry.calls == ['b200rl_dntd_fwd'] and per.shape == (6, )
+        # td_lambda_error and vtrace_error_discrete_action
+        dry.calls.clear()
+        op, t, p = cases.td_lambda_case(6, 8, 4)
+        ref.td_lambda_error(ref.td_lambda_data(t['value'], t['reward'], t['weight']), 0.9, 0.8)
+        assert dry.calls == ['b200rl_td_lambda_fwd']
+        dry.calls.clear()
+        op, t, p = cases.vtrace_case(7, 4, 8, 6)
+        ref.vtrace_error_discrete_action(ref.vtrace_data(*[t[k] for k in ('target_output', 'behaviour_output', 'action',
+                                                                          'value', 'reward', 'weight')]), 0.99, 0.95)
+        assert dry.calls[:2] == ['b200rl_vtrace_fused_supported', 'b200rl_vtrace_fwd_grad']
+        # per_fn_limit = 3 shapes per function, FIFO eviction (:80-81)
+        for Tn in (3, 4, 5, 6):
+            dn = ref.gae_data(torch.zeros(Tn, 2), torch.zeros(Tn, 2), torch.zeros(Tn, 2), None, None)
+            ref.gae(dn)
+        assert len(hw.hpc_fns['gae']) == 3 and 'gae_%d_%d' % (T, B) not in hw.hpc_fns['gae']
+    finally:
+        hw.hpc_fns.clear()
+        for k in list(sys.modules):
+            if k == 'hpc_rll' or k.startswith('hpc_rll.'):
+                del sys.modules[k]

@@ -7,7 +7,7 @@
   b200        ``di_engine_b200.rl_utils`` on the GPU (``-m gpu``): every assertion of the reference's test AND, whenever the
               reference is importable next to the GPU, value parity of every output and gradient against it (1e-5).
 
-Ported from ding/rl_utils/tests/test_gae.py, test_ppo.py (discrete part + shape_fn), test_td.py (the operators on this
+Ported from ding/rl_utils/tests/test_gae.py, test_ppo.py (discrete, continuous, shape_fn), test_a2c.py (discrete), test_td.py (the operators on this
 path: q_nstep, q_nstep_ngu, bdq_nstep, q_1step_compatible, dist_1step, dist_1step_compatible, dist_1step multi agent,
 dist_nstep, dist_nstep multi agent, rescale, rescale_ngu, td_lambda, v_1step, v_1step multi agent, v_nstep, the four shape_fn
 tests), test_vtrace.py (discrete), test_upgo.py and test_value_rescale.py.  The reference draws unseeded random inputs; the
@@ -218,6 +218,78 @@ def _mappo_body(api, dev, rec):
 
 def test_mappo(impl):
     _run(_mappo_body, impl)
+
+
+def _ppo_continuous_body(api, dev, rec, use_value_clip, dual_clip, weighted):
+    g = _gen(30)
+    B, N = 4, 6  # test_ppo.py:71-92
+    weight = (torch.rand(4, generator=g) + 1).to(dev) if weighted else None
+    mu_sigma_new = {'mu': torch.rand(B, N, generator=g).to(dev).requires_grad_(True),
+                    'sigma': (torch.rand(B, N, generator=g) + 0.1).to(dev).requires_grad_(True)}
+    mu_sigma_old = {
+        'mu': mu_sigma_new['mu'].detach() + torch.rand(B, N, generator=g).to(dev) * 0.1,
+        'sigma': mu_sigma_new['sigma'].detach() + torch.rand(B, N, generator=g).to(dev) * 0.1
+    }
+    action = torch.rand(B, N, generator=g).to(dev)
+    value_new = torch.randn(B, generator=g).to(dev).requires_grad_(True)
+    value_old = value_new.detach() + torch.rand(B, generator=g).to(dev) * 0.1
+    adv = torch.rand(B, generator=g).to(dev)
+    return_ = (torch.randn(B, generator=g) * 2).to(dev)
+    data = api.ppo_data(mu_sigma_new, mu_sigma_old, action, value_new, value_old, adv, return_, weight, None)
+    loss, info = api.ppo_error_continuous(data, use_value_clip=use_value_clip, dual_clip=dual_clip)
+    assert all([l.shape == tuple() for l in loss])
+    assert all([np.isscalar(i) for i in info])
+    assert mu_sigma_new['mu'].grad is None
+    assert value_new.grad is None
+    total_loss = sum(loss)
+    total_loss.backward()
+    assert isinstance(mu_sigma_new['mu'].grad, torch.Tensor)
+    assert isinstance(value_new.grad, torch.Tensor)
+    for k, v in zip(loss._fields, loss):
+        rec.put(k, v)
+    rec.put('approx_kl', info.approx_kl)
+    rec.put('grad_mu', mu_sigma_new['mu'].grad)
+    rec.put('grad_sigma', mu_sigma_new['sigma'].grad)
+    rec.put('grad_value', value_new.grad)
+
+
+@pytest.mark.parametrize('use_value_clip', [True, False])
+@pytest.mark.parametrize('dual_clip', [None, 5.0])
+@pytest.mark.parametrize('weighted', [False, True])
+def test_ppo_error_continous(impl, use_value_clip, dual_clip, weighted):
+    _run(_ppo_continuous_body, impl, use_value_clip, dual_clip, weighted)
+
+
+# =================================================================================================================
+# ding/rl_utils/tests/test_a2c.py (discrete)
+# =================================================================================================================
+def _a2c_body(api, dev, rec, weighted):
+    g = _gen(31)
+    B, N = 4, 32  # test_a2c.py:12-27
+    weight = (torch.rand(4, generator=g) + 1).to(dev) if weighted else None
+    logit = torch.randn(B, N, generator=g).to(dev).requires_grad_(True)
+    action = torch.randint(0, N, size=(B, ), generator=g).to(dev)
+    value = torch.randn(B, generator=g).to(dev).requires_grad_(True)
+    adv = torch.rand(B, generator=g).to(dev)
+    return_ = (torch.randn(B, generator=g) * 2).to(dev)
+    data = api.a2c_data(logit, action, value, adv, return_, weight)
+    loss = api.a2c_error(data)
+    assert all([l.shape == tuple() for l in loss])
+    assert logit.grad is None
+    assert value.grad is None
+    total_loss = sum(loss)
+    total_loss.backward()
+    assert isinstance(logit.grad, torch.Tensor)
+    assert isinstance(value.grad, torch.Tensor)
+    for k, v in zip(loss._fields, loss):
+        rec.put(k, v)
+    rec.put('grad_logit', logit.grad)
+    rec.put('grad_value', value.grad)
+
+
+@pytest.mark.parametrize('weighted', [False, True])
+def test_a2c(impl, weighted):
+    _run(_a2c_body, impl, weighted)
 
 
 # =================================================================================================================
