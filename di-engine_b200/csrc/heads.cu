@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(HD_NT) ppoc_kernel(PpocArgs a, float* ws) {
         for (int d = 0; d < a.D; ++d) ent += kHalfPlusHalfLog2Pi + logf(sg[d]);
         const float ratio = expf(lp_n - lp_o);
         float dsel, dterm, dk = 0.f, klv = 0.f;
-        const float sel = surrogate(ratio, a.adv[s], a.clip_lo, a.clip_hi, a.dual_clip, dsel);
+        const float sel = surrogate(ratio, a.adv[s], a.clip_lo, a.clip_hi, a.dual_clip, dsel, true);
         const float vt = value_term(a.value_new[s], a.value_old[s], a.ret[s], a.clip, a.use_value_clip, dterm);
         if (has_pre) klv = kl_term(lp_n - normal_logp(a.mu_pre + o, a.sigma_pre + o, ac, a.D), a.kl_type, dk);
         acc[0] -= sel * w;

@@ -43,8 +43,10 @@ struct PpoArgs {
 
 // d(selected surrogate)/d(ratio) with torch's tie rules: min/max split the gradient 0.5/0.5 on equality, clamp passes
 // gradient on the closed interval (ppo.py:208-216).  Also returns the selected surrogate value.
+// dual_all: ppo_error_continuous applies max(., dual_clip * adv) to EVERY sample (ppo.py:346-347), the discrete loss only where
+// adv < 0 (ppo.py:211-214)
 __device__ __forceinline__ float surrogate(float ratio, float adv, float lo, float hi, float dual_clip,
-                                           float& dsel_dratio) {
+                                           float& dsel_dratio, bool dual_all = false) {
     const float rc = fminf(fmaxf(ratio, lo), hi);
     const float s1 = ratio * adv, s2 = rc * adv;
     const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
@@ -54,7 +56,7 @@ __device__ __forceinline__ float surrogate(float ratio, float adv, float lo, flo
     else { w1 = 0.5f; w2 = 0.5f; }
     float sel = fminf(s1, s2);
     float d = adv * (w1 + w2 * in_range);
-    if (dual_clip > 0.f && adv < 0.f) {
+    if (dual_clip > 0.f && (dual_all || adv < 0.f)) {
         const float floor_ = dual_clip * adv;
         if (sel < floor_) { sel = floor_; d = 0.f; }
         else if (sel == floor_) { d *= 0.5f; }
