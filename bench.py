@@ -914,7 +914,10 @@ def run_gpu(args):
     dbg('per-kernel done')
     packed = not args.e2e_separate_copies
     if packed:  # one pinned buffer + one device buffer per slot: the H2D transfer of a step is a single copy
-        slots = [b2.PackedBatch(wl.make_batch(2000 * rank + i), dev) for i in range(2)]
+        narrow = None
+        if args.e2e_compact:  # one-byte actions and flags on the wire, widened on the device after the copy (exact)
+            narrow = {k: torch.uint8 for k in ('action', 'done', 'traj_flag', 'next_n_action', 'act', 'next_n_act')}
+        slots = [b2.PackedBatch(wl.make_batch(2000 * rank + i), dev, narrow=narrow) for i in range(2)]
         host = slots
         h2d = slots[0].payload_bytes()
     else:
@@ -1118,6 +1121,8 @@ def main():
     ap.add_argument('--unfused', action='store_true', help='config D: separate gae / ppo forward / ppo backward kernels')
     ap.add_argument('--three', action='store_true',
                     help='config D: gae, fused ppo forward+grad, verification as three calls (default: the one-launch step)')
+    ap.add_argument('--e2e-wide', dest='e2e_compact', action='store_false',
+                    help='e2e: int64 actions / fp32 flags on the wire (default: one byte each, widened on the device)')
     ap.add_argument('--e2e-separate-copies', action='store_true',
                     help='e2e: one pinned tensor and one H2D copy per input (default: di_engine_b200.PackedBatch, one copy)')
     args = ap.parse_args()
