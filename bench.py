@@ -236,6 +236,14 @@ class DeviceStepD:
         self.b['next_value'].copy_(self.nv0)
 
 
+def DeviceStep(host_batch, dev, fused='onepass'):
+    """entry point of the round-1 experiment tools (tools/exp_*.py, trace_*.py, sweep_col.py): one config-D buffer set with
+    the launch decomposition they name ('onepass' | True = three launches | False = unfused)"""
+    mode = {'onepass': 'onepass', True: 'three', False: 'unfused'}[fused]
+    T, B = host_batch['value'].shape
+    return DeviceStepD(WorkloadD(B=B, T=T, N=host_batch['logit_new'].shape[-1], mode=mode), host_batch, dev)
+
+
 class WorkloadB:
     """q_nstep_td_error forward + backward: one launch + its verification; 120 B / sample at N=6, n=3 with value_gamma."""
     key = 'B'

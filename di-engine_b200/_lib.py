@@ -45,6 +45,8 @@ PROTOTYPES = {
     "b200rl_upgo_head_fwd": [P, P, P, P, P, P, LL, LL, LL, P, P, P, c_size_t, P],
     "b200rl_upgo_head_bwd": [P, P, P, P, P, LL, LL, LL, P, P],
     "b200rl_vtrace_fwd": [P, P, P, P, P, P, LL, LL, LL, D, D, D, D, D, P, P, P, P, P, c_size_t, P],
+    "b200rl_vtrace_continuous_fwd": [P, P, P, P, P, P, P, P, LL, LL, LL, D, D, D, D, D, P, P, P, P, P, c_size_t, P],
+    "b200rl_vtrace_continuous_bwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, P, P, P, P],
     "b200rl_vtrace_fused_supported": [P, P, P, P, P, P, LL, LL, LL, P, P],
     "b200rl_vtrace_fwd_grad": [P, P, P, P, P, P, LL, LL, LL, D, D, D, D, D, P, I, P, P, P, P, P, P, P, P, P, c_size_t, P],
     "b200rl_gae_ppo_supported": [P, P, P, P, P, LL, LL, P, P, P, P, P, P, P, P, LL, P, P],

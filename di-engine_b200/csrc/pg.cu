@@ -360,6 +360,76 @@ __global__ void __launch_bounds__(NT) vtrace_bwd_kernel(VtArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// vtrace_error_continuous_action (ding/rl_utils/vtrace.py:139-212): Independent(Normal(mu, sigma)) policies.  Rows kernel ->
+// the shared scan -> backward rows kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct VtcArgs {
+    const float* mu_t;     // (M, D) target policy
+    const float* sigma_t;
+    const float* mu_b;     // (M, D) behaviour policy
+    const float* sigma_b;
+    const float* action;   // (M, D)
+    const float* weight;   // nullable (M)
+    long long M;
+    int D;
+    float* lp_t;           // (M) log pi(a)            | backward: unused
+    float* isw;            // (M) importance weight    | backward: cpg = adv*w
+    float* ent;            // (M) entropy              | backward: dV
+    const float* g_pg;
+    const float* g_val;
+    const float* g_ent;
+    float* grad_mu;
+    float* grad_sigma;
+    float* grad_value;     // (T+1, B)
+    long long B;
+};
+
+__device__ __forceinline__ float vtc_logp(const float* mu, const float* sg, const float* ac, int D) {
+    float lp = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float df = ac[d] - mu[d], s_ = sg[d];
+        lp += -(df * df) / (2.f * s_ * s_) - logf(s_) - 0.9189385332046727f;  // Normal.log_prob
+    }
+    return lp;
+}
+
+__global__ void __launch_bounds__(256) vtc_rows_kernel(VtcArgs a) {
+    pdl_prologue();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.M; i += (long long)gridDim.x * 256) {
+        const long long o = i * a.D;
+        const float lp = vtc_logp(a.mu_t + o, a.sigma_t + o, a.action + o, a.D);
+        const float lb = vtc_logp(a.mu_b + o, a.sigma_b + o, a.action + o, a.D);
+        float e = 0.f;
+        for (int d = 0; d < a.D; ++d) e += 1.4189385332046727f + logf(a.sigma_t[o + d]);  // Normal.entropy
+        a.lp_t[i] = lp;
+        a.isw[i] = expf(lp - lb);  // isw.py:49-53
+        a.ent[i] = e;
+    }
+}
+
+__global__ void __launch_bounds__(256) vtc_bwd_kernel(VtcArgs a) {
+    pdl_prologue();
+    const float g_pg = a.g_pg ? *a.g_pg : 0.f, g_val = a.g_val ? *a.g_val : 0.f, g_ent = a.g_ent ? *a.g_ent : 0.f;
+    const float inv_m = 1.f / (float)a.M;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.M + a.B; i += (long long)gridDim.x * 256) {
+        if (i >= a.M) {  // the bootstrap row V_T receives no gradient
+            a.grad_value[i] = 0.f;
+            continue;
+        }
+        const long long o = i * a.D;
+        const float w = a.weight ? a.weight[i] : 1.f;
+        const float c_lp = g_pg * (-a.isw[i]) * inv_m;  // d (-mean(lp * adv * w)) / d lp
+        const float c_ent = g_ent * w * inv_m;
+        for (int d = 0; d < a.D; ++d) {
+            const float sd = a.sigma_t[o + d], df = a.action[o + d] - a.mu_t[o + d], inv = 1.f / sd;
+            a.grad_mu[o + d] = c_lp * df * inv * inv;
+            a.grad_sigma[o + d] = c_lp * (df * df * inv * inv * inv - inv) + c_ent * inv;
+        }
+        a.grad_value[i] = g_val * a.ent[i];
+    }
+}
+
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -733,6 +803,19 @@ static bool vt_tile_ok(const VtArgs& a, bool bwd) {
     return al && a.N <= 32;
 }
 
+// the column-tile scan that turns (log pi(a), importance weight, entropy) rows into vs / advantages / losses / gradient
+// coefficients: shared by the discrete and the continuous head
+static int launch_vt_scan(const VtArgs& a, float* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (a.B >= 16 * 296) {
+        if (!ws_partials_fit((long long)(3 * div_up(a.B, 16)), workspace_bytes)) return B200RL_ERR_WORKSPACE;
+        (void)launch_k(vtrace_scan_kernel<16, 256, 64>, div_up(a.B, 16), 256, 0, st, a, workspace);
+    } else {
+        if (!ws_partials_fit((long long)(3 * div_up(a.B, 8)), workspace_bytes)) return B200RL_ERR_WORKSPACE;
+        (void)launch_k(vtrace_scan_kernel<8, 64, 64>, div_up(a.B, 8), 64, 0, st, a, workspace);
+    }
+    return (int)cudaGetLastError();
+}
+
 static int vt_mode(const VtArgs& a) {
     const bool al = aligned16(a.target) && aligned16(a.behaviour) && (!a.grad_logit || aligned16(a.grad_logit));
     if (a.N <= 32 && al) return 0;
@@ -771,14 +854,7 @@ extern "C" int b200rl_vtrace_fwd(const float* target_output, const float* behavi
     }
     int rc = (int)cudaGetLastError();
     if (rc) return rc;
-    if (B >= 16 * 296) {
-        if (!ws_partials_fit((long long)(3 * div_up(B, 16)), workspace_bytes)) return B200RL_ERR_WORKSPACE;
-        (void)launch_k(vtrace_scan_kernel<16, 256, 64>, div_up(B, 16), 256, 0, st, a, workspace);
-    } else {
-        if (!ws_partials_fit((long long)(3 * div_up(B, 8)), workspace_bytes)) return B200RL_ERR_WORKSPACE;
-        (void)launch_k(vtrace_scan_kernel<8, 64, 64>, div_up(B, 8), 64, 0, st, a, workspace);
-    }
-    return (int)cudaGetLastError();
+    return launch_vt_scan(a, workspace, workspace_bytes, st);
 }
 
 extern "C" int b200rl_vtrace_bwd(const float* target_output, const long long* action, const float* weight,
@@ -801,5 +877,50 @@ extern "C" int b200rl_vtrace_bwd(const float* target_output, const long long* ac
     if (mode == 0) (void)launch_k(vtrace_bwd_kernel<NT, 0>, div_up(M, NT), NT, (size_t)NT * a.N * sizeof(float), st, a);
     else if (mode == 1) (void)launch_k(vtrace_bwd_kernel<NT, 1>, div_up(M, NT), NT, 0, st, a);
     else (void)launch_k(vtrace_bwd_kernel<NT, 2>, div_up(M, NT / 32), NT, 0, st, a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_vtrace_continuous_fwd(const float* mu_target, const float* sigma_target, const float* mu_behaviour,
+                                            const float* sigma_behaviour, const float* action, const float* value,
+                                            const float* reward, const float* weight, long long T, long long B, long long D,
+                                            double gamma, double lambda_, double rho_clip_ratio, double c_clip_ratio,
+                                            double rho_pg_clip_ratio, float* out3, float* lp_saved, float* cpg_saved,
+                                            float* dv_saved, float* workspace, size_t workspace_bytes, void* stream) {
+    if (T <= 0 || B <= 0 || D < 1 || !mu_target || !sigma_target || !mu_behaviour || !sigma_behaviour || !action || !value ||
+        !reward || !out3 || !lp_saved || !cpg_saved || !dv_saved || !workspace)
+        return B200RL_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    VtcArgs r{};
+    r.mu_t = mu_target; r.sigma_t = sigma_target; r.mu_b = mu_behaviour; r.sigma_b = sigma_behaviour; r.action = action;
+    r.M = T * B; r.D = (int)D; r.lp_t = lp_saved; r.isw = cpg_saved; r.ent = dv_saved;
+    long long grid = div_up(r.M, 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    (void)launch_k(vtc_rows_kernel, (int)grid, 256, 0, st, r);
+    int rc = (int)cudaGetLastError();
+    if (rc) return rc;
+    VtArgs a{};
+    a.value = value; a.reward = reward; a.weight = weight; a.T = T; a.B = B; a.N = (int)D; a.gamma = (float)gamma;
+    a.gamma_lambda = (float)(gamma * lambda_);
+    a.rho_clip = (float)rho_clip_ratio; a.c_clip = (float)c_clip_ratio; a.rho_pg_clip = (float)rho_pg_clip_ratio;
+    a.lp_t = lp_saved; a.isw = cpg_saved; a.ent = dv_saved; a.out = out3;
+    return launch_vt_scan(a, workspace, workspace_bytes, st);
+}
+
+extern "C" int b200rl_vtrace_continuous_bwd(const float* mu_target, const float* sigma_target, const float* action,
+                                            const float* weight, const float* cpg_saved, const float* dv_saved,
+                                            const float* g_policy, const float* g_value, const float* g_entropy, long long T,
+                                            long long B, long long D, float* grad_mu, float* grad_sigma, float* grad_value,
+                                            void* stream) {
+    if (T <= 0 || B <= 0 || D < 1 || !mu_target || !sigma_target || !action || !cpg_saved || !dv_saved || !grad_mu ||
+        !grad_sigma || !grad_value)
+        return B200RL_ERR_ARG;
+    VtcArgs r{};
+    r.mu_t = mu_target; r.sigma_t = sigma_target; r.action = action; r.weight = weight; r.M = T * B; r.B = B; r.D = (int)D;
+    r.isw = const_cast<float*>(cpg_saved); r.ent = const_cast<float*>(dv_saved);
+    r.g_pg = g_policy; r.g_val = g_value; r.g_ent = g_entropy; r.grad_mu = grad_mu; r.grad_sigma = grad_sigma;
+    r.grad_value = grad_value;
+    long long grid = div_up(r.M + B, 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    (void)launch_k(vtc_bwd_kernel, (int)grid, 256, 0, (cudaStream_t)stream, r);
     return (int)cudaGetLastError();
 }

@@ -839,3 +839,42 @@ class VTraceFunction(torch.autograd.Function):
             )
         _lib.check(rc, 'b200rl_vtrace_bwd')
         return (grad_logit, grad_value) + (None, ) * 9
+
+
+class VTraceContinuousFunction(torch.autograd.Function):
+    """vtrace_error_continuous_action (ding/rl_utils/vtrace.py:139-212): rows kernel -> shared scan -> backward rows kernel."""
+
+    @staticmethod
+    def forward(ctx, mu, sigma, value, mu_b, sigma_b, action, reward, weight, D, gamma, lambda_, rho_clip, c_clip,
+                rho_pg_clip):
+        T, B = reward.shape
+        dev = mu.device
+        out = torch.empty(4, dtype=torch.float32, device=dev)
+        lp = torch.empty(T, B, dtype=torch.float32, device=dev)
+        cpg = torch.empty(T, B, dtype=torch.float32, device=dev)
+        dv = torch.empty(T, B, dtype=torch.float32, device=dev)
+        with on_device(dev):
+            ws = workspace(dev)
+            rc = lib().b200rl_vtrace_continuous_fwd(
+                ptr(mu), ptr(sigma), ptr(mu_b), ptr(sigma_b), ptr(action), ptr(value), ptr(reward), ptr(weight), T, B, D,
+                gamma, lambda_, rho_clip, c_clip, rho_pg_clip, ptr(out), ptr(lp), ptr(cpg), ptr(dv), ptr(ws),
+                ws.numel() * 4, stream_ptr())
+        _lib.check(rc, 'b200rl_vtrace_continuous_fwd')
+        ctx.save_for_backward(mu, sigma, action, weight, cpg, dv)
+        ctx.cfg = (T, B, D)
+        ctx.set_materialize_grads(False)
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_p, g_v, g_e):
+        mu, sigma, action, weight, cpg, dv = ctx.saved_tensors
+        T, B, D = ctx.cfg
+        keep = [_g(x) for x in (g_p, g_v, g_e)]
+        gm, gs = torch.empty_like(mu), torch.empty_like(sigma)
+        gv = torch.empty(T + 1, B, dtype=torch.float32, device=mu.device)
+        with on_device(mu.device):
+            rc = lib().b200rl_vtrace_continuous_bwd(ptr(mu), ptr(sigma), ptr(action), ptr(weight), ptr(cpg), ptr(dv),
+                                                    keep[0][1], keep[1][1], keep[2][1], T, B, D, ptr(gm), ptr(gs), ptr(gv),
+                                                    stream_ptr())
+        _lib.check(rc, 'b200rl_vtrace_continuous_bwd')
+        return (gm, gs, gv) + (None, ) * 11

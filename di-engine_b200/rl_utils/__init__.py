@@ -12,14 +12,16 @@ from .td import (bdq_nstep_td_error, dist_1step_td_data, dist_1step_td_error, di
                  v_1step_td_data, v_1step_td_error, v_nstep_td_data, v_nstep_td_error)
 from .upgo import tb_cross_entropy, upgo_loss, upgo_returns
 from .value_rescale import value_inv_transform, value_transform
-from .vtrace import impala_reshape_data, shape_fn_vtrace_discrete_action, vtrace_data, vtrace_error_discrete_action, vtrace_loss
+from .vtrace import (impala_reshape_data, shape_fn_vtrace_discrete_action, vtrace_data, vtrace_error_continuous_action,
+                     vtrace_error_discrete_action, vtrace_loss)
 
 HOT_PATH_FUNCTIONS = [
     'gae', 'ppo_error', 'q_nstep_td_error', 'q_nstep_td_error_with_rescale', 'dist_nstep_td_error', 'td_lambda_error',
     'generalized_lambda_returns', 'upgo_loss', 'vtrace_error_discrete_action',
     # siblings on the same kernels
     'q_1step_td_error', 'v_1step_td_error', 'v_nstep_td_error', 'ppo_policy_error', 'ppo_value_error',
-    'dist_1step_td_error', 'bdq_nstep_td_error', 'upgo_returns', 'tb_cross_entropy', 'ppo_error_continuous', 'a2c_error'
+    'dist_1step_td_error', 'bdq_nstep_td_error', 'upgo_returns', 'tb_cross_entropy', 'ppo_error_continuous', 'a2c_error',
+    'vtrace_error_continuous_action'
 ]
 HOT_PATH_TYPES = [
     'gae_data', 'ppo_data', 'ppo_loss', 'ppo_info', 'q_nstep_td_data', 'dist_nstep_td_data', 'td_lambda_data',

@@ -59,6 +59,43 @@ def vtrace_error_discrete_action(
     return vtrace_loss(p, vl, e)
 
 
+def vtrace_error_continuous_action(
+        data: namedtuple,
+        gamma: float = 0.99,
+        lambda_: float = 0.95,
+        rho_clip_ratio: float = 1.0,
+        c_clip_ratio: float = 1.0,
+        rho_pg_clip_ratio: float = 1.0
+):
+    """
+    V-trace (IMPALA) loss for a continuous action space, drop-in for ding/rl_utils/vtrace.py:139-212: ``target_output`` and
+    ``behaviour_output`` are dicts ``{'mu': (T, B, D), 'sigma': (T, B, D)}`` of ``Independent(Normal)`` policies, action
+    (T, B, D) float, value (T+1, B), reward / weight (T, B).  Returns ``vtrace_loss``; gradients reach the target policy's
+    ``mu`` / ``sigma`` and ``value``.  Rows kernel -> the scan of the discrete head -> backward rows kernel (csrc/pg.cu).
+    """
+    target_output, behaviour_output, action, value, reward, weight = data
+    mu, sigma = target_output['mu'], target_output['sigma']
+    dev = ops.compute_device(mu, value)
+    host_out = not mu.is_cuda
+    T, B = reward.shape
+    D = mu.shape[-1]
+    for name, t_, n in (('mu', mu, T * B * D), ('sigma', sigma, T * B * D), ('behaviour mu', behaviour_output['mu'], T * B * D),
+                        ('behaviour sigma', behaviour_output['sigma'], T * B * D), ('action', action, T * B * D),
+                        ('value', value, (T + 1) * B)):
+        if t_.numel() != n:
+            raise ValueError("vtrace_error_continuous_action: %s %s does not match reward %s" %
+                             (name, tuple(t_.shape), tuple(reward.shape)))
+    f = lambda t, nm: ops.f32c(ops.to_device(t, dev), nm)  # noqa: E731
+    w = f(weight.detach(), 'weight') if weight is not None else None
+    p, v, e = ops.VTraceContinuousFunction.apply(
+        f(mu, 'mu'), f(sigma, 'sigma'), f(value, 'value'), f(behaviour_output['mu'].detach(), 'mu_b'),
+        f(behaviour_output['sigma'].detach(), 'sigma_b'), f(action.detach(), 'action'), f(reward.detach(), 'reward'), w, D,
+        float(gamma), float(lambda_), float(rho_clip_ratio), float(c_clip_ratio), float(rho_pg_clip_ratio))
+    if host_out:
+        p, v, e = p.cpu(), v.cpu(), e.cpu()
+    return vtrace_loss(p, v, e)
+
+
 def impala_reshape_data(values: torch.Tensor, rewards: torch.Tensor, done: torch.Tensor):
     """
     The masking ``IMPALAPolicy._reshape_data`` applies between the model output and ``vtrace_error_*`` (ding/policy/impala.py:

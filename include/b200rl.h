@@ -218,6 +218,20 @@ B200RL_API int b200rl_vtrace_bwd(const float* target_output, const long long* ac
                       const float* g_entropy, long long T, long long B, long long N, float* grad_target_output,
                       float* grad_value, void* stream);
 
+/* vtrace_error_continuous_action (ding/rl_utils/vtrace.py:139-212): Independent(Normal(mu, sigma)) target / behaviour
+ * policies, mu / sigma / action (T*B, D) floats; otherwise as b200rl_vtrace_fwd / _bwd (rows kernel -> the shared scan ->
+ * backward rows kernel; gradients reach mu_target, sigma_target and value). */
+B200RL_API int b200rl_vtrace_continuous_fwd(const float* mu_target, const float* sigma_target, const float* mu_behaviour,
+                                 const float* sigma_behaviour, const float* action, const float* value,
+                                 const float* reward, const float* weight, long long T, long long B, long long D,
+                                 double gamma, double lambda_, double rho_clip_ratio, double c_clip_ratio,
+                                 double rho_pg_clip_ratio, float* out3, float* lp_saved, float* cpg_saved, float* dv_saved,
+                                 float* workspace, size_t workspace_bytes, void* stream);
+B200RL_API int b200rl_vtrace_continuous_bwd(const float* mu_target, const float* sigma_target, const float* action,
+                                 const float* weight, const float* cpg_saved, const float* dv_saved, const float* g_policy,
+                                 const float* g_value, const float* g_entropy, long long T, long long B, long long D,
+                                 float* grad_mu, float* grad_sigma, float* grad_value, void* stream);
+
 /* ---- V-trace in one launch: forward AND gradients (csrc/vtws.cu) ---------------------------------------------------
  * Same semantics as b200rl_vtrace_fwd followed by b200rl_vtrace_bwd, but the batch crosses HBM once (96 B per transition at
  * N = 6): column tiles, warp-specialised loader / scanner / consumer warps.  The gradients are produced in the forward

@@ -705,3 +705,33 @@ def vtrace_error_discrete_action(
     value_loss = (torch.nn.functional.mse_loss(value[:-1], vs, reduction='none') * weight).mean()  # no 0.5
     entropy_loss = (_row_entropy(lp_all) * weight).mean()
     return pg_loss, value_loss, entropy_loss
+
+
+def vtrace_error_continuous_action(mu_target, sigma_target, mu_behaviour, sigma_behaviour, action, value, reward, weight=None,
+                                   gamma: float = 0.99, lambda_: float = 0.95, rho_clip_ratio: float = 1.0,
+                                   c_clip_ratio: float = 1.0, rho_pg_clip_ratio: float = 1.0):
+    """vtrace.py:139-212 with the Independent(Normal) log-prob / entropy written out (see ppo_error_continuous)."""
+
+    def logp(mu, sigma):
+        return (-((action - mu) ** 2) / (2 * sigma ** 2) - sigma.log() - math.log(math.sqrt(2 * math.pi))).sum(-1)
+
+    with torch.no_grad():
+        IS = torch.exp(logp(mu_target, sigma_target) - logp(mu_behaviour, sigma_behaviour))  # isw.py:49-53
+        rhos = torch.clamp(IS, max=rho_clip_ratio)
+        cs = torch.clamp(IS, max=c_clip_ratio)
+        deltas = rhos * (reward + gamma * value[1:] - value[:-1])  # vtrace.py:22
+        trace = gamma * lambda_
+        return_ = value[:-1].clone()
+        carry = 0.
+        for t in range(reward.size(0) - 1, -1, -1):  # vtrace.py:26-28
+            carry = deltas[t] + trace * cs[t] * carry
+            return_[t] += carry
+        pg_rhos = torch.clamp(IS, max=rho_pg_clip_ratio)
+        return_t_plus_1 = torch.cat([return_[1:], value[-1:]], 0)
+        adv = pg_rhos * (reward + gamma * return_t_plus_1 - value[:-1])  # vtrace.py:32-45
+    if weight is None:
+        weight = torch.ones_like(reward)
+    pg_loss = -(logp(mu_target, sigma_target) * adv * weight).mean()
+    value_loss = (torch.nn.functional.mse_loss(value[:-1], return_, reduction='none') * weight).mean()
+    entropy_loss = ((0.5 + 0.5 * math.log(2 * math.pi) + torch.log(sigma_target)).sum(-1) * weight).mean()
+    return pg_loss, value_loss, entropy_loss

@@ -22,6 +22,7 @@ GRAD_INPUTS = {
     'ppo_value': ['value_new'],
     'ppoc': ['mu_new', 'sigma_new', 'value_new'],
     'a2c': ['logit', 'value'],
+    'vtc': ['mu_target', 'sigma_target', 'value'],
     'qntd': ['q'],
     'qntd_rescale': ['q'],
     'q1td': ['q'],
@@ -42,6 +43,7 @@ LOSS_MIX = {
     'ppo_value': [0.7],
     'ppoc': [1.0, 0.5, -0.01, 0.3],
     'a2c': [1.0, 0.5, -0.01],
+    'vtc': [1.0, 0.5, -0.01],
     'qntd': [1.0],
     'qntd_rescale': [1.0],
     'q1td': [1.0],
@@ -386,6 +388,21 @@ def _qntd_marl(seed):
     return t, dict(gamma=0.9, nstep=nstep, cum_reward=False)
 
 
+def vtc_case(seed, T, B, D, weight='none', **params):
+    """vtrace_error_continuous_action (tests/test_vtrace.py:25-47)"""
+    g = _g(seed)
+    t = OrderedDict()
+    t['mu_target'] = _randn(g, T, B, D)
+    t['sigma_target'] = torch.exp(0.3 * _randn(g, T, B, D))
+    t['mu_behaviour'] = t['mu_target'] + 0.2 * _randn(g, T, B, D)
+    t['sigma_behaviour'] = torch.exp(0.3 * _randn(g, T, B, D))
+    t['action'] = _randn(g, T, B, D)
+    t['value'] = _randn(g, T + 1, B)
+    t['reward'] = _rand(g, T, B)
+    t['weight'] = None if weight == 'none' else _rand(g, T, B)
+    return 'vtc', t, params
+
+
 def build_cases():
     """Small cases: what the golden fixtures hold and what every implementation is compared on."""
     c = OrderedDict()
@@ -457,6 +474,8 @@ def build_cases():
     c['ppoc_w_dc_novc'] = ppoc_case(111, 33, 3, weight='tensor', dual_clip=5.0, use_value_clip=False)
     c['ppoc_kl_k3'] = ppoc_case(112, 20, 4, weight='tensor', pretrained=True, kl_type='k3')
     c['ppoc_old_1d'] = ppoc_case(113, 17, 1, old_1d=True)
+    c['vtc_small'] = vtc_case(116, 4, 8, 16, rho_clip_ratio=1.1)
+    c['vtc_w_clips'] = vtc_case(117, 13, 5, 3, weight='tensor', rho_clip_ratio=0.8, c_clip_ratio=1.3, rho_pg_clip_ratio=2.0)
     c['a2c_basic'] = a2c_case(114, 64, 6)
     c['a2c_w_wide'] = a2c_case(115, 9, 130, weight='tensor')
     # ---- dist_nstep (tests/test_td.py:130-204) ---------------------------------------------------------------
@@ -550,6 +569,15 @@ def run_api(api, op, tensors, params, device='cpu'):
             res['out_' + k] = _np(getattr(loss, k))
         res['out_approx_kl'] = np.float32(info.approx_kl)
         res['out_clipfrac'] = np.float32(info.clipfrac)
+        _backward(op, list(loss), t, res)
+        return res
+    if op == 'vtc':
+        data = api.vtrace_data({'mu': t['mu_target'], 'sigma': t['sigma_target']},
+                               {'mu': t['mu_behaviour'], 'sigma': t['sigma_behaviour']}, t['action'], t['value'], t['reward'],
+                               t['weight'])
+        loss = api.vtrace_error_continuous_action(data, **p)
+        for k in ('policy_loss', 'value_loss', 'entropy_loss'):
+            res['out_' + k] = _np(getattr(loss, k))
         _backward(op, list(loss), t, res)
         return res
     if op == 'a2c':
@@ -719,6 +747,12 @@ def run_oracle(orc, op, tensors, params):
         res['out_approx_kl'] = np.float32(out[4])
         res['out_clipfrac'] = np.float32(out[5])
         _backward(op, list(out[:4]), t, res)
+        return res
+    if op == 'vtc':
+        out = orc.vtrace_error_continuous_action(**t, **p)
+        for k, v in zip(('policy_loss', 'value_loss', 'entropy_loss'), out):
+            res['out_' + k] = _np(v)
+        _backward(op, list(out), t, res)
         return res
     if op == 'a2c':
         out = orc.a2c_error(**t)

@@ -18,6 +18,7 @@ INPUT_ORDER = {
     'ppoc': ['mu_new', 'sigma_new', 'mu_old', 'sigma_old', 'action', 'value_new', 'value_old', 'adv', 'return_', 'weight',
              'mu_pretrained', 'sigma_pretrained'],
     'a2c': ['logit', 'action', 'value', 'adv', 'return_', 'weight'],
+    'vtc': ['mu_target', 'sigma_target', 'mu_behaviour', 'sigma_behaviour', 'action', 'value', 'reward', 'weight'],
     'qntd': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight', 'value_gamma'],
     'qntd_rescale': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'weight', 'value_gamma'],
     'q1td': ['q', 'next_q', 'act', 'next_act', 'reward', 'done', 'weight'],

@@ -200,6 +200,7 @@ EXPECTED_CALLS = {
     'ppo_value': ['b200rl_ppo_value_fwd', 'b200rl_scale'],
     'ppoc': ['b200rl_ppo_continuous_fwd_grad', 'b200rl_ppo_continuous_fwd_grad'],
     'a2c': ['b200rl_a2c_fwd_grad', 'b200rl_a2c_fwd_grad'],
+    'vtc': ['b200rl_vtrace_continuous_fwd', 'b200rl_vtrace_continuous_bwd'],
     'qntd': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'qntd_rescale': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],
     'q1td': ['b200rl_qntd_fwd', 'b200rl_qntd_bwd'],

@@ -731,6 +731,40 @@ def test_vtrace_discrete_action(impl):
     _run(_vtrace_body, impl)
 
 
+def _vtrace_continuous_body(api, dev, rec):
+    g = _gen(32)
+    T, B, N = 4, 8, 16  # test_vtrace.py:25-47
+    value = torch.randn(T + 1, B, generator=g).to(dev).requires_grad_(True)
+    reward = torch.rand(T, B, generator=g).to(dev)
+    target_output = {}
+    target_output['mu'] = torch.randn(T, B, N, generator=g).to(dev).requires_grad_(True)
+    target_output['sigma'] = torch.exp(torch.randn(T, B, N, generator=g)).to(dev).requires_grad_(True)
+    behaviour_output = {}
+    behaviour_output['mu'] = torch.randn(T, B, N, generator=g).to(dev)
+    behaviour_output['sigma'] = torch.exp(torch.randn(T, B, N, generator=g)).to(dev)
+    action = torch.randn((T, B, N), generator=g).to(dev)
+    data = api.vtrace_data(target_output, behaviour_output, action, value, reward, None)
+    loss = api.vtrace_error_continuous_action(data, rho_clip_ratio=1.1)
+    assert all([l.shape == tuple() for l in loss])
+    assert target_output['mu'].grad is None
+    assert target_output['sigma'].grad is None
+    assert value.grad is None
+    for k, v in zip(loss._fields, loss):
+        rec.put(k, v)
+    loss = sum(loss)
+    loss.backward()
+    assert isinstance(target_output['mu'], torch.Tensor)
+    assert isinstance(target_output['sigma'], torch.Tensor)
+    assert isinstance(value, torch.Tensor)
+    rec.put('grad_mu', target_output['mu'].grad)
+    rec.put('grad_sigma', target_output['sigma'].grad)
+    rec.put('grad_value', value.grad)
+
+
+def test_vtrace_continuous_action(impl):
+    _run(_vtrace_continuous_body, impl)
+
+
 # =================================================================================================================
 # ding/rl_utils/tests/test_upgo.py
 # =================================================================================================================
