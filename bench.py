@@ -236,6 +236,108 @@ class DeviceStepD:
         self.b['next_value'].copy_(self.nv0)
 
 
+class WorkloadP(WorkloadD):
+    """Config D as PPOPolicy._forward_learn really composes it (ding/policy/ppo.py:274-306): value-norm scale -> gae ->
+    unnormalized return / stored value / return_ + running statistics -> (adv - mean) / (std + 1e-8) -> ppo_error, backward.
+    gae_returns 36 B (20 in + 16 out) + adv_stats 4 B + ppo forward-with-gradient 104 B per transition."""
+    key = 'P'
+    alg_bytes = {'gae_returns': 36, 'adv_stats': 4, 'ppo_fwd_grad': 104, 'ppo_bwd_check': 0}
+    step_bytes_per_unit = 144
+    STD = 1.7320508
+
+    def __init__(self, B=B_COLS, T=T_LEN, N=N_ACT):
+        super().__init__(B=B, T=T, N=N, mode='policy')
+        self.metric = 'learner transitions/sec (PPOPolicy advantage recompute + ppo_error fwd+bwd, T=128 x B=4096 per GPU)'
+        self.workload = ('configs[3] as PPOPolicy._forward_learn composes it (policy/ppo.py:274-306): value_norm scale, gae, '
+                         'returns + running stats, advantage normalisation, ppo_error fwd+bwd; T=%d x B=%d x N=%d per GPU, '
+                         'fp32' % (T, B, N))
+
+    def make_batch(self, seed):
+        b = make_batch(seed, self.T, self.B, self.N)
+        del b['return_'], b['value_old']  # both come out of the advantage recompute (policy/ppo.py:283-292)
+        return b
+
+    def cpu_step(self, api, b, device=None):
+        """policy/ppo.py:274-306 executed literally around the reference API (RunningMeanStd.update's numpy reduction included)"""
+        std = self.STD
+        with torch.no_grad():
+            value, next_value = b['value'] * std, b['next_value'] * std
+            adv = api.gae(api.gae_data(value, next_value, b['reward'], b['done'], b['traj_flag']), GAMMA, LAMBDA)
+            unnormalized_returns = value + adv
+            value, return_ = value / std, unnormalized_returns / std
+            x = unnormalized_returns.cpu().numpy()
+            x.mean(), x.var()
+            adv = adv.reshape(-1)
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        ln = b['logit_new'].detach().requires_grad_(True)
+        vn = b['value_new'].detach().requires_grad_(True)
+        loss, info = api.ppo_error(api.ppo_data(ln, b['logit_old'], b['action'], vn, value.reshape(-1), adv,
+                                                return_.reshape(-1), None, None), CLIP, True, None)
+        (loss.policy_loss + W_VALUE * loss.value_loss + W_ENTROPY * loss.entropy_loss).backward()
+        return loss.policy_loss.detach()
+
+    def device_step(self, host_batch, dev, exchange=None):
+        return DeviceStepP(self, host_batch, dev)
+
+    def e2e_compute(self, b2, d, three):
+        ln = d['logit_new'].requires_grad_(True)
+        vn = d['value_new'].requires_grad_(True)
+        g = b2.gae_returns(b2.gae_data(d['value'], d['next_value'], d['reward'], d['done'], d['traj_flag']), GAMMA, LAMBDA,
+                           self.STD)
+        loss, info = b2.ppo_error_adv_norm(
+            b2.ppo_data(ln, d['logit_old'], d['action'], vn, g.value.view(-1), g.adv.view(-1), g.return_.view(-1), None, None),
+            CLIP, True, None)
+        total = loss.policy_loss + W_VALUE * loss.value_loss + W_ENTROPY * loss.entropy_loss
+        total.backward()
+        return total
+
+
+class DeviceStepP(DeviceStepD):
+
+    def __init__(self, wl, host_batch, dev):
+        super().__init__(wl, host_batch, dev)
+        self.unnorm, self.vout, self.rout = (torch.empty_like(self.adv) for _ in range(3))
+        self.ret_stats = torch.zeros(3, device=dev)
+        self.adv_stats = torch.zeros(2, device=dev)
+
+    def _ppo_in(self):
+        b, o = self.b, self.ops
+        return (_p(o, b['logit_new']), _p(o, b['logit_old']), None, _p(o, b['action']), _p(o, b['value_new']),
+                _p(o, self.vout), _p(o, self.adv), _p(o, self.rout), None, self.S, 1, self.wl.N, CLIP, 1, 0.0, 1,
+                _p(o, self.adv_stats))
+
+    def gae_returns(self):
+        b, o = self.b, self.ops
+        rc = o.lib().b200rl_gae_returns(
+            _p(o, b['value']), _p(o, b['next_value']), _p(o, b['reward']), _p(o, b['done']), _p(o, b['traj_flag']), self.wl.T,
+            self.wl.B, 1, GAMMA, LAMBDA, 0, self.wl.STD, _p(o, self.adv), _p(o, self.unnorm), _p(o, self.vout), _p(o, self.rout),
+            _p(o, self.ret_stats), _p(o, self.ws), self.ws.numel() * 4, o.stream_ptr())
+        assert rc == 0, rc
+
+    def adv_stats_k(self):
+        o = self.ops
+        rc = o.lib().b200rl_adv_stats(_p(o, self.adv), self.S, _p(o, self.adv_stats), _p(o, self.ws), self.ws.numel() * 4,
+                                      o.stream_ptr())
+        assert rc == 0, rc
+
+    def kernels(self):
+        return [('gae_returns', self.gae_returns), ('adv_stats', self.adv_stats_k), ('ppo_fwd_grad', self.ppo_fwd_grad),
+                ('ppo_bwd_check', self.ppo_bwd_check)]
+
+    def launches_per_step(self):
+        return 6  # gae scan, returns + statistics, adv_stats, ppo forward-with-gradient, finalize_sums, backward check
+
+    def check(self, host_batch):
+        from oracle import rl_oracle
+        self()
+        torch.cuda.synchronize()
+        hb = host_batch
+        want = rl_oracle.ppo_policy_gae_returns(hb['value'], hb['next_value'], hb['reward'], hb['done'], hb['traj_flag'], GAMMA,
+                                                LAMBDA, self.wl.STD)
+        for got, w, name in zip((self.adv, self.vout, self.rout, self.unnorm), want[:4], ('adv', 'value', 'return', 'unnorm')):
+            assert torch.equal(got.cpu(), w), 'gae_returns parity broken: ' + name
+
+
 def DeviceStep(host_batch, dev, fused='onepass'):
     """entry point of the round-1 experiment tools (tools/exp_*.py, trace_*.py, sweep_col.py): one config-D buffer set with
     the launch decomposition they name ('onepass' | True = three launches | False = unfused)"""
@@ -480,7 +582,7 @@ class DeviceStepE:
         assert torch.isfinite(self.out[:3]).all()
 
 
-WORKLOADS = {'D': WorkloadD, 'B': WorkloadB, 'C': WorkloadC, 'E': WorkloadE}
+WORKLOADS = {'D': WorkloadD, 'P': WorkloadP, 'B': WorkloadB, 'C': WorkloadC, 'E': WorkloadE}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -705,6 +807,8 @@ def run_gpu(args):
         wl = WorkloadD(B=Bl, mode='unfused' if args.unfused else ('three' if args.three else 'onepass'))
     elif args.config == 'E':
         wl = WorkloadE(B=(8192 // world) if strong else 8192)
+    elif args.config == 'P':
+        wl = WorkloadP(B=(B_COLS // world) if strong else B_COLS)
     else:
         wl = WORKLOADS[args.config]()
         if world > 1:
@@ -961,7 +1065,7 @@ def run_gpu(args):
             last = total.item()  # D2H read of the step's result
         return last
 
-    e2e_steps = max(5, min(K, 20)) if wl.key in ('D', 'E') else max(20, min(K, 200))
+    e2e_steps = max(5, min(K, 20)) if wl.key in ('D', 'E', 'P') else max(20, min(K, 200))
     e2e_loop(3)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -997,7 +1101,7 @@ def run_gpu(args):
         else:  # the exchange rides inside the kernel: per-kernel timing alone would deadlock on the peers
             roof.update({'kernel': names[0], 'achieved': step_achieved, 'frac': step_achieved / peak, 'traffic': None,
                          'traffic_source': 'per-kernel timing is a single-GPU leg', 'alg_bytes_per_launch': step_bytes})
-        cpu = run_cpu(wl, steps=8 if wl.key in ('D', 'E') else 40, warmup=2) if world == 1 else None
+        cpu = run_cpu(wl, steps=8 if wl.key in ('D', 'E', 'P') else 40, warmup=2) if world == 1 else None
         e2e_value = units_per_step / (e2e_ms / e2e_steps * 1e-3)
         coll = 'none'
         if world > 1:
@@ -1028,7 +1132,7 @@ def run_gpu(args):
             'cpu_baseline': None if cpu is None else {
                 'value': cpu['value'], 'unit': wl.unit + '/s', 'cores': cpu['cores'], 'kind': cpu['kind'],
                 'sample': 'full batch of the workload, median of %d steps after 2 warm-up (%.1f s CPU), %s' %
-                          (8 if wl.key in ('D', 'E') else 40, cpu['total_s'], cpu_model()),
+                          (8 if wl.key in ('D', 'E', 'P') else 40, cpu['total_s'], cpu_model()),
                 'ms_per_step': cpu['ms_per_step'],
             },
             'e2e': {'value': e2e_value, 'unit': wl.unit + '/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 + (8 if wl.key == 'D' else 0),
@@ -1061,7 +1165,7 @@ def run_reference(args):
         return
     cfg = getattr(args, 'config', 'D')
     wl = WORKLOADS[cfg]()
-    steps = min(args.steps, 400 if cfg in ('D', 'E') else 2000)
+    steps = min(args.steps, 400 if cfg in ('D', 'E', 'P') else 2000)
     r = run_cpu(wl, steps=steps, warmup=max(args.warmup, 1))
     line = {
         'impl': 'reference', 'metric': wl.metric, 'value': r['value'], 'unit': wl.unit + '/s', 'n_gpus': args.gpus,
@@ -1120,7 +1224,7 @@ def main():
     ap.add_argument('--steps', type=int, default=2000)
     ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-cuda'])
-    ap.add_argument('--config', default='D', choices=['D', 'B', 'C', 'E'],
+    ap.add_argument('--config', default='D', choices=['D', 'P', 'B', 'C', 'E'],
                     help='BASELINE.json configs: D (default) gae+ppo_error, B q_nstep_td_error, C dist_nstep_td_error, E vtrace')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='N>1: weak = a full batch per GPU (default); strong = the config-D/E batch sharded over the GPUs')

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "b200rl_ppo_continuous_fwd_grad": [P, P, P, P, P, P, P, P, P, P, P, P, LL, LL, D, I, D, I, P, I, P, P, P, P, P, P, P, P, P,
                                        P, P, c_size_t, P],
     "b200rl_gae_ppo_set_impl": [I],
+    "b200rl_vtrace_set_impl": [I],
     "b200rl_p2p_allreduce_mean": [P, P, I, I, I, P, P, P],
     "b200rl_p2p_mailbox_floats": [I],
     "b200rl_probe_copy": [P, P, LL, I, P],

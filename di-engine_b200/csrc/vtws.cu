@@ -418,11 +418,283 @@ static int vw_pick_stages(int N, bool has_w, int tc = 32) {
     return 0;
 }
 
-static bool vtws_ok(const VtFusedArgs& a) {
+// ---------------------------------------------------------------------------------------------------------------------
+// Resident-tile variant for short trajectories (IMPALA unroll lengths: T*TC transitions fit one CTA's shared memory).
+// A CTA owns TC columns for all T and loads its WHOLE tile with one burst of 16-byte cp.async copies from all 256 threads
+// (every byte of the tile is in flight at once; several CTAs per SM are at different points of load -> phase A -> scan ->
+// phase B, so the SM overlaps one tile's arithmetic with its neighbours' loads without any in-CTA pipeline):
+//   phase A  (thread = transition, strided)  softmax statistics, IS -> shared; {lse, entropy} parked in the behaviour row,
+//                                            which is dead from here on
+//   scan     (warp 0, lane = column)         the reverse recurrence in 16-step register batches, vs rows -> shared
+//   phase B  (thread = transition)           advantages, the three loss terms, both gradients straight to HBM
+// Same arithmetic, operation for operation, as vtrace_ws_kernel; same backward contract (verify launch).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int VR_NT = 256;
+
+__host__ __device__ inline size_t vr_smem_bytes(long long T, int N, bool has_w, int tc) {
+    const size_t e = (size_t)T * tc;
+    return e * (2 * (size_t)N * 4 + 8 + (has_w ? 4 : 0) + 4 + 4) + 2 * (size_t)(T + 1) * tc * 4 + 16;
+}
+
+template <int NC, bool GRADS, int TC>
+__global__ void __launch_bounds__(VR_NT) vtrace_res_kernel(VtFusedArgs a, float* ws) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = NC ? NC : a.N;
+    constexpr int NR = NC ? NC : 1;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool has_w = a.weight != nullptr;
+    const int T = (int)a.T;
+    const long long B = a.B;
+    const int E = T * TC;  // transitions of the tile, e = t * TC + c
+    const long long c0 = (long long)blockIdx.x * TC;
+    const int W = (int)((B - c0) < TC ? (B - c0) : TC);
+    float* zt = reinterpret_cast<float*>(smem);
+    float* zb = zt + (size_t)E * N;
+    long long* sact = reinterpret_cast<long long*>(zb + (size_t)E * N);
+    float* sw = reinterpret_cast<float*>(sact + E);
+    float* sv = sw + (has_w ? E : 0);  // [T+1][TC]
+    float* sr = sv + (T + 1) * TC;     // [T][TC]
+    float* sis = sr + E;               // [T][TC]
+    float* svs = sis + E;              // [T+1][TC]
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    float g_pg = 0.f, g_val = 0.f, g_ent = 0.f;
+    if (GRADS) {
+        if (a.verify) {
+            g_pg = a.g_pg ? *a.g_pg : 0.f;
+            g_val = a.g_val ? *a.g_val : 0.f;
+            g_ent = a.g_ent ? *a.g_ent : 0.f;
+            if (a.g_hint && blockIdx.x == 0 && tid == 0) {
+                a.g_hint[0] = g_pg; a.g_hint[1] = g_val; a.g_hint[2] = g_ent;
+            }
+            if (g_pg == a.g_used[0] && g_val == a.g_used[1] && g_ent == a.g_used[2]) return;  // uniform over the grid
+        } else {
+            g_pg = a.g_expected[0]; g_val = a.g_expected[1]; g_ent = a.g_expected[2];
+            if (blockIdx.x == 0 && tid == 0) {
+                a.g_used[0] = g_pg; a.g_used[1] = g_val; a.g_used[2] = g_ent;
+            }
+        }
+    }
+    // ---- the whole tile, one burst: per time step one contiguous segment of W * esz bytes per tensor ------------------------
+    {
+        auto rows = [&](void* dst, const void* src, int n_rows, int esz) {
+            const int P = TC * esz / 16, Pv = W * esz / 16;  // pieces per row in shared memory / valid ones
+            const unsigned char* g = reinterpret_cast<const unsigned char*>(src) + c0 * esz;
+            const long long rstride = B * esz;
+            unsigned char* d = reinterpret_cast<unsigned char*>(dst);
+            const int n = n_rows * P;
+            for (int p = tid; p < n; p += VR_NT) {
+                const int row = p / P, o = p - row * P;
+                if (o < Pv) cpa16(d + (size_t)p * 16, g + row * rstride + o * 16);
+            }
+        };
+        rows(zt, a.target, T, N * 4);
+        rows(zb, a.behaviour, T, N * 4);
+        rows(sact, a.action, T, 8);
+        rows(sv, a.value, T + 1, 4);
+        rows(sr, a.reward, T, 4);
+        if (has_w) rows(sw, a.weight, T, 4);
+        cpa_commit();
+        cpa_wait<0>();
+    }
+    __syncthreads();
+    // ---- phase A -----------------------------------------------------------------------------------------------------------
+    for (int e = tid; e < E; e += VR_NT) {
+        const int c = e % TC;
+        if (c >= W) continue;
+        const float* z = zt + (size_t)e * N;
+        float* zo_ = zb + (size_t)e * N;
+        const int act = (int)sact[e];
+        float m = kF32Min, sum = 0.f, u2 = 0.f, mb = kF32Min, sb = 0.f;
+        const float zta = z[act], zba = zo_[act];
+        if (NC) {
+            float zz[NR], zo[NR];
+            load_row<NR>(z, zz);
+            load_row<NR>(zo_, zo);
+#pragma unroll
+            for (int k = 0; k < NR; ++k) { m = fmaxf(m, zz[k]); mb = fmaxf(mb, zo[k]); }
+            const float m2 = m * kLog2e, mb2 = mb * kLog2e;
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+                const float t = fmaxf(fmaf(zz[k], kLog2e, -m2), kF32Min);
+                const float ex = ex2f_(t);
+                sum += ex;
+                u2 = fmaf(ex, t, u2);
+                sb += ex2f_(fmaf(zo[k], kLog2e, -mb2));
+            }
+        } else {
+            for (int k = 0; k < N; ++k) { m = fmaxf(m, z[k]); mb = fmaxf(mb, zo_[k]); }
+            const float m2 = m * kLog2e, mb2 = mb * kLog2e;
+            for (int k = 0; k < N; ++k) {
+                const float t = fmaxf(fmaf(z[k], kLog2e, -m2), kF32Min);
+                const float ex = ex2f_(t);
+                sum += ex;
+                u2 = fmaf(ex, t, u2);
+                sb += ex2f_(fmaf(zo_[k], kLog2e, -mb2));
+            }
+        }
+        const float l2s = lg2f_(sum);
+        const float lse = m + l2s * kLn2;
+        const float ent = (l2s - u2 * rcpf_(sum)) * kLn2;
+        const float lp = zta - lse;
+        const float lp_b = (zba - mb) - lg2f_(sb) * kLn2;
+        sis[e] = ex2f_((lp - lp_b) * kLog2e);
+        zo_[0] = lse;  // the behaviour row is dead: park the two statistics phase B needs (N >= 2)
+        zo_[1] = ent;
+    }
+    __syncthreads();
+    // ---- scan (vtrace.py:22-29): lane = column ------------------------------------------------------------------------------
+    if (tid < W) {
+        const int c = tid;
+        float carry = 0.f, above = sv[T * TC + c];
+        svs[T * TC + c] = above;  // vs_T = V_T
+        if (GRADS) a.grad_value[(long long)T * B + c0 + c] = 0.f;
+        int t1 = T;
+        for (; t1 >= 16; t1 -= 16) {
+            const int t0 = t1 - 16;
+            float d[16], g[16], vv[17];
+#pragma unroll
+            for (int k = 0; k <= 16; ++k) vv[k] = sv[(t0 + k) * TC + c];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float is = sis[(t0 + k) * TC + c], rw = sr[(t0 + k) * TC + c];
+                d[k] = fmul(fminf(is, a.rho_clip), fsub(fadd(rw, fmul(a.gamma, vv[k + 1])), vv[k]));
+                g[k] = fmul(a.gamma_lambda, fminf(is, a.c_clip));
+            }
+#pragma unroll
+            for (int k = 15; k >= 0; --k) {
+                carry = fadd(d[k], fmul(g[k], carry));
+                vv[k] = fadd(vv[k], carry);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) svs[(t0 + k) * TC + c] = vv[k];
+        }
+        for (int t = t1 - 1; t >= 0; --t) {
+            const int e = t * TC + c;
+            const float is = sis[e], v = sv[e];
+            const float dl = fmul(fminf(is, a.rho_clip), fsub(fadd(sr[e], fmul(a.gamma, sv[e + TC])), v));
+            carry = fadd(dl, fmul(fmul(a.gamma_lambda, fminf(is, a.c_clip)), carry));
+            svs[e] = fadd(v, carry);
+        }
+    }
+    __syncthreads();
+    // ---- phase B -----------------------------------------------------------------------------------------------------------
+    float acc[3] = {0.f, 0.f, 0.f};
+    const float inv_m = 1.f / (float)((long long)T * B);
+    for (int e = tid; e < E; e += VR_NT) {
+        const int t = e / TC, c = e - t * TC;
+        if (c >= W) continue;
+        const float* z = zt + (size_t)e * N;
+        const float lse = zb[(size_t)e * N], ent = zb[(size_t)e * N + 1];
+        const int act = (int)sact[e];
+        const float lp = z[act] - lse;
+        const float is = sis[e];
+        const float v = sv[e], rw = sr[e];
+        const float w = has_w ? sw[e] : 1.f;
+        const float adv = fmul(fminf(is, a.rho_pg_clip), fsub(fadd(rw, fmul(a.gamma, svs[e + TC])), v));
+        const float dv = v - svs[e];
+        acc[0] += lp * adv * w;
+        acc[1] += dv * dv * w;
+        acc[2] += ent * w;
+        if (GRADS) {
+            const long long g = (long long)t * B + c0 + c;
+            const float c_act = g_pg * (-adv * w) * inv_m, c_ent = g_ent * w * inv_m;
+            float* gz = a.grad_logit + g * N;
+            if (NC) {
+                float zz[NR], gj[NR];
+                load_row<NR>(z, zz);
+#pragma unroll
+                for (int k = 0; k < NR; ++k) {
+                    const float lpk = zz[k] - lse;
+                    const float p = ex2f_(lpk * kLog2e);
+                    gj[k] = -c_act * p - c_ent * p * (lpk + ent);
+                    if (k == act) gj[k] += c_act;
+                }
+                store_row<NR>(gz, gj);
+            } else {
+                for (int k = 0; k < N; ++k) {
+                    const float lpk = z[k] - lse;
+                    const float p = ex2f_(lpk * kLog2e);
+                    float gk = -c_act * p - c_ent * p * (lpk + ent);
+                    if (k == act) gk += c_act;
+                    gz[k] = gk;
+                }
+            }
+            a.grad_value[g] = g_val * (2.f * w * dv * inv_m);
+        }
+    }
+    if (!a.verify) grid_store_partials<3, VR_NT>(acc, ws);  // summed by finalize_sums_kernel
+}
+
+// widest tile that leaves at least two CTAs per SM (227 KB of shared memory per SM, 1 KB reserved per CTA); 0 = no fit
+static int g_vt_impl = 0;  // b200rl_vtrace_set_impl: 0 = automatic, 1 = streaming column tiles only
+static int vr_pick_tc(const VtFusedArgs& a) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("B200RL_VT_RES");  // 0 = never, 4 | 8 = that tile width
+        forced = e ? atoi(e) : -2;
+    }
+    if (forced == 0 || g_vt_impl == 1 || a.N < 2) return 0;
+    const bool has_w = a.weight != nullptr;
+    if (forced == 4 || forced == 8) return vr_smem_bytes(a.T, a.N, has_w, forced) <= 226 * 1024 ? forced : 0;
+    if (a.B % 8 == 0 && vr_smem_bytes(a.T, a.N, has_w, 8) <= 112 * 1024) return 8;
+    if (vr_smem_bytes(a.T, a.N, has_w, 4) <= 112 * 1024) return 4;
+    return 0;
+}
+
+template <int NC, bool GRADS, int TC>
+static int launch_vtres(const VtFusedArgs& a, float* out, float* ws, size_t ws_bytes, cudaStream_t st) {
+    const size_t smem = vr_smem_bytes(a.T, a.N, a.weight != nullptr, TC);
+    auto kern = vtrace_res_kernel<NC, GRADS, TC>;
+    static size_t smem_set = 0;
+    cudaError_t e;
+    if (smem > smem_set) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+            return (int)e;
+        smem_set = smem;
+    }
+    const long long grid = (a.B + TC - 1) / TC;
+    if (ws_bytes < WS_MIN_BYTES || !ws_partials_fit((long long)(grid * 3), ws_bytes)) return B200RL_ERR_WORKSPACE;
+    (void)launch_k(kern, (int)grid, VR_NT, smem, st, a, ws);
+    if (!a.verify) {
+        FinalizeArgs fa{};
+        const double im = 1.0 / ((double)a.T * (double)a.B);
+        fa.scale[0] = -im; fa.scale[1] = im; fa.scale[2] = im;
+        fa.k = 3; fa.n_blocks = (int)grid;
+        (void)launch_finalize(ws, out, fa, st);
+    }
+    return (int)cudaGetLastError();
+}
+
+template <bool GRADS, int TC>
+static int dispatch_vtres(const VtFusedArgs& a, float* out, float* ws, size_t ws_bytes, cudaStream_t st) {
+    switch (a.N) {
+#define B200RL_CASE(n) \
+    case n: return launch_vtres<n, GRADS, TC>(a, out, ws, ws_bytes, st);
+        B200RL_CASE(2) B200RL_CASE(3) B200RL_CASE(4) B200RL_CASE(5) B200RL_CASE(6) B200RL_CASE(7) B200RL_CASE(8)
+        B200RL_CASE(9) B200RL_CASE(10) B200RL_CASE(12) B200RL_CASE(14) B200RL_CASE(16) B200RL_CASE(18)
+#undef B200RL_CASE
+        default: return launch_vtres<0, GRADS, TC>(a, out, ws, ws_bytes, st);
+    }
+}
+
+
+static bool vt_layout_ok(const VtFusedArgs& a) {
     const bool al = aligned16(a.target) && aligned16(a.behaviour) && aligned16(a.action) && aligned16(a.value) &&
                     aligned16(a.reward) && (!a.weight || aligned16(a.weight)) &&
                     (!a.grad_logit || (aligned16(a.grad_logit) && aligned16(a.grad_value)));
-    return al && a.N >= 1 && a.N <= 32 && a.T >= 1 && a.B >= 4 && (a.B % 4) == 0 && vw_pick_stages(a.N, a.weight != nullptr) >= 3;
+    return al && a.N >= 1 && a.T >= 1 && a.B >= 4 && (a.B % 4) == 0;
+}
+// streaming column tiles (any T): the stage ring has to fit twice per SM
+static bool vtws_ok(const VtFusedArgs& a) {
+    return vt_layout_ok(a) && a.N <= 32 && vw_pick_stages(a.N, a.weight != nullptr) >= 3;
+}
+// resident tiles (short T): tile width, 0 = does not fit
+static int vtres_tc(const VtFusedArgs& a) {
+    if (!vt_layout_ok(a) || a.T > (1 << 20)) return 0;
+    const int tc = vr_pick_tc(a);
+    if (tc && WS_CTRL_WORDS + (a.B + tc - 1) / tc * 3 > WS_PARTIAL_LIMIT_WORDS) return 0;
+    return tc;
 }
 
 template <int NC, bool GRADS, int TC>
@@ -510,6 +782,13 @@ static void fill_vt(VtFusedArgs& a, const float* target_output, const float* beh
     a.trace = tr;
 }
 
+extern "C" int b200rl_vtrace_set_impl(int impl) {
+    if (impl < 0 || impl > 1) return B200RL_ERR_ARG;
+    const int old = g_vt_impl;
+    g_vt_impl = impl;
+    return old;
+}
+
 extern "C" int b200rl_vtrace_fused_supported(const float* target_output, const float* behaviour_output,
                                              const long long* action, const float* value, const float* reward,
                                              const float* weight, long long T, long long B, long long N,
@@ -524,7 +803,7 @@ extern "C" int b200rl_vtrace_fused_supported(const float* target_output, const f
         const char* e = getenv("B200RL_VTRACE_FUSED");
         off = (e && e[0] == '0') ? 1 : 0;
     }
-    return (!off && vtws_ok(a)) ? 1 : 0;
+    return (!off && (vtres_tc(a) || vtws_ok(a))) ? 1 : 0;
 }
 
 extern "C" int b200rl_vtrace_fwd_grad(const float* target_output, const float* behaviour_output, const long long* action,
@@ -545,8 +824,15 @@ extern "C" int b200rl_vtrace_fwd_grad(const float* target_output, const float* b
             c_clip_ratio, rho_pg_clip_ratio);
     a.g_expected = g_expected; a.verify = verify ? 1 : 0; a.g_pg = g_policy; a.g_val = g_value; a.g_ent = g_entropy;
     a.g_used = g_used; a.g_hint = g_hint; a.grad_logit = grad_target_output; a.grad_value = grad_value;
-    if (!vtws_ok(a)) return B200RL_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    const int rtc = vtres_tc(a);
+    if (rtc == 8)
+        return grads ? dispatch_vtres<true, 8>(a, out3, workspace, workspace_bytes, st)
+                     : dispatch_vtres<false, 8>(a, out3, workspace, workspace_bytes, st);
+    if (rtc == 4)
+        return grads ? dispatch_vtres<true, 4>(a, out3, workspace, workspace_bytes, st)
+                     : dispatch_vtres<false, 4>(a, out3, workspace, workspace_bytes, st);
+    if (!vtws_ok(a)) return B200RL_ERR_ARG;
     return grads ? dispatch_vtws<true>(a, out3, workspace, workspace_bytes, st)
                  : dispatch_vtws<false>(a, out3, workspace, workspace_bytes, st);
 }

@@ -405,9 +405,18 @@ def _vtrace_close(td, tw, loss, lw):
         assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max()), k
 
 
+@pytest.fixture(params=['auto', 'stream'])
+def vtrace_impl(request):
+    """auto = resident tiles where they fit (short T), else the streaming column tiles; stream = column tiles only"""
+    from di_engine_b200 import ops
+    old = ops.lib().b200rl_vtrace_set_impl({'auto': 0, 'stream': 1}[request.param])
+    yield request.param
+    ops.lib().b200rl_vtrace_set_impl(old)
+
+
 @pytest.mark.parametrize('shape', [(64, 8192, 6), (70, 48, 6), (16, 16, 2), (5, 4, 7), (33, 20, 11), (130, 1028, 6),
                                    (1, 8, 3), (40, 64, 12), (20, 4808, 3)])  # B > 4736: 32-column tiles (the last one 8 wide), ragged T
-def test_vtrace_one_launch_kernel_matches_oracle(shape):
+def test_vtrace_one_launch_kernel_matches_oracle(shape, vtrace_impl):
     """csrc/vtws.cu through the public operator: forward + gradients in one launch, device-verified backward"""
     T, B, N = shape
     from di_engine_b200 import ops
@@ -422,6 +431,20 @@ def test_vtrace_one_launch_kernel_matches_oracle(shape):
         tw, lw, _ = _vtrace_once(t, p, mix, device='cpu')
         td, loss, _ = _vtrace_once(t, p, mix)
         _vtrace_close(td, tw, loss, lw)
+    ops.vtrace_hint(torch.device(DEV)).copy_(torch.tensor([1.0, 0.5, -0.01]))
+
+
+@pytest.mark.parametrize('shape', [(64, 64, 18), (32, 40, 32), (48, 16, 100), (300, 8, 6), (17, 8, 2)])
+def test_vtrace_resident_tiles_take_wide_rows_and_odd_tiles(shape):
+    """shapes the streaming kernel does not take (N > 14: no three-stage ring) or takes with one tile: resident tiles"""
+    T, B, N = shape
+    op, t, p = cases.vtrace_case(970 + T, T, B, N, weight='tensor' if T % 2 else 'none', gamma=0.99, lambda_=0.95,
+                                 rho_clip_ratio=0.9, c_clip_ratio=1.1, rho_pg_clip_ratio=1.3)
+    for mix in ([1.0, 0.5, -0.01], [0.3, 1.7, 0.2]):
+        tw, lw, _ = _vtrace_once(t, p, mix, device='cpu')
+        td, loss, _ = _vtrace_once(t, p, mix)
+        _vtrace_close(td, tw, loss, lw)
+    from di_engine_b200 import ops
     ops.vtrace_hint(torch.device(DEV)).copy_(torch.tensor([1.0, 0.5, -0.01]))
 
 
@@ -445,7 +468,7 @@ def test_vtrace_one_launch_repeated_backward_nograd_legacy_and_fallback():
         ops.VTRACE_FUSED = True
     _vtrace_close(td3, tw, l3, lw)
     assert torch.allclose(td3['target_output'].grad, g1, rtol=1e-5, atol=1e-9)
-    # B % 4 != 0, or N too large for a three-stage ring -> not supported by the one-launch kernel -> pg.cu path
+    # B % 4 != 0 -> not supported by the one-launch kernels -> pg.cu path; N = 18: resident tiles (no three-stage ring)
     for shape in ((20, 30, 6), (24, 64, 18)):
         op, t, p = cases.vtrace_case(951, *shape)
         tw, lw, _ = _vtrace_once(t, p, mix, device='cpu')
