@@ -476,16 +476,34 @@ __global__ void __launch_bounds__(VR_NT) vtrace_res_kernel(VtFusedArgs a, float*
         }
     }
     // ---- the whole tile, one burst: per time step one contiguous segment of W * esz bytes per tensor ------------------------
+    // A thread owns one 16-byte column of the row segment and walks down the rows: two pointer increments per copy, no
+    // division in the loop (the p -> (row, piece) arithmetic of a flat loop was 31 % of the kernel's instructions).
     {
         auto rows = [&](void* dst, const void* src, int n_rows, int esz) {
             const int P = TC * esz / 16, Pv = W * esz / 16;  // pieces per row in shared memory / valid ones
-            const unsigned char* g = reinterpret_cast<const unsigned char*>(src) + c0 * esz;
             const long long rstride = B * esz;
-            unsigned char* d = reinterpret_cast<unsigned char*>(dst);
-            const int n = n_rows * P;
-            for (int p = tid; p < n; p += VR_NT) {
-                const int row = p / P, o = p - row * P;
-                if (o < Pv) cpa16(d + (size_t)p * 16, g + row * rstride + o * 16);
+            if (P <= VR_NT) {
+                const int RP = VR_NT / P;  // rows per pass
+                const int r0 = tid / P, o = tid - r0 * P;
+                if (r0 < RP && o < Pv) {
+                    const unsigned char* g = reinterpret_cast<const unsigned char*>(src) + c0 * esz + r0 * rstride + o * 16;
+                    uint32_t d = smem_u32(dst) + (uint32_t)(r0 * P + o) * 16u;
+                    const long long gstep = (long long)RP * rstride;
+                    const uint32_t dstep = (uint32_t)(RP * P) * 16u;
+                    for (int row = r0; row < n_rows; row += RP) {
+                        cpa16_s(d, g);
+                        g += gstep;
+                        d += dstep;
+                    }
+                }
+            } else {  // very wide rows: flat loop
+                const unsigned char* g = reinterpret_cast<const unsigned char*>(src) + c0 * esz;
+                unsigned char* d = reinterpret_cast<unsigned char*>(dst);
+                const int n = n_rows * P;
+                for (int p = tid; p < n; p += VR_NT) {
+                    const int row = p / P, o = p - row * P;
+                    if (o < Pv) cpa16(d + (size_t)p * 16, g + row * rstride + o * 16);
+                }
             }
         };
         rows(zt, a.target, T, N * 4);

@@ -402,6 +402,56 @@ class QNStepTDFunction(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# quantile-regression n-step TD (QR-DQN / IQN / FQF)
+# ----------------------------------------------------------------------------------------------------------------
+class QuantileTDFunction(torch.autograd.Function):
+    """loss and the per-sample losses (both differentiable w.r.t. q, as in the reference, td.py:1166,:1346,:1436); the forward
+    launch also writes d loss / d q for a unit upstream gradient (verified on the device by the backward launch, as
+    QNStepTDFunction).  ``q_strides`` / ``nq_strides`` / ``tau_strides``: element strides of (sample, quantile[, action])."""
+
+    @staticmethod
+    def forward(ctx, q, next_n_q, action, next_n_action, reward, done, tau, weight, value_gamma, vg_stride, B, N, n_tau,
+                n_tau_prime, nstep, gamma, q_strides, nq_strides, tau_strides, form, kappa):
+        dev = q.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        td = torch.empty(B, dtype=torch.float32, device=dev)
+        dtheta = torch.empty(B, n_tau, dtype=torch.float32, device=dev)
+        grad_unit = torch.empty_like(q) if ctx.needs_input_grad[0] else None
+        with on_device(dev):
+            ws = workspace(dev)
+            rc = lib().b200rl_quantile_td_fwd(
+                ptr(q), ptr(next_n_q), ptr(action), ptr(next_n_action), ptr(reward), ptr(done), ptr(tau), ptr(weight),
+                ptr(value_gamma), vg_stride, B, N, n_tau, n_tau_prime, nstep, gamma, *q_strides, *nq_strides, *tau_strides,
+                form, kappa, ptr(loss), ptr(td), ptr(dtheta), ptr(grad_unit), ptr(ws), ws.numel() * 4, stream_ptr()
+            )
+        _lib.check(rc, 'b200rl_quantile_td_fwd')
+        ctx.save_for_backward(dtheta, action, weight)
+        ctx.cfg = (B, N, n_tau, q_strides)
+        ctx.q_shape = q.shape
+        ctx.spec = grad_unit
+        ctx.set_materialize_grads(False)
+        return loss, td
+
+    @staticmethod
+    def backward(ctx, g_loss, g_td):
+        if g_loss is None and g_td is None:
+            return (None, ) * 21
+        dtheta, action, weight = ctx.saved_tensors
+        B, N, n_tau, q_strides = ctx.cfg
+        keep, pg = _g(g_loss)
+        keep_td = f32c(g_td) if g_td is not None else None
+        grad_q, skip = ctx.spec, 1
+        ctx.spec = None
+        if grad_q is None or g_td is not None:  # repeated backward / a gradient through the per-sample losses
+            grad_q, skip = torch.empty(ctx.q_shape, dtype=torch.float32, device=dtheta.device), 0
+        with on_device(dtheta.device):
+            rc = lib().b200rl_quantile_td_bwd(ptr(dtheta), ptr(weight), ptr(action), pg, ptr(keep_td), B, N, n_tau,
+                                              *q_strides, skip, ptr(grad_q), stream_ptr())
+        _lib.check(rc, 'b200rl_quantile_td_bwd')
+        return (grad_q, ) + (None, ) * 20
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # distributional n-step TD (C51)
 # ----------------------------------------------------------------------------------------------------------------
 class DistNStepTDFunction(torch.autograd.Function):

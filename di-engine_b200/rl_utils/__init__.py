@@ -10,6 +10,8 @@ from .td import (bdq_nstep_td_error, dist_1step_td_data, dist_1step_td_error, di
                  q_nstep_td_error_sequence, q_nstep_td_error_with_rescale, q_nstep_td_seq_data, shape_fn_dntd,
                  shape_fn_qntd, shape_fn_qntd_rescale, shape_fn_td_lambda, td_lambda_data, td_lambda_error,
                  v_1step_td_data, v_1step_td_error, v_nstep_td_data, v_nstep_td_error)
+from .quantile import (fqf_nstep_td_data, fqf_nstep_td_error, iqn_nstep_td_data, iqn_nstep_td_error, qrdqn_nstep_td_data,
+                       qrdqn_nstep_td_error)
 from .upgo import tb_cross_entropy, upgo_loss, upgo_returns
 from .value_rescale import value_inv_transform, value_transform
 from .vtrace import (impala_reshape_data, shape_fn_vtrace_discrete_action, vtrace_data, vtrace_error_continuous_action,
@@ -21,10 +23,11 @@ HOT_PATH_FUNCTIONS = [
     # siblings on the same kernels
     'q_1step_td_error', 'v_1step_td_error', 'v_nstep_td_error', 'ppo_policy_error', 'ppo_value_error',
     'dist_1step_td_error', 'bdq_nstep_td_error', 'upgo_returns', 'tb_cross_entropy', 'ppo_error_continuous', 'a2c_error',
-    'vtrace_error_continuous_action'
+    'vtrace_error_continuous_action', 'qrdqn_nstep_td_error', 'iqn_nstep_td_error', 'fqf_nstep_td_error'
 ]
 HOT_PATH_TYPES = [
     'gae_data', 'ppo_data', 'ppo_loss', 'ppo_info', 'q_nstep_td_data', 'dist_nstep_td_data', 'td_lambda_data',
     'vtrace_data', 'vtrace_loss', 'q_1step_td_data', 'v_1step_td_data', 'v_nstep_td_data',
-    'ppo_policy_data', 'ppo_policy_loss', 'ppo_value_data', 'dist_1step_td_data', 'a2c_data', 'a2c_loss'
+    'ppo_policy_data', 'ppo_policy_loss', 'ppo_value_data', 'dist_1step_td_data', 'a2c_data', 'a2c_loss',
+    'qrdqn_nstep_td_data', 'iqn_nstep_td_data', 'fqf_nstep_td_data'
 ]

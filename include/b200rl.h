@@ -264,6 +264,26 @@ B200RL_API int b200rl_ppo_value_fwd(const float* value_new, const float* value_o
                          const float* weight, long long S, double clip_ratio, int use_value_clip, float* loss,
                          float* dvalue_unit, float* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- quantile-regression n-step TD: qrdqn_nstep_td_error (ding/rl_utils/td.py:1098-1166, form 0), iqn_nstep_td_error
+ * (:1253-1346, form 1), fqf_nstep_td_error (:1359-1436, form 2) -- csrc/quantile.cu, one kernel, the layouts are strides:
+ * theta_i = q[b*q_sb + i*q_si + action_b*q_sa] (i < n_tau), theta'_j from next_n_q likewise (j < n_tau_prime),
+ * tau_i = tau[b*tau_sb + i*tau_si] (a stride may be 0); reward (nstep, B), done / weight(nullable) (B), value_gamma nullable
+ * with element stride vg_stride (0 = one value).  kappa is used by forms 1 and 2 (td.py:1329,:1341,:1431).
+ * Writes loss (scalar), td (B) = the per-sample losses, dtheta (B, n_tau) = d td_b / d theta_i and -- grad_q_unit non-null,
+ * q's layout -- d loss / d q for a unit upstream gradient.  b200rl_quantile_td_bwd: grad_q = (g_loss * w_b / B + g_td_b) *
+ * dtheta scattered to the chosen action (zeros elsewhere); skip_if_unit = 1: grad_q already holds the unit gradient, the
+ * launch returns at once when *g_loss == 1 and g_td is null. */
+B200RL_API int b200rl_quantile_td_fwd(const float* q, const float* next_n_q, const long long* action,
+                           const long long* next_n_action, const float* reward, const float* done, const float* tau,
+                           const float* weight, const float* value_gamma, long long vg_stride, long long B, long long N,
+                           long long n_tau, long long n_tau_prime, long long nstep, double gamma, long long q_sb,
+                           long long q_si, long long q_sa, long long nq_sb, long long nq_sj, long long nq_sa,
+                           long long tau_sb, long long tau_si, int form, double kappa, float* loss, float* td,
+                           float* dtheta, float* grad_q_unit, float* workspace, size_t workspace_bytes, void* stream);
+B200RL_API int b200rl_quantile_td_bwd(const float* dtheta, const float* weight, const long long* action,
+                           const float* g_loss, const float* g_td, long long B, long long N, long long n_tau,
+                           long long q_sb, long long q_si, long long q_sa, int skip_if_unit, float* grad_q, void* stream);
+
 /* ---- sibling heads, forward + gradients in ONE launch each (csrc/heads.cu) ---------------------
  * Same backward contract as b200rl_vtrace_fwd_grad: verify = 0 writes the losses and (grad_* non-null) the gradients for the
  * expected upstream gradients g_expected[k], recording them in g_used; verify = 1 with the actual upstream gradients (device

@@ -735,3 +735,72 @@ def vtrace_error_continuous_action(mu_target, sigma_target, mu_behaviour, sigma_
     value_loss = (torch.nn.functional.mse_loss(value[:-1], return_, reduction='none') * weight).mean()
     entropy_loss = ((0.5 + 0.5 * math.log(2 * math.pi) + torch.log(sigma_target)).sum(-1) * weight).mean()
     return pg_loss, value_loss, entropy_loss
+
+
+def _quantile_target(next_theta, reward, done, gamma, nstep, value_gamma):
+    """n-step target of the three quantile heads (td.py:1144-1159): ``reward_factor`` built in fp32 by repeated multiplication,
+    ``matmul`` with the (nstep, B) rewards, ``gamma ** nstep`` in python double."""
+    reward_factor = torch.ones(nstep)
+    for i in range(1, nstep):
+        reward_factor[i] = gamma * reward_factor[i - 1]
+    r = torch.matmul(reward_factor, reward)  # (B,)
+    g = (gamma ** nstep) if value_gamma is None else value_gamma.reshape(-1, 1)
+    return r.unsqueeze(-1) + g * next_theta * (1 - done).unsqueeze(-1)  # (B, n')
+
+
+def _quantile_loss(theta, target, tau, weight, huber, strict, divisor, mean_over_target):
+    """theta (B, n), target (B, n'), tau (B, n); u = target_j - theta_i, rho = |tau_i - 1[u <= 0 or < 0]| huber(u) / divisor.
+    QR-DQN lays u out as (B, n, n') and takes sum(-1).mean(1) (td.py:1162-1164); IQN / FQF lay it out as (B, n', n, 1) and take
+    sum(dim=2).mean(dim=1)[:, 0] (td.py:1325-1344, :1419-1434) -- kept, so that the summation order is the reference's."""
+    if mean_over_target:
+        u = target.unsqueeze(-1)[:, :, None, :] - theta.unsqueeze(-1)[:, None, :, :]  # (B, n', n, 1)
+        ind = ((u < 0) if strict else (u <= 0)).float().detach()
+        t = tau.unsqueeze(-1)[:, None, :, :].repeat([1, target.shape[1], 1, 1])
+        loss = ((torch.abs(t - ind) * huber(u)) / divisor).sum(dim=2).mean(dim=1)[:, 0]
+    else:
+        u = target.unsqueeze(1) - theta.unsqueeze(2)  # (B, n, n')
+        ind = ((u < 0) if strict else (u <= 0)).float().detach()
+        loss = (huber(u) * (tau.unsqueeze(2) - ind).abs()).sum(-1).mean(1)
+    if weight is None:
+        weight = torch.ones_like(loss)
+    return (loss * weight).mean(), loss
+
+
+def _smooth_l1(u):
+    return torch.where(u.abs() < 1.0, 0.5 * u * u, u.abs() - 0.5)
+
+
+def qrdqn_nstep_td_error(q, next_n_q, action, next_n_action, reward, done, tau, weight=None, gamma: float = 0.99,
+                         nstep: int = 1, value_gamma=None):
+    """td.py:1098-1166: q / next_n_q (B, N, num), smooth-l1, indicator u <= 0, sum over the target axis, mean over num."""
+    rows = torch.arange(action.shape[0])
+    theta = q[rows, action]                # (B, num)
+    target = _quantile_target(next_n_q[rows, next_n_action], reward, done, gamma, nstep, value_gamma)
+    B, num = theta.shape
+    t = torch.broadcast_to(torch.as_tensor(tau, dtype=torch.float32), (B, num, target.shape[1]))[:, :, 0]
+    return _quantile_loss(theta, target, t, weight, _smooth_l1, False, 1.0, False)
+
+
+def iqn_nstep_td_error(q, next_n_q, action, next_n_action, reward, done, replay_quantiles, weight=None, gamma: float = 0.99,
+                       nstep: int = 1, kappa: float = 1.0, value_gamma=None):
+    """td.py:1253-1346: q (tau, B, N), next_n_q (tau', B, N), Huber(kappa) through torch.where(|u| <= kappa), indicator u < 0,
+    / kappa, sum over tau, mean over tau'."""
+    tau_n, B = q.shape[0], done.shape[0]
+    rows = torch.arange(B)
+    theta = q[:, rows, action].t()         # (B, tau)
+    target = _quantile_target(next_n_q[:, rows, next_n_action].t(), reward, done, gamma, nstep, value_gamma)
+
+    def huber(u):
+        return torch.where(u.abs() <= kappa, 0.5 * u ** 2, kappa * (u.abs() - 0.5 * kappa))
+
+    return _quantile_loss(theta, target, replay_quantiles.reshape(tau_n, B).t(), weight, huber, True, kappa, True)
+
+
+def fqf_nstep_td_error(q, next_n_q, action, next_n_action, reward, done, quantiles_hats, weight=None, gamma: float = 0.99,
+                       nstep: int = 1, kappa: float = 1.0, value_gamma=None):
+    """td.py:1359-1436: q (B, tau, N), next_n_q (B, tau', N), smooth-l1 (beta 1), indicator u < 0, / kappa, sum over tau, mean
+    over tau'."""
+    rows = torch.arange(action.shape[0])
+    theta = q[rows, :, action]             # (B, tau)
+    target = _quantile_target(next_n_q[rows, :, next_n_action], reward, done, gamma, nstep, value_gamma)
+    return _quantile_loss(theta, target, quantiles_hats, weight, _smooth_l1, True, kappa, True)

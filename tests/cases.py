@@ -35,6 +35,9 @@ GRAD_INPUTS = {
     'td_lambda': ['value'],
     'upgo': ['target_output'],
     'vtrace': ['target_output', 'value'],
+    'qrdqn': ['q'],
+    'iqn': ['q'],
+    'fqf': ['q'],
 }
 # upstream gradient for each returned loss head (distinct, non-trivial)
 LOSS_MIX = {
@@ -56,6 +59,9 @@ LOSS_MIX = {
     'td_lambda': [1.0],
     'upgo': [1.0],
     'vtrace': [1.0, 0.5, -0.01],
+    'qrdqn': [1.0],
+    'iqn': [1.0],
+    'fqf': [1.0],
 }
 
 
@@ -403,6 +409,37 @@ def vtc_case(seed, T, B, D, weight='none', **params):
     return 'vtc', t, params
 
 
+_QF = ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done')
+QUANTILE_FIELDS = {'qrdqn': _QF + ('tau', 'weight'), 'iqn': _QF + ('replay_quantiles', 'weight'), 'fqf': _QF + ('quantiles_hats', 'weight')}
+
+
+def quantile_case(seed, kind, B, N, n, n_p, nstep, weight='none', value_gamma='none', gamma=0.95, kappa=None, tau='tensor'):
+    """kind 'qrdqn' (q (B, N, n)), 'iqn' (q (n, B, N), replay quantiles (n, B, 1)) or 'fqf' (q (B, n, N), quantile hats (B, n))"""
+    g = _g(seed)
+    t = OrderedDict()
+    shape = {'qrdqn': lambda k: (B, N, k), 'iqn': lambda k: (k, B, N), 'fqf': lambda k: (B, k, N)}[kind]
+    t['q'] = _randn(g, *shape(n))
+    t['next_n_q'] = _randn(g, *shape(n_p))
+    t['action'] = _randint(g, N, B)
+    t['next_n_action'] = _randint(g, N, B)
+    t['reward'] = _rand(g, nstep, B)
+    t['done'] = _bern(g, 0.3, B)
+    if kind == 'qrdqn':
+        mid = (torch.arange(n, dtype=torch.float32) + 0.5) / n  # the QRDQN head's quantile midpoints
+        t['tau'] = {'tensor': mid.view(1, n, 1).repeat(B, 1, 1), 'row': mid.view(1, n, 1), 'scalar': torch.tensor(0.3)}[tau]
+    elif kind == 'iqn':
+        t['replay_quantiles'] = _rand(g, n, B, 1)
+    else:
+        t['quantiles_hats'] = _rand(g, B, n).sort(dim=1).values
+    t['weight'] = None if weight == 'none' else _rand(g, B) + 0.5
+    p = dict(gamma=gamma, nstep=nstep)
+    if value_gamma != 'none':
+        t['value_gamma'] = torch.tensor(0.9) if value_gamma == 'scalar' else _rand(g, B) * 0.5 + 0.5
+    if kappa is not None:
+        p['kappa'] = kappa
+    return kind, t, p
+
+
 def build_cases():
     """Small cases: what the golden fixtures hold and what every implementation is compared on."""
     c = OrderedDict()
@@ -476,6 +513,14 @@ def build_cases():
     c['ppoc_old_1d'] = ppoc_case(113, 17, 1, old_1d=True)
     c['vtc_small'] = vtc_case(116, 4, 8, 16, rho_clip_ratio=1.1)
     c['vtc_w_clips'] = vtc_case(117, 13, 5, 3, weight='tensor', rho_clip_ratio=0.8, c_clip_ratio=1.3, rho_pg_clip_ratio=2.0)
+    # ---- quantile-regression TD heads (tests/test_td.py:249-268, :461-505) -----------------------------------------------------
+    c['qrdqn_basic'] = quantile_case(130, 'qrdqn', 8, 4, 7, 7, 3)
+    c['qrdqn_w_vg'] = quantile_case(131, 'qrdqn', 6, 3, 32, 32, 5, weight='tensor', value_gamma='tensor', tau='row')
+    c['qrdqn_scalar_tau'] = quantile_case(132, 'qrdqn', 4, 3, 3, 3, 1, value_gamma='scalar', tau='scalar')
+    c['iqn_basic'] = quantile_case(133, 'iqn', 8, 4, 8, 6, 3)
+    c['iqn_w_kappa'] = quantile_case(134, 'iqn', 5, 6, 32, 32, 2, weight='tensor', value_gamma='tensor', kappa=0.6)
+    c['fqf_basic'] = quantile_case(135, 'fqf', 8, 4, 8, 8, 3)
+    c['fqf_w_kappa'] = quantile_case(136, 'fqf', 5, 6, 32, 16, 4, weight='tensor', value_gamma='scalar', kappa=1.7)
     c['a2c_basic'] = a2c_case(114, 64, 6)
     c['a2c_w_wide'] = a2c_case(115, 9, 130, weight='tensor')
     # ---- dist_nstep (tests/test_td.py:130-204) ---------------------------------------------------------------
@@ -585,6 +630,13 @@ def run_api(api, op, tensors, params, device='cpu'):
         for k in ('policy_loss', 'value_loss', 'entropy_loss'):
             res['out_' + k] = _np(getattr(loss, k))
         _backward(op, list(loss), t, res)
+        return res
+    if op in ('qrdqn', 'iqn', 'fqf'):
+        data = getattr(api, op + '_nstep_td_data')(*[t[k] for k in QUANTILE_FIELDS[op]])
+        loss, per = getattr(api, op + '_nstep_td_error')(data, value_gamma=t.get('value_gamma'), **p)
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
         return res
     if op == 'ppo_policy':
         data = api.ppo_policy_data(*[t[k] for k in ('logit_new', 'logit_old', 'action', 'adv', 'weight',
@@ -759,6 +811,12 @@ def run_oracle(orc, op, tensors, params):
         for k, v in zip(('policy_loss', 'value_loss', 'entropy_loss'), out):
             res['out_' + k] = _np(v)
         _backward(op, list(out), t, res)
+        return res
+    if op in ('qrdqn', 'iqn', 'fqf'):
+        loss, per = getattr(orc, op + '_nstep_td_error')(*[t[k] for k in QUANTILE_FIELDS[op]], value_gamma=t.get('value_gamma'), **p)
+        res['out_loss'] = _np(loss)
+        res['out_td_error_per_sample'] = _np(per)
+        _backward(op, [loss], t, res)
         return res
     if op == 'ppo_policy':
         out = orc.ppo_policy_error(**t, **p)

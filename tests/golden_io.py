@@ -31,6 +31,9 @@ INPUT_ORDER = {
     'td_lambda': ['value', 'reward', 'weight'],
     'upgo': ['target_output', 'action', 'rhos', 'rewards', 'bootstrap_values', 'mask'],
     'vtrace': ['target_output', 'behaviour_output', 'action', 'value', 'reward', 'weight'],
+    'qrdqn': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'tau', 'weight', 'value_gamma'],
+    'iqn': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'replay_quantiles', 'weight', 'value_gamma'],
+    'fqf': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'quantiles_hats', 'weight', 'value_gamma'],
 }
 
 

@@ -643,6 +643,54 @@ def test_td_heads_exact_for_any_upstream_gradient(op_case):
             assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * max(np.abs(b).max(), 1e-30)), (op_case, scale, use_td)
 
 
+QUANTILE_BIG = {
+    'qrdqn_atari': lambda: cases.quantile_case(160, 'qrdqn', 64, 6, 200, 200, 3, weight='tensor'),   # num_quantiles 200
+    'qrdqn_B600': lambda: cases.quantile_case(161, 'qrdqn', 600, 4, 32, 32, 1, value_gamma='tensor', tau='row'),
+    'iqn_atari': lambda: cases.quantile_case(162, 'iqn', 64, 6, 32, 32, 3, weight='tensor', kappa=1.0),
+    'iqn_ragged': lambda: cases.quantile_case(163, 'iqn', 37, 5, 150, 9, 5, value_gamma='scalar', kappa=0.3),
+    'fqf_atari': lambda: cases.quantile_case(164, 'fqf', 64, 6, 32, 32, 3, weight='tensor'),
+    'fqf_B1030': lambda: cases.quantile_case(165, 'fqf', 1030, 3, 8, 64, 2, value_gamma='tensor', kappa=2.0),
+}
+
+
+@pytest.mark.parametrize('name', sorted(QUANTILE_BIG.keys()))
+def test_quantile_td_heads_match_oracle(name):
+    op, tensors, params = QUANTILE_BIG[name]()
+    want = cases.run_oracle(rl_oracle, op, tensors, params)
+    got = _run(op, tensors, params)
+    cases.compare(got, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('kind', ['qrdqn', 'iqn', 'fqf'])
+def test_quantile_td_exact_for_any_upstream_gradient(kind):
+    """unit-gradient buffer of the forward launch, any other upstream value, gradients through td_error_per_sample, and a
+    repeated backward"""
+    op, t, p = cases.quantile_case(170, kind, 70, 5, 16, 12, 3, weight='tensor', value_gamma='tensor')
+    fields = cases.QUANTILE_FIELDS[op]
+
+    def run(api_kind, scale, use_td):
+        tt = cases.prepare(op, t, DEV if api_kind == 'b200' else 'cpu')
+        if api_kind == 'b200':
+            data = getattr(b2, kind + '_nstep_td_data')(*[tt[k] for k in fields])
+            loss, per = getattr(b2, kind + '_nstep_td_error')(data, value_gamma=tt['value_gamma'], **p)
+        else:
+            loss, per = getattr(rl_oracle, kind + '_nstep_td_error')(*[tt[k] for k in fields], value_gamma=tt['value_gamma'], **p)
+        total = scale * loss
+        if use_td:
+            total = total + (per * torch.linspace(-1, 1, per.numel(), device=per.device)).sum()
+        total.backward(retain_graph=True)
+        g1 = tt['q'].grad.clone()
+        total.backward()
+        return g1, tt['q'].grad.clone()
+
+    for scale, use_td in ((1.0, False), (2.5, False), (1.0, True), (0.0, True)):
+        w1, w2 = run('oracle', scale, use_td)
+        g1, g2 = run('b200', scale, use_td)
+        for a, b in ((g1, w1), (g2, w2)):
+            a, b = a.cpu().numpy(), b.numpy()
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * max(np.abs(b).max(), 1e-30)), (kind, scale, use_td)
+
+
 def test_lambda_returns_backward_matches_autograd_of_the_recurrence():
     """Gradients w.r.t. values, rewards and tensor gammas / lambdas against autograd of an out-of-place restatement
     (the reference's in-place loop supports the first two; MBSAC needs them, mbpolicy/mbsac.py:137,153); UPGO mode too."""

@@ -213,6 +213,9 @@ EXPECTED_CALLS = {
     'td_lambda': ['b200rl_td_lambda_fwd', 'b200rl_scale'],
     'upgo': ['b200rl_lambda_returns', 'b200rl_upgo_head_fwd', 'b200rl_upgo_head_bwd'],
     'vtrace': ['b200rl_vtrace_fused_supported', 'b200rl_vtrace_fwd_grad', 'b200rl_vtrace_fwd_grad'],
+    'qrdqn': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
+    'iqn': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
+    'fqf': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
 }
 
 

@@ -9,7 +9,7 @@
 
 Ported from ding/rl_utils/tests/test_gae.py, test_ppo.py (discrete, continuous, shape_fn), test_a2c.py (discrete), test_td.py (the operators on this
 path: q_nstep, q_nstep_ngu, bdq_nstep, q_1step_compatible, dist_1step, dist_1step_compatible, dist_1step multi agent,
-dist_nstep, dist_nstep multi agent, rescale, rescale_ngu, td_lambda, v_1step, v_1step multi agent, v_nstep, the four shape_fn
+dist_nstep, dist_nstep multi agent, rescale, rescale_ngu, qrdqn_nstep, iqn_nstep, fqf_nstep, td_lambda, v_1step, v_1step multi agent, v_nstep, the four shape_fn
 tests), test_vtrace.py (discrete), test_upgo.py and test_value_rescale.py.  The reference draws unseeded random inputs; the
 ports seed them (so the three implementations see identical bits) and keep every assertion.
 """
@@ -375,6 +375,51 @@ def _bdq_nstep_td_body(api, dev, rec):
 
 def test_bdq_nstep_td(impl):
     _run(_bdq_nstep_td_body, impl)
+
+
+def _quantile_body(kind):
+    """test_td.py:249-268 (qrdqn), :461-481 (iqn), :485-505 (fqf)"""
+
+    def body(api, dev, rec):
+        g = _gen({'qrdqn': 21, 'iqn': 22, 'fqf': 23}[kind])
+        batch_size, action_dim, tau = 4, 3, 3
+        shape = {'qrdqn': (batch_size, action_dim, tau), 'iqn': (tau, batch_size, action_dim),
+                 'fqf': (batch_size, tau, action_dim)}[kind]
+        next_q = torch.randn(*shape, generator=g).to(dev)
+        done = torch.randn(batch_size, generator=g).to(dev)
+        action = torch.randint(0, action_dim, size=(batch_size, ), generator=g).to(dev)
+        next_action = torch.randint(0, action_dim, size=(batch_size, ), generator=g).to(dev)
+        data_t = getattr(api, kind + '_nstep_td_data')
+        fn = getattr(api, kind + '_nstep_td_error')
+        for nstep in range(1, 10):
+            q = torch.randn(*shape, generator=g).to(dev).requires_grad_(True)
+            if kind == 'qrdqn':
+                extra = tau  # a python int, as in the reference's test
+            elif kind == 'iqn':
+                extra = torch.randn([tau, batch_size, 1], generator=g).to(dev)
+            else:
+                extra = torch.randn([batch_size, tau], generator=g).to(dev)
+            reward = torch.rand(nstep, batch_size, generator=g).to(dev)
+            data = data_t(q, next_q, action, next_action, reward, done, extra, None)
+            loss, td_error_per_sample = fn(data, 0.95, nstep=nstep)
+            assert td_error_per_sample.shape == (batch_size, )
+            assert loss.shape == ()
+            assert q.grad is None
+            loss.backward()
+            assert isinstance(q.grad, torch.Tensor)
+            rec.put('loss_%d' % nstep, loss)
+            rec.put('td_%d' % nstep, td_error_per_sample)
+            rec.put('grad_%d' % nstep, q.grad)
+            loss, td_error_per_sample = fn(data, 0.95, nstep=nstep, value_gamma=torch.tensor(0.9).to(dev))
+            assert td_error_per_sample.shape == (batch_size, )
+            rec.put('vg_loss_%d' % nstep, loss)
+
+    return body
+
+
+@pytest.mark.parametrize('kind', ['qrdqn', 'iqn', 'fqf'])
+def test_quantile_nstep_td(impl, kind):
+    _run(_quantile_body(kind), impl)
 
 
 def _q_nstep_td_ngu_body(api, dev, rec):
