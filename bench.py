@@ -239,10 +239,11 @@ class DeviceStepD:
 class WorkloadP(WorkloadD):
     """Config D as PPOPolicy._forward_learn really composes it (ding/policy/ppo.py:274-306): value-norm scale -> gae ->
     unnormalized return / stored value / return_ + running statistics -> (adv - mean) / (std + 1e-8) -> ppo_error, backward.
-    gae_returns 36 B (20 in + 16 out) + adv_stats 4 B + ppo forward-with-gradient 104 B per transition."""
+    gae_returns 36 B (20 in + 16 out; the advantage statistics come out of the same pass) + ppo forward-with-gradient 104 B per
+    transition."""
     key = 'P'
-    alg_bytes = {'gae_returns': 36, 'adv_stats': 4, 'ppo_fwd_grad': 104, 'ppo_bwd_check': 0}
-    step_bytes_per_unit = 144
+    alg_bytes = {'gae_returns': 36, 'ppo_fwd_grad': 104, 'ppo_bwd_check': 0}
+    step_bytes_per_unit = 140
     STD = 1.7320508
 
     def __init__(self, B=B_COLS, T=T_LEN, N=N_ACT):
@@ -286,7 +287,7 @@ class WorkloadP(WorkloadD):
                            self.STD)
         loss, info = b2.ppo_error_adv_norm(
             b2.ppo_data(ln, d['logit_old'], d['action'], vn, g.value.view(-1), g.adv.view(-1), g.return_.view(-1), None, None),
-            CLIP, True, None)
+            CLIP, True, None, adv_stats=g.adv_stats)
         total = loss.policy_loss + W_VALUE * loss.value_loss + W_ENTROPY * loss.entropy_loss
         total.backward()
         return total
@@ -311,21 +312,14 @@ class DeviceStepP(DeviceStepD):
         rc = o.lib().b200rl_gae_returns(
             _p(o, b['value']), _p(o, b['next_value']), _p(o, b['reward']), _p(o, b['done']), _p(o, b['traj_flag']), self.wl.T,
             self.wl.B, 1, GAMMA, LAMBDA, 0, self.wl.STD, _p(o, self.adv), _p(o, self.unnorm), _p(o, self.vout), _p(o, self.rout),
-            _p(o, self.ret_stats), _p(o, self.ws), self.ws.numel() * 4, o.stream_ptr())
-        assert rc == 0, rc
-
-    def adv_stats_k(self):
-        o = self.ops
-        rc = o.lib().b200rl_adv_stats(_p(o, self.adv), self.S, _p(o, self.adv_stats), _p(o, self.ws), self.ws.numel() * 4,
-                                      o.stream_ptr())
+            _p(o, self.ret_stats), _p(o, self.adv_stats), _p(o, self.ws), self.ws.numel() * 4, o.stream_ptr())
         assert rc == 0, rc
 
     def kernels(self):
-        return [('gae_returns', self.gae_returns), ('adv_stats', self.adv_stats_k), ('ppo_fwd_grad', self.ppo_fwd_grad),
-                ('ppo_bwd_check', self.ppo_bwd_check)]
+        return [('gae_returns', self.gae_returns), ('ppo_fwd_grad', self.ppo_fwd_grad), ('ppo_bwd_check', self.ppo_bwd_check)]
 
     def launches_per_step(self):
-        return 6  # gae scan, returns + statistics, adv_stats, ppo forward-with-gradient, finalize_sums, backward check
+        return 5  # gae scan, returns + both statistics, ppo forward-with-gradient, finalize_sums, backward check
 
     def check(self, host_batch):
         from oracle import rl_oracle

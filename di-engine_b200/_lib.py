@@ -22,7 +22,7 @@ PROTOTYPES = {
     "b200rl_built_for_sm": [],
     "b200rl_workspace_bytes": [],
     "b200rl_gae": [P, P, P, P, P, P, LL, LL, LL, D, D, I, P],
-    "b200rl_gae_returns": [P, P, P, P, P, LL, LL, LL, D, D, I, D, P, P, P, P, P, P, c_size_t, P],
+    "b200rl_gae_returns": [P, P, P, P, P, LL, LL, LL, D, D, I, D, P, P, P, P, P, P, P, c_size_t, P],
     "b200rl_adv_stats": [P, LL, P, P, c_size_t, P],
     "b200rl_normalize": [P, P, LL, P, P],
     "b200rl_impala_mask": [P, P, P, LL, LL, P, P, P, P],

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
                 if (row >= jmin && o < Pv) cpa16(dst + p * 16, g + row * rstride + o * 16);
             }
         };
+        const bool fast_rows = f.loader != 1;  // B200RL_COL_LOADER=1: the flat loop everywhere (A/B experiments)
         CwItem it = first;
         int s = 0, ph = 0;
         for (int j = 0; item_valid(it); ++j) {
@@ -149,14 +150,29 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
             const int jmin = t0 < 0 ? (int)-t0 : 0;
             const int W = (int)((B - c0) < CW_TC ? (B - c0) : CW_TC);
             unsigned char* st = smem + s * L.stage_bytes;
-            rows_of(st, a.logit_new, t0, c0, N * 4, jmin, W);
-            rows_of(st + L.off_old, a.logit_old, t0, c0, N * 4, jmin, W);
-            if (has_pre) rows_of(st + L.off_pre, a.logit_pre, t0, c0, N * 4, jmin, W);
-            rows_of(st + L.off_act, a.action, t0, c0, 8, jmin, W);
-            rows_of(st + L.off_vn, a.value_new, t0, c0, 4, jmin, W);
-            rows_of(st + L.off_vo, a.value_old, t0, c0, 4, jmin, W);
-            rows_of(st + L.off_ret, a.ret, t0, c0, 4, jmin, W);
-            if (has_w) rows_of(st + L.off_w, a.weight, t0, c0, 4, jmin, W);
+            if (jmin == 0 && W == CW_TC && fast_rows) {
+                // full chunk of a full tile: a row segment is TC * esz / 16 = esz pieces (4 N | 8 | 4)
+                const uint32_t sb = smem_u32(st);
+                const long long e0 = t0 * B + c0;
+                const long long ls = B * N * 4;
+                warp_copy_rows<4, CW_R, NC>(sb, a.logit_new + e0 * N, ls, N, lane);
+                warp_copy_rows<4, CW_R, NC>(sb + L.off_old, a.logit_old + e0 * N, ls, N, lane);
+                if (has_pre) warp_copy_rows<4, CW_R, NC>(sb + L.off_pre, a.logit_pre + e0 * N, ls, N, lane);
+                warp_copy_rows<4, CW_R, 2>(sb + L.off_act, a.action + e0, B * 8, 2, lane);
+                warp_copy_rows<4, CW_R, 1>(sb + L.off_vn, a.value_new + e0, B * 4, 1, lane);
+                warp_copy_rows<4, CW_R, 1>(sb + L.off_vo, a.value_old + e0, B * 4, 1, lane);
+                warp_copy_rows<4, CW_R, 1>(sb + L.off_ret, a.ret + e0, B * 4, 1, lane);
+                if (has_w) warp_copy_rows<4, CW_R, 1>(sb + L.off_w, a.weight + e0, B * 4, 1, lane);
+            } else {
+                rows_of(st, a.logit_new, t0, c0, N * 4, jmin, W);
+                rows_of(st + L.off_old, a.logit_old, t0, c0, N * 4, jmin, W);
+                if (has_pre) rows_of(st + L.off_pre, a.logit_pre, t0, c0, N * 4, jmin, W);
+                rows_of(st + L.off_act, a.action, t0, c0, 8, jmin, W);
+                rows_of(st + L.off_vn, a.value_new, t0, c0, 4, jmin, W);
+                rows_of(st + L.off_vo, a.value_old, t0, c0, 4, jmin, W);
+                rows_of(st + L.off_ret, a.ret, t0, c0, 4, jmin, W);
+                if (has_w) rows_of(st + L.off_w, a.weight, t0, c0, 4, jmin, W);
+            }
             cpa_mbar_arrive(&full[s]);
             if (lane == 0 && j < 6) CW_TRACE(21 + 2 * j);
             if (++s == S) { s = 0; ph ^= 1; }
@@ -305,9 +321,9 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
             const long long c0 = it.tile * CW_TC;
             const long long t = T - (it.q + 1) * CW_R + jj;
             unsigned char* st = smem + s * L.stage_bytes;
-            mbar_wait(&full[s], (uint32_t)ph);
+            if (f.wait_ns) mbar_wait_hint(&full[s], (uint32_t)ph, (uint32_t)f.wait_ns); else mbar_wait(&full[s], (uint32_t)ph);
             if (tid == 0 && j < 6) CW_TRACE(1 + 3 * j);
-            mbar_wait(&adv_ready[s], (uint32_t)ph);
+            if (f.wait_ns) mbar_wait_hint(&adv_ready[s], (uint32_t)ph, (uint32_t)f.wait_ns); else mbar_wait(&adv_ready[s], (uint32_t)ph);
             if (tid == 0 && j < 6) CW_TRACE(2 + 3 * j);
             if (t >= 0 && c0 + c < B) {
                 const long long g = t * B + c0 + c;  // global transition index

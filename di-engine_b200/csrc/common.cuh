@@ -426,6 +426,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// same with a suspend-time hint: the warp may stay suspended up to `ns` nanoseconds per attempt instead of re-issuing
+// try_wait as fast as the default time-out lets it (spinning warps take issue slots from the loader / scanner warps)
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITH_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra WAITH_DONE;\n"
+        "bra WAITH_LOOP;\n"
+        "WAITH_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(ns)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
@@ -458,6 +473,27 @@ __device__ __forceinline__ void cpa16(void* smem_dst, const void* gmem_src) {
 // same with the shared-memory address already converted (loops that step it by a constant)
 __device__ __forceinline__ void cpa16_s(uint32_t smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+// Loader-warp copy of R row segments of P = PG * G 16-byte pieces each: `rstride` bytes apart in global memory, packed in shared
+// memory.  lane -> (piece o of every G-piece group, row r of every 32/G-row pass): ONE address computation per lane, every copy
+// at an immediate offset from it -- the flat p -> (row, piece) loop it replaces spent ~35 instructions per copy on the division
+// and the 64-bit row * stride product, and the loader warp is the longest serial chain of a chunk.
+// Requires full rows (no ragged tile / chunk): the callers keep the flat loop for those.
+template <int G, int R, int PG>  // PG = 0: runtime `pg_rt`
+__device__ __forceinline__ void warp_copy_rows(uint32_t dst, const void* src, long long rstride, int pg_rt, int lane) {
+    constexpr int RP = 32 / G;
+    static_assert(R % RP == 0, "rows per pass");
+    const int o = lane & (G - 1), r = lane / G;
+    const int pg = PG ? PG : pg_rt;
+    const unsigned char* s = reinterpret_cast<const unsigned char*>(src) + r * rstride + o * 16;
+    uint32_t d = dst + (uint32_t)(r * pg * G + o) * 16u;
+#pragma unroll
+    for (int pass = 0; pass < R / RP; ++pass) {
+#pragma unroll
+        for (int k = 0; k < pg; ++k) cpa16_s(d + (uint32_t)k * (G * 16u), s + (size_t)k * (G * 16));
+        s += RP * rstride;
+        d += (uint32_t)(RP * pg * G) * 16u;
+    }
 }
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

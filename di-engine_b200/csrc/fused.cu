@@ -339,6 +339,20 @@ static void fill_fused(FusedArgs& f, const float* value, float* next_value, cons
         }
         f.trace = tr;
     }
+    {
+        static int ld = -1;
+        if (ld < 0) {
+            const char* e = getenv("B200RL_COL_LOADER");  // 1 = flat copy loop in the loader warp (the round-1 loader)
+            ld = e ? atoi(e) : 0;
+        }
+        f.loader = ld;
+        static int wn = -1;
+        if (wn < 0) {
+            const char* e = getenv("B200RL_COL_WAIT_NS");
+            wn = e ? atoi(e) : 0;
+        }
+        f.wait_ns = wn;
+    }
 }
 
 extern "C" int b200rl_gae_ppo_supported(const float* value, const float* next_value, const float* reward,

@@ -59,7 +59,17 @@ struct RetArgs {
     float* value_out;   // nullable: (value*s)/s
     float* ret_out;     // nullable: unnormalized / s
     float* stats;       // nullable: {mean, population variance, count} of the unnormalized returns (RunningMeanStd.update input)
+    float* adv_stats;   // nullable: {mean, std(unbiased) + 1e-8} of adv (ppo.py:304-306 when the whole batch is one minibatch)
 };
+
+// {mean, torch.std (unbiased) + 1e-8} from the fp64 sums of x and x^2
+__device__ __forceinline__ void write_adv_stats(float* out, double s1, double s2, double nn) {
+    const double m = s1 / nn;
+    const double var = (s2 - s1 * m) / (nn - 1.0);  // n == 1 -> nan, as torch.std
+    const double sd = var != var ? var : sqrt(fmax(var, 0.0));
+    out[0] = (float)m;
+    out[1] = fadd((float)sd, 1e-8f);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // 1-D GAE with segment-parallel scan (single CTA, T <= GS_MAX_T)
@@ -171,10 +181,12 @@ __global__ void __launch_bounds__(GS_NT) gae_seq_kernel(const float* __restrict_
     }
     __syncthreads();
     // ---- phase 4: write-out (+ returns, value-norm, statistics)
-    double acc[2] = {0.0, 0.0};
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int t = tid; t < T; t += GS_NT) {
         const float a = s_d[t];
         adv[t] = a;
+        acc[2] += (double)a;
+        acc[3] += (double)a * (double)a;
         if (ra.ret_unnorm || ra.value_out || ra.ret_out || ra.stats) {
             float v = value[t];
             if (vs != 0.f) v = fmul(v, vs);
@@ -186,14 +198,17 @@ __global__ void __launch_bounds__(GS_NT) gae_seq_kernel(const float* __restrict_
             acc[1] += (double)r * (double)r;
         }
     }
-    if (ra.stats) {
-        double tot[2];
-        block_sum_d<2, GS_NT>(acc, tot);
+    if (ra.stats || ra.adv_stats) {
+        double tot[4];
+        block_sum_d<4, GS_NT>(acc, tot);
         if (tid == 0) {
             const double n = (double)T, m = tot[0] / n;
-            ra.stats[0] = (float)m;
-            ra.stats[1] = (float)fmax(tot[1] / n - m * m, 0.0);  // np.var: population variance
-            ra.stats[2] = (float)n;
+            if (ra.stats) {
+                ra.stats[0] = (float)m;
+                ra.stats[1] = (float)fmax(tot[1] / n - m * m, 0.0);  // np.var: population variance
+                ra.stats[2] = (float)n;
+            }
+            if (ra.adv_stats) write_adv_stats(ra.adv_stats, tot[2], tot[3], n);
         }
     }
 }
@@ -203,40 +218,70 @@ __global__ void __launch_bounds__(GS_NT) gae_seq_kernel(const float* __restrict_
 // The two statistics are reduced with the one-round-trip scheme of grid_sum_fx on scaled integers (sum of r and of r^2 as
 // doubles); the CTA that completes the second sum joins them through one more atomic.
 // ---------------------------------------------------------------------------------------------------------------
+template <bool VEC>
 __global__ void __launch_bounds__(256) returns_kernel(const float* __restrict__ value, const float* __restrict__ adv,
                                                       long long n, RetArgs ra, double* __restrict__ ws_d,
                                                       unsigned int* __restrict__ ws_join) {
     pdl_prologue();
     const float vs = ra.vscale;
-    double acc[2] = {0.0, 0.0};
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-        float v = value[i];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    auto one = [&](float v, float a, float& ru, float& vo, float& ro) {
         if (vs != 0.f) v = fmul(v, vs);
-        const float r = fadd(v, adv[i]);
-        if (ra.ret_unnorm) ra.ret_unnorm[i] = r;
-        if (ra.value_out) ra.value_out[i] = vs != 0.f ? __fdiv_rn(v, vs) : v;
-        if (ra.ret_out) ra.ret_out[i] = vs != 0.f ? __fdiv_rn(r, vs) : r;
+        const float r = fadd(v, a);
+        ru = r;
+        vo = vs != 0.f ? __fdiv_rn(v, vs) : v;
+        ro = vs != 0.f ? __fdiv_rn(r, vs) : r;
         acc[0] += (double)r;
         acc[1] += (double)r * (double)r;
+        acc[2] += (double)a;
+        acc[3] += (double)a * (double)a;
+    };
+    if (VEC) {  // n % 4 == 0, 16-byte aligned tensors
+        const long long n4 = n >> 2;
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+            const float4 v = reinterpret_cast<const float4*>(value)[i], a = reinterpret_cast<const float4*>(adv)[i];
+            float4 ru, vo, ro;
+            one(v.x, a.x, ru.x, vo.x, ro.x);
+            one(v.y, a.y, ru.y, vo.y, ro.y);
+            one(v.z, a.z, ru.z, vo.z, ro.z);
+            one(v.w, a.w, ru.w, vo.w, ro.w);
+            if (ra.ret_unnorm) reinterpret_cast<float4*>(ra.ret_unnorm)[i] = ru;
+            if (ra.value_out) reinterpret_cast<float4*>(ra.value_out)[i] = vo;
+            if (ra.ret_out) reinterpret_cast<float4*>(ra.ret_out)[i] = ro;
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+            float ru, vo, ro;
+            one(value[i], adv[i], ru, vo, ro);
+            if (ra.ret_unnorm) ra.ret_unnorm[i] = ru;
+            if (ra.value_out) ra.value_out[i] = vo;
+            if (ra.ret_out) ra.ret_out[i] = ro;
+        }
     }
-    if (!ra.stats) return;
-    double tot[2];
-    block_sum_d<2, 256>(acc, tot);
+    if (!ra.stats && !ra.adv_stats) return;
+    double tot[4];
+    block_sum_d<4, 256>(acc, tot);
     if (threadIdx.x == 0) {
         // fp64 atomics: order-dependent in the last bits of a double only (the results are rounded to fp32 afterwards)
-        atomicAdd(ws_d, tot[0]);
-        atomicAdd(ws_d + 1, tot[1]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(ws_d + k, tot[k]);
         __threadfence();
         const unsigned int t = atomicAdd(ws_join, 1u);
         if (t == gridDim.x - 1) {
             __threadfence();
-            const double s1 = atomicAdd(ws_d, 0.0), s2 = atomicAdd(ws_d + 1, 0.0);
-            const double nn = (double)n, m = s1 / nn;
-            ra.stats[0] = (float)m;
-            ra.stats[1] = (float)fmax(s2 / nn - m * m, 0.0);
-            ra.stats[2] = (float)nn;
-            ws_d[0] = 0.0;
-            ws_d[1] = 0.0;
+            double s[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                s[k] = atomicAdd(ws_d + k, 0.0);
+                ws_d[k] = 0.0;
+            }
+            const double nn = (double)n, m = s[0] / nn;
+            if (ra.stats) {
+                ra.stats[0] = (float)m;
+                ra.stats[1] = (float)fmax(s[1] / nn - m * m, 0.0);
+                ra.stats[2] = (float)nn;
+            }
+            if (ra.adv_stats) write_adv_stats(ra.adv_stats, s[2], s[3], nn);
             *ws_join = 0u;
         }
     }
@@ -270,11 +315,7 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict_
         ws_d[1] = 0.0;
         *ws_join = 0u;
     }
-    const double nn = (double)n, m = s1 / nn;
-    const double var = (s2 - s1 * m) / (nn - 1.0);  // unbiased; n == 1 -> nan, as torch.std
-    const double sd = var != var ? var : sqrt(fmax(var, 0.0));
-    out[0] = (float)m;
-    out[1] = fadd((float)sd, 1e-8f);
+    write_adv_stats(out, s1, s2, (double)n);
 }
 
 __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, const float* __restrict__ stats,
@@ -345,13 +386,14 @@ extern "C" int b200rl_gae_returns(const float* value, float* next_value, const f
                                   const float* traj_flag, long long T, long long C, long long A, double gamma,
                                   double lambda_, int mask_next_value_inplace, double value_scale, float* adv,
                                   float* unnormalized_return, float* value_out, float* return_out, float* stats3,
-                                  float* workspace, size_t workspace_bytes, void* stream) {
+                                  float* adv_stats2, float* workspace, size_t workspace_bytes, void* stream) {
     if (T < 1 || C < 1 || A < 1 || !value || !next_value || !reward || !adv || !workspace ||
         workspace_bytes < WS_MIN_BYTES || value_scale < 0.0)
         return B200RL_ERR_ARG;
     RetArgs ra{};
     ra.vscale = (float)value_scale;
     ra.ret_unnorm = unnormalized_return; ra.value_out = value_out; ra.ret_out = return_out; ra.stats = stats3;
+    ra.adv_stats = adv_stats2;
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 1 && T <= GS_MAX_T) {  // the real PPO learner's call: one sequence, everything in one launch
         const size_t smem = (size_t)2 * T * sizeof(float);
@@ -369,12 +411,18 @@ extern "C" int b200rl_gae_returns(const float* value, float* next_value, const f
     int rc = gae_scan(value, next_value, reward, done, traj_flag, adv, T, C, A, gamma, lambda_, mask_next_value_inplace,
                       (float)value_scale, stream);
     if (rc != 0) return rc;
-    if (unnormalized_return || value_out || return_out || stats3) {
+    if (unnormalized_return || value_out || return_out || stats3 || adv_stats2) {
         const long long n = T * C;
-        long long grid = div_up(n, 256 * 8);
-        if (grid > 148 * 4) grid = 148 * 4;
-        (void)launch_k(returns_kernel, (int)grid, 256, 0, st, value, (const float*)adv, n, ra, ws_doubles(workspace),
-                       ws_joins(workspace));
+        const bool vec = (n % 4 == 0) && aligned16(value) && aligned16(adv) && (!unnormalized_return || aligned16(unnormalized_return)) &&
+                         (!value_out || aligned16(value_out)) && (!return_out || aligned16(return_out));
+        long long grid = div_up(n, 256 * (vec ? 8 : 4));
+        if (grid > 148 * 8) grid = 148 * 8;
+        if (vec)
+            (void)launch_k(returns_kernel<true>, (int)grid, 256, 0, st, value, (const float*)adv, n, ra, ws_doubles(workspace),
+                           ws_joins(workspace));
+        else
+            (void)launch_k(returns_kernel<false>, (int)grid, 256, 0, st, value, (const float*)adv, n, ra, ws_doubles(workspace),
+                           ws_joins(workspace));
     }
     return (int)cudaGetLastError();
 }

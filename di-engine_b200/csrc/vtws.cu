@@ -167,11 +167,22 @@ __global__ void __launch_bounds__(VW_THREADS, 2) vtrace_ws_kernel(VtFusedArgs a,
             const int jmin = t0 < 0 ? (int)-t0 : 0;
             const int W = (int)((B - c0) < VW_TC ? (B - c0) : VW_TC);
             unsigned char* st = smem + s * stage_bytes;
-            if (wid == VW_CW || VW_LW == 1) rows_of(st, a.target, t0, c0, N * 4, jmin, W);
-            if (wid != VW_CW || VW_LW == 1) {
-                rows_of(st + off_beh, a.behaviour, t0, c0, N * 4, jmin, W);
-                rows_of(st + off_act, a.action, t0, c0, 8, jmin, W);
-                if (has_w) rows_of(st + off_w, a.weight, t0, c0, 4, jmin, W);
+            if (VW_LW == 1 && jmin == 0 && W == VW_TC) {
+                // full chunk of a full tile: lane-owns-a-piece-column copies (common.cuh warp_copy_rows); a row segment is
+                // TC * esz / 16 pieces = (TC / 4) * (N | 2 | 1) for logits | actions | weights
+                const uint32_t sb = smem_u32(st);
+                const long long e0 = t0 * B + c0;
+                warp_copy_rows<VW_TC / 4, VW_R, NC>(sb, a.target + e0 * N, B * N * 4, N, lane);
+                warp_copy_rows<VW_TC / 4, VW_R, NC>(sb + off_beh, a.behaviour + e0 * N, B * N * 4, N, lane);
+                warp_copy_rows<VW_TC / 4, VW_R, 2>(sb + off_act, a.action + e0, B * 8, 2, lane);
+                if (has_w) warp_copy_rows<VW_TC / 4, VW_R, 1>(sb + off_w, a.weight + e0, B * 4, 1, lane);
+            } else {
+                if (wid == VW_CW || VW_LW == 1) rows_of(st, a.target, t0, c0, N * 4, jmin, W);
+                if (wid != VW_CW || VW_LW == 1) {
+                    rows_of(st + off_beh, a.behaviour, t0, c0, N * 4, jmin, W);
+                    rows_of(st + off_act, a.action, t0, c0, 8, jmin, W);
+                    if (has_w) rows_of(st + off_w, a.weight, t0, c0, 4, jmin, W);
+                }
             }
             cpa_mbar_arrive(&full[s]);
             if (tid == VW_CT && j < 8) VW_TRACE(49 + 2 * j);

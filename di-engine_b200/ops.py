@@ -149,9 +149,9 @@ def gae_(value, next_value, reward, done, traj_flag, gamma, lambda_, agents, mas
 
 
 def gae_returns_(value, next_value, reward, done, traj_flag, gamma, lambda_, agents, vscale, want_returns, want_stats,
-                 mask_inplace=False):
+                 mask_inplace=False, want_adv_stats=False):
     """gae + the pieces around it in PPOPolicy._forward_learn (ding/policy/ppo.py:274-297) -- csrc/policy.cu.
-    -> (adv, unnormalized_return, value_out, return_out, stats3) (None where not requested)."""
+    -> (adv, unnormalized_return, value_out, return_out, stats3[, adv_stats2]) (None where not requested)."""
     T = value.shape[0]
     C = value.numel() // T
     dev = value.device
@@ -160,14 +160,17 @@ def gae_returns_(value, next_value, reward, done, traj_flag, gamma, lambda_, age
     vout = torch.empty_like(value) if (want_returns and vscale != 0.0) else None
     rout = torch.empty_like(value) if (want_returns and vscale != 0.0) else None
     stats = torch.empty(3, dtype=torch.float32, device=dev) if want_stats else None
+    astats = torch.empty(2, dtype=torch.float32, device=dev) if want_adv_stats else None
     with on_device(dev):
         ws = workspace(dev)
         rc = lib().b200rl_gae_returns(
             ptr(value), ptr(next_value), ptr(reward), ptr(done), ptr(traj_flag), T, C, agents, float(gamma), float(lambda_),
-            1 if mask_inplace else 0, float(vscale), ptr(adv), ptr(unnorm), ptr(vout), ptr(rout), ptr(stats), ptr(ws),
-            ws.numel() * 4, stream_ptr()
+            1 if mask_inplace else 0, float(vscale), ptr(adv), ptr(unnorm), ptr(vout), ptr(rout), ptr(stats), ptr(astats),
+            ptr(ws), ws.numel() * 4, stream_ptr()
         )
     _lib.check(rc, 'b200rl_gae_returns')
+    if want_adv_stats:
+        return adv, unnorm, vout, rout, stats, astats
     return adv, unnorm, vout, rout, stats
 
 

@@ -6,7 +6,7 @@ import torch
 from .. import ops
 
 gae_data = namedtuple('gae_data', ['value', 'next_value', 'reward', 'done', 'traj_flag'])
-gae_returns_out = namedtuple('gae_returns_out', ['adv', 'value', 'return_', 'unnormalized_return', 'return_stats'])
+gae_returns_out = namedtuple('gae_returns_out', ['adv', 'value', 'return_', 'unnormalized_return', 'return_stats', 'adv_stats'])
 
 
 def shape_fn_gae(args, kwargs):
@@ -73,7 +73,9 @@ def gae_returns(data: namedtuple, gamma: float = 0.99, lambda_: float = 0.97, va
     ``value_norm_std`` None (value_norm off) or the running std.  The inputs are NOT modified.  Returns
     ``gae_returns_out(adv, value, return_, unnormalized_return, return_stats)``; ``return_stats`` = (mean, population variance,
     count) of the unnormalized returns: what ``RunningMeanStd.update`` (ding/utils/default_helper.py:547-567) computes from the
-    array the reference first copies to the host.
+    array the reference first copies to the host; ``adv_stats`` = (adv.mean(), adv.std() + 1e-8) of the whole batch, computed
+    in the same pass: hand it to ``ppo_error_adv_norm(..., adv_stats=...)`` when the batch is ONE minibatch
+    (policy/ppo.py:304-306 normalises per minibatch: those take their own statistics, ``ops.adv_stats_``).
     """
     value, next_value, reward, done, traj_flag = data
     dev = ops.compute_device(value, next_value, reward)
@@ -87,8 +89,9 @@ def gae_returns(data: namedtuple, gamma: float = 0.99, lambda_: float = 0.97, va
     d = ops.f32c(ops.to_device(done.detach(), dev), 'done') if done is not None else None
     tf = ops.f32c(ops.to_device(traj_flag.detach(), dev), 'traj_flag') if traj_flag is not None else None
     vs = 0.0 if value_norm_std is None else float(value_norm_std)
-    adv, unnorm, vout, rout, stats = ops.gae_returns_(v, nv, r, d, tf, gamma, lambda_, 1, vs, True, True)
+    adv, unnorm, vout, rout, stats, astats = ops.gae_returns_(v, nv, r, d, tf, gamma, lambda_, 1, vs, True, True,
+                                                              want_adv_stats=True)
     if vs == 0.0:
         vout, rout = v, unnorm
-    out = gae_returns_out(adv, vout, rout, unnorm, stats)
+    out = gae_returns_out(adv, vout, rout, unnorm, stats, astats)
     return gae_returns_out(*[t.cpu() for t in out]) if host_out else out

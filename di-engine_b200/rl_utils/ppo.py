@@ -67,18 +67,20 @@ def ppo_error_adv_norm(
         clip_ratio: float = 0.2,
         use_value_clip: bool = True,
         dual_clip: Optional[float] = None,
-        kl_type: str = 'k1'
+        kl_type: str = 'k1',
+        adv_stats: Optional[torch.Tensor] = None
 ) -> Tuple[namedtuple, namedtuple]:
     """
     ``ppo_error`` evaluated on ``(adv - adv.mean()) / (adv.std() + 1e-8)`` -- the normalisation PPOPolicy applies to every
     train batch right before the call (ding/policy/ppo.py:304-306; not a reference function, exactly those lines + ppo_error).
-    One small statistics launch; the normalisation itself happens on load inside the loss kernels (no normalised copy of
-    ``adv`` is written).  Same arguments and results as ``ppo_error``.
+    One small statistics launch -- none when ``adv_stats`` (two device floats {mean, std + 1e-8}, e.g. ``gae_returns(...).adv_stats``
+    for a batch that is one minibatch) is handed in; the normalisation itself happens on load inside the loss kernels (no
+    normalised copy of ``adv`` is written).  Same arguments and results as ``ppo_error``.
     """
-    return _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, 'ppo', True)
+    return _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, 'ppo', True, adv_stats)
 
 
-def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind, adv_norm=False):
+def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind, adv_norm=False, adv_stats=None):
     assert dual_clip is None or dual_clip > 1.0, "dual_clip value must be greater than 1.0, but get value: {}".format(
         dual_clip
     )
@@ -119,7 +121,14 @@ def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind,
         if w.numel() != S:
             w = w.expand_as(ad).contiguous()
     act = ops.i64c(ops.to_device(action, dev))
-    stats = ops.adv_stats_(ad) if adv_norm else None
+    stats = None
+    if adv_norm:
+        if adv_stats is None:
+            stats = ops.adv_stats_(ad)
+        else:
+            stats = ops.f32c(ops.to_device(adv_stats.detach(), ad.device), 'adv_stats').reshape(-1)
+            if stats.numel() != 2:
+                raise ValueError("adv_stats must hold two floats {mean, std + 1e-8}")
     p, v, e, k, out = ops.PPOFunction.apply(
         ln, vn, lo, act, vo, ad, rt, w, lp, S, G, N, float(clip_ratio), 1 if use_value_clip else 0,
         float(dual_clip) if dual_clip is not None else 0.0, _KL_TYPES.get(kl_type, 1), _hint_kind, stats

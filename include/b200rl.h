@@ -58,6 +58,8 @@ B200RL_API int b200rl_gae(const float* value, float* next_value, const float* re
  * adv = gae(value*s, next_value*s, reward, done, traj_flag); unnormalized_return = value*s + adv; value_out = (value*s)/s;
  * return_out = unnormalized_return / s; stats3 = {mean, population variance, count} of unnormalized_return -- the three
  * numbers RunningMeanStd.update (ding/utils/default_helper.py:547-567) needs, instead of the reference's full D2H copy.
+ * adv_stats2 = {mean, std(unbiased) + 1e-8} of adv in the same pass -- the `adv_stats` operand of the ppo entry points when
+ * the whole batch is one minibatch (ding/policy/ppo.py:304-306); minibatches take theirs from b200rl_adv_stats.
  * value_scale = s = RunningMeanStd.std (0: value_norm off, s = 1 and no scaling).  Every output but adv is nullable.
  * C == 1 (the real learner: ONE sequence of n_sample steps, T <= 24576): one launch of one CTA; the sequence is cut at every
  * traj_flag == 1 and each segment is scanned by its own lane -- bit-identical to the reference loop.  (T, C > 1): the
@@ -65,8 +67,8 @@ B200RL_API int b200rl_gae(const float* value, float* next_value, const float* re
 B200RL_API int b200rl_gae_returns(const float* value, float* next_value, const float* reward, const float* done,
                        const float* traj_flag, long long T, long long C, long long A, double gamma, double lambda_,
                        int mask_next_value_inplace, double value_scale, float* adv, float* unnormalized_return,
-                       float* value_out, float* return_out, float* stats3, float* workspace, size_t workspace_bytes,
-                       void* stream);
+                       float* value_out, float* return_out, float* stats3, float* adv_stats2, float* workspace,
+                       size_t workspace_bytes, void* stream);
 /* {mean, std(unbiased) + 1e-8} of x[0..n) as two device floats (ding/policy/ppo.py:304-306: adv.mean(), adv.std() + 1e-8),
  * one launch; pass the result as `adv_stats` to the ppo entry points, or materialise (x - mean) / (std + 1e-8): */
 B200RL_API int b200rl_adv_stats(const float* x, long long n, float* stats2, float* workspace, size_t workspace_bytes,

@@ -811,6 +811,10 @@ def test_gae_returns_matches_policy_lines(case):
         assert torch.equal(x.cpu(), y), 'inputs must not be modified'
     st = got.return_stats.cpu().numpy().astype(np.float64)
     assert np.allclose(st, np.array(want[4]), rtol=2e-6, atol=1e-6), (st, want[4])
+    if want[0].numel() > 1:  # adv.mean(), adv.std() + 1e-8 out of the same pass (policy/ppo.py:304-306 for a one-minibatch batch)
+        a64 = want[0].double()
+        ast = got.adv_stats.cpu().numpy().astype(np.float64)
+        assert np.allclose(ast, [a64.mean().item(), a64.std().item() + 1e-8], rtol=2e-6, atol=1e-6), ast
     # plain gae on one sequence takes the same segment-parallel kernel: identical advantage, in-place mask as the reference
     dev2 = [x.clone().to(DEV) for x in data]
     if std is None:
@@ -843,6 +847,11 @@ def test_ppo_error_adv_norm_matches_policy_lines(S, N):
         assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max()), k
     na = b2.normalize_advantage(td['adv'])
     assert torch.allclose(na.cpu(), tt['adv'], rtol=1e-6, atol=1e-6)
+    # statistics handed in (e.g. gae_returns(...).adv_stats): same losses, no statistics launch
+    stats = torch.stack([td['adv'].mean(), td['adv'].std() + 1e-8])
+    loss2, _ = b2.ppo_error_adv_norm(data, adv_stats=stats, **p)
+    for got, want in zip(loss2, out[:4]):
+        assert torch.allclose(got.cpu(), want.detach(), rtol=1e-5, atol=1e-5)
 
 
 def test_impala_reshape_data_then_vtrace_matches_policy_lines():
