@@ -139,7 +139,11 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
                 if (row >= jmin && o < Pv) cpa16(dst + p * 16, g + row * rstride + o * 16);
             }
         };
-        const bool fast_rows = f.loader != 1;  // B200RL_COL_LOADER=1: the flat loop everywhere (A/B experiments)
+        // B200RL_COL_LOADER: 0 (default) = the flat loop; 2 | 3 = lane-owns-a-piece-column copies in 4- | 8-piece groups.
+        // The cheap copies cut the loader's instructions ~10x and make THIS kernel slower on every box measured (16.6 us flat,
+        // 17.1 us 8-piece groups, 17.2 us 4-piece groups): the copies then leave in bursts and the consumers' own stores
+        // and shared-memory traffic queue behind them.  vtws.cu, whose loader is the pacer, gains 0.65 us from the same change.
+        const bool fast_rows = f.loader >= 2;
         CwItem it = first;
         int s = 0, ph = 0;
         for (int j = 0; item_valid(it); ++j) {
@@ -151,14 +155,23 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
             const int W = (int)((B - c0) < CW_TC ? (B - c0) : CW_TC);
             unsigned char* st = smem + s * L.stage_bytes;
             if (jmin == 0 && W == CW_TC && fast_rows) {
-                // full chunk of a full tile: a row segment is TC * esz / 16 = esz pieces (4 N | 8 | 4)
+                // full chunk of a full tile: a row segment is TC * esz / 16 = esz pieces (4 N | 8 | 4).  Logits and actions
+                // go in 8-piece groups (a lane group covers one full 128-byte line per row: the 4-piece grouping doubles the
+                // number of L2 requests and measured 0.3 us SLOWER than the flat loop); the float tensors have 64-byte rows.
                 const uint32_t sb = smem_u32(st);
                 const long long e0 = t0 * B + c0;
                 const long long ls = B * N * 4;
-                warp_copy_rows<4, CW_R, NC>(sb, a.logit_new + e0 * N, ls, N, lane);
-                warp_copy_rows<4, CW_R, NC>(sb + L.off_old, a.logit_old + e0 * N, ls, N, lane);
-                if (has_pre) warp_copy_rows<4, CW_R, NC>(sb + L.off_pre, a.logit_pre + e0 * N, ls, N, lane);
-                warp_copy_rows<4, CW_R, 2>(sb + L.off_act, a.action + e0, B * 8, 2, lane);
+                if (f.loader != 3 || (N & 1)) {
+                    warp_copy_rows<4, CW_R, NC>(sb, a.logit_new + e0 * N, ls, N, lane);
+                    warp_copy_rows<4, CW_R, NC>(sb + L.off_old, a.logit_old + e0 * N, ls, N, lane);
+                    if (has_pre) warp_copy_rows<4, CW_R, NC>(sb + L.off_pre, a.logit_pre + e0 * N, ls, N, lane);
+                    warp_copy_rows<4, CW_R, 2>(sb + L.off_act, a.action + e0, B * 8, 2, lane);
+                } else {
+                    warp_copy_rows<8, CW_R, NC / 2>(sb, a.logit_new + e0 * N, ls, N / 2, lane);
+                    warp_copy_rows<8, CW_R, NC / 2>(sb + L.off_old, a.logit_old + e0 * N, ls, N / 2, lane);
+                    if (has_pre) warp_copy_rows<8, CW_R, NC / 2>(sb + L.off_pre, a.logit_pre + e0 * N, ls, N / 2, lane);
+                    warp_copy_rows<8, CW_R, 1>(sb + L.off_act, a.action + e0, B * 8, 1, lane);
+                }
                 warp_copy_rows<4, CW_R, 1>(sb + L.off_vn, a.value_new + e0, B * 4, 1, lane);
                 warp_copy_rows<4, CW_R, 1>(sb + L.off_vo, a.value_old + e0, B * 4, 1, lane);
                 warp_copy_rows<4, CW_R, 1>(sb + L.off_ret, a.ret + e0, B * 4, 1, lane);

@@ -656,13 +656,18 @@ __global__ void __launch_bounds__(VR_NT) vtrace_res_kernel(VtFusedArgs a, float*
 }
 
 // widest tile that leaves at least two CTAs per SM (227 KB of shared memory per SM, 1 KB reserved per CTA); 0 = no fit
-static int g_vt_impl = 0;  // b200rl_vtrace_set_impl: 0 = automatic, 1 = streaming column tiles only
-static int vr_pick_tc(const VtFusedArgs& a) {
+static int g_vt_impl = 0;  // b200rl_vtrace_set_impl: 0 = automatic, 1 = streaming column tiles only, 2 = resident tiles first
+static int vr_env() {
     static int forced = -1;
     if (forced < 0) {
-        const char* e = getenv("B200RL_VT_RES");  // 0 = never, 4 | 8 = that tile width
+        const char* e = getenv("B200RL_VT_RES");  // 0 = never, 4 | 8 = that tile width (and before the streaming kernel)
         forced = e ? atoi(e) : -2;
     }
+    return forced;
+}
+static bool vr_forced() { return vr_env() == 4 || vr_env() == 8 || g_vt_impl == 2; }
+static int vr_pick_tc(const VtFusedArgs& a) {
+    const int forced = vr_env();
     if (forced == 0 || g_vt_impl == 1 || a.N < 2) return 0;
     const bool has_w = a.weight != nullptr;
     if (forced == 4 || forced == 8) return vr_smem_bytes(a.T, a.N, has_w, forced) <= 226 * 1024 ? forced : 0;
@@ -812,7 +817,7 @@ static void fill_vt(VtFusedArgs& a, const float* target_output, const float* beh
 }
 
 extern "C" int b200rl_vtrace_set_impl(int impl) {
-    if (impl < 0 || impl > 1) return B200RL_ERR_ARG;
+    if (impl < 0 || impl > 2) return B200RL_ERR_ARG;
     const int old = g_vt_impl;
     g_vt_impl = impl;
     return old;
@@ -854,7 +859,9 @@ extern "C" int b200rl_vtrace_fwd_grad(const float* target_output, const float* b
     a.g_expected = g_expected; a.verify = verify ? 1 : 0; a.g_pg = g_policy; a.g_val = g_value; a.g_ent = g_entropy;
     a.g_used = g_used; a.g_hint = g_hint; a.grad_logit = grad_target_output; a.grad_value = grad_value;
     cudaStream_t st = (cudaStream_t)stream;
-    const int rtc = vtres_tc(a);
+    // streaming column tiles wherever they fit (measured faster at config E: 15.4 vs 19.4 us); resident tiles take the shapes
+    // they cannot (N > 14: no three-stage ring) -- B200RL_VT_RES=4|8 forces them (experiments)
+    const int rtc = (vtws_ok(a) && !vr_forced()) ? 0 : vtres_tc(a);
     if (rtc == 8)
         return grads ? dispatch_vtres<true, 8>(a, out3, workspace, workspace_bytes, st)
                      : dispatch_vtres<false, 8>(a, out3, workspace, workspace_bytes, st);

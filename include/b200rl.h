@@ -242,10 +242,11 @@ B200RL_API int b200rl_vtrace_continuous_bwd(const float* mu_target, const float*
  * (device scalars, null = 0): the launch is a no-op when they equal g_used, otherwise everything is recomputed with the
  * actual values (exact for any upstream gradient, no host sync); g_hint (nullable) is refreshed with the actual values.
  * grad_target_output == null (verify = 0 only): losses only.  out3 is written by the verify = 0 launch only.
- * Two kernels behind the entry point: resident tiles when the (T x 8 | 4 columns) tile of a CTA fits shared memory twice
- * per SM (IMPALA unroll lengths; any N that fits), else the streaming column tiles (any T, N <= 32 with the ring fitting two
- * CTAs per SM).  Requires b200rl_vtrace_fused_supported(...) == 1 (one of the two fits, B % 4 == 0, 16-byte aligned
- * tensors).  b200rl_vtrace_set_impl: 0 = automatic (default), 1 = streaming column tiles only; returns the previous value. */
+ * Two kernels behind the entry point: the streaming column tiles (any T; N <= 14 with weights: the stage ring has to fit two
+ * CTAs per SM) and, for the rows they cannot take, resident tiles (the T x 8 | 4-column tile of a CTA fits shared memory twice
+ * per SM: IMPALA unroll lengths, any N that fits).  Requires b200rl_vtrace_fused_supported(...) == 1 (one of the two fits,
+ * B % 4 == 0, 16-byte aligned tensors).  b200rl_vtrace_set_impl: 0 = automatic (default), 1 = streaming column tiles only,
+ * 2 = resident tiles wherever they fit; returns the previous value. */
 B200RL_API int b200rl_vtrace_set_impl(int impl);
 B200RL_API int b200rl_vtrace_fused_supported(const float* target_output, const float* behaviour_output,
                                   const long long* action, const float* value, const float* reward,

@@ -405,11 +405,11 @@ def _vtrace_close(td, tw, loss, lw):
         assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max()), k
 
 
-@pytest.fixture(params=['auto', 'stream'])
+@pytest.fixture(params=['auto', 'resident'])
 def vtrace_impl(request):
-    """auto = resident tiles where they fit (short T), else the streaming column tiles; stream = column tiles only"""
+    """auto = streaming column tiles where they fit, else resident tiles; resident = resident tiles wherever they fit"""
     from di_engine_b200 import ops
-    old = ops.lib().b200rl_vtrace_set_impl({'auto': 0, 'stream': 1}[request.param])
+    old = ops.lib().b200rl_vtrace_set_impl({'auto': 0, 'resident': 2}[request.param])
     yield request.param
     ops.lib().b200rl_vtrace_set_impl(old)
 

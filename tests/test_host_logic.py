@@ -120,6 +120,28 @@ def test_signatures_match_reference_defaults():
                                 ('bootstrap_values', E), ('mask', None)]
 
 
+def test_every_hot_path_signature_matches_the_live_reference():
+    """every rebound function, against the unmodified reference: same parameter names in the same order, same defaults
+    (callables / modules by type or by name)"""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference not importable here')
+    ref = ref_loader.load()
+    for name in b2.rl_utils.HOT_PATH_FUNCTIONS:
+        ours, theirs = getattr(b2.rl_utils, name), getattr(ref, name, None)
+        assert theirs is not None, name
+        po, pt = inspect.signature(ours).parameters, inspect.signature(theirs).parameters
+        assert list(po) == list(pt), (name, list(po), list(pt))
+        for k in po:
+            a, b = po[k].default, pt[k].default
+            if callable(a) or callable(b):
+                assert type(a) is type(b) or getattr(a, '__name__', None) == getattr(b, '__name__', None), (name, k)
+            else:
+                assert a == b, (name, k, a, b)
+    for name in b2.rl_utils.HOT_PATH_TYPES:
+        assert getattr(b2.rl_utils, name)._fields == getattr(ref, name)._fields, name
+
+
 def test_shape_fns():
     r = b2.rl_utils
     d = r.gae_data(None, None, torch.zeros(5, 3), None, None)
