@@ -1099,9 +1099,10 @@ def run_gpu(args):
         e2e_value = units_per_step / (e2e_ms / e2e_steps * 1e-3)
         coll = 'none'
         if world > 1:
-            coll = {'fused': 'the 6 loss scalars are exchanged by the step\'s own finalize launch (NVLink peer-memory '
-                             'mailboxes, {sequence,value} words; mean of rank means); step j-1 is consumed in step j, one '
-                             'drain kernel after the last step; no collective launch',
+            coll = {'fused': 'the 6 loss scalars ride on the step\'s own launches: finalize_sums stages {tag, value} locally, the first '
+                             'CTA of the NEXT step\'s kernel consumes the peers\' words of two steps ago and publishes the staged ones '
+                             '(one 8-byte st.relaxed.sys per peer into NVLink peer-memory mailboxes) while it waits for its first '
+                             'chunk; mean of rank means; one drain kernel after the last step; no collective launch, no forked branch',
                     'p2p-kernel': 'one small NVLink peer-memory kernel per step (b200rl_p2p_allreduce_mean) on a forked '
                                   'graph branch',
                     'nccl': 'one NCCL all-reduce of the 6 loss scalars per step on a forked graph branch'}[exchange]

@@ -60,6 +60,7 @@ PROTOTYPES = {
                                        P, P, c_size_t, P],
     "b200rl_gae_ppo_set_impl": [I],
     "b200rl_vtrace_set_impl": [I],
+    "b200rl_q_retraces": [P, P, P, P, P, P, LL, LL, LL, D, P, P],
     "b200rl_quantile_td_fwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, LL, LL, LL, D, LL, LL, LL, LL, LL, LL, LL, LL, I, D, P, P,
                                P, P, P, c_size_t, P],
     "b200rl_quantile_td_bwd": [P, P, P, P, P, LL, LL, LL, LL, LL, LL, I, P, P],

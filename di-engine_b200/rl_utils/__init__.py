@@ -12,6 +12,7 @@ from .td import (bdq_nstep_td_error, dist_1step_td_data, dist_1step_td_error, di
                  v_1step_td_data, v_1step_td_error, v_nstep_td_data, v_nstep_td_error)
 from .quantile import (fqf_nstep_td_data, fqf_nstep_td_error, iqn_nstep_td_data, iqn_nstep_td_error, qrdqn_nstep_td_data,
                        qrdqn_nstep_td_error)
+from .retrace import compute_q_retraces
 from .upgo import tb_cross_entropy, upgo_loss, upgo_returns
 from .value_rescale import value_inv_transform, value_transform
 from .vtrace import (impala_reshape_data, shape_fn_vtrace_discrete_action, vtrace_data, vtrace_error_continuous_action,
@@ -23,7 +24,8 @@ HOT_PATH_FUNCTIONS = [
     # siblings on the same kernels
     'q_1step_td_error', 'v_1step_td_error', 'v_nstep_td_error', 'ppo_policy_error', 'ppo_value_error',
     'dist_1step_td_error', 'bdq_nstep_td_error', 'upgo_returns', 'tb_cross_entropy', 'ppo_error_continuous', 'a2c_error',
-    'vtrace_error_continuous_action', 'qrdqn_nstep_td_error', 'iqn_nstep_td_error', 'fqf_nstep_td_error'
+    'vtrace_error_continuous_action', 'qrdqn_nstep_td_error', 'iqn_nstep_td_error', 'fqf_nstep_td_error',
+    'compute_q_retraces'
 ]
 HOT_PATH_TYPES = [
     'gae_data', 'ppo_data', 'ppo_loss', 'ppo_info', 'q_nstep_td_data', 'dist_nstep_td_data', 'td_lambda_data',

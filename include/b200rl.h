@@ -267,6 +267,13 @@ B200RL_API int b200rl_ppo_value_fwd(const float* value_new, const float* value_o
                          const float* weight, long long S, double clip_ratio, int use_value_clip, float* loss,
                          float* dvalue_unit, float* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- compute_q_retraces: ding/rl_utils/retrace.py:7-56 (ACER's Retrace targets; no gradient, as in the reference) -----------
+ * q_values, ratio (T+1 | T, B, N) -- row T of q_values is never read; v_pred (T+1, B); rewards / weights (T, B); actions (T, B)
+ * int64; q_retraces (T+1, B).  Bit-identical to the reference loop (same fp32 operations in the same order). */
+B200RL_API int b200rl_q_retraces(const float* q_values, const float* v_pred, const float* rewards, const long long* actions,
+                      const float* weights, const float* ratio, long long T, long long B, long long N, double gamma,
+                      float* q_retraces, void* stream);
+
 /* ---- quantile-regression n-step TD: qrdqn_nstep_td_error (ding/rl_utils/td.py:1098-1166, form 0), iqn_nstep_td_error
  * (:1253-1346, form 1), fqf_nstep_td_error (:1359-1436, form 2) -- csrc/quantile.cu, one kernel, the layouts are strides:
  * theta_i = q[b*q_sb + i*q_si + action_b*q_sa] (i < n_tau), theta'_j from next_n_q likewise (j < n_tau_prime),

@@ -37,6 +37,7 @@ FILES = [
     "ding/rl_utils/vtrace.py",
     "ding/rl_utils/upgo.py",
     "ding/rl_utils/a2c.py",            # sibling head
+    "ding/rl_utils/retrace.py",        # ACER's return operator
 ]
 
 

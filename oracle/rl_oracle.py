@@ -804,3 +804,18 @@ def fqf_nstep_td_error(q, next_n_q, action, next_n_action, reward, done, quantil
     theta = q[rows, :, action]             # (B, tau)
     target = _quantile_target(next_n_q[rows, :, next_n_action], reward, done, gamma, nstep, value_gamma)
     return _quantile_loss(theta, target, quantiles_hats, weight, _smooth_l1, True, kappa, True)
+
+
+def compute_q_retraces(q_values, v_pred, rewards, actions, weights, ratio, gamma: float = 0.9):
+    """retrace.py:7-56: Qret[T] = V[T]; Qret[t] = r_t + gamma w_t tmp; tmp = min(ratio_t[a_t], 1) (Qret[t] - Q_t[a_t]) + V_t."""
+    T = q_values.size()[0] - 1
+    rewards, actions, weights = rewards.unsqueeze(-1), actions.unsqueeze(-1), weights.unsqueeze(-1)
+    q_retraces = torch.zeros_like(v_pred)
+    tmp = v_pred[-1]
+    q_retraces[-1] = v_pred[-1]
+    q_gather = q_values[0:-1].gather(-1, actions)
+    ratio_gather = ratio.gather(-1, actions)
+    for idx in reversed(range(T)):
+        q_retraces[idx] = rewards[idx] + gamma * weights[idx] * tmp
+        tmp = ratio_gather[idx].clamp(max=1.0) * (q_retraces[idx] - q_gather[idx]) + v_pred[idx]
+    return q_retraces
