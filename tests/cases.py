@@ -38,6 +38,7 @@ GRAD_INPUTS = {
     'qrdqn': ['q'],
     'iqn': ['q'],
     'fqf': ['q'],
+    'retrace': [],
 }
 # upstream gradient for each returned loss head (distinct, non-trivial)
 LOSS_MIX = {
@@ -409,6 +410,19 @@ def vtc_case(seed, T, B, D, weight='none', **params):
     return 'vtc', t, params
 
 
+def retrace_case(seed, T, B, N, gamma=0.99):
+    """tests/test_retrace.py:8-18"""
+    g = _g(seed)
+    t = OrderedDict()
+    t['q_values'] = _randn(g, T + 1, B, N)
+    t['v_pred'] = _randn(g, T + 1, B, 1)
+    t['rewards'] = _randn(g, T, B)
+    t['actions'] = _randint(g, N, T, B)
+    t['weights'] = _rand(g, T, B)
+    t['ratio'] = _rand(g, T, B, N) * 0.8 + 0.6  # both sides of the clamp at 1
+    return 'retrace', t, dict(gamma=gamma)
+
+
 _QF = ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done')
 QUANTILE_FIELDS = {'qrdqn': _QF + ('tau', 'weight'), 'iqn': _QF + ('replay_quantiles', 'weight'), 'fqf': _QF + ('quantiles_hats', 'weight')}
 
@@ -521,6 +535,9 @@ def build_cases():
     c['iqn_w_kappa'] = quantile_case(134, 'iqn', 5, 6, 32, 32, 2, weight='tensor', value_gamma='tensor', kappa=0.6)
     c['fqf_basic'] = quantile_case(135, 'fqf', 8, 4, 8, 8, 3)
     c['fqf_w_kappa'] = quantile_case(136, 'fqf', 5, 6, 32, 16, 4, weight='tensor', value_gamma='scalar', kappa=1.7)
+    # ---- ACER Retrace targets (tests/test_retrace.py) ----------------------------------------------------------------------
+    c['retrace_ref_test'] = retrace_case(140, 64, 32, 6)
+    c['retrace_ragged'] = retrace_case(141, 13, 5, 3, gamma=0.9)
     c['a2c_basic'] = a2c_case(114, 64, 6)
     c['a2c_w_wide'] = a2c_case(115, 9, 130, weight='tensor')
     # ---- dist_nstep (tests/test_td.py:130-204) ---------------------------------------------------------------
@@ -630,6 +647,9 @@ def run_api(api, op, tensors, params, device='cpu'):
         for k in ('policy_loss', 'value_loss', 'entropy_loss'):
             res['out_' + k] = _np(getattr(loss, k))
         _backward(op, list(loss), t, res)
+        return res
+    if op == 'retrace':
+        res['out_q_retraces'] = _np(api.compute_q_retraces(*t.values(), **p))
         return res
     if op in ('qrdqn', 'iqn', 'fqf'):
         data = getattr(api, op + '_nstep_td_data')(*[t[k] for k in QUANTILE_FIELDS[op]])
@@ -812,6 +832,9 @@ def run_oracle(orc, op, tensors, params):
             res['out_' + k] = _np(v)
         _backward(op, list(out), t, res)
         return res
+    if op == 'retrace':
+        res['out_q_retraces'] = _np(orc.compute_q_retraces(*t.values(), **p))
+        return res
     if op in ('qrdqn', 'iqn', 'fqf'):
         loss, per = getattr(orc, op + '_nstep_td_error')(*[t[k] for k in QUANTILE_FIELDS[op]], value_gamma=t.get('value_gamma'), **p)
         res['out_loss'] = _np(loss)
@@ -890,7 +913,7 @@ def run_oracle(orc, op, tensors, params):
 
 
 # outputs that are driven by integer / boolean decisions and must match bit-for-bit on the GPU as well
-EXACT_KEYS = {'gae': ['out_adv', 'out_next_value_after']}
+EXACT_KEYS = {'gae': ['out_adv', 'out_next_value_after'], 'retrace': ['out_q_retraces']}
 
 
 def compare(res, ref, rtol=1e-5, atol=1e-5, exact=False):

@@ -27,7 +27,7 @@ def _run(op, tensors, params, device=DEV):
 def test_matches_reference_golden(name):
     op, tensors, params, expected = golden_io.load(name)
     got = _run(op, tensors, params)
-    if op == 'gae':
+    if op in ('gae', 'retrace'):
         cases.compare(got, expected, exact=True)
     else:
         cases.compare(got, expected, rtol=1e-5, atol=1e-5)
@@ -38,7 +38,7 @@ def test_host_buffer_path_matches_golden(name):
     """CPU tensors in -> staged to the GPU -> results (and the in-place next_value mask) back on the host."""
     op, tensors, params, expected = golden_io.load(name)
     got = _run(op, tensors, params, device='cpu')
-    cases.compare(got, expected, exact=(op == 'gae'))
+    cases.compare(got, expected, exact=(op in ('gae', 'retrace')))
 
 
 BIG = {
@@ -65,6 +65,8 @@ BIG = {
     'vtrace_E': lambda: cases.vtrace_case(104, 64, 8192, 6, gamma=0.99, lambda_=0.95),
     'vtrace_ragged': lambda: cases.vtrace_case(121, 130, 333, 7, weight='tensor', rho_clip_ratio=0.9),
     'vtrace_N100': lambda: cases.vtrace_case(122, 8, 16, 100),
+    'retrace_E': lambda: cases.retrace_case(123, 64, 8192, 6),
+    'retrace_long': lambda: cases.retrace_case(124, 1003, 130, 18, gamma=0.997),
 }
 
 
@@ -73,7 +75,7 @@ def test_matches_oracle_at_baseline_sizes(name):
     op, tensors, params = BIG[name]()
     want = cases.run_oracle(rl_oracle, op, tensors, params)
     got = _run(op, tensors, params)
-    if op == 'gae':
+    if op in ('gae', 'retrace'):
         cases.compare(got, want, exact=True)
     else:
         cases.compare(got, want, rtol=1e-5, atol=1e-5)

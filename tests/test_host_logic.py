@@ -238,6 +238,7 @@ EXPECTED_CALLS = {
     'qrdqn': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
     'iqn': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
     'fqf': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
+    'retrace': ['b200rl_q_retraces'],
 }
 
 

@@ -25,7 +25,7 @@ def test_oracle_matches_golden(name):
     op, tensors, params, expected = golden_io.load(name)
     res = cases.run_oracle(rl_oracle, op, tensors, params)
     # same torch build; another host CPU may vectorise exp/log differently -> 1-2 ulp. gae is pure mul/add: exact.
-    if op == 'gae':
+    if op in ('gae', 'retrace'):
         cases.compare(res, expected, exact=True)
     else:
         cases.compare(res, expected, rtol=2e-6, atol=2e-6)

@@ -10,7 +10,7 @@
 Ported from ding/rl_utils/tests/test_gae.py, test_ppo.py (discrete, continuous, shape_fn), test_a2c.py (discrete), test_td.py (the operators on this
 path: q_nstep, q_nstep_ngu, bdq_nstep, q_1step_compatible, dist_1step, dist_1step_compatible, dist_1step multi agent,
 dist_nstep, dist_nstep multi agent, rescale, rescale_ngu, qrdqn_nstep, iqn_nstep, fqf_nstep, td_lambda, v_1step, v_1step multi agent, v_nstep, the four shape_fn
-tests), test_vtrace.py (discrete), test_upgo.py and test_value_rescale.py.  The reference draws unseeded random inputs; the
+tests), test_vtrace.py (discrete), test_retrace.py, test_upgo.py and test_value_rescale.py.  The reference draws unseeded random inputs; the
 ports seed them (so the three implementations see identical bits) and keep every assertion.
 """
 import contextlib
@@ -420,6 +420,26 @@ def _quantile_body(kind):
 @pytest.mark.parametrize('kind', ['qrdqn', 'iqn', 'fqf'])
 def test_quantile_nstep_td(impl, kind):
     _run(_quantile_body(kind), impl)
+
+
+def _q_retraces_body(api, dev, rec):
+    g = _gen(31)
+    T, B, N = 64, 32, 6  # tests/test_retrace.py:8-18
+    q_values = torch.randn(T + 1, B, N, generator=g).to(dev)
+    v_pred = torch.randn(T + 1, B, 1, generator=g).to(dev)
+    rewards = torch.randn(T, B, generator=g).to(dev)
+    ratio = (torch.rand(T, B, N, generator=g) * 0.4 + 0.8).to(dev)
+    assert ratio.max() <= 1.2 and ratio.min() >= 0.8
+    weights = torch.rand(T, B, generator=g).to(dev)
+    actions = torch.randint(0, N, size=(T, B), generator=g).to(dev)
+    with torch.no_grad():
+        q_retraces = api.compute_q_retraces(q_values, v_pred, rewards, actions, weights, ratio, gamma=0.99)
+    assert q_retraces.shape == (T + 1, B, 1)
+    rec.put('q_retraces', q_retraces)
+
+
+def test_compute_q_retraces(impl):
+    _run(_q_retraces_body, impl)
 
 
 def _q_nstep_td_ngu_body(api, dev, rec):
