@@ -159,7 +159,7 @@ class DeviceStepD:
     def _ppo_in(self):
         b, o = self.b, self.ops
         return (_p(o, b['logit_new']), _p(o, b['logit_old']), None, _p(o, b['action']), _p(o, b['value_new']),
-                _p(o, b['value_old']), _p(o, self.adv), _p(o, b['return_']), None, self.S, 1, self.wl.N, CLIP, 1, 0.0, 1, None)
+                _p(o, b['value_old']), _p(o, self.adv), _p(o, b['return_']), None, self.S, 1, self.wl.N, CLIP, 1, 0.0, 1, None, None)
 
     def gae(self):
         b, o = self.b, self.ops
@@ -305,7 +305,7 @@ class DeviceStepP(DeviceStepD):
         b, o = self.b, self.ops
         return (_p(o, b['logit_new']), _p(o, b['logit_old']), None, _p(o, b['action']), _p(o, b['value_new']),
                 _p(o, self.vout), _p(o, self.adv), _p(o, self.rout), None, self.S, 1, self.wl.N, CLIP, 1, 0.0, 1,
-                _p(o, self.adv_stats))
+                _p(o, self.adv_stats), None)
 
     def gae_returns(self):
         b, o = self.b, self.ops

@@ -26,9 +26,9 @@ PROTOTYPES = {
     "b200rl_adv_stats": [P, LL, P, P, c_size_t, P],
     "b200rl_normalize": [P, P, LL, P, P],
     "b200rl_impala_mask": [P, P, P, LL, LL, P, P, P, P],
-    "b200rl_ppo_fwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, c_size_t, P],
-    "b200rl_ppo_bwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, P, P, P, P],
-    "b200rl_ppo_fwd_grad": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, P, c_size_t, P],
+    "b200rl_ppo_fwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, c_size_t, P],
+    "b200rl_ppo_bwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, P, P, P, P, P],
+    "b200rl_ppo_fwd_grad": [P, P, P, P, P, P, P, P, P, LL, LL, LL, D, I, D, I, P, P, P, P, P, P, P, P, c_size_t, P],
     "b200rl_ppo_value_fwd": [P, P, P, P, LL, D, I, P, P, P, c_size_t, P],
     "b200rl_ppo_fused_supported": [P, P, P, P, P, P, P, P, P, P, LL, LL],
     "b200rl_qntd_fwd": [P, P, P, P, P, P, P, P, LL, P, LL, LL, LL, I, D, I, I, D, I, D, I, LL, D, P, P, P, P, P, P, P,

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NT) ppo_fwd_kernel(PpoArgs a, float* out, floa
             const float ratio = (G == 1) ? ratio_sum : ratio_sum / (float)G;
             const float ent = (G == 1) ? ent_sum : ent_sum / (float)G;
             float dsel;
-            const float sel = surrogate(ratio, adv, a.clip_lo, a.clip_hi, a.dual_clip, dsel);
+            const float sel = surrogate(ratio, adv, a.clip_lo, a.clip_hi, a.dual_clip, dsel, false, a.factor ? a.factor[s] : 1.f);
             acc[0] -= sel * w;
             float dterm;
             acc[1] += value_term(a.value_new[s], a.value_old[s], a.ret[s], a.clip, a.use_value_clip, dterm) * w;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(NT) ppo_bwd_kernel(PpoArgs a) {
         const float ratio_g = expf(lp_n - (ro[act] - lse_o));
         if (G == 1) ratio_s = ratio_g;
         float dsel;
-        surrogate(ratio_s, adv, a.clip_lo, a.clip_hi, a.dual_clip, dsel);
+        surrogate(ratio_s, adv, a.clip_lo, a.clip_hi, a.dual_clip, dsel, false, a.factor ? a.factor[s] : 1.f);
         // d policy_loss / d logp_new(row) = -(w/S) * dsel/dratio * ratio_g / G
         float c_act = g_pol * (-w * inv_s) * dsel * ratio_g / (float)G;
         if (zp) {
@@ -450,8 +450,10 @@ using namespace b200rl;
 static int fill_args(PpoArgs& a, const float* logit_new, const float* logit_old, const float* logit_pretrained,
                      const long long* action, const float* value_new, const float* value_old, const float* adv,
                      const float* return_, const float* weight, long long S, long long G, long long N,
-                     double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* adv_stats) {
+                     double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* adv_stats,
+                     const float* factor) {
     a.adv_stats = adv_stats;
+    a.factor = factor;
     a.logit_new = logit_new; a.logit_old = logit_old; a.logit_pre = logit_pretrained; a.action = action;
     a.value_new = value_new; a.value_old = value_old; a.adv = adv; a.ret = return_; a.weight = weight;
     a.S = S; a.G = (int)G; a.N = (int)N; a.clip = (float)clip_ratio; a.clip_lo = (float)(1.0 - clip_ratio);
@@ -475,11 +477,11 @@ extern "C" int b200rl_ppo_fwd(const float* logit_new, const float* logit_old, co
                               const long long* action, const float* value_new, const float* value_old,
                               const float* adv, const float* return_, const float* weight, long long S, long long G,
                               long long N, double clip_ratio, int use_value_clip, double dual_clip, int kl_type,
-                              const float* adv_stats, float* out, float* workspace, size_t workspace_bytes,
-                              void* stream) {
+                              const float* adv_stats, const float* factor, float* out, float* workspace,
+                              size_t workspace_bytes, void* stream) {
     PpoArgs a{};
     int rc = fill_args(a, logit_new, logit_old, logit_pretrained, action, value_new, value_old, adv, return_, weight,
-                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, adv_stats);
+                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, adv_stats, factor);
     if (rc != B200RL_OK || !out || !workspace) return rc != B200RL_OK ? rc : B200RL_ERR_ARG;
     if (S == 0) return B200RL_ERR_ARG;  // mean over an empty batch is undefined (reference returns nan)
     cudaStream_t st = (cudaStream_t)stream;
@@ -498,12 +500,13 @@ extern "C" int b200rl_ppo_fwd_grad(const float* logit_new, const float* logit_ol
                                    const long long* action, const float* value_new, const float* value_old,
                                    const float* adv, const float* return_, const float* weight, long long S,
                                    long long G, long long N, double clip_ratio, int use_value_clip, double dual_clip,
-                                   int kl_type, const float* adv_stats, const float* g_expected, float* g_used, float* out,
+                                   int kl_type, const float* adv_stats, const float* factor, const float* g_expected,
+                                   float* g_used, float* out,
                                    float* grad_logit_new, float* grad_value_new, float* workspace,
                                    size_t workspace_bytes, void* stream) {
     PpoArgs a{};
     int rc = fill_args(a, logit_new, logit_old, logit_pretrained, action, value_new, value_old, adv, return_, weight,
-                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, adv_stats);
+                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, adv_stats, factor);
     if (rc != B200RL_OK) return rc;
     if (!out || !workspace || !g_expected || !g_used || !grad_logit_new || !grad_value_new || S == 0)
         return B200RL_ERR_ARG;
@@ -529,13 +532,13 @@ extern "C" int b200rl_ppo_bwd(const float* logit_new, const float* logit_old, co
                               const long long* action, const float* value_new, const float* value_old,
                               const float* adv, const float* return_, const float* weight, long long S, long long G,
                               long long N, double clip_ratio, int use_value_clip, double dual_clip, int kl_type,
-                              const float* adv_stats, const float* g_policy, const float* g_value, const float* g_entropy,
-                              const float* g_kl,
+                              const float* adv_stats, const float* factor, const float* g_policy, const float* g_value,
+                              const float* g_entropy, const float* g_kl,
                               const float* g_used, float* g_hint, float* grad_logit_new, float* grad_value_new,
                               void* stream) {
     PpoArgs a{};
     int rc = fill_args(a, logit_new, logit_old, logit_pretrained, action, value_new, value_old, adv, return_, weight,
-                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, adv_stats);
+                       S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, adv_stats, factor);
     if (rc != B200RL_OK) return rc;
     a.g_policy = g_policy; a.g_value = g_value; a.g_entropy = g_entropy; a.g_kl = g_kl;
     a.g_used = const_cast<float*>(g_used); a.g_hint = g_hint;

@@ -38,6 +38,9 @@ struct PpoArgs {
     // nullable: {mean, std + 1e-8} of the advantage batch (device floats, b200rl_adv_stats): when given every kernel uses
     // (adv - mean) / (std + 1e-8) -- PPOPolicy's per-batch advantage normalisation (ding/policy/ppo.py:304-306) applied on load
     const float* adv_stats;
+    // nullable, (S): happo_error's per-sample factor (the other agents' ratio product, ding/rl_utils/happo.py:124-125): the
+    // selected surrogate is multiplied by it before the dual clip
+    const float* factor;
     int dbg;        // tuning experiments only (B200RL_PPO_DBG): 1 = consumers skip the row math, 2 = skip gradient stores
 };
 
@@ -45,8 +48,9 @@ struct PpoArgs {
 // gradient on the closed interval (ppo.py:208-216).  Also returns the selected surrogate value.
 // dual_all: ppo_error_continuous applies max(., dual_clip * adv) to EVERY sample (ppo.py:346-347), the discrete loss only where
 // adv < 0 (ppo.py:211-214)
+// fac: happo's factor multiplies min(surr1, surr2) before the dual clip (happo.py:124-130); 1 for every PPO loss
 __device__ __forceinline__ float surrogate(float ratio, float adv, float lo, float hi, float dual_clip,
-                                           float& dsel_dratio, bool dual_all = false) {
+                                           float& dsel_dratio, bool dual_all = false, float fac = 1.f) {
     const float rc = fminf(fmaxf(ratio, lo), hi);
     const float s1 = ratio * adv, s2 = rc * adv;
     const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
@@ -54,8 +58,8 @@ __device__ __forceinline__ float surrogate(float ratio, float adv, float lo, flo
     if (s1 < s2) { w1 = 1.f; w2 = 0.f; }
     else if (s1 > s2) { w1 = 0.f; w2 = 1.f; }
     else { w1 = 0.5f; w2 = 0.5f; }
-    float sel = fminf(s1, s2);
-    float d = adv * (w1 + w2 * in_range);
+    float sel = fminf(s1, s2) * fac;
+    float d = adv * (w1 + w2 * in_range) * fac;
     if (dual_clip > 0.f && (dual_all || adv < 0.f)) {
         const float floor_ = dual_clip * adv;
         if (sel < floor_) { sel = floor_; d = 0.f; }
@@ -194,7 +198,7 @@ struct PpoUpstream {
 template <int NC, bool LOSSES, bool GRADS>
 __device__ __forceinline__ void ppo_row_compute_to(const PpoArgs& a, const PpoTileLayout& L, const unsigned char* st,
                                                    int tid, int N, float adv, float* gr, float* gv,
-                                                   const PpoUpstream& up, float (&acc)[6]) {
+                                                   const PpoUpstream& up, float (&acc)[6], float fac = 1.f) {
     adv = adv_in(a, adv);
     const bool has_pre = a.logit_pre != nullptr, has_w = a.weight != nullptr;
     const float g_pol = up.g_pol, g_val = up.g_val, g_ent = up.g_ent, g_kl = up.g_kl, inv_s = up.inv_s;
@@ -253,7 +257,7 @@ __device__ __forceinline__ void ppo_row_compute_to(const PpoArgs& a, const PpoTi
             const float lp_o = (zo[act] - mo) - lg2f_(so) * kLn2;
             const float ratio = ex2f_((lp_n - lp_o) * kLog2e);
             float dsel, dterm, dk = 0.f, klv = 0.f;
-            const float sel = surrogate(ratio, adv, a.clip_lo, a.clip_hi, a.dual_clip, dsel);
+            const float sel = surrogate(ratio, adv, a.clip_lo, a.clip_hi, a.dual_clip, dsel, false, fac);
             const float vt = value_term(v_new, v_old, ret, a.clip, a.use_value_clip, dterm);
             if (has_pre) {
                 const float* zp = reinterpret_cast<const float*>(st + L.off_pre) + tid * N;
@@ -308,7 +312,7 @@ __device__ __forceinline__ void ppo_row_compute(const PpoArgs& a, const PpoTileL
     const bool via_smem = full_tile && !(a.dbg & 4);
     float* gr = GRADS ? (via_smem ? gtile + tid * N : a.grad_logit + (row0 + tid) * N) : nullptr;
     float* gv = GRADS ? a.grad_value + row0 + tid : nullptr;
-    ppo_row_compute_to<NC, LOSSES, GRADS>(a, L, st, tid, N, adv, gr, gv, up, acc);
+    ppo_row_compute_to<NC, LOSSES, GRADS>(a, L, st, tid, N, adv, gr, gv, up, acc, a.factor ? a.factor[row0 + tid] : 1.f);
 }
 
 }  // namespace b200rl

@@ -208,7 +208,7 @@ def ppo_hint(device, kind='ppo'):
     key = (device.index, kind)
     h = _PPO_HINT.get(key)
     if h is None:
-        init = [1.0, 0.5, -0.01, 0.0] if kind == 'ppo' else [1.0, 0.0, -0.01, 0.0]
+        init = [1.0, 0.5, -0.01, 0.0] if kind in ('ppo', 'happo') else [1.0, 0.0, -0.01, 0.0]
         h = torch.tensor(init, dtype=torch.float32, device=device)
         _PPO_HINT[key] = h
     return h
@@ -220,15 +220,16 @@ class PPOFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre, S, G, N,
-                clip_ratio, use_value_clip, dual_clip, kl_type, hint_kind, adv_stats=None):
+                clip_ratio, use_value_clip, dual_clip, kl_type, hint_kind, adv_stats=None, factor=None):
         dev = logit_new.device
         ctx.hint_kind = hint_kind
         ctx.adv_stats = adv_stats  # {mean, std + 1e-8} device floats or None; kept alive for the backward launch
+        ctx.factor = factor        # happo_error's per-sample factor (S,) or None; likewise
         out = torch.empty(8, dtype=torch.float32, device=dev)
         L = lib()
         tensors = (ptr(logit_new), ptr(logit_old), ptr(logit_pre), ptr(action), ptr(value_new), ptr(value_old),
                    ptr(adv), ptr(return_), ptr(weight))
-        cfg = (S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, ptr(adv_stats))
+        cfg = (S, G, N, clip_ratio, use_value_clip, dual_clip, kl_type, ptr(adv_stats), ptr(factor))
         ctx.fused = False
         want_grad = PPO_FUSED_BACKWARD and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         with on_device(dev):
@@ -279,7 +280,7 @@ class PPOFunction(torch.autograd.Function):
                 stream_ptr()
             )
         _lib.check(rc, 'b200rl_ppo_bwd')
-        return (grad_logit, grad_value) + (None, ) * 16
+        return (grad_logit, grad_value) + (None, ) * 17
 
 
 class GAEPPOFunction(torch.autograd.Function):

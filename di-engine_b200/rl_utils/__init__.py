@@ -2,6 +2,8 @@
 namedtuples, computed by the sm_100a kernels behind the C ABI of ``include/b200rl.h``."""
 from .a2c import a2c_data, a2c_error, a2c_loss
 from .fused import gae_ppo_error
+from .happo import (happo_data, happo_error, happo_info, happo_loss, happo_policy_data, happo_policy_error, happo_policy_loss,
+                    happo_value_data, happo_value_error)
 from .gae import gae, gae_data, gae_returns, gae_returns_out, shape_fn_gae
 from .ppo import (normalize_advantage, ppo_data, ppo_error, ppo_error_adv_norm, ppo_error_continuous, ppo_info, ppo_loss, ppo_policy_data, ppo_policy_error, ppo_policy_loss,
                   ppo_value_data, ppo_value_error, shape_fn_ppo)
@@ -25,11 +27,12 @@ HOT_PATH_FUNCTIONS = [
     'q_1step_td_error', 'v_1step_td_error', 'v_nstep_td_error', 'ppo_policy_error', 'ppo_value_error',
     'dist_1step_td_error', 'bdq_nstep_td_error', 'upgo_returns', 'tb_cross_entropy', 'ppo_error_continuous', 'a2c_error',
     'vtrace_error_continuous_action', 'qrdqn_nstep_td_error', 'iqn_nstep_td_error', 'fqf_nstep_td_error',
-    'compute_q_retraces'
+    'compute_q_retraces', 'happo_error', 'happo_policy_error', 'happo_value_error'
 ]
 HOT_PATH_TYPES = [
     'gae_data', 'ppo_data', 'ppo_loss', 'ppo_info', 'q_nstep_td_data', 'dist_nstep_td_data', 'td_lambda_data',
     'vtrace_data', 'vtrace_loss', 'q_1step_td_data', 'v_1step_td_data', 'v_nstep_td_data',
     'ppo_policy_data', 'ppo_policy_loss', 'ppo_value_data', 'dist_1step_td_data', 'a2c_data', 'a2c_loss',
-    'qrdqn_nstep_td_data', 'iqn_nstep_td_data', 'fqf_nstep_td_data'
+    'qrdqn_nstep_td_data', 'iqn_nstep_td_data', 'fqf_nstep_td_data',
+    'happo_data', 'happo_policy_data', 'happo_value_data', 'happo_loss', 'happo_policy_loss', 'happo_info'
 ]

@@ -80,7 +80,7 @@ def ppo_error_adv_norm(
     return _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, 'ppo', True, adv_stats)
 
 
-def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind, adv_norm=False, adv_stats=None):
+def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind, adv_norm=False, adv_stats=None, factor=None):
     assert dual_clip is None or dual_clip > 1.0, "dual_clip value must be greater than 1.0, but get value: {}".format(
         dual_clip
     )
@@ -129,9 +129,14 @@ def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind,
             stats = ops.f32c(ops.to_device(adv_stats.detach(), ad.device), 'adv_stats').reshape(-1)
             if stats.numel() != 2:
                 raise ValueError("adv_stats must hold two floats {mean, std + 1e-8}")
+    fac = None
+    if factor is not None:  # happo_error: (B, 1) -> squeeze(1) -> one factor per sample (happo.py:124-125)
+        fac = stage(factor.detach(), 'factor').reshape(-1)
+        if fac.numel() != S:
+            raise ValueError("happo_error: factor %s does not match adv %s" % (tuple(factor.shape), tuple(adv.shape)))
     p, v, e, k, out = ops.PPOFunction.apply(
         ln, vn, lo, act, vo, ad, rt, w, lp, S, G, N, float(clip_ratio), 1 if use_value_clip else 0,
-        float(dual_clip) if dual_clip is not None else 0.0, _KL_TYPES.get(kl_type, 1), _hint_kind, stats
+        float(dual_clip) if dual_clip is not None else 0.0, _KL_TYPES.get(kl_type, 1), _hint_kind, stats, fac
     )
     if LAZY_INFO:
         info = ppo_info(out[4], out[5])

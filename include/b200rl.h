@@ -88,12 +88,14 @@ B200RL_API int b200rl_impala_mask(const float* values, const float* rewards, con
  * value_new, value_old, adv, return_, weight(nullable): (S).  dual_clip <= 0 means None; kl_type 1|2|3 = 'k1'|'k2'|'k3'.
  * adv_stats (nullable): {mean, std + 1e-8} of the advantage batch as two device floats (b200rl_adv_stats); when given the
  * kernels use (adv - mean) / (std + 1e-8) -- PPOPolicy's advantage normalisation (ding/policy/ppo.py:304-306) -- on load.
+ * factor (nullable, (S)): happo_error's per-sample factor (ding/rl_utils/happo.py:124-130): min(surr1, surr2) is multiplied
+ * by it before the dual clip; null = ppo_error.
  * out[0..5] = policy_loss, value_loss, entropy_loss, kl_div, approx_kl, clipfrac  (out has room for 8 floats). */
 B200RL_API int b200rl_ppo_fwd(const float* logit_new, const float* logit_old, const float* logit_pretrained,
                    const long long* action, const float* value_new, const float* value_old, const float* adv,
                    const float* return_, const float* weight, long long S, long long G, long long N,
                    double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* adv_stats,
-                   float* out, float* workspace, size_t workspace_bytes, void* stream);
+                   const float* factor, float* out, float* workspace, size_t workspace_bytes, void* stream);
 /* gradients of  g_policy*policy_loss + g_value*value_loss + g_entropy*entropy_loss + g_kl*kl_div  w.r.t.
  * logit_new (S*G, N) and value_new (S); autograd tie rules of torch.min/max/clamp reproduced (ppo.py:208-216,:269-272).
  * g_used / g_hint (both nullable) belong to the fused forward below: when g_used is given and equals the four actual
@@ -103,7 +105,7 @@ B200RL_API int b200rl_ppo_bwd(const float* logit_new, const float* logit_old, co
                    const long long* action, const float* value_new, const float* value_old, const float* adv,
                    const float* return_, const float* weight, long long S, long long G, long long N,
                    double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* adv_stats,
-                   const float* g_policy, const float* g_value, const float* g_entropy, const float* g_kl,
+                   const float* factor, const float* g_policy, const float* g_value, const float* g_entropy, const float* g_kl,
                    const float* g_used, float* g_hint, float* grad_logit_new, float* grad_value_new, void* stream);
 /* Fused forward: the losses of b200rl_ppo_fwd AND the gradients of b200rl_ppo_bwd for the EXPECTED upstream gradients
  * g_expected[0..3] (policy, value, entropy, kl; device floats -- the loss weights of the training loop), in one pass
@@ -114,7 +116,7 @@ B200RL_API int b200rl_ppo_fwd_grad(const float* logit_new, const float* logit_ol
                         const long long* action, const float* value_new, const float* value_old, const float* adv,
                         const float* return_, const float* weight, long long S, long long G, long long N,
                         double clip_ratio, int use_value_clip, double dual_clip, int kl_type, const float* adv_stats,
-                        const float* g_expected, float* g_used, float* out, float* grad_logit_new,
+                        const float* factor, const float* g_expected, float* g_used, float* out, float* grad_logit_new,
                         float* grad_value_new, float* workspace, size_t workspace_bytes, void* stream);
 B200RL_API int b200rl_ppo_fused_supported(const float* logit_new, const float* logit_old, const float* logit_pretrained,
                                const long long* action, const float* value_new, const float* value_old,

@@ -819,3 +819,40 @@ def compute_q_retraces(q_values, v_pred, rewards, actions, weights, ratio, gamma
         q_retraces[idx] = rewards[idx] + gamma * weights[idx] * tmp
         tmp = ratio_gather[idx].clamp(max=1.0) * (q_retraces[idx] - q_gather[idx]) + v_pred[idx]
     return q_retraces
+
+
+def happo_error(logit_new, logit_old, action, value_new, value_old, adv, return_, weight=None, factor=None,
+                clip_ratio: float = 0.2, use_value_clip: bool = True, dual_clip: Optional[float] = None):
+    """happo.py:18-78 (= happo_policy_error :81-147 + happo_value_error :150-192): ppo_error whose selected surrogate is
+    multiplied by ``factor.squeeze(1)`` before the dual clip.  Returns (policy_loss, value_loss, entropy_loss, approx_kl,
+    clipfrac)."""
+    assert dual_clip is None or dual_clip > 1.0
+    w = torch.ones_like(adv) if weight is None else weight
+    lp_new_all = _log_softmax_rows(logit_new)
+    lp_new = _chosen(lp_new_all, action)
+    lp_old = _chosen(_log_softmax_rows(logit_old), action)
+    ent = _row_entropy(lp_new_all)
+    if ent.shape != w.shape:  # happo.py:114-115
+        ent = ent.mean(dim=1)
+    entropy_loss = (ent * w).mean()
+    ratio = torch.exp(lp_new - lp_old)
+    if ratio.shape != adv.shape:
+        ratio = ratio.mean(dim=1)
+    surr1 = ratio * adv
+    surr2 = ratio.clamp(1 - clip_ratio, 1 + clip_ratio) * adv
+    clip1 = torch.min(surr1, surr2) * factor.squeeze(1)  # happo.py:125
+    if dual_clip is not None:
+        clip2 = torch.max(clip1, dual_clip * adv)
+        policy_loss = -(torch.where(adv < 0, clip2, clip1) * w).mean()
+    else:
+        policy_loss = (-clip1 * w).mean()
+    with torch.no_grad():
+        approx_kl = (lp_old - lp_new).mean().item()
+        clipfrac = (ratio.gt(1 + clip_ratio) | ratio.lt(1 - clip_ratio)).float().mean().item()
+    wv = torch.ones_like(value_old) if weight is None else weight
+    if use_value_clip:
+        value_clip = value_old + (value_new - value_old).clamp(-clip_ratio, clip_ratio)
+        value_loss = 0.5 * (torch.max((return_ - value_new).pow(2), (return_ - value_clip).pow(2)) * wv).mean()
+    else:
+        value_loss = 0.5 * ((return_ - value_new).pow(2) * wv).mean()
+    return policy_loss, value_loss, entropy_loss, approx_kl, clipfrac

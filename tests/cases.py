@@ -39,6 +39,7 @@ GRAD_INPUTS = {
     'iqn': ['q'],
     'fqf': ['q'],
     'retrace': [],
+    'happo': ['logit_new', 'value_new'],
 }
 # upstream gradient for each returned loss head (distinct, non-trivial)
 LOSS_MIX = {
@@ -63,6 +64,7 @@ LOSS_MIX = {
     'qrdqn': [1.0],
     'iqn': [1.0],
     'fqf': [1.0],
+    'happo': [1.0, 0.5, -0.01],
 }
 
 
@@ -410,6 +412,14 @@ def vtc_case(seed, T, B, D, weight='none', **params):
     return 'vtc', t, params
 
 
+def happo_case(seed, B, N, weight='none', **params):
+    """ppo_case + the per-sample factor (B, 1) of happo_data (happo.py:12-14)"""
+    op, t, p = ppo_case(seed, B, N, weight=weight, **params)
+    t = OrderedDict((k, v) for k, v in t.items() if k != 'logit_pretrained')
+    t['factor'] = _rand(_g(seed + 7919), B, 1) * 1.5 + 0.25
+    return 'happo', t, p
+
+
 def retrace_case(seed, T, B, N, gamma=0.99):
     """tests/test_retrace.py:8-18"""
     g = _g(seed)
@@ -423,6 +433,7 @@ def retrace_case(seed, T, B, N, gamma=0.99):
     return 'retrace', t, dict(gamma=gamma)
 
 
+HAPPO_FIELDS = ('logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv', 'return_', 'weight', 'factor')
 _QF = ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done')
 QUANTILE_FIELDS = {'qrdqn': _QF + ('tau', 'weight'), 'iqn': _QF + ('replay_quantiles', 'weight'), 'fqf': _QF + ('quantiles_hats', 'weight')}
 
@@ -535,6 +546,10 @@ def build_cases():
     c['iqn_w_kappa'] = quantile_case(134, 'iqn', 5, 6, 32, 32, 2, weight='tensor', value_gamma='tensor', kappa=0.6)
     c['fqf_basic'] = quantile_case(135, 'fqf', 8, 4, 8, 8, 3)
     c['fqf_w_kappa'] = quantile_case(136, 'fqf', 5, 6, 32, 16, 4, weight='tensor', value_gamma='scalar', kappa=1.7)
+    # ---- HAPPO (tests/test_happo.py) -------------------------------------------------------------------------------------------
+    c['happo_basic'] = happo_case(150, 64, 6, clip_ratio=0.2)
+    c['happo_w_dc'] = happo_case(151, 33, 5, weight='tensor', dual_clip=3.0, clip_ratio=0.3)
+    c['happo_noclip'] = happo_case(152, 12, 40, use_value_clip=False)
     # ---- ACER Retrace targets (tests/test_retrace.py) ----------------------------------------------------------------------
     c['retrace_ref_test'] = retrace_case(140, 64, 32, 6)
     c['retrace_ragged'] = retrace_case(141, 13, 5, 3, gamma=0.9)
@@ -650,6 +665,14 @@ def run_api(api, op, tensors, params, device='cpu'):
         return res
     if op == 'retrace':
         res['out_q_retraces'] = _np(api.compute_q_retraces(*t.values(), **p))
+        return res
+    if op == 'happo':
+        loss, info = api.happo_error(api.happo_data(*[t[k] for k in HAPPO_FIELDS]), **p)
+        for k in ('policy_loss', 'value_loss', 'entropy_loss'):
+            res['out_' + k] = _np(getattr(loss, k))
+        res['out_approx_kl'] = np.float32(info.approx_kl)
+        res['out_clipfrac'] = np.float32(info.clipfrac)
+        _backward(op, list(loss), t, res)
         return res
     if op in ('qrdqn', 'iqn', 'fqf'):
         data = getattr(api, op + '_nstep_td_data')(*[t[k] for k in QUANTILE_FIELDS[op]])
@@ -834,6 +857,14 @@ def run_oracle(orc, op, tensors, params):
         return res
     if op == 'retrace':
         res['out_q_retraces'] = _np(orc.compute_q_retraces(*t.values(), **p))
+        return res
+    if op == 'happo':
+        out = orc.happo_error(*[t[k] for k in HAPPO_FIELDS], **p)
+        for k, v in zip(('policy_loss', 'value_loss', 'entropy_loss'), out[:3]):
+            res['out_' + k] = _np(v)
+        res['out_approx_kl'] = np.float32(out[3])
+        res['out_clipfrac'] = np.float32(out[4])
+        _backward(op, list(out[:3]), t, res)
         return res
     if op in ('qrdqn', 'iqn', 'fqf'):
         loss, per = getattr(orc, op + '_nstep_td_error')(*[t[k] for k in QUANTILE_FIELDS[op]], value_gamma=t.get('value_gamma'), **p)

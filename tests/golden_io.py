@@ -33,6 +33,7 @@ INPUT_ORDER = {
     'vtrace': ['target_output', 'behaviour_output', 'action', 'value', 'reward', 'weight'],
     'qrdqn': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'tau', 'weight', 'value_gamma'],
     'iqn': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'replay_quantiles', 'weight', 'value_gamma'],
+    'happo': ['logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv', 'return_', 'weight', 'factor'],
     'retrace': ['q_values', 'v_pred', 'rewards', 'actions', 'weights', 'ratio'],
     'fqf': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'quantiles_hats', 'weight', 'value_gamma'],
 }

@@ -65,6 +65,8 @@ BIG = {
     'vtrace_E': lambda: cases.vtrace_case(104, 64, 8192, 6, gamma=0.99, lambda_=0.95),
     'vtrace_ragged': lambda: cases.vtrace_case(121, 130, 333, 7, weight='tensor', rho_clip_ratio=0.9),
     'vtrace_N100': lambda: cases.vtrace_case(122, 8, 16, 100),
+    'happo_big': lambda: cases.happo_case(125, 128 * 512 + 37, 6, weight='tensor', dual_clip=3.0),
+    'happo_N40': lambda: cases.happo_case(126, 3000, 40, weight='tensor'),
     'retrace_E': lambda: cases.retrace_case(123, 64, 8192, 6),
     'retrace_long': lambda: cases.retrace_case(124, 1003, 130, 18, gamma=0.997),
 }

@@ -239,6 +239,7 @@ EXPECTED_CALLS = {
     'iqn': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
     'fqf': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
     'retrace': ['b200rl_q_retraces'],
+    'happo': ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad', 'b200rl_ppo_bwd'],
 }
 
 

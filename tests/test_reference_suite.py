@@ -10,7 +10,7 @@
 Ported from ding/rl_utils/tests/test_gae.py, test_ppo.py (discrete, continuous, shape_fn), test_a2c.py (discrete), test_td.py (the operators on this
 path: q_nstep, q_nstep_ngu, bdq_nstep, q_1step_compatible, dist_1step, dist_1step_compatible, dist_1step multi agent,
 dist_nstep, dist_nstep multi agent, rescale, rescale_ngu, qrdqn_nstep, iqn_nstep, fqf_nstep, td_lambda, v_1step, v_1step multi agent, v_nstep, the four shape_fn
-tests), test_vtrace.py (discrete), test_retrace.py, test_upgo.py and test_value_rescale.py.  The reference draws unseeded random inputs; the
+tests), test_vtrace.py (discrete), test_happo.py (discrete), test_retrace.py, test_upgo.py and test_value_rescale.py.  The reference draws unseeded random inputs; the
 ports seed them (so the three implementations see identical bits) and keep every assertion.
 """
 import contextlib
@@ -188,6 +188,51 @@ def _ppo_body(api, dev, rec, use_value_clip, dual_clip, weighted):
 @pytest.mark.parametrize('weighted', [False, True])
 def test_ppo(impl, use_value_clip, dual_clip, weighted):
     _run(_ppo_body, impl, use_value_clip, dual_clip, weighted)
+
+
+def _happo_body(api, dev, rec, use_value_clip, dual_clip, weighted):
+    g = _gen(33)
+    B, N = 4, 32  # tests/test_happo.py:27-45
+    weight = (torch.rand(4, generator=g) + 1).to(dev) if weighted else None
+    factor = torch.rand(4, 1, generator=g).to(dev)
+    logit_new = torch.randn(B, N, generator=g).to(dev).requires_grad_(True)
+    logit_old = logit_new.detach() + torch.rand(B, N, generator=g).to(dev) * 0.1
+    action = torch.randint(0, N, size=(B, ), generator=g).to(dev)
+    value_new = torch.randn(B, generator=g).to(dev).requires_grad_(True)
+    value_old = value_new.detach() + torch.rand(B, generator=g).to(dev) * 0.1
+    adv = torch.rand(B, generator=g).to(dev)
+    return_ = (torch.randn(B, generator=g) * 2).to(dev)
+    data = api.happo_data(logit_new, logit_old, action, value_new, value_old, adv, return_, weight, factor)
+    loss, info = api.happo_error(data, use_value_clip=use_value_clip, dual_clip=dual_clip)
+    assert all([l.shape == tuple() for l in loss])
+    assert all([np.isscalar(i) for i in info])
+    assert logit_new.grad is None
+    assert value_new.grad is None
+    total_loss = sum(loss)
+    total_loss.backward()
+    assert isinstance(logit_new.grad, torch.Tensor)
+    assert isinstance(value_new.grad, torch.Tensor)
+    for k, v in zip(loss._fields, loss):
+        rec.put(k, v)
+    rec.put('approx_kl', info.approx_kl)
+    rec.put('clipfrac', info.clipfrac)
+    rec.put('grad_logit', logit_new.grad)
+    rec.put('grad_value', value_new.grad)
+    # the two halves, as HAPPOPolicy could call them (happo.py:81,150)
+    ln2 = logit_new.detach().clone().requires_grad_(True)
+    pl, pinfo = api.happo_policy_error(api.happo_policy_data(ln2, logit_old, action, adv, weight, factor), dual_clip=dual_clip)
+    vl = api.happo_value_error(api.happo_value_data(value_new.detach(), value_old, return_, weight),
+                               use_value_clip=use_value_clip)
+    rec.put('half_policy', pl.policy_loss)
+    rec.put('half_entropy', pl.entropy_loss)
+    rec.put('half_value', vl)
+
+
+@pytest.mark.parametrize('use_value_clip', [True, False])
+@pytest.mark.parametrize('dual_clip', [None, 5.0])
+@pytest.mark.parametrize('weighted', [False, True])
+def test_happo(impl, use_value_clip, dual_clip, weighted):
+    _run(_happo_body, impl, use_value_clip, dual_clip, weighted)
 
 
 def _mappo_body(api, dev, rec):
