@@ -308,7 +308,7 @@ class GAEPPOFunction(torch.autograd.Function):
             )
         _lib.check(rc, 'b200rl_gae_ppo_fwd_grad')
         ctx.save_for_backward(logit_new, value_new, logit_old, action, value_old, adv, return_, weight, logit_pre)
-        ctx.cfg = (T * B, 1, N, clip_ratio, use_value_clip, dual_clip, kl_type, None)
+        ctx.cfg = (T * B, 1, N, clip_ratio, use_value_clip, dual_clip, kl_type, None, None)  # no adv_stats, no factor
         ctx.fused = want_grad
         ctx.spec = (grad_logit, grad_value, g_used)
         ctx.bwd_calls = 0

@@ -256,6 +256,21 @@ def test_marshalling_dry_run(dry, name):
         assert 'grad_' + k in res and res['grad_' + k].shape == tuple(tensors[k].shape)
 
 
+def test_gae_ppo_error_dry_run_forward_and_backward(dry):
+    """the one-launch step through the public API: every ctypes call (forward, verification) marshals to its prototype"""
+    T, B, N = 8, 16, 6
+    _, g, _ = cases.gae_case(50, T, B)
+    _, t, _ = cases.ppo_case(51, T * B, N)
+    tt = cases.prepare('ppo', t)
+    gd = b2.gae_data(g['value'], g['next_value'], g['reward'], g['done'], g['traj_flag'])
+    pd = b2.ppo_data(tt['logit_new'], tt['logit_old'], tt['action'], tt['value_new'], tt['value_old'], None, tt['return_'], None,
+                     None)
+    adv, loss, info = b2.gae_ppo_error(gd, pd, 0.99, 0.95, 0.2, True, None)
+    (loss.policy_loss + 0.5 * loss.value_loss - 0.01 * loss.entropy_loss).backward()
+    assert tt['logit_new'].grad is not None and tt['value_new'].grad is not None
+    assert dry.calls[-1] == 'b200rl_ppo_bwd', dry.calls
+
+
 def test_custom_criterion_and_transforms_dry_run(dry):
     op, t, p = cases.qntd_case(1, 8, 4, 3, weight='tensor')
     t = cases.prepare(op, t)
