@@ -60,6 +60,11 @@ PROTOTYPES = {
                                        P, P, c_size_t, P],
     "b200rl_gae_ppo_set_impl": [I],
     "b200rl_vtrace_set_impl": [I],
+    "b200rl_acer_policy_fwd": [P, P, P, P, P, P, LL, LL, D, P, P, P],
+    "b200rl_acer_policy_bwd": [P, P, P, P, P, P, P, P, LL, LL, D, P, P],
+    "b200rl_acer_value_fwd": [P, P, P, LL, LL, P, P],
+    "b200rl_acer_value_bwd": [P, P, P, P, LL, LL, P, P],
+    "b200rl_acer_trust_region": [P, P, LL, LL, D, P, P],
     "b200rl_q_retraces": [P, P, P, P, P, P, LL, LL, LL, D, P, P],
     "b200rl_quantile_td_fwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, LL, LL, LL, D, LL, LL, LL, LL, LL, LL, LL, LL, I, D, P, P,
                                P, P, P, c_size_t, P],

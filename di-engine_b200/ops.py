@@ -406,6 +406,78 @@ class QNStepTDFunction(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# ACER heads (csrc/acer.cu): un-reduced per-transition losses, plain forward / backward launches
+# ----------------------------------------------------------------------------------------------------------------
+class AcerPolicyFunction(torch.autograd.Function):
+    """(actor_loss, bias_correction_loss), each (M,); differentiable w.r.t. target_logit only (acer.py:44-56)."""
+
+    @staticmethod
+    def forward(ctx, target_logit, q_values, q_retraces, v_pred, actions, ratio, M, N, c_clip_ratio):
+        dev = target_logit.device
+        actor = torch.empty(M, dtype=torch.float32, device=dev)
+        bias = torch.empty(M, dtype=torch.float32, device=dev)
+        with on_device(dev):
+            rc = lib().b200rl_acer_policy_fwd(ptr(q_values), ptr(q_retraces), ptr(v_pred), ptr(target_logit), ptr(actions),
+                                              ptr(ratio), M, N, c_clip_ratio, ptr(actor), ptr(bias), stream_ptr())
+        _lib.check(rc, 'b200rl_acer_policy_fwd')
+        ctx.save_for_backward(target_logit, q_values, q_retraces, v_pred, actions, ratio)
+        ctx.cfg = (M, N, c_clip_ratio)
+        ctx.set_materialize_grads(False)
+        return actor, bias
+
+    @staticmethod
+    def backward(ctx, g_actor, g_bias):
+        if g_actor is None and g_bias is None:
+            return (None, ) * 9
+        target_logit, q_values, q_retraces, v_pred, actions, ratio = ctx.saved_tensors
+        M, N, c = ctx.cfg
+        ga = f32c(g_actor) if g_actor is not None else None
+        gb = f32c(g_bias) if g_bias is not None else None
+        grad = torch.empty_like(target_logit)
+        with on_device(target_logit.device):
+            rc = lib().b200rl_acer_policy_bwd(ptr(q_values), ptr(q_retraces), ptr(v_pred), ptr(target_logit), ptr(actions),
+                                              ptr(ratio), ptr(ga), ptr(gb), M, N, c, ptr(grad), stream_ptr())
+        _lib.check(rc, 'b200rl_acer_policy_bwd')
+        return (grad, ) + (None, ) * 8
+
+
+class AcerValueFunction(torch.autograd.Function):
+    """critic_loss (M,) = 0.5 (q_retraces - q_values[a])^2; differentiable w.r.t. q_values (acer.py:81-82)."""
+
+    @staticmethod
+    def forward(ctx, q_values, q_retraces, actions, M, N):
+        loss = torch.empty(M, dtype=torch.float32, device=q_values.device)
+        with on_device(q_values.device):
+            rc = lib().b200rl_acer_value_fwd(ptr(q_values), ptr(q_retraces), ptr(actions), M, N, ptr(loss), stream_ptr())
+        _lib.check(rc, 'b200rl_acer_value_fwd')
+        ctx.save_for_backward(q_values, q_retraces, actions)
+        ctx.cfg = (M, N)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        q_values, q_retraces, actions = ctx.saved_tensors
+        M, N = ctx.cfg
+        gg = f32c(g)
+        grad = torch.empty_like(q_values)
+        with on_device(q_values.device):
+            rc = lib().b200rl_acer_value_bwd(ptr(q_values), ptr(q_retraces), ptr(actions), ptr(gg), M, N, ptr(grad),
+                                             stream_ptr())
+        _lib.check(rc, 'b200rl_acer_value_bwd')
+        return grad, None, None, None, None
+
+
+def acer_trust_region_(grad, avg_logit, delta):
+    N = grad.shape[-1]
+    M = grad.numel() // N
+    out = torch.empty_like(grad)
+    with on_device(grad.device):
+        rc = lib().b200rl_acer_trust_region(ptr(grad), ptr(avg_logit), M, N, float(delta), ptr(out), stream_ptr())
+    _lib.check(rc, 'b200rl_acer_trust_region')
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # quantile-regression n-step TD (QR-DQN / IQN / FQF)
 # ----------------------------------------------------------------------------------------------------------------
 class QuantileTDFunction(torch.autograd.Function):

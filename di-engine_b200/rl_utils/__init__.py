@@ -1,6 +1,7 @@
 """Mirror of the hot-path part of ``ding.rl_utils`` (ding/rl_utils/__init__.py:1-27): identical names, signatures and
 namedtuples, computed by the sm_100a kernels behind the C ABI of ``include/b200rl.h``."""
 from .a2c import a2c_data, a2c_error, a2c_loss
+from .acer import acer_policy_error, acer_trust_region_update, acer_value_error
 from .fused import gae_ppo_error
 from .happo import (happo_data, happo_error, happo_info, happo_loss, happo_policy_data, happo_policy_error, happo_policy_loss,
                     happo_value_data, happo_value_error)
@@ -27,7 +28,8 @@ HOT_PATH_FUNCTIONS = [
     'q_1step_td_error', 'v_1step_td_error', 'v_nstep_td_error', 'ppo_policy_error', 'ppo_value_error',
     'dist_1step_td_error', 'bdq_nstep_td_error', 'upgo_returns', 'tb_cross_entropy', 'ppo_error_continuous', 'a2c_error',
     'vtrace_error_continuous_action', 'qrdqn_nstep_td_error', 'iqn_nstep_td_error', 'fqf_nstep_td_error',
-    'compute_q_retraces', 'happo_error', 'happo_policy_error', 'happo_value_error'
+    'compute_q_retraces', 'happo_error', 'happo_policy_error', 'happo_value_error',
+    'acer_policy_error', 'acer_value_error', 'acer_trust_region_update'
 ]
 HOT_PATH_TYPES = [
     'gae_data', 'ppo_data', 'ppo_loss', 'ppo_info', 'q_nstep_td_data', 'dist_nstep_td_data', 'td_lambda_data',

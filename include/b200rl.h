@@ -276,6 +276,25 @@ B200RL_API int b200rl_q_retraces(const float* q_values, const float* v_pred, con
                       const float* weights, const float* ratio, long long T, long long B, long long N, double gamma,
                       float* q_retraces, void* stream);
 
+/* ---- ACER heads: ding/rl_utils/acer.py:8-57 (policy), :60-83 (value), :86-124 (trust region) -- csrc/acer.cu ---------------
+ * M = T * B transitions, un-reduced per-transition outputs (ACERPolicy weights and sums them itself, policy/acer.py:247-270).
+ * q_values, target_logit (= log pi), ratio: (M, N); q_retraces, v_pred, actor_loss, bias_correction_loss, critic_loss: (M);
+ * actions (M) int64.  Gradients: policy -> target_logit (g_actor / g_bias: upstream (M), nullable = 0); value -> q_values.
+ * acer_trust_region: out = g - max(((g . k) - delta) / (k . k), 0) * k with k = exp(avg_logit), row by row. */
+B200RL_API int b200rl_acer_policy_fwd(const float* q_values, const float* q_retraces, const float* v_pred,
+                           const float* target_logit, const long long* actions, const float* ratio, long long M, long long N,
+                           double c_clip_ratio, float* actor_loss, float* bias_correction_loss, void* stream);
+B200RL_API int b200rl_acer_policy_bwd(const float* q_values, const float* q_retraces, const float* v_pred,
+                           const float* target_logit, const long long* actions, const float* ratio, const float* g_actor,
+                           const float* g_bias, long long M, long long N, double c_clip_ratio, float* grad_target_logit,
+                           void* stream);
+B200RL_API int b200rl_acer_value_fwd(const float* q_values, const float* q_retraces, const long long* actions, long long M,
+                          long long N, float* critic_loss, void* stream);
+B200RL_API int b200rl_acer_value_bwd(const float* q_values, const float* q_retraces, const long long* actions,
+                          const float* g_loss, long long M, long long N, float* grad_q_values, void* stream);
+B200RL_API int b200rl_acer_trust_region(const float* actor_gradient, const float* avg_logit, long long M, long long N,
+                             double trust_region_value, float* out, void* stream);
+
 /* ---- quantile-regression n-step TD: qrdqn_nstep_td_error (ding/rl_utils/td.py:1098-1166, form 0), iqn_nstep_td_error
  * (:1253-1346, form 1), fqf_nstep_td_error (:1359-1436, form 2) -- csrc/quantile.cu, one kernel, the layouts are strides:
  * theta_i = q[b*q_sb + i*q_si + action_b*q_sa] (i < n_tau), theta'_j from next_n_q likewise (j < n_tau_prime),

@@ -39,6 +39,7 @@ FILES = [
     "ding/rl_utils/a2c.py",            # sibling head
     "ding/rl_utils/retrace.py",        # ACER's return operator
     "ding/rl_utils/happo.py",          # HAPPO heads (ppo_error with the per-sample factor)
+    "ding/rl_utils/acer.py",           # ACER heads
 ]
 
 

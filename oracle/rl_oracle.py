@@ -856,3 +856,30 @@ def happo_error(logit_new, logit_old, action, value_new, value_old, adv, return_
     else:
         value_loss = 0.5 * ((return_ - value_new).pow(2) * wv).mean()
     return policy_loss, value_loss, entropy_loss, approx_kl, clipfrac
+
+
+def acer_policy_error(q_values, q_retraces, v_pred, target_logit, actions, ratio, c_clip_ratio: float = 10.0):
+    """acer.py:8-57 -> (actor_loss, bias_correction_loss), both (T, B, 1)."""
+    actions = actions.unsqueeze(-1)
+    with torch.no_grad():
+        advantage_retraces = q_retraces - v_pred
+        advantage_native = q_values - v_pred
+    actor_loss = ratio.gather(-1, actions).clamp(max=c_clip_ratio) * advantage_retraces * target_logit.gather(-1, actions)
+    bias = (1.0 - c_clip_ratio / (ratio + 1e-8)).clamp(min=0.0) * torch.exp(target_logit).detach() * advantage_native * \
+        target_logit
+    return actor_loss, bias.sum(-1, keepdim=True)
+
+
+def acer_value_error(q_values, q_retraces, actions):
+    """acer.py:60-83."""
+    return 0.5 * (q_retraces - q_values.gather(-1, actions.unsqueeze(-1))).pow(2)
+
+
+def acer_trust_region_update(actor_gradients, target_logit, avg_logit, trust_region_value):
+    """acer.py:86-124."""
+    with torch.no_grad():
+        k = torch.exp(avg_logit)
+    g = actor_gradients[0]
+    scale = g.mul(k).sum(-1, keepdim=True) - trust_region_value
+    scale = torch.div(scale, k.mul(k).sum(-1, keepdim=True)).clamp(min=0.0)
+    return [g - scale * k]

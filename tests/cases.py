@@ -40,6 +40,7 @@ GRAD_INPUTS = {
     'fqf': ['q'],
     'retrace': [],
     'happo': ['logit_new', 'value_new'],
+    'acer': ['target_logit', 'q_values'],
 }
 # upstream gradient for each returned loss head (distinct, non-trivial)
 LOSS_MIX = {
@@ -420,6 +421,22 @@ def happo_case(seed, B, N, weight='none', **params):
     return 'happo', t, p
 
 
+def acer_case(seed, T, B, N, c_clip_ratio=10.0, trust_region_value=1.0):
+    """the operands of ACERPolicy._forward_learn (policy/acer.py:215-260): log-softmax policy outputs, Retrace targets, ratios
+    on both sides of the truncation, an actor gradient for the trust-region projection"""
+    g = _g(seed)
+    t = OrderedDict()
+    t['q_values'] = _randn(g, T, B, N)
+    t['q_retraces'] = _randn(g, T, B, 1)
+    t['v_pred'] = _randn(g, T, B, 1)
+    t['target_logit'] = torch.log_softmax(_randn(g, T, B, N), dim=-1)
+    t['actions'] = _randint(g, N, T, B)
+    t['ratio'] = _rand(g, T, B, N) * 3.0 * c_clip_ratio / 2.0  # both sides of 1 - c / ratio > 0
+    t['avg_logit'] = torch.log_softmax(_randn(g, T, B, N), dim=-1)
+    t['actor_gradient'] = _randn(g, T, B, N)
+    return 'acer', t, dict(c_clip_ratio=c_clip_ratio, trust_region_value=trust_region_value)
+
+
 def retrace_case(seed, T, B, N, gamma=0.99):
     """tests/test_retrace.py:8-18"""
     g = _g(seed)
@@ -546,6 +563,9 @@ def build_cases():
     c['iqn_w_kappa'] = quantile_case(134, 'iqn', 5, 6, 32, 32, 2, weight='tensor', value_gamma='tensor', kappa=0.6)
     c['fqf_basic'] = quantile_case(135, 'fqf', 8, 4, 8, 8, 3)
     c['fqf_w_kappa'] = quantile_case(136, 'fqf', 5, 6, 32, 16, 4, weight='tensor', value_gamma='scalar', kappa=1.7)
+    # ---- ACER heads (no reference unit test; operands as policy/acer.py builds them) -------------------------------------------
+    c['acer_small'] = acer_case(160, 5, 4, 6, c_clip_ratio=2.0, trust_region_value=0.2)
+    c['acer_default'] = acer_case(161, 16, 9, 3)
     # ---- HAPPO (tests/test_happo.py) -------------------------------------------------------------------------------------------
     c['happo_basic'] = happo_case(150, 64, 6, clip_ratio=0.2)
     c['happo_w_dc'] = happo_case(151, 33, 5, weight='tensor', dual_clip=3.0, clip_ratio=0.3)
@@ -665,6 +685,18 @@ def run_api(api, op, tensors, params, device='cpu'):
         return res
     if op == 'retrace':
         res['out_q_retraces'] = _np(api.compute_q_retraces(*t.values(), **p))
+        return res
+    if op == 'acer':
+        actor, bias = api.acer_policy_error(t['q_values'].detach(), t['q_retraces'], t['v_pred'], t['target_logit'], t['actions'],
+                                            t['ratio'], p['c_clip_ratio'])
+        critic = api.acer_value_error(t['q_values'], t['q_retraces'], t['actions'])
+        res['out_actor_loss'], res['out_bias_correction_loss'], res['out_critic_loss'] = _np(actor), _np(bias), _np(critic)
+        w = torch.linspace(0.5, 1.5, actor.numel(), device=actor.device).reshape(actor.shape)
+        ((actor * w).sum() + 0.3 * (bias * w.flip(0)).sum()).backward()
+        (critic * w).sum().backward()
+        res['grad_target_logit'], res['grad_q_values'] = _np(t['target_logit'].grad), _np(t['q_values'].grad)
+        res['out_trust_region'] = _np(api.acer_trust_region_update([t['actor_gradient']], t['target_logit'].detach(),
+                                                                   t['avg_logit'], p['trust_region_value'])[0])
         return res
     if op == 'happo':
         loss, info = api.happo_error(api.happo_data(*[t[k] for k in HAPPO_FIELDS]), **p)
@@ -857,6 +889,18 @@ def run_oracle(orc, op, tensors, params):
         return res
     if op == 'retrace':
         res['out_q_retraces'] = _np(orc.compute_q_retraces(*t.values(), **p))
+        return res
+    if op == 'acer':
+        actor, bias = orc.acer_policy_error(t['q_values'].detach(), t['q_retraces'], t['v_pred'], t['target_logit'], t['actions'],
+                                            t['ratio'], p['c_clip_ratio'])
+        critic = orc.acer_value_error(t['q_values'], t['q_retraces'], t['actions'])
+        res['out_actor_loss'], res['out_bias_correction_loss'], res['out_critic_loss'] = _np(actor), _np(bias), _np(critic)
+        w = torch.linspace(0.5, 1.5, actor.numel(), device=actor.device).reshape(actor.shape)
+        ((actor * w).sum() + 0.3 * (bias * w.flip(0)).sum()).backward()
+        (critic * w).sum().backward()
+        res['grad_target_logit'], res['grad_q_values'] = _np(t['target_logit'].grad), _np(t['q_values'].grad)
+        res['out_trust_region'] = _np(orc.acer_trust_region_update([t['actor_gradient']], t['target_logit'].detach(),
+                                                                   t['avg_logit'], p['trust_region_value'])[0])
         return res
     if op == 'happo':
         out = orc.happo_error(*[t[k] for k in HAPPO_FIELDS], **p)

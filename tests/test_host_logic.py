@@ -239,6 +239,8 @@ EXPECTED_CALLS = {
     'iqn': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
     'fqf': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
     'retrace': ['b200rl_q_retraces'],
+    'acer': ['b200rl_acer_policy_fwd', 'b200rl_acer_value_fwd', 'b200rl_acer_policy_bwd', 'b200rl_acer_value_bwd',
+             'b200rl_acer_trust_region'],
     'happo': ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad', 'b200rl_ppo_bwd'],
 }
 
