@@ -56,7 +56,7 @@ PROTOTYPES = {
                                    P, P, I, I, P, P, P, c_size_t, P],
     "b200rl_p2p_drain_mean": [P, I, I, I, P, P, P],
     "b200rl_a2c_fwd_grad": [P, P, P, P, P, P, LL, LL, P, I, P, P, P, P, P, P, P, P, P, c_size_t, P],
-    "b200rl_ppo_continuous_fwd_grad": [P, P, P, P, P, P, P, P, P, P, P, P, LL, LL, D, I, D, I, P, I, P, P, P, P, P, P, P, P, P,
+    "b200rl_ppo_continuous_fwd_grad": [P, P, P, P, P, P, P, P, P, P, P, P, P, LL, LL, D, I, D, I, P, I, P, P, P, P, P, P, P, P, P,
                                        P, P, c_size_t, P],
     "b200rl_gae_ppo_set_impl": [I],
     "b200rl_vtrace_set_impl": [I],
@@ -65,6 +65,7 @@ PROTOTYPES = {
     "b200rl_acer_value_fwd": [P, P, P, LL, LL, P, P],
     "b200rl_acer_value_bwd": [P, P, P, P, LL, LL, P, P],
     "b200rl_acer_trust_region": [P, P, LL, LL, D, P, P],
+    "b200rl_ppg_bc_fwd": [P, P, P, LL, LL, P, P, P, c_size_t, P],
     "b200rl_q_retraces": [P, P, P, P, P, P, LL, LL, LL, D, P, P],
     "b200rl_quantile_td_fwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, LL, LL, LL, D, LL, LL, LL, LL, LL, LL, LL, LL, I, D, P, P,
                                P, P, P, c_size_t, P],

@@ -118,6 +118,9 @@ struct PpocArgs {
     const float* adv;
     const float* ret;
     const float* weight;  // nullable
+    // nullable (S): happo_error_continuous (ding/rl_utils/happo.py:195-284): min(surr1, surr2) * factor before the dual clip,
+    // and the entropy / approx_kl means run over the S * D per-dimension terms (Normal instead of Independent(Normal))
+    const float* factor;
     long long S;
     int D;
     float clip, clip_lo, clip_hi, dual_clip;
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(HD_NT) ppoc_kernel(PpocArgs a, float* ws) {
     if (head_upstream<4>(a.h, g, has_pre ? 0u : 8u)) return;  // no pretrained policy: the kl term has no gradient to compare
     if (!has_pre) g[3] = 0.f;
     const float inv_s = 1.f / (float)a.S;
+    const float ent_scale = a.factor ? 1.f / (float)a.D : 1.f;  // happo: mean over S * D elements
     float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (long long s = (long long)blockIdx.x * HD_NT + threadIdx.x; s < a.S; s += (long long)gridDim.x * HD_NT) {
         const long long o = s * a.D;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(HD_NT) ppoc_kernel(PpocArgs a, float* ws) {
         for (int d = 0; d < a.D; ++d) ent += kHalfPlusHalfLog2Pi + logf(sg[d]);
         const float ratio = expf(lp_n - lp_o);
         float dsel, dterm, dk = 0.f, klv = 0.f;
-        const float sel = surrogate(ratio, a.adv[s], a.clip_lo, a.clip_hi, a.dual_clip, dsel, true);
+        const float sel = surrogate(ratio, a.adv[s], a.clip_lo, a.clip_hi, a.dual_clip, dsel, true, a.factor ? a.factor[s] : 1.f);
         const float vt = value_term(a.value_new[s], a.value_old[s], a.ret[s], a.clip, a.use_value_clip, dterm);
         if (has_pre) klv = kl_term(lp_n - normal_logp(a.mu_pre + o, a.sigma_pre + o, ac, a.D), a.kl_type, dk);
         acc[0] -= sel * w;
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(HD_NT) ppoc_kernel(PpocArgs a, float* ws) {
         acc[5] += (ratio > a.clip_hi || ratio < a.clip_lo) ? 1.f : 0.f;
         if (grads) {
             const float c_lp = g[0] * (-w * inv_s) * dsel * ratio + g[3] * dk * inv_s;  // d total / d logp_new
-            const float c_ent = g[2] * w * inv_s;                                         // d total / d entropy
+            const float c_ent = g[2] * w * inv_s * ent_scale;                             // d total / d entropy
             for (int d = 0; d < a.D; ++d) {
                 const float sd = sg[d], df = ac[d] - mu[d], inv = 1.f / sd;
                 a.grad_mu[o + d] = c_lp * df * inv * inv;
@@ -181,10 +185,45 @@ __global__ void __launch_bounds__(HD_NT) ppoc_kernel(PpocArgs a, float* ws) {
     }
     if (a.h.verify) return;
     const double is = 1.0 / (double)a.S;
+    const double per_dim = a.factor ? 1.0 / (double)a.D : 1.0;
     grid_sum_fx<6, HD_NT>(acc, ws, [&](int k, double t) {
-        const double sc = k == 1 ? 0.5 * is : (k == 3 && !has_pre ? 0.0 : is);
+        double sc = k == 1 ? 0.5 * is : (k == 3 && !has_pre ? 0.0 : is);
+        if (k == 2 || k == 4) sc *= per_dim;
         a.out[k] = (float)(t * sc);
     });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ppg_joint_error's behavioural-cloning term (ding/rl_utils/ppg.py:62-67): F.kl_div(logp_new, logp_old, 'batchmean') with the
+// LOG-probability of the old policy passed as the (non-log) target, exactly as the reference does:
+//   loss = (1/B) sum_b [ xlogy(t_b, t_b) - t_b * x_b ],   x_b = log pi_new(a_b), t_b = log pi_old(a_b) <= 0
+// xlogy(t, t) is NaN for t < 0, so the VALUE is NaN whenever any old log-probability is negative (as in the reference); the
+// GRADIENT d loss / d x_b = -t_b / B is finite and is what PPG trains on.  dlogit_unit = that gradient through log-softmax.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HD_NT) ppg_bc_kernel(const float* __restrict__ logit_new, const float* __restrict__ logit_old,
+                                                       const long long* __restrict__ action, long long B, int N,
+                                                       float* __restrict__ loss, float* __restrict__ dlogit_unit, float* ws) {
+    pdl_prologue();
+    float acc[1] = {0.f};
+    const float inv_b = 1.f / (float)B;
+    for (long long b = (long long)blockIdx.x * HD_NT + threadIdx.x; b < B; b += (long long)gridDim.x * HD_NT) {
+        const float* zn = logit_new + b * N;
+        const float* zo = logit_old + b * N;
+        const long long a = action[b];
+        float mn = kF32Min, mo = kF32Min;
+        for (int j = 0; j < N; ++j) { mn = fmaxf(mn, zn[j]); mo = fmaxf(mo, zo[j]); }
+        float sn = 0.f, so = 0.f;
+        for (int j = 0; j < N; ++j) { sn += expf(zn[j] - mn); so += expf(zo[j] - mo); }
+        const float lse_n = mn + logf(sn);
+        const float x = zn[a] - lse_n, t = (zo[a] - mo) - logf(so);
+        acc[0] += (t == 0.f ? 0.f : t * logf(t)) - t * x;  // xlogy(t, t) - t * x
+        if (dlogit_unit) {
+            const float c = -t * inv_b;
+            float* g = dlogit_unit + b * N;
+            for (int j = 0; j < N; ++j) g[j] = c * ((j == a ? 1.f : 0.f) - expf(zn[j] - lse_n));
+        }
+    }
+    grid_sum_fx<1, HD_NT>(acc, ws, [=](int, double tot) { *loss = (float)(tot * (double)inv_b); });
 }
 
 static int head_grid(long long S) {
@@ -218,8 +257,9 @@ extern "C" int b200rl_a2c_fwd_grad(const float* logit, const long long* action, 
 extern "C" int b200rl_ppo_continuous_fwd_grad(
     const float* mu_new, const float* sigma_new, const float* mu_old, const float* sigma_old, const float* mu_pretrained,
     const float* sigma_pretrained, const float* action, const float* value_new, const float* value_old, const float* adv,
-    const float* return_, const float* weight, long long S, long long D, double clip_ratio, int use_value_clip,
-    double dual_clip, int kl_type, const float* g_expected, int verify, const float* g_policy, const float* g_value,
+    const float* return_, const float* weight, const float* factor, long long S, long long D, double clip_ratio,
+    int use_value_clip, double dual_clip, int kl_type, const float* g_expected, int verify, const float* g_policy,
+    const float* g_value,
     const float* g_entropy, const float* g_kl, float* g_used, float* g_hint, float* out6, float* grad_mu, float* grad_sigma,
     float* grad_value, float* workspace, size_t workspace_bytes, void* stream) {
     if (S < 1 || D < 1 || !mu_new || !sigma_new || !mu_old || !sigma_old || !action || !value_new || !value_old || !adv ||
@@ -232,12 +272,22 @@ extern "C" int b200rl_ppo_continuous_fwd_grad(
     PpocArgs a{};
     a.mu_new = mu_new; a.sigma_new = sigma_new; a.mu_old = mu_old; a.sigma_old = sigma_old; a.mu_pre = mu_pretrained;
     a.sigma_pre = sigma_pretrained; a.action = action; a.value_new = value_new; a.value_old = value_old; a.adv = adv;
-    a.ret = return_; a.weight = weight; a.S = S; a.D = (int)D; a.clip = (float)clip_ratio;
+    a.ret = return_; a.weight = weight; a.factor = factor; a.S = S; a.D = (int)D; a.clip = (float)clip_ratio;
     a.clip_lo = (float)(1.0 - clip_ratio); a.clip_hi = (float)(1.0 + clip_ratio); a.dual_clip = (float)dual_clip;
     a.use_value_clip = use_value_clip; a.kl_type = kl_type; a.out = out6; a.grad_mu = grad_mu; a.grad_sigma = grad_sigma;
     a.grad_value = grad_value;
     a.h.g_expected = g_expected; a.h.g_actual[0] = g_policy; a.h.g_actual[1] = g_value; a.h.g_actual[2] = g_entropy;
     a.h.g_actual[3] = g_kl; a.h.g_used = g_used; a.h.g_hint = g_hint; a.h.verify = verify;
     (void)launch_k(ppoc_kernel, head_grid(S), HD_NT, 0, (cudaStream_t)stream, a, workspace);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int b200rl_ppg_bc_fwd(const float* logit_new, const float* logit_old, const long long* action, long long B,
+                                 long long N, float* loss, float* dlogit_unit, float* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    if (B < 1 || N < 1 || !logit_new || !logit_old || !action || !loss || !workspace || workspace_bytes < WS_MIN_BYTES)
+        return B200RL_ERR_ARG;
+    (void)launch_k(ppg_bc_kernel, head_grid(B), HD_NT, 0, (cudaStream_t)stream, logit_new, logit_old, action, B, (int)N, loss,
+                   dlogit_unit, workspace);
     return (int)cudaGetLastError();
 }

@@ -22,7 +22,7 @@ def _originals():
     base = sys.modules.get('ding.rl_utils')
     for name in _ours.HOT_PATH_FUNCTIONS:
         objs = set()
-        cands = [base] + [sys.modules.get('ding.rl_utils.' + m) for m in ('gae', 'ppo', 'td', 'vtrace', 'upgo', 'a2c', 'retrace', 'happo', 'acer')]
+        cands = [base] + [sys.modules.get('ding.rl_utils.' + m) for m in ('gae', 'ppo', 'td', 'vtrace', 'upgo', 'a2c', 'retrace', 'happo', 'acer', 'ppg')]
         for mod in cands:
             fn = getattr(mod, name, None) if mod is not None else None
             if fn is not None and fn is not getattr(_ours, name):

@@ -339,6 +339,23 @@ def ppo_value_(value_new, value_old, return_, weight, clip_ratio, use_value_clip
     return loss
 
 
+def ppg_bc_(logit_new, logit_old, action):
+    """behavioural-cloning term of ppg_joint_error (ppg.py:62-67): value (NaN-propagating, as the reference) and gradient."""
+    dev = logit_new.device
+    B, N = logit_new.shape
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    want_grad = logit_new.requires_grad and torch.is_grad_enabled()
+    dlogit = torch.empty_like(logit_new) if want_grad else None
+    with on_device(dev):
+        ws = workspace(dev)
+        rc = lib().b200rl_ppg_bc_fwd(ptr(logit_new), ptr(logit_old), ptr(action), B, N, ptr(loss), ptr(dlogit), ptr(ws),
+                                     ws.numel() * 4, stream_ptr())
+    _lib.check(rc, 'b200rl_ppg_bc_fwd')
+    if want_grad:
+        return _ScaleSaved.apply(logit_new, loss, dlogit)
+    return loss
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # q n-step TD
 # ----------------------------------------------------------------------------------------------------------------
@@ -787,16 +804,17 @@ class PPOContinuousFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mu, sigma, value_new, mu_old, sigma_old, mu_pre, sigma_pre, action, value_old, adv, return_, weight, S,
-                D, clip_ratio, use_value_clip, dual_clip, kl_type):
+                D, clip_ratio, use_value_clip, dual_clip, kl_type, factor=None):
         dev = mu.device
+        ctx.factor = factor  # happo_error_continuous's per-sample factor (S,) or None; kept alive for the backward launch
         out = torch.empty(8, dtype=torch.float32, device=dev)
         want = any(ctx.needs_input_grad[:3])
         gm = torch.empty_like(mu) if want else None
         gs = torch.empty_like(sigma) if want else None
         gv = torch.empty_like(value_new) if want else None
         g_used = torch.empty(4, dtype=torch.float32, device=dev) if want else None
-        ctx.hint = head_hint(dev, 'ppoc', [1.0, 0.5, -0.01, 0.0])
-        ctx.args = (S, D, clip_ratio, use_value_clip, dual_clip, kl_type)
+        ctx.hint = head_hint(dev, 'ppoc' if factor is None else 'happoc', [1.0, 0.5, -0.01, 0.0])
+        ctx.args = (ptr(factor), S, D, clip_ratio, use_value_clip, dual_clip, kl_type)
         with on_device(dev):
             ws = workspace(dev)
             rc = lib().b200rl_ppo_continuous_fwd_grad(
@@ -831,7 +849,7 @@ class PPOContinuousFunction(torch.autograd.Function):
                 keep[3][1], ptr(g_used), ptr(ctx.hint), None, ptr(gm), ptr(gs), ptr(gv), ptr(ws), ws.numel() * 4,
                 stream_ptr())
         _lib.check(rc, 'b200rl_ppo_continuous_fwd_grad(verify)')
-        return (gm, gs, gv) + (None, ) * 15
+        return (gm, gs, gv) + (None, ) * 16
 
 
 class ImpalaMaskFunction(torch.autograd.Function):

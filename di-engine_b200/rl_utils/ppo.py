@@ -162,6 +162,10 @@ def ppo_error_continuous(
     Returns ``(ppo_loss, ppo_info)``; gradients reach ``mu``, ``sigma`` of the new policy and ``value_new``.  Forward and
     gradients in one launch (csrc/heads.cu), device-verified backward.
     """
+    return _ppo_error_continuous(data, clip_ratio, use_value_clip, dual_clip, kl_type)
+
+
+def _ppo_error_continuous(data, clip_ratio, use_value_clip, dual_clip, kl_type, factor=None):
     assert dual_clip is None or dual_clip > 1.0, "dual_clip value must be greater than 1.0, but get value: {}".format(
         dual_clip
     )
@@ -192,9 +196,10 @@ def ppo_error_continuous(
     args += [stage(action.detach(), 'action', S * D), stage(value_old.detach(), 'value_old', S), stage(adv.detach(), 'adv', S),
              stage(return_.detach(), 'return_', S),
              stage(weight.detach(), 'weight', S) if weight is not None else None]
+    fac = stage(factor.detach(), 'factor', S).reshape(-1) if factor is not None else None
     p, v, e, k, out = ops.PPOContinuousFunction.apply(
         *args, S, D, float(clip_ratio), 1 if use_value_clip else 0, float(dual_clip) if dual_clip is not None else 0.0,
-        _KL_TYPES.get(kl_type, 1))
+        _KL_TYPES.get(kl_type, 1), fac)
     if LAZY_INFO:
         info = ppo_info(out[4], out[5])
     else:

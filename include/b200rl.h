@@ -323,7 +323,9 @@ B200RL_API int b200rl_quantile_td_bwd(const float* dtheta, const float* weight, 
  * a2c_error (ding/rl_utils/a2c.py:10-44): logit (S, N), action (S) int64, value / adv / return_ / weight(nullable) (S);
  * out3 = policy_loss -mean(logp*adv*w), value_loss mean(w*(return_-value)^2), entropy_loss mean(H*w).
  * ppo_error_continuous (ding/rl_utils/ppo.py:278-374): Independent(Normal(mu, sigma)) policies, mu / sigma / action (S, D)
- * (a 1-D old policy is D = 1), pretrained pair nullable; out6 as b200rl_ppo_fwd. */
+ * (a 1-D old policy is D = 1), pretrained pair nullable; out6 as b200rl_ppo_fwd.  factor (nullable, (S)) selects
+ * happo_error_continuous (ding/rl_utils/happo.py:195-284): min(surr1, surr2) * factor before the dual clip, entropy and
+ * approx_kl averaged over the S * D per-dimension terms. */
 B200RL_API int b200rl_a2c_fwd_grad(const float* logit, const long long* action, const float* value, const float* adv,
                         const float* return_, const float* weight, long long S, long long N, const float* g_expected,
                         int verify, const float* g_policy, const float* g_value, const float* g_entropy, float* g_used,
@@ -332,10 +334,17 @@ B200RL_API int b200rl_a2c_fwd_grad(const float* logit, const long long* action, 
 B200RL_API int b200rl_ppo_continuous_fwd_grad(
     const float* mu_new, const float* sigma_new, const float* mu_old, const float* sigma_old, const float* mu_pretrained,
     const float* sigma_pretrained, const float* action, const float* value_new, const float* value_old, const float* adv,
-    const float* return_, const float* weight, long long S, long long D, double clip_ratio, int use_value_clip,
-    double dual_clip, int kl_type, const float* g_expected, int verify, const float* g_policy, const float* g_value,
-    const float* g_entropy, const float* g_kl, float* g_used, float* g_hint, float* out6, float* grad_mu, float* grad_sigma,
-    float* grad_value, float* workspace, size_t workspace_bytes, void* stream);
+    const float* return_, const float* weight, const float* factor, long long S, long long D, double clip_ratio,
+    int use_value_clip, double dual_clip, int kl_type, const float* g_expected, int verify, const float* g_policy,
+    const float* g_value, const float* g_entropy, const float* g_kl, float* g_used, float* g_hint, float* out6, float* grad_mu,
+    float* grad_sigma, float* grad_value, float* workspace, size_t workspace_bytes, void* stream);
+
+/* ppg_joint_error's behavioural-cloning term (ding/rl_utils/ppg.py:62-67): F.kl_div(logp_new, logp_old, 'batchmean') -- the
+ * reference passes the old LOG-probability as the non-log target, so the value is NaN whenever an old log-probability is
+ * negative while the gradient (-logp_old / B through log-softmax) is finite; both are reproduced.  dlogit_unit (nullable,
+ * (B, N)) = d loss / d logit_new for a unit upstream gradient.  The auxiliary value term is b200rl_ppo_value_fwd. */
+B200RL_API int b200rl_ppg_bc_fwd(const float* logit_new, const float* logit_old, const long long* action, long long B,
+                      long long N, float* loss, float* dlogit_unit, float* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- fused learner step: gae (gae.py:25-70) followed by ppo_error (ppo.py:77-140) in ONE launch ------------------
  * Semantics are exactly b200rl_gae(value, next_value, reward, done, traj_flag -> adv) followed by b200rl_ppo_fwd_grad

@@ -40,6 +40,7 @@ FILES = [
     "ding/rl_utils/retrace.py",        # ACER's return operator
     "ding/rl_utils/happo.py",          # HAPPO heads (ppo_error with the per-sample factor)
     "ding/rl_utils/acer.py",           # ACER heads
+    "ding/rl_utils/ppg.py",            # PPG joint (auxiliary phase) loss
 ]
 
 

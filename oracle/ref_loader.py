@@ -23,7 +23,7 @@ import warnings
 
 REF_ROOT = os.environ.get("DI_ENGINE_REFERENCE", "/root/reference")
 ARCHIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ding_hotpath.zip")
-_HOT_MODULES = ["value_rescale", "gae", "td", "ppo", "isw", "vtrace", "upgo", "a2c", "retrace", "happo", "acer"]
+_HOT_MODULES = ["value_rescale", "gae", "td", "ppo", "isw", "vtrace", "upgo", "a2c", "retrace", "happo", "acer", "ppg"]
 _loaded = None
 
 

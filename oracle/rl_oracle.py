@@ -883,3 +883,54 @@ def acer_trust_region_update(actor_gradients, target_logit, avg_logit, trust_reg
     scale = g.mul(k).sum(-1, keepdim=True) - trust_region_value
     scale = torch.div(scale, k.mul(k).sum(-1, keepdim=True)).clamp(min=0.0)
     return [g - scale * k]
+
+
+def happo_error_continuous(mu_new, sigma_new, mu_old, sigma_old, action, value_new, value_old, adv, return_, weight=None,
+                           factor=None, clip_ratio: float = 0.2, use_value_clip: bool = True,
+                           dual_clip: Optional[float] = None):
+    """happo.py:195-284 with Normal.log_prob / entropy written out (per dimension, NOT summed: the reference uses Normal, not
+    Independent(Normal), so the entropy mean and approx_kl run over the B x D terms).  Returns (policy_loss, value_loss,
+    entropy_loss, approx_kl, clipfrac)."""
+    assert dual_clip is None or dual_clip > 1.0
+    if weight is None:
+        weight = torch.ones_like(adv)
+
+    def logp(mu, sigma):
+        return -((action - mu) ** 2) / (2 * sigma ** 2) - sigma.log() - math.log(math.sqrt(2 * math.pi))
+
+    if mu_old.dim() == 1:  # happo.py:237-238
+        mu_old, sigma_old = mu_old.unsqueeze(-1), sigma_old.unsqueeze(-1)
+    logp_new, logp_old = logp(mu_new, sigma_new), logp(mu_old, sigma_old)
+    entropy_loss = ((0.5 + 0.5 * math.log(2 * math.pi) + torch.log(sigma_new)) * weight.unsqueeze(1)).mean()
+    ratio = torch.prod(torch.exp(logp_new - logp_old), dim=-1)
+    surr1 = ratio * adv
+    surr2 = ratio.clamp(1 - clip_ratio, 1 + clip_ratio) * adv
+    if dual_clip is not None:
+        policy_loss = (-torch.max(factor.squeeze(1) * torch.min(surr1, surr2), dual_clip * adv) * weight).mean()
+    else:
+        policy_loss = (-factor.squeeze(1) * torch.min(surr1, surr2) * weight).mean()
+    with torch.no_grad():
+        approx_kl = (logp_old - logp_new).mean().item()
+        clipfrac = (ratio.gt(1 + clip_ratio) | ratio.lt(1 - clip_ratio)).float().mean().item()
+    if use_value_clip:
+        value_clip = value_old + (value_new - value_old).clamp(-clip_ratio, clip_ratio)
+        value_loss = 0.5 * (torch.max((return_ - value_new).pow(2), (return_ - value_clip).pow(2)) * weight).mean()
+    else:
+        value_loss = 0.5 * ((return_ - value_new).pow(2) * weight).mean()
+    return policy_loss, value_loss, entropy_loss, approx_kl, clipfrac
+
+
+def ppg_joint_error(logit_new, logit_old, action, value_new, value_old, return_, weight=None, clip_ratio: float = 0.2,
+                    use_value_clip: bool = True):
+    """ppg.py:10-69 -> (auxiliary_loss, behavioral_cloning_loss).  The second is F.kl_div(logp_new, logp_old, 'batchmean') with a
+    log-probability where kl_div expects a probability: NaN value, finite gradient -- restated as written."""
+    if weight is None:
+        weight = torch.ones_like(return_)
+    if use_value_clip:
+        value_clip = value_old + (value_new - value_old).clamp(-clip_ratio, clip_ratio)
+        auxiliary_loss = 0.5 * (torch.max((return_ - value_new).pow(2), (return_ - value_clip).pow(2)) * weight).mean()
+    else:
+        auxiliary_loss = 0.5 * ((return_ - value_new).pow(2) * weight).mean()
+    logp_new = _chosen(_log_softmax_rows(logit_new), action)
+    logp_old = _chosen(_log_softmax_rows(logit_old), action)
+    return auxiliary_loss, torch.nn.functional.kl_div(logp_new, logp_old, reduction='batchmean')

@@ -41,6 +41,8 @@ GRAD_INPUTS = {
     'retrace': [],
     'happo': ['logit_new', 'value_new'],
     'acer': ['target_logit', 'q_values'],
+    'happoc': ['mu_new', 'sigma_new', 'value_new'],
+    'ppg': ['logit_new', 'value_new'],
 }
 # upstream gradient for each returned loss head (distinct, non-trivial)
 LOSS_MIX = {
@@ -66,6 +68,8 @@ LOSS_MIX = {
     'iqn': [1.0],
     'fqf': [1.0],
     'happo': [1.0, 0.5, -0.01],
+    'happoc': [1.0, 0.5, -0.01],
+    'ppg': [1.0, 0.7],
 }
 
 
@@ -437,6 +441,21 @@ def acer_case(seed, T, B, N, c_clip_ratio=10.0, trust_region_value=1.0):
     return 'acer', t, dict(c_clip_ratio=c_clip_ratio, trust_region_value=trust_region_value)
 
 
+def happoc_case(seed, B, D, weight='none', **params):
+    """happo_error_continuous (tests/test_happo.py:49-75): ppoc_case + the per-sample factor"""
+    op, t, p = ppoc_case(seed, B, D, weight=weight, **params)
+    t = OrderedDict((k, v) for k, v in t.items() if not k.endswith('_pretrained'))
+    t['factor'] = _rand(_g(seed + 7919), B, 1) * 1.5 + 0.25
+    return 'happoc', t, p
+
+
+def ppg_case(seed, B, N, weight='none', **params):
+    """ppg_joint_error (tests/test_ppg.py): ppo_case without adv / pretrained"""
+    op, t, p = ppo_case(seed, B, N, weight=weight, **params)
+    t = OrderedDict((k, t[k]) for k in ('logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'return_', 'weight'))
+    return 'ppg', t, p
+
+
 def retrace_case(seed, T, B, N, gamma=0.99):
     """tests/test_retrace.py:8-18"""
     g = _g(seed)
@@ -570,6 +589,10 @@ def build_cases():
     c['happo_basic'] = happo_case(150, 64, 6, clip_ratio=0.2)
     c['happo_w_dc'] = happo_case(151, 33, 5, weight='tensor', dual_clip=3.0, clip_ratio=0.3)
     c['happo_noclip'] = happo_case(152, 12, 40, use_value_clip=False)
+    c['happoc_basic'] = happoc_case(153, 16, 6)
+    c['ppg_basic'] = ppg_case(155, 32, 6)
+    c['ppg_w_noclip'] = ppg_case(156, 9, 17, weight='tensor', use_value_clip=False, clip_ratio=0.1)
+    c['happoc_w_dc'] = happoc_case(154, 33, 3, weight='tensor', dual_clip=3.0, clip_ratio=0.3, use_value_clip=False)
     # ---- ACER Retrace targets (tests/test_retrace.py) ----------------------------------------------------------------------
     c['retrace_ref_test'] = retrace_case(140, 64, 32, 6)
     c['retrace_ragged'] = retrace_case(141, 13, 5, 3, gamma=0.9)
@@ -697,6 +720,21 @@ def run_api(api, op, tensors, params, device='cpu'):
         res['grad_target_logit'], res['grad_q_values'] = _np(t['target_logit'].grad), _np(t['q_values'].grad)
         res['out_trust_region'] = _np(api.acer_trust_region_update([t['actor_gradient']], t['target_logit'].detach(),
                                                                    t['avg_logit'], p['trust_region_value'])[0])
+        return res
+    if op == 'ppg':
+        loss = api.ppg_joint_error(api.ppg_data(*t.values()), **p)
+        res['out_auxiliary_loss'], res['out_behavioral_cloning_loss'] = _np(loss[0]), _np(loss[1])
+        _backward(op, list(loss), t, res)
+        return res
+    if op == 'happoc':
+        data = api.happo_data({'mu': t['mu_new'], 'sigma': t['sigma_new']}, {'mu': t['mu_old'], 'sigma': t['sigma_old']},
+                              t['action'], t['value_new'], t['value_old'], t['adv'], t['return_'], t['weight'], t['factor'])
+        loss, info = api.happo_error_continuous(data, **p)
+        for k in ('policy_loss', 'value_loss', 'entropy_loss'):
+            res['out_' + k] = _np(getattr(loss, k))
+        res['out_approx_kl'] = np.float32(info.approx_kl)
+        res['out_clipfrac'] = np.float32(info.clipfrac)
+        _backward(op, list(loss), t, res)
         return res
     if op == 'happo':
         loss, info = api.happo_error(api.happo_data(*[t[k] for k in HAPPO_FIELDS]), **p)
@@ -901,6 +939,19 @@ def run_oracle(orc, op, tensors, params):
         res['grad_target_logit'], res['grad_q_values'] = _np(t['target_logit'].grad), _np(t['q_values'].grad)
         res['out_trust_region'] = _np(orc.acer_trust_region_update([t['actor_gradient']], t['target_logit'].detach(),
                                                                    t['avg_logit'], p['trust_region_value'])[0])
+        return res
+    if op == 'ppg':
+        loss = orc.ppg_joint_error(**t, **p)
+        res['out_auxiliary_loss'], res['out_behavioral_cloning_loss'] = _np(loss[0]), _np(loss[1])
+        _backward(op, list(loss), t, res)
+        return res
+    if op == 'happoc':
+        out = orc.happo_error_continuous(**t, **p)
+        for k, v in zip(('policy_loss', 'value_loss', 'entropy_loss'), out[:3]):
+            res['out_' + k] = _np(v)
+        res['out_approx_kl'] = np.float32(out[3])
+        res['out_clipfrac'] = np.float32(out[4])
+        _backward(op, list(out[:3]), t, res)
         return res
     if op == 'happo':
         out = orc.happo_error(*[t[k] for k in HAPPO_FIELDS], **p)

@@ -35,6 +35,9 @@ INPUT_ORDER = {
     'iqn': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'replay_quantiles', 'weight', 'value_gamma'],
     'happo': ['logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'adv', 'return_', 'weight', 'factor'],
     'acer': ['q_values', 'q_retraces', 'v_pred', 'target_logit', 'actions', 'ratio', 'avg_logit', 'actor_gradient'],
+    'happoc': ['mu_new', 'sigma_new', 'mu_old', 'sigma_old', 'action', 'value_new', 'value_old', 'adv', 'return_', 'weight',
+               'factor'],
+    'ppg': ['logit_new', 'logit_old', 'action', 'value_new', 'value_old', 'return_', 'weight'],
     'retrace': ['q_values', 'v_pred', 'rewards', 'actions', 'weights', 'ratio'],
     'fqf': ['q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done', 'quantiles_hats', 'weight', 'value_gamma'],
 }

@@ -239,6 +239,8 @@ EXPECTED_CALLS = {
     'iqn': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
     'fqf': ['b200rl_quantile_td_fwd', 'b200rl_quantile_td_bwd'],
     'retrace': ['b200rl_q_retraces'],
+    'ppg': ['b200rl_ppo_value_fwd', 'b200rl_ppg_bc_fwd', 'b200rl_scale', 'b200rl_scale'],
+    'happoc': ['b200rl_ppo_continuous_fwd_grad', 'b200rl_ppo_continuous_fwd_grad'],
     'acer': ['b200rl_acer_policy_fwd', 'b200rl_acer_value_fwd', 'b200rl_acer_policy_bwd', 'b200rl_acer_value_bwd',
              'b200rl_acer_trust_region'],
     'happo': ['b200rl_ppo_fused_supported', 'b200rl_ppo_fwd_grad', 'b200rl_ppo_bwd'],
