@@ -18,6 +18,7 @@ returned losses are differentiable through autograd (the oracle for the CUDA bac
 import math
 from typing import Optional, Sequence, Union
 
+import numpy as np
 import torch
 
 _F32_MIN = torch.finfo(torch.float32).min
@@ -934,3 +935,66 @@ def ppg_joint_error(logit_new, logit_old, action, value_new, value_old, return_,
     logp_new = _chosen(_log_softmax_rows(logit_new), action)
     logp_old = _chosen(_log_softmax_rows(logit_old), action)
     return auxiliary_loss, torch.nn.functional.kl_div(logp_new, logp_old, reduction='batchmean')
+
+
+# PARITY UNPINNED for the two functions below: ding.policy.common_utils / ding.utils.data import treetensor, easydict, gym ...,
+# none of which is installed here, so the live functions cannot be run next to this restatement (unlike everything above).
+def default_collate_flat(batch, cat_1dim=True):
+    """ding/utils/data/collate_fn.py:80-160 for the field types a transition dict holds: tensors ((1,) samples are concatenated
+    when cat_1dim, :133-135), numpy arrays, python floats (-> float32), ints (-> int64), bools, nested dicts."""
+    elem = batch[0]
+    if isinstance(elem, torch.Tensor):
+        if elem.shape == (1, ) and cat_1dim:
+            return torch.cat(batch, 0)
+        return torch.stack(batch, 0)
+    if type(elem).__module__ == 'numpy':
+        if type(elem).__name__ == 'ndarray':
+            return default_collate_flat([torch.as_tensor(b) for b in batch], cat_1dim)
+        return torch.as_tensor(batch)
+    if isinstance(elem, bool):
+        return torch.tensor(batch)
+    if isinstance(elem, float):
+        return torch.tensor(batch, dtype=torch.float32)
+    if isinstance(elem, int):
+        return torch.tensor(batch, dtype=torch.int64)
+    if isinstance(elem, dict):
+        return {k: default_collate_flat([d[k] for d in batch], cat_1dim) for k in elem if not str(k).startswith('collate_ignore')}
+    if elem is None:
+        return None
+    raise TypeError(type(elem))
+
+
+def default_preprocess_learn(data, use_priority_IS_weight=False, use_priority=False, use_nstep=False, ignore_done=False):
+    """ding/policy/common_utils.py:28-98, line for line on top of the collate restatement above."""
+    elem = data[0]
+    if isinstance(elem['action'], (np.ndarray, torch.Tensor)) and elem['action'].dtype in [np.int64, torch.int64]:
+        data = default_collate_flat(data, cat_1dim=True)
+    else:
+        data = default_collate_flat(data, cat_1dim=False)
+    if 'value' in data and data['value'].dim() == 2 and data['value'].shape[1] == 1:
+        data['value'] = data['value'].squeeze(-1)
+    if 'adv' in data and data['adv'].dim() == 2 and data['adv'].shape[1] == 1:
+        data['adv'] = data['adv'].squeeze(-1)
+    data['done'] = torch.zeros_like(data['done']).float() if ignore_done else data['done'].float()
+    if data['done'].dim() == 2 and data['done'].shape[1] == 1:
+        data['done'] = data['done'].squeeze(-1)
+    if use_priority_IS_weight:
+        assert use_priority, "Use IS Weight correction, but Priority is not used."
+    if use_priority and use_priority_IS_weight:
+        data['weight'] = data['priority_IS'] if 'priority_IS' in data else data['IS']
+    else:
+        data['weight'] = data.get('weight', None)
+    if use_nstep:
+        reward = data['reward']
+        if len(reward.shape) == 1:
+            reward = reward.unsqueeze(1)
+        if reward.ndim == 2:
+            data['reward'] = reward.transpose(0, 1).contiguous()
+        elif reward.ndim == 3:
+            data['reward'] = reward.permute(2, 0, 1).contiguous()
+        else:
+            raise ValueError("The 'reward' tensor must be either 2D or 3D. Got shape: {}".format(reward.shape))
+    else:
+        if data['reward'].dim() == 2 and data['reward'].shape[1] == 1:
+            data['reward'] = data['reward'].squeeze(-1)
+    return data
