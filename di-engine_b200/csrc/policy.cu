@@ -18,58 +18,12 @@
 //   adv_stats_kernel      {mean, std(unbiased) + 1e-8} of a batch in one launch; the PPO kernels apply the normalisation on load
 //                         (ppo_math.cuh adv_in), normalize_kernel materialises it for callers that want the tensor.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/b200rl.h"
-#include "common.cuh"
+#include "policy_stats.cuh"
 
 namespace b200rl {
-
-template <class T>
-__device__ __forceinline__ T warp_sum_t(T v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// CTA-wide sum of K doubles per thread; result valid in thread 0 (fixed order: deterministic)
-template <int K, int NT>
-__device__ __forceinline__ void block_sum_d(double (&v)[K], double (&tot)[K]) {
-    __shared__ double s_bs[K][NT / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const double r = warp_sum_t(v[k]);
-        if (lane == 0) s_bs[k][wid] = r;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double r = 0.0;
-            for (int w = 0; w < NT / 32; ++w) r += s_bs[k][w];
-            tot[k] = r;
-        }
-    }
-    __syncthreads();
-}
-
-struct RetArgs {
-    float vscale;      // 0: no value_norm
-    float* ret_unnorm;  // nullable
-    float* value_out;   // nullable: (value*s)/s
-    float* ret_out;     // nullable: unnormalized / s
-    float* stats;       // nullable: {mean, population variance, count} of the unnormalized returns (RunningMeanStd.update input)
-    float* adv_stats;   // nullable: {mean, std(unbiased) + 1e-8} of adv (ppo.py:304-306 when the whole batch is one minibatch)
-};
-
-// {mean, torch.std (unbiased) + 1e-8} from the fp64 sums of x and x^2
-__device__ __forceinline__ void write_adv_stats(float* out, double s1, double s2, double nn) {
-    const double m = s1 / nn;
-    const double var = (s2 - s1 * m) / (nn - 1.0);  // n == 1 -> nan, as torch.std
-    const double sd = var != var ? var : sqrt(fmax(var, 0.0));
-    out[0] = (float)m;
-    out[1] = fadd((float)sd, 1e-8f);
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // 1-D GAE with segment-parallel scan (single CTA, T <= GS_MAX_T)
@@ -353,6 +307,9 @@ __global__ void __launch_bounds__(256) impala_mask_kernel(const float* __restric
 using namespace b200rl;
 
 namespace b200rl {
+int gae_scan_returns(const float* value, float* next_value, const float* reward, const float* done, const float* traj_flag,
+                     float* adv, long long T, long long C, double gamma_d, double lambda_d, int mask_next_value_inplace,
+                     const RetArgs& ra, double* ws_d, unsigned int* ws_join, void* stream);
 int gae_scan(const float* value, float* next_value, const float* reward, const float* done, const float* traj_flag, float* adv,
              long long T, long long C, long long A, double gamma_d, double lambda_d, int mask_next_value_inplace,
              float vscale, void* stream);
@@ -407,11 +364,21 @@ extern "C" int b200rl_gae_returns(const float* value, float* next_value, const f
                        (float)gamma, (float)(gamma * lambda_), mask_next_value_inplace, ra);
         return (int)cudaGetLastError();
     }
-    // (T, B): the streaming scan (value_norm scaling applied on load), then one elementwise epilogue
+    // (T, B): the streaming scan (value_norm scaling applied on load) with the returns / statistics epilogue in its storer stage:
+    // one launch.  B200RL_GAE_RET_SPLIT=1: scan, then the separate elementwise epilogue launch (returns_kernel; A/B experiments)
+    static int split = -1;
+    if (split < 0) {
+        const char* e = getenv("B200RL_GAE_RET_SPLIT");
+        split = (e && e[0] == '1') ? 1 : 0;
+    }
+    const bool want_epi = unnormalized_return || value_out || return_out || stats3 || adv_stats2;
+    if (want_epi && A == 1 && !split)
+        return gae_scan_returns(value, next_value, reward, done, traj_flag, adv, T, C, gamma, lambda_, mask_next_value_inplace, ra,
+                                ws_doubles(workspace), ws_joins(workspace), stream);
     int rc = gae_scan(value, next_value, reward, done, traj_flag, adv, T, C, A, gamma, lambda_, mask_next_value_inplace,
                       (float)value_scale, stream);
     if (rc != 0) return rc;
-    if (unnormalized_return || value_out || return_out || stats3 || adv_stats2) {
+    if (want_epi) {
         const long long n = T * C;
         const bool vec = (n % 4 == 0) && aligned16(value) && aligned16(adv) && (!unnormalized_return || aligned16(unnormalized_return)) &&
                          (!value_out || aligned16(value_out)) && (!return_out || aligned16(return_out));
