@@ -364,13 +364,16 @@ extern "C" int b200rl_gae_returns(const float* value, float* next_value, const f
                        (float)gamma, (float)(gamma * lambda_), mask_next_value_inplace, ra);
         return (int)cudaGetLastError();
     }
-    // (T, B): the streaming scan (value_norm scaling applied on load) with the returns / statistics epilogue in its storer stage:
-    // one launch.  B200RL_GAE_RET_SPLIT=1: scan, then the separate elementwise epilogue launch (returns_kernel; A/B experiments)
-    static int split = -1;
-    if (split < 0) {
-        const char* e = getenv("B200RL_GAE_RET_SPLIT");
-        split = (e && e[0] == '1') ? 1 : 0;
+    // (T, B): the streaming scan (value_norm scaling applied on load), then one elementwise epilogue launch (returns_kernel).
+    // B200RL_GAE_RET_FUSED=1: the epilogue rides in the scan kernel's storer stage instead (gae.cu gae_ret_ws_kernel, one
+    // launch) -- built, parity-tested and measured: 14.1 us either way at config P (the storer warps then wait on the value
+    // re-read and the statistics join lengthens the kernel's tail by what the second launch cost), the step 0.8 us slower.
+    static int fused_epi = -1;
+    if (fused_epi < 0) {
+        const char* e = getenv("B200RL_GAE_RET_FUSED");
+        fused_epi = (e && e[0] == '1') ? 1 : 0;
     }
+    const int split = !fused_epi;
     const bool want_epi = unnormalized_return || value_out || return_out || stats3 || adv_stats2;
     if (want_epi && A == 1 && !split)
         return gae_scan_returns(value, next_value, reward, done, traj_flag, adv, T, C, gamma, lambda_, mask_next_value_inplace, ra,

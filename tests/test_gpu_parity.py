@@ -832,6 +832,35 @@ def test_gae_returns_matches_policy_lines(case):
         assert torch.equal(dev2[1].cpu(), ref_in[1]), 'next_value masked in place'
 
 
+def test_gae_returns_fused_epilogue_variant_in_a_fresh_process():
+    """B200RL_GAE_RET_FUSED=1 (the returns epilogue inside the scan kernel; read once per process): same bits, same statistics"""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import di_engine_b200 as b2
+from oracle import rl_oracle
+from tests import cases
+for seed, T, B, std in ((206, 128, 4096, None), (207, 67, 1001, 0.37), (208, 33, 36, 1.5)):
+    _, t, _ = cases.gae_case(seed, T, B, p_done=0.03)
+    data = tuple(t.values())
+    want = rl_oracle.ppo_policy_gae_returns(*[x.clone() for x in data], 0.99, 0.95, std)
+    got = b2.gae_returns(b2.gae_data(*[x.clone().cuda() for x in data]), 0.99, 0.95, value_norm_std=std)
+    for name, a, b in zip(got._fields[:4], got[:4], want[:4]):
+        assert torch.equal(a.cpu(), b), name
+    st = got.return_stats.cpu().numpy().astype(np.float64)
+    assert np.allclose(st, np.array(want[4]), rtol=2e-6, atol=1e-6), (st, want[4])
+    a64 = want[0].double()
+    assert np.allclose(got.adv_stats.cpu().numpy(), [a64.mean().item(), a64.std().item() + 1e-8], rtol=2e-6, atol=1e-6)
+print('fused epilogue ok')
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200RL_GAE_RET_FUSED='1')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'fused epilogue ok' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize('S,N', [(320, 6), (64, 6), (524288, 6), (1000, 40)])
 def test_ppo_error_adv_norm_matches_policy_lines(S, N):
     op, t, p = cases.ppo_case(210 + N, S, N, weight='tensor', clip_ratio=0.2)
