@@ -1,7 +1,7 @@
 """Per-operator micro-benchmarks at the BASELINE.json configs (device-resident inputs, CUDA-graph replay over rotated
 buffer sets larger than L2, CUDA events).  Prints one JSON line per op: us per call and algorithmic GB/s.
 
-    python tools/bench_ops.py [gae] [qntd] [dntd] [vtrace] [tdl] [upgo]
+    python tools/bench_ops.py [gae] [qntd] [dntd] [vtrace] [tdl] [upgo] [gae1d] [quantile] [retrace] [happo]
 """
 import json
 import os
@@ -108,6 +108,19 @@ def bench_api(name, op, mk, alg_bytes, units, unit_name, nsets=4):
         elif op == 'upgo':
             loss = r.upgo_loss(td['target_output'], td['rhos'], td['action'], td['rewards'], td['bootstrap_values'],
                                td['mask'])
+        elif op in ('qrdqn', 'iqn', 'fqf'):
+            data = getattr(r, op + '_nstep_td_data')(*[td[k] for k in cases.QUANTILE_FIELDS[op]])
+            loss = getattr(r, op + '_nstep_td_error')(data, value_gamma=td.get('value_gamma'), **p)[0]
+        elif op == 'retrace':
+            r.compute_q_retraces(*td.values(), **p)
+            return
+        elif op == 'happo':
+            l, _ = r.happo_error(r.happo_data(*[td[k] for k in cases.HAPPO_FIELDS]), **p)
+            torch.autograd.backward([l.policy_loss, l.value_loss, l.entropy_loss], [G1, G05, GM001])
+            return
+        elif op == 'gae1d':
+            r.gae_returns(r.gae_data(td['value'], td['next_value'], td['reward'], td['done'], td['traj_flag']), 0.99, 0.95, 1.7)
+            return
         loss.backward()
 
     us = timed([lambda td=td, p=p: call(td, p) for td, p in sets], reps=200)
@@ -115,7 +128,7 @@ def bench_api(name, op, mk, alg_bytes, units, unit_name, nsets=4):
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['gae', 'qntd', 'dntd', 'vtrace', 'tdl', 'upgo']
+    which = sys.argv[1:] or ['gae', 'qntd', 'dntd', 'vtrace', 'tdl', 'upgo', 'gae1d', 'quantile', 'retrace', 'happo']
     b2.rl_utils.td.CHECK_DIST_POSITIVE = False
     if 'gae' in which:
         bench_gae()
@@ -138,3 +151,20 @@ if __name__ == '__main__':
     if 'upgo' in which:
         bench_api('upgo T=256 B=256 N=256', 'upgo', lambda i: cases.upgo_case(i, 256, 256, 256),
                   (8 * 256 + 20) * 65536, 65536, 'transitions')
+    if 'gae1d' in which:
+        cases.GRAD_INPUTS['gae1d'] = []
+        bench_api('gae_returns 1-D T=3200 (the PPO learner call: value-norm, returns, both statistics)', 'gae1d',
+                  lambda i: ('gae1d', ) + cases.gae_case(i, 3200, 1, one_d=True, p_done=0.0025)[1:], 36 * 3200, 3200, 'transitions')
+    if 'quantile' in which:
+        bench_api('qrdqn_nstep_td_error B=64 N=6 num=200 n=3', 'qrdqn',
+                  lambda i: cases.quantile_case(i, 'qrdqn', 64, 6, 200, 200, 3, weight='tensor'), 64 * (2 * 6 * 200 * 4 + 40), 64,
+                  'samples')
+        bench_api('iqn_nstep_td_error B=64 N=6 tau=32 n=3', 'iqn',
+                  lambda i: cases.quantile_case(i, 'iqn', 64, 6, 32, 32, 3, weight='tensor'), 64 * (2 * 6 * 32 * 4 + 40), 64,
+                  'samples')
+    if 'retrace' in which:
+        bench_api('compute_q_retraces T=64 B=8192 N=6', 'retrace', lambda i: cases.retrace_case(i, 64, 8192, 6),
+                  64 * 8192 * (4 * 6 * 2 + 24), 64 * 8192, 'transitions')
+    if 'happo' in which:
+        bench_api('happo_error B=65536 N=6', 'happo', lambda i: cases.happo_case(i, 65536, 6, weight='tensor'), 108 * 65536, 65536,
+                  'samples')
