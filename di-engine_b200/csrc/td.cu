@@ -423,109 +423,128 @@ struct LamArgs {
 template <int TC, int NT, int CHUNK, int MODE, int HEAD>
 __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
     pdl_prologue();
-    __shared__ float s_r[CHUNK][TC];
-    __shared__ float s_m[CHUNK][TC];
-    __shared__ float s_disc[CHUNK][TC];
-    __shared__ float s_c[CHUNK][TC];
+    // Chunks of CHUNK time steps, newest first, double-buffered: while the TC scan lanes run the dependent chain of chunk k
+    // out of shared memory, every thread already has the global loads of chunk k+1 in flight (U elements per thread in
+    // registers); they are turned into the scan's operands and written to the other buffer once the scan is done.  (Without
+    // the overlap T = 1024, B = 64 took 46 us: eight times load latency + scan + store in a row.)
+    constexpr int U = CHUNK * TC / NT;
+    static_assert(U * NT == CHUNK * TC && U >= 1, "one pass per chunk");
+    __shared__ float s_r[2][CHUNK][TC];
+    __shared__ float s_m[2][CHUNK][TC];
+    __shared__ float s_disc[2][CHUNK][TC];
+    __shared__ float s_c[2][CHUNK][TC];
     const long long c0 = (long long)blockIdx.x * TC;
     const long long T = a.T, B = a.B;
-    float carry = 0.f;
-    float acc[1] = {0.f};
-    for (long long hi = T; hi > 0; hi -= CHUNK) {
-        const long long lo = hi > CHUNK ? hi - CHUNK : 0;
-        const int rows = (int)(hi - lo);
-        // U elements per thread at a time: all global loads of the batch are issued before any of them is consumed (the
-        // shared-memory stores of a one-element loop body would serialise the loads: T=1024, B=64 took 78 us, mostly here)
-        constexpr int U = 8;
-        for (int i0 = threadIdx.x; i0 < rows * TC; i0 += NT * U) {
-            float rw[U], vn[U], g[U], l[U], dn[U], r2[U], v2[U];
-            bool ok[U];
+    struct Raw {
+        float rw[U], vn[U], g[U], l[U], dn[U], r2[U], v2[U];
+        bool ok[U];
+    };
+    // all global loads of a chunk are issued before any of them is consumed
+    auto fetch = [&](long long lo, int rows, Raw& x) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * NT;
-                const int r = i / TC, cc = i % TC;
-                const long long c = c0 + cc, t = lo + r;
-                ok[u] = i < rows * TC && c < B;
-                rw[u] = vn[u] = dn[u] = r2[u] = v2[u] = 0.f;
-                g[u] = a.gamma;
-                l[u] = a.lambda;
-                if (ok[u]) {
-                    const long long off = t * B + c;
-                    rw[u] = a.reward[off];
-                    vn[u] = a.value[off + B];  // V_{t+1}
-                    if (MODE == 1) {
-                        if (t < T - 1) {
-                            r2[u] = a.reward[off + B];
-                            v2[u] = a.value[off + 2 * B];
-                        }
-                    } else {
-                        if (a.gammas) g[u] = a.gammas[off];
-                        if (a.lambdas) l[u] = a.lambdas[off];
-                    }
-                    if (a.done) dn[u] = a.done[off];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!ok[u]) continue;
-                const int i = i0 + u * NT;
-                const int r = i / TC, cc = i % TC;
-                const long long t = lo + r;
-                float gg = g[u], ll = l[u];
+        for (int u = 0; u < U; ++u) {
+            const int i = threadIdx.x + u * NT;
+            const int r = i / TC, cc = i % TC;
+            const long long c = c0 + cc, t = lo + r;
+            x.ok[u] = i < rows * TC && c < B;
+            x.rw[u] = x.vn[u] = x.dn[u] = x.r2[u] = x.v2[u] = 0.f;
+            x.g[u] = a.gamma;
+            x.l[u] = a.lambda;
+            if (x.ok[u]) {
+                const long long off = t * B + c;
+                x.rw[u] = a.reward[off];
+                x.vn[u] = a.value[off + B];  // V_{t+1}
                 if (MODE == 1) {
-                    gg = 1.f;
-                    ll = 1.f;
-                    if (t < T - 1) ll = (fadd(r2[u], v2[u]) >= vn[u]) ? 1.f : 0.f;
-                }
-                const float m = a.done ? fsub(1.f, dn[u]) : 1.f;
-                const float disc = fmul(gg, ll);
-                s_r[r][cc] = rw[u];
-                s_m[r][cc] = m;
-                if (t == T - 1) {
-                    // closed form of the last row kept in s_c; disc = 0 so the carry (0) is ignored exactly
-                    s_disc[r][cc] = 0.f;
-                    s_c[r][cc] = fmul(fmul(m, gg), vn[u]);
-                    s_m[r][cc] = 1.f;
+                    if (t < T - 1) {
+                        x.r2[u] = a.reward[off + B];
+                        x.v2[u] = a.value[off + 2 * B];
+                    }
                 } else {
-                    s_disc[r][cc] = disc;
-                    s_c[r][cc] = fmul(fsub(gg, disc), vn[u]);
+                    if (a.gammas) x.g[u] = a.gammas[off];
+                    if (a.lambdas) x.l[u] = a.lambdas[off];
                 }
+                if (a.done) x.dn[u] = a.done[off];
             }
         }
-        __syncthreads();
+    };
+    auto commit = [&](int buf, long long lo, const Raw& x) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!x.ok[u]) continue;
+            const int i = threadIdx.x + u * NT;
+            const int r = i / TC, cc = i % TC;
+            const long long t = lo + r;
+            float gg = x.g[u], ll = x.l[u];
+            if (MODE == 1) {
+                gg = 1.f;
+                ll = 1.f;
+                if (t < T - 1) ll = (fadd(x.r2[u], x.v2[u]) >= x.vn[u]) ? 1.f : 0.f;
+            }
+            const float m = a.done ? fsub(1.f, x.dn[u]) : 1.f;
+            const float disc = fmul(gg, ll);
+            s_r[buf][r][cc] = x.rw[u];
+            s_m[buf][r][cc] = m;
+            if (t == T - 1) {
+                // closed form of the last row kept in s_c; disc = 0 so the carry (0) is ignored exactly
+                s_disc[buf][r][cc] = 0.f;
+                s_c[buf][r][cc] = fmul(fmul(m, gg), x.vn[u]);
+                s_m[buf][r][cc] = 1.f;
+            } else {
+                s_disc[buf][r][cc] = disc;
+                s_c[buf][r][cc] = fmul(fsub(gg, disc), x.vn[u]);
+            }
+        }
+    };
+    float carry = 0.f;
+    float acc[1] = {0.f};
+    {
+        const long long lo = T > CHUNK ? T - CHUNK : 0;
+        Raw x;
+        fetch(lo, (int)(T - lo), x);
+        commit(0, lo, x);
+    }
+    __syncthreads();
+    int buf = 0;
+    for (long long hi = T; hi > 0; hi -= CHUNK, buf ^= 1) {
+        const long long lo = hi > CHUNK ? hi - CHUNK : 0;
+        const int rows = (int)(hi - lo);
+        const bool have_next = lo > 0;
+        const long long nlo = lo > CHUNK ? lo - CHUNK : 0;
+        Raw nx;
+        if (have_next) fetch(nlo, (int)(lo - nlo), nx);
         if (threadIdx.x < TC && c0 + threadIdx.x < B) {
             const int cc = threadIdx.x;
             // 16 rows at a time: the shared-memory operands of the next 16 steps are in registers before the dependent
             // chain needs them, so each step costs only its 4 dependent fp32 operations
-            constexpr int U = 16;
+            constexpr int UU = 16;
             int r = rows - 1;
-            for (; r >= U - 1; r -= U) {
-                float rr[U], mm[U], dd[U], cq[U];
+            for (; r >= UU - 1; r -= UU) {
+                float rr[UU], mm[UU], dd[UU], cq[UU];
 #pragma unroll
-                for (int j = 0; j < U; ++j) {
-                    rr[j] = s_r[r - j][cc];
-                    mm[j] = s_m[r - j][cc];
-                    dd[j] = s_disc[r - j][cc];
-                    cq[j] = s_c[r - j][cc];
+                for (int j = 0; j < UU; ++j) {
+                    rr[j] = s_r[buf][r - j][cc];
+                    mm[j] = s_m[buf][r - j][cc];
+                    dd[j] = s_disc[buf][r - j][cc];
+                    cq[j] = s_c[buf][r - j][cc];
                 }
 #pragma unroll
-                for (int j = 0; j < U; ++j) {
+                for (int j = 0; j < UU; ++j) {
                     carry = fadd(rr[j], fmul(mm[j], fadd(fmul(dd[j], carry), cq[j])));
-                    s_r[r - j][cc] = carry;
+                    s_r[buf][r - j][cc] = carry;
                 }
             }
             for (; r >= 0; --r) {
-                carry = fadd(s_r[r][cc], fmul(s_m[r][cc], fadd(fmul(s_disc[r][cc], carry), s_c[r][cc])));
-                s_r[r][cc] = carry;
+                carry = fadd(s_r[buf][r][cc], fmul(s_m[buf][r][cc], fadd(fmul(s_disc[buf][r][cc], carry), s_c[buf][r][cc])));
+                s_r[buf][r][cc] = carry;
             }
         }
         __syncthreads();
-        for (int i0 = threadIdx.x; i0 < rows * TC; i0 += NT * U) {
+        {
             float w[U], v[U];
             bool ok[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {  // the head's global loads first, batched like the input phase
-                const int i = i0 + u * NT;
+                const int i = threadIdx.x + u * NT;
                 const long long c = c0 + i % TC;
                 ok[u] = i < rows * TC && c < B;
                 w[u] = 1.f;
@@ -539,10 +558,10 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (!ok[u]) continue;
-                const int i = i0 + u * NT;
+                const int i = threadIdx.x + u * NT;
                 const int r = i / TC, cc = i % TC;
                 const long long off = (lo + r) * B + c0 + cc;
-                const float gret = s_r[r][cc];
+                const float gret = s_r[buf][r][cc];
                 if (a.ret) a.ret[off] = gret;
                 if (HEAD == 1) {
                     const float d = gret - v[u];
@@ -551,7 +570,8 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
                 }
             }
         }
-        if (lo > 0) __syncthreads();
+        if (have_next) commit(buf ^ 1, nlo, nx);
+        __syncthreads();
     }
     if (HEAD == 1) {
         // last value row receives no gradient (value[:-1], td.py:1570)
@@ -768,9 +788,9 @@ extern "C" int b200rl_dntd_bwd(const float* dist, const long long* act, const fl
 template <int MODE, int HEAD>
 static int launch_lambda(const LamArgs& a, float* ws, cudaStream_t st) {
     if (a.B >= 16 * 296) {
-        (void)launch_k(lambda_scan_kernel<16, 128, 64, MODE, HEAD>, div_up(a.B, 16), 128, 0, st, a, ws);
+        (void)launch_k(lambda_scan_kernel<16, 256, 64, MODE, HEAD>, div_up(a.B, 16), 256, 0, st, a, ws);
     } else {
-        (void)launch_k(lambda_scan_kernel<8, 64, 128, MODE, HEAD>, div_up(a.B, 8), 64, 0, st, a, ws);
+        (void)launch_k(lambda_scan_kernel<8, 256, 128, MODE, HEAD>, div_up(a.B, 8), 256, 0, st, a, ws);
     }
     return (int)cudaGetLastError();
 }
