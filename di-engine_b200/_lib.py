@@ -42,8 +42,8 @@ PROTOTYPES = {
     "b200rl_tb_cross_entropy_bwd": [P, P, P, P, LL, LL, LL, P, P],
     "b200rl_td_lambda_fwd": [P, P, P, D, D, LL, LL, P, P, P, c_size_t, P],
     "b200rl_scale": [P, P, P, LL, P],
-    "b200rl_upgo_head_fwd": [P, P, P, P, P, P, LL, LL, LL, P, P, P, c_size_t, P],
-    "b200rl_upgo_head_bwd": [P, P, P, P, P, LL, LL, LL, P, P],
+    "b200rl_upgo_head_fwd": [P, P, P, P, P, P, LL, LL, LL, P, P, P, P, c_size_t, P],
+    "b200rl_upgo_head_bwd": [P, P, P, P, P, LL, LL, LL, I, P, P],
     "b200rl_vtrace_fwd": [P, P, P, P, P, P, LL, LL, LL, D, D, D, D, D, P, P, P, P, P, c_size_t, P],
     "b200rl_vtrace_continuous_fwd": [P, P, P, P, P, P, P, P, LL, LL, LL, D, D, D, D, D, P, P, P, P, P, c_size_t, P],
     "b200rl_vtrace_continuous_bwd": [P, P, P, P, P, P, P, P, P, LL, LL, LL, P, P, P, P],

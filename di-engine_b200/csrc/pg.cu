@@ -42,6 +42,8 @@ struct UpgoArgs {
     float* adv_saved;  // (TB)
     const float* g_loss;
     float* grad_logit;
+    float* grad_unit;   // forward: nullable, d loss / d logit for a unit upstream gradient (one pass over the logits)
+    int skip_if_unit;   // backward: grad_logit already holds the unit gradient -> return when *g_loss == 1
 };
 
 template <int NT, int L>
@@ -52,17 +54,28 @@ __global__ void __launch_bounds__(NT) upgo_fwd_kernel(UpgoArgs a, float* ws) {
                                   : (long long)blockIdx.x * NT + threadIdx.x;
     float acc[1] = {0.f};
     if (s < a.TB) {
+        const float adv = fmul(a.rho[s], fsub(a.ret[s], a.value[s]));  // upgo.py:107
         float metric = 0.f;
         for (int k = 0; k < a.K; ++k) {
             const long long row = s * a.K + k;
             const float* z = a.logit + row * a.N;
             const float lse = row_lse<L>([&](int j) { return z[j]; }, a.N, lane);
-            float lp = z[a.action[row]] - lse;
-            if (a.mask) lp *= a.mask[row];
+            const int act = (int)a.action[row];
+            float lp = z[act] - lse;
+            const float mk = a.mask ? a.mask[row] : 1.f;
+            lp *= mk;
             metric += lp;
+            if (a.grad_unit) {  // the row is still in L1: its gradient for a unit upstream gradient goes out in the same pass
+                const float c = -adv * mk / (float)a.TB;  // d loss / d logp(row)
+                float* gz = a.grad_unit + row * a.N;
+                for (int j = lane; j < a.N; j += L) {
+                    float gj = -c * expf(z[j] - lse);
+                    if (j == act) gj += c;
+                    gz[j] = gj;
+                }
+            }
         }
         if (lane == 0) {
-            const float adv = fmul(a.rho[s], fsub(a.ret[s], a.value[s]));  // upgo.py:107
             a.adv_saved[s] = adv;
             acc[0] = adv * metric;
         }
@@ -78,11 +91,12 @@ __global__ void __launch_bounds__(NT) upgo_bwd_kernel(UpgoArgs a) {
     const long long row = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
                                     : (long long)blockIdx.x * NT + threadIdx.x;
     if (row >= a.TB * a.K) return;
+    const float g = a.g_loss ? *a.g_loss : 0.f;
+    if (a.skip_if_unit && g == 1.f) return;  // the forward launch already wrote exactly this gradient
     const long long s = row / a.K;
     const float* z = a.logit + row * a.N;
     float* gz = a.grad_logit + row * a.N;
     const float lse = row_lse<L>([&](int j) { return z[j]; }, a.N, lane);
-    const float g = a.g_loss ? *a.g_loss : 0.f;
     float c = -g * a.adv_saved[s] / (float)a.TB;  // d loss / d logp(row)
     if (a.mask) c *= a.mask[row];
     const int act = (int)a.action[row];
@@ -436,13 +450,13 @@ using namespace b200rl;
 
 extern "C" int b200rl_upgo_head_fwd(const float* logit, const long long* action, const float* mask, const float* rho,
                                     const float* ret, const float* value, long long TB, long long K, long long N,
-                                    float* loss, float* adv_saved, float* workspace, size_t workspace_bytes,
-                                    void* stream) {
+                                    float* loss, float* adv_saved, float* grad_logit_unit, float* workspace,
+                                    size_t workspace_bytes, void* stream) {
     if (TB <= 0 || K < 1 || N < 1 || !logit || !action || !rho || !ret || !value || !loss || !adv_saved || !workspace)
         return B200RL_ERR_ARG;
     UpgoArgs a{};
     a.logit = logit; a.action = action; a.mask = mask; a.rho = rho; a.ret = ret; a.value = value; a.TB = TB;
-    a.K = (int)K; a.N = (int)N; a.loss = loss; a.adv_saved = adv_saved;
+    a.K = (int)K; a.N = (int)N; a.loss = loss; a.adv_saved = adv_saved; a.grad_unit = grad_logit_unit;
     constexpr int NT = 128;
     cudaStream_t st = (cudaStream_t)stream;
     if (N > 64) {
@@ -459,11 +473,11 @@ extern "C" int b200rl_upgo_head_fwd(const float* logit, const long long* action,
 
 extern "C" int b200rl_upgo_head_bwd(const float* logit, const long long* action, const float* mask,
                                     const float* adv_saved, const float* g_loss, long long TB, long long K,
-                                    long long N, float* grad_logit, void* stream) {
+                                    long long N, int skip_if_unit, float* grad_logit, void* stream) {
     if (TB <= 0 || K < 1 || N < 1 || !logit || !action || !adv_saved || !grad_logit) return B200RL_ERR_ARG;
     UpgoArgs a{};
     a.logit = logit; a.action = action; a.mask = mask; a.adv_saved = const_cast<float*>(adv_saved); a.TB = TB;
-    a.K = (int)K; a.N = (int)N; a.g_loss = g_loss; a.grad_logit = grad_logit;
+    a.K = (int)K; a.N = (int)N; a.g_loss = g_loss; a.grad_logit = grad_logit; a.skip_if_unit = skip_if_unit;
     constexpr int NT = 128;
     cudaStream_t st = (cudaStream_t)stream;
     if (N > 64) (void)launch_k(upgo_bwd_kernel<NT, 32>, div_up(TB * K, NT / 32), NT, 0, st, a);

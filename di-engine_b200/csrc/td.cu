@@ -433,10 +433,14 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
     __shared__ float s_m[2][CHUNK][TC];
     __shared__ float s_disc[2][CHUNK][TC];
     __shared__ float s_c[2][CHUNK][TC];
+    // HEAD: V_t and the weight of the chunk, fetched with the scan operands one chunk ahead (single-buffered: a thread writes
+    // the slots of chunk k+1 only after it has consumed the same slots of chunk k)
+    __shared__ float s_hv[HEAD ? CHUNK : 1][TC];
+    __shared__ float s_hw[HEAD ? CHUNK : 1][TC];
     const long long c0 = (long long)blockIdx.x * TC;
     const long long T = a.T, B = a.B;
     struct Raw {
-        float rw[U], vn[U], g[U], l[U], dn[U], r2[U], v2[U];
+        float rw[U], vn[U], g[U], l[U], dn[U], r2[U], v2[U], hv[U], hw[U];
         bool ok[U];
     };
     // all global loads of a chunk are issued before any of them is consumed
@@ -464,6 +468,10 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
                     if (a.lambdas) x.l[u] = a.lambdas[off];
                 }
                 if (a.done) x.dn[u] = a.done[off];
+                if (HEAD == 1) {
+                    x.hv[u] = a.value[off];
+                    x.hw[u] = a.weight ? a.weight[off] : 1.f;
+                }
             }
         }
     };
@@ -482,6 +490,10 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
             }
             const float m = a.done ? fsub(1.f, x.dn[u]) : 1.f;
             const float disc = fmul(gg, ll);
+            if (HEAD == 1) {
+                s_hv[r][cc] = x.hv[u];
+                s_hw[r][cc] = x.hw[u];
+            }
             s_r[buf][r][cc] = x.rw[u];
             s_m[buf][r][cc] = m;
             if (t == T - 1) {
@@ -539,35 +551,19 @@ __global__ void __launch_bounds__(NT) lambda_scan_kernel(LamArgs a, float* ws) {
             }
         }
         __syncthreads();
-        {
-            float w[U], v[U];
-            bool ok[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {  // the head's global loads first, batched like the input phase
-                const int i = threadIdx.x + u * NT;
-                const long long c = c0 + i % TC;
-                ok[u] = i < rows * TC && c < B;
-                w[u] = 1.f;
-                v[u] = 0.f;
-                if (HEAD == 1 && ok[u]) {
-                    const long long off = (lo + i / TC) * B + c;
-                    if (a.weight) w[u] = a.weight[off];
-                    v[u] = a.value[off];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!ok[u]) continue;
-                const int i = threadIdx.x + u * NT;
-                const int r = i / TC, cc = i % TC;
-                const long long off = (lo + r) * B + c0 + cc;
-                const float gret = s_r[buf][r][cc];
-                if (a.ret) a.ret[off] = gret;
-                if (HEAD == 1) {
-                    const float d = gret - v[u];
-                    acc[0] += w[u] * d * d;
-                    a.dvalue[off] = -w[u] * d / (float)(T * B);  // 0.5 * w * 2 * (V - G) / count
-                }
+        for (int u = 0; u < U; ++u) {
+            const int i = threadIdx.x + u * NT;
+            const int r = i / TC, cc = i % TC;
+            if (i >= rows * TC || c0 + cc >= B) continue;
+            const long long off = (lo + r) * B + c0 + cc;
+            const float gret = s_r[buf][r][cc];
+            if (a.ret) a.ret[off] = gret;
+            if (HEAD == 1) {
+                const float w = s_hw[r][cc];
+                const float d = gret - s_hv[r][cc];
+                acc[0] += w * d * d;
+                a.dvalue[off] = -w * d / (float)(T * B);  // 0.5 * w * 2 * (V - G) / count
             }
         }
         if (have_next) commit(buf ^ 1, nlo, nx);

@@ -708,32 +708,40 @@ def td_lambda_(value, reward, weight, gamma, lambda_):
 # UPGO head
 # ----------------------------------------------------------------------------------------------------------------
 class UPGOFunction(torch.autograd.Function):
+    """upgo_loss head (upgo.py:77-111).  The forward launch also writes d loss / d logit for a unit upstream gradient while each
+    row is still in L1 (ONE pass over the logits); backward verifies the upstream gradient on the device and recomputes only
+    when it is not 1 (or on a repeated backward)."""
 
     @staticmethod
     def forward(ctx, logit, action, mask, rho, ret, value, TB, K, N):
         dev = logit.device
         loss = torch.empty((), dtype=torch.float32, device=dev)
         adv = torch.empty(TB, dtype=torch.float32, device=dev)
+        grad_unit = torch.empty_like(logit) if ctx.needs_input_grad[0] else None
         with on_device(dev):
             ws = workspace(dev)
             rc = lib().b200rl_upgo_head_fwd(
                 ptr(logit), ptr(action), ptr(mask), ptr(rho), ptr(ret), ptr(value), TB, K, N, ptr(loss), ptr(adv),
-                ptr(ws), ws.numel() * 4, stream_ptr()
+                ptr(grad_unit), ptr(ws), ws.numel() * 4, stream_ptr()
             )
         _lib.check(rc, 'b200rl_upgo_head_fwd')
         ctx.save_for_backward(logit, action, mask, adv)
         ctx.cfg = (TB, K, N)
+        ctx.spec = grad_unit
         return loss
 
     @staticmethod
     def backward(ctx, g):
         logit, action, mask, adv = ctx.saved_tensors
         TB, K, N = ctx.cfg
-        grad = torch.empty_like(logit)
+        grad, skip = ctx.spec, 1
+        ctx.spec = None  # sole owner now: autograd can adopt the buffer as .grad
+        if grad is None:  # a repeated backward: the first buffer may belong to .grad
+            grad, skip = torch.empty_like(logit), 0
         keep, pg = _g(g)
         with on_device(logit.device):
             rc = lib().b200rl_upgo_head_bwd(
-                ptr(logit), ptr(action), ptr(mask), ptr(adv), pg, TB, K, N, ptr(grad), stream_ptr()
+                ptr(logit), ptr(action), ptr(mask), ptr(adv), pg, TB, K, N, skip, ptr(grad), stream_ptr()
             )
         _lib.check(rc, 'b200rl_upgo_head_bwd')
         return (grad, ) + (None, ) * 8

@@ -195,12 +195,16 @@ B200RL_API int b200rl_scale(const float* g, const float* in, float* out, long lo
 
 /* ---- upgo_loss head: ding/rl_utils/upgo.py:77-111 (tb_cross_entropy :7-43) --------------------------------------
  * logit: (TB*K, N) with K = 1 for (T,B,N) logits or N2 for (T,B,N2,N); action, mask(nullable): (TB*K);
- * rho, ret (from b200rl_lambda_returns upgo mode), value (= bootstrap_values[:-1]): (TB). */
+ * rho, ret (from b200rl_lambda_returns upgo mode), value (= bootstrap_values[:-1]): (TB).
+ * grad_logit_unit (nullable, logit's shape): the forward launch also writes d loss / d logit for a unit upstream gradient while
+ * each row is still in L1 (one pass over the logits instead of two).  b200rl_upgo_head_bwd with skip_if_unit = 1 and that
+ * buffer as grad_logit returns at once when *g_loss == 1 and recomputes otherwise. */
 B200RL_API int b200rl_upgo_head_fwd(const float* logit, const long long* action, const float* mask, const float* rho,
                          const float* ret, const float* value, long long TB, long long K, long long N, float* loss,
-                         float* adv_saved, float* workspace, size_t workspace_bytes, void* stream);
+                         float* adv_saved, float* grad_logit_unit, float* workspace, size_t workspace_bytes, void* stream);
 B200RL_API int b200rl_upgo_head_bwd(const float* logit, const long long* action, const float* mask, const float* adv_saved,
-                         const float* g_loss, long long TB, long long K, long long N, float* grad_logit, void* stream);
+                         const float* g_loss, long long TB, long long K, long long N, int skip_if_unit, float* grad_logit,
+                         void* stream);
 
 /* tb_cross_entropy alone (upgo.py:7-43): ce (TB) = sum_k mask_k * log softmax(logit)[action]; backward for an upstream
  * gradient g_ce (TB). */

@@ -699,6 +699,26 @@ def test_quantile_td_exact_for_any_upstream_gradient(kind):
             assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * max(np.abs(b).max(), 1e-30)), (kind, scale, use_td)
 
 
+@pytest.mark.parametrize('shape', [(33, 17, 6, None), (16, 16, 200, None), (12, 9, 5, 3)])
+def test_upgo_head_exact_for_any_upstream_gradient(shape):
+    """the forward launch writes the gradient for a unit upstream gradient in the same pass over the logits; any other upstream
+    value and a repeated backward go through the recompute path"""
+    T, B, N, N2 = shape
+    op, t, p = cases.upgo_case(180 + N, T, B, N, N2=N2, mask=N2 is not None)
+    for scale in (1.0, 2.5, 0.0):
+        tw = cases.prepare(op, t)
+        (scale * rl_oracle.upgo_loss(**tw)).backward()
+        td = cases.prepare(op, t, DEV)
+        loss = b2.upgo_loss(td['target_output'], td['rhos'], td['action'], td['rewards'], td['bootstrap_values'], td['mask'])
+        total = scale * loss
+        total.backward(retain_graph=True)
+        g1 = td['target_output'].grad.clone()
+        total.backward()
+        b = tw['target_output'].grad.numpy()
+        for a, f in ((g1, 1.0), (td['target_output'].grad, 2.0)):
+            assert np.allclose(a.cpu().numpy(), f * b, rtol=1e-5, atol=1e-5 * max(np.abs(b).max(), 1e-30)), (shape, scale, f)
+
+
 def test_lambda_returns_backward_matches_autograd_of_the_recurrence():
     """Gradients w.r.t. values, rewards and tensor gammas / lambdas against autograd of an out-of-place restatement
     (the reference's in-place loop supports the first two; MBSAC needs them, mbpolicy/mbsac.py:137,153); UPGO mode too."""
