@@ -50,10 +50,13 @@ template <int NT, int L>
 __global__ void __launch_bounds__(NT) upgo_fwd_kernel(UpgoArgs a, float* ws) {
     pdl_prologue();
     const int lane = (L == 32) ? (threadIdx.x & 31) : 0;
-    const long long s = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
-                                  : (long long)blockIdx.x * NT + threadIdx.x;
+    // grid-stride over the samples: a bounded grid keeps the per-CTA loss reduction (ticket + fence) off the critical path -- one
+    // CTA per four rows spent most of the kernel in it (T = B = N = 256: 16 384 CTAs)
+    const long long s0 = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
+                                   : (long long)blockIdx.x * NT + threadIdx.x;
+    const long long stride = (L == 32) ? (long long)gridDim.x * (NT / 32) : (long long)gridDim.x * NT;
     float acc[1] = {0.f};
-    if (s < a.TB) {
+    for (long long s = s0; s < a.TB; s += stride) {
         const float adv = fmul(a.rho[s], fsub(a.ret[s], a.value[s]));  // upgo.py:107
         float metric = 0.f;
         for (int k = 0; k < a.K; ++k) {
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(NT) upgo_fwd_kernel(UpgoArgs a, float* ws) {
         }
         if (lane == 0) {
             a.adv_saved[s] = adv;
-            acc[0] = adv * metric;
+            acc[0] += adv * metric;
         }
     }
     double tot[1];
@@ -459,12 +462,15 @@ extern "C" int b200rl_upgo_head_fwd(const float* logit, const long long* action,
     a.K = (int)K; a.N = (int)N; a.loss = loss; a.adv_saved = adv_saved; a.grad_unit = grad_logit_unit;
     constexpr int NT = 128;
     cudaStream_t st = (cudaStream_t)stream;
+    constexpr int MAX_GRID = 148 * 16;
     if (N > 64) {
-        const int grid = div_up(TB, NT / 32);
+        int grid = div_up(TB, NT / 32);
+        if (grid > MAX_GRID) grid = MAX_GRID;
         if (!ws_partials_fit((long long)(grid), workspace_bytes)) return B200RL_ERR_WORKSPACE;
         (void)launch_k(upgo_fwd_kernel<NT, 32>, grid, NT, 0, st, a, workspace);
     } else {
-        const int grid = div_up(TB, NT);
+        int grid = div_up(TB, NT);
+        if (grid > MAX_GRID) grid = MAX_GRID;
         if (!ws_partials_fit((long long)(grid), workspace_bytes)) return B200RL_ERR_WORKSPACE;
         (void)launch_k(upgo_fwd_kernel<NT, 1>, grid, NT, 0, st, a, workspace);
     }
