@@ -91,22 +91,25 @@ template <int NT, int L>
 __global__ void __launch_bounds__(NT) upgo_bwd_kernel(UpgoArgs a) {
     pdl_prologue();
     const int lane = (L == 32) ? (threadIdx.x & 31) : 0;
-    const long long row = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
-                                    : (long long)blockIdx.x * NT + threadIdx.x;
-    if (row >= a.TB * a.K) return;
     const float g = a.g_loss ? *a.g_loss : 0.f;
     if (a.skip_if_unit && g == 1.f) return;  // the forward launch already wrote exactly this gradient
-    const long long s = row / a.K;
-    const float* z = a.logit + row * a.N;
-    float* gz = a.grad_logit + row * a.N;
-    const float lse = row_lse<L>([&](int j) { return z[j]; }, a.N, lane);
-    float c = -g * a.adv_saved[s] / (float)a.TB;  // d loss / d logp(row)
-    if (a.mask) c *= a.mask[row];
-    const int act = (int)a.action[row];
-    for (int j = lane; j < a.N; j += L) {
-        float gj = -c * expf(z[j] - lse);
-        if (j == act) gj += c;
-        gz[j] = gj;
+    // bounded grid-stride grid: the verification launch must be cheap (one CTA per four rows took 18.7 us just to return)
+    const long long r0 = (L == 32) ? (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)
+                                   : (long long)blockIdx.x * NT + threadIdx.x;
+    const long long stride = (L == 32) ? (long long)gridDim.x * (NT / 32) : (long long)gridDim.x * NT;
+    for (long long row = r0; row < a.TB * a.K; row += stride) {
+        const long long s = row / a.K;
+        const float* z = a.logit + row * a.N;
+        float* gz = a.grad_logit + row * a.N;
+        const float lse = row_lse<L>([&](int j) { return z[j]; }, a.N, lane);
+        float c = -g * a.adv_saved[s] / (float)a.TB;  // d loss / d logp(row)
+        if (a.mask) c *= a.mask[row];
+        const int act = (int)a.action[row];
+        for (int j = lane; j < a.N; j += L) {
+            float gj = -c * expf(z[j] - lse);
+            if (j == act) gj += c;
+            gz[j] = gj;
+        }
     }
 }
 
@@ -486,8 +489,10 @@ extern "C" int b200rl_upgo_head_bwd(const float* logit, const long long* action,
     a.K = (int)K; a.N = (int)N; a.g_loss = g_loss; a.grad_logit = grad_logit; a.skip_if_unit = skip_if_unit;
     constexpr int NT = 128;
     cudaStream_t st = (cudaStream_t)stream;
-    if (N > 64) (void)launch_k(upgo_bwd_kernel<NT, 32>, div_up(TB * K, NT / 32), NT, 0, st, a);
-    else (void)launch_k(upgo_bwd_kernel<NT, 1>, div_up(TB * K, NT), NT, 0, st, a);
+    int grid = N > 64 ? div_up(TB * K, NT / 32) : div_up(TB * K, NT);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (N > 64) (void)launch_k(upgo_bwd_kernel<NT, 32>, grid, NT, 0, st, a);
+    else (void)launch_k(upgo_bwd_kernel<NT, 1>, grid, NT, 0, st, a);
     return (int)cudaGetLastError();
 }
 
