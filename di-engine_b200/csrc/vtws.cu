@@ -222,8 +222,15 @@ __global__ void __launch_bounds__(VW_THREADS, 2) vtrace_ws_kernel(VtFusedArgs a,
             const long long c0 = it.tile * VW_TC;
             const long long t0 = T - (it.q + 1) * VW_R;
             unsigned char* st = smem + s * stage_bytes;
-            // one cp.async group per prologue chunk and per iteration: chunk j is group j (j < S) or j + 2, of S + j
-            if (S >= 4) cpa_wait<1>(); else cpa_wait<0>();
+            // one cp.async group per prologue chunk and per iteration: chunk j is group j (j < S) or j + 2, of the S + j committed
+            // so far -- S - 1 younger groups may stay in flight for the prologue chunks, S - 3 afterwards.  (Waiting for all but
+            // one from the first chunk on -- as this line did -- held chunk 0's scan until the rows of chunks 1 and 2 had landed
+            // behind the loader's 20 MB burst: first vs published at 4.35 us instead of ~2.8, tools/trace_vt_warps.py.)
+            if (S >= 4) {
+                if (j < S) cpa_wait<3>(); else cpa_wait<1>();
+            } else {
+                if (j < S) cpa_wait<2>(); else cpa_wait<0>();
+            }
             __syncwarp();
             mbar_wait(&is_ready[s], (uint32_t)ph);
             if (lane == 0 && j < 8) VW_TRACE(32 + 2 * j);
