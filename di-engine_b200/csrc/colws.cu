@@ -139,11 +139,15 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
                 if (row >= jmin && o < Pv) cpa16(dst + p * 16, g + row * rstride + o * 16);
             }
         };
-        // B200RL_COL_LOADER: 0 (default) = the flat loop; 2 | 3 = lane-owns-a-piece-column copies in 4- | 8-piece groups.
-        // The cheap copies cut the loader's instructions ~10x and make THIS kernel slower on every box measured (16.6 us flat,
-        // 17.1 us 8-piece groups, 17.2 us 4-piece groups): the copies then leave in bursts and the consumers' own stores
-        // and shared-memory traffic queue behind them.  vtws.cu, whose loader is the pacer, gains 0.65 us from the same change.
-        const bool fast_rows = f.loader >= 2;
+        // B200RL_COL_LOADER: 0 (default) = lane-owns-a-piece-column copies (common.cuh warp_copy_rows, ~3 instructions per copy) for
+        // the FIRST stage of a CTA, the flat loop (~35 instructions per copy) afterwards; 1 = the flat loop everywhere; 2 | 3 =
+        // the cheap copies everywhere in 4- | 8-piece groups.  Measured (same box, us per step): first stage only 16.52, flat
+        // 16.99, everywhere 17.06 - 17.24.  The kernel streams at the HBM roofline in steady state (a 256-transition chunk per CTA
+        // every 1.28 us on 256 CTAs = 6.55 TB/s of reads + writes), so a faster loader buys nothing there -- issued in bursts the
+        // copies only deepen the queues in front of everybody's next chunk -- but the first stage is pure latency: 1 us of address
+        // arithmetic before the first byte is requested.
+        const bool fast_rows = f.loader == 2 || f.loader == 3;
+        const bool fast_first = f.loader == 0;
         CwItem it = first;
         int s = 0, ph = 0;
         for (int j = 0; item_valid(it); ++j) {
@@ -154,14 +158,14 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
             const int jmin = t0 < 0 ? (int)-t0 : 0;
             const int W = (int)((B - c0) < CW_TC ? (B - c0) : CW_TC);
             unsigned char* st = smem + s * L.stage_bytes;
-            if (jmin == 0 && W == CW_TC && fast_rows) {
+            if (jmin == 0 && W == CW_TC && (fast_rows || (fast_first && j == 0))) {
                 // full chunk of a full tile: a row segment is TC * esz / 16 = esz pieces (4 N | 8 | 4).  Logits and actions
                 // go in 8-piece groups (a lane group covers one full 128-byte line per row: the 4-piece grouping doubles the
                 // number of L2 requests and measured 0.3 us SLOWER than the flat loop); the float tensors have 64-byte rows.
                 const uint32_t sb = smem_u32(st);
                 const long long e0 = t0 * B + c0;
                 const long long ls = B * N * 4;
-                if (f.loader != 3 || (N & 1)) {
+                if (f.loader == 2 || (N & 1)) {
                     warp_copy_rows<4, CW_R, NC>(sb, a.logit_new + e0 * N, ls, N, lane);
                     warp_copy_rows<4, CW_R, NC>(sb + L.off_old, a.logit_old + e0 * N, ls, N, lane);
                     if (has_pre) warp_copy_rows<4, CW_R, NC>(sb + L.off_pre, a.logit_pre + e0 * N, ls, N, lane);

@@ -17,7 +17,7 @@ struct FusedArgs {
     int mask_inplace;
     int trace;
     int wait_ns;  // colws.cu consumers: suspend-time hint of the mbarrier waits in ns (0 = none; B200RL_COL_WAIT_NS)
-    int loader;  // colws.cu: 0 = flat copy loop (default, measured fastest), 2 | 3 = lane-owns-a-piece-column copies (experiments)
+    int loader;  // colws.cu loader warp: 0 = cheap copies for the first stage only (default), 1 = flat loop, 2 | 3 = cheap copies everywhere
     // optional data-parallel exchange of the six loss scalars, fused into the step's finalize launch (colws.cu; common.cuh)
     const unsigned long long* x_mailboxes;
     unsigned int* x_seq;
