@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
         // copies only deepen the queues in front of everybody's next chunk -- but the first stage is pure latency: 1 us of address
         // arithmetic before the first byte is requested.
         const bool fast_rows = f.loader == 2 || f.loader == 3;
-        const bool fast_first = f.loader == 0;
+        const int fast_first = f.loader == 0 ? 1 : (f.loader >= 5 && f.loader <= 7 ? f.loader - 3 : 0);  // stages copied cheaply
         CwItem it = first;
         int s = 0, ph = 0;
         for (int j = 0; item_valid(it); ++j) {
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(CW_THREADS, 2) gae_ppo_ws_kernel(FusedArgs f, 
             const int jmin = t0 < 0 ? (int)-t0 : 0;
             const int W = (int)((B - c0) < CW_TC ? (B - c0) : CW_TC);
             unsigned char* st = smem + s * L.stage_bytes;
-            if (jmin == 0 && W == CW_TC && (fast_rows || (fast_first && j == 0))) {
+            if (jmin == 0 && W == CW_TC && (fast_rows || j < fast_first)) {
                 // full chunk of a full tile: a row segment is TC * esz / 16 = esz pieces (4 N | 8 | 4).  Logits and actions
                 // go in 8-piece groups (a lane group covers one full 128-byte line per row: the 4-piece grouping doubles the
                 // number of L2 requests and measured 0.3 us SLOWER than the flat loop); the float tensors have 64-byte rows.

@@ -53,6 +53,7 @@ struct VtFusedArgs {
     float* grad_logit;        // (T*B, N), nullable = losses only
     float* grad_value;        // (T+1, B)
     int trace;
+    int loader;  // streaming kernel's loader warp: number of leading stages copied with warp_copy_rows (0 = flat loop only, default: all)
 };
 
 // timeline instrumentation (B200RL_FUSED_TRACE=1, tools/trace_vt.py): 64 globaltimer stamps per CTA at workspace word 65536;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(VW_THREADS, 2) vtrace_ws_kernel(VtFusedArgs a,
             const int jmin = t0 < 0 ? (int)-t0 : 0;
             const int W = (int)((B - c0) < VW_TC ? (B - c0) : VW_TC);
             unsigned char* st = smem + s * stage_bytes;
-            if (VW_LW == 1 && jmin == 0 && W == VW_TC) {
+            if (VW_LW == 1 && jmin == 0 && W == VW_TC && j < a.loader) {
                 // full chunk of a full tile: lane-owns-a-piece-column copies (common.cuh warp_copy_rows); a row segment is
                 // TC * esz / 16 pieces = (TC / 4) * (N | 2 | 1) for logits | actions | weights
                 const uint32_t sb = smem_u32(st);
@@ -821,6 +822,12 @@ static void fill_vt(VtFusedArgs& a, const float* target_output, const float* beh
         tr = (e && e[0] == '1') ? 1 : 0;
     }
     a.trace = tr;
+    static int ld = -1;
+    if (ld < 0) {
+        const char* e = getenv("B200RL_VT_LOADER");  // leading stages copied cheaply (experiments); default: every stage
+        ld = e ? atoi(e) : (1 << 30);
+    }
+    a.loader = ld;
 }
 
 extern "C" int b200rl_vtrace_set_impl(int impl) {
