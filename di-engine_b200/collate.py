@@ -165,3 +165,46 @@ def get_gae(data, last_value, gamma, gae_lambda, device=None):
     for i in range(len(data)):
         data[i]['adv'] = adv[i]
     return data
+
+
+def nstep_return_data(reward, done, nstep, gamma=0.99, cum_reward=False, correct_terminate_gamma=True):
+    """``Adder.get_nstep_return_data`` (ding/rl_utils/adder.py:97-155) for ONE trajectory held as stacked tensors instead of a
+    deque of dicts: ``reward`` (T, ..., 1) -- the collector's per-step reward of shape (1,) or (agent_num, 1) stacked along T --
+    and ``done`` (T,).  Returns ``(reward_n, done_n, value_gamma, next_index)``:
+
+    * ``reward_n``  (T, ..., nstep): step i holds rewards i .. i+nstep-1, zero-padded past the end of the trajectory (the
+      reference's ``fake_reward``); with ``cum_reward`` (T, ..., 1): ``sum_j gamma**j * reward[i+j]`` over the steps that exist;
+    * ``done_n``    (T,): ``done[i+nstep-1]``, the last step's flag for the tail;
+    * ``value_gamma`` (T,) fp32: ``gamma**nstep``, ``gamma**(T-i-1)`` for the tail (only meaningful with
+      ``correct_terminate_gamma``, returned either way);
+    * ``next_index`` (T,) int64: ``next_obs`` of step i is ``obs[next_index[i]]`` for i < T - nstep and the trajectory's last
+      ``next_obs`` (index T, i.e. one past the stacked observations) for the tail.
+
+    Index arithmetic only (gathers over a padded copy): works on host or device tensors alike."""
+    T = reward.shape[0]
+    if nstep == 1:
+        ar = torch.arange(T, device=reward.device)
+        return reward, done, torch.full((T, ), float(gamma), device=reward.device), ar + 1
+    dev = reward.device
+    idx = torch.arange(T, device=dev).unsqueeze(1) + torch.arange(nstep, device=dev).unsqueeze(0)  # (T, nstep): step i + j
+    valid = idx < T
+    pad = torch.cat([reward, torch.zeros((nstep, ) + tuple(reward.shape[1:]), dtype=reward.dtype, device=dev)], 0)
+    win = pad[idx.clamp(max=T + nstep - 1)]                      # (T, nstep, ..., 1)
+    win = win.movedim(1, -1).squeeze(-2)                         # (T, ..., nstep)
+    if cum_reward:
+        # the reference sums python-side: data[i]['reward'] * gamma**0 + data[i+1]['reward'] * gamma**1 + ... in that order
+        out = torch.zeros_like(reward)
+        for j in range(nstep):
+            term = win[..., j:j + 1] * (gamma ** j)
+            out = term if j == 0 else out + term
+        reward_n = out
+    else:
+        reward_n = win
+    last = torch.clamp(torch.arange(T, device=dev) + nstep - 1, max=T - 1)
+    done_n = done[last]
+    steps_left = (T - 1 - torch.arange(T, device=dev)).clamp(max=nstep).to(torch.float32)
+    tail = torch.arange(T, device=dev) >= max(0, T - nstep)
+    value_gamma = torch.where(tail, torch.pow(torch.tensor(float(gamma), device=dev), steps_left),
+                              torch.full((T, ), float(gamma) ** nstep, device=dev))
+    next_index = torch.where(tail, torch.full((T, ), T, device=dev), torch.arange(T, device=dev) + nstep)
+    return reward_n, done_n, value_gamma, next_index

@@ -998,3 +998,34 @@ def default_preprocess_learn(data, use_priority_IS_weight=False, use_priority=Fa
         if data['reward'].dim() == 2 and data['reward'].shape[1] == 1:
             data['reward'] = data['reward'].squeeze(-1)
     return data
+
+
+def adder_get_nstep_return_data(data, nstep, cum_reward=False, correct_terminate_gamma=True, gamma=0.99):
+    """ding/rl_utils/adder.py:97-155, line for line on a list of per-step dicts (PARITY UNPINNED: adder.py imports ding.utils)."""
+    if nstep == 1:
+        return data
+    fake_reward = torch.zeros_like(data[0]['reward'])
+    next_obs_flag = 'next_obs' in data[0]
+    for i in range(len(data) - nstep):
+        if next_obs_flag:
+            data[i]['next_obs'] = data[i + nstep]['obs']
+        if cum_reward:
+            data[i]['reward'] = sum([data[i + j]['reward'] * (gamma ** j) for j in range(nstep)])
+        else:
+            data[i]['reward'] = torch.cat([data[i + j]['reward'] for j in range(nstep)], dim=-1)
+        data[i]['done'] = data[i + nstep - 1]['done']
+        if correct_terminate_gamma:
+            data[i]['value_gamma'] = gamma ** nstep
+    for i in range(max(0, len(data) - nstep), len(data)):
+        if next_obs_flag:
+            data[i]['next_obs'] = data[-1]['next_obs']
+        if cum_reward:
+            data[i]['reward'] = sum([data[i + j]['reward'] * (gamma ** j) for j in range(len(data) - i)])
+        else:
+            data[i]['reward'] = torch.cat(
+                [data[i + j]['reward'] for j in range(len(data) - i)] + [fake_reward for _ in range(nstep - (len(data) - i))], dim=-1
+            )
+        data[i]['done'] = data[-1]['done']
+        if correct_terminate_gamma:
+            data[i]['value_gamma'] = gamma ** (len(data) - i - 1)
+    return data

@@ -106,3 +106,25 @@ def test_get_gae_matches_adder():
     want = rl_oracle.gae(value, nv, torch.stack([d['reward'] for d in data]), None, None, 0.99, 0.95)
     out = b2.collate.get_gae([dict(d) for d in data], last, 0.99, 0.95, device='cuda:0')
     assert all(torch.equal(out[i]['adv'], want[i]) for i in range(T))
+
+
+@pytest.mark.parametrize('T,nstep,agents,cum', [(10, 3, None, False), (10, 3, None, True), (5, 8, None, False), (7, 2, 4, False),
+                                                (7, 5, 4, True), (1, 3, None, False), (6, 1, None, False)])
+def test_nstep_return_data_matches_adder_rules(T, nstep, agents, cum):
+    """di_engine_b200.collate.nstep_return_data on stacked tensors against the restated Adder.get_nstep_return_data on a list of
+    per-step dicts (ding/rl_utils/adder.py:97-155)"""
+    g = torch.Generator().manual_seed(T * 31 + nstep)
+    shape = (1, ) if agents is None else (agents, 1)
+    data = [dict(obs=torch.full((2, ), float(i)), next_obs=torch.full((2, ), float(i + 1)), reward=torch.rand(*shape, generator=g),
+                 done=bool(i == T - 1)) for i in range(T)]
+    want = rl_oracle.adder_get_nstep_return_data([dict(d) for d in data], nstep, cum_reward=cum, gamma=0.97)
+    reward = torch.stack([d['reward'] for d in data])
+    done = torch.tensor([d['done'] for d in data])
+    obs_ext = torch.stack([d['obs'] for d in data] + [data[-1]['next_obs']])   # obs 0..T-1 and the final next_obs at index T
+    r_n, d_n, vg, nxt = b2.collate.nstep_return_data(reward, done, nstep, gamma=0.97, cum_reward=cum)
+    for i in range(T):
+        assert torch.allclose(r_n[i], want[i]['reward'], rtol=1e-6, atol=1e-7), (i, r_n[i], want[i]['reward'])
+        assert bool(d_n[i]) == bool(want[i]['done']), i
+        if nstep > 1:
+            assert abs(float(vg[i]) - want[i]['value_gamma']) < 1e-6, i
+            assert torch.equal(obs_ext[nxt[i]], want[i]['next_obs']), i
