@@ -5,11 +5,14 @@ This module is the *checker*: only ``tests/``, ``__graft_entry__.smoke()`` and `
 does; it fails loudly when its CUDA library is missing.
 
 Every function restates one reference operator with plain fp32 torch-CPU primitives, in the reference's
-evaluation order (so that on CPU it is bit-identical to the reference, which ``tests/test_oracle_vs_reference.py``
-asserts whenever ``/root/reference`` is present, and which the committed fixtures in ``tests/golden/`` pin for
-the GPU box where the reference tree does not exist).  Parity status: **pinned** -- the reference has no golden
-vectors of its own for this path, so the pins are outputs of the reference itself, run in the
-build container by ``tests/golden/make_golden.py``.
+evaluation order (so that on CPU it is bit-identical to the reference, which
+``tests/test_oracle.py::test_oracle_bit_exact_vs_live_reference`` asserts for every seeded case whenever the reference is
+importable -- the tree here, the byte-compiled archive ``oracle/_ref/ding_hotpath.zip`` on the GPU box -- and which the
+committed fixtures in ``tests/golden/`` pin as well).  Parity status: **pinned** -- the reference has no golden vectors of
+its own for this path, so the pins are outputs of the reference itself, run in the build container by
+``tests/golden/make_golden.py``.  Exception, marked where it occurs: the collector-side restatements at the end of the file
+(``default_collate_flat``, ``default_preprocess_learn``, ``adder_get_nstep_return_data``) are **parity unpinned** -- their
+reference modules import packages that are not installed here, so the live code cannot run next to them.
 
 Citations are ``file:line`` relative to ``/root/reference/ding/rl_utils/``.
 Inputs are torch tensors; tensors that need gradients must have ``requires_grad`` set by the caller and the
