@@ -19,6 +19,7 @@ from .data import PackedBatch
 
 _SLOTS = {}   # (device, layout signature) -> [PackedBatch, PackedBatch] (double-buffered: batch i+1 is staged while i is in use)
 _TURN = {}
+MAX_LAYOUTS = 8  # staging-buffer pairs kept alive (one pair per distinct batch layout, e.g. a smaller last minibatch)
 
 
 def _leaf_spec(elem, cat_1dim):
@@ -76,6 +77,9 @@ def collate(data, device, cat_1dim=True, stream=None):
     if slots is None:
         tmpl = OrderedDict((p, None if spec is None else torch.zeros(spec[0], dtype=spec[1])) for p, spec in like.items())
         slots = [PackedBatch(tmpl, device), PackedBatch(tmpl, device)]
+        if len(_SLOTS) >= MAX_LAYOUTS:  # pinned memory is a scarce resource: forget the least recently created layout
+            old = next(iter(_SLOTS))
+            del _SLOTS[old], _TURN[old]
         _SLOTS[sig] = slots
         _TURN[sig] = 0
     slot = slots[_TURN[sig]]

@@ -128,3 +128,9 @@ def test_nstep_return_data_matches_adder_rules(T, nstep, agents, cum):
         if nstep > 1:
             assert abs(float(vg[i]) - want[i]['value_gamma']) < 1e-6, i
             assert torch.equal(obs_ext[nxt[i]], want[i]['next_obs']), i
+
+
+def test_staging_cache_is_bounded():
+    for B in range(2, 2 + b2.collate.MAX_LAYOUTS + 4):
+        b2.preprocess_learn(_transitions(B, B, 'ppo'), 'cpu')
+    assert len(b2.collate._SLOTS) <= b2.collate.MAX_LAYOUTS
