@@ -417,9 +417,10 @@ def vtc_case(seed, T, B, D, weight='none', **params):
     return 'vtc', t, params
 
 
-def happo_case(seed, B, N, weight='none', **params):
-    """ppo_case + the per-sample factor (B, 1) of happo_data (happo.py:12-14)"""
-    op, t, p = ppo_case(seed, B, N, weight=weight, **params)
+def happo_case(seed, B, N, weight='none', A=None, **params):
+    """ppo_case + the per-sample factor (B, 1) of happo_data (happo.py:12-14); A: (B, A, N) logits against (B,) adv, the
+    ratio.mean(dim=1) branch (happo.py:114-121)"""
+    op, t, p = ppo_case(seed, B, N, A=A, weight=weight, **params)
     t = OrderedDict((k, v) for k, v in t.items() if k != 'logit_pretrained')
     t['factor'] = _rand(_g(seed + 7919), B, 1) * 1.5 + 0.25
     return 'happo', t, p
@@ -589,6 +590,7 @@ def build_cases():
     c['happo_basic'] = happo_case(150, 64, 6, clip_ratio=0.2)
     c['happo_w_dc'] = happo_case(151, 33, 5, weight='tensor', dual_clip=3.0, clip_ratio=0.3)
     c['happo_noclip'] = happo_case(152, 12, 40, use_value_clip=False)
+    c['happo_marl'] = happo_case(157, 12, 7, A=4, weight='tensor', dual_clip=3.0)
     c['happoc_basic'] = happoc_case(153, 16, 6)
     c['ppg_basic'] = ppg_case(155, 32, 6)
     c['ppg_w_noclip'] = ppg_case(156, 9, 17, weight='tensor', use_value_clip=False, clip_ratio=0.1)

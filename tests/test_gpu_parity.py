@@ -67,6 +67,7 @@ BIG = {
     'vtrace_N100': lambda: cases.vtrace_case(122, 8, 16, 100),
     'happo_big': lambda: cases.happo_case(125, 128 * 512 + 37, 6, weight='tensor', dual_clip=3.0),
     'happo_N40': lambda: cases.happo_case(126, 3000, 40, weight='tensor'),
+    'happo_marl_big': lambda: cases.happo_case(131, 2000, 9, A=5, weight='tensor'),
     'happoc_big': lambda: cases.happoc_case(129, 4099, 6, weight='tensor', dual_clip=2.0),
     'ppg_big': lambda: cases.ppg_case(130, 4099, 18, weight='tensor'),
     'acer_big': lambda: cases.acer_case(127, 64, 512, 6),
