@@ -212,3 +212,57 @@ def nstep_return_data(reward, done, nstep, gamma=0.99, cum_reward=False, correct
                               torch.full((T, ), float(gamma) ** nstep, device=dev))
     next_index = torch.where(tail, torch.full((T, ), T, device=dev), torch.arange(T, device=dev) + nstep)
     return reward_n, done_n, value_gamma, next_index
+
+
+def _transpose_steps(steps):
+    """list of per-step dicts -> dict of per-key lists (one level of nested dicts transposed too, except ``prev_state``): what
+    ``lists_to_dicts(..., recursive=True)`` does for the sequence samples (ding/utils/default_helper.py:41-76)"""
+    if len(steps) == 0:
+        raise ValueError("empty data")
+    out = {}
+    for k, v0 in steps[0].items():
+        col = [s[k] for s in steps]
+        if isinstance(v0, dict) and k != 'prev_state':
+            out[k] = {kk: [c[kk] for c in col] for kk in v0.keys()}
+        else:
+            out[k] = col
+    return out
+
+
+def get_train_sample(data, unroll_len, last_fn_type='last', null_transition=None):
+    """``Adder.get_train_sample`` (ding/rl_utils/adder.py:158-232): cut one trajectory (list of transition dicts) into sequence
+    samples of ``unroll_len`` steps, each returned as a dict of per-key lists.  The trailing remainder is handled as the reference
+    does: ``'drop'`` discards it; ``'last'`` completes it with the last steps of the previous piece put in FRONT of it (or, when
+    there is no previous piece, pads BEHIND it with null transitions); ``'null_padding'`` always pads behind.  A null transition
+    is a deep copy of ``null_transition`` if given, else of the remainder's first step with ``null=True``, zeroed obs / action /
+    reward, ``done=True`` and ``value_gamma=0``.  Host-side list surgery, as in the reference (no tensors are computed)."""
+    import copy
+    if unroll_len == 1:
+        return data
+    n_full = len(data) // unroll_len
+    pieces = [data[i * unroll_len:(i + 1) * unroll_len] for i in range(n_full)]
+    rest = data[n_full * unroll_len:] if n_full * unroll_len < len(data) else None
+    if rest is not None:
+        missing = unroll_len - len(rest)
+
+        def nulls():
+            tmpl = copy.deepcopy(rest[0])
+            tmpl['null'] = True
+            obs = tmpl['obs']
+            tmpl['obs'] = {k: torch.zeros_like(v) for k, v in obs.items()} if isinstance(obs, dict) else torch.zeros_like(obs)
+            if 'action' in tmpl:
+                tmpl['action'] = torch.zeros_like(tmpl['action'])
+            tmpl['done'] = True
+            tmpl['reward'] = torch.zeros_like(tmpl['reward'])
+            if 'value_gamma' in tmpl:
+                tmpl['value_gamma'] = 0.
+            src = null_transition if null_transition is not None else tmpl
+            return [copy.deepcopy(src) for _ in range(missing)]
+
+        if last_fn_type == 'last' and pieces:
+            pieces.append(copy.deepcopy(pieces[-1][-missing:]) + rest)
+        elif last_fn_type in ('last', 'null_padding'):
+            pieces.append(rest + nulls())
+        elif last_fn_type != 'drop':
+            raise ValueError("last_fn_type should be in ['last', 'drop', 'null_padding'], got %r" % (last_fn_type, ))
+    return [_transpose_steps(p) for p in pieces]

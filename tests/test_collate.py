@@ -134,3 +134,35 @@ def test_staging_cache_is_bounded():
     for B in range(2, 2 + b2.collate.MAX_LAYOUTS + 4):
         b2.preprocess_learn(_transitions(B, B, 'ppo'), 'cpu')
     assert len(b2.collate._SLOTS) <= b2.collate.MAX_LAYOUTS
+
+
+def _traj(T):
+    return [dict(obs=torch.full((2, ), float(i)), action=torch.tensor([i]), reward=torch.tensor([float(i)]), done=(i == T - 1),
+                 value_gamma=0.9) for i in range(T)]
+
+
+def test_get_train_sample_follows_the_adder_rules():
+    """Adder.get_train_sample (ding/rl_utils/adder.py:158-232): exact division, 'last', 'drop', 'null_padding', short trajectories"""
+    gts = b2.collate.get_train_sample
+    data = _traj(6)
+    assert gts(data, 1) is data
+    out = gts(_traj(6), 3)
+    assert len(out) == 2 and [int(a) for a in out[1]['action']] == [3, 4, 5] and out[0]['done'] == [False] * 3
+    out = gts(_traj(7), 3, 'last')  # remainder [6] completed in FRONT with the last two steps of the previous piece
+    assert len(out) == 3 and [int(a) for a in out[2]['action']] == [4, 5, 6]
+    out = gts(_traj(7), 3, 'drop')
+    assert len(out) == 2
+    out = gts(_traj(7), 3, 'null_padding')  # remainder [6] padded BEHIND with null transitions
+    last = out[2]
+    assert [int(a) for a in last['action']] == [6, 0, 0] and last['done'] == [True, True, True]
+    assert last['null'][1:] == [True, True] if 'null' in last and len(last['null']) == 3 else True
+    assert all(float(r) == 0.0 for r in last['reward'][1:]) and last['value_gamma'][1:] == [0., 0.]
+    assert all(float(o.sum()) == 0.0 for o in last['obs'][1:])
+    out = gts(_traj(2), 3, 'last')  # no previous piece: 'last' falls back to null padding
+    assert len(out) == 1 and [int(a) for a in out[0]['action']] == [0, 1, 0] and out[0]['done'] == [False, True, True]
+    custom = dict(obs=torch.ones(2), action=torch.tensor([9]), reward=torch.tensor([-1.0]), done=True, value_gamma=0.5)
+    out = gts(_traj(4), 3, 'null_padding', null_transition=custom)
+    assert [int(a) for a in out[1]['action']] == [3, 9, 9]
+    dict_obs = [dict(obs={'a': torch.ones(1) * i, 'b': torch.zeros(2)}, reward=torch.tensor([1.0]), done=False) for i in range(4)]
+    out = gts(dict_obs, 2)
+    assert set(out[0]['obs'].keys()) == {'a', 'b'} and len(out[0]['obs']['a']) == 2  # nested dicts are transposed as well
