@@ -353,6 +353,40 @@ def test_install_rebinds_and_uninstall_restores(dry, monkeypatch):
     assert fake['ding.policy.ppo'].gae is ref_gae and fake['ding.rl_utils'].ppo_error is ref_ppo
 
 
+def test_install_on_the_live_reference_rebinds_every_hot_path_function(dry):
+    """the real ding.rl_utils modules (oracle/ref_loader.py): install() replaces every function of HOT_PATH_FUNCTIONS in the
+    package namespace and in the submodule that defines it; a policy-like module that imported the names keeps working through
+    the rebinding; uninstall() restores the originals"""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference not importable here')
+    ref = ref_loader.load()
+    originals = {n: getattr(ref, n) for n in b2.rl_utils.HOT_PATH_FUNCTIONS}
+    policy = types.ModuleType('ding.policy.fake_for_install_test')
+    for n, fn in originals.items():
+        setattr(policy, n, fn)  # `from ding.rl_utils import ...` at import time
+    sys.modules[policy.__name__] = policy
+    try:
+        done = b2.install()
+        names = {n for _, n in done}
+        assert names == set(b2.rl_utils.HOT_PATH_FUNCTIONS), set(b2.rl_utils.HOT_PATH_FUNCTIONS) - names
+        for n in b2.rl_utils.HOT_PATH_FUNCTIONS:
+            ours = getattr(b2.rl_utils, n)
+            assert getattr(ref, n) is ours, n
+            assert getattr(policy, n) is ours, n
+            defining = sys.modules[originals[n].__module__]
+            assert getattr(defining, n) is ours, (n, defining.__name__)
+        # a rebound operator is callable through the reference's own namedtuple (positional unpacking)
+        op, t, p = cases.gae_case(1, 6, 4)
+        adv = policy.gae(ref.gae_data(t['value'], t['next_value'], t['reward'], t['done'], t['traj_flag']), 0.9, 0.8)
+        assert adv.shape == (6, 4) and dry.calls[-1] == 'b200rl_gae'
+    finally:
+        b2.uninstall()
+        del sys.modules[policy.__name__]
+    for n, fn in originals.items():
+        assert getattr(ref, n) is fn, n
+
+
 def test_hpc_rll_shim_layout(monkeypatch):
     for k in list(sys.modules):
         if k == 'hpc_rll' or k.startswith('hpc_rll.'):
