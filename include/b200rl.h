@@ -240,7 +240,8 @@ B200RL_API int b200rl_vtrace_continuous_bwd(const float* mu_target, const float*
                                  const float* g_value, const float* g_entropy, long long T, long long B, long long D,
                                  float* grad_mu, float* grad_sigma, float* grad_value, void* stream);
 
-/* ---- V-trace in one launch: forward AND gradients (csrc/vtws.cu) ---------------------------------------------------
+/* ---- vtrace_error_discrete_action in one launch: ding/rl_utils/vtrace.py:72-136 (returns :9-29, advantages :32-45,
+ * importance weights isw.py:55-58), forward AND gradients (csrc/vtws.cu) -------------------------------------------------
  * Same semantics as b200rl_vtrace_fwd followed by b200rl_vtrace_bwd, but the batch crosses HBM once (96 B per transition at
  * N = 6): column tiles, warp-specialised loader / scanner / consumer warps.  The gradients are produced in the forward
  * launch (verify = 0) for the upstream gradients g_expected[3] = d total / d (policy, value, entropy) loss and the values
@@ -394,7 +395,8 @@ B200RL_API int b200rl_gae_ppo_fwd_grad_dp(const float* value, float* next_value,
                                void* stream);
 B200RL_API int b200rl_p2p_drain_mean(const unsigned long long* mailbox_ptrs_dev, int rank, int world, int n,
                           unsigned int* seq_dev, float* out_mean, void* stream);
-/* Kernels behind the calls above.  Column tiles: a CTA owns 16 batch columns for all T and runs their scan and their
+/* Kernels behind the calls above (gae, ding/rl_utils/gae.py:25-70, followed by ppo_error, ding/rl_utils/ppo.py:77-140).
+ * Column tiles: a CTA owns 16 batch columns for all T and runs their scan and their
  * ppo_error rows -- no cross-CTA dependency; chosen when B >= 1024 or T*B <= 16384.  Three builds of that scheme exist:
  * csrc/colws.cu (warp-specialised loader / scanner / consumer warps on an mbarrier pipeline, cp.async copies; the default),
  * csrc/coltile.cu (every thread copies and computes; any N <= 32) and csrc/coltma.cu (2-D tensor-map TMA copies;
