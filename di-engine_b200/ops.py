@@ -5,6 +5,8 @@ arithmetic step of the hot path runs in the CUDA kernels of ``csrc/``.
 Nothing here computes on the CPU.  Host (CPU) tensors are accepted by the public API in ``rl_utils`` by staging them
 to the current CUDA device and returning results on the host -- the "host buffers" end-to-end path.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -86,9 +88,20 @@ def f32c(t, name='tensor'):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def i64c(t):
+# B200RL_CHECK_INDICES=1 (or ops.CHECK_INDICES = True): every action / label tensor is range-checked on the host before its
+# pointer goes to a kernel -- an out-of-range index raises IndexError as torch's gather would, at the price of one device
+# synchronisation per call.  Off by default: the kernels index with the value they are given.
+CHECK_INDICES = os.environ.get('B200RL_CHECK_INDICES', '0') == '1'
+
+
+def i64c(t, n=None, name='action'):
     if t.dtype != torch.int64:
         t = t.long()
+    if CHECK_INDICES and n is not None and t.numel():
+        lo, hi = torch.aminmax(t)
+        lo, hi = int(lo), int(hi)
+        if lo < 0 or hi >= n:
+            raise IndexError("di_engine_b200: %s holds index %d, out of range for %d classes" % (name, lo if lo < 0 else hi, n))
     return t if t.is_contiguous() else t.contiguous()
 
 

@@ -26,7 +26,7 @@ def a2c_error(data: namedtuple) -> namedtuple:
             raise ValueError("a2c_error: %s %s does not match logit %s" % (name, tuple(t_.shape), tuple(logit.shape)))
     z = ops.f32c(ops.to_device(logit, dev), 'logit')
     v = ops.f32c(ops.to_device(value, dev), 'value')
-    a = ops.i64c(ops.to_device(action, dev))
+    a = ops.i64c(ops.to_device(action, dev), logit.shape[-1])
     ad = ops.f32c(ops.to_device(adv.detach(), dev), 'adv')
     rt = ops.f32c(ops.to_device(return_.detach(), dev), 'return_')
     w = ops.f32c(ops.to_device(weight.detach(), dev), 'weight') if weight is not None else None

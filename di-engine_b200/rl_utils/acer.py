@@ -38,7 +38,7 @@ def acer_policy_error(
     actor, bias = ops.AcerPolicyFunction.apply(
         ops.f32c(ops.to_device(target_logit, dev), 'target_logit'), ops.f32c(ops.to_device(q_values.detach(), dev), 'q_values'),
         ops.f32c(ops.to_device(q_retraces.detach(), dev), 'q_retraces'), ops.f32c(ops.to_device(v_pred.detach(), dev), 'v_pred'),
-        ops.i64c(ops.to_device(actions, dev)), ops.f32c(ops.to_device(ratio.detach(), dev), 'ratio'), M, N, float(c_clip_ratio)
+        ops.i64c(ops.to_device(actions, dev), N, 'actions'), ops.f32c(ops.to_device(ratio.detach(), dev), 'ratio'), M, N, float(c_clip_ratio)
     )
     actor, bias = actor.view(lead + (1, )), bias.view(lead + (1, ))
     return (actor.cpu(), bias.cpu()) if host_out else (actor, bias)
@@ -56,7 +56,7 @@ def acer_value_error(q_values, q_retraces, actions):
     host_out = not q_values.is_cuda
     loss = ops.AcerValueFunction.apply(
         ops.f32c(ops.to_device(q_values, dev), 'q_values'), ops.f32c(ops.to_device(q_retraces.detach(), dev), 'q_retraces'),
-        ops.i64c(ops.to_device(actions, dev)), actions.numel(), N
+        ops.i64c(ops.to_device(actions, dev), N, 'actions'), actions.numel(), N
     ).view(lead + (1, ))
     return loss.cpu() if host_out else loss
 

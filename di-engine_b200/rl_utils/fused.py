@@ -69,7 +69,7 @@ def gae_ppo_error(
     w = f32(weight.detach(), 'weight') if weight is not None else None
     if w is not None and w.numel() != T * B:
         return fallback()
-    act = ops.i64c(action)
+    act = ops.i64c(action, N)
     ok = ops.lib().b200rl_gae_ppo_supported(
         ops.ptr(v), ops.ptr(nv), ops.ptr(r), ops.ptr(d), ops.ptr(tf), T, B, ops.ptr(ln), ops.ptr(lo), ops.ptr(lp),
         ops.ptr(act), ops.ptr(vn), ops.ptr(vo), ops.ptr(rt), ops.ptr(w), N, ops.ptr(v), None

@@ -32,5 +32,5 @@ def ppg_joint_error(
     dev = ops.compute_device(logit_new, value_new)
     host_out = not logit_new.is_cuda
     bc = ops.ppg_bc_(ops.f32c(ops.to_device(logit_new, dev), 'logit_new'),
-                     ops.f32c(ops.to_device(logit_old.detach(), dev), 'logit_old'), ops.i64c(ops.to_device(action, dev)))
+                     ops.f32c(ops.to_device(logit_old.detach(), dev), 'logit_old'), ops.i64c(ops.to_device(action, dev), logit_new.shape[-1]))
     return ppg_joint_loss(aux, bc.cpu() if host_out else bc)

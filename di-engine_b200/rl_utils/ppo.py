@@ -120,7 +120,7 @@ def _ppo_error(data, clip_ratio, use_value_clip, dual_clip, kl_type, _hint_kind,
         w = stage(weight.detach(), 'weight')
         if w.numel() != S:
             w = w.expand_as(ad).contiguous()
-    act = ops.i64c(ops.to_device(action, dev))
+    act = ops.i64c(ops.to_device(action, dev), N)
     stats = None
     if adv_norm:
         if adv_stats is None:

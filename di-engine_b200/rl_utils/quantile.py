@@ -43,8 +43,8 @@ def _run(q, next_n_q, action, next_n_action, reward, done, tau, weight, gamma, n
             or done.shape[0] != B or reward.shape[1] != B:
         raise ValueError("quantile td: q %s / next_n_q %s / action %s / reward %s / done %s do not agree on (B, N)" %
                          (tuple(q.shape), tuple(next_n_q.shape), tuple(action.shape), tuple(reward.shape), tuple(done.shape)))
-    act = ops.i64c(ops.to_device(action, dev))
-    nact = ops.i64c(ops.to_device(next_n_action, dev))
+    act = ops.i64c(ops.to_device(action, dev), N)
+    nact = ops.i64c(ops.to_device(next_n_action, dev), N, 'next_n_action')
     r = ops.f32c(ops.to_device(reward.detach(), dev), 'reward')
     d = ops.f32c(ops.to_device(done.detach(), dev), 'done')
     t = ops.to_device(tau.detach(), dev)

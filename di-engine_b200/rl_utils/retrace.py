@@ -30,7 +30,7 @@ def compute_q_retraces(
     q = ops.f32c(ops.to_device(q_values.detach(), dev), 'q_values')
     v = ops.f32c(ops.to_device(v_pred.detach(), dev), 'v_pred')
     r = ops.f32c(ops.to_device(rewards.detach(), dev), 'rewards')
-    a = ops.i64c(ops.to_device(actions, dev))
+    a = ops.i64c(ops.to_device(actions, dev), N, 'actions')
     w = ops.f32c(ops.to_device(weights.detach(), dev), 'weights')
     c = ops.f32c(ops.to_device(ratio.detach(), dev), 'ratio')
     out = torch.empty_like(v)

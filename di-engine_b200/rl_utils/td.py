@@ -119,8 +119,8 @@ def _qntd_rows(q, next_n_q, action, next_n_action, reward, done, weight, value_g
     gamma_f, gamma_ps = _gamma_arg(gamma, S, dev, cum_reward)
     qd = ops.f32c(ops.to_device(q, dev), 'q')
     nq = ops.f32c(ops.to_device(next_n_q.detach(), dev), 'next_n_q')
-    act = ops.i64c(ops.to_device(action, dev))
-    nact = ops.i64c(ops.to_device(next_n_action, dev))
+    act = ops.i64c(ops.to_device(action, dev), q.shape[-1])
+    nact = ops.i64c(ops.to_device(next_n_action, dev), q.shape[-1], 'next_n_action')
     r = ops.f32c(ops.to_device(reward.detach(), dev), 'reward')
     d = ops.f32c(ops.to_device(done.detach(), dev), 'done')
     if (nq.shape != qd.shape or act.numel() != S * G or nact.numel() != S * G or
@@ -437,8 +437,8 @@ def q_nstep_td_error_sequence(
                                   "with reduction='none'")
     qd = ops.f32c(ops.to_device(q, dev), 'q')
     nq = ops.f32c(ops.to_device(next_n_q.detach(), dev), 'next_n_q')
-    act = ops.i64c(ops.to_device(action, dev))
-    nact = ops.i64c(ops.to_device(next_n_action, dev))
+    act = ops.i64c(ops.to_device(action, dev), q.shape[-1])
+    nact = ops.i64c(ops.to_device(next_n_action, dev), q.shape[-1], 'next_n_action')
     r = ops.f32c(ops.to_device(reward.detach(), dev), 'reward')
     d = ops.f32c(ops.to_device(done.detach(), dev), 'done')
     S = T * B
@@ -581,8 +581,8 @@ def _dntd(data, gamma, v_min, v_max, n_atom, nstep, value_gamma, check_positive)
     assert reward.shape[0] == nstep and reward.numel() == nstep * B, reward.shape
     dd = ops.f32c(ops.to_device(dist, dev), 'dist')
     nd = ops.f32c(ops.to_device(next_n_dist.detach(), dev), 'next_n_dist')
-    a = ops.i64c(ops.to_device(act, dev))
-    na = ops.i64c(ops.to_device(next_n_act, dev))
+    a = ops.i64c(ops.to_device(act, dev), N, 'act')
+    na = ops.i64c(ops.to_device(next_n_act, dev), N, 'next_n_act')
     r = ops.f32c(ops.to_device(reward.detach(), dev), 'reward')
     d = ops.f32c(ops.to_device(done.detach(), dev), 'done')
     if weight is None:

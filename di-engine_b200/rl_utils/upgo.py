@@ -24,7 +24,7 @@ def tb_cross_entropy(logit: torch.Tensor, label: torch.Tensor, mask=None) -> tor
     if logit.numel() != T * B * K * N:
         raise ValueError("logit %s does not match label %s" % (tuple(logit.shape), tuple(label.shape)))
     z = ops.f32c(ops.to_device(logit, dev), 'logit')
-    lab = ops.i64c(ops.to_device(label, dev))
+    lab = ops.i64c(ops.to_device(label, dev), logit.shape[-1], 'label')
     m = None
     if mask is not None and K > 1:
         m = ops.f32c(ops.to_device(mask.detach(), dev), 'mask')
@@ -79,7 +79,7 @@ def upgo_loss(
         raise ValueError("target_output %s does not match action %s" % (tuple(target_output.shape),
                                                                         tuple(action.shape)))
     logit = ops.f32c(ops.to_device(target_output, dev), 'target_output')
-    act = ops.i64c(ops.to_device(action, dev))
+    act = ops.i64c(ops.to_device(action, dev), target_output.shape[-1])
     m = None
     if mask is not None and K > 1:  # the reference ignores mask for 3-D logits (upgo.py:38-42)
         m = ops.f32c(ops.to_device(mask.detach(), dev), 'mask')

@@ -42,7 +42,7 @@ def vtrace_error_discrete_action(
             tuple(reward.shape)))
     tgt = ops.f32c(ops.to_device(target_output, dev), 'target_output')
     beh = ops.f32c(ops.to_device(behaviour_output.detach(), dev), 'behaviour_output')
-    act = ops.i64c(ops.to_device(action, dev))
+    act = ops.i64c(ops.to_device(action, dev), target_output.shape[-1])
     v = ops.f32c(ops.to_device(value, dev), 'value')
     r = ops.f32c(ops.to_device(reward.detach(), dev), 'reward')
     w = None

@@ -275,6 +275,31 @@ def test_gae_ppo_error_dry_run_forward_and_backward(dry):
     assert dry.calls[-1] == 'b200rl_ppo_bwd', dry.calls
 
 
+def test_optional_index_range_check(dry, monkeypatch):
+    """B200RL_CHECK_INDICES / ops.CHECK_INDICES: out-of-range actions raise IndexError before any pointer reaches a kernel
+    (off by default: the check costs a device synchronisation)"""
+    op, t, p = cases.ppo_case(3, 12, 5)
+    bad = dict(t)
+    bad['action'] = t['action'].clone()
+    bad['action'][3] = 5
+    data = b2.ppo_data(*bad.values())
+    b2.ppo_error(data)  # unchecked by default
+    monkeypatch.setattr(ops, 'CHECK_INDICES', True)
+    dry.calls.clear()
+    with pytest.raises(IndexError, match='out of range for 5 classes'):
+        b2.ppo_error(data)
+    assert dry.calls == []
+    op, t, p = cases.qntd_case(4, 8, 4, 3)
+    t = dict(t)
+    t['next_n_action'] = t['next_n_action'].clone()
+    t['next_n_action'][0] = -1
+    with pytest.raises(IndexError, match='next_n_action'):
+        b2.q_nstep_td_error(b2.q_nstep_td_data(*[t[k] for k in ('q', 'next_n_q', 'action', 'next_n_action', 'reward', 'done',
+                                                                  'weight')]), 0.9, nstep=3)
+    op, t, p = cases.vtrace_case(5, 6, 4, 3)
+    b2.vtrace_error_discrete_action(b2.vtrace_data(*t.values()))  # in range: passes with the check on
+
+
 def test_custom_criterion_and_transforms_dry_run(dry):
     op, t, p = cases.qntd_case(1, 8, 4, 3, weight='tensor')
     t = cases.prepare(op, t)
